@@ -1,0 +1,197 @@
+"""Pin the oracle to the live reference and freeze golden vectors.
+
+Runs ONLY in the build container, where the unmodified reference is mounted at
+/root/reference (it does not exist on the GPU box).  It
+
+  1. imports the reference's own FluxGNN / build_chain_graph / HybridSolver /
+     BaselineSolver,
+  2. checks every function of oracle/ref_port.py against them on seeded inputs
+     (bit-exact in fp32: same primitives, same order, same machine), and
+  3. writes the REFERENCE's outputs as fixtures under tests/golden/.
+
+    python -m oracle.make_golden            # from the repo root
+
+Environment recorded in tests/golden/MANIFEST.json (numpy >= 2 keeps the
+forward FFT of a float32 density in complex64; the reference's pinned numpy
+1.26.4 would use complex128 -- a ~1e-7 relative effect on E).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(REF, "src"))      # `from config import MODEL_CONFIG` (src/hybrid_solver.py:21)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from src.baseline_solver import BaselineSolver            # noqa: E402  (reference)
+from src.flux_gnn import FluxGNN                          # noqa: E402  (reference)
+from src.graph_constructor import build_chain_graph       # noqa: E402  (reference)
+from src.hybrid_solver import HybridSolver                # noqa: E402  (reference)
+
+from oracle import batched, ref_port as P                 # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def same(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    if not np.array_equal(a, b):
+        raise AssertionError(f"{what}: port differs from reference, max |d| = {np.abs(a - b).max()}")
+    print(f"  ok  {what}  {a.shape} {a.dtype}")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)          # one thread: BLAS blocking is deterministic
+    torch.manual_seed(0)
+    model = FluxGNN(input_dim=4, hidden_dim=128, num_layers=4).eval()
+    weights = {k: v.numpy().copy() for k, v in model.state_dict().items()}
+    same_w = P.init_weights(0)
+    for key in weights:
+        same(same_w[key], weights[key], f"init_weights[{key}]")
+    np.savez_compressed(os.path.join(OUT, "weights_seed0.npz"), **weights)
+    ckpt = os.path.join(tempfile.mkdtemp(), "w.pt")
+    torch.save(model.state_dict(), ckpt)
+
+    # ---- G4 field solve + grid + initial conditions ----------------------
+    g4 = {}
+    for nx in (64, 1024, 96):
+        ref = BaselineSolver(nx=nx)
+        g = P.Grid(nx=nx)
+        same(g.x, ref.x, f"grid.x nx={nx}")
+        same(g.k, ref.k, f"grid.k nx={nx}")
+        for seed in (0, 1, 123):
+            ic = ref.initial_condition(seed=seed)
+            same(P.initial_condition(g, seed), ic, f"initial_condition nx={nx} seed={seed}")
+            g4[f"ic_nx{nx}_s{seed}"] = ic
+        rng = np.random.RandomState(7)
+        cases = {
+            "modes": ref.initial_condition(seed=5)[0],
+            "white": (1.0 + 0.3 * rng.randn(nx)).astype(np.float32),
+            "nyquist": (1.0 + 0.2 * np.cos(np.pi * np.arange(nx))).astype(np.float32),
+            "const": np.full(nx, 1.7, dtype=np.float32),
+        }
+        for name, dens in cases.items():
+            e_ref = ref.solve_poisson(dens)
+            same(P.solve_poisson(dens, g.k), e_ref, f"solve_poisson {name} nx={nx}")
+            conv = np.real(np.fft.ifft(np.fft.fft(P.poisson_kernel(nx, g.length)) * np.fft.fft((dens - 1.0).astype(np.float64))))
+            assert np.abs(conv - e_ref).max() <= 2e-6 * max(1.0, np.abs(e_ref).max()), name
+            g4[f"n_{name}_nx{nx}"] = dens
+            g4[f"E_{name}_nx{nx}"] = e_ref
+    np.savez_compressed(os.path.join(OUT, "g4_poisson_ic.npz"), **g4)
+
+    # ---- G1 FluxGNN.forward on ring graphs --------------------------------
+    g1 = {}
+    for nx in (64, 1024):
+        ref = BaselineSolver(nx=nx)
+        g = P.Grid(nx=nx)
+        state = ref.initial_condition(seed=11)
+        nf, ei = build_chain_graph(state, ref.x)
+        same(P.node_features(state, g.x), nf.numpy(), f"node_features nx={nx}")
+        same(P.ring_edges(nx, 1), ei.numpy(), f"ring_edges r=1 nx={nx}")
+        g1[f"state_nx{nx}"] = state
+        for r in (1, 2, 3):
+            edges = P.ring_edges(nx, r)
+            assert np.array_equal(edges[:, :2 * nx], ei.numpy())
+            with torch.no_grad():
+                out = model(nf, torch.from_numpy(edges)).numpy()
+            same(P.fluxgnn_forward(weights, nf.numpy(), edges), out, f"forward nx={nx} r={r}")
+            closed = batched.edge_fluxes(weights, torch.from_numpy(state)[None], torch.from_numpy(g.x.astype(np.float32)), r)[0].numpy()
+            err = np.abs(closed - out).max() / np.abs(out).max()
+            assert err < 2e-6, (nx, r, err)
+            print(f"      closed form vs reference forward: rel {err:.2e}")
+            g1[f"flux_nx{nx}_r{r}"] = out
+    # a tiny ring where hops wrap onto themselves (nx <= 2r)
+    state = np.random.RandomState(3).randn(3, 4).astype(np.float32)
+    g = P.Grid(nx=4)
+    nf = torch.from_numpy(P.node_features(state, g.x))
+    with torch.no_grad():
+        out = model(nf, torch.from_numpy(P.ring_edges(4, 3))).numpy()
+    g1["state_nx4"], g1["flux_nx4_r3"] = state, out
+    np.savez_compressed(os.path.join(OUT, "g1_forward.npz"), **g1)
+
+    # ---- G2 / G3 hybrid step and the repo-default rollout (C1) ------------
+    hs = HybridSolver(ckpt, 1, nx=64, dt=5e-3, device="cpu")
+    g = P.Grid(nx=64, dt=5e-3)
+    ics = np.stack([hs.baseline.initial_condition(seed=s) for s in range(20)])
+    step1 = np.stack([hs.step(ic) for ic in ics])
+    for s in (0, 7, 19):
+        same(P.hybrid_step(weights, ics[s], g), step1[s], f"hybrid_step seed={s}")
+    roll = np.stack([hs.run(ic, n_steps=30) for ic in ics])           # [20,31,3,64]
+    same(P.hybrid_run(weights, ics[3], g, 30), roll[3], "hybrid_run 30 steps seed=3")
+    bt = batched.hybrid_step(weights, torch.from_numpy(ics), g.x, g.k, g.dt, g.dx).numpy()
+    print("      batched closed form vs reference step: rel", P.rel_err(bt, step1))
+    assert P.rel_err(bt, step1).max() < 2e-6
+    np.savez_compressed(os.path.join(OUT, "g23_hybrid_c1.npz"), ics=ics, step1=step1, rollout=roll,
+                        dt=5e-3, nx=64, radius=1)
+
+    # hybrid step at nx=1024 (reference semantics, radius 1) and radius-r steps
+    # (reference forward on the r-ring + reference FV arithmetic, via the port)
+    hs1k = HybridSolver(ckpt, 1, nx=1024, dt=3e-4, device="cpu")
+    g1k = P.Grid(nx=1024, dt=3e-4)
+    ic1k = np.stack([P.stable_initial_condition(g1k, s) for s in range(2)])
+    st1k = np.stack([hs1k.step(ic) for ic in ic1k])
+    same(P.hybrid_step(weights, ic1k[0], g1k), st1k[0], "hybrid_step nx=1024")
+    extra = {"ic_nx1024": ic1k, "step_nx1024_r1": st1k}
+    for r in (2, 3):
+        extra[f"step_nx1024_r{r}"] = np.stack([P.hybrid_step(weights, ic, g1k, radius=r) for ic in ic1k])
+        extra[f"step_nx64_r{r}"] = np.stack([P.hybrid_step(weights, ic, g, radius=r) for ic in ics[:4]])
+    np.savez_compressed(os.path.join(OUT, "g2_hybrid_radius.npz"), **extra)
+
+    # ---- G5 baseline solver ------------------------------------------------
+    g5 = {}
+    for nx, dt, steps in ((64, 5e-3, 40), (1024, 3e-4, 10)):
+        ref = BaselineSolver(nx=nx, dt=dt, nu=1e-3)
+        g = P.Grid(nx=nx, dt=dt, nu=1e-3)
+        ic = ref.initial_condition(seed=2)
+        new, fn = ref.step(ic, return_flux=True)
+        pn, pf = P.baseline_step(ic, g, return_flux=True)
+        same(pn, new, f"baseline_step nx={nx}")
+        same(pf, fn, f"baseline_step flux nx={nx}")
+        states, fluxes = ref.run(ic, n_steps=steps)
+        ps, pfl = P.baseline_run(ic, g, steps)
+        same(ps, states, f"baseline_run nx={nx}")
+        same(pfl, fluxes, f"baseline_run fluxes nx={nx}")
+        g5[f"states_nx{nx}"], g5[f"fluxes_nx{nx}"], g5[f"dt_nx{nx}"] = states, fluxes, dt
+    np.savez_compressed(os.path.join(OUT, "g5_baseline.npz"), **g5)
+
+    # ---- G6 1000-step stabilised rollout + fp64 noise floor -----------------
+    hs = HybridSolver(ckpt, 1, nx=64, dt=1e-3, device="cpu")
+    g = P.Grid(nx=64, dt=1e-3)
+    g6_ic = np.stack([P.stable_initial_condition(g, s) for s in range(4)])
+    snaps32, snaps64 = [], []
+    for ic in g6_ic:
+        r32 = hs.run(ic, n_steps=1000)
+        assert np.isfinite(r32).all()
+        r64 = P.hybrid_run(weights, ic, g, 1000, dtype=torch.float64)
+        snaps32.append(r32[::100])
+        snaps64.append(r64[::100])
+    snaps32, snaps64 = np.stack(snaps32), np.stack(snaps64)       # [4,11,3,64]
+    floor = P.rel_err(snaps32[:, -1], snaps64[:, -1])
+    print("      reference fp32 vs fp64 after 1000 steps (n,u,E):", floor)
+    np.savez_compressed(os.path.join(OUT, "g6_long_rollout.npz"), ics=g6_ic, ref_fp32=snaps32,
+                        fp64=snaps64, dt=1e-3, nx=64, radius=1, every=100)
+
+    manifest = {
+        "generated_by": "oracle/make_golden.py",
+        "reference": "/root/reference (shanedirksen/gnn-plasma-flux, unmodified)",
+        "numpy": np.__version__, "torch": torch.__version__, "torch_threads": 1,
+        "forward_fft": "complex64 (numpy>=2 on float32 input)",
+        "noise_floor_1000_steps_fp32_vs_fp64": floor.tolist(),
+        "files": sorted(f for f in os.listdir(OUT) if f.endswith(".npz")),
+    }
+    with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1)
+    print("goldens written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
