@@ -1,0 +1,71 @@
+"""ctypes binding of libfluxgnn.so (C ABI in include/fluxgnn.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call
+fails, the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfluxgnn.so")
+
+ABI_VERSION = 1
+MAX_HOPS = 4
+MAX_LAYERS = 8
+HIDDEN = 128
+INPUT_DIM = 4
+
+# name -> (restype, argtypes); mirrors include/fluxgnn.h declaration by declaration
+SIGNATURES = {
+    "fluxgnn_abi_version": (c_int, []),
+    "fluxgnn_last_error": (c_char_p, []),
+    "fluxgnn_launch_count": (c_ulonglong, []),
+    "fluxgnn_packed_weight_bytes": (c_size_t, [c_int]),
+    "fluxgnn_pack_weights": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
+    "fluxgnn_poisson_table": (c_int, [c_int, c_double, c_void_p, c_void_p]),
+    "fluxgnn_poisson_spectral": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p]),
+    "fluxgnn_forward_ring": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_hybrid_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_hybrid_rollout": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
+                                         c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class FluxGNNError(RuntimeError):
+    """A libfluxgnn entry point returned a negative status."""
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FluxGNNError(
+                f"{LIB_PATH} not found: build it with `python -m gnn_plasma_flux_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        if handle.fluxgnn_abi_version() != ABI_VERSION:
+            raise FluxGNNError("libfluxgnn.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().fluxgnn_last_error().decode("utf-8", "replace")
+        raise FluxGNNError(f"{what} failed ({status}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().fluxgnn_launch_count())

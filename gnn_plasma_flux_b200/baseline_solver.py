@@ -1,0 +1,153 @@
+"""BaselineSolver, drop-in for src/baseline_solver.py of the reference, on sm_100a.
+
+Same constructor, attributes (`nx, length, dx, dt, t_end, x, n0, nu, k`) and
+methods; numpy [3, nx] float32 in -> numpy out as in the reference.  Every
+method additionally accepts a batch: a numpy [B, 3, nx] array, or a CUDA
+tensor [B, 3, nx] that is advanced without leaving the device.
+
+Arithmetic runs in libfluxgnn.so (no CPU fallback); only the random initial
+condition generator, which is an input generator rather than part of the
+step, stays on the host so that its numpy RandomState draw order is kept
+(src/baseline_solver.py:29-57).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .grid import PeriodicGrid
+
+
+def _as_device_batch(state, device):
+    """-> (tensor [B,3,nx] float32 contiguous on device, kind) with kind in
+    {'np1','npB','t1','tB'} describing how to hand the result back."""
+    if isinstance(state, np.ndarray):
+        arr = np.ascontiguousarray(state, dtype=np.float32)
+        kind = "np1" if arr.ndim == 2 else "npB"
+        t = torch.from_numpy(arr if arr.ndim == 3 else arr[None])
+        return t.to(device, non_blocking=False), kind
+    if not torch.is_tensor(state):
+        raise TypeError("state must be a numpy array or a torch tensor")
+    kind = "t1" if state.dim() == 2 else "tB"
+    t = state if state.dim() == 3 else state.unsqueeze(0)
+    return t.to(device=device, dtype=torch.float32).contiguous(), kind
+
+
+def _hand_back(t: torch.Tensor, kind: str, lead: int = 0):
+    """Undo _as_device_batch; `lead` = number of leading (time) axes in front of [B,3,nx]."""
+    if kind in ("np1", "t1"):
+        t = t.select(lead, 0)
+    return t.cpu().numpy() if kind.startswith("np") else t
+
+
+class BaselineSolver:
+    """1D fluid-Poisson model with viscosity (upwind fluxes, forward Euler, spectral field solve)."""
+
+    def __init__(self, nx=64, length=2 * math.pi, dt=5e-3, t_end=1.0, nu=1e-3, *, device="cuda"):
+        self.grid = PeriodicGrid(nx, length)
+        self.nx, self.length, self.dx = self.grid.nx, self.grid.length, self.grid.dx
+        self.dt, self.t_end, self.nu = dt, t_end, nu
+        self.x, self.k = self.grid.x, self.grid.k
+        self.n0 = 1.0
+        self.device = torch.device(device)
+        if self.dt / self.dx > 0.5:
+            print("Warning: dt/dx may be large; consider reducing dt for stability.")
+
+    # ---- scalars exactly as numpy's weak python floats act on float32 arrays ----
+    @property
+    def _c(self):
+        return float(np.float32(self.dt / self.dx))
+
+    # ------------------------------------------------------------------ inputs
+    def initial_condition(self, seed=None):
+        """Random-mode initial condition [3, nx] float32; draw order as the reference:
+        randint(3,6) density modes, each (randint(1,6), rand, rand); two velocity
+        modes likewise; then randn(nx) noise (src/baseline_solver.py:29-57)."""
+        rng = np.random.RandomState(seed)
+        x = self.x
+
+        def mode(lo, span, trig):
+            k_mode = rng.randint(1, 6)
+            amp = lo + span * rng.rand()
+            phase = 2 * np.pi * rng.rand()
+            return amp * trig(k_mode * x + phase).astype(np.float32)
+
+        n = np.full(self.nx, self.n0, dtype=np.float32)
+        for _ in range(rng.randint(3, 6)):
+            n += mode(0.15, 0.15, np.sin)
+        u = np.zeros(self.nx, dtype=np.float32)
+        for _ in range(2):
+            u += mode(0.1, 0.1, np.cos)
+        u += 0.05 * rng.randn(self.nx).astype(np.float32)
+        E = self.solve_poisson(n)
+        return np.stack([n, u, np.asarray(E, dtype=np.float32)], axis=0).astype(np.float32)
+
+    # ------------------------------------------------------------------ field solve
+    def solve_poisson(self, n):
+        """E = Re ifft(i fft(n - n0)/k) (src/baseline_solver.py:59-68); n is [nx] or [B, nx]."""
+        is_np = isinstance(n, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(n, dtype=np.float32)) if is_np else n
+        single = t.dim() == 1
+        t = (t.unsqueeze(0) if single else t).to(device=self.device, dtype=torch.float32).contiguous()
+        _, gtab = self.grid.tables(self.device)
+        with torch.cuda.device(self.device):
+            out = torch.empty_like(t)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib().fluxgnn_poisson_spectral(t.data_ptr(), self.nx, out.data_ptr(), self.nx,
+                                                           gtab.data_ptr(), t.shape[0], self.nx, stream),
+                       "fluxgnn_poisson_spectral")
+        out = out[0] if single else out
+        return out.cpu().numpy() if is_np else out
+
+    # ---- small host helpers kept for API compatibility (src/baseline_solver.py:70-78) ----
+    def compute_flux_n(self, n, u):
+        return (n * u).astype(np.float32)
+
+    def compute_flux_u(self, u):
+        return (0.5 * u * u).astype(np.float32)
+
+    def laplacian_u(self, u):
+        return (np.roll(u, -1) - 2 * u + np.roll(u, 1)) / (self.dx ** 2)
+
+    # ------------------------------------------------------------------ stepping
+    def rollout(self, state: torch.Tensor, n_steps: int, record_every: int = 0, record_flux: bool = False):
+        """Device-resident rollout of state [B,3,nx] (CUDA float32).
+        Returns (final [B,3,nx], traj [n_steps//record_every, B,3,nx] | None, flux_n [n_steps,B,nx] | None)."""
+        B, _, nx = state.shape
+        if nx != self.nx:
+            raise ValueError(f"state has nx={nx}, solver has nx={self.nx}")
+        dev = self.device
+        _, gtab = self.grid.tables(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty_like(state)
+            work = torch.empty_like(state) if n_steps > 1 else None
+            traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
+                    if record_every else None)
+            flux = torch.empty(n_steps, B, nx, dtype=torch.float32, device=dev) if record_flux else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib().fluxgnn_baseline_rollout(
+                state.data_ptr(), out.data_ptr(), gtab.data_ptr(), B, nx,
+                self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)),
+                n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
+                flux.data_ptr() if flux is not None else None,
+                work.data_ptr() if work is not None else None, stream), "fluxgnn_baseline_rollout")
+        return out, traj, flux
+
+    def step(self, state, return_flux=False):
+        """One step (src/baseline_solver.py:80-101); with return_flux also the continuity flux F_n."""
+        dev_state, kind = _as_device_batch(state, self.device)
+        out, _, flux = self.rollout(dev_state, 1, record_flux=return_flux)
+        new = _hand_back(out, kind)
+        if return_flux:
+            return new, _hand_back(flux[0], kind)
+        return new
+
+    def run(self, state0, n_steps=10, record_flux=True):
+        """[T+1,3,nx] states including state0 and [T,nx] fluxes (src/baseline_solver.py:103-118)."""
+        dev_state, kind = _as_device_batch(state0, self.device)
+        _, traj, flux = self.rollout(dev_state, n_steps, record_every=1, record_flux=record_flux)
+        states = torch.cat([dev_state.unsqueeze(0), traj], dim=0)
+        return _hand_back(states, kind, lead=1), (_hand_back(flux, kind, lead=1) if record_flux else None)

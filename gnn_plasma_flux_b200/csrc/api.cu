@@ -1,0 +1,267 @@
+// C ABI of libfluxgnn.so (declared in include/fluxgnn.h): argument checking,
+// tiling decisions and launch sequencing.  No allocation, no synchronisation,
+// no CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "field_kernels.cuh"
+#include "hybrid_kernel.cuh"
+
+namespace fluxgnn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t err, const char* what) {
+    return set_error(FLUXGNN_ECUDA, "CUDA error %d (%s) in %s", (int)err, cudaGetErrorString(err), what);
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+static int sm_count(int* out) {
+    int dev = 0;
+    FLUXGNN_CUDA_OK(cudaGetDevice(&dev));
+    FLUXGNN_CUDA_OK(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return FLUXGNN_OK;
+}
+
+// Tiling of [B][nx] cells into 128-row tiles (see hybrid_kernel.cu).
+static int plan_tiles(HybridArgs& a, int* fast_radius) {
+    const int nx = a.nx;
+    if (nx <= kTileRows) {
+        a.whole_ic = 1;
+        a.ics_per_tile = kTileRows / nx;
+        a.tiles_per_ic = 0;
+        a.valid = a.halo = 0;
+        const long long tiles = ((long long)a.B + a.ics_per_tile - 1) / a.ics_per_tile;
+        if (tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");
+        a.num_tiles = (int)tiles;
+        *fast_radius = (nx % 8 == 0 && a.radius <= 4) ? a.radius : 0;
+    } else {
+        a.whole_ic = 0;
+        a.ics_per_tile = 0;
+        a.halo = a.L * a.radius + a.hops;
+        a.valid = kTileRows - 2 * a.halo;
+        if (a.valid < 8)
+            return set_error(FLUXGNN_EUNSUP, "receptive field L*radius+hops = %d cells does not fit a 128-cell tile", a.halo);
+        a.tiles_per_ic = (nx + a.valid - 1) / a.valid;
+        const long long tiles = (long long)a.B * a.tiles_per_ic;
+        if (tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");
+        a.num_tiles = (int)tiles;
+        *fast_radius = (a.radius <= 4) ? a.radius : 0;
+    }
+    // test hook: walk the prev/next tables even where the 128-bit window path applies
+    const char* force = getenv("FLUXGNN_FORCE_GENERIC");
+    if (force != nullptr && force[0] == '1') *fast_radius = 0;
+    return FLUXGNN_OK;
+}
+
+static int check_model(const void* packed, int L, int B, int nx, int radius) {
+    if (packed == nullptr) return set_error(FLUXGNN_EINVAL, "packed weights pointer is null");
+    if (L < 1 || L > kMaxL) return set_error(FLUXGNN_EUNSUP, "num_layers must be in 1..%d, got %d", kMaxL, L);
+    if (B < 1 || nx < 1) return set_error(FLUXGNN_EINVAL, "B and nx must be >= 1 (B=%d nx=%d)", B, nx);
+    if (radius < 1) return set_error(FLUXGNN_EINVAL, "radius must be >= 1, got %d", radius);
+    return FLUXGNN_OK;
+}
+
+static int launch_tiles(const HybridArgs& a, int fast_radius, cudaStream_t stream) {
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    FLUXGNN_CUDA_OK(launch_hybrid_tiles(a, fast_radius, grid, stream));
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+static int launch_poisson(const float* n, long long ns, float* E, long long es, const double* gtab,
+                          int B, int nx, cudaStream_t stream) {
+    if (nx > kPoissonDirectMaxNx)
+        return set_error(FLUXGNN_EUNSUP, "field solve for nx=%d > %d is not implemented in this build", nx,
+                         kPoissonDirectMaxNx);
+    dim3 grid((unsigned)B, (unsigned)((nx + 255) / 256));
+    poisson_direct_kernel<<<grid, 256, (size_t)nx * sizeof(float), stream>>>(n, ns, E, es, gtab, nx);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+}  // namespace fluxgnn
+
+using namespace fluxgnn;
+
+extern "C" {
+
+int fluxgnn_abi_version(void) { return FLUXGNN_ABI_VERSION; }
+
+const char* fluxgnn_last_error(void) { return g_err; }
+
+unsigned long long fluxgnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t fluxgnn_packed_weight_bytes(int num_layers) {
+    if (num_layers < 1 || num_layers > kMaxL) return 0;
+    return packed_floats(num_layers) * sizeof(float);
+}
+
+int fluxgnn_pack_weights(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
+                         const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
+                         int num_layers, void* packed, void* stream) {
+    if (num_layers < 1 || num_layers > kMaxL)
+        return set_error(FLUXGNN_EUNSUP, "num_layers must be in 1..%d, got %d", kMaxL, num_layers);
+    if (!w_in || !b_in || !w_upd || !b_upd || !w_e1 || !b_e1 || !w_e2 || !b_e2 || !packed)
+        return set_error(FLUXGNN_EINVAL, "null weight pointer");
+    const size_t total = packed_floats(num_layers);
+    const int blocks = (int)((total + 255) / 256);
+    pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_in, b_in, w_upd, b_upd, w_e1, b_e1, w_e2, b_e2,
+                                                                   num_layers, (float*)packed);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+int fluxgnn_poisson_table(int nx, double length, double* gtab, void* stream) {
+    if (nx < 1 || !(length > 0.0) || gtab == nullptr)
+        return set_error(FLUXGNN_EINVAL, "poisson_table: nx=%d length=%g gtab=%p", nx, length, (void*)gtab);
+    poisson_table_kernel<<<nx, 128, 0, (cudaStream_t)stream>>>(nx, length, gtab);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+int fluxgnn_poisson_spectral(const float* n, long long n_ic_stride, float* E, long long e_ic_stride,
+                             const double* gtab, int B, int nx, void* stream) {
+    if (!n || !E || !gtab || B < 1 || nx < 1 || n_ic_stride < nx || e_ic_stride < nx)
+        return set_error(FLUXGNN_EINVAL, "poisson_spectral: bad argument (B=%d nx=%d)", B, nx);
+    return launch_poisson(n, n_ic_stride, E, e_ic_stride, gtab, B, nx, (cudaStream_t)stream);
+}
+
+int fluxgnn_forward_ring(const void* packed, int num_layers, const float* state, const float* x,
+                         int B, int nx, int radius, int hops, float* flux_edges, float* face_flux,
+                         void* stream) {
+    int rc = check_model(packed, num_layers, B, nx, radius);
+    if (rc != FLUXGNN_OK) return rc;
+    if (!state || !x) return set_error(FLUXGNN_EINVAL, "forward_ring: null state or x");
+    if (hops < 1 || hops > kMaxHops || hops > radius)
+        return set_error(FLUXGNN_EINVAL, "forward_ring: hops must be in 1..min(radius,%d), got %d", kMaxHops, hops);
+    if (!flux_edges && !face_flux) return set_error(FLUXGNN_EINVAL, "forward_ring: no output requested");
+    HybridArgs a{};
+    a.packed = (const float*)packed;
+    a.state_in = state;
+    a.x = x;
+    a.flux_edges = flux_edges;
+    a.face_flux = face_flux;
+    a.B = B; a.nx = nx; a.radius = radius; a.L = num_layers; a.hops = hops;
+    a.do_update = 0; a.steps = 1; a.record_every = 1;
+    int fast = 0;
+    rc = plan_tiles(a, &fast);
+    if (rc != FLUXGNN_OK) return rc;
+    return launch_tiles(a, fast, (cudaStream_t)stream);
+}
+
+size_t fluxgnn_hybrid_workspace_bytes(int B, int nx) {
+    if (B < 1 || nx < 1) return 0;
+    return nx <= kTileRows ? 0 : (size_t)B * 3 * nx * sizeof(float);
+}
+
+int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* state_in, float* state_out,
+                           const float* x, const double* gtab, int B, int nx, int radius, float c, float dt,
+                           int steps, int record_every, float* traj, void* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_model(packed, num_layers, B, nx, radius);
+    if (rc != FLUXGNN_OK) return rc;
+    if (!state_in || !state_out || !x || !gtab) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: null pointer");
+    if (state_in == state_out) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: state_in and state_out alias");
+    if (steps < 1) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: steps must be >= 1, got %d", steps);
+    if (traj && record_every < 1) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: record_every must be >= 1");
+    HybridArgs a{};
+    a.packed = (const float*)packed;
+    a.x = x;
+    a.gtab = gtab;
+    a.B = B; a.nx = nx; a.radius = radius; a.L = num_layers; a.hops = 1;
+    a.do_update = 1;
+    a.c = c; a.dt = dt;
+    a.record_every = record_every < 1 ? 1 : record_every;
+    int fast = 0;
+    rc = plan_tiles(a, &fast);
+    if (rc != FLUXGNN_OK) return rc;
+
+    if (a.whole_ic) {
+        // whole ICs per tile: the complete rollout is ONE persistent launch, state in shared memory
+        a.state_in = state_in;
+        a.state_out = state_out;
+        a.traj = traj;
+        a.steps = steps;
+        return launch_tiles(a, fast, stream);
+    }
+    // window tiles: per step  tile kernel (n', u')  ->  field-solve kernel (E')
+    if (steps > 1 && workspace == nullptr)
+        return set_error(FLUXGNN_EINVAL, "hybrid_rollout: workspace required for nx > %d and steps > 1", kTileRows);
+    const size_t state_floats = (size_t)B * 3 * nx;
+    const float* src = state_in;
+    a.steps = 1;
+    a.traj = nullptr;
+    for (int t = 0; t < steps; ++t) {
+        float* dst = ((steps - 1 - t) % 2 == 0) ? state_out : (float*)workspace;
+        a.state_in = src;
+        a.state_out = dst;
+        rc = launch_tiles(a, fast, stream);
+        if (rc != FLUXGNN_OK) return rc;
+        rc = launch_poisson(dst, 3LL * nx, dst + 2 * (size_t)nx, 3LL * nx, gtab, B, nx, stream);
+        if (rc != FLUXGNN_OK) return rc;
+        if (traj && (t + 1) % record_every == 0) {
+            FLUXGNN_CUDA_OK(cudaMemcpyAsync(traj + (size_t)((t + 1) / record_every - 1) * state_floats, dst,
+                                            state_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        }
+        src = dst;
+    }
+    return FLUXGNN_OK;
+}
+
+int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const double* gtab, int B, int nx,
+                             float c, float dt, float nu, float dx2, int steps, int record_every, float* traj,
+                             float* flux_n, void* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!state_in || !state_out || !gtab || B < 1 || nx < 1)
+        return set_error(FLUXGNN_EINVAL, "baseline_rollout: bad argument (B=%d nx=%d)", B, nx);
+    if (state_in == state_out) return set_error(FLUXGNN_EINVAL, "baseline_rollout: state_in and state_out alias");
+    if (steps < 1) return set_error(FLUXGNN_EINVAL, "baseline_rollout: steps must be >= 1, got %d", steps);
+    if (steps > 1 && workspace == nullptr)
+        return set_error(FLUXGNN_EINVAL, "baseline_rollout: workspace of B*3*nx floats required for steps > 1");
+    if (traj && record_every < 1) return set_error(FLUXGNN_EINVAL, "baseline_rollout: record_every must be >= 1");
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    const size_t state_floats = (size_t)B * 3 * nx;
+    const long long cells = (long long)B * nx;
+    long long blocks = (cells + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    const float* src = state_in;
+    for (int t = 0; t < steps; ++t) {
+        float* dst = ((steps - 1 - t) % 2 == 0) ? state_out : (float*)workspace;
+        baseline_fv_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, flux_n ? flux_n + (size_t)t * cells : nullptr,
+                                                                 B, nx, c, dt, nu, dx2);
+        FLUXGNN_CUDA_OK(cudaGetLastError());
+        count_launch();
+        rc = launch_poisson(dst, 3LL * nx, dst + 2 * (size_t)nx, 3LL * nx, gtab, B, nx, stream);
+        if (rc != FLUXGNN_OK) return rc;
+        if (traj && (t + 1) % record_every == 0) {
+            FLUXGNN_CUDA_OK(cudaMemcpyAsync(traj + (size_t)((t + 1) / record_every - 1) * state_floats, dst,
+                                            state_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        }
+        src = dst;
+    }
+    return FLUXGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Field solve, classical finite-volume step and weight packing kernels (sm_100a).
+//
+//   poisson_table_kernel   g = Re ifft(i/k)                    src/baseline_solver.py:26,59-68
+//   poisson_direct_kernel  E = g (*) (n - 1), any nx           src/baseline_solver.py:59-68
+//   baseline_fv_kernel     upwind / forward-Euler + viscosity  src/baseline_solver.py:70-94
+//   pack_weights_kernel    state_dict -> streaming layout      src/flux_gnn.py:17-38
+#include "common.cuh"
+#include "field_kernels.cuh"
+
+namespace fluxgnn {
+
+// ---------------------------------------------------------------------------
+// g_j = Re (1/N) sum_{m != 0} (i/k_m) e^{2 pi i m j/N},  k_m = 2 pi m / length
+//     = -(length / (pi N)) * sum_{m=1..M} sin(2 pi m j / N) / m,   M = floor((N-1)/2)
+// (the m = N/2 term of an even N is purely imaginary and vanishes under Re()).
+// One block per j, exact integer reduction of m*j mod N keeps the phase accurate.
+// ---------------------------------------------------------------------------
+__global__ void poisson_table_kernel(int nx, double length, double* __restrict__ gtab) {
+    const int j = blockIdx.x;
+    const int M = (nx - 1) / 2;
+    double s = 0.0;
+    for (int m = 1 + threadIdx.x; m <= M; m += blockDim.x) {
+        const long long r = ((long long)m * j) % nx;
+        s += sinpi(2.0 * (double)r / (double)nx) / (double)m;
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) gtab[j] = -(length / (3.14159265358979323846 * (double)nx)) * s;
+    }
+}
+
+// One block per (IC = blockIdx.x, slab of 256 outputs = blockIdx.y).  rho staged in shared memory as fp32
+// (rho = n - 1 rounded to fp32 exactly as numpy does), fp64 accumulation.
+__global__ void __launch_bounds__(256) poisson_direct_kernel(const float* __restrict__ n, long long n_stride,
+                                                             float* __restrict__ E, long long e_stride,
+                                                             const double* __restrict__ gtab, int nx) {
+    extern __shared__ float rho[];
+    const int ic = blockIdx.x;
+    const float* src = n + (size_t)ic * n_stride;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) rho[i] = __fsub_rn(src[i], 1.0f);
+    __syncthreads();
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= nx) return;
+    double acc0 = 0.0, acc1 = 0.0;
+    int d = j;                       // d = (j - i) mod nx
+    int i = 0;
+    for (; i + 1 < nx; i += 2) {
+        acc0 = fma(__ldg(gtab + d), (double)rho[i], acc0);
+        d = (d == 0) ? nx - 1 : d - 1;
+        acc1 = fma(__ldg(gtab + d), (double)rho[i + 1], acc1);
+        d = (d == 0) ? nx - 1 : d - 1;
+    }
+    if (i < nx) acc0 = fma(__ldg(gtab + d), (double)rho[i], acc0);
+    E[(size_t)ic * e_stride + j] = (float)(acc0 + acc1);
+}
+
+// Every intermediate is rounded to fp32 exactly where numpy rounds it
+// (python-float scalars are weak, so c, dt, nu and dx^2 act as float32).
+__global__ void __launch_bounds__(256) baseline_fv_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                          float* __restrict__ flux_n, int B, int nx,
+                                                          float c, float dt, float nu, float dx2) {
+    const long long total = (long long)B * nx;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int ic = (int)(idx / nx);
+        const int i = (int)(idx - (long long)ic * nx);
+        const int im = (i == 0) ? nx - 1 : i - 1;
+        const int ip = (i == nx - 1) ? 0 : i + 1;
+        const float* pn = in + (size_t)ic * 3 * nx;
+        const float* pu = pn + nx;
+        const float* pe = pu + nx;
+        const float n0 = pn[i], nm = pn[im];
+        const float u0 = pu[i], um = pu[im], up = pu[ip];
+        const float fn = __fmul_rn(n0, u0), fnm = __fmul_rn(nm, um);                   // :70-71
+        const float n_new = __fsub_rn(n0, __fmul_rn(c, __fsub_rn(fn, fnm)));           // :85-86
+        const float fu = __fmul_rn(__fmul_rn(0.5f, u0), u0);                           // :73-74
+        const float fum = __fmul_rn(__fmul_rn(0.5f, um), um);
+        const float u_adv = __fsub_rn(u0, __fmul_rn(c, __fsub_rn(fu, fum)));           // :90-91
+        const float lap = __fdiv_rn(__fadd_rn(__fsub_rn(up, __fmul_rn(2.0f, u0)), um), dx2);   // :76-78
+        const float u_new = __fadd_rn(u_adv, __fmul_rn(dt, __fadd_rn(pe[i], __fmul_rn(nu, lap))));   // :94
+        float* po = out + (size_t)ic * 3 * nx;
+        po[i] = n_new;
+        po[nx + i] = u_new;
+        if (flux_n != nullptr) flux_n[idx] = fn;
+    }
+}
+
+// packed small block + (L+1) x 2 K-major halves (see common.cuh)
+__global__ void pack_weights_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
+                                    const float* __restrict__ w_upd, const float* __restrict__ b_upd,
+                                    const float* __restrict__ w_e1, const float* __restrict__ b_e1,
+                                    const float* __restrict__ w_e2, const float* __restrict__ b_e2,
+                                    int L, float* __restrict__ packed) {
+    const size_t total = packed_floats(L);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (idx < (size_t)SmallParams::count) {
+            const int o = (int)idx;
+            if (o < SmallParams::b_in) {                       // w_in[f][n] <- W_in[n][f]
+                const int f = o / kH, n = o % kH;
+                v = w_in[n * kF + f];
+            } else if (o < SmallParams::b_upd) {
+                v = b_in[o - SmallParams::b_in];
+            } else if (o < SmallParams::b_e1) {
+                const int q = o - SmallParams::b_upd;
+                v = (q < L * kH) ? b_upd[q] : 0.f;
+            } else if (o < SmallParams::w_e2) {
+                v = b_e1[o - SmallParams::b_e1];
+            } else if (o < SmallParams::b_e2) {
+                v = w_e2[o - SmallParams::w_e2];
+            } else if (o == SmallParams::b_e2) {
+                v = b_e2[0];
+            }
+        } else {
+            const size_t q = idx - SmallParams::count;
+            const int layer = (int)(q / kLayerFloats);
+            const int r = (int)(q % kLayerFloats);
+            const int half = r / kHalfFloats;                  // 0: W[:, H:], 1: W[:, :H]
+            const int k = (r % kHalfFloats) / kH;
+            const int n = r % kH;
+            const float* W = (layer < L) ? (w_upd + (size_t)layer * kH * 2 * kH) : w_e1;
+            v = W[(size_t)n * 2 * kH + (half == 0 ? kH : 0) + k];
+        }
+        packed[idx] = v;
+    }
+}
+
+}  // namespace fluxgnn

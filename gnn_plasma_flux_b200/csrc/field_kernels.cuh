@@ -1,0 +1,19 @@
+// Kernels of field_kernels.cu (declarations for api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace fluxgnn {
+
+__global__ void poisson_table_kernel(int nx, double length, double* gtab);
+__global__ void poisson_direct_kernel(const float* n, long long n_stride, float* E, long long e_stride,
+                                      const double* gtab, int nx);
+__global__ void baseline_fv_kernel(const float* in, float* out, float* flux_n, int B, int nx,
+                                   float c, float dt, float nu, float dx2);
+__global__ void pack_weights_kernel(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
+                                    const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
+                                    int L, float* packed);
+
+constexpr int kPoissonDirectMaxNx = 12288;   // rho staged in 48 KiB of shared memory
+
+}  // namespace fluxgnn

@@ -1,0 +1,35 @@
+// Launch interface of the fused hybrid tile kernel (hybrid_kernel.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace fluxgnn {
+
+constexpr int kTileRows = 128;     // cells per tile (= GEMM M)
+
+struct HybridArgs {
+    const float* packed;       // fluxgnn_pack_weights() output
+    const float* state_in;     // [B][3][nx]
+    float* state_out;          // [B][3][nx]            (update mode)
+    const float* x;            // [nx] cell centres
+    const double* gtab;        // [nx] field-solve kernel (whole-IC update mode)
+    float* flux_edges;         // nullable [B][2*hops*nx]
+    float* face_flux;          // nullable [B][nx]
+    float* traj;               // nullable [steps/record_every][B][3][nx]
+    int B, nx, radius, L, hops;
+    int whole_ic;              // 1: tile = floor(128/nx) complete ICs; 0: window of one IC + halo
+    int ics_per_tile;          // whole-IC tiles
+    int tiles_per_ic, valid, halo;   // window tiles
+    int num_tiles;
+    int do_update;             // 0: forward only; 1: finite-volume update (+ field solve when whole_ic)
+    int steps, record_every;   // steps > 1 only for whole-IC update mode
+    float c, dt;               // float32(dt/dx), float32(dt)
+};
+
+size_t hybrid_tile_smem_bytes();
+
+// fast_radius 1..4 selects the compile-time-radius window path; 0 the generic path.
+cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream);
+
+}  // namespace fluxgnn

@@ -1,0 +1,41 @@
+"""Periodic cell-centred grid and its device-side tables.
+
+Restates the constructor arithmetic of src/baseline_solver.py:14-27 (dx, x, k)
+and owns the two device arrays every kernel call needs: the float32 cell
+centres (node feature 4, src/graph_constructor.py:30) and the float64
+circular-convolution table of the spectral field solve.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class PeriodicGrid:
+    def __init__(self, nx: int = 64, length: float = 2 * math.pi):
+        self.nx = int(nx)
+        self.length = float(length)
+        self.dx = self.length / self.nx
+        self.x = np.linspace(0.5 * self.dx, self.length - 0.5 * self.dx, self.nx)
+        self.k = 2.0 * np.pi * np.fft.fftfreq(self.nx, d=self.dx)
+        self._dev = {}
+
+    def tables(self, device) -> tuple[torch.Tensor, torch.Tensor]:
+        """(x float32 [nx], gtab float64 [nx]) on `device`, built once per device."""
+        device = torch.device(device)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        hit = self._dev.get(key)
+        if hit is None:
+            with torch.cuda.device(device):
+                x_dev = torch.as_tensor(self.x, dtype=torch.float32).to(device)
+                gtab = torch.empty(self.nx, dtype=torch.float64, device=device)
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _lib.check(_lib.lib().fluxgnn_poisson_table(self.nx, self.length, gtab.data_ptr(), stream),
+                           "fluxgnn_poisson_table")
+            hit = (x_dev, gtab)
+            self._dev[key] = hit
+        return hit

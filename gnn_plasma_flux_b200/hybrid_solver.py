@@ -1,0 +1,102 @@
+"""HybridSolver, drop-in for src/hybrid_solver.py of the reference, on sm_100a.
+
+    HybridSolver(model_path, radius, nx=64, length=2*pi, dt=5e-3, t_end=1.0, device='cuda')
+    .step(state[3,nx] np.float32) -> np.float32 [3,nx]            (src/hybrid_solver.py:34-64)
+    .run(state0, n_steps=40)      -> np.float32 [n_steps+1,3,nx]  (src/hybrid_solver.py:66-73)
+    .baseline, .model, .device, .radius                            (src/hybrid_solver.py:18,29-32)
+
+The whole step -- FluxGNN on the ring, finite-volume update, field solve -- is
+one call into libfluxgnn.so; for nx <= 128 a complete multi-step rollout is one
+persistent kernel launch.  Batched states ([B,3,nx] numpy or CUDA tensors) are
+accepted everywhere; CUDA tensors never leave the device.
+
+`radius`: in the reference it is only a label (the graph is always the
+nearest-neighbour ring), so by default this class reproduces that:
+results equal the reference's for every `radius`.  Pass `graph_radius=r` to
+really message-pass over hop distances 1..r (BASELINE.json's radius-2/3 configs).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .baseline_solver import BaselineSolver, _as_device_batch, _hand_back
+from .config import MODEL_CONFIG
+from .flux_gnn import FluxGNN
+
+
+class HybridSolver:
+    def __init__(self, model_path, radius, nx=64, length=2 * math.pi, dt=5e-3, t_end=1.0, device="cuda", *,
+                 graph_radius=None, model=None):
+        self.device = device
+        self.baseline = BaselineSolver(nx=nx, length=length, dt=dt, t_end=t_end, device=device)
+        if model is None:
+            model = FluxGNN(input_dim=MODEL_CONFIG["input_dim"], hidden_dim=MODEL_CONFIG["hidden_dim"],
+                            num_layers=MODEL_CONFIG["num_layers"])
+            model.load_state_dict(torch.load(model_path, map_location=device))
+        self.model = model.to(device)
+        self.model.eval()
+        self.radius = radius
+        self.graph_radius = 1 if graph_radius is None else int(graph_radius)
+        self._pinned = {}
+
+    # ------------------------------------------------------------------ device-resident API
+    def rollout(self, state: torch.Tensor, n_steps: int, record_every: int = 0, out: torch.Tensor | None = None):
+        """Advance state [B,3,nx] (CUDA float32, contiguous) by n_steps.
+        Returns (final [B,3,nx], traj [n_steps//record_every,B,3,nx] | None)."""
+        base = self.baseline
+        if state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != base.nx:
+            raise ValueError(f"state must be [B,3,{base.nx}], got {tuple(state.shape)}")
+        packed = self.model.packed_weights()
+        dev = packed.device
+        if state.device != dev or state.dtype != torch.float32 or not state.is_contiguous():
+            state = state.to(device=dev, dtype=torch.float32).contiguous()
+        B, _, nx = state.shape
+        x_dev, gtab = base.grid.tables(dev)
+        with torch.cuda.device(dev):
+            if out is None:
+                out = torch.empty_like(state)
+            traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
+                    if record_every else None)
+            ws_bytes = _lib.lib().fluxgnn_hybrid_workspace_bytes(B, nx)
+            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if (ws_bytes and n_steps > 1) else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib().fluxgnn_hybrid_rollout(
+                packed.data_ptr(), self.model.num_layers, state.data_ptr(), out.data_ptr(),
+                x_dev.data_ptr(), gtab.data_ptr(), B, nx, self.graph_radius,
+                float(np.float32(base.dt / base.dx)), float(np.float32(base.dt)),
+                n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
+                work.data_ptr() if work is not None else None, stream), "fluxgnn_hybrid_rollout")
+        return out, traj
+
+    def step_pinned(self, host_in: torch.Tensor, host_out: torch.Tensor, n_steps: int = 1):
+        """End-to-end step on HOST buffers: pinned [B,3,nx] float32 in -> pinned out, with the
+        host->device and device->host copies on the current stream; returns after the
+        result is readable on the host."""
+        dev = torch.device(self.device)
+        key = tuple(host_in.shape)
+        bufs = self._pinned.get(key)
+        if bufs is None:
+            bufs = (torch.empty(key, dtype=torch.float32, device=dev), torch.empty(key, dtype=torch.float32, device=dev))
+            self._pinned[key] = bufs
+        d_in, d_out = bufs
+        d_in.copy_(host_in, non_blocking=True)
+        self.rollout(d_in, n_steps, out=d_out)
+        host_out.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return host_out
+
+    # ------------------------------------------------------------------ reference API
+    def step(self, state):
+        dev_state, kind = _as_device_batch(state, self.device)
+        out, _ = self.rollout(dev_state, 1)
+        return _hand_back(out, kind)
+
+    def run(self, state0, n_steps=40):
+        dev_state, kind = _as_device_batch(state0, self.device)
+        _, traj = self.rollout(dev_state, n_steps, record_every=1)
+        states = torch.cat([dev_state.unsqueeze(0), traj], dim=0)      # [T+1,B,3,nx]
+        return _hand_back(states, kind, lead=1)

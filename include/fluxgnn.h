@@ -1,0 +1,134 @@
+/*
+ * fluxgnn.h -- C ABI of libfluxgnn.so, the sm_100a implementation of the hybrid
+ * rollout hot path of shanedirksen/gnn-plasma-flux.
+ *
+ * The reference is pure Python and has no FFI of its own; every entry point
+ * below names the reference code (path:line under /root/reference) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ / torch types.
+ *   - Every pointer is a DEVICE pointer owned by the caller unless its name
+ *     starts with `host_`.  Arrays are row-major contiguous float32 unless
+ *     stated.  The library never allocates caller-visible memory and never
+ *     synchronises; every call is asynchronous on `stream` (a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream).
+ *   - Return value: 0 on success, a negative FLUXGNN_E* code on failure.
+ *     fluxgnn_last_error() returns a thread-local message for the last failure.
+ *   - There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with FLUXGNN_ECUDA.
+ *
+ * State layout: state[B][3][nx] = (n, u, E) per initial condition ("IC"),
+ * the batched form of the reference's numpy [3, nx] state
+ * (src/hybrid_solver.py:34-35, src/baseline_solver.py:80-81).
+ */
+#ifndef FLUXGNN_H_
+#define FLUXGNN_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLUXGNN_ABI_VERSION 1
+
+#define FLUXGNN_OK        0
+#define FLUXGNN_EINVAL   -1   /* bad argument (shape, null pointer, unsupported size) */
+#define FLUXGNN_ECUDA    -2   /* CUDA runtime error (message has the CUDA string)    */
+#define FLUXGNN_EUNSUP   -3   /* valid request this build does not implement          */
+
+/* Architecture limits of this build (src/config.py:19-23 uses F=4, H=128, L=4). */
+#define FLUXGNN_INPUT_DIM   4
+#define FLUXGNN_HIDDEN    128
+#define FLUXGNN_MAX_LAYERS  8
+#define FLUXGNN_MAX_HOPS    4    /* edge blocks the forward entry point can emit */
+
+int fluxgnn_abi_version(void);
+const char* fluxgnn_last_error(void);
+
+/* Number of kernels this library has launched since it was loaded (all threads). */
+unsigned long long fluxgnn_launch_count(void);
+
+/* ---- weights: FluxGNN.state_dict() -> streaming layout -------------------
+ * Replaces the parameter container of src/flux_gnn.py:11-38.  Inputs are the
+ * tensors of the state_dict, unchanged (nn.Linear layout [out, in]):
+ *   w_in[H][F], b_in[H]                       input_mlp.0      (:17-20)
+ *   w_upd[l][H][2H], b_upd[l][H]  l<L         update_mlps.l.0  (:23-31), contiguous over l
+ *   w_e1[H][2H], b_e1[H]                      edge_mlp.0       (:34-36)
+ *   w_e2[H], b_e2[1]                          edge_mlp.2       (:37)
+ * `packed` receives fluxgnn_packed_weight_bytes(L) bytes: the small vectors,
+ * then for every layer the two [H(k)][H(n)] halves of the weight matrix in the
+ * 16-row chunks the kernel streams through shared memory with bulk copies. */
+size_t fluxgnn_packed_weight_bytes(int num_layers);
+int fluxgnn_pack_weights(const float* w_in, const float* b_in,
+                         const float* w_upd, const float* b_upd,
+                         const float* w_e1, const float* b_e1,
+                         const float* w_e2, const float* b_e2,
+                         int num_layers, void* packed, void* stream);
+
+/* ---- Poisson operator table ------------------------------------------------
+ * src/baseline_solver.py:59-68 is the circular convolution E = g (*) (n - 1)
+ * with g = Re ifft(i/k), g_hat(0) = 0 (the Nyquist bin drops out of Re()).
+ * Fills gtab[nx] (float64, device) for k = 2*pi*fftfreq(nx, length/nx)
+ * (src/baseline_solver.py:26). */
+int fluxgnn_poisson_table(int nx, double length, double* gtab, void* stream);
+
+/* E[B][nx] = solve_poisson(n[B][nx]) (src/baseline_solver.py:59-68), any nx >= 1.
+ * `n` and `E` have the given strides (in floats) between ICs so that a channel
+ * of a [B][3][nx] state can be passed directly. */
+int fluxgnn_poisson_spectral(const float* n, long long n_ic_stride,
+                             float* E, long long e_ic_stride,
+                             const double* gtab, int B, int nx, void* stream);
+
+/* ---- FluxGNN.forward on the radius-r ring ----------------------------------
+ * Replaces build_chain_graph + FluxGNN.forward (src/graph_constructor.py:30-38,
+ * src/flux_gnn.py:40-67) for the periodic chain, with no edge_index tensor:
+ * edge blocks are, for hop k = 1..hops, [i -> i+k] then [i+k -> i], nx edges
+ * each (k = 1 is exactly the reference's edge order).
+ *   state[B][3][nx], x[nx] (cell centres, float32)
+ *   flux_edges[B][2*hops*nx]  (nullable)    per directed edge, as FluxGNN.forward
+ *   face_flux[B][nx]          (nullable)    0.5*(fwd+bwd) of hop 1 (src/hybrid_solver.py:45-48)
+ * radius >= 1; hops in 1..FLUXGNN_MAX_HOPS, hops <= radius. */
+int fluxgnn_forward_ring(const void* packed, int num_layers,
+                         const float* state, const float* x,
+                         int B, int nx, int radius, int hops,
+                         float* flux_edges, float* face_flux, void* stream);
+
+/* ---- HybridSolver.step / .run ------------------------------------------------
+ * Replaces src/hybrid_solver.py:34-73 for a batch of ICs.  One call advances
+ * `steps` time steps:  GNN face flux -> n' = n - (dt/dx)(F_i - F_{i-1});
+ * u' = u - (dt/dx)(u_i^2/2 - u_{i-1}^2/2) + dt*E (no viscosity, as the
+ * reference) -> E' = solve_poisson(n').
+ *   state_in[B][3][nx] -> state_out[B][3][nx]   (may not alias)
+ *   traj: nullable; when given, the state after every `record_every`-th step
+ *         is stored at traj[(t/record_every)-1][B][3][nx], t = 1..steps.
+ *   workspace: fluxgnn_hybrid_workspace_bytes(B, nx) bytes (0 is possible).
+ *   c = float32(dt/dx) and dt = float32(dt), the scalars numpy uses
+ *   (src/hybrid_solver.py:52,57-58). */
+size_t fluxgnn_hybrid_workspace_bytes(int B, int nx);
+int fluxgnn_hybrid_rollout(const void* packed, int num_layers,
+                           const float* state_in, float* state_out,
+                           const float* x, const double* gtab,
+                           int B, int nx, int radius, float c, float dt,
+                           int steps, int record_every, float* traj,
+                           void* workspace, void* stream);
+
+/* ---- BaselineSolver.step / .run ------------------------------------------------
+ * Replaces src/baseline_solver.py:70-118: upwind continuity flux n*u,
+ * left-differenced u^2/2, viscous Laplacian, forward Euler, field solve.
+ *   flux_n: nullable [steps][B][nx], the continuity flux F_n of every step
+ *           (`return_flux` / `record_flux`, :84,:99-100,:109-111).
+ *   traj:   as above.  inv_dx2 = 1/float32(dx^2) is NOT used: the kernel
+ *           divides by dx2 = float32(dx*dx) exactly as numpy does (:78). */
+int fluxgnn_baseline_rollout(const float* state_in, float* state_out,
+                             const double* gtab, int B, int nx,
+                             float c, float dt, float nu, float dx2,
+                             int steps, int record_every, float* traj,
+                             float* flux_n, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUXGNN_H_ */

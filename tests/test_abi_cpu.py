@@ -1,0 +1,98 @@
+"""CPU suite: the C-ABI library builds, loads, exports every symbol include/fluxgnn.h
+declares, and the host-side drop-in classes keep the reference's surface.  No
+compute entry point is called here (no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "fluxgnn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fluxgnn_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(built_lib):
+    from gnn_plasma_flux_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 10
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(raw, name), f"{name} declared in fluxgnn.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES out of sync with fluxgnn.h"
+    assert built_lib.fluxgnn_abi_version() == _lib.ABI_VERSION
+
+
+def test_size_queries(built_lib):
+    small, layer = 2048, 2 * 128 * 128
+    for L in (1, 4, 8):
+        assert built_lib.fluxgnn_packed_weight_bytes(L) == 4 * (small + (L + 1) * layer)
+    assert built_lib.fluxgnn_packed_weight_bytes(0) == 0
+    assert built_lib.fluxgnn_packed_weight_bytes(9) == 0
+    assert built_lib.fluxgnn_hybrid_workspace_bytes(16, 64) == 0
+    assert built_lib.fluxgnn_hybrid_workspace_bytes(16, 1024) == 16 * 3 * 1024 * 4
+
+
+def test_argument_errors_without_gpu(built_lib):
+    from gnn_plasma_flux_b200 import _lib
+    rc = built_lib.fluxgnn_pack_weights(None, None, None, None, None, None, None, None, 4, None, None)
+    assert rc == -1 and b"null" in built_lib.fluxgnn_last_error()
+    rc = built_lib.fluxgnn_hybrid_rollout(None, 4, None, None, None, None, 1, 64, 1, 0.1, 0.1, 1, 1, None, None, None)
+    assert rc == -1
+    rc = built_lib.fluxgnn_forward_ring(ctypes.c_void_p(16), 12, None, None, 1, 64, 1, 1, None, None, None)
+    assert rc == -3                                               # unsupported layer count
+    with pytest.raises(_lib.FluxGNNError):
+        _lib.check(rc, "forward_ring")
+
+
+def test_fluxgnn_module_surface(weights):
+    from gnn_plasma_flux_b200 import FluxGNN, MODEL_CONFIG
+    torch.manual_seed(0)
+    m = FluxGNN(**MODEL_CONFIG)
+    sd = m.state_dict()
+    assert set(sd) == set(weights)
+    for key, val in sd.items():                                    # same construction order => same seeded init
+        np.testing.assert_array_equal(val.numpy(), weights[key])
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    d = FluxGNN()
+    assert (d.input_dim, d.hidden_dim, d.num_layers) == (2, 32, 2)     # reference defaults, src/flux_gnn.py:11
+    from gnn_plasma_flux_b200 import _lib
+    with pytest.raises(_lib.FluxGNNError):                         # loud failure, no CPU fallback
+        m(torch.zeros(64, 4), torch.from_numpy(__import__("oracle.ref_port", fromlist=["x"]).ring_edges(64, 1)))
+    with pytest.raises(NotImplementedError):                       # arbitrary graphs: documented deviation
+        m(torch.zeros(64, 4), torch.zeros(2, 128, dtype=torch.long))
+
+
+def test_build_chain_graph_matches_oracle():
+    from gnn_plasma_flux_b200 import build_chain_graph
+    from gnn_plasma_flux_b200.graph_constructor import is_ring
+    from oracle import ref_port as P
+    rng = np.random.RandomState(0)
+    state = rng.randn(3, 64)                                      # float64 in, as examples/smoke_test.py:36
+    x = np.linspace(0, 1, 64)
+    nf, ei = build_chain_graph(state, x, "cpu")
+    assert nf.shape == (64, 4) and nf.dtype == torch.float32
+    assert ei.shape == (2, 128) and ei.dtype == torch.long
+    np.testing.assert_array_equal(nf.numpy(), P.node_features(state, x))
+    np.testing.assert_array_equal(ei.numpy(), P.ring_edges(64, 1))
+    for r in (2, 3):
+        _, e = build_chain_graph(torch.from_numpy(state.astype(np.float32)), x, radius=r)
+        np.testing.assert_array_equal(e.numpy(), P.ring_edges(64, r))
+        assert is_ring(e.clone(), 64) == r                         # untagged copy is recognised by value
+    assert is_ring(torch.randint(0, 64, (2, 128)), 64) is None
+
+
+def test_baseline_host_surface():
+    from gnn_plasma_flux_b200.grid import PeriodicGrid
+    from oracle import ref_port as P
+    for nx in (64, 1000):
+        g, o = PeriodicGrid(nx), P.Grid(nx=nx)
+        np.testing.assert_array_equal(g.x, o.x)
+        np.testing.assert_array_equal(g.k, o.k)
+        assert g.dx == o.dx

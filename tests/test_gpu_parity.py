@@ -1,0 +1,263 @@
+"""GPU parity suite (-m gpu): the sm_100a path, called through the C ABI
+(ctypes -> libfluxgnn.so), against the golden vectors frozen from the live
+reference and against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 path <= 1e-5 relative per step
+(per channel, max-norm), <= 1e-4 over a 1000-step rollout measured against the
+reference's own fp32-vs-fp64 noise floor; integer/byte-exact work (n', u' of the
+classical solver, whose every fp32 rounding is reproduced) must be bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import batched, ref_port as P
+
+pytestmark = pytest.mark.gpu
+STEP_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def model(weights, built_lib):
+    from gnn_plasma_flux_b200 import FluxGNN, MODEL_CONFIG
+    m = FluxGNN(**MODEL_CONFIG)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    return m.to("cuda").eval()
+
+
+def make_solver(model, nx, dt, graph_radius=None, radius=1):
+    from gnn_plasma_flux_b200 import HybridSolver
+    return HybridSolver(None, radius, nx=nx, dt=dt, device="cuda", graph_radius=graph_radius, model=model)
+
+
+# ----------------------------------------------------------------------------- weights
+def test_pack_weights_layout(model, weights):
+    packed = model.packed_weights().cpu().numpy()
+    H, small = 128, 2048
+    assert packed.size == small + 5 * 2 * H * H
+    np.testing.assert_array_equal(packed[:4 * H].reshape(4, H), weights["input_mlp.0.weight"].T)
+    np.testing.assert_array_equal(packed[4 * H:5 * H], weights["input_mlp.0.bias"])
+    for l in range(4):
+        np.testing.assert_array_equal(packed[5 * H + l * H:5 * H + (l + 1) * H], weights[f"update_mlps.{l}.0.bias"])
+    np.testing.assert_array_equal(packed[13 * H:14 * H], weights["edge_mlp.0.bias"])
+    np.testing.assert_array_equal(packed[14 * H:15 * H], weights["edge_mlp.2.weight"][0])
+    assert packed[15 * H] == weights["edge_mlp.2.bias"][0]
+    stream = packed[small:].reshape(5, 2, H, H)                   # [layer][half][k][n]
+    for l in range(5):
+        W = weights[f"update_mlps.{l}.0.weight"] if l < 4 else weights["edge_mlp.0.weight"]
+        np.testing.assert_array_equal(stream[l, 0], W[:, H:].T)   # neighbour / col half
+        np.testing.assert_array_equal(stream[l, 1], W[:, :H].T)   # self / row half
+
+
+# ----------------------------------------------------------------------------- field solve
+@pytest.mark.parametrize("nx", [64, 96, 1024])
+def test_poisson_golden(built_lib, nx):
+    from gnn_plasma_flux_b200 import BaselineSolver
+    g4 = load_golden("g4_poisson_ic.npz")
+    sol = BaselineSolver(nx=nx, dt=1e-4)
+    _, gtab = sol.grid.tables("cuda")
+    g_ref = P.poisson_kernel(nx, sol.length)
+    assert np.abs(gtab.cpu().numpy() - g_ref).max() <= 1e-12 * np.abs(g_ref).max() + 1e-15
+    for name in ("modes", "white", "nyquist", "const"):
+        E = sol.solve_poisson(g4[f"n_{name}_nx{nx}"])
+        ref = g4[f"E_{name}_nx{nx}"]
+        assert E.dtype == np.float32 and E.shape == ref.shape
+        scale = max(np.abs(ref).max(), 1e-3)
+        assert np.abs(E - ref).max() <= 2e-6 * scale, name
+    for seed in (0, 1, 123):                                       # initial_condition goes through the same solve
+        ic = sol.initial_condition(seed)
+        ref = g4[f"ic_nx{nx}_s{seed}"]
+        np.testing.assert_array_equal(ic[:2], ref[:2])
+        assert P.rel_err(ic, ref).max() < 2e-6
+    batch = np.stack([g4[f"n_{k}_nx{nx}"] for k in ("modes", "white")])
+    Eb = sol.solve_poisson(torch.from_numpy(batch).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(Eb[1], sol.solve_poisson(batch[1]))
+
+
+# ----------------------------------------------------------------------------- FluxGNN.forward
+@pytest.mark.parametrize("nx,radius", [(64, 1), (64, 2), (64, 3), (1024, 1), (1024, 2), (1024, 3), (4, 3)])
+def test_forward_golden(model, nx, radius):
+    from gnn_plasma_flux_b200 import build_chain_graph
+    g1 = load_golden("g1_forward.npz")
+    state = g1[f"state_nx{nx}"]
+    x = P.Grid(nx=nx).x
+    nf, ei = build_chain_graph(state, x, "cuda", radius=radius)
+    with torch.no_grad():
+        out = model(nf, ei)
+    ref = g1[f"flux_nx{nx}_r{radius}"]
+    assert out.shape == (2 * radius * nx,) and out.dtype == torch.float32 and out.is_cuda
+    err = np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err <= STEP_TOL, err
+    # an untagged copy of the same edge_index is recognised by value
+    out2 = model(nf, ei.clone())
+    assert torch.equal(out, out2)
+
+
+def test_forward_rejects_arbitrary_graph(model):
+    with pytest.raises(NotImplementedError):
+        model(torch.randn(64, 4, device="cuda"), torch.randint(0, 64, (2, 128), device="cuda"))
+
+
+@pytest.mark.parametrize("nx,radius", [(40, 2), (100, 3), (64, 5), (7, 2), (130, 1), (300, 6), (128, 4), (8, 4)])
+def test_forward_ragged_sizes_vs_oracle(model, weights, nx, radius):
+    """Grids that exercise the generic neighbour walk, idle tile rows and window tiles."""
+    rng = np.random.RandomState(nx * 10 + radius)
+    B = 5
+    state = (rng.randn(B, 3, nx) * 0.3 + np.array([1.0, 0.0, 0.0])[None, :, None]).astype(np.float32)
+    x = P.Grid(nx=nx).x.astype(np.float32)
+    hops = min(radius, 4)
+    edges, face = model.ring_fluxes(torch.from_numpy(state).cuda(), torch.from_numpy(x).cuda(), radius=radius,
+                                    hops=hops, want_face=True)
+    ref = batched.edge_fluxes(weights, torch.from_numpy(state), torch.from_numpy(x), radius, hops=hops).numpy()
+    scale = np.abs(ref).max()
+    assert np.abs(edges.cpu().numpy() - ref).max() <= STEP_TOL * scale
+    face_ref = 0.5 * (ref[:, :nx] + ref[:, nx:2 * nx])
+    assert np.abs(face.cpu().numpy() - face_ref).max() <= STEP_TOL * scale
+
+
+# ----------------------------------------------------------------------------- HybridSolver
+def test_hybrid_step_golden_c1(model):
+    g = load_golden("g23_hybrid_c1.npz")
+    sol = make_solver(model, 64, 5e-3, radius=3)                   # radius is a label, as in the reference
+    out = sol.step(g["ics"])                                       # numpy [20,3,64] batch
+    assert out.shape == (20, 3, 64) and out.dtype == np.float32
+    assert P.rel_err(out, g["step1"]).max() <= STEP_TOL
+    one = sol.step(g["ics"][4])                                    # the reference's unbatched call
+    assert one.shape == (3, 64) and isinstance(one, np.ndarray)
+    np.testing.assert_array_equal(one, out[4])
+    # momentum update has no GNN in it: bit-exact
+    np.testing.assert_array_equal(out[:, 1], g["step1"][:, 1])
+
+
+def test_hybrid_run_golden_c1(model):
+    """BASELINE.json configs[0]: 20 ICs x 30 steps x 64 cells, dt=5e-3."""
+    g = load_golden("g23_hybrid_c1.npz")
+    sol = make_solver(model, 64, 5e-3)
+    roll = sol.run(g["ics"][0], n_steps=30)
+    assert roll.shape == (31, 3, 64) and roll.dtype == np.float32
+    np.testing.assert_array_equal(roll[0], g["ics"][0])
+    allr = sol.run(g["ics"], n_steps=30)                           # [31,20,3,64]
+    assert allr.shape == (31, 20, 3, 64)
+    np.testing.assert_array_equal(allr[:, 0], roll)
+    ref = np.moveaxis(g["rollout"], 0, 1)                          # [31,20,3,64]
+    for t in (1, 10, 30):
+        assert P.rel_err(allr[t], ref[t]).max() <= STEP_TOL * t, t
+    # step-by-step (evaluate_long_rollout.py style) equals the single persistent launch
+    s = g["ics"][0]
+    for _ in range(5):
+        s = sol.step(s)
+    np.testing.assert_array_equal(s, roll[5])
+
+
+@pytest.mark.parametrize("radius", [1, 2, 3])
+def test_hybrid_step_radius_golden(model, radius):
+    gr = load_golden("g2_hybrid_radius.npz")
+    g = load_golden("g23_hybrid_c1.npz")
+    sol = make_solver(model, 1024, 3e-4, graph_radius=radius)      # window tiles + separate field solve
+    out = sol.step(gr["ic_nx1024"])
+    assert P.rel_err(out, gr[f"step_nx1024_r{radius}"]).max() <= STEP_TOL
+    if radius > 1:
+        sol64 = make_solver(model, 64, 5e-3, graph_radius=radius)
+        out = sol64.step(g["ics"][:4])
+        assert P.rel_err(out, gr[f"step_nx64_r{radius}"]).max() <= STEP_TOL
+
+
+def test_hybrid_window_rollout_vs_oracle(model, weights):
+    """nx=1024 multi-step rollout (ping-pong workspace, trajectory copies) vs the batched oracle."""
+    grid = P.Grid(nx=1024, dt=3e-4)
+    ics = np.stack([P.stable_initial_condition(grid, s) for s in range(3)])
+    sol = make_solver(model, 1024, 3e-4, graph_radius=2)
+    final, traj = sol.rollout(torch.from_numpy(ics).cuda(), 6, record_every=2)
+    ref = batched.hybrid_run(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, 6, radius=2,
+                             record_every=2).numpy()
+    assert traj.shape == (3, 3, 3, 1024)
+    assert torch.equal(traj[-1], final)
+    for i in range(3):
+        assert P.rel_err(traj[i].cpu().numpy(), ref[i + 1]).max() <= STEP_TOL * 2 * (i + 1)
+
+
+def test_generic_path_equals_fast_path(model, monkeypatch):
+    g = load_golden("g23_hybrid_c1.npz")
+    sol = make_solver(model, 64, 5e-3, graph_radius=3)
+    fast = sol.step(g["ics"])
+    monkeypatch.setenv("FLUXGNN_FORCE_GENERIC", "1")
+    slow = sol.step(g["ics"])
+    monkeypatch.delenv("FLUXGNN_FORCE_GENERIC")
+    np.testing.assert_array_equal(fast, slow)
+
+
+def test_long_rollout_1000_steps(model):
+    """1000-step stabilised rollout vs the reference (fp32) and its fp64 restatement."""
+    g6 = load_golden("g6_long_rollout.npz")
+    sol = make_solver(model, 64, 1e-3)
+    final, traj = sol.rollout(torch.from_numpy(g6["ics"]).cuda(), 1000, record_every=100)
+    ours = np.concatenate([g6["ics"][None], traj.cpu().numpy()], 0)          # [11,4,3,64]
+    ours = np.moveaxis(ours, 0, 1)                                            # [4,11,3,64]
+    assert np.isfinite(ours).all()
+    floor = P.rel_err(g6["ref_fp32"][:, -1], g6["fp64"][:, -1])               # reference's own fp32 noise
+    vs64 = P.rel_err(ours[:, -1], g6["fp64"][:, -1])
+    vs32 = P.rel_err(ours[:, -1], g6["ref_fp32"][:, -1])
+    print("1000-step rel err: reference-vs-fp64", floor, "ours-vs-fp64", vs64, "ours-vs-reference", vs32)
+    # <= 1e-4, or within 2x of the reference's own distance from the fp64 trajectory where that is larger
+    assert (vs64 <= np.maximum(1e-4, 2.0 * floor)).all()
+    assert (vs32 <= np.maximum(1e-4, 3.0 * floor)).all()
+    # total mass conserved to round-off (flux form telescopes)
+    mass0 = g6["ics"][:, 0].astype(np.float64).sum(-1)
+    massT = ours[:, -1, 0].astype(np.float64).sum(-1)
+    assert np.abs(massT - mass0).max() <= 1000 * 64 * np.finfo(np.float32).eps
+
+
+def test_full_size_c2_properties(model, weights):
+    """BASELINE.json configs[1] shape: 4096 ICs x 64 cells, radius 3.  One step vs the batched
+    oracle on every IC, plus size-independent properties: IC-permutation equivariance,
+    translation equivariance along the periodic grid is NOT expected (x is a feature), mass conservation."""
+    nx, B = 64, 4096
+    grid = P.Grid(nx=nx, dt=1e-3)
+    base = np.stack([P.stable_initial_condition(grid, s) for s in range(64)])
+    ics = np.tile(base, (B // 64, 1, 1))
+    ics += (np.random.RandomState(0).randn(B, 1, 1) * 1e-3).astype(np.float32) * np.array([0, 1, 0], np.float32)[None, :, None]
+    sol = make_solver(model, nx, 1e-3, graph_radius=3)
+    dev = torch.from_numpy(ics).cuda()
+    out, _ = sol.rollout(dev, 1)
+    ref = batched.hybrid_step(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, radius=3).numpy()
+    assert P.rel_err(out.cpu().numpy(), ref).max() <= STEP_TOL
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+    out_p, _ = sol.rollout(dev[perm].contiguous(), 1)
+    assert torch.equal(out_p, out[perm])
+    final, _ = sol.rollout(dev, 50)
+    m0 = ics[:, 0].astype(np.float64).sum(-1)
+    mT = final[:, 0].double().sum(-1).cpu().numpy()
+    assert np.abs(mT - m0).max() <= 50 * nx * np.finfo(np.float32).eps
+
+
+# ----------------------------------------------------------------------------- BaselineSolver
+@pytest.mark.parametrize("nx", [64, 1024])
+def test_baseline_golden(built_lib, nx):
+    from gnn_plasma_flux_b200 import BaselineSolver
+    g5 = load_golden("g5_baseline.npz")
+    states, fluxes = g5[f"states_nx{nx}"], g5[f"fluxes_nx{nx}"]
+    sol = BaselineSolver(nx=nx, dt=float(g5[f"dt_nx{nx}"]), nu=1e-3)
+    new, fn = sol.step(states[0], return_flux=True)
+    np.testing.assert_array_equal(fn, fluxes[0])                   # bit-exact
+    np.testing.assert_array_equal(new[:2], states[1, :2])          # n', u' bit-exact
+    assert P.rel_err(new, states[1]).max() <= 2e-6
+    run_s, run_f = sol.run(states[0], n_steps=len(fluxes))
+    assert run_s.shape == states.shape and run_f.shape == fluxes.shape
+    np.testing.assert_array_equal(run_s[0], states[0])
+    assert P.rel_err(run_s[-1], states[-1]).max() <= STEP_TOL * len(fluxes)
+    s2, none = sol.run(states[0], n_steps=3, record_flux=False)
+    assert none is None and s2.shape == (4, 3, nx)
+
+
+def test_error_paths(model):
+    from gnn_plasma_flux_b200 import _lib
+    sol = make_solver(model, 64, 5e-3)
+    with pytest.raises(ValueError):
+        sol.rollout(torch.zeros(2, 3, 32, device="cuda"), 1)
+    st = torch.zeros(2, 3, 64, device="cuda")
+    with pytest.raises(_lib.FluxGNNError):
+        sol.rollout(st, 1, out=st)                                  # aliasing is refused by the C ABI
+    big = make_solver(model, 20000, 1e-5)
+    with pytest.raises(_lib.FluxGNNError):
+        big.rollout(torch.zeros(1, 3, 20000, device="cuda"), 1)     # field solve beyond this build's limit

@@ -1,0 +1,115 @@
+"""CPU suite: the oracle against the golden vectors frozen from the live reference
+(oracle/make_golden.py), and the internal consistency of its two restatements."""
+import numpy as np
+import torch
+
+from conftest import load_golden
+from oracle import batched, ref_port as P
+
+
+def test_weights_match_seeded_init(weights):
+    w = P.init_weights(0)
+    assert set(w) == set(weights)
+    for key in w:
+        np.testing.assert_array_equal(w[key], weights[key])
+    assert sum(v.size for v in w.values()) == 165249
+
+
+def test_ring_edges_reference_prefix():
+    for nx in (4, 64):
+        e1 = P.ring_edges(nx, 1)
+        assert e1.shape == (2, 2 * nx) and e1.dtype == np.int64
+        src = np.arange(nx)
+        np.testing.assert_array_equal(e1[0, :nx], src)
+        np.testing.assert_array_equal(e1[1, :nx], (src + 1) % nx)
+        np.testing.assert_array_equal(e1[0, nx:], (src + 1) % nx)
+        np.testing.assert_array_equal(e1[1, nx:], src)
+        e3 = P.ring_edges(nx, 3)
+        assert e3.shape == (2, 6 * nx)
+        np.testing.assert_array_equal(e3[:, :2 * nx], e1)
+
+
+def test_forward_golden(weights):
+    g1 = load_golden("g1_forward.npz")
+    for nx in (64, 1024):
+        grid = P.Grid(nx=nx)
+        feats = P.node_features(g1[f"state_nx{nx}"], grid.x)
+        for r in (1, 2, 3):
+            out = P.fluxgnn_forward(weights, feats, P.ring_edges(nx, r))
+            ref = g1[f"flux_nx{nx}_r{r}"]
+            assert out.shape == ref.shape == (2 * r * nx,)
+            # same primitives, same order; BLAS blocking may differ between thread counts
+            assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_poisson_and_ic_golden():
+    g4 = load_golden("g4_poisson_ic.npz")
+    for nx in (64, 96, 1024):
+        grid = P.Grid(nx=nx)
+        for seed in (0, 1, 123):
+            np.testing.assert_array_equal(P.initial_condition(grid, seed), g4[f"ic_nx{nx}_s{seed}"])
+        for name in ("modes", "white", "nyquist", "const"):
+            E = P.solve_poisson(g4[f"n_{name}_nx{nx}"], grid.k)
+            np.testing.assert_array_equal(E, g4[f"E_{name}_nx{nx}"])
+        assert np.abs(g4[f"E_nyquist_nx{nx}"]).max() < 1e-7      # Nyquist annihilated
+        assert np.abs(g4[f"E_const_nx{nx}"]).max() == 0.0        # k = 0 removed
+        # the circular-convolution form of the operator
+        g = P.poisson_kernel(nx, grid.length)
+        rho = (g4[f"n_white_nx{nx}"] - np.float32(1.0)).astype(np.float64)
+        conv = np.array([np.dot(g[(j - np.arange(nx)) % nx], rho) for j in range(nx)])
+        ref = g4[f"E_white_nx{nx}"]
+        assert np.abs(conv - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_hybrid_step_and_c1_rollout_golden(weights):
+    g = load_golden("g23_hybrid_c1.npz")
+    grid = P.Grid(nx=64, dt=5e-3)
+    for s in (0, 5, 19):
+        out = P.hybrid_step(weights, g["ics"][s], grid)
+        assert P.rel_err(out, g["step1"][s]).max() < 2e-6
+    roll = P.hybrid_run(weights, g["ics"][2], grid, 30)
+    assert roll.shape == (31, 3, 64) and roll.dtype == np.float32
+    assert P.rel_err(roll[-1], g["rollout"][2][-1]).max() < 1e-4
+    np.testing.assert_array_equal(roll[0], g["ics"][2])
+
+
+def test_batched_matches_port(weights):
+    g = load_golden("g23_hybrid_c1.npz")
+    grid = P.Grid(nx=64, dt=5e-3)
+    out = batched.hybrid_step(weights, torch.from_numpy(g["ics"]), grid.x, grid.k, grid.dt, grid.dx).numpy()
+    assert P.rel_err(out, g["step1"]).max() < 2e-6
+    gr = load_golden("g2_hybrid_radius.npz")
+    g1k = P.Grid(nx=1024, dt=3e-4)
+    for r in (1, 2, 3):
+        out = batched.hybrid_step(weights, torch.from_numpy(gr["ic_nx1024"]), g1k.x, g1k.k, g1k.dt, g1k.dx, radius=r).numpy()
+        assert P.rel_err(out, gr[f"step_nx1024_r{r}"]).max() < 5e-6
+    # tiny ring where hops wrap onto themselves
+    g1 = load_golden("g1_forward.npz")
+    g4x = P.Grid(nx=4)
+    fl = batched.edge_fluxes(weights, torch.from_numpy(g1["state_nx4"])[None],
+                             torch.from_numpy(g4x.x.astype(np.float32)), 3)[0].numpy()
+    assert np.abs(fl - g1["flux_nx4_r3"]).max() <= 2e-6 * np.abs(g1["flux_nx4_r3"]).max()
+
+
+def test_baseline_golden():
+    g5 = load_golden("g5_baseline.npz")
+    for nx in (64, 1024):
+        grid = P.Grid(nx=nx, dt=float(g5[f"dt_nx{nx}"]), nu=1e-3)
+        states, fluxes = g5[f"states_nx{nx}"], g5[f"fluxes_nx{nx}"]
+        ps, pf = P.baseline_run(states[0], grid, n_steps=len(fluxes))
+        np.testing.assert_array_equal(ps, states)
+        np.testing.assert_array_equal(pf, fluxes)
+        bt = batched.baseline_step(torch.from_numpy(states[:1]), grid.k, grid.dt, grid.dx, grid.nu).numpy()
+        np.testing.assert_array_equal(bt[0, :2], states[1, :2])        # n', u' bit-exact
+        assert P.rel_err(bt[0], states[1]).max() < 2e-6
+
+
+def test_long_rollout_noise_floor_golden():
+    g6 = load_golden("g6_long_rollout.npz")
+    floor = P.rel_err(g6["ref_fp32"][:, -1], g6["fp64"][:, -1])
+    assert np.isfinite(g6["ref_fp32"]).all()
+    assert floor.max() < 1e-3 and floor.min() > 1e-7           # the reference's own fp32 noise
+    # mass conservation of the reference to round-off
+    mass0 = g6["ref_fp32"][:, 0, 0].astype(np.float64).sum(-1)
+    massT = g6["ref_fp32"][:, -1, 0].astype(np.float64).sum(-1)
+    assert np.abs(massT - mass0).max() < 1000 * 64 * np.finfo(np.float32).eps
