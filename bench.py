@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- hybrid-rollout throughput of the sm_100a path (and of the CPU reference port).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], per GPU): an ensemble of 4096 initial conditions x
+64 cells, stencil radius 3, dt = 1e-3, MODEL_CONFIG weights (F=4, H=128, L=4, random
+init, seed 0), smooth random-mode synthetic ICs.  One bench "step" = one hybrid time
+step of the whole ensemble = ONE launch of the fused kernel; the K timed steps form a
+K-step rollout (each step consumes the previous step's state).  Metric:
+cell-updates/s = ICs x cells x steps / device time, summed over all GPUs (weak scaling:
+every rank owns its own 4096 ICs, no data-path collective).
+
+Timing: per-step CUDA-event pairs on the launching stream, an L2 flush (256 MiB write)
+between steps outside the pairs, barrier + synchronize on both sides of the K steps,
+max over ranks.  `e2e` runs the same K steps through HybridSolver.step_pinned(), i.e.
+pinned host state -> H2D -> fused step -> D2H every step.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, all host
+threads) on a bounded sample of the same workload and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hybrid_rollout_cell_updates_per_sec"
+UNIT = "cell-updates/s"
+ICS, NX, RADIUS, DT = 4096, 64, 3, 1e-3
+FLOP_PER_CELL_EXECUTED = 329_216      # split edge MLP; what the kernel executes
+FLOP_PER_CELL_REFERENCE = 394_752     # as the reference computes it
+BYTES_PER_CELL = 24                   # read n,u,E + write n',u',E'
+WORKLOAD = f"C2 ensemble rollout: {ICS} ICs x {NX} cells per GPU, radius {RADIUS}, dt={DT:g}, H=128 L=4"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_ics(n_ics: int, first_seed: int) -> np.ndarray:
+    from oracle import ref_port as P          # input generator only (the reference's IC family, stabilised)
+    grid = P.Grid(nx=NX, dt=DT)
+    base = np.stack([P.stable_initial_condition(grid, first_seed + s) for s in range(min(n_ics, 256))])
+    reps = (n_ics + len(base) - 1) // len(base)
+    ics = np.tile(base, (reps, 1, 1))[:n_ics].copy()
+    # make every IC distinct: a small per-IC velocity offset (E stays consistent with n)
+    off = np.random.RandomState(first_seed).uniform(-1e-2, 1e-2, size=(n_ics, 1)).astype(np.float32)
+    ics[:, 1] += off
+    return ics
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU reference port
+def cpu_reference_rate(n_ics: int, steps: int, warmup: int):
+    """cell-updates/s of the batched CPU port (all host threads) on n_ics ICs."""
+    from oracle import batched, ref_port as P
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = P.init_weights(0)
+    grid = P.Grid(nx=NX, dt=DT)
+    state = torch.from_numpy(make_ics(n_ics, 0))
+    for _ in range(warmup):
+        state = batched.hybrid_step(w, state, grid.x, grid.k, grid.dt, grid.dx, radius=RADIUS)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        state = batched.hybrid_step(w, state, grid.x, grid.k, grid.dt, grid.dx, radius=RADIUS)
+    dt = time.perf_counter() - t0
+    assert torch.isfinite(state).all()
+    return n_ics * NX * steps / dt, dt
+
+
+def cpu_unbatched_rate(n_ics: int, steps: int):
+    """cell-updates/s of the faithful one-IC-at-a-time port (the reference's own loop structure)."""
+    from oracle import ref_port as P
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = P.init_weights(0)
+    grid = P.Grid(nx=NX, dt=DT)
+    ics = make_ics(n_ics, 0)
+    t0 = time.perf_counter()
+    for ic in ics:
+        s = ic
+        for _ in range(steps):
+            s = P.hybrid_step(w, s, grid, radius=RADIUS)
+    return n_ics * NX * steps / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    sample_ics = 512
+    rate, secs = cpu_reference_rate(sample_ics, args.steps, max(args.warmup, 1))
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample_ics} of {ICS} ICs per step"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"batched CPU port (oracle/batched.py, torch {torch.__version__}, {cores} threads), "
+                                   f"{sample_ics} ICs x {NX} cells x {args.steps} steps"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- sm_100a path
+def run_ours(args):
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gnn_plasma_flux_b200 import FluxGNN, HybridSolver, MODEL_CONFIG, _lib
+    from oracle import ref_port as P          # weights initialiser + IC generator (inputs only)
+
+    weights = P.init_weights(0)
+    model = FluxGNN(**MODEL_CONFIG)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    solver = HybridSolver(None, RADIUS, nx=NX, dt=DT, device=dev, graph_radius=RADIUS, model=model.to(dev))
+    ics = make_ics(ICS, 1000 * rank)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    a = torch.from_numpy(ics).to(dev)
+    b = torch.empty_like(a)
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- device-resident K-step rollout, one launch per step --------------------------
+    for _ in range(W):
+        solver.rollout(a, 1, out=b)
+        a, b = b, a
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clocks:
+        wall0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()                                   # L2 flush, outside the timed pair
+            starts[i].record(stream)
+            solver.rollout(a, 1, out=b)
+            stops[i].record(stream)
+            a, b = b, a
+        barrier()
+        wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    assert torch.isfinite(a).all(), "rollout went non-finite"
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * ICS * NX * K / (dev_ms * 1e-3)
+
+    # ---- end to end: pinned host state in, pinned host state out, every step ---------------
+    h_in = torch.from_numpy(ics).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    for _ in range(max(W, 1)):
+        solver.step_pinned(h_in, h_out)
+        h_in, h_out = h_out, h_in
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        solver.step_pinned(h_in, h_out)
+        h_in, h_out = h_out, h_in
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * ICS * NX * K / float(t.item())
+    state_bytes = ICS * 3 * NX * 4
+
+    line = None
+    if rank == 0:
+        # ---- FP32-pipe roofline of this device, measured live ------------------------------
+        sink = torch.empty(148 * 8 * 256, dtype=torch.float32, device=dev)
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            flops = _lib.lib().fluxgnn_ffma_probe(sink.data_ptr(), 148 * 8, 20000, stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_gpu = ICS * NX * K / (dev_ms * 1e-3)
+        achieved_tf = per_gpu * FLOP_PER_CELL_EXECUTED / 1e12
+        roofline = {
+            "bound": "fp32-ffma", "kernel": "hybrid_tile_kernel<3>",
+            "achieved": achieved_tf, "peak": best, "unit": "TFLOP/s", "frac": achieved_tf / best if best else None,
+            "peak_source": "FFMA probe kernel timed in this run (fluxgnn_ffma_probe); nominal 148x128x2x1.965 GHz = 74.5",
+            "flop_per_cell": FLOP_PER_CELL_EXECUTED,
+            "achieved_reference_flop_count": per_gpu * FLOP_PER_CELL_REFERENCE / 1e12,
+            "traffic": None,
+            "hbm": {"achieved": per_gpu * BYTES_PER_CELL / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": per_gpu * BYTES_PER_CELL / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+                    "note": "the hybrid step is FP32-compute bound (16 kFLOP/B); HBM is not the binding roof"},
+            "avg_launch_ms": dev_ms / K,
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, secs = cpu_reference_rate(512, 12, 2)
+            unb = cpu_unbatched_rate(4, 100)
+            cpu = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"batched CPU port, 512 of {ICS} ICs x {NX} cells x 12 steps ({secs:.1f} s); "
+                             f"the reference's own one-IC-at-a-time loop (oracle/ref_port.py, 4 ICs x 100 steps) "
+                             f"reaches {unb:.3e} {UNIT}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB write) between timed steps",
+                       "launches_per_step": launches / K, "wall_s_incl_flush": wall},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
+                    "d2h_bytes_per_step": state_bytes},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,6 +90,24 @@ __global__ void __launch_bounds__(256) baseline_fv_kernel(const float* __restric
     }
 }
 
+// FP32 pipe probe: 16 independent FFMA chains per thread, register operands only.
+// Used by bench.py to measure the FFMA roofline of the box it runs on.
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ out, int iters, float a, float b) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // packed small block + (L+1) x 2 K-major halves (see common.cuh)
 __global__ void pack_weights_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
                                     const float* __restrict__ w_upd, const float* __restrict__ b_upd,
