@@ -109,9 +109,12 @@ const char* fluxgnn_last_error(void) { return g_err; }
 
 unsigned long long fluxgnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-long long fluxgnn_ffma_probe(float* out, int blocks, int iters, void* stream) {
+long long fluxgnn_ffma_probe(float* out, int blocks, int iters, int packed, void* stream) {
     if (out == nullptr || blocks < 1 || iters < 1) return set_error(FLUXGNN_EINVAL, "ffma_probe: bad argument");
-    ffma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
+    if (packed)
+        ffma2_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
+    else
+        ffma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
     FLUXGNN_CUDA_OK(cudaGetLastError());
     count_launch();
     return (long long)blocks * 256 * iters * kFfmaProbeFlopsPerIter;

@@ -20,12 +20,17 @@ constexpr int kMaxHops = FLUXGNN_MAX_HOPS;
 // K-major halves (src/flux_gnn.py:60,66 multiply [h, other] by W^T):
 //   half 0 = the half applied to the neighbour mean / to h_col   (W[:, H:])
 //   half 1 = the half applied to the node itself   / to h_row   (W[:, :H])
-// each stored as Wt[k][n] = W[n][half_off + k], i.e. 128 rows of 128 floats,
-// cut into 8 chunks of 16 rows (8 KiB) -- the unit of one bulk copy.
+// each stored as Wt[k][q] = W[weight_column(q)][half_off + k], i.e. 128 rows of
+// 128 floats with the columns permuted for the GEMM's register tile, cut into
+// chunks of kChunkK rows -- the unit of one bulk copy.
 // ---------------------------------------------------------------------------
-constexpr int kChunkK = 16;                       // k-rows per streamed chunk
-constexpr int kChunkFloats = kChunkK * kH;        // 2048 floats = 8 KiB
-constexpr int kChunksPerHalf = kH / kChunkK;      // 8
+#ifndef FLUXGNN_CHUNK_K
+#define FLUXGNN_CHUNK_K 32
+#endif
+constexpr int kChunkK = FLUXGNN_CHUNK_K;          // k-rows per streamed chunk (multiple of 8)
+constexpr int kChunkFloats = kChunkK * kH;        // 32 x 128 floats = 16 KiB
+constexpr int kChunksPerHalf = kH / kChunkK;      // 4
+static_assert(kChunkK % 8 == 0 && kH % kChunkK == 0, "chunk must tile K and keep the swizzle phase");
 constexpr int kHalfFloats = kH * kH;              // 16384
 constexpr int kLayerFloats = 2 * kHalfFloats;     // 32768
 
@@ -39,6 +44,14 @@ struct SmallParams {            // offsets (floats) inside the small block
     static constexpr int count = b_e2 + kH;                 // padded to a multiple of 128 floats
 };
 static_assert(SmallParams::count % 128 == 0, "stream must start 512-byte aligned");
+
+// Logical output feature stored at physical column q of a streamed weight row:
+// thread tx of the GEMM reads physical columns 4tx..4tx+3 and 64+4tx..64+4tx+3 and
+// owns the features tx + 16 j, j = 0..7 (see col_of() in hybrid_kernel_impl.cuh).
+__host__ __device__ inline int weight_column(int q) {
+    const int half = q >> 6, r = q & 63;
+    return (r >> 2) + 16 * ((r & 3) + 4 * half);
+}
 
 __host__ __device__ inline size_t packed_floats(int L) {
     return (size_t)SmallParams::count + (size_t)(L + 1) * kLayerFloats;

@@ -108,6 +108,24 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ out
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Same probe with packed fma.rn.f32x2 (SASS FFMA2): 8 independent float2 chains.
+__global__ void __launch_bounds__(256) ffma2_probe_kernel(float* __restrict__ out, int iters, float a, float b) {
+    float2 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = make_float2((float)(threadIdx.x + i), (float)(threadIdx.x - i));
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = __ffma2_rn(acc[i], a2, b2);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i].x + acc[i].y;
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // packed small block + (L+1) x 2 K-major halves (see common.cuh)
 __global__ void pack_weights_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
                                     const float* __restrict__ w_upd, const float* __restrict__ b_upd,
@@ -141,7 +159,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_in, const float*
             const int r = (int)(q % kLayerFloats);
             const int half = r / kHalfFloats;                  // 0: W[:, H:], 1: W[:, :H]
             const int k = (r % kHalfFloats) / kH;
-            const int n = r % kH;
+            const int n = weight_column(r % kH);
             const float* W = (layer < L) ? (w_upd + (size_t)layer * kH * 2 * kH) : w_e1;
             v = W[(size_t)n * 2 * kH + (half == 0 ? kH : 0) + k];
         }

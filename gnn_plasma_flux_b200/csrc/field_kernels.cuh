@@ -15,6 +15,7 @@ __global__ void pack_weights_kernel(const float* w_in, const float* b_in, const 
                                     int L, float* packed);
 
 __global__ void ffma_probe_kernel(float* out, int iters, float a, float b);
+__global__ void ffma2_probe_kernel(float* out, int iters, float a, float b);
 constexpr int kFfmaProbeFlopsPerIter = 2 * 8 * 16;   // per thread per iteration
 
 constexpr int kPoissonDirectMaxNx = 12288;   // rho staged in 48 KiB of shared memory

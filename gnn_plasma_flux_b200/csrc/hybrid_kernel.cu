@@ -1,479 +1,12 @@
-// Fused hybrid step for sm_100a: FluxGNN on the periodic chain + finite-volume
-// update + (for grids that fit one tile) the spectral field solve, all inside
-// one persistent kernel with the activations resident in shared memory.
-//
-// What it replaces (paths under /root/reference):
-//   src/graph_constructor.py:30-38   node features / ring edges  -> implicit
-//   src/flux_gnn.py:49               input MLP                   -> input_layer()
-//   src/flux_gnn.py:53-60            gather + index_add_ + mean + Linear + ReLU
-//                                    -> two K=128 GEMM passes + window epilogue
-//   src/flux_gnn.py:63-66            edge readout                -> split-W GEMM + edge epilogue
-//   src/hybrid_solver.py:45-58       face flux, continuity and momentum update
-//   src/baseline_solver.py:59-68     field solve (whole-IC tiles only)
-//
-// Algebra.  With W = [Wa | Wb] ([H][2H], nn.Linear layout) the reference's
-//   h' = relu(W [h ; mean_nbr(h)] + b)
-// is evaluated as  Y = Wa h,  Z = Wb h,  h'_i = relu(Y_i + mean_nbr(Z)_i + b)
-// (the mean is linear, so it commutes with Wb).  Every layer, and the edge
-// readout P = W1a h, Q = W1b h, is therefore the same [128 rows] x [K=128] x
-// [N=256] product, done as two N=128 passes:
-//   pass 0 -> Z (or Q) written to shared memory,
-//   pass 1 -> Y (or P) kept in registers, combined with a +-r row window of Z.
-//
-// Tile = 128 rows (cells).  "Whole-IC" tiles hold floor(128/nx) complete ICs
-// and wrap neighbours periodically inside each IC; "window" tiles (nx > 128)
-// carry a halo of L*r+hops recomputed cells per side.  Activations live
-// feature-major ([feature][row], row chunks XOR-swizzled) so that both the
-// register-tile loads of the GEMM and the row-window reads are 128-bit and
-// bank-conflict free.  Weights stream L2 -> shared memory in 8 KiB chunks with
-// cp.async.bulk (TMA, SASS UBLKCP) issued by a producer warp through a 4-stage
-// mbarrier ring; 8 consumer warps run an 8x8 register-tile FFMA kernel.
+// Radius dispatch of the fused hybrid tile kernel; the kernel itself is in
+// hybrid_kernel_impl.cuh and is instantiated once per radius in hybrid_r*.cu.
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
 
 namespace fluxgnn {
 
-namespace {
-
-constexpr int kStages = 4;
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumers = kConsumerWarps * 32;   // 256
-constexpr int kThreads = kConsumers + 32;         // + producer warp
-
-struct __align__(128) TileSmem {
-    float Hs[kH * kTileRows];            // activations h   [feature][row], swizzled
-    float Zs[kH * kTileRows];            // neighbour half  [feature][row], swizzled
-    float Ws[kStages][kChunkFloats];     // streamed weight chunks [16 k][128 n]
-    float small[SmallParams::count];
-    float sN[kTileRows], sU[kTileRows], sE[kTileRows], sX[kTileRows];
-    float sF[kTileRows], sRho[kTileRows];
-    float edge[2][2][kMaxHops][kTileRows];   // [column half][fwd/bwd][hop][row] partial dot products
-    double gtab[kTileRows];
-    int rowIC[kTileRows];                // owning IC of the row's output, -1 = not owned
-    int rowCell[kTileRows];
-    short prevRow[kTileRows], nextRow[kTileRows];
-    uint64_t full[kStages], empty[kStages];
-};
-static_assert(sizeof(TileSmem) <= 227 * 1024, "tile does not fit shared memory");
-
-struct Pipe {
-    int stage = 0;
-    uint32_t phase = 0;
-    __device__ __forceinline__ void advance() {
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-    }
-};
-
-// physical float offset of (feature n, row) in Hs / Zs
-__device__ __forceinline__ int sw_off(int n, int row) {
-    return n * kTileRows + ((((row >> 2) ^ ((n >> 2) & 7)) << 2) | (row & 3));
-}
-
-__device__ __forceinline__ int col_of(int tx, int j) {   // the thread's j-th output feature
-    return (j < 4) ? (tx * 4 + j) : (64 + tx * 4 + (j - 4));
-}
-
-// acc[i][j] += sum_k Hs[k][R0+i] * Wt[k][col_j]  over one K=128 half (8 streamed chunks)
-__device__ __forceinline__ void gemm_pass(float (&acc)[8][8], TileSmem& S, Pipe& pipe,
-                                          int ty, int tx, int lane) {
-    const int c0 = ty * 2, c1 = ty * 2 + 1;
-#pragma unroll 1
-    for (int kc = 0; kc < kChunksPerHalf; ++kc) {
-        mbar_wait(&S.full[pipe.stage], pipe.phase);
-        const float* __restrict__ wst = S.Ws[pipe.stage];
-        const float* __restrict__ hk = S.Hs + kc * kChunkK * kTileRows;
-#pragma unroll
-        for (int kk = 0; kk < kChunkK; ++kk) {
-            const int sw = ((kc * kChunkK + kk) >> 2) & 7;
-            const float4 a0 = *reinterpret_cast<const float4*>(hk + kk * kTileRows + ((c0 ^ sw) << 2));
-            const float4 a1 = *reinterpret_cast<const float4*>(hk + kk * kTileRows + ((c1 ^ sw) << 2));
-            const float4 b0 = *reinterpret_cast<const float4*>(wst + kk * kH + tx * 4);
-            const float4 b1 = *reinterpret_cast<const float4*>(wst + kk * kH + 64 + tx * 4);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[pipe.stage]);
-        pipe.advance();
-    }
-}
-
-// 16-row window Z[n][R0-4 .. R0+11] (periodic inside the segment) of feature n
-__device__ __forceinline__ void load_window(float (&v)[16], const float* zrow, int sw,
-                                            int cl, int c0, int c1, int cr) {
-    const float4 l = *reinterpret_cast<const float4*>(zrow + ((cl ^ sw) << 2));
-    const float4 m0 = *reinterpret_cast<const float4*>(zrow + ((c0 ^ sw) << 2));
-    const float4 m1 = *reinterpret_cast<const float4*>(zrow + ((c1 ^ sw) << 2));
-    const float4 r = *reinterpret_cast<const float4*>(zrow + ((cr ^ sw) << 2));
-    v[0] = l.x;  v[1] = l.y;  v[2] = l.z;  v[3] = l.w;
-    v[4] = m0.x; v[5] = m0.y; v[6] = m0.z; v[7] = m0.w;
-    v[8] = m1.x; v[9] = m1.y; v[10] = m1.z; v[11] = m1.w;
-    v[12] = r.x; v[13] = r.y; v[14] = r.z; v[15] = r.w;
-}
-
-}  // namespace
-
-// R = 1..4: radius known at compile time, 8-row groups never straddle an IC
-//           (nx % 8 == 0 or window tiles) -> 128-bit window reads.
-// R = 0   : any radius / any nx, neighbours found by walking prev/next tables.
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nx = a.nx;
-
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&S.full[s], 1);
-            mbar_init(&S.empty[s], kConsumerWarps);
-        }
-        mbar_fence_init();
-    }
-    for (int i = tid; i < SmallParams::count; i += kThreads) S.small[i] = a.packed[i];
-    if (a.whole_ic && a.do_update)
-        for (int i = tid; i < nx; i += kThreads) S.gtab[i] = a.gtab[i];
-    __syncthreads();
-
-    const int my_tiles = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int chunks_per_step = (a.L + 1) * 2 * kChunksPerHalf;
-
-    if (warp == kConsumerWarps) {
-        // ---------------- producer warp: stream the weights, forever in order ----------
-        if (lane == 0) {
-            const float* stream = a.packed + SmallParams::count;
-            const long long total = (long long)my_tiles * a.steps * chunks_per_step;
-            Pipe p;
-            int c = 0;
-            for (long long i = 0; i < total; ++i) {
-                mbar_wait(&S.empty[p.stage], p.phase ^ 1);
-                mbar_arrive_expect_tx(&S.full[p.stage], kChunkFloats * 4);
-                bulk_g2s(S.Ws[p.stage], stream + (size_t)c * kChunkFloats, kChunkFloats * 4, &S.full[p.stage]);
-                if (++c == chunks_per_step) c = 0;
-                p.advance();
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumer warps --------------------------------------------------
-    const int ty = (warp >> 1) * 4 + (lane >> 3);   // 0..15 : rows R0..R0+7
-    const int tx = (warp & 1) * 8 + (lane & 7);     // 0..15 : columns col_of(tx, 0..7)
-    const int R0 = ty * 8;
-    const int sw = tx & 7;                          // swizzle key of all 8 of the thread's features
-    const int c0 = ty * 2, c1 = ty * 2 + 1;
-    const int radius = (R > 0) ? R : a.radius;
-    const float inv_deg = 1.0f / (float)(2 * radius);
-    int cl = 0, cr = 0;                             // chunk indices of the wrapped window ends
-    if (R > 0) {
-        const int seg = a.whole_ic ? nx : kTileRows;
-        const int seg_start = (R0 / seg) * seg;
-        int left = R0 - 4, right = R0 + 8;
-        if (R0 == seg_start) left += seg;
-        if (right == seg_start + seg) right -= seg;
-        cl = (left & (kTileRows - 1)) >> 2;
-        cr = (right & (kTileRows - 1)) >> 2;
-    }
-    const int used_rows = a.whole_ic ? a.ics_per_tile * nx : kTileRows;
-    Pipe pipe;
-
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        // ---- row bookkeeping + state load -----------------------------------------
-        if (tid < kTileRows) {
-            const int j = tid;
-            int ic, cell, prev = (j - 1) & (kTileRows - 1), next = (j + 1) & (kTileRows - 1);
-            bool live, owned;
-            if (a.whole_ic) {
-                const int slot = j / nx;
-                cell = j - slot * nx;
-                ic = tile * a.ics_per_tile + slot;
-                live = (slot < a.ics_per_tile) && (ic < a.B);
-                owned = live;
-                if (slot < a.ics_per_tile) {
-                    prev = (cell == 0) ? j + nx - 1 : j - 1;
-                    next = (cell == nx - 1) ? j - nx + 1 : j + 1;
-                }
-            } else {
-                ic = tile / a.tiles_per_ic;
-                const int t = tile - ic * a.tiles_per_ic;
-                const long long gcell = (long long)t * a.valid - a.halo + j;
-                cell = (int)(((gcell % nx) + nx) % nx);
-                live = true;
-                owned = (j >= a.halo) && (j < a.halo + a.valid) && ((long long)t * a.valid + (j - a.halo) < nx);
-            }
-            S.rowIC[j] = owned ? ic : -1;
-            S.rowCell[j] = cell;
-            S.prevRow[j] = (short)prev;
-            S.nextRow[j] = (short)next;
-            float vn = 0.f, vu = 0.f, ve = 0.f, vx = 0.f;
-            if (live) {
-                const float* st = a.state_in + (size_t)ic * 3 * nx + cell;
-                vn = __ldg(st);
-                vu = __ldg(st + nx);
-                ve = __ldg(st + 2 * (size_t)nx);
-                vx = __ldg(a.x + cell);
-            }
-            S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
-        }
-        named_sync(1, kConsumers);
-
-        for (int step = 0; step < a.steps; ++step) {
-            float acc[8][8];
-
-            // ---- input MLP: h0 = relu(W_in [n,u,E,x] + b_in)  (src/flux_gnn.py:49) ----
-            {
-                float fn[8], fu[8], fe[8], fx[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    fn[i] = S.sN[R0 + i]; fu[i] = S.sU[R0 + i]; fe[i] = S.sE[R0 + i]; fx[i] = S.sX[R0 + i];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = col_of(tx, j);
-                    const float w0 = S.small[SmallParams::w_in + 0 * kH + n];
-                    const float w1 = S.small[SmallParams::w_in + 1 * kH + n];
-                    const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
-                    const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
-                    const float b = S.small[SmallParams::b_in + n];
-                    float h[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float v = fmaf(w0, fn[i], b);
-                        v = fmaf(w1, fu[i], v);
-                        v = fmaf(w2, fe[i], v);
-                        v = fmaf(w3, fx[i], v);
-                        h[i] = fmaxf(v, 0.f);
-                    }
-                    float* hr = S.Hs + n * kTileRows;
-                    *reinterpret_cast<float4*>(hr + ((c0 ^ sw) << 2)) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
-                }
-            }
-            named_sync(1, kConsumers);
-
-            for (int layer = 0; layer <= a.L; ++layer) {
-                // ---- pass 0: Z = W[:, H:] h  -> shared memory --------------------------
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-                gemm_pass(acc, S, pipe, ty, tx, lane);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float* zr = S.Zs + col_of(tx, j) * kTileRows;
-                    *reinterpret_cast<float4*>(zr + ((c0 ^ sw) << 2)) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
-                    *reinterpret_cast<float4*>(zr + ((c1 ^ sw) << 2)) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
-                }
-                // ---- pass 1: Y = W[:, :H] h + b  -> registers ---------------------------
-                {
-                    const float* bias = S.small + (layer < a.L ? SmallParams::b_upd + layer * kH : SmallParams::b_e1);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float b = bias[col_of(tx, j)];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i][j] = b;
-                    }
-                }
-                gemm_pass(acc, S, pipe, ty, tx, lane);
-                named_sync(1, kConsumers);      // Z complete; nobody reads Hs any more
-
-                if (layer < a.L) {
-                    // ---- node update: h' = relu(Y + mean_{|k|<=r, k!=0} Z_{i+k})  (src/flux_gnn.py:55-60)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int n = col_of(tx, j);
-                        const float* zr = S.Zs + n * kTileRows;
-                        float h[8];
-                        if (R > 0) {
-                            float v[16];
-                            load_window(v, zr, sw, cl, c0, c1, cr);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int c = 4 + i;
-                                float s = v[c + 1] + v[c - 1];
-#pragma unroll
-                                for (int k = 2; k <= R; ++k) { s += v[c + k]; s += v[c - k]; }
-                                h[i] = fmaxf(fmaf(s, inv_deg, acc[i][j]), 0.f);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                int rp = R0 + i, rm = R0 + i;
-                                float s = 0.f;
-                                for (int k = 0; k < radius; ++k) {
-                                    rp = S.nextRow[rp]; rm = S.prevRow[rm];
-                                    s += S.Zs[sw_off(n, rp)];
-                                    s += S.Zs[sw_off(n, rm)];
-                                }
-                                h[i] = fmaxf(fmaf(s, inv_deg, acc[i][j]), 0.f);
-                            }
-                        }
-                        float* hr = S.Hs + n * kTileRows;
-                        *reinterpret_cast<float4*>(hr + ((c0 ^ sw) << 2)) = make_float4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
-                    }
-                    named_sync(1, kConsumers);  // h' complete; Z free
-                } else {
-                    // ---- edge readout (src/flux_gnn.py:63-66): acc = P + b1, Zs = Q ---------
-                    //   fwd edge (row j, col j+k):  w2 . relu(P_j + Q_{j+k})
-                    //   bwd edge (row j, col j-k):  w2 . relu(P_j + Q_{j-k})   (edge index j-k)
-#pragma unroll
-                    for (int hop = 1; hop <= kMaxHops; ++hop) {
-                        if (hop <= a.hops) {
-                            float pf[8], pb[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) { pf[i] = 0.f; pb[i] = 0.f; }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int n = col_of(tx, j);
-                                const float w2 = S.small[SmallParams::w_e2 + n];
-                                const float* zr = S.Zs + n * kTileRows;
-                                if (R > 0) {
-                                    float v[16];
-                                    load_window(v, zr, sw, cl, c0, c1, cr);
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        pf[i] = fmaf(w2, fmaxf(acc[i][j] + v[4 + i + hop], 0.f), pf[i]);
-                                        pb[i] = fmaf(w2, fmaxf(acc[i][j] + v[4 + i - hop], 0.f), pb[i]);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        int rp = R0 + i, rm = R0 + i;
-                                        for (int k = 0; k < hop; ++k) { rp = S.nextRow[rp]; rm = S.prevRow[rm]; }
-                                        pf[i] = fmaf(w2, fmaxf(acc[i][j] + S.Zs[sw_off(n, rp)], 0.f), pf[i]);
-                                        pb[i] = fmaf(w2, fmaxf(acc[i][j] + S.Zs[sw_off(n, rm)], 0.f), pb[i]);
-                                    }
-                                }
-                            }
-                            // reduce over the 8 lanes that share these rows (lane bits 0..2)
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                                for (int m = 1; m <= 4; m <<= 1) {
-                                    pf[i] += __shfl_xor_sync(0xffffffffu, pf[i], m);
-                                    pb[i] += __shfl_xor_sync(0xffffffffu, pb[i], m);
-                                }
-                            }
-                            if ((lane & 7) == 0) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    S.edge[warp & 1][0][hop - 1][R0 + i] = pf[i];
-                                    S.edge[warp & 1][1][hop - 1][R0 + i] = pb[i];
-                                }
-                            }
-                        }
-                    }
-                    named_sync(1, kConsumers);
-                }
-            }   // layers
-
-            // ---- per-row: directed-edge fluxes, face flux (src/hybrid_solver.py:45-48) ----
-            float n_new = 0.f, u_new = 0.f;
-            if (tid < kTileRows) {
-                const int j = tid;
-                const float b2 = S.small[SmallParams::b_e2];
-                const int ic = S.rowIC[j], cell = S.rowCell[j];
-                float face = 0.f;
-                int jn = j;
-                for (int hop = 1; hop <= a.hops; ++hop) {
-                    jn = S.nextRow[jn];
-                    const float fwd = (S.edge[0][0][hop - 1][j] + S.edge[1][0][hop - 1][j]) + b2;
-                    const float bwd = (S.edge[0][1][hop - 1][jn] + S.edge[1][1][hop - 1][jn]) + b2;
-                    if (hop == 1) face = 0.5f * (fwd + bwd);
-                    if (a.flux_edges != nullptr && ic >= 0) {
-                        float* fe = a.flux_edges + (size_t)ic * 2 * a.hops * nx + (size_t)(2 * (hop - 1)) * nx + cell;
-                        fe[0] = fwd;
-                        fe[nx] = bwd;
-                    }
-                }
-                if (a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
-                S.sF[j] = face;
-            }
-            if (!a.do_update) continue;          // forward only (steps == 1)
-            named_sync(1, kConsumers);
-
-            // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
-            if (tid < kTileRows) {
-                const int j = tid, p = S.prevRow[j];
-                const float u = S.sU[j], up = S.sU[p];
-                n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
-                const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
-                const float fup = __fmul_rn(__fmul_rn(0.5f, up), up);
-                const float u_adv = __fsub_rn(u, __fmul_rn(a.c, __fsub_rn(fu, fup)));
-                u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, S.sE[j]));
-            }
-            if (!a.whole_ic) {
-                // window tiles: E' comes from the separate field-solve kernel
-                if (tid < kTileRows && S.rowIC[tid] >= 0) {
-                    float* so = a.state_out + (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
-                    so[0] = n_new;
-                    so[nx] = u_new;
-                }
-                continue;
-            }
-            named_sync(1, kConsumers);           // everyone has read the old n, u
-            if (tid < kTileRows) {
-                S.sN[tid] = n_new;
-                S.sU[tid] = u_new;
-                S.sRho[tid] = __fsub_rn(n_new, 1.0f);          // rho = n - n0  (src/baseline_solver.py:60)
-            }
-            named_sync(1, kConsumers);
-            // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
-            {
-                const int row = tid >> 1, half = tid & 1;
-                double e = 0.0;
-                if (row < used_rows) {
-                    const int cell = S.rowCell[row], base = row - cell;
-                    for (int i = half; i < nx; i += 2) {
-                        int d = cell - i;
-                        if (d < 0) d += nx;
-                        e = fma(S.gtab[d], (double)S.sRho[base + i], e);
-                    }
-                }
-                e += __shfl_xor_sync(0xffffffffu, e, 1);
-                if (half == 0) S.sE[row] = (float)e;
-            }
-            named_sync(1, kConsumers);
-            // ---- write-out: last step and recorded steps ---------------------------------
-            if (tid < kTileRows && S.rowIC[tid] >= 0) {
-                const size_t off = (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
-                if (step == a.steps - 1) {
-                    a.state_out[off] = S.sN[tid];
-                    a.state_out[off + nx] = S.sU[tid];
-                    a.state_out[off + 2 * (size_t)nx] = S.sE[tid];
-                }
-                if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
-                    float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
-                    tr[0] = S.sN[tid];
-                    tr[nx] = S.sU[tid];
-                    tr[2 * (size_t)nx] = S.sE[tid];
-                }
-            }
-        }   // steps
-        named_sync(1, kConsumers);   // state arrays are rewritten by the next tile's load
-    }       // tiles
-}
-
-// ---------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------
-size_t hybrid_tile_smem_bytes() { return sizeof(TileSmem); }
-
-template <int R>
-static cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream) {
-    // per device and per function; cheap and idempotent, so set it on every launch
-    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(TileSmem));
-    if (e != cudaSuccess) return e;
-    hybrid_tile_kernel<R><<<grid, kThreads, sizeof(TileSmem), stream>>>(a);
-    return cudaGetLastError();
-}
+cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream);
 
 cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream) {
     switch (fast_radius) {

@@ -27,8 +27,6 @@ struct HybridArgs {
     float c, dt;               // float32(dt/dx), float32(dt)
 };
 
-size_t hybrid_tile_smem_bytes();
-
 // fast_radius 1..4 selects the compile-time-radius window path; 0 the generic path.
 cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream);
 

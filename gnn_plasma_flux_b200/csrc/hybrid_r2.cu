@@ -1,0 +1,6 @@
+// hybrid_tile_kernel<2>: compile-time stencil radius 2
+#include "hybrid_kernel_impl.cuh"
+
+namespace fluxgnn {
+template cudaError_t launch_one<2>(const HybridArgs&, int, cudaStream_t);
+}

@@ -43,11 +43,14 @@ def test_pack_weights_layout(model, weights):
     np.testing.assert_array_equal(packed[13 * H:14 * H], weights["edge_mlp.0.bias"])
     np.testing.assert_array_equal(packed[14 * H:15 * H], weights["edge_mlp.2.weight"][0])
     assert packed[15 * H] == weights["edge_mlp.2.bias"][0]
-    stream = packed[small:].reshape(5, 2, H, H)                   # [layer][half][k][n]
+    stream = packed[small:].reshape(5, 2, H, H)                   # [layer][half][k][physical column q]
+    q = np.arange(H)
+    col = ((q & 63) >> 2) + 16 * ((q & 3) + 4 * (q >> 6))         # weight_column(q), csrc/common.cuh
+    assert sorted(col) == list(range(H))
     for l in range(5):
         W = weights[f"update_mlps.{l}.0.weight"] if l < 4 else weights["edge_mlp.0.weight"]
-        np.testing.assert_array_equal(stream[l, 0], W[:, H:].T)   # neighbour / col half
-        np.testing.assert_array_equal(stream[l, 1], W[:, :H].T)   # self / row half
+        np.testing.assert_array_equal(stream[l, 0], W[col, H:].T)   # neighbour / col half
+        np.testing.assert_array_equal(stream[l, 1], W[col, :H].T)   # self / row half
 
 
 # ----------------------------------------------------------------------------- field solve
