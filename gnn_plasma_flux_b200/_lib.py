@@ -27,13 +27,17 @@ SIGNATURES = {
     "fluxgnn_packed_weight_bytes": (c_size_t, [c_int]),
     "fluxgnn_pack_weights": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
     "fluxgnn_poisson_table": (c_int, [c_int, c_double, c_void_p, c_void_p]),
-    "fluxgnn_poisson_spectral": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p]),
+    "fluxgnn_poisson_uses_table": (c_int, [c_int]),
+    "fluxgnn_poisson_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_poisson_spectral": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_int, c_int, c_double,
+                                         c_void_p, c_void_p]),
     "fluxgnn_forward_ring": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p]),
     "fluxgnn_hybrid_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "fluxgnn_hybrid_rollout": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                       c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float,
+    "fluxgnn_hybrid_rollout": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double,
+                                       c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_baseline_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float,
                                          c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

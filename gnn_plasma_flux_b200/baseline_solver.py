@@ -95,10 +95,13 @@ class BaselineSolver:
         _, gtab = self.grid.tables(self.device)
         with torch.cuda.device(self.device):
             out = torch.empty_like(t)
+            ws_bytes = _lib.lib().fluxgnn_poisson_workspace_bytes(t.shape[0], self.nx)
+            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=self.device) if ws_bytes else None
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(_lib.lib().fluxgnn_poisson_spectral(t.data_ptr(), self.nx, out.data_ptr(), self.nx,
-                                                           gtab.data_ptr(), t.shape[0], self.nx, stream),
-                       "fluxgnn_poisson_spectral")
+            _lib.check(_lib.lib().fluxgnn_poisson_spectral(
+                t.data_ptr(), self.nx, out.data_ptr(), self.nx, gtab.data_ptr() if gtab is not None else None,
+                t.shape[0], self.nx, self.length, work.data_ptr() if work is not None else None, stream),
+                "fluxgnn_poisson_spectral")
         out = out[0] if single else out
         return out.cpu().numpy() if is_np else out
 
@@ -123,17 +126,18 @@ class BaselineSolver:
         _, gtab = self.grid.tables(dev)
         with torch.cuda.device(dev):
             out = torch.empty_like(state)
-            work = torch.empty_like(state) if n_steps > 1 else None
+            ws_bytes = _lib.lib().fluxgnn_baseline_workspace_bytes(B, nx)
+            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
             traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
                     if record_every else None)
             flux = torch.empty(n_steps, B, nx, dtype=torch.float32, device=dev) if record_flux else None
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(_lib.lib().fluxgnn_baseline_rollout(
-                state.data_ptr(), out.data_ptr(), gtab.data_ptr(), B, nx,
+                state.data_ptr(), out.data_ptr(), gtab.data_ptr() if gtab is not None else None, B, nx, self.length,
                 self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)),
                 n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
                 flux.data_ptr() if flux is not None else None,
-                work.data_ptr() if work is not None else None, stream), "fluxgnn_baseline_rollout")
+                work.data_ptr(), stream), "fluxgnn_baseline_rollout")
         return out, traj, flux
 
     def step(self, state, return_flux=False):

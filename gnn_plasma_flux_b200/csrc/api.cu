@@ -85,11 +85,15 @@ static int launch_tiles(const HybridArgs& a, int fast_radius, cudaStream_t strea
     return FLUXGNN_OK;
 }
 
+// Field solve dispatch: FFT for power-of-two grids of 256 cells and more, otherwise the
+// direct circular convolution with the fp64 table (any nx up to kPoissonDirectMaxNx).
 static int launch_poisson(const float* n, long long ns, float* E, long long es, const double* gtab,
-                          int B, int nx, cudaStream_t stream) {
+                          int B, int nx, double length, void* fft_ws, cudaStream_t stream) {
+    if (poisson_fft_supported(nx)) return launch_poisson_fft(n, ns, E, es, B, nx, length, fft_ws, stream);
     if (nx > kPoissonDirectMaxNx)
-        return set_error(FLUXGNN_EUNSUP, "field solve for nx=%d > %d is not implemented in this build", nx,
-                         kPoissonDirectMaxNx);
+        return set_error(FLUXGNN_EUNSUP, "field solve for nx=%d: only powers of two are supported above %d cells",
+                         nx, kPoissonDirectMaxNx);
+    if (gtab == nullptr) return set_error(FLUXGNN_EINVAL, "field solve for nx=%d needs the fluxgnn_poisson_table()", nx);
     dim3 grid((unsigned)B, (unsigned)((nx + 255) / 256));
     poisson_direct_kernel<<<grid, 256, (size_t)nx * sizeof(float), stream>>>(n, ns, E, es, gtab, nx);
     FLUXGNN_CUDA_OK(cudaGetLastError());
@@ -144,17 +148,26 @@ int fluxgnn_pack_weights(const float* w_in, const float* b_in, const float* w_up
 int fluxgnn_poisson_table(int nx, double length, double* gtab, void* stream) {
     if (nx < 1 || !(length > 0.0) || gtab == nullptr)
         return set_error(FLUXGNN_EINVAL, "poisson_table: nx=%d length=%g gtab=%p", nx, length, (void*)gtab);
+    if (nx > kPoissonDirectMaxNx)
+        return set_error(FLUXGNN_EUNSUP, "poisson_table: the direct solve covers nx <= %d", kPoissonDirectMaxNx);
     poisson_table_kernel<<<nx, 128, 0, (cudaStream_t)stream>>>(nx, length, gtab);
     FLUXGNN_CUDA_OK(cudaGetLastError());
     count_launch();
     return FLUXGNN_OK;
 }
 
+int fluxgnn_poisson_uses_table(int nx) { return (nx >= 1 && !poisson_fft_supported(nx)) ? 1 : 0; }
+
+size_t fluxgnn_poisson_workspace_bytes(int B, int nx) {
+    if (B < 1 || nx < 1 || !poisson_fft_supported(nx)) return 0;
+    return poisson_fft_workspace_bytes(B, nx);
+}
+
 int fluxgnn_poisson_spectral(const float* n, long long n_ic_stride, float* E, long long e_ic_stride,
-                             const double* gtab, int B, int nx, void* stream) {
-    if (!n || !E || !gtab || B < 1 || nx < 1 || n_ic_stride < nx || e_ic_stride < nx)
+                             const double* gtab, int B, int nx, double length, void* workspace, void* stream) {
+    if (!n || !E || B < 1 || nx < 1 || n_ic_stride < nx || e_ic_stride < nx || !(length > 0.0))
         return set_error(FLUXGNN_EINVAL, "poisson_spectral: bad argument (B=%d nx=%d)", B, nx);
-    return launch_poisson(n, n_ic_stride, E, e_ic_stride, gtab, B, nx, (cudaStream_t)stream);
+    return launch_poisson(n, n_ic_stride, E, e_ic_stride, gtab, B, nx, length, workspace, (cudaStream_t)stream);
 }
 
 int fluxgnn_forward_ring(const void* packed, int num_layers, const float* state, const float* x,
@@ -180,18 +193,27 @@ int fluxgnn_forward_ring(const void* packed, int num_layers, const float* state,
     return launch_tiles(a, fast, (cudaStream_t)stream);
 }
 
+// workspace = [state ping-pong buffer][FFT scratch]; both absent for nx <= 128
 size_t fluxgnn_hybrid_workspace_bytes(int B, int nx) {
+    if (B < 1 || nx < 1 || nx <= kTileRows) return 0;
+    return (size_t)B * 3 * nx * sizeof(float) + fluxgnn_poisson_workspace_bytes(B, nx);
+}
+
+size_t fluxgnn_baseline_workspace_bytes(int B, int nx) {
     if (B < 1 || nx < 1) return 0;
-    return nx <= kTileRows ? 0 : (size_t)B * 3 * nx * sizeof(float);
+    return (size_t)B * 3 * nx * sizeof(float) + fluxgnn_poisson_workspace_bytes(B, nx);
 }
 
 int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* state_in, float* state_out,
-                           const float* x, const double* gtab, int B, int nx, int radius, float c, float dt,
-                           int steps, int record_every, float* traj, void* workspace, void* stream_) {
+                           const float* x, const double* gtab, int B, int nx, double length, int radius,
+                           float c, float dt, int steps, int record_every, float* traj, void* workspace,
+                           void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_model(packed, num_layers, B, nx, radius);
     if (rc != FLUXGNN_OK) return rc;
-    if (!state_in || !state_out || !x || !gtab) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: null pointer");
+    if (!state_in || !state_out || !x) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: null pointer");
+    if (nx <= kTileRows && !gtab) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: gtab required for nx <= %d", kTileRows);
+    if (!(length > 0.0)) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: length must be positive");
     if (state_in == state_out) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: state_in and state_out alias");
     if (steps < 1) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: steps must be >= 1, got %d", steps);
     if (traj && record_every < 1) return set_error(FLUXGNN_EINVAL, "hybrid_rollout: record_every must be >= 1");
@@ -216,9 +238,11 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* stat
         return launch_tiles(a, fast, stream);
     }
     // window tiles: per step  tile kernel (n', u')  ->  field-solve kernel (E')
-    if (steps > 1 && workspace == nullptr)
-        return set_error(FLUXGNN_EINVAL, "hybrid_rollout: workspace required for nx > %d and steps > 1", kTileRows);
     const size_t state_floats = (size_t)B * 3 * nx;
+    const bool need_ws = steps > 1 || fluxgnn_poisson_workspace_bytes(B, nx) > 0;
+    if (need_ws && workspace == nullptr)
+        return set_error(FLUXGNN_EINVAL, "hybrid_rollout: fluxgnn_hybrid_workspace_bytes() of workspace required");
+    void* fft_ws = workspace ? (void*)((float*)workspace + state_floats) : nullptr;
     const float* src = state_in;
     a.steps = 1;
     a.traj = nullptr;
@@ -228,7 +252,7 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* stat
         a.state_out = dst;
         rc = launch_tiles(a, fast, stream);
         if (rc != FLUXGNN_OK) return rc;
-        rc = launch_poisson(dst, 3LL * nx, dst + 2 * (size_t)nx, 3LL * nx, gtab, B, nx, stream);
+        rc = launch_poisson(dst, 3LL * nx, dst + 2 * (size_t)nx, 3LL * nx, gtab, B, nx, length, fft_ws, stream);
         if (rc != FLUXGNN_OK) return rc;
         if (traj && (t + 1) % record_every == 0) {
             FLUXGNN_CUDA_OK(cudaMemcpyAsync(traj + (size_t)((t + 1) / record_every - 1) * state_floats, dst,
@@ -240,20 +264,21 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* stat
 }
 
 int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const double* gtab, int B, int nx,
-                             float c, float dt, float nu, float dx2, int steps, int record_every, float* traj,
-                             float* flux_n, void* workspace, void* stream_) {
+                             double length, float c, float dt, float nu, float dx2, int steps, int record_every,
+                             float* traj, float* flux_n, void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!state_in || !state_out || !gtab || B < 1 || nx < 1)
+    if (!state_in || !state_out || B < 1 || nx < 1 || !(length > 0.0))
         return set_error(FLUXGNN_EINVAL, "baseline_rollout: bad argument (B=%d nx=%d)", B, nx);
     if (state_in == state_out) return set_error(FLUXGNN_EINVAL, "baseline_rollout: state_in and state_out alias");
     if (steps < 1) return set_error(FLUXGNN_EINVAL, "baseline_rollout: steps must be >= 1, got %d", steps);
-    if (steps > 1 && workspace == nullptr)
-        return set_error(FLUXGNN_EINVAL, "baseline_rollout: workspace of B*3*nx floats required for steps > 1");
+    if ((steps > 1 || fluxgnn_poisson_workspace_bytes(B, nx) > 0) && workspace == nullptr)
+        return set_error(FLUXGNN_EINVAL, "baseline_rollout: fluxgnn_baseline_workspace_bytes() of workspace required");
     if (traj && record_every < 1) return set_error(FLUXGNN_EINVAL, "baseline_rollout: record_every must be >= 1");
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc != FLUXGNN_OK) return rc;
     const size_t state_floats = (size_t)B * 3 * nx;
+    void* fft_ws = workspace ? (void*)((float*)workspace + state_floats) : nullptr;
     const long long cells = (long long)B * nx;
     long long blocks = (cells + 255) / 256;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
@@ -264,7 +289,7 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const doub
                                                                  B, nx, c, dt, nu, dx2);
         FLUXGNN_CUDA_OK(cudaGetLastError());
         count_launch();
-        rc = launch_poisson(dst, 3LL * nx, dst + 2 * (size_t)nx, 3LL * nx, gtab, B, nx, stream);
+        rc = launch_poisson(dst, 3LL * nx, dst + 2 * (size_t)nx, 3LL * nx, gtab, B, nx, length, fft_ws, stream);
         if (rc != FLUXGNN_OK) return rc;
         if (traj && (t + 1) % record_every == 0) {
             FLUXGNN_CUDA_OK(cudaMemcpyAsync(traj + (size_t)((t + 1) / record_every - 1) * state_floats, dst,

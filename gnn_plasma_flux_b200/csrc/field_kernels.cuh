@@ -20,4 +20,13 @@ constexpr int kFfmaProbeFlopsPerIter = 2 * 8 * 16;   // per thread per iteration
 
 constexpr int kPoissonDirectMaxNx = 12288;   // rho staged in 48 KiB of shared memory
 
+// fft_poisson.cu: power-of-two grids, 2^kFftMinBits <= nx <= 2^kFftMaxBits
+constexpr int kFftMinBits = 8;
+constexpr int kFftRowBits = 14;              // longest transform done inside one CTA (128 KiB of complex64)
+constexpr int kFftMaxBits = 25;
+bool poisson_fft_supported(int nx);
+size_t poisson_fft_workspace_bytes(int B, int nx);
+int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e_stride, int B, int nx,
+                       double length, void* workspace, cudaStream_t stream);
+
 }  // namespace fluxgnn

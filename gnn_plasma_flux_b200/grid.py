@@ -24,18 +24,22 @@ class PeriodicGrid:
         self.k = 2.0 * np.pi * np.fft.fftfreq(self.nx, d=self.dx)
         self._dev = {}
 
-    def tables(self, device) -> tuple[torch.Tensor, torch.Tensor]:
-        """(x float32 [nx], gtab float64 [nx]) on `device`, built once per device."""
+    def tables(self, device):
+        """(x float32 [nx], gtab float64 [nx] | None) on `device`, built once per device.
+        gtab is only built where a kernel reads it: whole-IC tiles (nx <= 128) and grids
+        whose standalone field solve is the direct convolution rather than the FFT."""
         device = torch.device(device)
         key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
         hit = self._dev.get(key)
         if hit is None:
             with torch.cuda.device(device):
                 x_dev = torch.as_tensor(self.x, dtype=torch.float32).to(device)
-                gtab = torch.empty(self.nx, dtype=torch.float64, device=device)
-                stream = torch.cuda.current_stream(device).cuda_stream
-                _lib.check(_lib.lib().fluxgnn_poisson_table(self.nx, self.length, gtab.data_ptr(), stream),
-                           "fluxgnn_poisson_table")
+                gtab = None
+                if self.nx <= 128 or _lib.lib().fluxgnn_poisson_uses_table(self.nx):
+                    gtab = torch.empty(self.nx, dtype=torch.float64, device=device)
+                    stream = torch.cuda.current_stream(device).cuda_stream
+                    _lib.check(_lib.lib().fluxgnn_poisson_table(self.nx, self.length, gtab.data_ptr(), stream),
+                               "fluxgnn_poisson_table")
             hit = (x_dev, gtab)
             self._dev[key] = hit
         return hit

@@ -62,11 +62,12 @@ class HybridSolver:
             traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
                     if record_every else None)
             ws_bytes = _lib.lib().fluxgnn_hybrid_workspace_bytes(B, nx)
-            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if (ws_bytes and n_steps > 1) else None
+            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(_lib.lib().fluxgnn_hybrid_rollout(
                 packed.data_ptr(), self.model.num_layers, state.data_ptr(), out.data_ptr(),
-                x_dev.data_ptr(), gtab.data_ptr(), B, nx, self.graph_radius,
+                x_dev.data_ptr(), gtab.data_ptr() if gtab is not None else None, B, nx, base.length,
+                self.graph_radius,
                 float(np.float32(base.dt / base.dx)), float(np.float32(base.dt)),
                 n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
                 work.data_ptr() if work is not None else None, stream), "fluxgnn_hybrid_rollout")

@@ -75,19 +75,27 @@ int fluxgnn_pack_weights(const float* w_in, const float* b_in,
                          const float* w_e2, const float* b_e2,
                          int num_layers, void* packed, void* stream);
 
-/* ---- Poisson operator table ------------------------------------------------
- * src/baseline_solver.py:59-68 is the circular convolution E = g (*) (n - 1)
- * with g = Re ifft(i/k), g_hat(0) = 0 (the Nyquist bin drops out of Re()).
- * Fills gtab[nx] (float64, device) for k = 2*pi*fftfreq(nx, length/nx)
- * (src/baseline_solver.py:26). */
-int fluxgnn_poisson_table(int nx, double length, double* gtab, void* stream);
-
-/* E[B][nx] = solve_poisson(n[B][nx]) (src/baseline_solver.py:59-68), any nx >= 1.
+/* ---- field solve ------------------------------------------------------------
+ * src/baseline_solver.py:59-68:  E = Re ifft(i * fft(n - 1) / k),  E_hat(0) = 0,
+ * k = 2*pi*fftfreq(nx, length/nx) (:26); the Nyquist bin drops out of Re().
+ * Two exact realisations of that operator:
+ *   - power-of-two nx in 2^8..2^25: FFT (one CTA per IC up to 2^14 cells, a
+ *     transpose-free four-step transform above; needs
+ *     fluxgnn_poisson_workspace_bytes(B, nx) bytes of scratch, 0 up to 2^14);
+ *   - any other nx <= 12288 (and the in-kernel solve of whole-IC tiles,
+ *     nx <= 128): circular convolution E = g (*) (n - 1) with
+ *     g = Re ifft(i/k), accumulated in fp64.  fluxgnn_poisson_table() fills
+ *     gtab[nx] (float64, device); fluxgnn_poisson_uses_table(nx) says whether a
+ *     standalone solve at this nx reads it (gtab may be NULL otherwise).
  * `n` and `E` have the given strides (in floats) between ICs so that a channel
  * of a [B][3][nx] state can be passed directly. */
+int fluxgnn_poisson_uses_table(int nx);
+int fluxgnn_poisson_table(int nx, double length, double* gtab, void* stream);
+size_t fluxgnn_poisson_workspace_bytes(int B, int nx);
 int fluxgnn_poisson_spectral(const float* n, long long n_ic_stride,
                              float* E, long long e_ic_stride,
-                             const double* gtab, int B, int nx, void* stream);
+                             const double* gtab, int B, int nx, double length,
+                             void* workspace, void* stream);
 
 /* ---- FluxGNN.forward on the radius-r ring ----------------------------------
  * Replaces build_chain_graph + FluxGNN.forward (src/graph_constructor.py:30-38,
@@ -111,14 +119,15 @@ int fluxgnn_forward_ring(const void* packed, int num_layers,
  *   state_in[B][3][nx] -> state_out[B][3][nx]   (may not alias)
  *   traj: nullable; when given, the state after every `record_every`-th step
  *         is stored at traj[(t/record_every)-1][B][3][nx], t = 1..steps.
- *   workspace: fluxgnn_hybrid_workspace_bytes(B, nx) bytes (0 is possible).
+ *   workspace: fluxgnn_hybrid_workspace_bytes(B, nx) bytes (0 for nx <= 128).
+ *   gtab: required for nx <= 128 and wherever fluxgnn_poisson_uses_table(nx).
  *   c = float32(dt/dx) and dt = float32(dt), the scalars numpy uses
  *   (src/hybrid_solver.py:52,57-58). */
 size_t fluxgnn_hybrid_workspace_bytes(int B, int nx);
 int fluxgnn_hybrid_rollout(const void* packed, int num_layers,
                            const float* state_in, float* state_out,
                            const float* x, const double* gtab,
-                           int B, int nx, int radius, float c, float dt,
+                           int B, int nx, double length, int radius, float c, float dt,
                            int steps, int record_every, float* traj,
                            void* workspace, void* stream);
 
@@ -127,10 +136,13 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers,
  * left-differenced u^2/2, viscous Laplacian, forward Euler, field solve.
  *   flux_n: nullable [steps][B][nx], the continuity flux F_n of every step
  *           (`return_flux` / `record_flux`, :84,:99-100,:109-111).
- *   traj:   as above.  inv_dx2 = 1/float32(dx^2) is NOT used: the kernel
- *           divides by dx2 = float32(dx*dx) exactly as numpy does (:78). */
+ *   traj:   as above.  The kernel divides by dx2 = float32(dx*dx) exactly as
+ *           numpy does (:78).
+ *   workspace: fluxgnn_baseline_workspace_bytes(B, nx) bytes, required when
+ *           steps > 1 or the field solve needs scratch. */
+size_t fluxgnn_baseline_workspace_bytes(int B, int nx);
 int fluxgnn_baseline_rollout(const float* state_in, float* state_out,
-                             const double* gtab, int B, int nx,
+                             const double* gtab, int B, int nx, double length,
                              float c, float dt, float nu, float dx2,
                              int steps, int record_every, float* traj,
                              float* flux_n, void* workspace, void* stream);

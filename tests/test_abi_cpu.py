@@ -36,14 +36,18 @@ def test_size_queries(built_lib):
     assert built_lib.fluxgnn_packed_weight_bytes(0) == 0
     assert built_lib.fluxgnn_packed_weight_bytes(9) == 0
     assert built_lib.fluxgnn_hybrid_workspace_bytes(16, 64) == 0
-    assert built_lib.fluxgnn_hybrid_workspace_bytes(16, 1024) == 16 * 3 * 1024 * 4
+    assert built_lib.fluxgnn_hybrid_workspace_bytes(16, 1024) == 16 * 3 * 1024 * 4        # FFT inside one CTA: no scratch
+    assert built_lib.fluxgnn_poisson_workspace_bytes(2, 1 << 16) == 2 * (1 << 16) * 8      # four-step FFT: complex64 scratch
+    assert built_lib.fluxgnn_hybrid_workspace_bytes(2, 1 << 16) == 2 * (1 << 16) * (12 + 8)
+    assert built_lib.fluxgnn_baseline_workspace_bytes(2, 1000) == 2 * 3 * 1000 * 4
+    assert [built_lib.fluxgnn_poisson_uses_table(n) for n in (64, 128, 256, 1000, 1024, 1 << 20)] == [1, 1, 0, 1, 0, 0]
 
 
 def test_argument_errors_without_gpu(built_lib):
     from gnn_plasma_flux_b200 import _lib
     rc = built_lib.fluxgnn_pack_weights(None, None, None, None, None, None, None, None, 4, None, None)
     assert rc == -1 and b"null" in built_lib.fluxgnn_last_error()
-    rc = built_lib.fluxgnn_hybrid_rollout(None, 4, None, None, None, None, 1, 64, 1, 0.1, 0.1, 1, 1, None, None, None)
+    rc = built_lib.fluxgnn_hybrid_rollout(None, 4, None, None, None, None, 1, 64, 6.28, 1, 0.1, 0.1, 1, 1, None, None, None)
     assert rc == -1
     rc = built_lib.fluxgnn_forward_ring(ctypes.c_void_p(16), 12, None, None, 1, 64, 1, 1, None, None, None)
     assert rc == -3                                               # unsupported layer count
