@@ -301,6 +301,64 @@ def run_ours(args):
     return 0
 
 
+def run_side_workload(args):
+    """Secondary, single-GPU measurements (not the driver's bench line): BASELINE.json
+    configs[2] shape per GPU (c3: nx=1024, radius 2, window tiles + FFT field solve) and
+    configs[4] (c5: classical solver alone at 2^24 cells, HBM-bound)."""
+    if not torch.cuda.is_available():
+        raise SystemExit("needs a CUDA device")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    from gnn_plasma_flux_b200 import BaselineSolver, FluxGNN, HybridSolver, MODEL_CONFIG, _lib
+    from oracle import ref_port as P
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    K, W = args.steps, max(args.warmup, 3)
+    if args.workload == "c5":
+        nx, B = 1 << 24, args.batch or 1
+        dt = 0.2 * (2 * np.pi / nx) ** 2 / 1e-3          # explicit viscosity: nu*dt/dx^2 = 0.2 (0.02*dx would be unstable)
+        grid = P.Grid(nx=nx, dt=dt, nu=1e-3)
+        ic = P.stable_initial_condition(grid, 0)
+        state = torch.from_numpy(np.repeat(ic[None], B, 0)).to(dev)
+        sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device=dev)
+        step = lambda st, n: sol.rollout(st, n)[0]
+        name = f"C5 classical solver alone: {B} x 2^24 cells, nu=1e-3 (state {B * 3 * nx * 4 >> 20} MiB > L2, no flush needed)"
+        flop = None
+    else:
+        nx, B, r = 1024, args.batch or 2048, 2
+        dt = 3e-4
+        grid = P.Grid(nx=nx, dt=dt)
+        base = np.stack([P.stable_initial_condition(grid, s) for s in range(64)])
+        state = torch.from_numpy(np.tile(base, (B // 64 + 1, 1, 1))[:B].copy()).to(dev)
+        weights = P.init_weights(0)
+        model = FluxGNN(**MODEL_CONFIG)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+        sol = HybridSolver(None, r, nx=nx, dt=dt, device=dev, graph_radius=r, model=model.to(dev))
+        step = lambda st, n: sol.rollout(st, n)[0]
+        name = f"C3 shape per GPU (scaled): {B} ICs x 1024 cells, radius 2 (state {B * 3 * nx * 4 >> 20} MiB)"
+        flop = FLOP_PER_CELL_EXECUTED
+    for _ in range(W):
+        state = step(state, 1)
+    torch.cuda.synchronize(dev)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    state = step(state, K)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    assert torch.isfinite(state).all()
+    rate = B * nx * K / (ms * 1e-3)
+    line = {"metric": METRIC if flop else "baseline_rollout_cell_updates_per_sec", "value": rate, "unit": UNIT, "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name}, "gpu_launches": _lib.launch_count() - l0,
+            "roofline": {"bound": "hbm" if not flop else "fp32-ffma", "achieved": rate * BYTES_PER_CELL / 1e9 if not flop else rate * flop / 1e12,
+                         "peak": hbm_peak if not flop else None, "unit": "GB/s" if not flop else "TFLOP/s",
+                         "frac": rate * BYTES_PER_CELL / 1e9 / hbm_peak if not flop else None, "traffic": None}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,9 +366,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["c2", "c3", "c5"], default="c2",
+                    help="c2 (default) is the driver's bench line; c3/c5 are secondary single-GPU measurements")
+    ap.add_argument("--batch", type=int, default=0)
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")
+    if args.workload != "c2":
+        return run_side_workload(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

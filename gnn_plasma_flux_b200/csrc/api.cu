@@ -280,8 +280,8 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const doub
     const size_t state_floats = (size_t)B * 3 * nx;
     void* fft_ws = workspace ? (void*)((float*)workspace + state_floats) : nullptr;
     const long long cells = (long long)B * nx;
-    long long blocks = (cells + 255) / 256;
-    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    long long blocks = (((nx & 3) == 0 ? cells / 4 : cells) + 255) / 256;
+    if (blocks > (long long)sms * 64) blocks = (long long)sms * 64;
     const float* src = state_in;
     for (int t = 0; t < steps; ++t) {
         float* dst = ((steps - 1 - t) % 2 == 0) ? state_out : (float*)workspace;

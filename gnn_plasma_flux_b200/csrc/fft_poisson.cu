@@ -5,14 +5,14 @@
 //
 // nx <= 2^14: one CTA per IC, the whole transform lives in shared memory:
 //     load rho -> DIF forward FFT (bit-reversed spectrum) -> multiply -> DIT inverse -> store Re.
-// nx  > 2^14: four-step factorisation nx = N1 * N2, N2 = 2^14, element n = n1*N2 + n2:
+// nx  > 2^14: four-step factorisation nx = N1 * N2, N2 = 2^13, element n = n1*N2 + n2:
 //     A  columns: for a tile of T consecutive n2, length-N1 FFT over n1, times W_nx^(n2*k1)  -> Y[k1][n2]
 //     B  rows   : for each k1, length-N2 FFT over n2 -> k2, multiply by i/k(k1 + N1*k2),
 //                 inverse FFT k2 -> n2, times conj twiddle                                      (in place)
 //     C  columns: inverse length-N1 FFT over k1 -> n1, real part / nx -> E[n1*N2 + n2]
 // No transposes: forward transforms are decimation-in-frequency (natural in, bit-reversed
 // out), inverse ones decimation-in-time (bit-reversed in, natural out), and the spectral
-// multiply is index-agnostic.  Shared-memory radix-2 stages with sincospi twiddles.
+// multiply is index-agnostic.  Each shared-memory round trip runs a radix-16 transform in registers.
 #include "common.cuh"
 #include "field_kernels.cuh"
 
@@ -20,7 +20,8 @@ namespace fluxgnn {
 
 namespace {
 
-constexpr int kFftThreads = 512;
+constexpr int kFftThreads = 512;       // whole-transform kernel (upper bound; it launches nx/16)
+constexpr int kFftStepThreads = 256;   // four-step kernels: 3 CTAs per SM by registers and shared memory
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -35,39 +36,114 @@ __device__ __forceinline__ float2 twiddle(int q, int n, float sign) {
     return make_float2(c, s);
 }
 
-// `cnt` interleaved transforms of length n = 2^bits: element idx of transform t at s[idx*cnt + t].
-// Forward (sign -1): DIF, natural order in -> bit-reversed order out.
-__device__ void fft_dif(float2* s, int bits, int cnt, float sign) {
-    const int n = 1 << bits;
-    const int work = (n >> 1) * cnt;
-    for (int h = n >> 1; h >= 1; h >>= 1) {
-        for (int w = threadIdx.x; w < work; w += blockDim.x) {
-            const int t = w % cnt, b = w / cnt;
-            const int j = b & (h - 1);
-            const int i0 = ((b - j) << 1) + j, i1 = i0 + h;
-            const float2 u = s[i0 * cnt + t], v = s[i1 * cnt + t];
-            s[i0 * cnt + t] = make_float2(u.x + v.x, u.y + v.y);
-            s[i1 * cnt + t] = cmul(make_float2(u.x - v.x, u.y - v.y), twiddle(j * (n / (2 * h)), n, sign));
+// Shared-memory address of element idx of interleaved transform t.  A lone transform is
+// padded by one element per 16 so that the strided register-radix accesses of the short
+// block lengths spread over all banks; interleaved transforms are conflict-free as they are.
+__device__ __forceinline__ int saddr(int idx, int t, int cnt) {
+    return cnt == 1 ? idx + (idx >> 4) : idx * cnt + t;
+}
+
+// exp(sign * 2*pi*i * m / (2*half)), m < half <= 8: the constant part of a register-radix twiddle
+__device__ __forceinline__ float2 unit_root(int m, int half, float sign) {
+    const int q = m * (8 / half);                  // angle in sixteenths of a turn
+    const float c[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                        0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+    const float sn[8] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                         1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+    return make_float2(c[q], sign * sn[q]);
+}
+
+// One radix-R pass over blocks of length L (R | L): every work item owns the R elements
+// blk*L + base + m*(L/R) and runs log2(R) radix-2 stages on them in registers.
+// DIF (kDit = false): butterfly then twiddle, spans shrink; DIT: twiddle then butterfly, spans grow.
+// The twiddle of register-span `half` at offset mm is  W_L^(base * (R/2)/half) * W_(2 half)^mm.
+template <int R, bool kDit>
+__device__ __forceinline__ void radix_pass(float2* s, int n, int L, int cnt, float sign) {
+    const int sub = L / R;                         // stride between a work item's elements (power of two)
+    const int items = (n / R) * cnt;
+    const int cnt_bits = 31 - __clz(cnt), sub_bits = 31 - __clz(sub);
+    for (int w = threadIdx.x; w < items; w += blockDim.x) {
+        const int t = w & (cnt - 1), q = w >> cnt_bits;
+        const int base = q & (sub - 1), blk = q >> sub_bits;
+        const int e0 = blk * L + base;
+        float2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = s[saddr(e0 + m * sub, t, cnt)];
+        // per-item twiddles W_L^(base * 2^k), k = 0..log2(R)-1
+        float2 wp[4];
+        wp[0] = twiddle(base, L, sign);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) wp[k] = cmul(wp[k - 1], wp[k - 1]);
+        if (!kDit) {
+#pragma unroll
+            for (int half = R / 2, k = 0; half >= 1; half >>= 1, ++k) {
+#pragma unroll
+                for (int a = 0; a < R; ++a) {
+                    if ((a & half) == 0) {
+                        const int mm = a & (half - 1);
+                        const float2 u = v[a], x = v[a + half];
+                        v[a] = make_float2(u.x + x.x, u.y + x.y);
+                        const float2 tw = cmul(wp[k], unit_root(mm, half, sign));
+                        v[a + half] = cmul(make_float2(u.x - x.x, u.y - x.y), tw);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int half = 1, k = 0; half < R; half <<= 1, ++k) {
+                // log2(R) - 1 - k indexes the same twiddle power the DIF stage of this span used
+                int kk = 0;
+#pragma unroll
+                for (int hh = R / 2; hh > half; hh >>= 1) ++kk;
+#pragma unroll
+                for (int a = 0; a < R; ++a) {
+                    if ((a & half) == 0) {
+                        const int mm = a & (half - 1);
+                        const float2 tw = cmul(wp[kk], unit_root(mm, half, sign));
+                        const float2 u = v[a], x = cmul(v[a + half], tw);
+                        v[a] = make_float2(u.x + x.x, u.y + x.y);
+                        v[a + half] = make_float2(u.x - x.x, u.y - x.y);
+                    }
+                }
+            }
         }
-        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < R; ++m) s[saddr(e0 + m * sub, t, cnt)] = v[m];
+    }
+    __syncthreads();
+}
+
+template <bool kDit>
+__device__ __forceinline__ void radix_dispatch(float2* s, int n, int L, int R, int cnt, float sign) {
+    switch (R) {
+        case 16: radix_pass<16, kDit>(s, n, L, cnt, sign); break;
+        case 8: radix_pass<8, kDit>(s, n, L, cnt, sign); break;
+        case 4: radix_pass<4, kDit>(s, n, L, cnt, sign); break;
+        default: radix_pass<2, kDit>(s, n, L, cnt, sign); break;
     }
 }
 
-// Inverse of the above ordering: DIT, bit-reversed order in -> natural order out.
+// `cnt` interleaved transforms of length n = 2^bits (addressing: saddr()).
+// Forward ordering: DIF, natural order in -> bit-reversed order out.  Radix-16 passes over
+// block lengths n, n/16, ...; the last pass takes the remaining 2, 4 or 8.
+__device__ void fft_dif(float2* s, int bits, int cnt, float sign) {
+    const int n = 1 << bits;
+    int L = n;
+    while (L > 1) {
+        const int R = L >= 16 ? 16 : L;
+        radix_dispatch<false>(s, n, L, R, cnt, sign);
+        L /= R;
+    }
+}
+
+// Inverse ordering: DIT, bit-reversed order in -> natural order out: the same passes, backwards.
 __device__ void fft_dit(float2* s, int bits, int cnt, float sign) {
     const int n = 1 << bits;
-    const int work = (n >> 1) * cnt;
-    for (int h = 1; h < n; h <<= 1) {
-        for (int w = threadIdx.x; w < work; w += blockDim.x) {
-            const int t = w % cnt, b = w / cnt;
-            const int j = b & (h - 1);
-            const int i0 = ((b - j) << 1) + j, i1 = i0 + h;
-            const float2 u = s[i0 * cnt + t];
-            const float2 v = cmul(s[i1 * cnt + t], twiddle(j * (n / (2 * h)), n, sign));
-            s[i0 * cnt + t] = make_float2(u.x + v.x, u.y + v.y);
-            s[i1 * cnt + t] = make_float2(u.x - v.x, u.y - v.y);
-        }
-        __syncthreads();
+    int L = 1 << (bits & 3);                       // block length of the short pass (1 = none)
+    if (L > 1) radix_dispatch<true>(s, n, L, L, cnt, sign);
+    while (L < n) {
+        L *= 16;
+        radix_dispatch<true>(s, n, L, 16, cnt, sign);
     }
 }
 
@@ -102,82 +178,89 @@ __global__ void __launch_bounds__(kFftThreads) poisson_fft_small_kernel(const fl
     extern __shared__ float2 sfft[];
     const int nx = 1 << bits;
     const float* src = n + (size_t)blockIdx.x * n_stride;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) sfft[i] = make_float2(__fsub_rn(src[i], 1.0f), 0.f);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x)
+        sfft[saddr(i, 0, 1)] = make_float2(__fsub_rn(src[i], 1.0f), 0.f);
     __syncthreads();
     fft_dif(sfft, bits, 1, -1.f);
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) sfft[i] = spectral_multiply(sfft[i], bitrev(i, bits), nx, length);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        float2& v = sfft[saddr(i, 0, 1)];
+        v = spectral_multiply(v, bitrev(i, bits), nx, length);
+    }
     __syncthreads();
     fft_dit(sfft, bits, 1, +1.f);
     float* dst = E + (size_t)blockIdx.x * e_stride;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) dst[i] = sfft[i].x;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) dst[i] = sfft[saddr(i, 0, 1)].x;
 }
 
 // ---------------------------------------------------------------------------
 // four-step, pass A: forward column transforms.  grid = (N2 / T, B)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFftThreads) poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride,
+__global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride,
                                                                            float2* __restrict__ Y, int bits1, int bits2,
                                                                            int T) {
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1;
     const long long N2 = 1LL << bits2, nx = (long long)N1 << bits2;
     const long long n2_0 = (long long)blockIdx.x * T;
+    const int t_bits = 31 - __clz(T);
     const float* src = n + (size_t)blockIdx.y * n_stride;
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w % T, n1 = w / T;
+        const int t = w & (T - 1), n1 = w >> t_bits;
         sfft[w] = make_float2(__fsub_rn(src[(size_t)n1 * N2 + n2_0 + t], 1.0f), 0.f);
     }
     __syncthreads();
     fft_dif(sfft, bits1, T, -1.f);
     float2* dst = Y + (size_t)blockIdx.y * nx;
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w % T, pos = w / T;
+        const int t = w & (T - 1), pos = w >> t_bits;
         const int k1 = bitrev(pos, bits1);
         const long long n2 = n2_0 + t;
-        dst[(size_t)k1 * N2 + n2] = cmul(sfft[w], big_twiddle((n2 * k1) % nx, nx, -1.f));      // W_nx^(n2*k1)
+        dst[(size_t)k1 * N2 + n2] = cmul(sfft[w], big_twiddle((n2 * k1) & (nx - 1), nx, -1.f));      // W_nx^(n2*k1)
     }
 }
 
 // pass B: rows.  grid = (N1, B); one length-N2 row per CTA, in place.
-__global__ void __launch_bounds__(kFftThreads) poisson_fft_rows_kernel(float2* __restrict__ Y, int bits1, int bits2,
+__global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_rows_kernel(float2* __restrict__ Y, int bits1, int bits2,
                                                                        double length) {
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1, N2 = 1 << bits2;
     const long long nx = (long long)N1 << bits2;
     const int k1 = blockIdx.x;
     float2* row = Y + (size_t)blockIdx.y * nx + (size_t)k1 * N2;
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) sfft[i] = row[i];
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) sfft[saddr(i, 0, 1)] = row[i];
     __syncthreads();
     fft_dif(sfft, bits2, 1, -1.f);
     for (int i = threadIdx.x; i < N2; i += blockDim.x) {
         const long long kbin = (long long)k1 + (long long)N1 * bitrev(i, bits2);
-        sfft[i] = spectral_multiply(sfft[i], kbin, nx, length);
+        float2& v = sfft[saddr(i, 0, 1)];
+        v = spectral_multiply(v, kbin, nx, length);
     }
     __syncthreads();
     fft_dit(sfft, bits2, 1, +1.f);
     for (int i = threadIdx.x; i < N2; i += blockDim.x) {
-        row[i] = cmul(sfft[i], big_twiddle(((long long)i * k1) % nx, nx, +1.f));              // conj twiddle
+        row[i] = cmul(sfft[saddr(i, 0, 1)], big_twiddle(((long long)i * k1) & (nx - 1), nx, +1.f));  // conj twiddle
     }
 }
 
 // pass C: inverse column transforms, real part out.  grid = (N2 / T, B)
-__global__ void __launch_bounds__(kFftThreads) poisson_fft_cols_inv_kernel(const float2* __restrict__ Y,
+__global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_cols_inv_kernel(const float2* __restrict__ Y,
                                                                            float* __restrict__ E, long long e_stride,
                                                                            int bits1, int bits2, int T) {
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1;
     const long long N2 = 1LL << bits2, nx = (long long)N1 << bits2;
     const long long n2_0 = (long long)blockIdx.x * T;
+    const int t_bits = 31 - __clz(T);
     const float2* src = Y + (size_t)blockIdx.y * nx;
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w % T, k1 = w / T;
+        const int t = w & (T - 1), k1 = w >> t_bits;
         sfft[w] = src[(size_t)k1 * N2 + n2_0 + t];
     }
     __syncthreads();
     fft_dif(sfft, bits1, T, +1.f);                 // natural k1 in -> bit-reversed n1 out
     float* dst = E + (size_t)blockIdx.y * e_stride;
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w % T, pos = w / T;
+        const int t = w & (T - 1), pos = w >> t_bits;
         dst[(size_t)bitrev(pos, bits1) * N2 + n2_0 + t] = sfft[w].x;
     }
 }
@@ -208,10 +291,10 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     if (bits < kFftMinBits || bits > kFftMaxBits)
         return set_error(FLUXGNN_EUNSUP, "FFT field solve needs nx = 2^%d..2^%d, got %d", kFftMinBits, kFftMaxBits, nx);
     if (bits <= kFftRowBits) {
-        const size_t smem = (size_t)nx * sizeof(float2);
+        const size_t smem = (size_t)(nx + nx / 16) * sizeof(float2);
         FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        const int threads = nx / 2 < kFftThreads ? (nx / 2 < 32 ? 32 : nx / 2) : kFftThreads;
+        const int threads = nx / 16 < kFftThreads ? (nx / 16 < 64 ? 64 : nx / 16) : kFftThreads;
         poisson_fft_small_kernel<<<B, threads, smem, stream>>>(n, n_stride, E, e_stride, bits, length);
         FLUXGNN_CUDA_OK(cudaGetLastError());
         count_launch();
@@ -220,20 +303,25 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     if (workspace == nullptr)
         return set_error(FLUXGNN_EINVAL, "field solve for nx=%d needs fluxgnn_poisson_workspace_bytes() of scratch", nx);
     if (B > 65535) return set_error(FLUXGNN_EUNSUP, "field solve for nx=%d handles at most 65535 ICs per call", nx);
-    const int bits2 = kFftRowBits, bits1 = bits - bits2;
+    // rows as long as configured, but never leave the column transform shorter than 2 or
+    // longer than the column tile
+    int bits2 = FLUXGNN_FFT_STEP_ROW_BITS;
+    if (bits - bits2 > FLUXGNN_FFT_STEP_COL_BITS - 1) bits2 = bits - (FLUXGNN_FFT_STEP_COL_BITS - 1);
+    const int bits1 = bits - bits2;
     const int N1 = 1 << bits1, N2 = 1 << bits2;
-    const int T = (1 << kFftRowBits) / N1;                   // N1 * T = 2^14 complex = 128 KiB
-    const size_t smem = (size_t)(1 << kFftRowBits) * sizeof(float2);
+    const int T = (1 << FLUXGNN_FFT_STEP_COL_BITS) / N1;     // N1 * T complex per column tile
+    const size_t smem = (size_t)(1 << FLUXGNN_FFT_STEP_COL_BITS) * sizeof(float2);
+    const size_t smem_row = (size_t)(N2 + N2 / 16) * sizeof(float2);
     float2* Y = (float2*)workspace;
     FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
     FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 gcol((unsigned)(N2 / T), (unsigned)B), grow((unsigned)N1, (unsigned)B);
-    poisson_fft_cols_fwd_kernel<<<gcol, kFftThreads, smem, stream>>>(n, n_stride, Y, bits1, bits2, T);
+    poisson_fft_cols_fwd_kernel<<<gcol, kFftStepThreads, smem, stream>>>(n, n_stride, Y, bits1, bits2, T);
     FLUXGNN_CUDA_OK(cudaGetLastError());
-    poisson_fft_rows_kernel<<<grow, kFftThreads, smem, stream>>>(Y, bits1, bits2, length);
+    poisson_fft_rows_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(Y, bits1, bits2, length);
     FLUXGNN_CUDA_OK(cudaGetLastError());
-    poisson_fft_cols_inv_kernel<<<gcol, kFftThreads, smem, stream>>>(Y, E, e_stride, bits1, bits2, T);
+    poisson_fft_cols_inv_kernel<<<gcol, kFftStepThreads, smem, stream>>>(Y, E, e_stride, bits1, bits2, T);
     FLUXGNN_CUDA_OK(cudaGetLastError());
     count_launch(3);
     return FLUXGNN_OK;

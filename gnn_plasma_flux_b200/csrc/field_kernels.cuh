@@ -23,6 +23,12 @@ constexpr int kPoissonDirectMaxNx = 12288;   // rho staged in 48 KiB of shared m
 // fft_poisson.cu: power-of-two grids, 2^kFftMinBits <= nx <= 2^kFftMaxBits
 constexpr int kFftMinBits = 8;
 constexpr int kFftRowBits = 14;              // longest transform done inside one CTA (128 KiB of complex64)
+#ifndef FLUXGNN_FFT_STEP_ROW_BITS
+#define FLUXGNN_FFT_STEP_ROW_BITS 13         // four-step: row length 2^13 (68 KiB padded -> 3 CTAs per SM)
+#endif
+#ifndef FLUXGNN_FFT_STEP_COL_BITS
+#define FLUXGNN_FFT_STEP_COL_BITS 13         // four-step: N1 * T = 2^13 complex per column tile (64 KiB)
+#endif
 constexpr int kFftMaxBits = 25;
 bool poisson_fft_supported(int nx);
 size_t poisson_fft_workspace_bytes(int B, int nx);
