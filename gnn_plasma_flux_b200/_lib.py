@@ -17,6 +17,7 @@ MAX_HOPS = 4
 MAX_LAYERS = 8
 HIDDEN = 128
 INPUT_DIM = 4
+TC_PRECISIONS = {"tf32x3": 1, "tf32": 2}     # FLUXGNN_TC_* of include/fluxgnn.h
 
 # name -> (restype, argtypes); mirrors include/fluxgnn.h declaration by declaration
 SIGNATURES = {
@@ -36,6 +37,12 @@ SIGNATURES = {
     "fluxgnn_hybrid_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_hybrid_rollout": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double,
                                        c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_packed_tc_weight_bytes": (c_size_t, [c_int]),
+    "fluxgnn_pack_weights_tc": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
+    "fluxgnn_forward_ring_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_hybrid_rollout_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                          c_double, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fluxgnn_baseline_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float,
                                          c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -75,12 +75,16 @@ static int check_model(const void* packed, int L, int B, int nx, int radius) {
     return FLUXGNN_OK;
 }
 
+// fast_radius >= 0: FP32-pipe kernel (0 = generic walk); < 0: tensor-core kernel of radius -fast_radius
 static int launch_tiles(const HybridArgs& a, int fast_radius, cudaStream_t stream) {
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc != FLUXGNN_OK) return rc;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    FLUXGNN_CUDA_OK(launch_hybrid_tiles(a, fast_radius, grid, stream));
+    if (fast_radius < 0)
+        FLUXGNN_CUDA_OK(launch_hybrid_tc_tiles(a, -fast_radius, grid, stream));
+    else
+        FLUXGNN_CUDA_OK(launch_hybrid_tiles(a, fast_radius, grid, stream));
     count_launch();
     return FLUXGNN_OK;
 }
@@ -145,6 +149,27 @@ int fluxgnn_pack_weights(const float* w_in, const float* b_in, const float* w_up
     return FLUXGNN_OK;
 }
 
+size_t fluxgnn_packed_tc_weight_bytes(int num_layers) {
+    if (num_layers < 1 || num_layers > kMaxL) return 0;
+    return packed_tc_floats(num_layers) * sizeof(float);
+}
+
+int fluxgnn_pack_weights_tc(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
+                            const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
+                            int num_layers, void* packed, void* stream) {
+    if (num_layers < 1 || num_layers > kMaxL)
+        return set_error(FLUXGNN_EUNSUP, "num_layers must be in 1..%d, got %d", kMaxL, num_layers);
+    if (!w_in || !b_in || !w_upd || !b_upd || !w_e1 || !b_e1 || !w_e2 || !b_e2 || !packed)
+        return set_error(FLUXGNN_EINVAL, "null weight pointer");
+    const size_t total = packed_tc_floats(num_layers);
+    const int blocks = (int)((total + 255) / 256);
+    pack_weights_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_in, b_in, w_upd, b_upd, w_e1, b_e1, w_e2, b_e2,
+                                                                      num_layers, (float*)packed);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 int fluxgnn_poisson_table(int nx, double length, double* gtab, void* stream) {
     if (nx < 1 || !(length > 0.0) || gtab == nullptr)
         return set_error(FLUXGNN_EINVAL, "poisson_table: nx=%d length=%g gtab=%p", nx, length, (void*)gtab);
@@ -170,9 +195,19 @@ int fluxgnn_poisson_spectral(const float* n, long long n_ic_stride, float* E, lo
     return launch_poisson(n, n_ic_stride, E, e_ic_stride, gtab, B, nx, length, workspace, (cudaStream_t)stream);
 }
 
-int fluxgnn_forward_ring(const void* packed, int num_layers, const float* state, const float* x,
-                         int B, int nx, int radius, int hops, float* flux_edges, float* face_flux,
-                         void* stream) {
+}  // extern "C"
+
+static int tc_shape_ok(int whole_ic, int nx, int radius) {
+    if (radius > 4) return set_error(FLUXGNN_EUNSUP, "tensor path: radius must be <= 4, got %d", radius);
+    if (whole_ic && nx != 32 && nx != 64 && nx != 128)
+        return set_error(FLUXGNN_EUNSUP, "tensor path: whole-IC tiles need nx in {32, 64, 128}, got %d "
+                                         "(use the fp32 entry point)", nx);
+    return FLUXGNN_OK;
+}
+
+static int forward_ring_impl(int precision, const void* packed, int num_layers, const float* state, const float* x,
+                             int B, int nx, int radius, int hops, float* flux_edges, float* face_flux,
+                             void* stream) {
     int rc = check_model(packed, num_layers, B, nx, radius);
     if (rc != FLUXGNN_OK) return rc;
     if (!state || !x) return set_error(FLUXGNN_EINVAL, "forward_ring: null state or x");
@@ -190,7 +225,31 @@ int fluxgnn_forward_ring(const void* packed, int num_layers, const float* state,
     int fast = 0;
     rc = plan_tiles(a, &fast);
     if (rc != FLUXGNN_OK) return rc;
+    if (precision != 0) {
+        if (hops != 1) return set_error(FLUXGNN_EUNSUP, "tensor path: forward emits hop 1 only");
+        rc = tc_shape_ok(a.whole_ic, nx, radius);
+        if (rc != FLUXGNN_OK) return rc;
+        a.tc_parts = (precision == FLUXGNN_TC_TF32X3) ? 2 : 1;
+        fast = -radius;
+    }
     return launch_tiles(a, fast, (cudaStream_t)stream);
+}
+
+extern "C" {
+
+int fluxgnn_forward_ring(const void* packed, int num_layers, const float* state, const float* x,
+                         int B, int nx, int radius, int hops, float* flux_edges, float* face_flux,
+                         void* stream) {
+    return forward_ring_impl(0, packed, num_layers, state, x, B, nx, radius, hops, flux_edges, face_flux, stream);
+}
+
+int fluxgnn_forward_ring_tc(const void* packed_tc, int num_layers, int precision, const float* state,
+                            const float* x, int B, int nx, int radius, float* flux_edges, float* face_flux,
+                            void* stream) {
+    if (precision != FLUXGNN_TC_TF32X3 && precision != FLUXGNN_TC_TF32)
+        return set_error(FLUXGNN_EINVAL, "forward_ring_tc: precision must be FLUXGNN_TC_TF32X3 or FLUXGNN_TC_TF32");
+    return forward_ring_impl(precision, packed_tc, num_layers, state, x, B, nx, radius, 1, flux_edges, face_flux,
+                             stream);
 }
 
 // workspace = [state ping-pong buffer][FFT scratch]; both absent for nx <= 128
@@ -204,10 +263,13 @@ size_t fluxgnn_baseline_workspace_bytes(int B, int nx) {
     return (size_t)B * 3 * nx * sizeof(float) + fluxgnn_poisson_workspace_bytes(B, nx);
 }
 
-int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* state_in, float* state_out,
-                           const float* x, const double* gtab, int B, int nx, double length, int radius,
-                           float c, float dt, int steps, int record_every, float* traj, void* workspace,
-                           void* stream_) {
+}  // extern "C"
+
+// precision: 0 = fp32 (FP32-pipe kernel), 1 = tf32x3, 2 = tf32 (tensor-core kernel)
+static int hybrid_rollout_impl(int precision, const void* packed, int num_layers, const float* state_in,
+                               float* state_out, const float* x, const double* gtab, int B, int nx, double length,
+                               int radius, float c, float dt, int steps, int record_every, float* traj,
+                               void* workspace, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_model(packed, num_layers, B, nx, radius);
     if (rc != FLUXGNN_OK) return rc;
@@ -228,6 +290,12 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* stat
     int fast = 0;
     rc = plan_tiles(a, &fast);
     if (rc != FLUXGNN_OK) return rc;
+    if (precision != 0) {
+        rc = tc_shape_ok(a.whole_ic, nx, radius);
+        if (rc != FLUXGNN_OK) return rc;
+        a.tc_parts = (precision == FLUXGNN_TC_TF32X3) ? 2 : 1;
+        fast = -radius;                                   // launch_tiles(): negative = tensor kernel
+    }
 
     if (a.whole_ic) {
         // whole ICs per tile: the complete rollout is ONE persistent launch, state in shared memory
@@ -261,6 +329,26 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* stat
         src = dst;
     }
     return FLUXGNN_OK;
+}
+
+extern "C" {
+
+int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* state_in, float* state_out,
+                           const float* x, const double* gtab, int B, int nx, double length, int radius,
+                           float c, float dt, int steps, int record_every, float* traj, void* workspace,
+                           void* stream) {
+    return hybrid_rollout_impl(0, packed, num_layers, state_in, state_out, x, gtab, B, nx, length, radius, c, dt,
+                               steps, record_every, traj, workspace, stream);
+}
+
+int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precision, const float* state_in,
+                              float* state_out, const float* x, const double* gtab, int B, int nx, double length,
+                              int radius, float c, float dt, int steps, int record_every, float* traj,
+                              void* workspace, void* stream) {
+    if (precision != FLUXGNN_TC_TF32X3 && precision != FLUXGNN_TC_TF32)
+        return set_error(FLUXGNN_EINVAL, "hybrid_rollout_tc: precision must be FLUXGNN_TC_TF32X3 or FLUXGNN_TC_TF32");
+    return hybrid_rollout_impl(precision, packed_tc, num_layers, state_in, state_out, x, gtab, B, nx, length, radius,
+                               c, dt, steps, record_every, traj, workspace, stream);
 }
 
 int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const double* gtab, int B, int nx,

@@ -204,4 +204,57 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_in, const float*
     }
 }
 
+// Tensor-path stream: small block + pre-swizzled UMMA operand images (layout: common.cuh)
+__global__ void pack_weights_tc_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
+                                       const float* __restrict__ w_upd, const float* __restrict__ b_upd,
+                                       const float* __restrict__ w_e1, const float* __restrict__ b_e1,
+                                       const float* __restrict__ w_e2, const float* __restrict__ b_e2,
+                                       int L, float* __restrict__ packed) {
+    const size_t total = packed_tc_floats(L);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (idx < (size_t)SmallParams::count) {
+            const int o = (int)idx;
+            if (o < SmallParams::b_in) {
+                const int f = o / kH, n = o % kH;
+                v = w_in[n * kF + f];
+            } else if (o < SmallParams::b_upd) {
+                v = b_in[o - SmallParams::b_in];
+            } else if (o < SmallParams::b_e1) {
+                const int q = o - SmallParams::b_upd;
+                v = (q < L * kH) ? b_upd[q] : 0.f;
+            } else if (o < SmallParams::w_e2) {
+                v = b_e1[o - SmallParams::b_e1];
+            } else if (o < SmallParams::b_e2) {
+                v = w_e2[o - SmallParams::w_e2];
+            } else if (o == SmallParams::b_e2) {
+                v = b_e2[0];
+            }
+        } else {
+            const size_t q = idx - SmallParams::count;
+            const int layer = (int)(q / ((size_t)kTcUnitsPerLayer * kTcUnitFloats));
+            const int u = (int)((q / kTcUnitFloats) % kTcUnitsPerLayer);
+            const int within = (int)(q % kTcUnitFloats);
+            const int row = within >> 5;                        // output feature n (128 bytes per row)
+            const int chunk_phys = (within & 31) >> 2, e = within & 3;
+            const int kk = ((chunk_phys ^ (row & 7)) << 2) | e; // k inside the 32-wide K-block
+            const int kb = u >> 2, blk = (u >> 1) & 1, part = u & 1;
+            const float* W = (layer < L) ? (w_upd + (size_t)layer * kH * 2 * kH) : w_e1;
+            const float w = W[(size_t)row * 2 * kH + (blk == 0 ? kH : 0) + kb * 32 + kk];
+            uint32_t hi_bits;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi_bits) : "f"(w));
+            const float hi = __uint_as_float(hi_bits);
+            if (part == 0) {
+                v = hi;
+            } else {
+                uint32_t lo_bits;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_bits) : "f"(w - hi));
+                v = __uint_as_float(lo_bits);
+            }
+        }
+        packed[idx] = v;
+    }
+}
+
 }  // namespace fluxgnn

@@ -25,9 +25,13 @@ struct HybridArgs {
     int do_update;             // 0: forward only; 1: finite-volume update (+ field solve when whole_ic)
     int steps, record_every;   // steps > 1 only for whole-IC update mode
     float c, dt;               // float32(dt/dx), float32(dt)
+    int tc_parts;              // tensor path only: 2 = tf32x3 (hi/lo split), 1 = plain tf32
 };
 
 // fast_radius 1..4 selects the compile-time-radius window path; 0 the generic path.
 cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream);
+
+// Tensor-core (tcgen05) variant, hybrid_tc_kernel.cu: radius 1..4, a.hops == 1, segments of 32/64/128 rows.
+cudaError_t launch_hybrid_tc_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream);
 
 }  // namespace fluxgnn

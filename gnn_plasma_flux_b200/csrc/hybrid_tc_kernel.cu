@@ -1,0 +1,417 @@
+// Tensor-core variant of the fused hybrid step (sm_100a: tcgen05.mma + TMEM + bulk-copy TMA).
+//
+// Same tile structure, algebra and finite-volume / field-solve tail as the FP32-pipe
+// kernel (hybrid_kernel_impl.cuh); only the five [128 x 128] x [128 x 256] contractions
+// per step move to the 5th-generation tensor cores (src/flux_gnn.py:60,66 of the reference).
+//
+// The product is issued TRANSPOSED, D^T[n][i] = sum_k W[n][k] h[i][k]: the weight half is
+// the UMMA "A" operand (M = 128 output features), the activations are the "B" operand
+// (N = 128 tile rows), and the accumulator lands in TMEM with lane = feature, column = row.
+// A thread that owns TMEM lane n therefore sees every row i of its feature in its own
+// registers, so the +-r neighbour window of the message-passing mean needs no shuffles and
+// no shared-memory round trip.  D_Z = W[:, H:] h lives in TMEM columns [0,128),
+// D_Y = W[:, :H] h in [128,256).
+//
+// Precision modes (HybridArgs::tc_parts):
+//   2  "tf32x3": h = h_hi + h_lo, W = W_hi + W_lo (each part a TF32 number);
+//                D = W_hi h_hi + W_hi h_lo + W_lo h_hi, fp32 accumulation -> fp32-level accuracy
+//   1  "tf32"  : D = tf32(W) tf32(h) (looser, documented tolerance)
+//
+// Warp roles (320 threads): warps 0-7 epilogue/compute (two warpgroups, each TMEM lane
+// quadrant x half of the rows), warp 8 weight producer (cp.async.bulk of pre-swizzled 16 KiB
+// operand images), warp 9 TMEM allocator + single-thread UMMA issuer.
+#include "common.cuh"
+#include "hybrid_kernel.cuh"
+
+namespace fluxgnn {
+
+namespace {
+
+constexpr int kTcStages = 4;
+constexpr int kEpiThreads = 256;
+constexpr int kProducerWarp = 8, kMmaWarp = 9;
+constexpr int kTcThreads = kEpiThreads + 64;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColZ = 0, kColY = 128;
+
+struct __align__(1024) TcSmem {
+    float Bhi[4][kTileRows * 32];        // activations, hi part: 4 K-blocks of [128 rows][32 k], SW128 K-major
+    float Blo[4][kTileRows * 32];        // activations, lo part (tf32x3 only)
+    float Ws[kTcStages][kTcUnitFloats];  // streamed weight operand images
+    float small[SmallParams::count];
+    float sN[kTileRows], sU[kTileRows], sE[kTileRows], sX[kTileRows];
+    float sF[kTileRows], sRho[kTileRows];
+    float edge[2][kTileRows];            // per row: fwd (row j -> j+1) and bwd (row j -> j-1) dot products
+    double gtab[kTileRows];
+    int rowIC[kTileRows];
+    int rowCell[kTileRows];
+    short prevRow[kTileRows], nextRow[kTileRows];
+    uint64_t full[kTcStages], empty[kTcStages];
+    uint64_t act_ready, acc_ready;
+    uint32_t tmem_base;
+};
+static_assert(sizeof(TcSmem) + 1024 <= 227 * 1024, "tensor tile does not fit shared memory");
+
+struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+    }
+};
+
+// byte offset of activation element (row i, feature k) inside Bhi / Blo
+__device__ __forceinline__ uint32_t act_off(int i, int k) {
+    return (uint32_t)((k >> 5) * (kTileRows * 128) + i * 128 + ((((k & 31) >> 2) ^ (i & 7)) << 4) + ((k & 3) << 2));
+}
+
+}  // namespace
+
+template <int R>
+__global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nx = a.nx;
+    const int parts = a.tc_parts;
+
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], 1);
+        }
+        mbar_init(&S.act_ready, kEpiThreads);
+        mbar_init(&S.acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&S.tmem_base, kTmemCols);
+    for (int i = tid; i < SmallParams::count; i += kTcThreads) S.small[i] = a.packed[i];
+    if (a.whole_ic && a.do_update)
+        for (int i = tid; i < nx; i += kTcThreads) S.gtab[i] = a.gtab[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    const int my_tiles = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int layers = a.L + 1;
+
+    if (warp == kProducerWarp) {
+        // ---------------- weight producer ------------------------------------------------
+        if (lane == 0) {
+            const float* stream = a.packed + SmallParams::count;
+            Ring r;
+            for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
+                for (int layer = 0; layer < layers; ++layer) {
+                    for (int u = 0; u < kTcUnitsPerLayer; ++u) {
+                        if (parts == 1 && (u & 1)) continue;          // plain tf32: no lo units
+                        mbar_wait(&S.empty[r.stage], r.phase ^ 1);
+                        mbar_arrive_expect_tx(&S.full[r.stage], kTcUnitFloats * 4);
+                        bulk_g2s(S.Ws[r.stage], stream + ((size_t)layer * kTcUnitsPerLayer + u) * kTcUnitFloats,
+                                 kTcUnitFloats * 4, &S.full[r.stage]);
+                        r.advance();
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ---------------- UMMA issuer (one thread) ---------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, 128);
+            const uint32_t bhi = smem_u32(S.Bhi), blo = smem_u32(S.Blo);
+            Ring r;
+            uint32_t act_phase = 0;
+            for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
+                for (int layer = 0; layer < layers; ++layer) {
+                    mbar_wait(&S.act_ready, act_phase);
+                    act_phase ^= 1;
+                    tc_fence_after();
+                    for (int kb = 0; kb < 4; ++kb) {
+                        for (int blk = 0; blk < 2; ++blk) {
+                            const uint32_t d = tmem + (blk == 0 ? kColZ : kColY);
+                            // hi weights x (hi [+ lo] activations)
+                            mbar_wait(&S.full[r.stage], r.phase);
+                            tc_fence_after();
+                            uint32_t wbase = smem_u32(S.Ws[r.stage]);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = umma_desc_sw128(wbase + ks * 32);
+                                umma_tf32(d, ad, umma_desc_sw128(bhi + kb * (kTileRows * 128) + ks * 32), idesc,
+                                          (kb | ks) != 0);
+                                if (parts == 2)
+                                    umma_tf32(d, ad, umma_desc_sw128(blo + kb * (kTileRows * 128) + ks * 32), idesc, 1);
+                            }
+                            umma_commit(&S.empty[r.stage]);
+                            r.advance();
+                            if (parts == 2) {
+                                // lo weights x hi activations
+                                mbar_wait(&S.full[r.stage], r.phase);
+                                tc_fence_after();
+                                wbase = smem_u32(S.Ws[r.stage]);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_tf32(d, umma_desc_sw128(wbase + ks * 32),
+                                              umma_desc_sw128(bhi + kb * (kTileRows * 128) + ks * 32), idesc, 1);
+                                umma_commit(&S.empty[r.stage]);
+                                r.advance();
+                            }
+                        }
+                    }
+                    umma_commit(&S.acc_ready);
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue / compute warps ---------------------------------------
+        const int q = warp & 3, hsel = warp >> 2;
+        const int n = 32 * q + lane;                          // this thread's feature = TMEM lane
+        const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+        unsigned char* const bhi_bytes = reinterpret_cast<unsigned char*>(S.Bhi);
+        unsigned char* const blo_bytes = reinterpret_cast<unsigned char*>(S.Blo);
+        const float inv_deg = 1.0f / (float)(2 * R);
+        const int seg = a.whole_ic ? nx : kTileRows;          // periodic segment inside the tile (multiple of 32)
+        uint32_t acc_phase = 0;
+
+        auto store_act = [&](int i, float h) {
+            const uint32_t off = act_off(i, n);
+            const float hi = to_tf32(h);
+            *reinterpret_cast<float*>(bhi_bytes + off) = hi;
+            if (parts == 2) *reinterpret_cast<float*>(blo_bytes + off) = to_tf32(h - hi);
+        };
+
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            // ---- row bookkeeping + state load (as in the FP32-pipe kernel) ----------------
+            if (tid < kTileRows) {
+                const int j = tid;
+                int ic, cell, prev = (j - 1) & (kTileRows - 1), next = (j + 1) & (kTileRows - 1);
+                bool live, owned;
+                if (a.whole_ic) {
+                    const int slot = j / nx;
+                    cell = j - slot * nx;
+                    ic = tile * a.ics_per_tile + slot;
+                    live = ic < a.B;
+                    owned = live;
+                    prev = (cell == 0) ? j + nx - 1 : j - 1;
+                    next = (cell == nx - 1) ? j - nx + 1 : j + 1;
+                } else {
+                    ic = tile / a.tiles_per_ic;
+                    const int t = tile - ic * a.tiles_per_ic;
+                    const long long gcell = (long long)t * a.valid - a.halo + j;
+                    cell = (int)(((gcell % nx) + nx) % nx);
+                    live = true;
+                    owned = (j >= a.halo) && (j < a.halo + a.valid) && ((long long)t * a.valid + (j - a.halo) < nx);
+                }
+                S.rowIC[j] = owned ? ic : -1;
+                S.rowCell[j] = cell;
+                S.prevRow[j] = (short)prev;
+                S.nextRow[j] = (short)next;
+                float vn = 0.f, vu = 0.f, ve = 0.f, vx = 0.f;
+                if (live) {
+                    const float* st = a.state_in + (size_t)ic * 3 * nx + cell;
+                    vn = __ldg(st);
+                    vu = __ldg(st + nx);
+                    ve = __ldg(st + 2 * (size_t)nx);
+                    vx = __ldg(a.x + cell);
+                }
+                S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
+            }
+            named_sync(1, kEpiThreads);
+
+            for (int step = 0; step < a.steps; ++step) {
+                // ---- input MLP (src/flux_gnn.py:49): feature n, rows of this warpgroup's half ----
+                {
+                    const float w0 = S.small[SmallParams::w_in + 0 * kH + n];
+                    const float w1 = S.small[SmallParams::w_in + 1 * kH + n];
+                    const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
+                    const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
+                    const float b = S.small[SmallParams::b_in + n];
+#pragma unroll 8
+                    for (int jj = 0; jj < 64; ++jj) {
+                        const int i = 64 * hsel + jj;
+                        float v = fmaf(w0, S.sN[i], b);
+                        v = fmaf(w1, S.sU[i], v);
+                        v = fmaf(w2, S.sE[i], v);
+                        v = fmaf(w3, S.sX[i], v);
+                        store_act(i, fmaxf(v, 0.f));
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(&S.act_ready);
+
+                for (int layer = 0; layer < layers; ++layer) {
+                    mbar_wait(&S.acc_ready, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                    const bool is_edge = (layer == a.L);
+                    const float bias = S.small[(is_edge ? SmallParams::b_e1 : SmallParams::b_upd + layer * kH) + n];
+                    const float w_out = S.small[SmallParams::w_e2 + n];
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        const int i0 = 32 * (2 * hsel + c);
+                        const int seg0 = (i0 / seg) * seg;
+                        const int cl = (i0 == seg0) ? i0 - 4 + seg : i0 - 4;
+                        const int cr = (i0 + 32 == seg0 + seg) ? i0 + 32 - seg : i0 + 32;
+                        float y[32], zc[32], zl[4], zr[4];
+                        tmem_ld32(tlane + kColY + i0, y);
+                        tmem_ld32(tlane + kColZ + i0, zc);
+                        tmem_ld4(tlane + kColZ + cl, zl);
+                        tmem_ld4(tlane + kColZ + cr, zr);
+                        tc_wait_ld();
+                        float zw[40];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { zw[t] = zl[t]; zw[36 + t] = zr[t]; }
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) zw[4 + t] = zc[t];
+                        if (!is_edge) {
+                            // h'_i = relu(Y_i + b + mean_{0<|k|<=R} Z_{i+k})   (src/flux_gnn.py:55-60)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float s = zw[4 + j + 1] + zw[4 + j - 1];
+#pragma unroll
+                                for (int k = 2; k <= R; ++k) { s += zw[4 + j + k]; s += zw[4 + j - k]; }
+                                store_act(i0 + j, fmaxf(fmaf(s, inv_deg, y[j] + bias), 0.f));
+                            }
+                        } else {
+                            // edge readout (src/flux_gnn.py:63-66): this feature's term of the two dot products
+                            // of row i, written feature-transposed so that one thread can sum a row:
+                            //   fwd (row i, col i+1): w2[n] relu(P_i + b1 + Q_{i+1});  bwd (row i, col i-1)
+                            float* fbuf = reinterpret_cast<float*>(S.Bhi);
+                            float* gbuf = reinterpret_cast<float*>(S.Blo);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int i = i0 + j;
+                                const float p = y[j] + bias;
+                                fbuf[i * kH + (n ^ (i & 31))] = w_out * fmaxf(p + zw[4 + j + 1], 0.f);
+                                gbuf[i * kH + (n ^ (i & 31))] = w_out * fmaxf(p + zw[4 + j - 1], 0.f);
+                            }
+                        }
+                    }
+                    if (!is_edge) {
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(&S.act_ready);
+                    }
+                }
+
+                // ---- reduce the edge terms over the 128 features: thread (row, which) ------------
+                named_sync(1, kEpiThreads);
+                {
+                    const int row = tid & (kTileRows - 1), which = tid >> 7;
+                    const float* buf = reinterpret_cast<const float*>(which ? S.Blo : S.Bhi) + row * kH;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+                    for (int m = 0; m < kH; m += 4) {
+                        s0 += buf[(m + 0) ^ (row & 31)];
+                        s1 += buf[(m + 1) ^ (row & 31)];
+                        s2 += buf[(m + 2) ^ (row & 31)];
+                        s3 += buf[(m + 3) ^ (row & 31)];
+                    }
+                    S.edge[which][row] = (s0 + s1) + (s2 + s3);
+                }
+                named_sync(1, kEpiThreads);
+
+                // ---- per row: face flux (src/hybrid_solver.py:45-48) ----------------------------
+                float n_new = 0.f, u_new = 0.f;
+                if (tid < kTileRows) {
+                    const int j = tid, jn = S.nextRow[j];
+                    const float b2 = S.small[SmallParams::b_e2];
+                    const float fwd = S.edge[0][j] + b2;          // edge (row j, col j+1)
+                    const float bwd = S.edge[1][jn] + b2;         // edge (row j+1, col j)
+                    const float face = 0.5f * (fwd + bwd);
+                    const int ic = S.rowIC[j], cell = S.rowCell[j];
+                    if (a.flux_edges != nullptr && ic >= 0) {
+                        float* fe = a.flux_edges + (size_t)ic * 2 * nx + cell;
+                        fe[0] = fwd;
+                        fe[nx] = bwd;
+                    }
+                    if (a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
+                    S.sF[j] = face;
+                }
+                if (!a.do_update) continue;
+                named_sync(1, kEpiThreads);
+
+                // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
+                if (tid < kTileRows) {
+                    const int j = tid, p = S.prevRow[j];
+                    const float u = S.sU[j], up = S.sU[p];
+                    n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
+                    const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
+                    const float fup = __fmul_rn(__fmul_rn(0.5f, up), up);
+                    const float u_adv = __fsub_rn(u, __fmul_rn(a.c, __fsub_rn(fu, fup)));
+                    u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, S.sE[j]));
+                }
+                if (!a.whole_ic) {
+                    if (tid < kTileRows && S.rowIC[tid] >= 0) {
+                        float* so = a.state_out + (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+                        so[0] = n_new;
+                        so[nx] = u_new;
+                    }
+                    continue;
+                }
+                named_sync(1, kEpiThreads);
+                if (tid < kTileRows) {
+                    S.sN[tid] = n_new;
+                    S.sU[tid] = u_new;
+                    S.sRho[tid] = __fsub_rn(n_new, 1.0f);
+                }
+                named_sync(1, kEpiThreads);
+                // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
+                {
+                    const int row = tid >> 1, half = tid & 1;
+                    const int cell = S.rowCell[row], base = row - cell;
+                    double e = 0.0;
+                    for (int i = half; i < nx; i += 2) {
+                        int d = cell - i;
+                        if (d < 0) d += nx;
+                        e = fma(S.gtab[d], (double)S.sRho[base + i], e);
+                    }
+                    e += __shfl_xor_sync(0xffffffffu, e, 1);
+                    if (half == 0) S.sE[row] = (float)e;
+                }
+                named_sync(1, kEpiThreads);
+                if (tid < kTileRows && S.rowIC[tid] >= 0) {
+                    const size_t off = (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+                    if (step == a.steps - 1) {
+                        a.state_out[off] = S.sN[tid];
+                        a.state_out[off + nx] = S.sU[tid];
+                        a.state_out[off + 2 * (size_t)nx] = S.sE[tid];
+                    }
+                    if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
+                        float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
+                        tr[0] = S.sN[tid];
+                        tr[nx] = S.sU[tid];
+                        tr[2 * (size_t)nx] = S.sE[tid];
+                    }
+                }
+            }   // steps
+            named_sync(1, kEpiThreads);
+        }       // tiles
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int R>
+static cudaError_t launch_tc_one(const HybridArgs& a, int grid, cudaStream_t stream) {
+    const int smem = (int)sizeof(TcSmem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tc_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    hybrid_tc_kernel<R><<<grid, kTcThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hybrid_tc_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream) {
+    switch (radius) {
+        case 1: return launch_tc_one<1>(a, grid, stream);
+        case 2: return launch_tc_one<2>(a, grid, stream);
+        case 3: return launch_tc_one<3>(a, grid, stream);
+        case 4: return launch_tc_one<4>(a, grid, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace fluxgnn

@@ -35,8 +35,7 @@ class FluxGNN(nn.Module):
         self.input_mlp = _linear_relu(input_dim, hidden_dim)
         self.update_mlps = nn.ModuleList(_linear_relu(2 * hidden_dim, hidden_dim) for _ in range(num_layers))
         self.edge_mlp = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, 1))
-        self._packed = None
-        self._packed_key = None
+        self._packed = {}            # layout name -> (key, tensor)
 
     # ------------------------------------------------------------------ weights
     def _check_supported(self):
@@ -45,9 +44,10 @@ class FluxGNN(nn.Module):
                 f"the sm_100a kernel supports input_dim={_lib.INPUT_DIM}, hidden_dim={_lib.HIDDEN}, "
                 f"1..{_lib.MAX_LAYERS} layers; got ({self.input_dim}, {self.hidden_dim}, {self.num_layers})")
 
-    def packed_weights(self) -> torch.Tensor:
-        """Weights in the kernel's streaming layout (device float32), repacked only
-        when a parameter was replaced, moved or modified in place."""
+    def packed_weights(self, layout: str = "fp32") -> torch.Tensor:
+        """Weights in a kernel's streaming layout (device float32), repacked only when a
+        parameter was replaced, moved or modified in place.  layout "fp32": K-major halves
+        for the FP32-pipe kernel; "tc": pre-swizzled TF32 hi/lo UMMA operand images."""
         self._check_supported()
         params = list(self.parameters())
         dev = params[0].device
@@ -55,7 +55,8 @@ class FluxGNN(nn.Module):
             raise _lib.FluxGNNError("FluxGNN parameters are on %s: the forward pass needs a CUDA device "
                                     "(there is no CPU fallback)" % dev)
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is None or key != self._packed_key:
+        hit = self._packed.get(layout)
+        if hit is None or hit[0] != key:
             with torch.cuda.device(dev), torch.no_grad():
                 f32 = lambda t: t.detach().to(torch.float32).contiguous()
                 w_upd = torch.stack([f32(m[0].weight) for m in self.update_mlps]).contiguous()
@@ -63,35 +64,49 @@ class FluxGNN(nn.Module):
                 small = [f32(self.input_mlp[0].weight), f32(self.input_mlp[0].bias), w_upd, b_upd,
                          f32(self.edge_mlp[0].weight), f32(self.edge_mlp[0].bias),
                          f32(self.edge_mlp[2].weight), f32(self.edge_mlp[2].bias)]
-                nbytes = _lib.lib().fluxgnn_packed_weight_bytes(self.num_layers)
-                packed = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+                size_fn, pack_fn = ((_lib.lib().fluxgnn_packed_tc_weight_bytes, _lib.lib().fluxgnn_pack_weights_tc)
+                                    if layout == "tc" else
+                                    (_lib.lib().fluxgnn_packed_weight_bytes, _lib.lib().fluxgnn_pack_weights))
+                packed = torch.empty(size_fn(self.num_layers) // 4, dtype=torch.float32, device=dev)
                 stream = torch.cuda.current_stream(dev).cuda_stream
-                _lib.check(_lib.lib().fluxgnn_pack_weights(*[t.data_ptr() for t in small], self.num_layers,
-                                                           packed.data_ptr(), stream), "fluxgnn_pack_weights")
+                _lib.check(pack_fn(*[t.data_ptr() for t in small], self.num_layers, packed.data_ptr(), stream),
+                           "fluxgnn_pack_weights" + ("_tc" if layout == "tc" else ""))
                 # `small` must outlive the (asynchronous) packing kernel: same-stream
                 # allocator reuse is ordered after it, so dropping the references is safe.
-            self._packed, self._packed_key = packed, key
-        return self._packed
+            hit = (key, packed)
+            self._packed[layout] = hit
+        return hit[1]
 
     # ------------------------------------------------------------------ structured entry points
     def ring_fluxes(self, state: torch.Tensor, x: torch.Tensor, radius: int = 1, hops: int | None = None,
-                    want_edges: bool = True, want_face: bool = False):
-        """state [B,3,nx] (CUDA float32), x [nx] -> (flux_edges [B, 2*hops*nx] | None, face_flux [B,nx] | None)."""
+                    want_edges: bool = True, want_face: bool = False, precision: str = "fp32"):
+        """state [B,3,nx] (CUDA float32), x [nx] -> (flux_edges [B, 2*hops*nx] | None, face_flux [B,nx] | None).
+        precision 'tf32x3' / 'tf32' runs the tensor-core kernel (hop 1 only)."""
         if state.dim() != 3 or state.shape[1] != 3:
             raise ValueError(f"state must be [B,3,nx], got {tuple(state.shape)}")
-        packed = self.packed_weights()
+        tensor_path = precision != "fp32"
+        if tensor_path and precision not in _lib.TC_PRECISIONS:
+            raise ValueError(f"precision must be 'fp32', 'tf32x3' or 'tf32', got {precision!r}")
+        packed = self.packed_weights("tc" if tensor_path else "fp32")
         state = state.to(device=packed.device, dtype=torch.float32).contiguous()
         x = x.to(device=packed.device, dtype=torch.float32).contiguous()
         B, _, nx = state.shape
-        hops = radius if hops is None else hops
+        hops = (1 if tensor_path else radius) if hops is None else hops
         with torch.cuda.device(packed.device):
             edges = torch.empty(B, 2 * hops * nx, dtype=torch.float32, device=packed.device) if want_edges else None
             face = torch.empty(B, nx, dtype=torch.float32, device=packed.device) if want_face else None
             stream = torch.cuda.current_stream(packed.device).cuda_stream
-            _lib.check(_lib.lib().fluxgnn_forward_ring(
-                packed.data_ptr(), self.num_layers, state.data_ptr(), x.data_ptr(), B, nx, radius, hops,
-                edges.data_ptr() if want_edges else None, face.data_ptr() if want_face else None, stream),
-                "fluxgnn_forward_ring")
+            outs = (edges.data_ptr() if want_edges else None, face.data_ptr() if want_face else None, stream)
+            if tensor_path:
+                if hops != 1:
+                    raise NotImplementedError("the tensor-core forward emits hop-1 edges only")
+                _lib.check(_lib.lib().fluxgnn_forward_ring_tc(
+                    packed.data_ptr(), self.num_layers, _lib.TC_PRECISIONS[precision], state.data_ptr(), x.data_ptr(),
+                    B, nx, radius, *outs), "fluxgnn_forward_ring_tc")
+            else:
+                _lib.check(_lib.lib().fluxgnn_forward_ring(
+                    packed.data_ptr(), self.num_layers, state.data_ptr(), x.data_ptr(), B, nx, radius, hops, *outs),
+                    "fluxgnn_forward_ring")
         return edges, face
 
     # ------------------------------------------------------------------ reference API

@@ -30,7 +30,7 @@ from .flux_gnn import FluxGNN
 
 class HybridSolver:
     def __init__(self, model_path, radius, nx=64, length=2 * math.pi, dt=5e-3, t_end=1.0, device="cuda", *,
-                 graph_radius=None, model=None):
+                 graph_radius=None, model=None, precision="fp32"):
         self.device = device
         self.baseline = BaselineSolver(nx=nx, length=length, dt=dt, t_end=t_end, device=device)
         if model is None:
@@ -41,6 +41,9 @@ class HybridSolver:
         self.model.eval()
         self.radius = radius
         self.graph_radius = 1 if graph_radius is None else int(graph_radius)
+        if precision != "fp32" and precision not in _lib.TC_PRECISIONS:
+            raise ValueError(f"precision must be 'fp32', 'tf32x3' or 'tf32', got {precision!r}")
+        self.precision = precision
         self._pinned = {}
 
     # ------------------------------------------------------------------ device-resident API
@@ -50,7 +53,8 @@ class HybridSolver:
         base = self.baseline
         if state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != base.nx:
             raise ValueError(f"state must be [B,3,{base.nx}], got {tuple(state.shape)}")
-        packed = self.model.packed_weights()
+        tensor_path = self.precision != "fp32"
+        packed = self.model.packed_weights("tc" if tensor_path else "fp32")
         dev = packed.device
         if state.device != dev or state.dtype != torch.float32 or not state.is_contiguous():
             state = state.to(device=dev, dtype=torch.float32).contiguous()
@@ -64,8 +68,11 @@ class HybridSolver:
             ws_bytes = _lib.lib().fluxgnn_hybrid_workspace_bytes(B, nx)
             work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.lib().fluxgnn_hybrid_rollout(
-                packed.data_ptr(), self.model.num_layers, state.data_ptr(), out.data_ptr(),
+            head = ((packed.data_ptr(), self.model.num_layers, _lib.TC_PRECISIONS[self.precision]) if tensor_path
+                    else (packed.data_ptr(), self.model.num_layers))
+            entry = _lib.lib().fluxgnn_hybrid_rollout_tc if tensor_path else _lib.lib().fluxgnn_hybrid_rollout
+            _lib.check(entry(
+                *head, state.data_ptr(), out.data_ptr(),
                 x_dev.data_ptr(), gtab.data_ptr() if gtab is not None else None, B, nx, base.length,
                 self.graph_radius,
                 float(np.float32(base.dt / base.dx)), float(np.float32(base.dt)),

@@ -131,6 +131,38 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers,
                            int steps, int record_every, float* traj,
                            void* workspace, void* stream);
 
+/* ---- tensor-core variant of the same step (tcgen05 / TMEM) ---------------------
+ * The five 128x128x256 contractions of src/flux_gnn.py:60,66 run on the tensor cores;
+ * everything else (window mean, ReLU, edge readout, finite-volume update, field solve)
+ * is unchanged.  precision:
+ *   FLUXGNN_TC_TF32X3  h and W are split into two TF32 parts and three products are
+ *                      accumulated in fp32: fp32-level accuracy (same parity gates as
+ *                      fluxgnn_hybrid_rollout).
+ *   FLUXGNN_TC_TF32    one TF32 product: ~1e-3 relative flux error, for throughput
+ *                      studies only (tolerance stated in DESIGN.md).
+ * packed_tc comes from fluxgnn_pack_weights_tc (same inputs as fluxgnn_pack_weights;
+ * the stream holds pre-swizzled UMMA operand images, hi and lo parts).
+ * Supported: radius <= 4; nx in {32, 64, 128} or nx > 128; other shapes -> FLUXGNN_EUNSUP
+ * (the caller decides to use the fp32 entry point; there is no silent fallback). */
+#define FLUXGNN_TC_TF32X3 1
+#define FLUXGNN_TC_TF32   2
+size_t fluxgnn_packed_tc_weight_bytes(int num_layers);
+int fluxgnn_pack_weights_tc(const float* w_in, const float* b_in,
+                            const float* w_upd, const float* b_upd,
+                            const float* w_e1, const float* b_e1,
+                            const float* w_e2, const float* b_e2,
+                            int num_layers, void* packed_tc, void* stream);
+int fluxgnn_forward_ring_tc(const void* packed_tc, int num_layers, int precision,
+                            const float* state, const float* x,
+                            int B, int nx, int radius,
+                            float* flux_edges /* [B][2*nx], hop 1 */, float* face_flux, void* stream);
+int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precision,
+                              const float* state_in, float* state_out,
+                              const float* x, const double* gtab,
+                              int B, int nx, double length, int radius, float c, float dt,
+                              int steps, int record_every, float* traj,
+                              void* workspace, void* stream);
+
 /* ---- BaselineSolver.step / .run ------------------------------------------------
  * Replaces src/baseline_solver.py:70-118: upwind continuity flux n*u,
  * left-differenced u^2/2, viscous Laplacian, forward Euler, field solve.

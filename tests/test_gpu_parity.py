@@ -26,9 +26,10 @@ def model(weights, built_lib):
     return m.to("cuda").eval()
 
 
-def make_solver(model, nx, dt, graph_radius=None, radius=1):
+def make_solver(model, nx, dt, graph_radius=None, radius=1, precision="fp32"):
     from gnn_plasma_flux_b200 import HybridSolver
-    return HybridSolver(None, radius, nx=nx, dt=dt, device="cuda", graph_radius=graph_radius, model=model)
+    return HybridSolver(None, radius, nx=nx, dt=dt, device="cuda", graph_radius=graph_radius, model=model,
+                        precision=precision)
 
 
 # ----------------------------------------------------------------------------- weights
@@ -303,6 +304,82 @@ def test_full_size_c2_properties(model, weights):
     m0 = ics[:, 0].astype(np.float64).sum(-1)
     mT = final[:, 0].double().sum(-1).cpu().numpy()
     assert np.abs(mT - m0).max() <= 50 * nx * np.finfo(np.float32).eps
+
+
+# ----------------------------------------------------------------------------- tensor-core path
+TF32_STEP_TOL = 1e-5          # plain TF32: state-level tolerance per step (flux error ~1e-3 enters as c*dF)
+TF32_FLUX_TOL = 2e-2          # plain TF32: relative error of the GNN flux itself
+TF32X3_FLUX_TOL = 2e-5        # 3xTF32 split: flux error at fp32 rounding level
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("nx,radius", [(64, 1), (64, 3), (32, 2), (128, 4), (1024, 2), (300, 3)])
+def test_tc_flux_vs_fp64_oracle(model, weights, precision, nx, radius):
+    """Edge fluxes of the tcgen05 kernel vs the fp64 restatement, beside the fp32 kernel's own error."""
+    B = 6
+    grid = P.Grid(nx=nx)
+    state = np.stack([P.initial_condition(grid, seed=s) for s in range(B)])
+    x32 = grid.x.astype(np.float32)
+    dev, xd = torch.from_numpy(state).cuda(), torch.from_numpy(x32).cuda()
+    ref = batched.edge_fluxes(weights, torch.from_numpy(state).double(), torch.from_numpy(x32), radius, hops=1).numpy()
+    e_tc, f_tc = model.ring_fluxes(dev, xd, radius=radius, want_face=True, precision=precision)
+    e_32, _ = model.ring_fluxes(dev, xd, radius=radius, hops=1)
+    scale = np.abs(ref).max()
+    err_tc = np.abs(e_tc.cpu().numpy() - ref).max() / scale
+    err_32 = np.abs(e_32.cpu().numpy() - ref).max() / scale
+    print(f"flux rel err vs fp64: {precision} {err_tc:.2e}, fp32 kernel {err_32:.2e}")
+    assert err_tc <= (TF32X3_FLUX_TOL if precision == "tf32x3" else TF32_FLUX_TOL)
+    face_ref = 0.5 * (ref[:, :nx] + ref[:, nx:])
+    assert np.abs(f_tc.cpu().numpy() - face_ref).max() / scale <= (TF32X3_FLUX_TOL if precision == "tf32x3" else TF32_FLUX_TOL)
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+def test_tc_hybrid_step_and_rollout_golden(model, precision):
+    g = load_golden("g23_hybrid_c1.npz")
+    gr = load_golden("g2_hybrid_radius.npz")
+    tol = STEP_TOL if precision == "tf32x3" else TF32_STEP_TOL
+    sol = make_solver(model, 64, 5e-3, precision=precision)
+    out = sol.step(g["ics"])
+    assert P.rel_err(out, g["step1"]).max() <= tol
+    np.testing.assert_array_equal(out[:, 1], g["step1"][:, 1])                 # momentum update: no GNN, bit-exact
+    allr = sol.run(g["ics"], n_steps=30)
+    ref = np.moveaxis(g["rollout"], 0, 1)
+    for t in (1, 10, 30):
+        assert P.rel_err(allr[t], ref[t]).max() <= tol * t, t
+    for radius in (2, 3):
+        sol_r = make_solver(model, 1024, 3e-4, graph_radius=radius, precision=precision)   # window tiles
+        assert P.rel_err(sol_r.step(gr["ic_nx1024"]), gr[f"step_nx1024_r{radius}"]).max() <= tol
+        sol_r = make_solver(model, 64, 5e-3, graph_radius=radius, precision=precision)
+        assert P.rel_err(sol_r.step(g["ics"][:4]), gr[f"step_nx64_r{radius}"]).max() <= tol
+
+
+def test_tc_long_rollout_1000_steps(model):
+    """tf32x3 must pass the same 1000-step gate as the fp32 kernel; plain tf32 is reported."""
+    g6 = load_golden("g6_long_rollout.npz")
+    floor = P.rel_err(g6["ref_fp32"][:, -1], g6["fp64"][:, -1])
+    for precision in ("tf32x3", "tf32"):
+        sol = make_solver(model, 64, 1e-3, precision=precision)
+        final, _ = sol.rollout(torch.from_numpy(g6["ics"]).cuda(), 1000)
+        final = final.cpu().numpy()
+        assert np.isfinite(final).all()
+        vs64 = P.rel_err(final, g6["fp64"][:, -1])
+        vs32 = P.rel_err(final, g6["ref_fp32"][:, -1])
+        print(f"1000 steps {precision}: vs fp64 {vs64}, vs reference fp32 {vs32} (reference-vs-fp64 floor {floor})")
+        if precision == "tf32x3":
+            assert (vs64 <= np.maximum(1e-4, 2.0 * floor)).all()
+            assert (vs32 <= np.maximum(1e-4, 3.0 * floor)).all()
+        else:
+            assert (vs32 <= 2e-3).all()                                          # documented looser tolerance
+        mass0 = g6["ics"][:, 0].astype(np.float64).sum(-1)
+        assert np.abs(final[:, 0].astype(np.float64).sum(-1) - mass0).max() <= 1000 * 64 * np.finfo(np.float32).eps
+
+
+def test_tc_rejects_unsupported_shapes(model):
+    from gnn_plasma_flux_b200 import _lib
+    with pytest.raises(_lib.FluxGNNError):                                       # nx=40: no silent fallback
+        make_solver(model, 40, 5e-3, precision="tf32x3").rollout(torch.zeros(2, 3, 40, device="cuda"), 1)
+    with pytest.raises(ValueError):
+        make_solver(model, 64, 5e-3, precision="fp16")
 
 
 # ----------------------------------------------------------------------------- BaselineSolver
