@@ -178,7 +178,8 @@ def run_ours(args):
     weights = P.init_weights(0)
     model = FluxGNN(**MODEL_CONFIG)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
-    solver = HybridSolver(None, RADIUS, nx=NX, dt=DT, device=dev, graph_radius=RADIUS, model=model.to(dev))
+    solver = HybridSolver(None, RADIUS, nx=NX, dt=DT, device=dev, graph_radius=RADIUS, model=model.to(dev),
+                          precision=args.precision)
     ics = make_ics(ICS, 1000 * rank)
     K, W = args.steps, args.warmup
 
@@ -238,6 +239,34 @@ def run_ours(args):
     e2e_value = world * ICS * NX * K / float(t.item())
     state_bytes = ICS * 3 * NX * 4
 
+    # ---- the tensor-core variants of the same step, reported beside the headline ----------------
+    tensor_extra = {}
+    if not args.no_tensor_path:
+        for prec in ("tf32x3", "tf32"):
+            if prec == args.precision:
+                continue
+            tsol = HybridSolver(None, RADIUS, nx=NX, dt=DT, device=dev, graph_radius=RADIUS, model=solver.model,
+                                precision=prec)
+            ta = torch.from_numpy(ics).to(dev)
+            tb = torch.empty_like(ta)
+            for _ in range(W):
+                tsol.rollout(ta, 1, out=tb)
+                ta, tb = tb, ta
+            t_ms = 0.0
+            barrier()
+            for i in range(K):
+                flush.zero_()
+                starts[i].record(stream)
+                tsol.rollout(ta, 1, out=tb)
+                stops[i].record(stream)
+                ta, tb = tb, ta
+            barrier()
+            t_ms = sum(s_.elapsed_time(e_) for s_, e_ in zip(starts, stops))
+            tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tensor_extra[prec] = float(tt.item())
+
     line = None
     if rank == 0:
         # ---- FP32-pipe roofline of this device, measured live ------------------------------
@@ -259,8 +288,23 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         per_gpu = ICS * NX * K / (dev_ms * 1e-3)
         achieved_tf = per_gpu * FLOP_PER_CELL_EXECUTED / 1e12
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        tensor_path = {}
+        for prec, t_ms in tensor_extra.items():
+            rate = world * ICS * NX * K / (t_ms * 1e-3)
+            products = 3 if prec == "tf32x3" else 1
+            executed = rate / world * 327_680 * products / 1e12      # tensor-core FLOPs actually issued per GPU
+            tensor_path[prec] = {
+                "value": rate, "unit": UNIT, "ms_per_step": t_ms / K, "kernel": "hybrid_tc_kernel<3>",
+                "parity": ("same gates as fp32 (<=1e-5 per step, 1000-step gate; flux error vs fp64 ~4e-7)"
+                           if prec == "tf32x3" else "looser: flux error ~3e-4, state <=1e-5 per step, <=2e-3 over 1000 steps"),
+                "roofline": {"bound": "tensor", "achieved": executed, "peak": bf16_peak / 2, "unit": "TFLOP/s",
+                             "frac": executed / (bf16_peak / 2), "traffic": None,
+                             "note": f"kind::tf32, {products} UMMA product(s) per contraction; peak = measured bf16 "
+                                     "cuBLAS burst / 2 (no direct TF32 measurement in MEASURED_PEAKS.json)"}}
+        headline_kernel = "hybrid_tile_kernel<3>" if args.precision == "fp32" else "hybrid_tc_kernel<3>"
         roofline = {
-            "bound": "fp32-ffma", "kernel": "hybrid_tile_kernel<3>",
+            "bound": "fp32-ffma", "kernel": headline_kernel,
             "achieved": achieved_tf, "peak": best, "unit": "TFLOP/s", "frac": achieved_tf / best if best else None,
             "peak_source": "register-only FMA probe kernels timed in this run (fluxgnn_ffma_probe: FFMA %.1f, FFMA2 %.1f TFLOP/s); "
                            "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5" % (probe[0], probe[1]),
@@ -286,13 +330,15 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB write) between timed steps",
                        "launches_per_step": launches / K, "wall_s_incl_flush": wall},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
                     "d2h_bytes_per_step": state_bytes},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+            "tensor_path": tensor_path,
         }
+        line["config"]["precision"] = args.precision
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -369,6 +415,9 @@ def main():
     ap.add_argument("--workload", choices=["c2", "c3", "c5"], default="c2",
                     help="c2 (default) is the driver's bench line; c3/c5 are secondary single-GPU measurements")
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--precision", choices=["fp32", "tf32x3", "tf32"], default="fp32",
+                    help="kernel of the headline number: fp32 = FP32-pipe FFMA kernel (default), tf32x3/tf32 = tcgen05 kernel")
+    ap.add_argument("--no-tensor-path", action="store_true", help="skip the extra tensor-core measurements")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

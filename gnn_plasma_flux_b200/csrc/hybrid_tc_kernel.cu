@@ -17,9 +17,9 @@
 //                D = W_hi h_hi + W_hi h_lo + W_lo h_hi, fp32 accumulation -> fp32-level accuracy
 //   1  "tf32"  : D = tf32(W) tf32(h) (looser, documented tolerance)
 //
-// Warp roles (320 threads): warps 0-7 epilogue/compute (two warpgroups, each TMEM lane
-// quadrant x half of the rows), warp 8 weight producer (cp.async.bulk of pre-swizzled 16 KiB
-// operand images), warp 9 TMEM allocator + single-thread UMMA issuer.
+// Warp roles (576 threads): warps 0-15 epilogue/compute (TMEM lane quadrant = warp % 4,
+// 32-row chunk = warp / 4), warp 16 weight producer (cp.async.bulk of pre-swizzled 16 KiB
+// operand images), warp 17 TMEM allocator + single-thread UMMA issuer.
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
 
@@ -27,9 +27,9 @@ namespace fluxgnn {
 
 namespace {
 
-constexpr int kTcStages = 4;
-constexpr int kEpiThreads = 256;
-constexpr int kProducerWarp = 8, kMmaWarp = 9;
+constexpr int kTcStages = 5;
+constexpr int kEpiThreads = 512;
+constexpr int kProducerWarp = 16, kMmaWarp = 17;
 constexpr int kTcThreads = kEpiThreads + 64;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColZ = 0, kColY = 128;
@@ -59,11 +59,6 @@ struct Ring {
         if (++stage == kTcStages) { stage = 0; phase ^= 1; }
     }
 };
-
-// byte offset of activation element (row i, feature k) inside Bhi / Blo
-__device__ __forceinline__ uint32_t act_off(int i, int k) {
-    return (uint32_t)((k >> 5) * (kTileRows * 128) + i * 128 + ((((k & 31) >> 2) ^ (i & 7)) << 4) + ((k & 3) << 2));
-}
 
 }  // namespace
 
@@ -164,7 +159,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
         }
     } else {
         // ---------------- epilogue / compute warps ---------------------------------------
-        const int q = warp & 3, hsel = warp >> 2;
+        const int q = warp & 3, chunk = warp >> 2;            // TMEM lane quadrant, 32-row chunk
+        const int i0 = 32 * chunk;
         const int n = 32 * q + lane;                          // this thread's feature = TMEM lane
         const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
         unsigned char* const bhi_bytes = reinterpret_cast<unsigned char*>(S.Bhi);
@@ -173,8 +169,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
         const int seg = a.whole_ic ? nx : kTileRows;          // periodic segment inside the tile (multiple of 32)
         uint32_t acc_phase = 0;
 
-        auto store_act = [&](int i, float h) {
-            const uint32_t off = act_off(i, n);
+        // activation element (row i0 + j, feature n): K-block q, 16-byte chunk (lane/4) ^ (j & 7)
+        const uint32_t act_base = (uint32_t)(q * (kTileRows * 128) + i0 * 128 + ((lane & 3) << 2));
+        uint32_t act_x[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) act_x[v] = act_base + ((uint32_t)((lane >> 2) ^ v) << 4);
+        auto store_act = [&](int j, float h) {                // j: row inside the chunk (compile-time after unrolling)
+            const uint32_t off = act_x[j & 7] + (uint32_t)j * 128;
             const float hi = to_tf32(h);
             *reinterpret_cast<float*>(bhi_bytes + off) = hi;
             if (parts == 2) *reinterpret_cast<float*>(blo_bytes + off) = to_tf32(h - hi);
@@ -226,14 +227,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
                     const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
                     const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
                     const float b = S.small[SmallParams::b_in + n];
-#pragma unroll 8
-                    for (int jj = 0; jj < 64; ++jj) {
-                        const int i = 64 * hsel + jj;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int i = i0 + j;
                         float v = fmaf(w0, S.sN[i], b);
                         v = fmaf(w1, S.sU[i], v);
                         v = fmaf(w2, S.sE[i], v);
                         v = fmaf(w3, S.sX[i], v);
-                        store_act(i, fmaxf(v, 0.f));
+                        store_act(j, fmaxf(v, 0.f));
                     }
                 }
                 tc_fence_before();
@@ -247,9 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
                     const bool is_edge = (layer == a.L);
                     const float bias = S.small[(is_edge ? SmallParams::b_e1 : SmallParams::b_upd + layer * kH) + n];
                     const float w_out = S.small[SmallParams::w_e2 + n];
-#pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        const int i0 = 32 * (2 * hsel + c);
+                    {
                         const int seg0 = (i0 / seg) * seg;
                         const int cl = (i0 == seg0) ? i0 - 4 + seg : i0 - 4;
                         const int cr = (i0 + 32 == seg0 + seg) ? i0 + 32 - seg : i0 + 32;
@@ -271,7 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
                                 float s = zw[4 + j + 1] + zw[4 + j - 1];
 #pragma unroll
                                 for (int k = 2; k <= R; ++k) { s += zw[4 + j + k]; s += zw[4 + j - k]; }
-                                store_act(i0 + j, fmaxf(fmaf(s, inv_deg, y[j] + bias), 0.f));
+                                store_act(j, fmaxf(fmaf(s, inv_deg, y[j] + bias), 0.f));
                             }
                         } else {
                             // edge readout (src/flux_gnn.py:63-66): this feature's term of the two dot products
@@ -297,7 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
 
                 // ---- reduce the edge terms over the 128 features: thread (row, which) ------------
                 named_sync(1, kEpiThreads);
-                {
+                if (tid < 2 * kTileRows) {
                     const int row = tid & (kTileRows - 1), which = tid >> 7;
                     const float* buf = reinterpret_cast<const float*>(which ? S.Blo : S.Bhi) + row * kH;
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -359,16 +358,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
                 named_sync(1, kEpiThreads);
                 // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
                 {
-                    const int row = tid >> 1, half = tid & 1;
+                    const int row = tid >> 2, part = tid & 3;
                     const int cell = S.rowCell[row], base = row - cell;
                     double e = 0.0;
-                    for (int i = half; i < nx; i += 2) {
+                    for (int i = part; i < nx; i += 4) {
                         int d = cell - i;
                         if (d < 0) d += nx;
                         e = fma(S.gtab[d], (double)S.sRho[base + i], e);
                     }
                     e += __shfl_xor_sync(0xffffffffu, e, 1);
-                    if (half == 0) S.sE[row] = (float)e;
+                    e += __shfl_xor_sync(0xffffffffu, e, 2);
+                    if (part == 0) S.sE[row] = (float)e;
                 }
                 named_sync(1, kEpiThreads);
                 if (tid < kTileRows && S.rowIC[tid] >= 0) {
