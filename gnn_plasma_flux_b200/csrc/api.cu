@@ -351,6 +351,47 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                                c, dt, steps, record_every, traj, workspace, stream);
 }
 
+int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, const float* state_ext,
+                             const float* x_ext, float* state_out, int B, int owned, int halo, int radius,
+                             float c, float dt, void* stream) {
+    int rc = check_model(packed, num_layers, B, owned, radius);
+    if (rc != FLUXGNN_OK) return rc;
+    if (!state_ext || !x_ext || !state_out) return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: null pointer");
+    if (precision != 0 && precision != FLUXGNN_TC_TF32X3 && precision != FLUXGNN_TC_TF32)
+        return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: bad precision %d", precision);
+    if (halo != num_layers * radius + 1)
+        return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: halo must be num_layers*radius+1 = %d, got %d",
+                         num_layers * radius + 1, halo);
+    if (owned < halo) return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: a slab must own at least `halo` cells");
+    HybridArgs a{};
+    a.packed = (const float*)packed;
+    a.state_in = state_ext;
+    a.state_out = state_out;
+    a.x = x_ext;
+    a.B = B; a.nx = owned; a.radius = radius; a.L = num_layers; a.hops = 1;
+    a.do_update = 1; a.steps = 1; a.record_every = 1;
+    a.c = c; a.dt = dt;
+    // always window tiles: the receptive field is served by the ghost cells
+    a.whole_ic = 0;
+    a.halo = halo;
+    a.valid = kTileRows - 2 * halo;
+    if (a.valid < 8) return set_error(FLUXGNN_EUNSUP, "receptive field of %d cells does not fit a 128-cell tile", halo);
+    a.tiles_per_ic = (owned + a.valid - 1) / a.valid;
+    const long long tiles = (long long)B * a.tiles_per_ic;
+    if (tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");
+    a.num_tiles = (int)tiles;
+    a.slab = 1;
+    a.ld_in = owned + 2 * halo;
+    int fast = (radius <= 4) ? radius : 0;
+    if (precision != 0) {
+        rc = tc_shape_ok(0, owned, radius);
+        if (rc != FLUXGNN_OK) return rc;
+        a.tc_parts = (precision == FLUXGNN_TC_TF32X3) ? 2 : 1;
+        fast = -radius;
+    }
+    return launch_tiles(a, fast, (cudaStream_t)stream);
+}
+
 int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const double* gtab, int B, int nx,
                              double length, float c, float dt, float nu, float dx2, int steps, int record_every,
                              float* traj, float* flux_n, void* workspace, void* stream_) {

@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
             const int j = tid;
             int ic, cell, prev = (j - 1) & (kTileRows - 1), next = (j + 1) & (kTileRows - 1);
             bool live, owned;
+            int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
             if (a.whole_ic) {
                 const int slot = j / nx;
                 cell = j - slot * nx;
@@ -262,6 +263,13 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                 cell = (int)(((gcell % nx) + nx) % nx);
                 live = true;
                 owned = (j >= a.halo) && (j < a.halo + a.valid) && ((long long)t * a.valid + (j - a.halo) < nx);
+                if (a.slab) {                       // ghost cells instead of the periodic wrap
+                    long long s = gcell + a.halo;
+                    s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
+                    src = (int)s;
+                    ld = a.ld_in;
+                    cell = (int)(gcell < 0 ? 0 : (gcell >= nx ? nx - 1 : gcell));
+                }
             }
             S.rowIC[j] = owned ? ic : -1;
             S.rowCell[j] = cell;
@@ -269,11 +277,12 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
             S.nextRow[j] = (short)next;
             float vn = 0.f, vu = 0.f, ve = 0.f, vx = 0.f;
             if (live) {
-                const float* st = a.state_in + (size_t)ic * 3 * nx + cell;
+                if (src < 0) src = cell;
+                const float* st = a.state_in + (size_t)ic * 3 * ld + src;
                 vn = __ldg(st);
-                vu = __ldg(st + nx);
-                ve = __ldg(st + 2 * (size_t)nx);
-                vx = __ldg(a.x + cell);
+                vu = __ldg(st + ld);
+                ve = __ldg(st + 2 * (size_t)ld);
+                vx = __ldg(a.x + src);
             }
             S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
         }

@@ -163,6 +163,20 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                               int steps, int record_every, float* traj,
                               void* workspace, void* stream);
 
+/* ---- one slab of a domain-decomposed grid (single large grid) -------
+ * The same hybrid step for `owned` consecutive cells of a longer periodic grid held
+ * by another rank.  The caller supplies ghost cells instead of the periodic wrap:
+ *   state_ext[B][3][owned + 2*halo]  cells -halo .. owned+halo-1 of this slab
+ *   x_ext[owned + 2*halo]            their GLOBAL cell centres (float32)
+ *   state_out[B][3][owned]           n' and u' are written; E' is NOT (the field solve
+ *                                    is global: gather n' and call fluxgnn_poisson_spectral)
+ * halo must equal num_layers*radius + 1, the receptive field of one step.
+ * precision: 0 = fp32 kernel (packed from fluxgnn_pack_weights), FLUXGNN_TC_* = tensor
+ * kernel (packed from fluxgnn_pack_weights_tc). */
+int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision,
+                             const float* state_ext, const float* x_ext, float* state_out,
+                             int B, int owned, int halo, int radius, float c, float dt, void* stream);
+
 /* ---- BaselineSolver.step / .run ------------------------------------------------
  * Replaces src/baseline_solver.py:70-118: upwind continuity flux n*u,
  * left-differenced u^2/2, viscous Laplacian, forward Euler, field solve.
