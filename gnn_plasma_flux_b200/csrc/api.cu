@@ -64,6 +64,9 @@ static int plan_tiles(HybridArgs& a, int* fast_radius) {
     // test hook: walk the prev/next tables even where the 128-bit window path applies
     const char* force = getenv("FLUXGNN_FORCE_GENERIC");
     if (force != nullptr && force[0] == '1') *fast_radius = 0;
+    // two skewed 64-row groups when the halves of a tile hold different ICs (test hook to disable)
+    const char* nosplit = getenv("FLUXGNN_NO_SPLIT");
+    a.split = (a.whole_ic && nx <= 64 && 64 % nx == 0 && !(nosplit != nullptr && nosplit[0] == '1')) ? 1 : 0;
     return FLUXGNN_OK;
 }
 

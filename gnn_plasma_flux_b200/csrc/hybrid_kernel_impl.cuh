@@ -41,7 +41,7 @@ namespace {
 #define FLUXGNN_FFMA2 1          // packed fma.rn.f32x2 (SASS FFMA2) in the GEMM inner loop
 #endif
 #ifndef FLUXGNN_STAGES
-#define FLUXGNN_STAGES 4
+#define FLUXGNN_STAGES 5
 #endif
 constexpr int kStages = FLUXGNN_STAGES;
 constexpr int kConsumerWarps = 8;
@@ -52,7 +52,6 @@ struct __align__(128) TileSmem {
     float Hs[kH * kTileRows];            // activations h   [feature][row], swizzled
     float Zs[kH * kTileRows];            // neighbour half  [feature][row], swizzled
     float Ws[kStages][kChunkFloats];     // streamed weight chunks [kChunkK k][128 permuted columns]
-    float small[SmallParams::count];
     float sN[kTileRows], sU[kTileRows], sE[kTileRows], sX[kTileRows];
     float sF[kTileRows], sRho[kTileRows];
     float edge[2][2][kMaxHops][kTileRows];   // [column half][fwd/bwd][hop][row] partial dot products
@@ -61,12 +60,21 @@ struct __align__(128) TileSmem {
     int rowCell[kTileRows];
     short prevRow[kTileRows], nextRow[kTileRows];
     uint64_t full[kStages], empty[kStages];
+    uint64_t skew;                       // split mode: group 1 starts once group 0 is kSkewChunks ahead
 };
 static_assert(sizeof(TileSmem) <= 227 * 1024, "tile does not fit shared memory");
+
+// Split mode (whole-IC tiles with nx | 64): the two 64-row halves of a tile hold different ICs, so
+// warps 0-3 (rows 0-63) and warps 4-7 (rows 64-127) never exchange data.  They run as two groups
+// with their own named barrier, sharing only the weight ring, and group 1 is started a few chunks
+// late: while one group is in an epilogue (little FMA work) the other is in its GEMM and has the
+// FMA pipe of every scheduler to itself.
+constexpr int kSkewChunks = (kStages >= 8) ? 3 : 2;
 
 struct Pipe {
     int stage = 0;
     uint32_t phase = 0;
+    int consumed = 0;                    // chunks this warp has finished (only compared with kSkewChunks)
     __device__ __forceinline__ void advance() {
         if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
@@ -89,7 +97,7 @@ __device__ __forceinline__ int col_of(int tx, int j) { return tx + 16 * j; }
 // xo[s] = float offset of row chunk c0 under swizzle key s; chunk c1 = c0 ^ 1 is 4 floats
 // above (s even) or below (s odd) because c0 is even.
 __device__ __forceinline__ void gemm_pass(float (&acc)[8][8], TileSmem& S, Pipe& pipe,
-                                          const int (&xo)[8], int tx, int lane) {
+                                          const int (&xo)[8], int tx, int lane, bool leads_skew) {
 #if FLUXGNN_FFMA2
     // Packed accumulators: for row pair p = (2p, 2p+1) and column pair q = (2q, 2q+1)
     //   d[p][q] = {acc[2p][2q],   acc[2p+1][2q+1]}   (a pair) * (b pair)
@@ -140,7 +148,10 @@ __device__ __forceinline__ void gemm_pass(float (&acc)[8][8], TileSmem& S, Pipe&
 #endif
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[pipe.stage]);
+        if (lane == 0) {
+            mbar_arrive(&S.empty[pipe.stage]);
+            if (leads_skew && ++pipe.consumed == kSkewChunks) mbar_arrive(&S.skew);
+        }
         pipe.advance();
     }
 #if FLUXGNN_FFMA2
@@ -187,9 +198,9 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
             mbar_init(&S.full[s], 1);
             mbar_init(&S.empty[s], kConsumerWarps);
         }
+        mbar_init(&S.skew, kConsumerWarps / 2);
         mbar_fence_init();
     }
-    for (int i = tid; i < SmallParams::count; i += kThreads) S.small[i] = a.packed[i];
     if (a.whole_ic && a.do_update)
         for (int i = tid; i < nx; i += kThreads) S.gtab[i] = a.gtab[i];
     __syncthreads();
@@ -238,11 +249,21 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
     }
     const int used_rows = a.whole_ic ? a.ics_per_tile * nx : kTileRows;
     Pipe pipe;
+    // group geometry: one group of 256 threads / 128 rows, or two groups of 128 threads / 64 rows
+    const int grp = a.split ? (warp >> 2) : 0;
+    const int gthreads = a.split ? kConsumers / 2 : kConsumers;
+    const int lt = a.split ? (tid & (kConsumers / 2 - 1)) : tid;      // thread index inside the group
+    const int nrows = a.split ? kTileRows / 2 : kTileRows;
+    const int row0 = grp * (kTileRows / 2);
+    const int myrow = (lt < nrows) ? row0 + lt : -1;                   // the row this thread looks after
+    const int bar = 1 + grp;
+    const bool leads_skew = a.split && grp == 0;
+    if (a.split && grp == 1) mbar_wait(&S.skew, 0);
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         // ---- row bookkeeping + state load -----------------------------------------
-        if (tid < kTileRows) {
-            const int j = tid;
+        if (myrow >= 0) {
+            const int j = myrow;
             int ic, cell, prev = (j - 1) & (kTileRows - 1), next = (j + 1) & (kTileRows - 1);
             bool live, owned;
             int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
@@ -286,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
             }
             S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
         }
-        named_sync(1, kConsumers);
+        named_sync(bar, gthreads);
 
         for (int step = 0; step < a.steps; ++step) {
             float acc[8][8];
@@ -301,11 +322,11 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int n = col_of(tx, j);
-                    const float w0 = S.small[SmallParams::w_in + 0 * kH + n];
-                    const float w1 = S.small[SmallParams::w_in + 1 * kH + n];
-                    const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
-                    const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
-                    const float b = S.small[SmallParams::b_in + n];
+                    const float w0 = __ldg(a.packed + SmallParams::w_in + 0 * kH + n);
+                    const float w1 = __ldg(a.packed + SmallParams::w_in + 1 * kH + n);
+                    const float w2 = __ldg(a.packed + SmallParams::w_in + 2 * kH + n);
+                    const float w3 = __ldg(a.packed + SmallParams::w_in + 3 * kH + n);
+                    const float b = __ldg(a.packed + SmallParams::b_in + n);
                     float h[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -320,20 +341,20 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                     *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
                 }
             }
-            named_sync(1, kConsumers);
+            named_sync(bar, gthreads);
 
             for (int layer = 0; layer <= a.L; ++layer) {
                 // ---- pass 0: Z = W[:, H:] h -> shared memory;  pass 1: Y = W[:, :H] h + b -> registers
-                const float* bias = S.small + (layer < a.L ? SmallParams::b_upd + layer * kH : SmallParams::b_e1);
+                const float* bias = a.packed + (layer < a.L ? SmallParams::b_upd + layer * kH : SmallParams::b_e1);
 #pragma unroll 1
                 for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float b = pass ? bias[col_of(tx, j)] : 0.f;
+                        const float b = pass ? __ldg(bias + col_of(tx, j)) : 0.f;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) acc[i][j] = b;
                     }
-                    gemm_pass(acc, S, pipe, xo, tx, lane);
+                    gemm_pass(acc, S, pipe, xo, tx, lane, leads_skew);
                     if (pass == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -343,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         }
                     }
                 }
-                named_sync(1, kConsumers);      // Z complete; nobody reads Hs any more
+                named_sync(bar, gthreads);      // Z complete; nobody reads Hs any more
 
                 if (layer < a.L) {
                     // ---- node update: h' = relu(Y + mean_{|k|<=r, k!=0} Z_{i+k})  (src/flux_gnn.py:55-60)
@@ -380,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         *reinterpret_cast<float4*>(hr + ((c0 ^ sw) << 2)) = make_float4(h[0], h[1], h[2], h[3]);
                         *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
                     }
-                    named_sync(1, kConsumers);  // h' complete; Z free
+                    named_sync(bar, gthreads);  // h' complete; Z free
                 } else {
                     // ---- edge readout (src/flux_gnn.py:63-66): acc = P + b1, Zs = Q ---------
                     //   fwd edge (row j, col j+k):  w2 . relu(P_j + Q_{j+k})
@@ -394,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int n = col_of(tx, j);
-                                const float w2 = S.small[SmallParams::w_e2 + n];
+                                const float w2 = __ldg(a.packed + SmallParams::w_e2 + n);
                                 const float* zr = S.Zs + n * kTileRows;
                                 if (R > 0) {
                                     float v[16];
@@ -432,15 +453,15 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                             }
                         }
                     }
-                    named_sync(1, kConsumers);
+                    named_sync(bar, gthreads);
                 }
             }   // layers
 
             // ---- per-row: directed-edge fluxes, face flux (src/hybrid_solver.py:45-48) ----
             float n_new = 0.f, u_new = 0.f;
-            if (tid < kTileRows) {
-                const int j = tid;
-                const float b2 = S.small[SmallParams::b_e2];
+            if (myrow >= 0) {
+                const int j = myrow;
+                const float b2 = __ldg(a.packed + SmallParams::b_e2);
                 const int ic = S.rowIC[j], cell = S.rowCell[j];
                 float face = 0.f;
                 int jn = j;
@@ -459,11 +480,11 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                 S.sF[j] = face;
             }
             if (!a.do_update) continue;          // forward only (steps == 1)
-            named_sync(1, kConsumers);
+            named_sync(bar, gthreads);
 
             // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
-            if (tid < kTileRows) {
-                const int j = tid, p = S.prevRow[j];
+            if (myrow >= 0) {
+                const int j = myrow, p = S.prevRow[j];
                 const float u = S.sU[j], up = S.sU[p];
                 n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
                 const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
@@ -473,23 +494,23 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
             }
             if (!a.whole_ic) {
                 // window tiles: E' comes from the separate field-solve kernel
-                if (tid < kTileRows && S.rowIC[tid] >= 0) {
-                    float* so = a.state_out + (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+                if (myrow >= 0 && S.rowIC[myrow] >= 0) {
+                    float* so = a.state_out + (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
                     so[0] = n_new;
                     so[nx] = u_new;
                 }
                 continue;
             }
-            named_sync(1, kConsumers);           // everyone has read the old n, u
-            if (tid < kTileRows) {
-                S.sN[tid] = n_new;
-                S.sU[tid] = u_new;
-                S.sRho[tid] = __fsub_rn(n_new, 1.0f);          // rho = n - n0  (src/baseline_solver.py:60)
+            named_sync(bar, gthreads);           // everyone has read the old n, u
+            if (myrow >= 0) {
+                S.sN[myrow] = n_new;
+                S.sU[myrow] = u_new;
+                S.sRho[myrow] = __fsub_rn(n_new, 1.0f);        // rho = n - n0  (src/baseline_solver.py:60)
             }
-            named_sync(1, kConsumers);
+            named_sync(bar, gthreads);
             // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
             {
-                const int row = tid >> 1, half = tid & 1;
+                const int row = row0 + (lt >> 1), half = lt & 1;
                 double e = 0.0;
                 if (row < used_rows) {
                     const int cell = S.rowCell[row], base = row - cell;
@@ -502,24 +523,24 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                 e += __shfl_xor_sync(0xffffffffu, e, 1);
                 if (half == 0) S.sE[row] = (float)e;
             }
-            named_sync(1, kConsumers);
+            named_sync(bar, gthreads);
             // ---- write-out: last step and recorded steps ---------------------------------
-            if (tid < kTileRows && S.rowIC[tid] >= 0) {
-                const size_t off = (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+            if (myrow >= 0 && S.rowIC[myrow] >= 0) {
+                const size_t off = (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
                 if (step == a.steps - 1) {
-                    a.state_out[off] = S.sN[tid];
-                    a.state_out[off + nx] = S.sU[tid];
-                    a.state_out[off + 2 * (size_t)nx] = S.sE[tid];
+                    a.state_out[off] = S.sN[myrow];
+                    a.state_out[off + nx] = S.sU[myrow];
+                    a.state_out[off + 2 * (size_t)nx] = S.sE[myrow];
                 }
                 if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
                     float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
-                    tr[0] = S.sN[tid];
-                    tr[nx] = S.sU[tid];
-                    tr[2 * (size_t)nx] = S.sE[tid];
+                    tr[0] = S.sN[myrow];
+                    tr[nx] = S.sU[myrow];
+                    tr[2 * (size_t)nx] = S.sE[myrow];
                 }
             }
         }   // steps
-        named_sync(1, kConsumers);   // state arrays are rewritten by the next tile's load
+        named_sync(bar, gthreads);   // state arrays are rewritten by the next tile's load
     }       // tiles
 }
 
