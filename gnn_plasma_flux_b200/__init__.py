@@ -12,6 +12,9 @@ from .config import DATASET_CONFIG, EVAL_CONFIG, MODEL_CONFIG, STENCIL_RADII
 from .flux_gnn import FluxGNN
 from .graph_constructor import build_chain_graph, ring_edge_index
 from .hybrid_solver import HybridSolver
+from .datagen import generate_dataset
+from .metrics import compute_metrics, first_nonfinite_step, rollout_metrics
 
 __all__ = ["BaselineSolver", "FluxGNN", "HybridSolver", "build_chain_graph", "ring_edge_index",
+           "generate_dataset", "compute_metrics", "rollout_metrics", "first_nonfinite_step",
            "DATASET_CONFIG", "EVAL_CONFIG", "MODEL_CONFIG", "STENCIL_RADII"]

@@ -43,6 +43,7 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p]),
     "fluxgnn_hybrid_rollout_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_double, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_rollout_metrics": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     "fluxgnn_hybrid_slab_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                          c_float, c_float, c_void_p]),
     "fluxgnn_baseline_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -354,6 +354,16 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                                c, dt, steps, record_every, traj, workspace, stream);
 }
 
+int fluxgnn_rollout_metrics(const float* pred, const float* truth, long long num_states, int nx, float* out,
+                            void* stream) {
+    if (!pred || !out || num_states < 1 || nx < 1 || num_states > 0x7fffffffLL)
+        return set_error(FLUXGNN_EINVAL, "rollout_metrics: bad argument (states=%lld nx=%d)", num_states, nx);
+    rollout_metrics_kernel<<<(unsigned)num_states, 256, 0, (cudaStream_t)stream>>>(pred, truth, nx, out);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, const float* state_ext,
                              const float* x_ext, float* state_out, int B, int owned, int halo, int radius,
                              float c, float dt, void* stream) {

@@ -204,6 +204,51 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_in, const float*
     }
 }
 
+// Rollout diagnostics of the reference's evaluation scripts, one block per stored state (t, b):
+//   out[(t*B + b)*8 + 0..2] = mean((pred - true)^2) per channel (n, u, E)   scripts/evaluation/evaluate_all.py:130-132
+//   out[.. + 3] = 0.5 * mean(u^2 + E^2)   (energy)                          evaluate_all.py:136-137
+//   out[.. + 4] = mean(n)                 (charge)                          evaluate_all.py:142-143
+//   out[.. + 5] = number of non-finite values in the state                  evaluate_long_rollout.py:56-60
+// fp64 accumulation; `truth` may be null (MSE columns are 0 then).
+__global__ void __launch_bounds__(256) rollout_metrics_kernel(const float* __restrict__ pred,
+                                                              const float* __restrict__ truth, int nx,
+                                                              float* __restrict__ out) {
+    const size_t sid = blockIdx.x;                       // flattened (t, b)
+    const float* p = pred + sid * 3 * nx;
+    const float* q = truth ? truth + sid * 3 * nx : nullptr;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        const float n = p[i], u = p[nx + i], e = p[2 * (size_t)nx + i];
+        if (q != nullptr) {
+            const double dn = (double)n - q[i], du = (double)u - q[nx + i], de = (double)e - q[2 * (size_t)nx + i];
+            acc[0] += dn * dn; acc[1] += du * du; acc[2] += de * de;
+        }
+        acc[3] += (double)u * u + (double)e * e;
+        acc[4] += n;
+        acc[5] += (isfinite(n) ? 0.0 : 1.0) + (isfinite(u) ? 0.0 : 1.0) + (isfinite(e) ? 0.0 : 1.0);
+    }
+    __shared__ double red[6][8];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+        const int k = threadIdx.x;
+        float r;
+        if (k < 3) r = (float)(v / nx);
+        else if (k == 3) r = (float)(0.5 * v / nx);
+        else if (k == 4) r = (float)(v / nx);
+        else r = (float)v;
+        out[sid * 8 + k] = r;
+    }
+    if (threadIdx.x >= 6 && threadIdx.x < 8) out[sid * 8 + threadIdx.x] = 0.f;
+}
+
 // Tensor-path stream: small block + pre-swizzled UMMA operand images (layout: common.cuh)
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
                                        const float* __restrict__ w_upd, const float* __restrict__ b_upd,

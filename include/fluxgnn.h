@@ -163,6 +163,16 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                               int steps, int record_every, float* traj,
                               void* workspace, void* stream);
 
+/* ---- rollout diagnostics on the device ---------------------------
+ * The metrics every evaluation script of the reference computes on the host after
+ * copying whole trajectories back (scripts/evaluation/evaluate_all.py:118-159,
+ * evaluate_long_rollout.py:38-66).  pred / truth: num_states stored states [3][nx]
+ * (any leading [T][B] shape flattened); truth nullable.  out[num_states][8]:
+ *   0..2 mean squared error per channel (n, u, E); 3 energy 0.5*mean(u^2+E^2);
+ *   4 charge mean(n); 5 count of non-finite values; 6..7 zero. */
+int fluxgnn_rollout_metrics(const float* pred, const float* truth, long long num_states, int nx,
+                            float* out, void* stream);
+
 /* ---- one slab of a domain-decomposed grid (single large grid) -------
  * The same hybrid step for `owned` consecutive cells of a longer periodic grid held
  * by another rank.  The caller supplies ghost cells instead of the periodic wrap:

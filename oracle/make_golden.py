@@ -180,6 +180,29 @@ def main():
     np.savez_compressed(os.path.join(OUT, "g6_long_rollout.npz"), ics=g6_ic, ref_fp32=snaps32,
                         fp64=snaps64, dt=1e-3, nx=64, radius=1, every=100)
 
+    # ---- G7 evaluation metrics and data generation --------------------
+    sys.path.insert(0, os.path.join(REF, "scripts", "training"))      # evaluate_all imports train_pure_gnn bare
+    from scripts.evaluation.evaluate_all import compute_metrics as ref_metrics      # reference
+    from scripts.training.generate_data import generate_dataset as ref_generate     # reference
+    g23 = dict(np.load(os.path.join(OUT, "g23_hybrid_c1.npz")))
+    pred = g23["rollout"][0]                                              # hybrid trajectory [31,3,64]
+    base = BaselineSolver(nx=64, dt=5e-3)
+    truth, _ = base.run(g23["ics"][0], n_steps=30)
+    m_ref, m_port = ref_metrics(pred, truth), P.compute_metrics(pred, truth)
+    g7 = {"truth": truth}
+    for key, val in m_ref.items():
+        np.testing.assert_allclose(np.asarray(m_port[key], dtype=np.float64), np.asarray(val, dtype=np.float64), rtol=1e-12)
+        g7["metric_" + key] = np.asarray(val, dtype=np.float64)
+    print("  ok  compute_metrics vs reference")
+    tmp_npz = os.path.join(tempfile.mkdtemp(), "d.npz")
+    st_, fl_, nx_, x_, dt_, dx_, nu_ = ref_generate(nx=64, num_initial_conditions=3, steps_per_ic=5, out_path=tmp_npz)
+    ps, pf, pn = P.generate_dataset(nx=64, num_initial_conditions=3, steps_per_ic=5)
+    same(ps, st_, "generate_dataset state_t")
+    same(pf, fl_, "generate_dataset flux_t")
+    same(pn, nx_, "generate_dataset state_next")
+    g7.update(ds_state_t=st_, ds_flux_t=fl_, ds_state_next=nx_, ds_x=x_, ds_dx=dx_)
+    np.savez_compressed(os.path.join(OUT, "g7_metrics_datagen.npz"), **g7)
+
     manifest = {
         "generated_by": "oracle/make_golden.py",
         "reference": "/root/reference (shanedirksen/gnn-plasma-flux, unmodified)",

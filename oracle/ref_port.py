@@ -300,3 +300,30 @@ def energy(states) -> np.ndarray:
 def charge(states) -> np.ndarray:
     """mean(n) per stored step (scripts/evaluation/evaluate_all.py:140-141)."""
     return np.mean(np.asarray(states, dtype=np.float64)[..., 0, :], axis=-1)
+
+
+def compute_metrics(states_pred, states_true) -> dict:
+    """Evaluation metrics of scripts/evaluation/evaluate_all.py:118-159 for trajectories
+    [T,3,nx]: per-step channel MSE, energy / charge and their drifts, final values."""
+    sp, st = np.asarray(states_pred), np.asarray(states_true)
+    mse = [np.mean((sp[:, c] - st[:, c]) ** 2, axis=1) for c in range(3)]
+    total = mse[0] + mse[1] + mse[2]
+    e_pred = 0.5 * np.mean(sp[:, 1] ** 2 + sp[:, 2] ** 2, axis=1)
+    e_true = 0.5 * np.mean(st[:, 1] ** 2 + st[:, 2] ** 2, axis=1)
+    c_pred, c_true = np.mean(sp[:, 0], axis=1), np.mean(st[:, 0], axis=1)
+    return {"mse_n": mse[0], "mse_u": mse[1], "mse_E": mse[2], "mse_total": total,
+            "energy_drift_pred": np.abs(e_pred - e_pred[0]), "energy_drift_true": np.abs(e_true - e_true[0]),
+            "charge_drift_pred": np.abs(c_pred - c_pred[0]), "charge_drift_true": np.abs(c_true - c_true[0]),
+            "final_mse": float(total[-1]), "mean_mse": float(np.mean(total)),
+            "final_energy_drift": float(np.abs(e_pred - e_pred[0])[-1]),
+            "final_charge_drift": float(np.abs(c_pred - c_pred[0])[-1])}
+
+
+def generate_dataset(nx=64, num_initial_conditions=20, steps_per_ic=30, dt=5e-3, nu=1e-3):
+    """scripts/training/generate_data.py:12-54 without the file output: (state_t, flux_t, state_next)."""
+    g = Grid(nx=nx, dt=dt, nu=nu)
+    st, fl, nxt = [], [], []
+    for ic in range(num_initial_conditions):
+        states, fluxes = baseline_run(initial_condition(g, seed=ic), g, n_steps=steps_per_ic)
+        st.append(states[:-1]); fl.append(fluxes); nxt.append(states[1:])
+    return np.concatenate(st), np.concatenate(fl), np.concatenate(nxt)

@@ -440,3 +440,49 @@ def test_error_paths(model):
     big = make_solver(model, 20000, 1e-5)
     with pytest.raises(_lib.FluxGNNError):
         big.rollout(torch.zeros(1, 3, 20000, device="cuda"), 1)     # field solve beyond this build's limit
+
+
+# ----------------------------------------------------------------------------- next rows: N1 metrics, N3 data generation
+def test_device_metrics_vs_reference(built_lib):
+    from gnn_plasma_flux_b200 import compute_metrics, first_nonfinite_step, rollout_metrics
+    g7 = load_golden("g7_metrics_datagen.npz")
+    g23 = load_golden("g23_hybrid_c1.npz")
+    pred, truth = g23["rollout"][0], g7["truth"]                             # [31,3,64] each
+    m = compute_metrics(torch.from_numpy(pred).cuda(), torch.from_numpy(truth).cuda())
+    for key in ("mse_n", "mse_u", "mse_E", "mse_total", "energy_drift_pred", "energy_drift_true",
+                "charge_drift_pred", "charge_drift_true", "final_mse", "mean_mse", "final_energy_drift",
+                "final_charge_drift"):
+        ref = g7["metric_" + key]
+        got = m[key].double().cpu().numpy()
+        # fp32 reductions of the reference vs fp64 accumulation here: drifts are differences of O(1) numbers
+        atol = 3e-7 if "drift" in key else 0.0
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=atol, err_msg=key)
+    # batched trajectories and non-finite detection
+    traj = torch.from_numpy(np.moveaxis(g23["rollout"], 0, 1).copy()).cuda()      # [31,20,3,64]
+    bm = rollout_metrics(traj)
+    assert bm["energy"].shape == (31, 20)
+    np.testing.assert_allclose(bm["charge"][:, 3].cpu().numpy(), traj[:, 3, 0].mean(-1).cpu().numpy(), rtol=1e-6)
+    assert (first_nonfinite_step(traj) == -1).all()
+    traj[7, 5, 1, 9] = float("nan")
+    traj[4, 2, 0, 0] = float("inf")
+    first = first_nonfinite_step(traj).cpu().numpy()
+    assert first[5] == 7 and first[2] == 4 and (np.delete(first, [2, 5]) == -1).all()
+
+
+def test_generate_dataset_golden(built_lib, tmp_path):
+    from gnn_plasma_flux_b200 import generate_dataset
+    g7 = load_golden("g7_metrics_datagen.npz")
+    out = tmp_path / "data" / "dataset.npz"
+    st, fl, nxt, x, dt, dx, nu = generate_dataset(nx=64, num_initial_conditions=3, steps_per_ic=5, out_path=str(out))
+    assert st.shape == (15, 3, 64) and fl.shape == (15, 64) and nxt.shape == (15, 3, 64)
+    first = np.arange(3) * 5                                                    # first step of every IC: same input state
+    np.testing.assert_array_equal(fl[first], g7["ds_flux_t"][first])            # -> F_n and n' bit-exact
+    np.testing.assert_array_equal(nxt[first][:, 0], g7["ds_state_next"][first][:, 0])
+    np.testing.assert_array_equal(st[first][:, :2], g7["ds_state_t"][first][:, :2])    # (u' already sees E of the IC's field solve)
+    # later steps inherit the ~1e-7 difference of the field solve (different FFT arithmetic)
+    assert np.abs(fl - g7["ds_flux_t"]).max() <= 5 * STEP_TOL * np.abs(g7["ds_flux_t"]).max()
+    assert P.rel_err(st, g7["ds_state_t"]).max() <= 5 * STEP_TOL and P.rel_err(nxt, g7["ds_state_next"]).max() <= 5 * STEP_TOL
+    np.testing.assert_array_equal(x, g7["ds_x"])
+    saved = np.load(out)
+    assert sorted(saved.files) == ["dt", "dx", "flux_t", "nu", "state_next", "state_t", "x"]     # generate_data.py:38-47
+    assert float(saved["dx"]) == float(g7["ds_dx"])

@@ -113,3 +113,17 @@ def test_long_rollout_noise_floor_golden():
     mass0 = g6["ref_fp32"][:, 0, 0].astype(np.float64).sum(-1)
     massT = g6["ref_fp32"][:, -1, 0].astype(np.float64).sum(-1)
     assert np.abs(massT - mass0).max() < 1000 * 64 * np.finfo(np.float32).eps
+
+
+def test_metrics_and_datagen_golden():
+    """the oracle's restatements of evaluate_all.compute_metrics and
+    generate_data.generate_dataset against outputs of the reference's own functions."""
+    g7 = load_golden("g7_metrics_datagen.npz")
+    g23 = load_golden("g23_hybrid_c1.npz")
+    m = P.compute_metrics(g23["rollout"][0], g7["truth"])
+    for key, val in m.items():
+        np.testing.assert_allclose(np.asarray(val, dtype=np.float64), g7["metric_" + key], rtol=1e-12)
+    st, fl, nxt = P.generate_dataset(nx=64, num_initial_conditions=3, steps_per_ic=5)
+    np.testing.assert_array_equal(st, g7["ds_state_t"])
+    np.testing.assert_array_equal(fl, g7["ds_flux_t"])
+    np.testing.assert_array_equal(nxt, g7["ds_state_next"])
