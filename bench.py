@@ -238,6 +238,21 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * ICS * NX * K / float(t.item())
     state_bytes = ICS * 3 * NX * 4
+    # same loop with the kernel reading / writing the pinned host state directly (zero-copy over PCIe)
+    for _ in range(max(W, 1)):
+        solver.step_pinned(h_in, h_out, zero_copy=True)
+        h_in, h_out = h_out, h_in
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        solver.step_pinned(h_in, h_out, zero_copy=True)
+        h_in, h_out = h_out, h_in
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_zero_copy = world * ICS * NX * K / float(t.item())
+    assert torch.isfinite(h_in).all()
 
     # ---- the tensor-core variants of the same step, reported beside the headline ----------------
     tensor_extra = {}
@@ -275,7 +290,7 @@ def run_ours(args):
         for packed in (0, 1, 0, 1, 0, 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            flops = _lib.lib().fluxgnn_ffma_probe(sink.data_ptr(), 148 * 8, 20000, packed, stream.cuda_stream)
+            flops = _lib.lib().fluxgnn_ffma_probe(sink.data_ptr(), 148 * 8, 256, 20000, packed, stream.cuda_stream)
             e1.record(stream)
             torch.cuda.synchronize(dev)
             probe[packed] = max(probe[packed], flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
@@ -333,8 +348,11 @@ def run_ours(args):
             "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "flushed (256 MiB write) between timed steps",
                        "launches_per_step": launches / K, "wall_s_incl_flush": wall},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
-                    "d2h_bytes_per_step": state_bytes},
+            "e2e": {"value": max(e2e_value, e2e_zero_copy), "unit": UNIT, "h2d_bytes_per_step": state_bytes,
+                    "d2h_bytes_per_step": state_bytes,
+                    "copy_engine": e2e_value, "zero_copy": e2e_zero_copy,
+                    "note": "HybridSolver.step_pinned on pinned host state every step; `copy_engine` = cudaMemcpyAsync "
+                            "H2D + kernel + D2H, `zero_copy` = the kernel reads/writes the pinned buffers over PCIe"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
             "tensor_path": tensor_path,
         }

@@ -120,15 +120,16 @@ const char* fluxgnn_last_error(void) { return g_err; }
 
 unsigned long long fluxgnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-long long fluxgnn_ffma_probe(float* out, int blocks, int iters, int packed, void* stream) {
-    if (out == nullptr || blocks < 1 || iters < 1) return set_error(FLUXGNN_EINVAL, "ffma_probe: bad argument");
+long long fluxgnn_ffma_probe(float* out, int blocks, int threads, int iters, int packed, void* stream) {
+    if (out == nullptr || blocks < 1 || iters < 1 || threads < 32 || threads > 256 || threads % 32)
+        return set_error(FLUXGNN_EINVAL, "ffma_probe: bad argument");
     if (packed)
-        ffma2_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
+        ffma2_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
     else
-        ffma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
+        ffma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999f, 0.001f);
     FLUXGNN_CUDA_OK(cudaGetLastError());
     count_launch();
-    return (long long)blocks * 256 * iters * kFfmaProbeFlopsPerIter;
+    return (long long)blocks * threads * iters * kFfmaProbeFlopsPerIter;
 }
 
 size_t fluxgnn_packed_weight_bytes(int num_layers) {

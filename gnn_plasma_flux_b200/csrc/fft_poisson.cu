@@ -43,20 +43,110 @@ __device__ __forceinline__ int saddr(int idx, int t, int cnt) {
     return cnt == 1 ? idx + (idx >> 4) : idx * cnt + t;
 }
 
-// exp(sign * 2*pi*i * m / (2*half)), m < half <= 8: the constant part of a register-radix twiddle
-__device__ __forceinline__ float2 unit_root(int m, int half, float sign) {
-    const int q = m * (8 / half);                  // angle in sixteenths of a turn
-    const float c[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
-                        0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
-    const float sn[8] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
-                         1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
-    return make_float2(c[q], sign * sn[q]);
+// v * exp(sign * 2*pi*i * Q / 16) for a compile-time sixteenth-turn Q: trivial roots cost nothing,
+// eighth turns two multiplies, the rest one complex multiply.
+template <int Q>
+__device__ __forceinline__ float2 mul_root16(float2 v, float sign) {
+    constexpr int q = Q & 15;
+    if (q == 0) return v;
+    if (q == 8) return make_float2(-v.x, -v.y);
+    if (q == 4) return make_float2(-sign * v.y, sign * v.x);                 // * (sign i)
+    if (q == 12) return make_float2(sign * v.y, -sign * v.x);                // * (-sign i)
+    constexpr float kC[16] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                              0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                              -1.f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f,
+                              0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
+    constexpr float kS[16] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                              1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                              0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                              -1.f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+    const float c = kC[q], sn = sign * kS[q];
+    return make_float2(v.x * c - v.y * sn, v.x * sn + v.y * c);
+}
+
+__host__ __device__ constexpr int brev_bits(int v, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) r |= ((v >> b) & 1) << (bits - 1 - b);
+    return r;
+}
+__host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+
+// R-point DFT in registers, decimation in frequency: natural order in, bit-reversed order out,
+// constant roots only (stage of register-span `half`: W_(2 half)^mm on the lower output).
+template <int R, int HALF = R / 2>
+struct DifStages {
+    __device__ static __forceinline__ void run(float2 (&v)[R], float sign) {
+        constexpr int kStep = 8 / HALF;                    // sixteenth-turns per unit of mm
+        unroll<0>(v, sign, kStep);
+        DifStages<R, HALF / 2>::run(v, sign);
+    }
+    template <int A>
+    __device__ static __forceinline__ void unroll(float2 (&v)[R], float sign, int) {
+        if constexpr (A < R) {
+            if constexpr ((A & HALF) == 0) {
+                constexpr int mm = A & (HALF - 1);
+                const float2 u = v[A], x = v[A + HALF];
+                v[A] = make_float2(u.x + x.x, u.y + x.y);
+                v[A + HALF] = mul_root16<mm * (8 / HALF)>(make_float2(u.x - x.x, u.y - x.y), sign);
+            }
+            unroll<A + 1>(v, sign, 0);
+        }
+    }
+};
+template <int R>
+struct DifStages<R, 0> {
+    __device__ static __forceinline__ void run(float2 (&)[R], float) {}
+};
+
+// The matching decimation-in-time network: bit-reversed order in, natural order out.
+template <int R, int HALF = 1>
+struct DitStages {
+    __device__ static __forceinline__ void run(float2 (&v)[R], float sign) {
+        unroll<0>(v, sign);
+        DitStages<R, HALF * 2>::run(v, sign);
+    }
+    template <int A>
+    __device__ static __forceinline__ void unroll(float2 (&v)[R], float sign) {
+        if constexpr (A < R) {
+            if constexpr ((A & HALF) == 0) {
+                constexpr int mm = A & (HALF - 1);
+                const float2 u = v[A], x = mul_root16<mm * (8 / HALF)>(v[A + HALF], sign);
+                v[A] = make_float2(u.x + x.x, u.y + x.y);
+                v[A + HALF] = make_float2(u.x - x.x, u.y - x.y);
+            }
+            unroll<A + 1>(v, sign);
+        }
+    }
+};
+template <int R>
+struct DitStages<R, R> {
+    __device__ static __forceinline__ void run(float2 (&)[R], float) {}
+};
+
+// v * w^Q with w, w^2, w^4, w^8 given: the power is assembled from its binary digits, so only four
+// powers live in registers and no product is more than four multiplications away from the sincos.
+template <int Q>
+__device__ __forceinline__ float2 mul_power(float2 v, float2 p1, float2 p2, float2 p4, float2 p8) {
+    if constexpr (Q & 1) v = cmul(v, p1);
+    if constexpr (Q & 2) v = cmul(v, p2);
+    if constexpr (Q & 4) v = cmul(v, p4);
+    if constexpr (Q & 8) v = cmul(v, p8);
+    return v;
+}
+
+template <int R, int A = 1>
+__device__ __forceinline__ void twiddle_outputs(float2 (&v)[R], float2 p1, float2 p2, float2 p4, float2 p8) {
+    if constexpr (A < R) {
+        v[A] = mul_power<brev_bits(A, ilog2c(R))>(v[A], p1, p2, p4, p8);
+        twiddle_outputs<R, A + 1>(v, p1, p2, p4, p8);
+    }
 }
 
 // One radix-R pass over blocks of length L (R | L): every work item owns the R elements
-// blk*L + base + m*(L/R) and runs log2(R) radix-2 stages on them in registers.
-// DIF (kDit = false): butterfly then twiddle, spans shrink; DIT: twiddle then butterfly, spans grow.
-// The twiddle of register-span `half` at offset mm is  W_L^(base * (R/2)/half) * W_(2 half)^mm.
+// blk*L + base + m*(L/R).
+//   DIF (kDit = false): y = DFT_R(v), then y_q *= W_L^(base*q); output q sits in register bitrev(q),
+//                       i.e. sub-block bitrev(q) of the block -- the layout the next passes expect.
+//   DIT (kDit = true) : the transpose: register a *= W_L^(base*bitrev(a)), then the DIT network.
 template <int R, bool kDit>
 __device__ __forceinline__ void radix_pass(float2* s, int n, int L, int cnt, float sign) {
     const int sub = L / R;                         // stride between a work item's elements (power of two)
@@ -69,43 +159,14 @@ __device__ __forceinline__ void radix_pass(float2* s, int n, int L, int cnt, flo
         float2 v[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) v[m] = s[saddr(e0 + m * sub, t, cnt)];
-        // per-item twiddles W_L^(base * 2^k), k = 0..log2(R)-1
-        float2 wp[4];
-        wp[0] = twiddle(base, L, sign);
-#pragma unroll
-        for (int k = 1; k < 4; ++k) wp[k] = cmul(wp[k - 1], wp[k - 1]);
+        const float2 p1 = twiddle(base, L, sign);                     // W_L^base and its squarings
+        const float2 p2 = cmul(p1, p1), p4 = cmul(p2, p2), p8 = cmul(p4, p4);
         if (!kDit) {
-#pragma unroll
-            for (int half = R / 2, k = 0; half >= 1; half >>= 1, ++k) {
-#pragma unroll
-                for (int a = 0; a < R; ++a) {
-                    if ((a & half) == 0) {
-                        const int mm = a & (half - 1);
-                        const float2 u = v[a], x = v[a + half];
-                        v[a] = make_float2(u.x + x.x, u.y + x.y);
-                        const float2 tw = cmul(wp[k], unit_root(mm, half, sign));
-                        v[a + half] = cmul(make_float2(u.x - x.x, u.y - x.y), tw);
-                    }
-                }
-            }
+            DifStages<R>::run(v, sign);
+            if (sub > 1) twiddle_outputs<R>(v, p1, p2, p4, p8);     // sub == 1: base == 0, all twiddles are 1
         } else {
-#pragma unroll
-            for (int half = 1, k = 0; half < R; half <<= 1, ++k) {
-                // log2(R) - 1 - k indexes the same twiddle power the DIF stage of this span used
-                int kk = 0;
-#pragma unroll
-                for (int hh = R / 2; hh > half; hh >>= 1) ++kk;
-#pragma unroll
-                for (int a = 0; a < R; ++a) {
-                    if ((a & half) == 0) {
-                        const int mm = a & (half - 1);
-                        const float2 tw = cmul(wp[kk], unit_root(mm, half, sign));
-                        const float2 u = v[a], x = cmul(v[a + half], tw);
-                        v[a] = make_float2(u.x + x.x, u.y + x.y);
-                        v[a + half] = make_float2(u.x - x.x, u.y - x.y);
-                    }
-                }
-            }
+            if (sub > 1) twiddle_outputs<R>(v, p1, p2, p4, p8);
+            DitStages<R>::run(v, sign);
         }
 #pragma unroll
         for (int m = 0; m < R; ++m) s[saddr(e0 + m * sub, t, cnt)] = v[m];

@@ -80,11 +80,19 @@ class HybridSolver:
                 work.data_ptr() if work is not None else None, stream), "fluxgnn_hybrid_rollout")
         return out, traj
 
-    def step_pinned(self, host_in: torch.Tensor, host_out: torch.Tensor, n_steps: int = 1):
-        """End-to-end step on HOST buffers: pinned [B,3,nx] float32 in -> pinned out, with the
-        host->device and device->host copies on the current stream; returns after the
-        result is readable on the host."""
+    def step_pinned(self, host_in: torch.Tensor, host_out: torch.Tensor, n_steps: int = 1, zero_copy: bool = False):
+        """End-to-end step on HOST buffers: pinned [B,3,nx] float32 in -> pinned out; returns after
+        the result is readable on the host.  Default: H2D copy, kernel, D2H copy on the current
+        stream.  zero_copy=True: the kernel itself reads the pinned input and writes the pinned
+        output over PCIe (pinned memory is device-addressable under UVA), so the transfers of
+        one tile overlap the arithmetic of the others; only for nx <= 128 (one launch per call)."""
         dev = torch.device(self.device)
+        if zero_copy:
+            if not (host_in.is_pinned() and host_out.is_pinned()) or self.baseline.nx > 128:
+                raise ValueError("zero_copy needs pinned host tensors and nx <= 128")
+            self._rollout_raw(host_in, host_out, n_steps, dev)
+            torch.cuda.current_stream(dev).synchronize()
+            return host_out
         key = tuple(host_in.shape)
         bufs = self._pinned.get(key)
         if bufs is None:
@@ -96,6 +104,22 @@ class HybridSolver:
         host_out.copy_(d_out, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return host_out
+
+    def _rollout_raw(self, src: torch.Tensor, dst: torch.Tensor, n_steps: int, dev):
+        """fluxgnn_hybrid_rollout[_tc] on caller-provided device-addressable buffers (no checks, nx <= 128)."""
+        base = self.baseline
+        tensor_path = self.precision != "fp32"
+        packed = self.model.packed_weights("tc" if tensor_path else "fp32")
+        x_dev, gtab = base.grid.tables(dev)
+        B, _, nx = src.shape
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            head = ((packed.data_ptr(), self.model.num_layers, _lib.TC_PRECISIONS[self.precision]) if tensor_path
+                    else (packed.data_ptr(), self.model.num_layers))
+            entry = _lib.lib().fluxgnn_hybrid_rollout_tc if tensor_path else _lib.lib().fluxgnn_hybrid_rollout
+            _lib.check(entry(*head, src.data_ptr(), dst.data_ptr(), x_dev.data_ptr(), gtab.data_ptr(), B, nx,
+                             base.length, self.graph_radius, float(np.float32(base.dt / base.dx)),
+                             float(np.float32(base.dt)), n_steps, 1, None, None, stream), "fluxgnn_hybrid_rollout")
 
     # ------------------------------------------------------------------ reference API
     def step(self, state):

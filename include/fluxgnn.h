@@ -51,12 +51,12 @@ const char* fluxgnn_last_error(void);
 /* Number of kernels this library has launched since it was loaded (all threads). */
 unsigned long long fluxgnn_launch_count(void);
 
-/* Measurement aid (bench.py): launches `blocks` x 256 threads that each run `iters`
+/* Measurement aid (bench.py): launches `blocks` x `threads` (<= 256) threads that each run `iters`
  * iterations of 128 FMAs on registers (16 independent chains; packed != 0 uses the
- * two-wide fma.rn.f32x2 / FFMA2 form the GEMM uses); out[blocks*256] receives a
+ * two-wide fma.rn.f32x2 / FFMA2 form the GEMM uses); out[blocks*threads] receives a
  * checksum.  Returns the number of FLOPs the launch executes (negative = error).
  * Time it with CUDA events to get the FP32-pipe roofline of the device. */
-long long fluxgnn_ffma_probe(float* out, int blocks, int iters, int packed, void* stream);
+long long fluxgnn_ffma_probe(float* out, int blocks, int threads, int iters, int packed, void* stream);
 
 /* ---- weights: FluxGNN.state_dict() -> streaming layout -------------------
  * Replaces the parameter container of src/flux_gnn.py:11-38.  Inputs are the

@@ -252,6 +252,20 @@ def test_hybrid_window_rollout_vs_oracle(model, weights):
         assert P.rel_err(traj[i].cpu().numpy(), ref[i + 1]).max() <= STEP_TOL * 2 * (i + 1)
 
 
+def test_step_pinned_host_buffers(model):
+    """End-to-end entry on pinned host state: copy-engine and zero-copy variants equal the device path."""
+    g = load_golden("g23_hybrid_c1.npz")
+    sol = make_solver(model, 64, 5e-3, graph_radius=3)
+    want = sol.step(g["ics"])
+    h_in = torch.from_numpy(g["ics"]).pin_memory()
+    for zero_copy in (False, True):
+        h_out = torch.zeros_like(h_in).pin_memory()
+        sol.step_pinned(h_in, h_out, zero_copy=zero_copy)
+        np.testing.assert_array_equal(h_out.numpy(), want)
+    with pytest.raises(ValueError):
+        sol.step_pinned(torch.from_numpy(g["ics"]), torch.zeros(20, 3, 64), zero_copy=True)      # not pinned
+
+
 def test_generic_path_equals_fast_path(model, monkeypatch):
     g = load_golden("g23_hybrid_c1.npz")
     sol = make_solver(model, 64, 5e-3, graph_radius=3)
