@@ -17,9 +17,9 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gnn_plasma_flux_b200 import FluxGNN, HybridSolver, MODEL_CONFIG                       # noqa: E402
+from gnn_plasma_flux_b200 import BaselineSolver, HybridSolver                              # noqa: E402
 from gnn_plasma_flux_b200.domain import DomainDecomposedHybridSolver, TorchDistComm        # noqa: E402
-from oracle import ref_port as P                                                            # noqa: E402  (inputs only)
+from gnn_plasma_flux_b200.synthetic import seeded_model, stable_initial_conditions          # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--log2-cells-per-gpu", type=int, default=21)
@@ -40,12 +40,8 @@ comm = TorchDistComm()
 S = 1 << args.log2_cells_per_gpu
 nx = S * world
 dt = 0.02 * (2 * np.pi / nx)
-weights = P.init_weights(0)
-model = FluxGNN(**MODEL_CONFIG)
-model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
-model = model.to(dev).eval()
-grid = P.Grid(nx=nx, dt=dt)
-full = np.stack([P.stable_initial_condition(grid, s) for s in range(args.batch)])            # same on every rank
+model = seeded_model(0, dev)
+full = stable_initial_conditions(BaselineSolver(nx=nx, dt=dt, device=dev), args.batch).cpu().numpy()   # same on every rank
 local_state = torch.from_numpy(np.ascontiguousarray(full[..., rank * S:(rank + 1) * S])).to(dev)
 sol = DomainDecomposedHybridSolver(model, nx, dt=dt, graph_radius=args.radius, rank=rank, world=world, device=dev,
                                    precision=args.precision)

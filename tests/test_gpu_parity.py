@@ -252,6 +252,27 @@ def test_hybrid_window_rollout_vs_oracle(model, weights):
         assert P.rel_err(traj[i].cpu().numpy(), ref[i + 1]).max() <= STEP_TOL * 2 * (i + 1)
 
 
+def test_synthetic_inputs_match_oracle_recipe(weights, built_lib):
+    """bench.py's measured arm builds its inputs without the oracle: same weights, same IC recipe."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    from gnn_plasma_flux_b200.synthetic import seeded_model, stable_initial_conditions
+    sd = seeded_model(0, "cuda").state_dict()
+    for key, val in weights.items():
+        np.testing.assert_array_equal(sd[key].cpu().numpy(), val)
+    sol = BaselineSolver(nx=64, dt=1e-3)
+    grid = P.Grid(nx=64, dt=1e-3)
+    ics = stable_initial_conditions(sol, 300, first_seed=7).cpu().numpy()
+    assert ics.shape == (300, 3, 64) and np.isfinite(ics).all()
+    off = np.random.RandomState(7).uniform(-1e-2, 1e-2, size=(300, 1)).astype(np.float32)
+    for s in (0, 5, 255):
+        ref = P.stable_initial_condition(grid, 7 + s)
+        np.testing.assert_array_equal(ics[s, 0], ref[0])
+        np.testing.assert_array_equal(ics[s, 1], ref[1] + off[s])
+        assert np.abs(ics[s, 2] - ref[2]).max() <= 2e-6 * np.abs(ref[2]).max()
+    np.testing.assert_array_equal(ics[256, 0], ics[0, 0])                    # tiled beyond `distinct`
+    assert not np.array_equal(ics[256, 1], ics[0, 1])
+
+
 def test_step_pinned_host_buffers(model):
     """End-to-end entry on pinned host state: copy-engine and zero-copy variants equal the device path."""
     g = load_golden("g23_hybrid_c1.npz")
