@@ -43,6 +43,11 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p]),
     "fluxgnn_hybrid_rollout_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_double, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_train_acts_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fluxgnn_forward_ring_train": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                           c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_backward_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_backward_ring": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 11),
     "fluxgnn_rollout_metrics": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     "fluxgnn_hybrid_slab_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                          c_float, c_float, c_void_p]),

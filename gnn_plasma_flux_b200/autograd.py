@@ -1,0 +1,72 @@
+"""Autograd support for FluxGNN.forward on the ring.
+
+The reference trains through `model(node_features, edge_index)` with PyTorch autograd
+(scripts/training/train_ablation.py:128-206).  Here the forward pass is the fused sm_100a kernel
+with activations saved, and the backward pass is hand-written CUDA (csrc/train_kernels.cu) behind
+`fluxgnn_backward_ring`; PyTorch only carries the tensors and the graph edge.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class RingFluxes(torch.autograd.Function):
+    """flux_edges[B, 2*hops*nx] = FluxGNN(state[B,3,nx], x[nx]) on the radius-r ring, differentiable
+    w.r.t. `state` and the parameters (passed explicitly so that autograd tracks them)."""
+
+    @staticmethod
+    def forward(ctx, model, state, x, radius, hops, *params):
+        packed = model.packed_weights("fp32")
+        dev = packed.device
+        state = state.detach().to(device=dev, dtype=torch.float32).contiguous()
+        x = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, _, nx = state.shape
+        L = model.num_layers
+        with torch.cuda.device(dev):
+            edges = torch.empty(B, 2 * hops * nx, dtype=torch.float32, device=dev)
+            acts = torch.empty(_lib.lib().fluxgnn_train_acts_bytes(L, B, nx) // 4, dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib().fluxgnn_forward_ring_train(packed.data_ptr(), L, state.data_ptr(), x.data_ptr(), B, nx,
+                                                             radius, hops, edges.data_ptr(), acts.data_ptr(), stream),
+                       "fluxgnn_forward_ring_train")
+        ctx.model, ctx.radius, ctx.hops = model, radius, hops
+        ctx.save_for_backward(state, x, acts)
+        return edges
+
+    @staticmethod
+    def backward(ctx, dflux):
+        model, radius, hops = ctx.model, ctx.radius, ctx.hops
+        state, x, acts = ctx.saved_tensors
+        dev = state.device
+        B, _, nx = state.shape
+        L, H = model.num_layers, model.hidden_dim
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(dev), torch.no_grad():
+            w_in = f32(model.input_mlp[0].weight)
+            w_upd = torch.stack([f32(m[0].weight) for m in model.update_mlps]).contiguous()
+            w_e1, w_e2 = f32(model.edge_mlp[0].weight), f32(model.edge_mlp[2].weight)
+            z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+            g_w_in, g_b_in = z(H, model.input_dim), z(H)
+            g_w_upd, g_b_upd = z(L, H, 2 * H), z(L, H)
+            g_w_e1, g_b_e1, g_w_e2, g_b_e2 = z(H, 2 * H), z(H), z(1, H), z(1)
+            dstate = torch.empty_like(state) if ctx.needs_input_grad[1] else None
+            work = torch.empty(_lib.lib().fluxgnn_backward_workspace_bytes(B, nx) // 4, dtype=torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.lib().fluxgnn_backward_ring(
+                w_in.data_ptr(), w_upd.data_ptr(), w_e1.data_ptr(), w_e2.data_ptr(), L,
+                state.data_ptr(), x.data_ptr(), acts.data_ptr(), f32(dflux).data_ptr(), B, nx, radius, hops,
+                g_w_in.data_ptr(), g_b_in.data_ptr(), g_w_upd.data_ptr(), g_b_upd.data_ptr(),
+                g_w_e1.data_ptr(), g_b_e1.data_ptr(), g_w_e2.data_ptr(), g_b_e2.data_ptr(),
+                dstate.data_ptr() if dstate is not None else None, work.data_ptr(), stream), "fluxgnn_backward_ring")
+        # gradients in model.parameters() order: input_mlp, update_mlps[l], edge_mlp.0, edge_mlp.2
+        grads = [g_w_in, g_b_in]
+        for l in range(L):
+            grads += [g_w_upd[l], g_b_upd[l]]
+        grads += [g_w_e1, g_b_e1, g_w_e2, g_b_e2]
+        return (None, dstate, None, None, None, *grads)
+
+
+def ring_fluxes_with_grad(model, state, x, radius, hops):
+    return RingFluxes.apply(model, state, x, radius, hops, *model.parameters())

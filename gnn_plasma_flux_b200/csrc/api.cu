@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "field_kernels.cuh"
 #include "hybrid_kernel.cuh"
+#include "train_kernels.cuh"
 
 namespace fluxgnn {
 
@@ -211,7 +212,7 @@ static int tc_shape_ok(int whole_ic, int nx, int radius) {
 
 static int forward_ring_impl(int precision, const void* packed, int num_layers, const float* state, const float* x,
                              int B, int nx, int radius, int hops, float* flux_edges, float* face_flux,
-                             void* stream) {
+                             void* stream, float* acts = nullptr) {
     int rc = check_model(packed, num_layers, B, nx, radius);
     if (rc != FLUXGNN_OK) return rc;
     if (!state || !x) return set_error(FLUXGNN_EINVAL, "forward_ring: null state or x");
@@ -226,6 +227,8 @@ static int forward_ring_impl(int precision, const void* packed, int num_layers, 
     a.face_flux = face_flux;
     a.B = B; a.nx = nx; a.radius = radius; a.L = num_layers; a.hops = hops;
     a.do_update = 0; a.steps = 1; a.record_every = 1;
+    a.acts = acts;
+    a.acts_stride = (long long)B * nx * kH;
     int fast = 0;
     rc = plan_tiles(a, &fast);
     if (rc != FLUXGNN_OK) return rc;
@@ -353,6 +356,69 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
         return set_error(FLUXGNN_EINVAL, "hybrid_rollout_tc: precision must be FLUXGNN_TC_TF32X3 or FLUXGNN_TC_TF32");
     return hybrid_rollout_impl(precision, packed_tc, num_layers, state_in, state_out, x, gtab, B, nx, length, radius,
                                c, dt, steps, record_every, traj, workspace, stream);
+}
+
+size_t fluxgnn_train_acts_bytes(int num_layers, int B, int nx) {
+    if (num_layers < 1 || num_layers > kMaxL || B < 1 || nx < 1) return 0;
+    return (size_t)(num_layers + 3) * B * nx * kH * sizeof(float);
+}
+
+int fluxgnn_forward_ring_train(const void* packed, int num_layers, const float* state, const float* x, int B, int nx,
+                               int radius, int hops, float* flux_edges, float* acts, void* stream) {
+    if (!acts || !flux_edges) return set_error(FLUXGNN_EINVAL, "forward_ring_train: flux_edges and acts are required");
+    return forward_ring_impl(0, packed, num_layers, state, x, B, nx, radius, hops, flux_edges, nullptr, stream, acts);
+}
+
+size_t fluxgnn_backward_workspace_bytes(int B, int nx) {
+    if (B < 1 || nx < 1) return 0;
+    return (size_t)3 * B * nx * kH * sizeof(float);
+}
+
+int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_e1, const float* w_e2, int num_layers,
+                          const float* state, const float* x, const float* acts, const float* dflux, int B, int nx,
+                          int radius, int hops, float* g_w_in, float* g_b_in, float* g_w_upd, float* g_b_upd,
+                          float* g_w_e1, float* g_b_e1, float* g_w_e2, float* g_b_e2, float* dstate, void* workspace,
+                          void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int L = num_layers;
+    if (L < 1 || L > kMaxL) return set_error(FLUXGNN_EUNSUP, "num_layers must be in 1..%d, got %d", kMaxL, L);
+    if (B < 1 || nx < 1 || radius < 1 || hops < 1 || hops > kMaxHops || hops > radius)
+        return set_error(FLUXGNN_EINVAL, "backward_ring: bad shape (B=%d nx=%d radius=%d hops=%d)", B, nx, radius, hops);
+    if (!w_in || !w_upd || !w_e1 || !w_e2 || !state || !x || !acts || !dflux || !g_w_in || !g_b_in || !g_w_upd ||
+        !g_b_upd || !g_w_e1 || !g_b_e1 || !g_w_e2 || !g_b_e2 || !workspace)
+        return set_error(FLUXGNN_EINVAL, "backward_ring: null pointer");
+    const long long rows = (long long)B * nx;
+    const size_t stride = (size_t)rows * kH;
+    float* G0 = (float*)workspace;
+    float* G1 = G0 + stride;
+    float* G2 = G1 + stride;
+    const float* Pa = acts + (size_t)(L + 1) * stride;
+    const float* Qa = acts + (size_t)(L + 2) * stride;
+    const dim3 blk(32, 8);
+    const unsigned g8 = (unsigned)((rows + 7) / 8), g64 = (unsigned)((rows + 63) / 64), g256 = (unsigned)((rows + 255) / 256);
+    // edge readout
+    bwd_edge_kernel<<<g8, blk, 0, stream>>>(Pa, Qa, w_e2, dflux, G0, G1, g_w_e2, g_b_e1, g_b_e2, rows, nx, hops);
+    const float* HL = acts + (size_t)L * stride;
+    bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G0, HL, g_w_e1, 2 * kH, rows);          // d W1[:, :H] = dP^T h
+    bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G1, HL, g_w_e1 + kH, 2 * kH, rows);     // d W1[:, H:] = dQ^T h
+    bwd_gemm_nn_kernel<<<g64, 256, 0, stream>>>(G0, w_e1, G1, w_e1 + kH, 2 * kH, G2, rows);
+    count_launch(4);
+    // message-passing layers, last to first
+    for (int l = L - 1; l >= 0; --l) {
+        const float* W = w_upd + (size_t)l * kH * 2 * kH;
+        float* gW = g_w_upd + (size_t)l * kH * 2 * kH;
+        const float* Hl = acts + (size_t)l * stride;
+        bwd_mask_mean_kernel<<<g8, blk, 0, stream>>>(G2, acts + (size_t)(l + 1) * stride, G0, G1, g_b_upd + l * kH, rows,
+                                                     nx, radius);
+        bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G0, Hl, gW, 2 * kH, rows);           // d W[:, :H] = dpre^T h
+        bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G1, Hl, gW + kH, 2 * kH, rows);      // d W[:, H:] = mean(dpre)^T h
+        bwd_gemm_nn_kernel<<<g64, 256, 0, stream>>>(G0, W, G1, W + kH, 2 * kH, G2, rows);
+        count_launch(4);
+    }
+    bwd_input_kernel<<<g8, blk, 0, stream>>>(G2, acts, w_in, state, x, dstate, g_w_in, g_b_in, rows, nx);
+    count_launch();
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    return FLUXGNN_OK;
 }
 
 int fluxgnn_rollout_metrics(const float* pred, const float* truth, long long num_states, int nx, float* out,

@@ -26,6 +26,8 @@ struct HybridArgs {
     int steps, record_every;   // steps > 1 only for whole-IC update mode
     float c, dt;               // float32(dt/dx), float32(dt)
     int tc_parts;              // tensor path only: 2 = tf32x3 (hi/lo split), 1 = plain tf32
+    float* acts;               // nullable (FP32-pipe kernel, training forward): saved activations, row-major
+    long long acts_stride;     //   [L+3][B*nx][128]: h^0..h^L, then P + b1 and Q of the edge readout
     int split;                 // FP32-pipe kernel: two skewed 64-row groups per tile (whole-IC tiles, nx | 64)
     int slab;                  // 1: one slab of a domain-decomposed grid.  state_in and x are
     int ld_in;                 //    [..][ld_in] = nx owned cells + `halo` ghost cells per side, no

@@ -180,6 +180,21 @@ __device__ __forceinline__ void load_window(float (&v)[16], const float* zrow, i
     v[12] = r.x; v[13] = r.y; v[14] = r.z; v[15] = r.w;
 }
 
+// Training forward: copy the group's rows of a feature-major activation buffer to the row-major
+// global array dst[(ic*nx + cell)][128] (coalesced 512-byte rows; rows this tile does not own are skipped).
+__device__ __forceinline__ void save_rows(const float* buf, float* dst, const TileSmem& S, int lt, int gthreads,
+                                          int row0, int nrows, int nx) {
+    for (int w = lt; w < nrows * 32; w += gthreads) {
+        const int r = row0 + (w >> 5), fq = w & 31;
+        const int ic = S.rowIC[r];
+        if (ic < 0) continue;
+        const size_t grow = (size_t)ic * nx + S.rowCell[r];
+        const float4 v = make_float4(buf[sw_off(4 * fq, r)], buf[sw_off(4 * fq + 1, r)], buf[sw_off(4 * fq + 2, r)],
+                                     buf[sw_off(4 * fq + 3, r)]);
+        *reinterpret_cast<float4*>(dst + grow * kH + 4 * fq) = v;
+    }
+}
+
 }  // namespace
 
 // R = 1..4: radius known at compile time, 8-row groups never straddle an IC
@@ -342,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                 }
             }
             named_sync(bar, gthreads);
+            if (a.acts != nullptr) save_rows(S.Hs, a.acts, S, lt, gthreads, row0, nrows, nx);
 
             for (int layer = 0; layer <= a.L; ++layer) {
                 // ---- pass 0: Z = W[:, H:] h -> shared memory;  pass 1: Y = W[:, :H] h + b -> registers
@@ -402,10 +418,23 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
                     }
                     named_sync(bar, gthreads);  // h' complete; Z free
+                    if (a.acts != nullptr)
+                        save_rows(S.Hs, a.acts + (size_t)(layer + 1) * a.acts_stride, S, lt, gthreads, row0, nrows, nx);
                 } else {
                     // ---- edge readout (src/flux_gnn.py:63-66): acc = P + b1, Zs = Q ---------
                     //   fwd edge (row j, col j+k):  w2 . relu(P_j + Q_{j+k})
                     //   bwd edge (row j, col j-k):  w2 . relu(P_j + Q_{j-k})   (edge index j-k)
+                    if (a.acts != nullptr) {             // training forward: keep P + b1 and Q for the backward pass
+                        save_rows(S.Zs, a.acts + (size_t)(a.L + 2) * a.acts_stride, S, lt, gthreads, row0, nrows, nx);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {    // h^L is dead: park P in its buffer
+                            float* hr = S.Hs + col_of(tx, j) * kTileRows;
+                            *reinterpret_cast<float4*>(hr + ((c0 ^ sw) << 2)) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+                            *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
+                        }
+                        named_sync(bar, gthreads);
+                        save_rows(S.Hs, a.acts + (size_t)(a.L + 1) * a.acts_stride, S, lt, gthreads, row0, nrows, nx);
+                    }
 #pragma unroll
                     for (int hop = 1; hop <= kMaxHops; ++hop) {
                         if (hop <= a.hops) {

@@ -1,0 +1,307 @@
+// Backward pass of FluxGNN.forward on the radius-r ring: gradients of the
+// directed-edge fluxes w.r.t. every parameter and the node features, from activations the
+// forward tile kernel saved.  What it differentiates (paths under /root/reference):
+//   src/flux_gnn.py:49      h0 = relu(X W_in^T + b_in)
+//   src/flux_gnn.py:53-60   h' = relu(Wa h + Wb mean_nbr(h) + b)          (W = [Wa | Wb])
+//   src/flux_gnn.py:63-66   f(a->b) = w2 . relu(W1a h_a + W1b h_b + b1) + b2
+// used by the training loop scripts/training/train_ablation.py:128-206 through autograd.
+//
+// All tensors are row-major [row][feature] with row = ic * nx + cell.  mean_nbr is symmetric,
+// so with dpre = dh' * (h' > 0) and dZ = mean_nbr(dpre):
+//   dh = dpre Wa + dZ Wb,   dWa = dpre^T h,   dWb = dZ^T h,   db = sum_rows dpre.
+#include "common.cuh"
+#include "train_kernels.cuh"
+
+namespace fluxgnn {
+
+namespace {
+
+__device__ __forceinline__ float4 relu_mask(float4 g, float4 h) {
+    return make_float4(h.x > 0.f ? g.x : 0.f, h.y > 0.f ? g.y : 0.f, h.z > 0.f ? g.z : 0.f, h.w > 0.f ? g.w : 0.f);
+}
+
+__device__ __forceinline__ void add4(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// one feature of the edge-readout backward: the four pre-activations row i takes part in
+__device__ __forceinline__ void edge_acc(float& gp, float& gq, float& gw, float w, float s_f, float s_bm, float s_fm,
+                                         float s_b, float gf_i, float gf_m, float gb_i, float gb_m) {
+    gp += w * ((s_f > 0.f ? gf_i : 0.f) + (s_bm > 0.f ? gb_m : 0.f));
+    gq += w * ((s_fm > 0.f ? gf_m : 0.f) + (s_b > 0.f ? gb_i : 0.f));
+    gw += gf_i * fmaxf(s_f, 0.f) + gb_i * fmaxf(s_b, 0.f);
+}
+
+}  // namespace
+
+// dpre = dH * (H' > 0);  dZ = (1/2r) sum_{k=1..r} (dpre_{i-k} + dpre_{i+k});  db += sum_rows dpre.
+// One thread per (row, 4 features); blockDim = (32, 8): 32 feature quads x 8 rows.
+__global__ void __launch_bounds__(256) bwd_mask_mean_kernel(const float* __restrict__ dH, const float* __restrict__ Hn,
+                                                            float* __restrict__ dpre, float* __restrict__ dZ,
+                                                            float* __restrict__ db, long long rows, int nx, int radius) {
+    const int fq = threadIdx.x;                                   // feature quad 0..31
+    const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows) {
+        const long long ic_base = (row / nx) * nx;
+        const int cell = (int)(row - ic_base);
+        const float4* g4 = reinterpret_cast<const float4*>(dH);
+        const float4* h4 = reinterpret_cast<const float4*>(Hn);
+        mine = relu_mask(g4[row * 32 + fq], h4[row * 32 + fq]);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 1; k <= radius; ++k) {
+            const long long rp = ic_base + (cell + k) % nx;
+            long long rm = cell - k;
+            rm = ic_base + ((rm % nx) + nx) % nx;
+            add4(acc, relu_mask(g4[rp * 32 + fq], h4[rp * 32 + fq]));
+            add4(acc, relu_mask(g4[rm * 32 + fq], h4[rm * 32 + fq]));
+        }
+        const float inv = 1.0f / (float)(2 * radius);
+        reinterpret_cast<float4*>(dpre)[row * 32 + fq] = mine;
+        reinterpret_cast<float4*>(dZ)[row * 32 + fq] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+    // bias gradient: reduce the 8 rows of the block, then one atomic per feature
+    __shared__ float4 red[8][32];
+    red[threadIdx.y][fq] = mine;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float4 s = red[0][fq];
+        for (int r = 1; r < 8; ++r) add4(s, red[r][fq]);
+        atomicAdd(db + 4 * fq + 0, s.x);
+        atomicAdd(db + 4 * fq + 1, s.y);
+        atomicAdd(db + 4 * fq + 2, s.z);
+        atomicAdd(db + 4 * fq + 3, s.w);
+    }
+}
+
+// C[rows][128] = A1[rows][128] W1[128][ldw] + A2[rows][128] W2[128][ldw]   (W row-major, first 128 columns used)
+// Block: 64 rows x 128 columns, 256 threads, 4 rows x 8 columns each, K in slabs of 16.
+__global__ void __launch_bounds__(256) bwd_gemm_nn_kernel(const float* __restrict__ A1, const float* __restrict__ W1,
+                                                          const float* __restrict__ A2, const float* __restrict__ W2,
+                                                          int ldw, float* __restrict__ C, long long rows) {
+    __shared__ float As[16][64 + 4];       // [k][row]
+    __shared__ float Ws[16][128];          // [k][col]
+    const int tid = threadIdx.x;
+    const int tr = tid >> 4, tc = tid & 15;                      // 16 x 16 threads
+    const long long row0 = (long long)blockIdx.x * 64;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int prod = 0; prod < 2; ++prod) {
+        const float* A = prod ? A2 : A1;
+        const float* W = prod ? W2 : W1;
+        if (A == nullptr) continue;
+        for (int k0 = 0; k0 < kH; k0 += 16) {
+            // A slab: 64 rows x 16 k  (thread: row = tid/4, 4 consecutive k)
+            {
+                const int r = tid >> 2, kq = (tid & 3) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < rows) v = *reinterpret_cast<const float4*>(A + (row0 + r) * kH + k0 + kq);
+                As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+            }
+            // W slab: 16 k x 128 columns  (thread: k = tid/16, 8 consecutive columns)
+            {
+                const int k = tid >> 4, c = (tid & 15) * 8;
+                const float4 v0 = *reinterpret_cast<const float4*>(W + (size_t)(k0 + k) * ldw + c);
+                const float4 v1 = *reinterpret_cast<const float4*>(W + (size_t)(k0 + k) * ldw + c + 4);
+                *reinterpret_cast<float4*>(&Ws[k][c]) = v0;
+                *reinterpret_cast<float4*>(&Ws[k][c + 4]) = v1;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[k][tr * 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&Ws[k][tc * 8]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Ws[k][tc * 8 + 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = row0 + tr * 4 + i;
+        if (r < rows) {
+            *reinterpret_cast<float4*>(C + r * kH + tc * 8) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4*>(C + r * kH + tc * 8 + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+    }
+}
+
+// dW[n][ldw-strided k] += sum_rows A[row][n] * Bm[row][k]   (both [rows][128]); split over row slabs.
+// Block: 256 rows, full 128 x 128 output, 256 threads x (8 x 8), atomicAdd at the end.
+__global__ void __launch_bounds__(256) bwd_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                          float* __restrict__ dW, int ldw, long long rows) {
+    __shared__ float As[16][128];          // [row in slab][n]
+    __shared__ float Bs[16][128];          // [row in slab][k]
+    const int tid = threadIdx.x;
+    const int tn = tid >> 4, tk = tid & 15;
+    const long long row_begin = (long long)blockIdx.x * 256;
+    const long long row_end = row_begin + 256 < rows ? row_begin + 256 : rows;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (long long r0 = row_begin; r0 < row_end; r0 += 16) {
+        {
+            const int r = tid >> 4, c = (tid & 15) * 8;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+            if (r0 + r < row_end) {
+                a0 = *reinterpret_cast<const float4*>(A + (r0 + r) * kH + c);
+                a1 = *reinterpret_cast<const float4*>(A + (r0 + r) * kH + c + 4);
+                b0 = *reinterpret_cast<const float4*>(Bm + (r0 + r) * kH + c);
+                b1 = *reinterpret_cast<const float4*>(Bm + (r0 + r) * kH + c + 4);
+            }
+            *reinterpret_cast<float4*>(&As[r][c]) = a0;
+            *reinterpret_cast<float4*>(&As[r][c + 4]) = a1;
+            *reinterpret_cast<float4*>(&Bs[r][c]) = b0;
+            *reinterpret_cast<float4*>(&Bs[r][c + 4]) = b1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[r][tn * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[r][tn * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[r][tk * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[r][tk * 8 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dW + (size_t)(tn * 8 + i) * ldw + tk * 8 + j, acc[i][j]);
+}
+
+// Edge readout backward.  P already contains b1.  For hop k (edge blocks [i -> i+k], [i+k -> i]):
+//   fwd_k[i] = w2 . relu(P_i + Q_{i+k}) + b2,   bwd_k[i] = w2 . relu(P_{i+k} + Q_i) + b2
+// dflux layout per IC: [2*hops][nx].  Outputs dP, dQ [rows][128]; accumulates dw2[128], db1[128], db2[1].
+__global__ void __launch_bounds__(256) bwd_edge_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                       const float* __restrict__ w2, const float* __restrict__ dflux,
+                                                       float* __restrict__ dP, float* __restrict__ dQ,
+                                                       float* __restrict__ dw2, float* __restrict__ db1,
+                                                       float* __restrict__ db2, long long rows, int nx, int hops) {
+    const int fq = threadIdx.x;
+    const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f), gq = gp, gw = gp;
+    float gb2 = 0.f;
+    if (row < rows) {
+        const long long ic = row / nx, ic_base = ic * nx;
+        const int cell = (int)(row - ic_base);
+        const float4* P4 = reinterpret_cast<const float4*>(P);
+        const float4* Q4 = reinterpret_cast<const float4*>(Q);
+        const float4 w = reinterpret_cast<const float4*>(w2)[fq];
+        const float4 p0 = P4[row * 32 + fq], q0 = Q4[row * 32 + fq];
+        const float* df = dflux + ic * 2 * hops * nx;
+        for (int k = 1; k <= hops; ++k) {
+            const int cp = (cell + k) % nx, cm = ((cell - k) % nx + nx) % nx;
+            const long long rp = ic_base + cp, rm = ic_base + cm;
+            const float4 pp = P4[rp * 32 + fq], qp = Q4[rp * 32 + fq];
+            const float4 pm = P4[rm * 32 + fq], qm = Q4[rm * 32 + fq];
+            const float* dfw = df + (size_t)(2 * (k - 1)) * nx;       // fwd block of hop k
+            const float* dbw = dfw + nx;                              // bwd block of hop k
+            const float gf_i = dfw[cell], gf_m = dfw[cm], gb_i = dbw[cell], gb_m = dbw[cm];
+            // pre-activations this row takes part in
+            const float4 s_f = make_float4(p0.x + qp.x, p0.y + qp.y, p0.z + qp.z, p0.w + qp.w);   // fwd_k[i]   : P_i + Q_{i+k}
+            const float4 s_bm = make_float4(p0.x + qm.x, p0.y + qm.y, p0.z + qm.z, p0.w + qm.w);  // bwd_k[i-k] : P_i + Q_{i-k}
+            const float4 s_fm = make_float4(pm.x + q0.x, pm.y + q0.y, pm.z + q0.z, pm.w + q0.w);  // fwd_k[i-k] : P_{i-k} + Q_i
+            const float4 s_b = make_float4(pp.x + q0.x, pp.y + q0.y, pp.z + q0.z, pp.w + q0.w);   // bwd_k[i]   : P_{i+k} + Q_i
+            edge_acc(gp.x, gq.x, gw.x, w.x, s_f.x, s_bm.x, s_fm.x, s_b.x, gf_i, gf_m, gb_i, gb_m);
+            edge_acc(gp.y, gq.y, gw.y, w.y, s_f.y, s_bm.y, s_fm.y, s_b.y, gf_i, gf_m, gb_i, gb_m);
+            edge_acc(gp.z, gq.z, gw.z, w.z, s_f.z, s_bm.z, s_fm.z, s_b.z, gf_i, gf_m, gb_i, gb_m);
+            edge_acc(gp.w, gq.w, gw.w, w.w, s_f.w, s_bm.w, s_fm.w, s_b.w, gf_i, gf_m, gb_i, gb_m);
+            if (fq == 0) gb2 += gf_i + gb_i;
+        }
+        reinterpret_cast<float4*>(dP)[row * 32 + fq] = gp;
+        reinterpret_cast<float4*>(dQ)[row * 32 + fq] = gq;
+    }
+    __shared__ float4 redw[8][32], redb[8][32];
+    __shared__ float redb2[8];
+    redw[threadIdx.y][fq] = gw;
+    redb[threadIdx.y][fq] = gp;                                       // db1 = sum_rows dP
+    if (fq == 0) redb2[threadIdx.y] = gb2;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float4 sw = redw[0][fq], sb = redb[0][fq];
+        for (int r = 1; r < 8; ++r) { add4(sw, redw[r][fq]); add4(sb, redb[r][fq]); }
+        atomicAdd(dw2 + 4 * fq + 0, sw.x); atomicAdd(dw2 + 4 * fq + 1, sw.y);
+        atomicAdd(dw2 + 4 * fq + 2, sw.z); atomicAdd(dw2 + 4 * fq + 3, sw.w);
+        atomicAdd(db1 + 4 * fq + 0, sb.x); atomicAdd(db1 + 4 * fq + 1, sb.y);
+        atomicAdd(db1 + 4 * fq + 2, sb.z); atomicAdd(db1 + 4 * fq + 3, sb.w);
+        if (fq == 0) {
+            float s = 0.f;
+            for (int r = 0; r < 8; ++r) s += redb2[r];
+            atomicAdd(db2, s);
+        }
+    }
+}
+
+// Input layer backward: dpre0 = dH0 * (H0 > 0);  dfeat[row][f] = sum_n dpre0[n] W_in[n][f];
+// dW_in[n][f] += dpre0[n] feat[f];  db_in[n] += dpre0[n].  feat = (n, u, E, x) of the row.
+// One warp per row (lane owns features lane, lane+32, ...); 8 rows per block.
+__global__ void __launch_bounds__(256) bwd_input_kernel(const float* __restrict__ dH0, const float* __restrict__ H0,
+                                                        const float* __restrict__ w_in, const float* __restrict__ state,
+                                                        const float* __restrict__ x, float* __restrict__ dstate,
+                                                        float* __restrict__ dw_in, float* __restrict__ db_in,
+                                                        long long rows, int nx) {
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const long long row = (long long)blockIdx.x * blockDim.y + wy;
+    __shared__ float sgw[8][kH][kF];
+    __shared__ float sgb[8][kH];
+    float feat[4] = {0.f, 0.f, 0.f, 0.f};
+    float dfe[4] = {0.f, 0.f, 0.f, 0.f};
+    long long ic = 0;
+    int cell = 0;
+    if (row < rows) {
+        ic = row / nx;
+        cell = (int)(row - ic * nx);
+        const float* st = state + ic * 3 * nx + cell;
+        feat[0] = st[0]; feat[1] = st[nx]; feat[2] = st[2 * (size_t)nx]; feat[3] = x[cell];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int n = lane + 32 * q;
+        float g = 0.f;
+        if (row < rows) {
+            const float h = H0[row * kH + n];
+            g = h > 0.f ? dH0[row * kH + n] : 0.f;
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            dfe[f] = fmaf(g, w_in[n * kF + f], dfe[f]);
+            sgw[wy][n][f] = g * feat[f];
+        }
+        sgb[wy][n] = g;
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+        for (int o = 16; o > 0; o >>= 1) dfe[f] += __shfl_xor_sync(0xffffffffu, dfe[f], o);
+    if (row < rows && lane == 0 && dstate != nullptr) {
+        float* ds = dstate + ic * 3 * nx + cell;
+        ds[0] = dfe[0]; ds[nx] = dfe[1]; ds[2 * (size_t)nx] = dfe[2];      // x has no gradient
+    }
+    __syncthreads();
+    const int t = wy * 32 + lane;                                          // 256 threads: 2 per feature n
+    {
+        const int n = t >> 1, f0 = (t & 1) * 2;
+        float s0 = 0.f, s1 = 0.f, sb = 0.f;
+        for (int r = 0; r < 8; ++r) { s0 += sgw[r][n][f0]; s1 += sgw[r][n][f0 + 1]; sb += sgb[r][n]; }
+        atomicAdd(dw_in + n * kF + f0, s0);
+        atomicAdd(dw_in + n * kF + f0 + 1, s1);
+        if ((t & 1) == 0) atomicAdd(db_in + n, sb);
+    }
+}
+
+}  // namespace fluxgnn

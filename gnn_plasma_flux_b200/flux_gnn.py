@@ -3,8 +3,9 @@
 Same constructor, same sub-module names (so `state_dict()` / `load_state_dict()`
 exchange checkpoints with the reference, src/flux_gnn.py:17-38) and the same
 `forward(node_features[N,F], edge_index[2,E]) -> flux[E]` call
-(src/flux_gnn.py:40-67).  The forward pass runs the fused sm_100a stencil kernel
-and is inference-only (no autograd graph is recorded).
+(src/flux_gnn.py:40-67).  The forward pass runs the fused sm_100a stencil kernel; when
+gradients are enabled it also saves activations and backward() runs hand-written CUDA
+(autograd.py, csrc/train_kernels.cu), so the reference's training loops work unchanged.
 
 Deliberate deviations, all raised loudly rather than served by a second backend:
   * `edge_index` must be the periodic ring that `build_chain_graph` produces
@@ -123,6 +124,14 @@ class FluxGNN(nn.Module):
         if radius > _lib.MAX_HOPS:
             raise NotImplementedError(f"forward() emits at most {_lib.MAX_HOPS} hop blocks; radius={radius}")
         packed = self.packed_weights()
+        wants_grad = torch.is_grad_enabled() and (node_features.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
+        if wants_grad:
+            # training (scripts/training/train_ablation.py:128-206): saved activations + CUDA backward
+            from .autograd import ring_fluxes_with_grad
+            feats = node_features.to(device=packed.device, dtype=torch.float32)
+            state = feats[:, :3].t().unsqueeze(0)                # [1,3,N], still attached to node_features
+            return ring_fluxes_with_grad(self, state, feats[:, 3], radius, radius)[0]
         feats = node_features.detach().to(device=packed.device, dtype=torch.float32)
         state = feats[:, :3].t().contiguous().unsqueeze(0)       # [1,3,N]
         x = feats[:, 3].contiguous()

@@ -163,6 +163,28 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                               int steps, int record_every, float* traj,
                               void* workspace, void* stream);
 
+/* ---- training: FluxGNN.forward with saved activations and its backward pass --
+ * What scripts/training/train_ablation.py:128-206 needs from the model: the edge fluxes of
+ * src/flux_gnn.py:40-67 on the ring, differentiable w.r.t. every parameter and the node features.
+ *   fluxgnn_forward_ring_train  = fluxgnn_forward_ring (fp32 kernel) that also stores, row-major
+ *       [row = ic*nx + cell][128], h^0..h^L, (P + b1) and Q of the edge readout into
+ *       acts[(L+3)][B*nx][128]  (fluxgnn_train_acts_bytes).
+ *   fluxgnn_backward_ring: given dflux[B][2*hops*nx] (gradient w.r.t. flux_edges) ADDS the
+ *       parameter gradients into g_* (nn.Linear layouts, the caller zeroes them) and writes
+ *       dstate[B][3][nx] (gradient w.r.t. n, u, E; nullable).  Weights are the raw state_dict tensors
+ *       (w_upd contiguous over layers).  workspace: fluxgnn_backward_workspace_bytes(B, nx). */
+size_t fluxgnn_train_acts_bytes(int num_layers, int B, int nx);
+int fluxgnn_forward_ring_train(const void* packed, int num_layers, const float* state, const float* x,
+                               int B, int nx, int radius, int hops, float* flux_edges, float* acts,
+                               void* stream);
+size_t fluxgnn_backward_workspace_bytes(int B, int nx);
+int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_e1, const float* w_e2,
+                          int num_layers, const float* state, const float* x, const float* acts,
+                          const float* dflux, int B, int nx, int radius, int hops,
+                          float* g_w_in, float* g_b_in, float* g_w_upd, float* g_b_upd,
+                          float* g_w_e1, float* g_b_e1, float* g_w_e2, float* g_b_e2,
+                          float* dstate, void* workspace, void* stream);
+
 /* ---- rollout diagnostics on the device ---------------------------
  * The metrics every evaluation script of the reference computes on the host after
  * copying whole trajectories back (scripts/evaluation/evaluate_all.py:118-159,

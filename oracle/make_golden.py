@@ -203,6 +203,39 @@ def main():
     g7.update(ds_state_t=st_, ds_flux_t=fl_, ds_state_next=nx_, ds_x=x_, ds_dx=dx_)
     np.savez_compressed(os.path.join(OUT, "g7_metrics_datagen.npz"), **g7)
 
+    # ---- G8 gradients of the reference model through autograd ------------------
+    g8 = {}
+    state = BaselineSolver(nx=64).initial_condition(seed=21)
+    for r in (1, 2):
+        ref_model = FluxGNN(input_dim=4, hidden_dim=128, num_layers=4)
+        ref_model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+        nf = torch.from_numpy(P.node_features(state, P.Grid(nx=64).x)).requires_grad_(True)
+        edges = torch.from_numpy(P.ring_edges(64, r))
+        cot = torch.from_numpy(np.random.RandomState(100 + r).randn(2 * r * 64).astype(np.float32))
+        (ref_model(nf, edges) * cot).sum().backward()
+        g8[f"cot_r{r}"] = cot.numpy()
+        g8[f"dfeat_r{r}"] = nf.grad.numpy()
+        for name, p_ in ref_model.named_parameters():
+            g = p_.grad.numpy()
+            if g.size <= 1024:
+                g8[f"grad_r{r}_{name}"] = g
+            else:                                            # big matrices: norm + a corner + a few rows
+                g8[f"gradnorm_r{r}_{name}"] = np.float64(np.linalg.norm(g.astype(np.float64)))
+                g8[f"gradcorner_r{r}_{name}"] = g[:8, :8].copy()
+                g8[f"gradrows_r{r}_{name}"] = g[[5, 77], :].copy()
+        # the oracle's closed form under fp64 autograd agrees with the reference's autograd
+        wt = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in weights.items()}
+        st = torch.from_numpy(state).double()[None].requires_grad_(True)
+        fl = batched.edge_fluxes(wt, st, torch.from_numpy(P.Grid(nx=64).x.astype(np.float32)), r, hops=r)[0]
+        (fl * cot.double()).sum().backward()
+        for name, p_ in ref_model.named_parameters():
+            ref_g, orc_g = p_.grad.double().numpy(), wt[name].grad.numpy()
+            assert np.abs(ref_g - orc_g).max() <= 2e-4 * max(np.abs(ref_g).max(), 1e-6), (r, name)
+        assert np.abs(st.grad[0].numpy().T - nf.grad.numpy()[:, :3]).max() <= 2e-4 * np.abs(nf.grad.numpy()).max()
+        print(f"  ok  reference autograd vs oracle fp64 autograd, radius {r}")
+    g8["state"] = state
+    np.savez_compressed(os.path.join(OUT, "g8_gradients.npz"), **g8)
+
     manifest = {
         "generated_by": "oracle/make_golden.py",
         "reference": "/root/reference (shanedirksen/gnn-plasma-flux, unmodified)",

@@ -521,3 +521,88 @@ def test_generate_dataset_golden(built_lib, tmp_path):
     saved = np.load(out)
     assert sorted(saved.files) == ["dt", "dx", "flux_t", "nu", "state_next", "state_t", "x"]     # generate_data.py:38-47
     assert float(saved["dx"]) == float(g7["ds_dx"])
+
+
+# ----------------------------------------------------------------------------- next row N2: training (autograd + CUDA backward)
+GRAD_TOL = 2e-4        # fp32 kernels + atomic accumulation vs the reference's fp32 autograd / the fp64 oracle
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.mark.parametrize("radius", [1, 2])
+def test_forward_backward_vs_reference_autograd(weights, built_lib, radius):
+    """model(node_features, edge_index) with gradients enabled: the call of train_ablation.py:143-146."""
+    from gnn_plasma_flux_b200 import FluxGNN, MODEL_CONFIG, build_chain_graph
+    g8 = load_golden("g8_gradients.npz")
+    m = FluxGNN(**MODEL_CONFIG)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    m = m.cuda().train()
+    nf, ei = build_chain_graph(g8["state"], P.Grid(nx=64).x, "cuda", radius=radius)
+    nf.requires_grad_(True)
+    flux = m(nf, ei)
+    assert flux.requires_grad and flux.shape == (2 * radius * 64,)
+    (flux * torch.from_numpy(g8[f"cot_r{radius}"]).cuda()).sum().backward()
+    assert _rel(nf.grad.cpu().numpy()[:, :3], g8[f"dfeat_r{radius}"][:, :3]) <= GRAD_TOL
+    for name, p_ in m.named_parameters():
+        g = p_.grad.cpu().numpy()
+        if f"grad_r{radius}_{name}" in g8:
+            assert _rel(g, g8[f"grad_r{radius}_{name}"]) <= GRAD_TOL, name
+        else:
+            assert abs(np.linalg.norm(g.astype(np.float64)) / float(g8[f"gradnorm_r{radius}_{name}"]) - 1) <= GRAD_TOL, name
+            scale = np.abs(g).max()
+            assert np.abs(g[:8, :8] - g8[f"gradcorner_r{radius}_{name}"]).max() <= GRAD_TOL * scale, name
+            assert np.abs(g[[5, 77], :] - g8[f"gradrows_r{radius}_{name}"]).max() <= GRAD_TOL * scale, name
+    # an optimiser step changes the parameters in place -> the packed weights are rebuilt
+    before = m(nf.detach(), ei).detach().clone()
+    torch.optim.SGD(m.parameters(), lr=1e-2).step()
+    assert not torch.equal(m(nf.detach(), ei).detach(), before)
+
+
+@pytest.mark.parametrize("nx,B,radius,hops", [(64, 5, 3, 3), (1024, 2, 2, 1), (40, 3, 2, 2), (128, 2, 4, 4)])
+def test_backward_batched_vs_oracle_autograd(weights, built_lib, nx, B, radius, hops):
+    """Batched entry (whole-IC, window and generic tiles) vs fp64 autograd of the oracle's closed form."""
+    from gnn_plasma_flux_b200 import FluxGNN, MODEL_CONFIG
+    from gnn_plasma_flux_b200.autograd import ring_fluxes_with_grad
+    m = FluxGNN(**MODEL_CONFIG)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    m = m.cuda()
+    grid = P.Grid(nx=nx)
+    state = np.stack([P.initial_condition(grid, seed=s) for s in range(B)])
+    x32 = torch.from_numpy(grid.x.astype(np.float32))
+    cot = torch.from_numpy(np.random.RandomState(nx + radius).randn(B, 2 * hops * nx).astype(np.float32))
+    st = torch.from_numpy(state).cuda().requires_grad_(True)
+    flux = ring_fluxes_with_grad(m, st, x32.cuda(), radius, hops)
+    (flux * cot.cuda()).sum().backward()
+    wt = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in weights.items()}
+    st64 = torch.from_numpy(state).double().requires_grad_(True)
+    ref = batched.edge_fluxes(wt, st64, x32, radius, hops=hops)
+    assert _rel(flux.detach().cpu().numpy(), ref.detach().numpy()) <= STEP_TOL
+    (ref * cot.double()).sum().backward()
+    assert _rel(st.grad.cpu().numpy(), st64.grad.numpy()) <= GRAD_TOL
+    for name, p_ in m.named_parameters():
+        assert _rel(p_.grad.cpu().numpy(), wt[name].grad.numpy()) <= GRAD_TOL, name
+
+
+def test_training_loop_reduces_flux_loss(weights, built_lib):
+    """A miniature of train_ablation.py: Adam on the flux MSE against the classical flux n*u, through the
+    drop-in model (CUDA forward with saved activations + CUDA backward)."""
+    from gnn_plasma_flux_b200 import FluxGNN, MODEL_CONFIG, build_chain_graph
+    torch.manual_seed(0)
+    m = FluxGNN(**MODEL_CONFIG).cuda().train()
+    grid = P.Grid(nx=64)
+    state = P.initial_condition(grid, seed=4)
+    target = torch.from_numpy(state[0] * state[1]).cuda()
+    nf, ei = build_chain_graph(state, grid.x, "cuda")
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(25):
+        opt.zero_grad()
+        flux = m(nf, ei)
+        face = 0.5 * (flux[:64] + flux[64:])                       # src/hybrid_solver.py:45-48
+        loss = torch.mean((face - target) ** 2)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], losses[::6]
