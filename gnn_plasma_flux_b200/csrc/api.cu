@@ -395,7 +395,14 @@ int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_
     const float* Pa = acts + (size_t)(L + 1) * stride;
     const float* Qa = acts + (size_t)(L + 2) * stride;
     const dim3 blk(32, 8);
-    const unsigned g8 = (unsigned)((rows + 7) / 8), g64 = (unsigned)((rows + 63) / 64), g256 = (unsigned)((rows + 255) / 256);
+    int sms = 0;
+    int rc_sm = sm_count(&sms);
+    if (rc_sm != FLUXGNN_OK) return rc_sm;
+    const long long row_groups = (rows + 7) / 8;                  // elementwise kernels: grid-stride, 8 rows per block pass
+    const unsigned g8 = (unsigned)(row_groups < 16LL * sms ? row_groups : 16LL * sms);
+    const unsigned g64 = (unsigned)((rows + 63) / 64);
+    const long long slabs = (rows + 255) / 256;                   // weight-gradient GEMMs: at most 2 blocks per SM
+    const unsigned g256 = (unsigned)(slabs < 2LL * sms ? slabs : 2LL * sms);
     // edge readout
     bwd_edge_kernel<<<g8, blk, 0, stream>>>(Pa, Qa, w_e2, dflux, G0, G1, g_w_e2, g_b_e1, g_b_e2, rows, nx, hops);
     const float* HL = acts + (size_t)L * stride;

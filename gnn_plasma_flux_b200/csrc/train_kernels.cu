@@ -38,14 +38,15 @@ __global__ void __launch_bounds__(256) bwd_mask_mean_kernel(const float* __restr
                                                             float* __restrict__ dpre, float* __restrict__ dZ,
                                                             float* __restrict__ db, long long rows, int nx, int radius) {
     const int fq = threadIdx.x;                                   // feature quad 0..31
-    const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < rows) {
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);                // this thread's share of the bias gradient
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+         row += (long long)gridDim.x * blockDim.y) {
         const long long ic_base = (row / nx) * nx;
         const int cell = (int)(row - ic_base);
         const float4* g4 = reinterpret_cast<const float4*>(dH);
         const float4* h4 = reinterpret_cast<const float4*>(Hn);
-        mine = relu_mask(g4[row * 32 + fq], h4[row * 32 + fq]);
+        const float4 mine = relu_mask(g4[row * 32 + fq], h4[row * 32 + fq]);
+        add4(bsum, mine);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = 1; k <= radius; ++k) {
             const long long rp = ic_base + (cell + k) % nx;
@@ -58,9 +59,9 @@ __global__ void __launch_bounds__(256) bwd_mask_mean_kernel(const float* __restr
         reinterpret_cast<float4*>(dpre)[row * 32 + fq] = mine;
         reinterpret_cast<float4*>(dZ)[row * 32 + fq] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
     }
-    // bias gradient: reduce the 8 rows of the block, then one atomic per feature
+    // bias gradient: reduce the 8 row-lanes of the block, then one atomic per feature and block
     __shared__ float4 red[8][32];
-    red[threadIdx.y][fq] = mine;
+    red[threadIdx.y][fq] = bsum;
     __syncthreads();
     if (threadIdx.y == 0) {
         float4 s = red[0][fq];
@@ -134,20 +135,23 @@ __global__ void __launch_bounds__(256) bwd_gemm_nn_kernel(const float* __restric
 }
 
 // dW[n][ldw-strided k] += sum_rows A[row][n] * Bm[row][k]   (both [rows][128]); split over row slabs.
-// Block: 256 rows, full 128 x 128 output, 256 threads x (8 x 8), atomicAdd at the end.
+// Persistent blocks: each walks its share of the rows, keeps the full 128 x 128 partial product in
+// registers (256 threads x 8 x 8) and issues its atomicAdds once at the end.
 __global__ void __launch_bounds__(256) bwd_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                           float* __restrict__ dW, int ldw, long long rows) {
     __shared__ float As[16][128];          // [row in slab][n]
     __shared__ float Bs[16][128];          // [row in slab][k]
     const int tid = threadIdx.x;
     const int tn = tid >> 4, tk = tid & 15;
-    const long long row_begin = (long long)blockIdx.x * 256;
-    const long long row_end = row_begin + 256 < rows ? row_begin + 256 : rows;
+    const long long per_block = ((rows + gridDim.x - 1) / gridDim.x + 15) / 16 * 16;
+    const long long row_begin = (long long)blockIdx.x * per_block;
+    const long long row_end = row_begin + per_block < rows ? row_begin + per_block : rows;
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    if (row_begin >= rows) return;
     for (long long r0 = row_begin; r0 < row_end; r0 += 16) {
         {
             const int r = tid >> 4, c = (tid & 15) * 8;
@@ -194,10 +198,11 @@ __global__ void __launch_bounds__(256) bwd_edge_kernel(const float* __restrict__
                                                        float* __restrict__ dw2, float* __restrict__ db1,
                                                        float* __restrict__ db2, long long rows, int nx, int hops) {
     const int fq = threadIdx.x;
-    const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f), gq = gp, gw = gp;
+    float4 gw = make_float4(0.f, 0.f, 0.f, 0.f), gb1 = gw;       // accumulated over this thread's rows
     float gb2 = 0.f;
-    if (row < rows) {
+    for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+         row += (long long)gridDim.x * blockDim.y) {
+        float4 gp = make_float4(0.f, 0.f, 0.f, 0.f), gq = gp;
         const long long ic = row / nx, ic_base = ic * nx;
         const int cell = (int)(row - ic_base);
         const float4* P4 = reinterpret_cast<const float4*>(P);
@@ -226,11 +231,12 @@ __global__ void __launch_bounds__(256) bwd_edge_kernel(const float* __restrict__
         }
         reinterpret_cast<float4*>(dP)[row * 32 + fq] = gp;
         reinterpret_cast<float4*>(dQ)[row * 32 + fq] = gq;
+        add4(gb1, gp);                                                // db1 = sum_rows dP
     }
     __shared__ float4 redw[8][32], redb[8][32];
     __shared__ float redb2[8];
     redw[threadIdx.y][fq] = gw;
-    redb[threadIdx.y][fq] = gp;                                       // db1 = sum_rows dP
+    redb[threadIdx.y][fq] = gb1;
     if (fq == 0) redb2[threadIdx.y] = gb2;
     __syncthreads();
     if (threadIdx.y == 0) {
@@ -257,40 +263,46 @@ __global__ void __launch_bounds__(256) bwd_input_kernel(const float* __restrict_
                                                         float* __restrict__ dw_in, float* __restrict__ db_in,
                                                         long long rows, int nx) {
     const int lane = threadIdx.x, wy = threadIdx.y;
-    const long long row = (long long)blockIdx.x * blockDim.y + wy;
     __shared__ float sgw[8][kH][kF];
     __shared__ float sgb[8][kH];
-    float feat[4] = {0.f, 0.f, 0.f, 0.f};
-    float dfe[4] = {0.f, 0.f, 0.f, 0.f};
-    long long ic = 0;
-    int cell = 0;
-    if (row < rows) {
-        ic = row / nx;
-        cell = (int)(row - ic * nx);
+    // per-thread accumulators over this warp's rows: features n = lane + 32 q
+    float aw[4][4], ab[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        ab[q] = 0.f;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) aw[q][f] = 0.f;
+    }
+    for (long long row = (long long)blockIdx.x * blockDim.y + wy; row < rows; row += (long long)gridDim.x * blockDim.y) {
+        const long long ic = row / nx;
+        const int cell = (int)(row - ic * nx);
         const float* st = state + ic * 3 * nx + cell;
-        feat[0] = st[0]; feat[1] = st[nx]; feat[2] = st[2 * (size_t)nx]; feat[3] = x[cell];
+        const float feat[4] = {st[0], st[nx], st[2 * (size_t)nx], x[cell]};
+        float dfe[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int n = lane + 32 * q;
+            const float g = H0[row * kH + n] > 0.f ? dH0[row * kH + n] : 0.f;
+            ab[q] += g;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                dfe[f] = fmaf(g, w_in[n * kF + f], dfe[f]);
+                aw[q][f] = fmaf(g, feat[f], aw[q][f]);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            for (int o = 16; o > 0; o >>= 1) dfe[f] += __shfl_xor_sync(0xffffffffu, dfe[f], o);
+        if (lane == 0 && dstate != nullptr) {
+            float* ds = dstate + ic * 3 * nx + cell;
+            ds[0] = dfe[0]; ds[nx] = dfe[1]; ds[2 * (size_t)nx] = dfe[2];      // x has no gradient
+        }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int n = lane + 32 * q;
-        float g = 0.f;
-        if (row < rows) {
-            const float h = H0[row * kH + n];
-            g = h > 0.f ? dH0[row * kH + n] : 0.f;
-        }
+        sgb[wy][lane + 32 * q] = ab[q];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            dfe[f] = fmaf(g, w_in[n * kF + f], dfe[f]);
-            sgw[wy][n][f] = g * feat[f];
-        }
-        sgb[wy][n] = g;
-    }
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-        for (int o = 16; o > 0; o >>= 1) dfe[f] += __shfl_xor_sync(0xffffffffu, dfe[f], o);
-    if (row < rows && lane == 0 && dstate != nullptr) {
-        float* ds = dstate + ic * 3 * nx + cell;
-        ds[0] = dfe[0]; ds[nx] = dfe[1]; ds[2 * (size_t)nx] = dfe[2];      // x has no gradient
+        for (int f = 0; f < 4; ++f) sgw[wy][lane + 32 * q][f] = aw[q][f];
     }
     __syncthreads();
     const int t = wy * 32 + lane;                                          // 256 threads: 2 per feature n
