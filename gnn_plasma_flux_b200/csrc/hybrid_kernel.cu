@@ -5,17 +5,22 @@
 
 namespace fluxgnn {
 
-template <int R>
+template <int R, bool kSave>
 cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream);
 
-cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream) {
+template <bool kSave>
+static cudaError_t dispatch(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream) {
     switch (fast_radius) {
-        case 1: return launch_one<1>(a, grid, stream);
-        case 2: return launch_one<2>(a, grid, stream);
-        case 3: return launch_one<3>(a, grid, stream);
-        case 4: return launch_one<4>(a, grid, stream);
-        default: return launch_one<0>(a, grid, stream);
+        case 1: return launch_one<1, kSave>(a, grid, stream);
+        case 2: return launch_one<2, kSave>(a, grid, stream);
+        case 3: return launch_one<3, kSave>(a, grid, stream);
+        case 4: return launch_one<4, kSave>(a, grid, stream);
+        default: return launch_one<0, kSave>(a, grid, stream);
     }
+}
+
+cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream) {
+    return a.acts != nullptr ? dispatch<true>(a, fast_radius, grid, stream) : dispatch<false>(a, fast_radius, grid, stream);
 }
 
 }  // namespace fluxgnn

@@ -200,7 +200,9 @@ __device__ __forceinline__ void save_rows(const float* buf, float* dst, const Ti
 // R = 1..4: radius known at compile time, 8-row groups never straddle an IC
 //           (nx % 8 == 0 or window tiles) -> 128-bit window reads.
 // R = 0   : any radius / any nx, neighbours found by walking prev/next tables.
-template <int R>
+// kSave: training forward -- also store h^0..h^L, P + b1 and Q row-major for the backward pass.
+// A separate instantiation so that the inference kernel carries none of that code.
+template <int R, bool kSave>
 __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                 }
             }
             named_sync(bar, gthreads);
-            if (a.acts != nullptr) save_rows(S.Hs, a.acts, S, lt, gthreads, row0, nrows, nx);
+            if (kSave) save_rows(S.Hs, a.acts, S, lt, gthreads, row0, nrows, nx);
 
             for (int layer = 0; layer <= a.L; ++layer) {
                 // ---- pass 0: Z = W[:, H:] h -> shared memory;  pass 1: Y = W[:, :H] h + b -> registers
@@ -418,13 +420,13 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
                     }
                     named_sync(bar, gthreads);  // h' complete; Z free
-                    if (a.acts != nullptr)
+                    if (kSave)
                         save_rows(S.Hs, a.acts + (size_t)(layer + 1) * a.acts_stride, S, lt, gthreads, row0, nrows, nx);
                 } else {
                     // ---- edge readout (src/flux_gnn.py:63-66): acc = P + b1, Zs = Q ---------
                     //   fwd edge (row j, col j+k):  w2 . relu(P_j + Q_{j+k})
                     //   bwd edge (row j, col j-k):  w2 . relu(P_j + Q_{j-k})   (edge index j-k)
-                    if (a.acts != nullptr) {             // training forward: keep P + b1 and Q for the backward pass
+                    if (kSave) {                         // training forward: keep P + b1 and Q for the backward pass
                         save_rows(S.Zs, a.acts + (size_t)(a.L + 2) * a.acts_stride, S, lt, gthreads, row0, nrows, nx);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {    // h^L is dead: park P in its buffer
@@ -576,13 +578,13 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
 // ---------------------------------------------------------------------------
 // host side: one translation unit per radius instantiates this (hybrid_r*.cu)
 // ---------------------------------------------------------------------------
-template <int R>
+template <int R, bool kSave>
 cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream) {
     // per device and per function; cheap and idempotent, so set it on every launch
-    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(TileSmem));
     if (e != cudaSuccess) return e;
-    hybrid_tile_kernel<R><<<grid, kThreads, sizeof(TileSmem), stream>>>(a);
+    hybrid_tile_kernel<R, kSave><<<grid, kThreads, sizeof(TileSmem), stream>>>(a);
     return cudaGetLastError();
 }
 
