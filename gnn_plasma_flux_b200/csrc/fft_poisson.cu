@@ -3,16 +3,23 @@
 //   E = Re ifft( i * fft(n - 1) / k ),  k = 2*pi*fftfreq(nx, L/nx),  E_hat(0) = 0
 //   (src/baseline_solver.py:26,59-68; the Nyquist bin vanishes under Re()).
 //
-// nx <= 2^14: one CTA per IC, the whole transform lives in shared memory:
-//     load rho -> DIF forward FFT (bit-reversed spectrum) -> multiply -> DIT inverse -> store Re.
-// nx  > 2^14: four-step factorisation nx = N1 * N2, N2 = 2^13, element n = n1*N2 + n2:
-//     A  columns: for a tile of T consecutive n2, length-N1 FFT over n1, times W_nx^(n2*k1)  -> Y[k1][n2]
-//     B  rows   : for each k1, length-N2 FFT over n2 -> k2, multiply by i/k(k1 + N1*k2),
-//                 inverse FFT k2 -> n2, times conj twiddle                                      (in place)
-//     C  columns: inverse length-N1 FFT over k1 -> n1, real part / nx -> E[n1*N2 + n2]
-// No transposes: forward transforms are decimation-in-frequency (natural in, bit-reversed
-// out), inverse ones decimation-in-time (bit-reversed in, natural out), and the spectral
-// multiply is index-agnostic.  Each shared-memory round trip runs a radix-16 transform in registers.
+// Real-input formulation: rho (nx reals) is read as M = nx/2 complex numbers
+// z_j = rho_2j + i rho_2j+1.  With Z = FFT_M(z) and k' = (M - k) mod M,
+//   rho_hat[k]   = A + W_nx^k B,   A = (Z[k] + conj Z[k'])/2,  B = -i (Z[k] - conj Z[k'])/2,
+//   rho_hat[k+M] = conj(rho_hat[k'])                      (rho is real),
+// the multiplier i/k is applied to both, and the result is packed back the same way
+//   Zt[k] = (E_hat[k] + E_hat[k+M])/2 + i W_nx^-k (E_hat[k] - E_hat[k+M])/2,
+// so that IFFT_M(Zt) = E_2j + i E_2j+1: half the transform length, half the memory traffic.
+//
+// nx <= 2^15: one CTA per IC, everything in shared memory (DIF forward -> pair-wise spectral
+//             step -> DIT inverse; the bit-reversed order in between never has to be undone).
+// nx  > 2^15: four-step factorisation M = N1 * N2, N2 = 2^12, element j = j1*N2 + j2:
+//     A  columns: tiles of T consecutive j2, length-N1 FFT over j1, times W_M^(j2*k1)   -> Y[k1][j2]
+//     B  rows   : bins k and M-k live in rows k1 and N1-k1, so one CTA takes BOTH rows
+//                 (interleaved in shared memory): forward FFTs, pair-wise spectral step,
+//                 inverse FFTs, conj twiddle, in place.  Rows 0 and N1/2 pair with themselves.
+//     C  columns: inverse length-N1 FFT over k1 -> (E_2j, E_2j+1)
+// No transposes.  Each shared-memory round trip is a radix-16 transform in registers.
 #include "common.cuh"
 #include "field_kernels.cuh"
 
@@ -220,109 +227,177 @@ __device__ __forceinline__ float2 big_twiddle(long long r, long long nx, float s
     return make_float2((float)c, (float)s);
 }
 
-// spectrum bin kbin (0..nx-1) of rho -> bin of E, including the 1/nx of the inverse transform
-__device__ __forceinline__ float2 spectral_multiply(float2 v, long long kbin, long long nx, double length) {
-    if (kbin == 0 || 2 * kbin == nx) return make_float2(0.f, 0.f);
-    const long long m = (2 * kbin < nx) ? kbin : kbin - nx;
-    const float f = (float)(length / (6.283185307179586476925 * (double)m * (double)nx));   // 1/(k * nx)
-    return make_float2(-v.y * f, v.x * f);                                                  // i * v / k
+// The pair-wise spectral step for bins k and kp = (M - k) mod M of the half-length transform
+// (see the header): in  zk = Z[k], zp = Z[kp];  out  Zt[k], Zt[kp].  scale = L / (2 pi M) carries the
+// 1/M of the inverse transform; wk = W_nx^k.
+__device__ __forceinline__ void spectral_pair(float2 zk, float2 zp, long long k, long long M, float2 wk, double scale,
+                                              float2& ok, float2& op) {
+    if (k == 0) {                      // rho_hat[0] and the Nyquist bin: both multipliers are zero
+        ok = make_float2(0.f, 0.f);
+        op = ok;
+        return;
+    }
+    const float2 a = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));       // A[k];  A[kp] = conj
+    const float2 b = make_float2(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));      // B[k];  B[kp] = conj
+    const float2 wb = cmul(wk, b);
+    const float2 rk = make_float2(a.x + wb.x, a.y + wb.y);                          // rho_hat[k]
+    // W_nx^kp = -conj(W_nx^k):  rho_hat[kp] = conj(A) - conj(wk) conj(B) = conj(A - wk B)
+    const float2 rp = make_float2(a.x - wb.x, -(a.y - wb.y));                       // rho_hat[kp]
+    const long long kp = M - k;
+    const float fk = (float)(scale / (double)k), fkM = (float)(scale / (double)(k - M));
+    const float fp = (float)(scale / (double)kp), fpM = (float)(scale / (double)(kp - M));
+    // E_hat[q] = i f(q) rho_hat[q];  rho_hat[k+M] = conj(rho_hat[kp]),  rho_hat[kp+M] = conj(rho_hat[k])
+    const float2 ek = make_float2(-fk * rk.y, fk * rk.x), ekM = make_float2(fkM * rp.y, fkM * rp.x);
+    const float2 ep = make_float2(-fp * rp.y, fp * rp.x), epM = make_float2(fpM * rk.y, fpM * rk.x);
+    // Zt[k] = (ek + ekM)/2 + i conj(wk) (ek - ekM)/2 ;   Zt[kp] likewise with W_nx^-kp = -wk
+    const float2 sk = make_float2(0.5f * (ek.x + ekM.x), 0.5f * (ek.y + ekM.y));
+    const float2 tk = cmul(make_float2(wk.x, -wk.y), make_float2(0.5f * (ek.x - ekM.x), 0.5f * (ek.y - ekM.y)));
+    ok = make_float2(sk.x - tk.y, sk.y + tk.x);
+    const float2 sp = make_float2(0.5f * (ep.x + epM.x), 0.5f * (ep.y + epM.y));
+    const float2 tp = cmul(make_float2(-wk.x, -wk.y), make_float2(0.5f * (ep.x - epM.x), 0.5f * (ep.y - epM.y)));
+    op = make_float2(sp.x - tp.y, sp.y + tp.x);
+}
+
+// Spectral step inside ONE row of length n2 = 2^bits2 that pairs with itself (row k1 = 0 or k1 = N1/2):
+// position p holds k2 = bitrev(p); the partner bin sits at position pp.
+__device__ __forceinline__ void spectral_self_row(float2* s, int bits2, int k1, int N1, long long M, long long nx,
+                                                  double scale) {
+    const int n2 = 1 << bits2;
+    for (int p = threadIdx.x; p < n2; p += blockDim.x) {
+        const int k2 = bitrev(p, bits2);
+        int pp;
+        if (k1 == 0) pp = bitrev((n2 - k2) & (n2 - 1), bits2);      // k' = N1 * ((N2 - k2) mod N2)
+        else pp = n2 - 1 - p;                                       // k' = (N1 - k1) + N1 * (N2 - 1 - k2), same row
+        if (pp < p) continue;                                       // each unordered pair once
+        const long long k = (long long)k1 + (long long)N1 * k2;
+        float2 ok, op;
+        const float2 zk = s[saddr(p, 0, 1)], zp = s[saddr(pp, 0, 1)];
+        spectral_pair(zk, zp, k, M, big_twiddle(k, nx, -1.f), scale, ok, op);
+        s[saddr(p, 0, 1)] = ok;
+        if (pp != p) s[saddr(pp, 0, 1)] = op;
+    }
+    __syncthreads();
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------
-// whole transform in one CTA (nx = 2^bits <= 2^14)
+// whole transform in one CTA (M = nx/2 = 2^bits <= 2^14 complex points)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFftThreads) poisson_fft_small_kernel(const float* __restrict__ n, long long n_stride,
                                                                         float* __restrict__ E, long long e_stride,
                                                                         int bits, double length) {
     extern __shared__ float2 sfft[];
-    const int nx = 1 << bits;
-    const float* src = n + (size_t)blockIdx.x * n_stride;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x)
-        sfft[saddr(i, 0, 1)] = make_float2(__fsub_rn(src[i], 1.0f), 0.f);
-    __syncthreads();
-    fft_dif(sfft, bits, 1, -1.f);
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-        float2& v = sfft[saddr(i, 0, 1)];
-        v = spectral_multiply(v, bitrev(i, bits), nx, length);
+    const int M = 1 << bits;
+    const float2* src = reinterpret_cast<const float2*>(n + (size_t)blockIdx.x * n_stride);
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        const float2 v = src[j];
+        sfft[saddr(j, 0, 1)] = make_float2(__fsub_rn(v.x, 1.0f), __fsub_rn(v.y, 1.0f));
     }
     __syncthreads();
+    fft_dif(sfft, bits, 1, -1.f);
+    spectral_self_row(sfft, bits, 0, 1, M, 2LL * M, length / (6.283185307179586476925 * (double)M));
     fft_dit(sfft, bits, 1, +1.f);
-    float* dst = E + (size_t)blockIdx.x * e_stride;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) dst[i] = sfft[saddr(i, 0, 1)].x;
+    float2* dst = reinterpret_cast<float2*>(E + (size_t)blockIdx.x * e_stride);
+    for (int j = threadIdx.x; j < M; j += blockDim.x) dst[j] = sfft[saddr(j, 0, 1)];
 }
 
 // ---------------------------------------------------------------------------
 // four-step, pass A: forward column transforms.  grid = (N2 / T, B)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride,
-                                                                           float2* __restrict__ Y, int bits1, int bits2,
-                                                                           int T) {
+                                                                                  float2* __restrict__ Y, int bits1, int bits2,
+                                                                                  int T) {
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1;
-    const long long N2 = 1LL << bits2, nx = (long long)N1 << bits2;
-    const long long n2_0 = (long long)blockIdx.x * T;
+    const long long N2 = 1LL << bits2, M = (long long)N1 << bits2;
+    const long long j2_0 = (long long)blockIdx.x * T;
     const int t_bits = 31 - __clz(T);
-    const float* src = n + (size_t)blockIdx.y * n_stride;
+    const float2* src = reinterpret_cast<const float2*>(n + (size_t)blockIdx.y * n_stride);
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w & (T - 1), n1 = w >> t_bits;
-        sfft[w] = make_float2(__fsub_rn(src[(size_t)n1 * N2 + n2_0 + t], 1.0f), 0.f);
+        const int t = w & (T - 1), j1 = w >> t_bits;
+        const float2 v = src[(size_t)j1 * N2 + j2_0 + t];
+        sfft[w] = make_float2(__fsub_rn(v.x, 1.0f), __fsub_rn(v.y, 1.0f));
     }
     __syncthreads();
     fft_dif(sfft, bits1, T, -1.f);
-    float2* dst = Y + (size_t)blockIdx.y * nx;
+    float2* dst = Y + (size_t)blockIdx.y * M;
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
         const int t = w & (T - 1), pos = w >> t_bits;
         const int k1 = bitrev(pos, bits1);
-        const long long n2 = n2_0 + t;
-        dst[(size_t)k1 * N2 + n2] = cmul(sfft[w], big_twiddle((n2 * k1) & (nx - 1), nx, -1.f));      // W_nx^(n2*k1)
+        const long long j2 = j2_0 + t;
+        dst[(size_t)k1 * N2 + j2] = cmul(sfft[w], big_twiddle((j2 * k1) & (M - 1), M, -1.f));      // W_M^(j2*k1)
     }
 }
 
-// pass B: rows.  grid = (N1, B); one length-N2 row per CTA, in place.
+// pass B: row pairs.  grid = (N1/2 + 1, B): pair 0 -> row 0 alone, pair N1/2 -> row N1/2 alone,
+// pair q -> rows q and N1 - q, interleaved in shared memory (element idx of row t at s[2*idx + t]).
 __global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_rows_kernel(float2* __restrict__ Y, int bits1, int bits2,
-                                                                       double length) {
+                                                                              double length) {
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1, N2 = 1 << bits2;
-    const long long nx = (long long)N1 << bits2;
-    const int k1 = blockIdx.x;
-    float2* row = Y + (size_t)blockIdx.y * nx + (size_t)k1 * N2;
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) sfft[saddr(i, 0, 1)] = row[i];
-    __syncthreads();
-    fft_dif(sfft, bits2, 1, -1.f);
+    const long long M = (long long)N1 << bits2, nx = 2 * M;
+    const double scale = length / (6.283185307179586476925 * (double)M);
+    const int q = blockIdx.x;
+    float2* base = Y + (size_t)blockIdx.y * M;
+    if (q == 0 || 2 * q == N1) {
+        // ---- a row that pairs with itself ----------------------------------------------------
+        float2* row = base + (size_t)q * N2;
+        for (int i = threadIdx.x; i < N2; i += blockDim.x) sfft[saddr(i, 0, 1)] = row[i];
+        __syncthreads();
+        fft_dif(sfft, bits2, 1, -1.f);
+        spectral_self_row(sfft, bits2, q, N1, M, nx, scale);
+        fft_dit(sfft, bits2, 1, +1.f);
+        for (int i = threadIdx.x; i < N2; i += blockDim.x)
+            row[i] = cmul(sfft[saddr(i, 0, 1)], big_twiddle(((long long)i * q) & (M - 1), M, +1.f));   // conj twiddle
+        return;
+    }
+    // ---- rows k1 = q and k1' = N1 - q: bin (k1, k2) pairs with (k1', N2 - 1 - k2), i.e. position N2-1-p ----
+    const int k1a = q, k1b = N1 - q;
+    float2* rowa = base + (size_t)k1a * N2;
+    float2* rowb = base + (size_t)k1b * N2;
     for (int i = threadIdx.x; i < N2; i += blockDim.x) {
-        const long long kbin = (long long)k1 + (long long)N1 * bitrev(i, bits2);
-        float2& v = sfft[saddr(i, 0, 1)];
-        v = spectral_multiply(v, kbin, nx, length);
+        sfft[2 * i] = rowa[i];
+        sfft[2 * i + 1] = rowb[i];
     }
     __syncthreads();
-    fft_dit(sfft, bits2, 1, +1.f);
+    fft_dif(sfft, bits2, 2, -1.f);
+    for (int p = threadIdx.x; p < N2; p += blockDim.x) {
+        const int pp = N2 - 1 - p;
+        const long long k = (long long)k1a + (long long)N1 * bitrev(p, bits2);
+        float2 ok, op;
+        spectral_pair(sfft[2 * p], sfft[2 * pp + 1], k, M, big_twiddle(k, nx, -1.f), scale, ok, op);
+        sfft[2 * p] = ok;
+        sfft[2 * pp + 1] = op;
+    }
+    __syncthreads();
+    fft_dit(sfft, bits2, 2, +1.f);
     for (int i = threadIdx.x; i < N2; i += blockDim.x) {
-        row[i] = cmul(sfft[saddr(i, 0, 1)], big_twiddle(((long long)i * k1) & (nx - 1), nx, +1.f));  // conj twiddle
+        rowa[i] = cmul(sfft[2 * i], big_twiddle(((long long)i * k1a) & (M - 1), M, +1.f));
+        rowb[i] = cmul(sfft[2 * i + 1], big_twiddle(((long long)i * k1b) & (M - 1), M, +1.f));
     }
 }
 
-// pass C: inverse column transforms, real part out.  grid = (N2 / T, B)
+// pass C: inverse column transforms, (E_2j, E_2j+1) out.  grid = (N2 / T, B)
 __global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_cols_inv_kernel(const float2* __restrict__ Y,
-                                                                           float* __restrict__ E, long long e_stride,
-                                                                           int bits1, int bits2, int T) {
+                                                                                  float* __restrict__ E, long long e_stride,
+                                                                                  int bits1, int bits2, int T) {
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1;
-    const long long N2 = 1LL << bits2, nx = (long long)N1 << bits2;
-    const long long n2_0 = (long long)blockIdx.x * T;
+    const long long N2 = 1LL << bits2, M = (long long)N1 << bits2;
+    const long long j2_0 = (long long)blockIdx.x * T;
     const int t_bits = 31 - __clz(T);
-    const float2* src = Y + (size_t)blockIdx.y * nx;
+    const float2* src = Y + (size_t)blockIdx.y * M;
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
         const int t = w & (T - 1), k1 = w >> t_bits;
-        sfft[w] = src[(size_t)k1 * N2 + n2_0 + t];
+        sfft[w] = src[(size_t)k1 * N2 + j2_0 + t];
     }
     __syncthreads();
-    fft_dif(sfft, bits1, T, +1.f);                 // natural k1 in -> bit-reversed n1 out
-    float* dst = E + (size_t)blockIdx.y * e_stride;
+    fft_dif(sfft, bits1, T, +1.f);                 // natural k1 in -> bit-reversed j1 out
+    float2* dst = reinterpret_cast<float2*>(E + (size_t)blockIdx.y * e_stride);
     for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
         const int t = w & (T - 1), pos = w >> t_bits;
-        dst[(size_t)bitrev(pos, bits1) * N2 + n2_0 + t] = sfft[w].x;
+        dst[(size_t)bitrev(pos, bits1) * N2 + j2_0 + t] = sfft[w];
     }
 }
 
@@ -342,8 +417,8 @@ bool poisson_fft_supported(int nx) {
 
 size_t poisson_fft_workspace_bytes(int B, int nx) {
     const int bits = ilog2_exact(nx);
-    if (bits <= kFftRowBits) return 0;
-    return (size_t)B * (size_t)nx * sizeof(float2);
+    if (bits - 1 <= kFftRowBits) return 0;
+    return (size_t)B * (size_t)(nx / 2) * sizeof(float2);
 }
 
 int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e_stride, int B, int nx,
@@ -351,12 +426,16 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     const int bits = ilog2_exact(nx);
     if (bits < kFftMinBits || bits > kFftMaxBits)
         return set_error(FLUXGNN_EUNSUP, "FFT field solve needs nx = 2^%d..2^%d, got %d", kFftMinBits, kFftMaxBits, nx);
-    if (bits <= kFftRowBits) {
-        const size_t smem = (size_t)(nx + nx / 16) * sizeof(float2);
+    if ((n_stride & 1) || (e_stride & 1) || ((uintptr_t)n & 7) || ((uintptr_t)E & 7))
+        return set_error(FLUXGNN_EINVAL, "FFT field solve needs 8-byte aligned density / field rows");
+    const int mbits = bits - 1;                               // M = nx/2 complex points
+    if (mbits <= kFftRowBits) {
+        const int M = 1 << mbits;
+        const size_t smem = (size_t)(M + M / 16) * sizeof(float2);
         FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
-        const int threads = nx / 16 < kFftThreads ? (nx / 16 < 64 ? 64 : nx / 16) : kFftThreads;
-        poisson_fft_small_kernel<<<B, threads, smem, stream>>>(n, n_stride, E, e_stride, bits, length);
+        const int threads = M / 16 < kFftThreads ? (M / 16 < 64 ? 64 : M / 16) : kFftThreads;
+        poisson_fft_small_kernel<<<B, threads, smem, stream>>>(n, n_stride, E, e_stride, mbits, length);
         FLUXGNN_CUDA_OK(cudaGetLastError());
         count_launch();
         return FLUXGNN_OK;
@@ -364,20 +443,19 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     if (workspace == nullptr)
         return set_error(FLUXGNN_EINVAL, "field solve for nx=%d needs fluxgnn_poisson_workspace_bytes() of scratch", nx);
     if (B > 65535) return set_error(FLUXGNN_EUNSUP, "field solve for nx=%d handles at most 65535 ICs per call", nx);
-    // rows as long as configured, but never leave the column transform shorter than 2 or
-    // longer than the column tile
+    // rows as long as configured, but never leave the column transform longer than the column tile
     int bits2 = FLUXGNN_FFT_STEP_ROW_BITS;
-    if (bits - bits2 > FLUXGNN_FFT_STEP_COL_BITS - 1) bits2 = bits - (FLUXGNN_FFT_STEP_COL_BITS - 1);
-    const int bits1 = bits - bits2;
+    if (mbits - bits2 > FLUXGNN_FFT_STEP_COL_BITS - 1) bits2 = mbits - (FLUXGNN_FFT_STEP_COL_BITS - 1);
+    const int bits1 = mbits - bits2;
     const int N1 = 1 << bits1, N2 = 1 << bits2;
     const int T = (1 << FLUXGNN_FFT_STEP_COL_BITS) / N1;     // N1 * T complex per column tile
     const size_t smem = (size_t)(1 << FLUXGNN_FFT_STEP_COL_BITS) * sizeof(float2);
-    const size_t smem_row = (size_t)(N2 + N2 / 16) * sizeof(float2);
+    const size_t smem_row = (size_t)(2 * N2 + N2 / 8) * sizeof(float2);    // two interleaved rows, or one padded row
     float2* Y = (float2*)workspace;
     FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
     FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 gcol((unsigned)(N2 / T), (unsigned)B), grow((unsigned)N1, (unsigned)B);
+    dim3 gcol((unsigned)(N2 / T), (unsigned)B), grow((unsigned)(N1 / 2 + 1), (unsigned)B);
     poisson_fft_cols_fwd_kernel<<<gcol, kFftStepThreads, smem, stream>>>(n, n_stride, Y, bits1, bits2, T);
     FLUXGNN_CUDA_OK(cudaGetLastError());
     poisson_fft_rows_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(Y, bits1, bits2, length);

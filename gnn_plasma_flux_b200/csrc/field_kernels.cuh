@@ -26,9 +26,9 @@ constexpr int kPoissonDirectMaxNx = 12288;   // rho staged in 48 KiB of shared m
 
 // fft_poisson.cu: power-of-two grids, 2^kFftMinBits <= nx <= 2^kFftMaxBits
 constexpr int kFftMinBits = 8;
-constexpr int kFftRowBits = 14;              // longest transform done inside one CTA (128 KiB of complex64)
+constexpr int kFftRowBits = 14;              // longest complex transform done inside one CTA (nx = 2^15 reals)
 #ifndef FLUXGNN_FFT_STEP_ROW_BITS
-#define FLUXGNN_FFT_STEP_ROW_BITS 13         // four-step: row length 2^13 (68 KiB padded -> 3 CTAs per SM)
+#define FLUXGNN_FFT_STEP_ROW_BITS 12         // four-step: row length 2^12; a CTA holds a PAIR of rows (66 KiB -> 3 CTAs per SM)
 #endif
 #ifndef FLUXGNN_FFT_STEP_COL_BITS
 #define FLUXGNN_FFT_STEP_COL_BITS 13         // four-step: N1 * T = 2^13 complex per column tile (64 KiB)

@@ -37,8 +37,9 @@ def test_size_queries(built_lib):
     assert built_lib.fluxgnn_packed_weight_bytes(9) == 0
     assert built_lib.fluxgnn_hybrid_workspace_bytes(16, 64) == 0
     assert built_lib.fluxgnn_hybrid_workspace_bytes(16, 1024) == 16 * 3 * 1024 * 4        # FFT inside one CTA: no scratch
-    assert built_lib.fluxgnn_poisson_workspace_bytes(2, 1 << 16) == 2 * (1 << 16) * 8      # four-step FFT: complex64 scratch
-    assert built_lib.fluxgnn_hybrid_workspace_bytes(2, 1 << 16) == 2 * (1 << 16) * (12 + 8)
+    assert built_lib.fluxgnn_poisson_workspace_bytes(2, 1 << 15) == 0                      # nx/2 complex points fit one CTA
+    assert built_lib.fluxgnn_poisson_workspace_bytes(2, 1 << 16) == 2 * (1 << 16) * 4      # four-step FFT: nx/2 complex64 of scratch
+    assert built_lib.fluxgnn_hybrid_workspace_bytes(2, 1 << 16) == 2 * (1 << 16) * (12 + 4)
     assert built_lib.fluxgnn_baseline_workspace_bytes(2, 1000) == 2 * 3 * 1000 * 4
     assert [built_lib.fluxgnn_poisson_uses_table(n) for n in (64, 128, 256, 1000, 1024, 1 << 20)] == [1, 1, 0, 1, 0, 0]
 
