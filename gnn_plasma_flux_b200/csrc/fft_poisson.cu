@@ -230,7 +230,7 @@ __device__ __forceinline__ float2 big_twiddle(long long r, long long nx, float s
 // The pair-wise spectral step for bins k and kp = (M - k) mod M of the half-length transform
 // (see the header): in  zk = Z[k], zp = Z[kp];  out  Zt[k], Zt[kp].  scale = L / (2 pi M) carries the
 // 1/M of the inverse transform; wk = W_nx^k.
-__device__ __forceinline__ void spectral_pair(float2 zk, float2 zp, long long k, long long M, float2 wk, double scale,
+__device__ __forceinline__ void spectral_pair(float2 zk, float2 zp, long long k, long long M, float2 wk, float scale,
                                               float2& ok, float2& op) {
     if (k == 0) {                      // rho_hat[0] and the Nyquist bin: both multipliers are zero
         ok = make_float2(0.f, 0.f);
@@ -244,8 +244,9 @@ __device__ __forceinline__ void spectral_pair(float2 zk, float2 zp, long long k,
     // W_nx^kp = -conj(W_nx^k):  rho_hat[kp] = conj(A) - conj(wk) conj(B) = conj(A - wk B)
     const float2 rp = make_float2(a.x - wb.x, -(a.y - wb.y));                       // rho_hat[kp]
     const long long kp = M - k;
-    const float fk = (float)(scale / (double)k), fkM = (float)(scale / (double)(k - M));
-    const float fp = (float)(scale / (double)kp), fpM = (float)(scale / (double)(kp - M));
+    // bin numbers are < 2^24, exact in fp32; one rounding in the quotient
+    const float fk = __fdiv_rn(scale, (float)k), fkM = -__fdiv_rn(scale, (float)kp);     // k - M = -kp
+    const float fp = __fdiv_rn(scale, (float)kp), fpM = -__fdiv_rn(scale, (float)k);     // kp - M = -k
     // E_hat[q] = i f(q) rho_hat[q];  rho_hat[k+M] = conj(rho_hat[kp]),  rho_hat[kp+M] = conj(rho_hat[k])
     const float2 ek = make_float2(-fk * rk.y, fk * rk.x), ekM = make_float2(fkM * rp.y, fkM * rp.x);
     const float2 ep = make_float2(-fp * rp.y, fp * rp.x), epM = make_float2(fpM * rk.y, fpM * rk.x);
@@ -261,7 +262,7 @@ __device__ __forceinline__ void spectral_pair(float2 zk, float2 zp, long long k,
 // Spectral step inside ONE row of length n2 = 2^bits2 that pairs with itself (row k1 = 0 or k1 = N1/2):
 // position p holds k2 = bitrev(p); the partner bin sits at position pp.
 __device__ __forceinline__ void spectral_self_row(float2* s, int bits2, int k1, int N1, long long M, long long nx,
-                                                  double scale) {
+                                                  float scale) {
     const int n2 = 1 << bits2;
     for (int p = threadIdx.x; p < n2; p += blockDim.x) {
         const int k2 = bitrev(p, bits2);
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kFftThreads) poisson_fft_small_kernel(const fl
     }
     __syncthreads();
     fft_dif(sfft, bits, 1, -1.f);
-    spectral_self_row(sfft, bits, 0, 1, M, 2LL * M, length / (6.283185307179586476925 * (double)M));
+    spectral_self_row(sfft, bits, 0, 1, M, 2LL * M, (float)(length / (6.283185307179586476925 * (double)M)));
     fft_dit(sfft, bits, 1, +1.f);
     float2* dst = reinterpret_cast<float2*>(E + (size_t)blockIdx.x * e_stride);
     for (int j = threadIdx.x; j < M; j += blockDim.x) dst[j] = sfft[saddr(j, 0, 1)];
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_rows_kernel(fl
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1, N2 = 1 << bits2;
     const long long M = (long long)N1 << bits2, nx = 2 * M;
-    const double scale = length / (6.283185307179586476925 * (double)M);
+    const float scale = (float)(length / (6.283185307179586476925 * (double)M));
     const int q = blockIdx.x;
     float2* base = Y + (size_t)blockIdx.y * M;
     if (q == 0 || 2 * q == N1) {
