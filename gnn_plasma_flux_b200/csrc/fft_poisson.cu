@@ -28,7 +28,10 @@ namespace fluxgnn {
 namespace {
 
 constexpr int kFftThreads = 512;       // whole-transform kernel (upper bound; it launches nx/16)
-constexpr int kFftStepThreads = 256;   // four-step kernels: 3 CTAs per SM by registers and shared memory
+constexpr int kFftStepThreads = 256;   // four-step kernels
+#ifndef FLUXGNN_FFT_COL_CTAS
+#define FLUXGNN_FFT_COL_CTAS 2         // column kernels: CTAs per SM the register budget is set for
+#endif
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -68,7 +71,8 @@ __device__ __forceinline__ float2 mul_root16(float2 v, float sign) {
                               0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
                               -1.f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
     const float c = kC[q], sn = sign * kS[q];
-    return make_float2(v.x * c - v.y * sn, v.x * sn + v.y * c);
+    // packed: (c, c) * v + (-sn, sn) * (v.y, v.x)
+    return __ffma2_rn(make_float2(c, c), v, __fmul2_rn(make_float2(-sn, sn), make_float2(v.y, v.x)));
 }
 
 __host__ __device__ constexpr int brev_bits(int v, int bits) {
@@ -93,8 +97,8 @@ struct DifStages {
             if constexpr ((A & HALF) == 0) {
                 constexpr int mm = A & (HALF - 1);
                 const float2 u = v[A], x = v[A + HALF];
-                v[A] = make_float2(u.x + x.x, u.y + x.y);
-                v[A + HALF] = mul_root16<mm * (8 / HALF)>(make_float2(u.x - x.x, u.y - x.y), sign);
+                v[A] = __fadd2_rn(u, x);
+                v[A + HALF] = mul_root16<mm * (8 / HALF)>(__fadd2_rn(u, make_float2(-x.x, -x.y)), sign);
             }
             unroll<A + 1>(v, sign, 0);
         }
@@ -118,8 +122,8 @@ struct DitStages {
             if constexpr ((A & HALF) == 0) {
                 constexpr int mm = A & (HALF - 1);
                 const float2 u = v[A], x = mul_root16<mm * (8 / HALF)>(v[A + HALF], sign);
-                v[A] = make_float2(u.x + x.x, u.y + x.y);
-                v[A + HALF] = make_float2(u.x - x.x, u.y - x.y);
+                v[A] = __fadd2_rn(u, x);
+                v[A + HALF] = __fadd2_rn(u, make_float2(-x.x, -x.y));
             }
             unroll<A + 1>(v, sign);
         }
@@ -304,101 +308,332 @@ __global__ void __launch_bounds__(kFftThreads) poisson_fft_small_kernel(const fl
 }
 
 // ---------------------------------------------------------------------------
-// four-step, pass A: forward column transforms.  grid = (N2 / T, B)
+// Four-step kernels.  Index split of the half-length transform: element j = j1*N2 + j2, bin
+// k = k1 + N1*k2, N2 = 2^12.  The whole thing is ONE decimation-in-frequency network over M points
+// whose first log2(N1) stages (kernel A) work on columns and whose last 12 stages (kernel B) work
+// on rows; the "four-step twiddle" W_M^(j2*k1) is simply the inter-pass twiddle of that network
+// (W_L^(base*q) with base = b1*N2 + j2), so it costs one sincospi per 16 elements instead of one
+// per element.  Kernel C is the transposed (decimation-in-time) network of kernel A.
+// Y keeps its rows in POSITION order (row pos holds k1 = bitrev(pos)): no scatter anywhere.
+// The first pass of every kernel loads straight from global memory into registers and the last
+// pass stores straight from registers; shared memory is touched only between passes.
+// Arithmetic is packed (add/mul/fma.f32x2): a complex add is one instruction.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride,
-                                                                                  float2* __restrict__ Y, int bits1, int bits2,
-                                                                                  int T) {
+namespace {
+
+constexpr int kRowBits = FLUXGNN_FFT_STEP_ROW_BITS;                // 12
+constexpr int kRowLen = 1 << kRowBits;                             // 4096
+constexpr int kRowPad = kRowLen + kRowLen / 16;                    // padded row in shared memory
+static_assert(kRowBits == 12 && kFftStepThreads == 256, "row kernel is written for 4096 = 16*16*16 and 256 threads");
+
+__device__ __forceinline__ float2 pmul(float2 v, float2 w) {       // v * w, two packed instructions
+    return __ffma2_rn(make_float2(w.x, w.x), v, __fmul2_rn(make_float2(-w.y, w.y), make_float2(v.y, v.x)));
+}
+__device__ __forceinline__ float2 psqr(float2 w) {
+    return make_float2(fmaf(w.x, w.x, -w.y * w.y), 2.f * w.x * w.y);
+}
+__host__ __device__ constexpr int top_bit(int q) { return q <= 1 ? q : 2 * top_bit(q >> 1); }
+
+// pw[q] = w^q, q < R; every power is at most four multiplications away from the sincospi.
+// (template recursion: the indices must be compile-time constants or the arrays leave the registers)
+template <int R, int Q = 2>
+__device__ __forceinline__ void twiddle_powers_from(float2 (&pw)[R]) {
+    if constexpr (Q < R) {
+        constexpr int hb = top_bit(Q);
+        if constexpr (Q == hb) pw[Q] = psqr(pw[Q / 2]);
+        else pw[Q] = pmul(pw[Q - hb], pw[hb]);
+        twiddle_powers_from<R, Q + 1>(pw);
+    }
+}
+template <int R>
+__device__ __forceinline__ void twiddle_powers(float2 w, float2 (&pw)[R]) {
+    pw[0] = make_float2(1.f, 0.f);
+    if constexpr (R > 1) pw[1] = w;
+    twiddle_powers_from<R>(pw);
+}
+// register a (which holds / will hold output q = bitrev(a)) *= w^bitrev(a)
+template <int R, int A = 1>
+__device__ __forceinline__ void apply_powers(float2 (&v)[R], const float2 (&pw)[R]) {
+    if constexpr (A < R) {
+        v[A] = pmul(v[A], pw[brev_bits(A, ilog2c(R))]);
+        apply_powers<R, A + 1>(v, pw);
+    }
+}
+
+// exp(sign * 2 pi i * num / 2^den_bits), num < 2^24: the argument is exact in fp32
+__device__ __forceinline__ float2 unit_root(int num, int den_bits, float sign) {
+    float s, c;
+    sincospif(sign * (float)num * __int_as_float((127 + 1 - den_bits) << 23), &s, &c);
+    return make_float2(c, s);
+}
+
+__device__ __forceinline__ int cpad(int e) { return e + ((e >> 5) << 2); }     // column tile: 4 pads per 32
+__device__ __forceinline__ int rpad(int i) { return i + (i >> 4); }             // row: 1 pad per 16
+
+// ---- kernel A / C: column passes -------------------------------------------------------------
+// One pass over blocks of 2^LB rows (j1 units) of a tile of N1 x T elements held at s[cpad(j1*T + t)].
+// kInv = false: DIF, forward, natural j1 in -> position order out;  kInv = true: the transposed DIT pass.
+template <int BITS1, int TILE_BITS, int LB, bool kInv>
+__device__ __forceinline__ void column_pass(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s,
+                                            int j2_0) {
+    constexpr int RB = LB >= 4 ? 4 : LB, R = 1 << RB, SUBB = LB - RB, SUB = 1 << SUBB;
+    constexpr int TB = TILE_BITS - BITS1, T = 1 << TB;
+    // forward: the pass over the longest blocks comes first and reads global memory; inverse: last and writes it
+    constexpr bool kGlobalIn = kInv ? (SUBB == 0) : (LB == BITS1);
+    constexpr bool kGlobalOut = kInv ? (LB == BITS1) : (SUBB == 0);
+    constexpr int ITEMS = (1 << TILE_BITS) >> RB;
+    static_assert(ITEMS % kFftStepThreads == 0, "tile too small for the CTA");
+    constexpr int ITERS = ITEMS / kFftStepThreads;
+    constexpr bool kSharedTw = (SUB * T <= kFftStepThreads);   // (t, base) do not depend on the iteration
+    const float sign = kInv ? 1.f : -1.f;
+    float2 pw[R];
+    if constexpr (kSharedTw) {
+        const int w = threadIdx.x, t = w & (T - 1), base = (w >> TB) & (SUB - 1);
+        twiddle_powers<R>(unit_root((base << kRowBits) + j2_0 + t, LB + kRowBits, sign), pw);
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int w = threadIdx.x + it * kFftStepThreads;
+        const int t = w & (T - 1), q = w >> TB, base = q & (SUB - 1), blk = q >> SUBB;
+        const int j1_0 = (blk << LB) + base;
+        float2 v[R];
+        if constexpr (kGlobalIn) {
+#pragma unroll
+            for (int m = 0; m < R; ++m) v[m] = gin[((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t];
+            if constexpr (!kInv) {
+#pragma unroll
+                for (int m = 0; m < R; ++m) v[m] = make_float2(__fsub_rn(v[m].x, 1.0f), __fsub_rn(v[m].y, 1.0f));
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < R; ++m) v[m] = s[cpad(((j1_0 + (m << SUBB)) << TB) + t)];
+        }
+        if constexpr (!kSharedTw)
+            twiddle_powers<R>(unit_root((base << kRowBits) + j2_0 + t, LB + kRowBits, sign), pw);
+        if constexpr (!kInv) {
+            DifStages<R>::run(v, sign);
+            apply_powers<R>(v, pw);
+        } else {
+            apply_powers<R>(v, pw);
+            DitStages<R>::run(v, sign);
+        }
+        if constexpr (kGlobalOut) {
+#pragma unroll
+            for (int m = 0; m < R; ++m) gout[((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t] = v[m];
+        } else {
+#pragma unroll
+            for (int m = 0; m < R; ++m) s[cpad(((j1_0 + (m << SUBB)) << TB) + t)] = v[m];
+        }
+    }
+    if constexpr (!kGlobalOut) __syncthreads();
+}
+
+template <int BITS1, int TILE_BITS, int LB>
+__device__ __forceinline__ void columns_forward(const float2* gin, float2* gout, float2* s, int j2_0) {
+    column_pass<BITS1, TILE_BITS, LB, false>(gin, gout, s, j2_0);
+    constexpr int SUBB = LB - (LB >= 4 ? 4 : LB);
+    if constexpr (SUBB > 0) columns_forward<BITS1, TILE_BITS, SUBB>(gin, gout, s, j2_0);
+}
+template <int BITS1, int TILE_BITS, int LB>
+__device__ __forceinline__ void columns_inverse(const float2* gin, float2* gout, float2* s, int j2_0) {
+    column_pass<BITS1, TILE_BITS, LB, true>(gin, gout, s, j2_0);
+    if constexpr (LB < BITS1) columns_inverse<BITS1, TILE_BITS, LB + 4>(gin, gout, s, j2_0);
+}
+__host__ __device__ constexpr int first_inverse_lb(int bits1) { return bits1 < 4 ? bits1 : ((bits1 & 3) ? (bits1 & 3) : 4); }
+__host__ __device__ constexpr int column_tile_bits(int bits1) {
+    return bits1 + 2 > FLUXGNN_FFT_STEP_COL_BITS ? bits1 + 2 : FLUXGNN_FFT_STEP_COL_BITS;    // at least 4 columns per tile
+}
+
+}  // namespace
+
+// pass A: forward column stages.  grid = (N2 / T, B)
+template <int BITS1>
+__global__ void __launch_bounds__(kFftStepThreads, column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
+poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride, float2* __restrict__ Y) {
     extern __shared__ float2 sfft[];
-    const int N1 = 1 << bits1;
-    const long long N2 = 1LL << bits2, M = (long long)N1 << bits2;
-    const long long j2_0 = (long long)blockIdx.x * T;
-    const int t_bits = 31 - __clz(T);
+    constexpr int TILE_BITS = column_tile_bits(BITS1);
+    const int j2_0 = blockIdx.x << (TILE_BITS - BITS1);
     const float2* src = reinterpret_cast<const float2*>(n + (size_t)blockIdx.y * n_stride);
-    for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w & (T - 1), j1 = w >> t_bits;
-        const float2 v = src[(size_t)j1 * N2 + j2_0 + t];
-        sfft[w] = make_float2(__fsub_rn(v.x, 1.0f), __fsub_rn(v.y, 1.0f));
-    }
-    __syncthreads();
-    fft_dif(sfft, bits1, T, -1.f);
-    float2* dst = Y + (size_t)blockIdx.y * M;
-    for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w & (T - 1), pos = w >> t_bits;
-        const int k1 = bitrev(pos, bits1);
-        const long long j2 = j2_0 + t;
-        dst[(size_t)k1 * N2 + j2] = cmul(sfft[w], big_twiddle((j2 * k1) & (M - 1), M, -1.f));      // W_M^(j2*k1)
-    }
+    float2* dst = Y + ((size_t)blockIdx.y << (BITS1 + kRowBits));
+    columns_forward<BITS1, TILE_BITS, BITS1>(src, dst, sfft, j2_0);
 }
 
-// pass B: row pairs.  grid = (N1/2 + 1, B): pair 0 -> row 0 alone, pair N1/2 -> row N1/2 alone,
-// pair q -> rows q and N1 - q, interleaved in shared memory (element idx of row t at s[2*idx + t]).
-__global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_rows_kernel(float2* __restrict__ Y, int bits1, int bits2,
-                                                                              double length) {
+// pass C: inverse column stages, (E_2j, E_2j+1) out.  grid = (N2 / T, B)
+template <int BITS1>
+__global__ void __launch_bounds__(kFftStepThreads, column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
+poisson_fft_cols_inv_kernel(const float2* __restrict__ Y, float* __restrict__ E, long long e_stride) {
     extern __shared__ float2 sfft[];
-    const int N1 = 1 << bits1, N2 = 1 << bits2;
-    const long long M = (long long)N1 << bits2, nx = 2 * M;
-    const float scale = (float)(length / (6.283185307179586476925 * (double)M));
-    const int q = blockIdx.x;
-    float2* base = Y + (size_t)blockIdx.y * M;
-    if (q == 0 || 2 * q == N1) {
-        // ---- a row that pairs with itself ----------------------------------------------------
-        float2* row = base + (size_t)q * N2;
-        for (int i = threadIdx.x; i < N2; i += blockDim.x) sfft[saddr(i, 0, 1)] = row[i];
-        __syncthreads();
-        fft_dif(sfft, bits2, 1, -1.f);
-        spectral_self_row(sfft, bits2, q, N1, M, nx, scale);
-        fft_dit(sfft, bits2, 1, +1.f);
-        for (int i = threadIdx.x; i < N2; i += blockDim.x)
-            row[i] = cmul(sfft[saddr(i, 0, 1)], big_twiddle(((long long)i * q) & (M - 1), M, +1.f));   // conj twiddle
-        return;
-    }
-    // ---- rows k1 = q and k1' = N1 - q: bin (k1, k2) pairs with (k1', N2 - 1 - k2), i.e. position N2-1-p ----
-    const int k1a = q, k1b = N1 - q;
-    float2* rowa = base + (size_t)k1a * N2;
-    float2* rowb = base + (size_t)k1b * N2;
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) {
-        sfft[2 * i] = rowa[i];
-        sfft[2 * i + 1] = rowb[i];
-    }
-    __syncthreads();
-    fft_dif(sfft, bits2, 2, -1.f);
-    for (int p = threadIdx.x; p < N2; p += blockDim.x) {
-        const int pp = N2 - 1 - p;
-        const long long k = (long long)k1a + (long long)N1 * bitrev(p, bits2);
-        float2 ok, op;
-        spectral_pair(sfft[2 * p], sfft[2 * pp + 1], k, M, big_twiddle(k, nx, -1.f), scale, ok, op);
-        sfft[2 * p] = ok;
-        sfft[2 * pp + 1] = op;
-    }
-    __syncthreads();
-    fft_dit(sfft, bits2, 2, +1.f);
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) {
-        rowa[i] = cmul(sfft[2 * i], big_twiddle(((long long)i * k1a) & (M - 1), M, +1.f));
-        rowb[i] = cmul(sfft[2 * i + 1], big_twiddle(((long long)i * k1b) & (M - 1), M, +1.f));
-    }
-}
-
-// pass C: inverse column transforms, (E_2j, E_2j+1) out.  grid = (N2 / T, B)
-__global__ void __launch_bounds__(kFftStepThreads, 3) poisson_fft_cols_inv_kernel(const float2* __restrict__ Y,
-                                                                                  float* __restrict__ E, long long e_stride,
-                                                                                  int bits1, int bits2, int T) {
-    extern __shared__ float2 sfft[];
-    const int N1 = 1 << bits1;
-    const long long N2 = 1LL << bits2, M = (long long)N1 << bits2;
-    const long long j2_0 = (long long)blockIdx.x * T;
-    const int t_bits = 31 - __clz(T);
-    const float2* src = Y + (size_t)blockIdx.y * M;
-    for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w & (T - 1), k1 = w >> t_bits;
-        sfft[w] = src[(size_t)k1 * N2 + j2_0 + t];
-    }
-    __syncthreads();
-    fft_dif(sfft, bits1, T, +1.f);                 // natural k1 in -> bit-reversed j1 out
+    constexpr int TILE_BITS = column_tile_bits(BITS1);
+    const int j2_0 = blockIdx.x << (TILE_BITS - BITS1);
+    const float2* src = Y + ((size_t)blockIdx.y << (BITS1 + kRowBits));
     float2* dst = reinterpret_cast<float2*>(E + (size_t)blockIdx.y * e_stride);
-    for (int w = threadIdx.x; w < N1 * T; w += blockDim.x) {
-        const int t = w & (T - 1), pos = w >> t_bits;
-        dst[(size_t)bitrev(pos, bits1) * N2 + j2_0 + t] = sfft[w];
+    columns_inverse<BITS1, TILE_BITS, first_inverse_lb(BITS1)>(src, dst, sfft, j2_0);
+}
+
+namespace {
+
+// ---- kernel B: rows ----------------------------------------------------------------------------
+// Row passes over 4096 = 16*16*16 points; thread `tid` owns the same work item in both rows of a pair,
+// so every twiddle set is generated once and used twice.
+template <bool kInv>
+__device__ __forceinline__ void row_butterfly(float2 (&v)[16], const float2 (&pw)[16], bool twiddled) {
+    const float sign = kInv ? 1.f : -1.f;
+    if constexpr (!kInv) {
+        DifStages<16>::run(v, sign);
+        if (twiddled) apply_powers<16>(v, pw);
+    } else {
+        if (twiddled) apply_powers<16>(v, pw);
+        DitStages<16>::run(v, sign);
+    }
+}
+
+// alpha/beta form of the pair-wise spectral step (header comment):  with f(k) = scale/k,
+// s = (f(k) + f(M-k))/2, d = (f(k) - f(M-k))/2 and w = W_nx^k = (wx, wy),
+//   Zt[k]   = i (d + s wy) Z[k]    - s wx conj(Z[M-k])
+//   Zt[M-k] = i (-d + s wy) Z[M-k] + s wx conj(Z[k])
+// (algebraically identical to untangle -> multiply by i/k -> re-tangle).  k in 1..M-1.
+__device__ __forceinline__ void spectral_pair_ab(float2& zk, float2& zp, int k, int M, float2 w, float scale) {
+    const float fk = __fdividef(scale, (float)k), fp = __fdividef(scale, (float)(M - k));
+    const float s = 0.5f * (fk + fp), d = 0.5f * (fk - fp);
+    const float swy = s * w.y, be = s * w.x;
+    const float al = swy + d, alp = swy - d;
+    const float2 a = zk, b = zp;
+    zk = make_float2(-al * a.y - be * b.x, al * a.x + be * b.y);
+    zp = make_float2(-alp * b.y + be * a.x, alp * b.x - be * a.y);
+}
+
+// W_32^(-c) = exp(-2 pi i c / 32), c = 0..15
+__device__ __forceinline__ float2 root32_conj(int c) {
+    constexpr float kC[16] = {1.f, 0.98078528040323044f, 0.92387953251128674f, 0.83146961230254524f,
+                              0.70710678118654752f, 0.55557023301960222f, 0.38268343236508977f, 0.19509032201612827f,
+                              0.f, -0.19509032201612827f, -0.38268343236508977f, -0.55557023301960222f,
+                              -0.70710678118654752f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323044f};
+    constexpr float kS[16] = {0.f, 0.19509032201612827f, 0.38268343236508977f, 0.55557023301960222f,
+                              0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323044f,
+                              1.f, 0.98078528040323044f, 0.92387953251128674f, 0.83146961230254524f,
+                              0.70710678118654752f, 0.55557023301960222f, 0.38268343236508977f, 0.19509032201612827f};
+    return make_float2(kC[c], -kS[c]);
+}
+
+}  // namespace
+
+// pass B: row pairs.  grid = (N1/2 + 1, B): pair q -> the rows holding k1 = q and k1 = N1 - q
+// (rows 0 and N1/2 pair with themselves and take the shared-memory spectral step).
+__global__ void __launch_bounds__(kFftStepThreads, 2) poisson_fft_rows_kernel(float2* __restrict__ Y, int bits1,
+                                                                              float scale) {
+    extern __shared__ float2 sfft[];
+    const int N1 = 1 << bits1, M = N1 << kRowBits;
+    const int tid = threadIdx.x;
+    const int k1a = blockIdx.x, k1b = (N1 - k1a) & (N1 - 1);
+    const bool self = (k1a == k1b);
+    float2* base = Y + ((size_t)blockIdx.y << (bits1 + kRowBits));
+    float2* rowa = base + ((size_t)bitrev(k1a, bits1) << kRowBits);
+    float2* rowb = base + ((size_t)bitrev(k1b, bits1) << kRowBits);
+    float2* sa = sfft;
+    float2* sb = sfft + kRowPad;
+    float2 va[16], vb[16], pw[16];
+
+    // ---- forward pass 1: blocks of 4096, stride 256, straight from global memory ----
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = rowa[tid + 256 * m];
+    if (!self) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) vb[m] = rowb[tid + 256 * m];
+    }
+    twiddle_powers<16>(unit_root(tid, kRowBits, -1.f), pw);
+    row_butterfly<false>(va, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sa[rpad(tid + 256 * m)] = va[m];
+    if (!self) {
+        row_butterfly<false>(vb, pw, true);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sb[rpad(tid + 256 * m)] = vb[m];
+    }
+    __syncthreads();
+    // ---- forward pass 2: blocks of 256, stride 16 ----
+    const int e2 = (tid >> 4) * 256 + (tid & 15);
+    twiddle_powers<16>(unit_root(tid & 15, 8, -1.f), pw);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = sa[rpad(e2 + 16 * m)];
+    row_butterfly<false>(va, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sa[rpad(e2 + 16 * m)] = va[m];
+    if (!self) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(e2 + 16 * m)];
+        row_butterfly<false>(vb, pw, true);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sb[rpad(e2 + 16 * m)] = vb[m];
+    }
+    __syncthreads();
+    // ---- forward pass 3 (blocks of 16), spectral step, inverse pass 3 ----
+    if (!self) {
+        // position p = 16 tid + m of row a (bin k1a + N1*bitrev(p)) pairs with position 4095 - p of row b:
+        // this thread takes block tid of row a and block 255 - tid of row b, and the pairing stays in registers.
+        const int ea = tid * 16, eb = (255 - tid) * 16;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) va[m] = sa[rpad(ea + m)];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(eb + m)];
+        row_butterfly<false>(va, pw, false);
+        row_butterfly<false>(vb, pw, false);
+        // k = k1a + N1*bitrev12(16 tid + m) = k0 + bitrev4(m) * M/16;  W_nx^k = W_nx^k0 * W_32^bitrev4(m)
+        const int k0 = k1a + (bitrev(tid, 8) << bits1);
+        const float2 w0 = unit_root(k0, bits1 + kRowBits + 1, -1.f);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int c = brev_bits(m, 4);
+            spectral_pair_ab(va[m], vb[15 - m], k0 + c * (M >> 4), M, pmul(w0, root32_conj(c)), scale);
+        }
+        row_butterfly<true>(va, pw, false);
+        row_butterfly<true>(vb, pw, false);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sa[rpad(ea + m)] = va[m];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sb[rpad(eb + m)] = vb[m];
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) va[m] = sa[rpad(tid * 16 + m)];
+        row_butterfly<false>(va, pw, false);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sa[rpad(tid * 16 + m)] = va[m];
+        __syncthreads();
+        spectral_self_row(sa, kRowBits, k1a, N1, M, 2LL * M, scale);      // ends with a barrier
+#pragma unroll
+        for (int m = 0; m < 16; ++m) va[m] = sa[rpad(tid * 16 + m)];
+        row_butterfly<true>(va, pw, false);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sa[rpad(tid * 16 + m)] = va[m];
+    }
+    __syncthreads();
+    // ---- inverse pass 2 ----
+    twiddle_powers<16>(unit_root(tid & 15, 8, +1.f), pw);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = sa[rpad(e2 + 16 * m)];
+    row_butterfly<true>(va, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sa[rpad(e2 + 16 * m)] = va[m];
+    if (!self) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(e2 + 16 * m)];
+        row_butterfly<true>(vb, pw, true);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sb[rpad(e2 + 16 * m)] = vb[m];
+    }
+    __syncthreads();
+    // ---- inverse pass 1, straight to global memory ----
+    twiddle_powers<16>(unit_root(tid, kRowBits, +1.f), pw);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = sa[rpad(tid + 256 * m)];
+    row_butterfly<true>(va, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) rowa[tid + 256 * m] = va[m];
+    if (!self) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(tid + 256 * m)];
+        row_butterfly<true>(vb, pw, true);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) rowb[tid + 256 * m] = vb[m];
     }
 }
 
@@ -444,25 +679,38 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     if (workspace == nullptr)
         return set_error(FLUXGNN_EINVAL, "field solve for nx=%d needs fluxgnn_poisson_workspace_bytes() of scratch", nx);
     if (B > 65535) return set_error(FLUXGNN_EUNSUP, "field solve for nx=%d handles at most 65535 ICs per call", nx);
-    // rows as long as configured, but never leave the column transform longer than the column tile
-    int bits2 = FLUXGNN_FFT_STEP_ROW_BITS;
-    if (mbits - bits2 > FLUXGNN_FFT_STEP_COL_BITS - 1) bits2 = mbits - (FLUXGNN_FFT_STEP_COL_BITS - 1);
-    const int bits1 = mbits - bits2;
-    const int N1 = 1 << bits1, N2 = 1 << bits2;
-    const int T = (1 << FLUXGNN_FFT_STEP_COL_BITS) / N1;     // N1 * T complex per column tile
-    const size_t smem = (size_t)(1 << FLUXGNN_FFT_STEP_COL_BITS) * sizeof(float2);
-    const size_t smem_row = (size_t)(2 * N2 + N2 / 8) * sizeof(float2);    // two interleaved rows, or one padded row
+    const int bits1 = mbits - kRowBits;                       // 3..12
+    const int tile_bits = column_tile_bits(bits1);
+    const int T = 1 << (tile_bits - bits1);
+    const size_t tile = (size_t)1 << tile_bits;
+    const size_t smem = (tile + (tile >> 5) * 4) * sizeof(float2);
+    const size_t smem_row = (size_t)2 * kRowPad * sizeof(float2);
+    const float scale = (float)(length / (6.283185307179586476925 * (double)(1LL << mbits)));
     float2* Y = (float2*)workspace;
-    FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 gcol((unsigned)(kRowLen / T), (unsigned)B), grow((unsigned)((1 << bits1) / 2 + 1), (unsigned)B);
     FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-    FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 gcol((unsigned)(N2 / T), (unsigned)B), grow((unsigned)(N1 / 2 + 1), (unsigned)B);
-    poisson_fft_cols_fwd_kernel<<<gcol, kFftStepThreads, smem, stream>>>(n, n_stride, Y, bits1, bits2, T);
+#define FLUXGNN_FFT_COLS(BITS1, WHICH, ...)                                                                          \
+    case BITS1:                                                                                                     \
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(WHICH<BITS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        WHICH<BITS1><<<gcol, kFftStepThreads, smem, stream>>>(__VA_ARGS__);                                          \
+        break;
+#define FLUXGNN_FFT_COLS_ALL(WHICH, ...)                                                       \
+    switch (bits1) {                                                                          \
+        FLUXGNN_FFT_COLS(3, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(4, WHICH, __VA_ARGS__)       \
+        FLUXGNN_FFT_COLS(5, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(6, WHICH, __VA_ARGS__)       \
+        FLUXGNN_FFT_COLS(7, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(8, WHICH, __VA_ARGS__)       \
+        FLUXGNN_FFT_COLS(9, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(10, WHICH, __VA_ARGS__)      \
+        FLUXGNN_FFT_COLS(11, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(12, WHICH, __VA_ARGS__)     \
+        default: return set_error(FLUXGNN_EUNSUP, "four-step FFT: unsupported column length 2^%d", bits1); \
+    }
+    FLUXGNN_FFT_COLS_ALL(poisson_fft_cols_fwd_kernel, n, n_stride, Y)
     FLUXGNN_CUDA_OK(cudaGetLastError());
-    poisson_fft_rows_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(Y, bits1, bits2, length);
+    poisson_fft_rows_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(Y, bits1, scale);
     FLUXGNN_CUDA_OK(cudaGetLastError());
-    poisson_fft_cols_inv_kernel<<<gcol, kFftStepThreads, smem, stream>>>(Y, E, e_stride, bits1, bits2, T);
+    FLUXGNN_FFT_COLS_ALL(poisson_fft_cols_inv_kernel, Y, E, e_stride)
     FLUXGNN_CUDA_OK(cudaGetLastError());
+#undef FLUXGNN_FFT_COLS_ALL
+#undef FLUXGNN_FFT_COLS
     count_launch(3);
     return FLUXGNN_OK;
 }
