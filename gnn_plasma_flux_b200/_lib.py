@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfluxgnn.so")
+LIB_PATH = os.environ.get("FLUXGNN_LIB") or os.path.join(_HERE, "libfluxgnn.so")   # FLUXGNN_LIB: experiment builds
 
 ABI_VERSION = 1
 MAX_HOPS = 4

@@ -35,7 +35,11 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), suffix: str = "") -> str:
+    """`defines`/`suffix` build an experiment variant (e.g. -DFLUXGNN_FFT_COL_CTAS=3 -> libfluxgnn_x.so,
+    loaded with FLUXGNN_LIB=...); the default call builds the product library."""
+    OBJ = os.path.join(HERE, "build" + suffix)
+    LIB = os.path.join(HERE, f"libfluxgnn{suffix}.so")
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "fluxgnn.h"))
@@ -44,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         path = os.path.join(CSRC, src)
         if force or _stale(obj, [path] + headers):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
+            cmd = [_nvcc(), *NVCC_FLAGS, *defines, "-c", path, "-o", obj]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or res.returncode != 0:
                 sys.stderr.write(res.stdout + res.stderr)
@@ -64,4 +68,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    defs = tuple(a for a in sys.argv[1:] if a.startswith("-D"))
+    sfx = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")), "")
+    print(build_library(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, defines=defs, suffix=sfx))

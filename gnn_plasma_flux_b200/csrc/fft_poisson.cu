@@ -29,9 +29,8 @@ namespace {
 
 constexpr int kFftThreads = 512;       // whole-transform kernel (upper bound; it launches nx/16)
 constexpr int kFftStepThreads = 256;   // four-step kernels
-#ifndef FLUXGNN_FFT_COL_CTAS
-#define FLUXGNN_FFT_COL_CTAS 2         // column kernels: CTAs per SM the register budget is set for
-#endif
+#define FLUXGNN_FFT_COL_CTAS 2         // column kernels: CTAs per SM the register budget is set for (3 measured slower:
+                                       // the L1 data pipe, not occupancy, limits them -- 32-byte segments cost a wavefront each)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -367,6 +366,52 @@ __device__ __forceinline__ float2 unit_root(int num, int den_bits, float sign) {
     return make_float2(c, s);
 }
 
+// The twiddles of one work item: all R powers in registers (14 + 15 multiplications per 16 points).
+template <int R>
+struct TwiddleSet {
+    float2 pw[R];
+    __device__ __forceinline__ void init(float2 w) { twiddle_powers<R>(w, pw); }
+    __device__ __forceinline__ void apply(float2 (&v)[R]) const { apply_powers<R>(v, pw); }
+};
+
+// L2 residency hints (FLUXGNN_FFT_L2_HINTS): the spectrum Y (8 B per complex point, 64 MiB at 2^24
+// cells) is written by kernel A, rewritten in place by B and consumed by C; marking it evict_last
+// and the streamed density / consumed spectrum evict_first keeps it in the 126 MB L2 between kernels.
+#ifndef FLUXGNN_FFT_L2_HINTS
+#define FLUXGNN_FFT_L2_HINTS 1
+#endif
+enum class Hint { kNone, kFirst, kLast };
+template <Hint H>
+__device__ __forceinline__ uint64_t make_policy() {
+    uint64_t p = 0;
+#if FLUXGNN_FFT_L2_HINTS
+    if constexpr (H == Hint::kFirst) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    if constexpr (H == Hint::kLast) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+#endif
+    return p;
+}
+template <Hint H>
+__device__ __forceinline__ float2 gload(const float2* p, uint64_t pol) {
+#if FLUXGNN_FFT_L2_HINTS
+    if constexpr (H != Hint::kNone) {
+        float2 v;
+        asm("ld.global.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+        return v;
+    }
+#endif
+    return *p;
+}
+template <Hint H>
+__device__ __forceinline__ void gstore(float2* p, float2 v, uint64_t pol) {
+#if FLUXGNN_FFT_L2_HINTS
+    if constexpr (H != Hint::kNone) {
+        asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+        return;
+    }
+#endif
+    *p = v;
+}
+
 __device__ __forceinline__ int cpad(int e) { return e + ((e >> 5) << 2); }     // column tile: 4 pads per 32
 __device__ __forceinline__ int rpad(int i) { return i + (i >> 4); }             // row: 1 pad per 16
 
@@ -385,11 +430,14 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
     static_assert(ITEMS % kFftStepThreads == 0, "tile too small for the CTA");
     constexpr int ITERS = ITEMS / kFftStepThreads;
     constexpr bool kSharedTw = (SUB * T <= kFftStepThreads);   // (t, base) do not depend on the iteration
+    // forward: density in (streamed), spectrum out (kept);  inverse: spectrum in (consumed), field out
+    constexpr Hint kHin = Hint::kFirst, kHout = kInv ? Hint::kNone : Hint::kLast;
+    const uint64_t pol_in = kGlobalIn ? make_policy<kHin>() : 0, pol_out = kGlobalOut ? make_policy<kHout>() : 0;
     const float sign = kInv ? 1.f : -1.f;
-    float2 pw[R];
+    TwiddleSet<R> pw;
     if constexpr (kSharedTw) {
         const int w = threadIdx.x, t = w & (T - 1), base = (w >> TB) & (SUB - 1);
-        twiddle_powers<R>(unit_root((base << kRowBits) + j2_0 + t, LB + kRowBits, sign), pw);
+        pw.init(unit_root((base << kRowBits) + j2_0 + t, LB + kRowBits, sign));
     }
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -399,7 +447,8 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
         float2 v[R];
         if constexpr (kGlobalIn) {
 #pragma unroll
-            for (int m = 0; m < R; ++m) v[m] = gin[((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t];
+            for (int m = 0; m < R; ++m)
+                v[m] = gload<kHin>(gin + (((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t), pol_in);
             if constexpr (!kInv) {
 #pragma unroll
                 for (int m = 0; m < R; ++m) v[m] = make_float2(__fsub_rn(v[m].x, 1.0f), __fsub_rn(v[m].y, 1.0f));
@@ -408,18 +457,18 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
 #pragma unroll
             for (int m = 0; m < R; ++m) v[m] = s[cpad(((j1_0 + (m << SUBB)) << TB) + t)];
         }
-        if constexpr (!kSharedTw)
-            twiddle_powers<R>(unit_root((base << kRowBits) + j2_0 + t, LB + kRowBits, sign), pw);
+        if constexpr (!kSharedTw) pw.init(unit_root((base << kRowBits) + j2_0 + t, LB + kRowBits, sign));
         if constexpr (!kInv) {
             DifStages<R>::run(v, sign);
-            apply_powers<R>(v, pw);
+            pw.apply(v);
         } else {
-            apply_powers<R>(v, pw);
+            pw.apply(v);
             DitStages<R>::run(v, sign);
         }
         if constexpr (kGlobalOut) {
 #pragma unroll
-            for (int m = 0; m < R; ++m) gout[((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t] = v[m];
+            for (int m = 0; m < R; ++m)
+                gstore<kHout>(gout + (((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t), v[m], pol_out);
         } else {
 #pragma unroll
             for (int m = 0; m < R; ++m) s[cpad(((j1_0 + (m << SUBB)) << TB) + t)] = v[m];
@@ -492,9 +541,12 @@ __device__ __forceinline__ void row_butterfly(float2 (&v)[16], const float2 (&pw
 //   Zt[k]   = i (d + s wy) Z[k]    - s wx conj(Z[M-k])
 //   Zt[M-k] = i (-d + s wy) Z[M-k] + s wx conj(Z[k])
 // (algebraically identical to untangle -> multiply by i/k -> re-tangle).  k in 1..M-1.
-__device__ __forceinline__ void spectral_pair_ab(float2& zk, float2& zp, int k, int M, float2 w, float scale) {
-    const float fk = __fdividef(scale, (float)k), fp = __fdividef(scale, (float)(M - k));
-    const float s = 0.5f * (fk + fp), d = 0.5f * (fk - fp);
+// s = scale/2 * M / (k (M-k)),  d = scale/2 * (M - 2k) / (k (M-k)): one reciprocal per pair (the XU pipe was the
+// limiter with two divisions and two int->float conversions per pair); kf = (float)k is exact (k < 2^24).
+__device__ __forceinline__ void spectral_pair_ab(float2& zk, float2& zp, float kf, float Mf, float2 w, float half_scale) {
+    const float kpf = Mf - kf;
+    const float r = __fdividef(half_scale, kf * kpf);
+    const float s = r * Mf, d = r * (kpf - kf);
     const float swy = s * w.y, be = s * w.x;
     const float al = swy + d, alp = swy - d;
     const float2 a = zk, b = zp;
@@ -532,13 +584,14 @@ __global__ void __launch_bounds__(kFftStepThreads, 2) poisson_fft_rows_kernel(fl
     float2* sa = sfft;
     float2* sb = sfft + kRowPad;
     float2 va[16], vb[16], pw[16];
+    const uint64_t pol = make_policy<Hint::kLast>();
 
     // ---- forward pass 1: blocks of 4096, stride 256, straight from global memory ----
 #pragma unroll
-    for (int m = 0; m < 16; ++m) va[m] = rowa[tid + 256 * m];
+    for (int m = 0; m < 16; ++m) va[m] = gload<Hint::kLast>(rowa + tid + 256 * m, pol);
     if (!self) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) vb[m] = rowb[tid + 256 * m];
+        for (int m = 0; m < 16; ++m) vb[m] = gload<Hint::kLast>(rowb + tid + 256 * m, pol);
     }
     twiddle_powers<16>(unit_root(tid, kRowBits, -1.f), pw);
     row_butterfly<false>(va, pw, true);
@@ -580,10 +633,11 @@ __global__ void __launch_bounds__(kFftStepThreads, 2) poisson_fft_rows_kernel(fl
         // k = k1a + N1*bitrev12(16 tid + m) = k0 + bitrev4(m) * M/16;  W_nx^k = W_nx^k0 * W_32^bitrev4(m)
         const int k0 = k1a + (bitrev(tid, 8) << bits1);
         const float2 w0 = unit_root(k0, bits1 + kRowBits + 1, -1.f);
+        const float k0f = (float)k0, Mf = (float)M, M16f = (float)(M >> 4);
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             const int c = brev_bits(m, 4);
-            spectral_pair_ab(va[m], vb[15 - m], k0 + c * (M >> 4), M, pmul(w0, root32_conj(c)), scale);
+            spectral_pair_ab(va[m], vb[15 - m], k0f + (float)c * M16f, Mf, pmul(w0, root32_conj(c)), 0.5f * scale);
         }
         row_butterfly<true>(va, pw, false);
         row_butterfly<true>(vb, pw, false);
@@ -627,13 +681,13 @@ __global__ void __launch_bounds__(kFftStepThreads, 2) poisson_fft_rows_kernel(fl
     for (int m = 0; m < 16; ++m) va[m] = sa[rpad(tid + 256 * m)];
     row_butterfly<true>(va, pw, true);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) rowa[tid + 256 * m] = va[m];
+    for (int m = 0; m < 16; ++m) gstore<Hint::kLast>(rowa + tid + 256 * m, va[m], pol);
     if (!self) {
 #pragma unroll
         for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(tid + 256 * m)];
         row_butterfly<true>(vb, pw, true);
 #pragma unroll
-        for (int m = 0; m < 16; ++m) rowb[tid + 256 * m] = vb[m];
+        for (int m = 0; m < 16; ++m) gstore<Hint::kLast>(rowb + tid + 256 * m, vb[m], pol);
     }
 }
 
