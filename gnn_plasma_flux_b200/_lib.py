@@ -17,7 +17,13 @@ MAX_HOPS = 4
 MAX_LAYERS = 8
 HIDDEN = 128
 INPUT_DIM = 4
-TC_PRECISIONS = {"tf32x3": 1, "tf32": 2}     # FLUXGNN_TC_* of include/fluxgnn.h
+TC_PRECISIONS = {"tf32x3": 1, "tf32": 2, "fp16x3": 3, "fp16": 4, "bf16": 5}     # FLUXGNN_TC_* of include/fluxgnn.h
+
+
+def weight_layout(precision: str) -> str:
+    """Packed-weight layout a precision mode streams: the FP32-pipe kernel's K-major halves, the
+    TF32 UMMA operand images, or the 16-bit images (fp16 serves fp16x3 and fp16; bf16 its own)."""
+    return {"fp32": "fp32", "tf32x3": "tc", "tf32": "tc", "fp16x3": "tc16", "fp16": "tc16", "bf16": "tc16_bf16"}[precision]
 
 # name -> (restype, argtypes); mirrors include/fluxgnn.h declaration by declaration
 SIGNATURES = {
@@ -39,6 +45,8 @@ SIGNATURES = {
                                        c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fluxgnn_packed_tc_weight_bytes": (c_size_t, [c_int]),
     "fluxgnn_pack_weights_tc": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
+    "fluxgnn_packed_tc16_weight_bytes": (c_size_t, [c_int]),
+    "fluxgnn_pack_weights_tc16": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p, c_void_p]),
     "fluxgnn_forward_ring_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p]),
     "fluxgnn_hybrid_rollout_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

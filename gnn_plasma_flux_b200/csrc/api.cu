@@ -40,9 +40,11 @@ static int sm_count(int* out) {
 // Tiling of [B][nx] cells into 128-row tiles (see hybrid_kernel.cu).
 static int plan_tiles(HybridArgs& a, int* fast_radius) {
     const int nx = a.nx;
-    if (nx <= kTileRows) {
+    if (a.tile_rows == 0) a.tile_rows = kTileRows;
+    const int rows = a.tile_rows;                  // 128, or 256 for the 16-bit tensor kernel
+    if (nx <= kTileRows) {                         // whole ICs (the API's workspace / gtab rules key on 128)
         a.whole_ic = 1;
-        a.ics_per_tile = kTileRows / nx;
+        a.ics_per_tile = rows / nx;
         a.tiles_per_ic = 0;
         a.valid = a.halo = 0;
         const long long tiles = ((long long)a.B + a.ics_per_tile - 1) / a.ics_per_tile;
@@ -53,9 +55,9 @@ static int plan_tiles(HybridArgs& a, int* fast_radius) {
         a.whole_ic = 0;
         a.ics_per_tile = 0;
         a.halo = a.L * a.radius + a.hops;
-        a.valid = kTileRows - 2 * a.halo;
+        a.valid = rows - 2 * a.halo;
         if (a.valid < 8)
-            return set_error(FLUXGNN_EUNSUP, "receptive field L*radius+hops = %d cells does not fit a 128-cell tile", a.halo);
+            return set_error(FLUXGNN_EUNSUP, "receptive field L*radius+hops = %d cells does not fit a %d-cell tile", a.halo, rows);
         a.tiles_per_ic = (nx + a.valid - 1) / a.valid;
         const long long tiles = (long long)a.B * a.tiles_per_ic;
         if (tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");
@@ -85,7 +87,9 @@ static int launch_tiles(const HybridArgs& a, int fast_radius, cudaStream_t strea
     int rc = sm_count(&sms);
     if (rc != FLUXGNN_OK) return rc;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    if (fast_radius < 0)
+    if (fast_radius < 0 && a.tile_rows == kTc16TileRows)
+        FLUXGNN_CUDA_OK(launch_hybrid_tc16_tiles(a, -fast_radius, grid, stream));
+    else if (fast_radius < 0)
         FLUXGNN_CUDA_OK(launch_hybrid_tc_tiles(a, -fast_radius, grid, stream));
     else
         FLUXGNN_CUDA_OK(launch_hybrid_tiles(a, fast_radius, grid, stream));
@@ -175,6 +179,30 @@ int fluxgnn_pack_weights_tc(const float* w_in, const float* b_in, const float* w
     return FLUXGNN_OK;
 }
 
+size_t fluxgnn_packed_tc16_weight_bytes(int num_layers) {
+    if (num_layers < 1 || num_layers > kMaxL) return 0;
+    return packed_tc16_bytes(num_layers);
+}
+
+int fluxgnn_pack_weights_tc16(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
+                              const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
+                              int num_layers, int precision, void* packed, void* stream) {
+    if (num_layers < 1 || num_layers > kMaxL)
+        return set_error(FLUXGNN_EUNSUP, "num_layers must be in 1..%d, got %d", kMaxL, num_layers);
+    if (precision != FLUXGNN_TC_FP16X3 && precision != FLUXGNN_TC_FP16 && precision != FLUXGNN_TC_BF16)
+        return set_error(FLUXGNN_EINVAL, "pack_weights_tc16: precision must be FLUXGNN_TC_FP16X3, _FP16 or _BF16");
+    if (!w_in || !b_in || !w_upd || !b_upd || !w_e1 || !b_e1 || !w_e2 || !b_e2 || !packed)
+        return set_error(FLUXGNN_EINVAL, "null weight pointer");
+    const size_t total = packed_tc16_bytes(num_layers) / 2;
+    const int blocks = (int)((total + 255) / 256);
+    pack_weights_tc16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_in, b_in, w_upd, b_upd, w_e1, b_e1, w_e2, b_e2,
+                                                                        num_layers, precision == FLUXGNN_TC_BF16 ? 1 : 0,
+                                                                        (unsigned char*)packed);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 int fluxgnn_poisson_table(int nx, double length, double* gtab, void* stream) {
     if (nx < 1 || !(length > 0.0) || gtab == nullptr)
         return set_error(FLUXGNN_EINVAL, "poisson_table: nx=%d length=%g gtab=%p", nx, length, (void*)gtab);
@@ -201,6 +229,19 @@ int fluxgnn_poisson_spectral(const float* n, long long n_ic_stride, float* E, lo
 }
 
 }  // extern "C"
+
+static bool tc_precision_known(int precision) {
+    return precision == FLUXGNN_TC_TF32X3 || precision == FLUXGNN_TC_TF32 || precision == FLUXGNN_TC_FP16X3 ||
+           precision == FLUXGNN_TC_FP16 || precision == FLUXGNN_TC_BF16;
+}
+
+// Tensor-path fields of the launch arguments; must run BEFORE plan_tiles (the tile height depends on it).
+static void tc_configure(HybridArgs& a, int precision) {
+    a.tc_parts = (precision == FLUXGNN_TC_TF32X3 || precision == FLUXGNN_TC_FP16X3) ? 2 : 1;
+    a.tc_format = (precision == FLUXGNN_TC_BF16) ? 1 : 0;
+    const bool wide = precision == FLUXGNN_TC_FP16X3 || precision == FLUXGNN_TC_FP16 || precision == FLUXGNN_TC_BF16;
+    a.tile_rows = wide ? kTc16TileRows : kTileRows;
+}
 
 static int tc_shape_ok(int whole_ic, int nx, int radius) {
     if (radius > 4) return set_error(FLUXGNN_EUNSUP, "tensor path: radius must be <= 4, got %d", radius);
@@ -230,13 +271,13 @@ static int forward_ring_impl(int precision, const void* packed, int num_layers, 
     a.acts = acts;
     a.acts_stride = (long long)B * nx * kH;
     int fast = 0;
+    if (precision != 0) tc_configure(a, precision);
     rc = plan_tiles(a, &fast);
     if (rc != FLUXGNN_OK) return rc;
     if (precision != 0) {
         if (hops != 1) return set_error(FLUXGNN_EUNSUP, "tensor path: forward emits hop 1 only");
         rc = tc_shape_ok(a.whole_ic, nx, radius);
         if (rc != FLUXGNN_OK) return rc;
-        a.tc_parts = (precision == FLUXGNN_TC_TF32X3) ? 2 : 1;
         fast = -radius;
     }
     return launch_tiles(a, fast, (cudaStream_t)stream);
@@ -253,8 +294,8 @@ int fluxgnn_forward_ring(const void* packed, int num_layers, const float* state,
 int fluxgnn_forward_ring_tc(const void* packed_tc, int num_layers, int precision, const float* state,
                             const float* x, int B, int nx, int radius, float* flux_edges, float* face_flux,
                             void* stream) {
-    if (precision != FLUXGNN_TC_TF32X3 && precision != FLUXGNN_TC_TF32)
-        return set_error(FLUXGNN_EINVAL, "forward_ring_tc: precision must be FLUXGNN_TC_TF32X3 or FLUXGNN_TC_TF32");
+    if (!tc_precision_known(precision))
+        return set_error(FLUXGNN_EINVAL, "forward_ring_tc: precision must be one of FLUXGNN_TC_*, got %d", precision);
     return forward_ring_impl(precision, packed_tc, num_layers, state, x, B, nx, radius, 1, flux_edges, face_flux,
                              stream);
 }
@@ -295,12 +336,12 @@ static int hybrid_rollout_impl(int precision, const void* packed, int num_layers
     a.c = c; a.dt = dt;
     a.record_every = record_every < 1 ? 1 : record_every;
     int fast = 0;
+    if (precision != 0) tc_configure(a, precision);
     rc = plan_tiles(a, &fast);
     if (rc != FLUXGNN_OK) return rc;
     if (precision != 0) {
         rc = tc_shape_ok(a.whole_ic, nx, radius);
         if (rc != FLUXGNN_OK) return rc;
-        a.tc_parts = (precision == FLUXGNN_TC_TF32X3) ? 2 : 1;
         fast = -radius;                                   // launch_tiles(): negative = tensor kernel
     }
 
@@ -352,8 +393,8 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                               float* state_out, const float* x, const double* gtab, int B, int nx, double length,
                               int radius, float c, float dt, int steps, int record_every, float* traj,
                               void* workspace, void* stream) {
-    if (precision != FLUXGNN_TC_TF32X3 && precision != FLUXGNN_TC_TF32)
-        return set_error(FLUXGNN_EINVAL, "hybrid_rollout_tc: precision must be FLUXGNN_TC_TF32X3 or FLUXGNN_TC_TF32");
+    if (!tc_precision_known(precision))
+        return set_error(FLUXGNN_EINVAL, "hybrid_rollout_tc: precision must be one of FLUXGNN_TC_*, got %d", precision);
     return hybrid_rollout_impl(precision, packed_tc, num_layers, state_in, state_out, x, gtab, B, nx, length, radius,
                                c, dt, steps, record_every, traj, workspace, stream);
 }
@@ -444,7 +485,7 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, 
     int rc = check_model(packed, num_layers, B, owned, radius);
     if (rc != FLUXGNN_OK) return rc;
     if (!state_ext || !x_ext || !state_out) return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: null pointer");
-    if (precision != 0 && precision != FLUXGNN_TC_TF32X3 && precision != FLUXGNN_TC_TF32)
+    if (precision != 0 && !tc_precision_known(precision))
         return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: bad precision %d", precision);
     if (halo != num_layers * radius + 1)
         return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: halo must be num_layers*radius+1 = %d, got %d",
@@ -458,11 +499,14 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, 
     a.B = B; a.nx = owned; a.radius = radius; a.L = num_layers; a.hops = 1;
     a.do_update = 1; a.steps = 1; a.record_every = 1;
     a.c = c; a.dt = dt;
+    a.tile_rows = kTileRows;
+    if (precision != 0) tc_configure(a, precision);
     // always window tiles: the receptive field is served by the ghost cells
     a.whole_ic = 0;
     a.halo = halo;
-    a.valid = kTileRows - 2 * halo;
-    if (a.valid < 8) return set_error(FLUXGNN_EUNSUP, "receptive field of %d cells does not fit a 128-cell tile", halo);
+    a.valid = a.tile_rows - 2 * halo;
+    if (a.valid < 8)
+        return set_error(FLUXGNN_EUNSUP, "receptive field of %d cells does not fit a %d-cell tile", halo, a.tile_rows);
     a.tiles_per_ic = (owned + a.valid - 1) / a.valid;
     const long long tiles = (long long)B * a.tiles_per_ic;
     if (tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");
@@ -473,7 +517,6 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, 
     if (precision != 0) {
         rc = tc_shape_ok(0, owned, radius);
         if (rc != FLUXGNN_OK) return rc;
-        a.tc_parts = (precision == FLUXGNN_TC_TF32X3) ? 2 : 1;
         fast = -radius;
     }
     return launch_tiles(a, fast, (cudaStream_t)stream);

@@ -213,6 +213,22 @@ __host__ __device__ inline size_t packed_tc_floats(int L) {
 }
 
 // ---------------------------------------------------------------------------
+// 16-bit tensor-path weight stream (fluxgnn_pack_weights_tc16; hybrid_tc16_kernel.cu): small block as
+// above (fp32), then per layer 8 units of 16 KiB, each the shared-memory image of a K-major,
+// 128-byte-swizzled UMMA A operand [128 output features] x [64 k] of 16-bit numbers:
+//   unit index = (kb * 2 + blk) * 2 + part,  kb = k / 64 (0..1), blk as above,
+//   part 0 = r16(S W), 1 = r16(S W - part 0),  S = kTc16WeightScale, r16 = fp16 or bf16 rounding
+//   element (n, kk) at byte n*128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2.
+// ---------------------------------------------------------------------------
+constexpr int kTc16TileRows = 256;
+constexpr float kTc16WeightScale = 256.0f;
+constexpr int kTc16UnitBytes = kH * 64 * 2;            // 16 KiB
+constexpr int kTc16UnitsPerLayer = 8;
+__host__ __device__ inline size_t packed_tc16_bytes(int L) {
+    return (size_t)SmallParams::count * sizeof(float) + (size_t)(L + 1) * kTc16UnitsPerLayer * kTc16UnitBytes;
+}
+
+// ---------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------
 int set_error(int code, const char* fmt, ...);

@@ -4,6 +4,9 @@
 //   poisson_direct_kernel  E = g (*) (n - 1), any nx           src/baseline_solver.py:59-68
 //   baseline_fv_kernel     upwind / forward-Euler + viscosity  src/baseline_solver.py:70-94
 //   pack_weights_kernel    state_dict -> streaming layout      src/flux_gnn.py:17-38
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "field_kernels.cuh"
 
@@ -250,6 +253,62 @@ __global__ void __launch_bounds__(256) rollout_metrics_kernel(const float* __res
 }
 
 // Tensor-path stream: small block + pre-swizzled UMMA operand images (layout: common.cuh)
+// 16-bit tensor-path packing (layout in common.cuh): one thread per 16-bit element of the stream,
+// the small block is copied as fp32 by the first threads.  format 0 = fp16, 1 = bf16.
+__global__ void pack_weights_tc16_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
+                                         const float* __restrict__ w_upd, const float* __restrict__ b_upd,
+                                         const float* __restrict__ w_e1, const float* __restrict__ b_e1,
+                                         const float* __restrict__ w_e2, const float* __restrict__ b_e2,
+                                         int L, int format, unsigned char* __restrict__ packed) {
+    float* small = reinterpret_cast<float*>(packed);
+    unsigned short* stream = reinterpret_cast<unsigned short*>(packed + (size_t)SmallParams::count * sizeof(float));
+    const size_t elems = (size_t)(L + 1) * kTc16UnitsPerLayer * (kTc16UnitBytes / 2);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < elems + SmallParams::count;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        if (idx < (size_t)SmallParams::count) {
+            const int o = (int)idx;
+            float v = 0.f;
+            if (o < SmallParams::b_in) {
+                const int f = o / kH, n = o % kH;
+                v = w_in[n * kF + f];
+            } else if (o < SmallParams::b_upd) {
+                v = b_in[o - SmallParams::b_in];
+            } else if (o < SmallParams::b_e1) {
+                const int q = o - SmallParams::b_upd;
+                v = (q < L * kH) ? b_upd[q] : 0.f;
+            } else if (o < SmallParams::w_e2) {
+                v = b_e1[o - SmallParams::b_e1];
+            } else if (o < SmallParams::b_e2) {
+                v = w_e2[o - SmallParams::w_e2];
+            } else if (o == SmallParams::b_e2) {
+                v = b_e2[0];
+            }
+            small[o] = v;
+            continue;
+        }
+        const size_t q = idx - SmallParams::count;
+        constexpr int kUnitElems = kTc16UnitBytes / 2;               // 8192
+        const int layer = (int)(q / ((size_t)kTc16UnitsPerLayer * kUnitElems));
+        const int u = (int)((q / kUnitElems) % kTc16UnitsPerLayer);
+        const int within = (int)(q % kUnitElems);
+        const int row = within >> 6;                                 // output feature n (128 bytes = 64 elements per row)
+        const int chunk_phys = (within & 63) >> 3, e = within & 7;
+        const int kk = ((chunk_phys ^ (row & 7)) << 3) | e;          // k inside the 64-wide K-block
+        const int kb = u >> 2, blk = (u >> 1) & 1, part = u & 1;
+        const float* W = (layer < L) ? (w_upd + (size_t)layer * kH * 2 * kH) : w_e1;
+        const float w = kTc16WeightScale * W[(size_t)row * 2 * kH + (blk == 0 ? kH : 0) + kb * 64 + kk];
+        unsigned short bits;
+        if (format == 1) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+            bits = part == 0 ? __bfloat16_as_ushort(hi) : __bfloat16_as_ushort(__float2bfloat16_rn(w - __bfloat162float(hi)));
+        } else {
+            const __half hi = __float2half_rn(w);
+            bits = part == 0 ? __half_as_ushort(hi) : __half_as_ushort(__float2half_rn(w - __half2float(hi)));
+        }
+        stream[q] = bits;
+    }
+}
+
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w_in, const float* __restrict__ b_in,
                                        const float* __restrict__ w_upd, const float* __restrict__ b_upd,
                                        const float* __restrict__ w_e1, const float* __restrict__ b_e1,

@@ -17,6 +17,9 @@ __global__ void pack_weights_kernel(const float* w_in, const float* b_in, const 
 __global__ void pack_weights_tc_kernel(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
                                        const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
                                        int L, float* packed);
+__global__ void pack_weights_tc16_kernel(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
+                                         const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
+                                         int L, int format, unsigned char* packed);
 __global__ void rollout_metrics_kernel(const float* pred, const float* truth, int nx, float* out);
 __global__ void ffma_probe_kernel(float* out, int iters, float a, float b);
 __global__ void ffma2_probe_kernel(float* out, int iters, float a, float b);

@@ -25,7 +25,9 @@ struct HybridArgs {
     int do_update;             // 0: forward only; 1: finite-volume update (+ field solve when whole_ic)
     int steps, record_every;   // steps > 1 only for whole-IC update mode
     float c, dt;               // float32(dt/dx), float32(dt)
-    int tc_parts;              // tensor path only: 2 = tf32x3 (hi/lo split), 1 = plain tf32
+    int tc_parts;              // tensor path only: 2 = x3 split (hi/lo parts, three products), 1 = one product
+    int tc_format;             // 16-bit tensor path: 0 = fp16, 1 = bf16 operands
+    int tile_rows;             // cells per tile: 128 (kTileRows) or 256 (16-bit tensor path)
     float* acts;               // nullable (FP32-pipe kernel, training forward): saved activations, row-major
     long long acts_stride;     //   [L+3][B*nx][128]: h^0..h^L, then P + b1 and Q of the edge readout
     int split;                 // FP32-pipe kernel: two skewed 64-row groups per tile (whole-IC tiles, nx | 64)
@@ -39,5 +41,9 @@ cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, 
 
 // Tensor-core (tcgen05) variant, hybrid_tc_kernel.cu: radius 1..4, a.hops == 1, segments of 32/64/128 rows.
 cudaError_t launch_hybrid_tc_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream);
+
+// 16-bit tensor-core variant, hybrid_tc16_kernel.cu: 256-row tiles (a.tile_rows == 256), radius 1..4,
+// a.hops == 1, whole-IC segments of 32/64/128 rows.
+cudaError_t launch_hybrid_tc16_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream);
 
 }  // namespace fluxgnn

@@ -1,0 +1,528 @@
+// Tensor-core variant of the fused hybrid step with 16-bit operands and 256-row tiles
+// (sm_100a: tcgen05.mma kind::f16 + TMEM + bulk-copy TMA).
+//
+// Why this shape (measured with scripts/probes/umma_probe.cu on B200): one tcgen05.mma with
+// M = 128 costs ~136 clk for any N <= 128 and ~172 clk for N = 256, for a 32-byte K step of either
+// operand type.  Per flop an N = 256 instruction is therefore 1.6x cheaper than N = 128, and a
+// 16-bit operand (K = 16 per instruction) twice as cheap as TF32 (K = 8).  The tile is 256 rows
+// (cells) so that every instruction is M = 128 output features x N = 256 rows.
+//
+// The product is issued TRANSPOSED as in hybrid_tc_kernel.cu: D^T[n][i] = sum_k W[n][k] h[i][k];
+// the accumulator has TMEM lane = feature, column = row, so the +-r window of the message-passing
+// mean is register indexing.  D_Z = W[:, H:] h in TMEM columns [0,256), D_Y = W[:, :H] h in [256,512)
+// (the whole tensor memory of the SM: one CTA per SM).
+//
+// Precision modes (HybridArgs::tc_parts / tc_format):
+//   "fp16x3": h = h0 + h1, 256 W = w0 + w1 with every part an fp16 number (11 significant bits each,
+//             22 together -- the same as the tf32x3 split);  D = w0 h0 + w0 h1 + w1 h0 accumulated in
+//             fp32, then scaled by 2^-8 in the epilogue.  The power-of-two scale keeps w1 (~2^-11 |w0|)
+//             in fp16's normal range; h1 falls into the subnormal range only for |h| < 0.125, where
+//             the absolute error (<= 2^-25) is below the fp32 rounding noise of the sum.
+//   "fp16"  : D = w0 h0 (one product, 2x the TF32 rate; same 11-bit operands as plain tf32)
+//   "bf16"  : one product with bfloat16 operands (8 significant bits; loosest tolerance, widest range)
+//
+// Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quadrant = warp % 4, row chunks warp / 4
+// and warp / 4 + 4 of 32 rows each), warp 16 weight producer, warp 17 TMEM allocator + UMMA issuer.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "hybrid_kernel.cuh"
+
+namespace fluxgnn {
+
+namespace {
+
+constexpr int kRows = kTc16TileRows;              // 256 cells per tile (= UMMA N)
+constexpr int kStages = 4;
+constexpr int kEpiThreads = 512;
+constexpr int kProducerWarp = 16, kMmaWarp = 17;
+constexpr int kThreads = kEpiThreads + 64;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColZ = 0, kColY = 256;
+constexpr int kActBlockBytes = kRows * 128;       // [256 rows][64 k] 16-bit, K-major SW128: 32 KiB
+constexpr float kUnscale = 1.0f / kTc16WeightScale;
+
+struct __align__(1024) Smem {
+    unsigned char act[2][2][kActBlockBytes];      // [part][k-block]: the UMMA B operand (activations)
+    unsigned char Ws[kStages][kTc16UnitBytes];    // streamed weight operand images (UMMA A operand)
+    float small[SmallParams::count];
+    float sN[kRows], sU[kRows], sE[kRows], sX[kRows];
+    float sF[kRows], sRho[kRows];
+    float edgeP[4][2][kRows];                     // per feature quadrant: partial fwd / bwd dot products of each row
+    double gtab[128];
+    int rowIC[kRows];
+    int rowCell[kRows];
+    short prevRow[kRows], nextRow[kRows];
+    uint64_t full[kStages], empty[kStages];
+    uint64_t act_ready, acc_ready;
+    uint32_t tmem_base;
+#ifdef FLUXGNN_TC_TIMING
+    long long timing[16];
+#endif
+};
+static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "tensor tile does not fit shared memory");
+
+#ifdef FLUXGNN_TC_TIMING
+__device__ long long g_tc16_timing[16];
+#define TC_TICK(slot)                                                      \
+    do {                                                                   \
+        if (tid == 0 && blockIdx.x == 0) {                                 \
+            const long long now__ = clock64();                             \
+            S.timing[slot] += now__ - tc_last__;                           \
+            tc_last__ = now__;                                             \
+        }                                                                  \
+    } while (0)
+#else
+#define TC_TICK(slot) do {} while (0)
+#endif
+
+struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+};
+
+// kind::f16 instruction descriptor: fp32 accumulate, A and B K-major, fmt 0 = fp16, 1 = bf16.
+__device__ __forceinline__ uint32_t idesc_f16(int M, int N, int fmt) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// value -> (hi, lo) 16-bit parts.  kBf16 = false: fp16, true: bfloat16.
+template <bool kBf16>
+__device__ __forceinline__ void split16(float h, unsigned short& hi, unsigned short& lo) {
+    if constexpr (kBf16) {
+        const __nv_bfloat16 a = __float2bfloat16_rn(h);
+        hi = __bfloat16_as_ushort(a);
+        lo = __bfloat16_as_ushort(__float2bfloat16_rn(h - __bfloat162float(a)));
+    } else {
+        const __half a = __float2half_rn(h);
+        hi = __half_as_ushort(a);
+        lo = __half_as_ushort(__float2half_rn(h - __half2float(a)));
+    }
+}
+
+// Sum over the 32 lanes of v[r] for every r, result for r = lane (butterfly transpose-reduce:
+// 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < s; ++k) {
+            const float send = upper ? v[k] : v[k + s];
+            const float keep = upper ? v[k + s] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+}  // namespace
+
+// PARTS: 2 = x3 split (hi + lo parts), 1 = one product.
+template <int R, int PARTS, bool kBf16>
+__global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nx = a.nx;
+
+#ifdef FLUXGNN_TC_TIMING
+    if (tid < 16) S.timing[tid] = 0;
+#endif
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], 1);
+        }
+        mbar_init(&S.act_ready, kEpiThreads);
+        mbar_init(&S.acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&S.tmem_base, kTmemCols);
+    for (int i = tid; i < SmallParams::count; i += kThreads) S.small[i] = a.packed[i];
+    if (a.whole_ic && a.do_update)
+        for (int i = tid; i < nx; i += kThreads) S.gtab[i] = a.gtab[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    const int my_tiles = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int layers = a.L + 1;
+
+    if (warp == kProducerWarp) {
+        // ---------------- weight producer ------------------------------------------------
+        if (lane == 0) {
+            const unsigned char* stream = reinterpret_cast<const unsigned char*>(a.packed + SmallParams::count);
+            Ring r;
+            for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
+                for (int layer = 0; layer < layers; ++layer) {
+                    for (int u = 0; u < kTc16UnitsPerLayer; ++u) {
+                        if (PARTS == 1 && (u & 1)) continue;          // one product: no lo units
+                        mbar_wait(&S.empty[r.stage], r.phase ^ 1);
+                        mbar_arrive_expect_tx(&S.full[r.stage], kTc16UnitBytes);
+                        bulk_g2s(S.Ws[r.stage], stream + ((size_t)layer * kTc16UnitsPerLayer + u) * kTc16UnitBytes,
+                                 kTc16UnitBytes, &S.full[r.stage]);
+                        r.advance();
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ---------------- UMMA issuer (one thread) ---------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16(128, kRows, kBf16 ? 1 : 0);
+            const uint32_t bhi = smem_u32(S.act[0][0]), blo = smem_u32(S.act[1][0]);
+            Ring r;
+            uint32_t act_phase = 0;
+            for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
+                for (int layer = 0; layer < layers; ++layer) {
+                    mbar_wait(&S.act_ready, act_phase);
+                    act_phase ^= 1;
+                    tc_fence_after();
+                    for (int kb = 0; kb < 2; ++kb) {
+                        for (int blk = 0; blk < 2; ++blk) {
+                            const uint32_t d = tmem + (blk == 0 ? kColZ : kColY);
+                            // hi weights x (hi [+ lo] activations)
+                            mbar_wait(&S.full[r.stage], r.phase);
+                            tc_fence_after();
+                            uint32_t wbase = smem_u32(S.Ws[r.stage]);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = umma_desc_sw128(wbase + ks * 32);
+                                umma_f16(d, ad, umma_desc_sw128(bhi + kb * kActBlockBytes + ks * 32), idesc, (kb | ks) != 0);
+                                if (PARTS == 2)
+                                    umma_f16(d, ad, umma_desc_sw128(blo + kb * kActBlockBytes + ks * 32), idesc, 1);
+                            }
+                            umma_commit(&S.empty[r.stage]);
+                            r.advance();
+                            if (PARTS == 2) {
+                                // lo weights x hi activations
+                                mbar_wait(&S.full[r.stage], r.phase);
+                                tc_fence_after();
+                                wbase = smem_u32(S.Ws[r.stage]);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_f16(d, umma_desc_sw128(wbase + ks * 32),
+                                             umma_desc_sw128(bhi + kb * kActBlockBytes + ks * 32), idesc, 1);
+                                umma_commit(&S.empty[r.stage]);
+                                r.advance();
+                            }
+                        }
+                    }
+                    umma_commit(&S.acc_ready);
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue / compute warps ---------------------------------------
+        const int q = warp & 3, cw = warp >> 2;               // TMEM lane quadrant; row chunks cw and cw + 4
+        const int n = 32 * q + lane;                          // this thread's feature = TMEM lane
+        const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+        const float inv_deg = kUnscale / (float)(2 * R);
+        const int seg = a.whole_ic ? nx : kRows;              // periodic segment inside the tile (multiple of 32)
+        uint32_t acc_phase = 0;
+
+        // activation element (row i, feature n): k-block n / 64, 16-byte chunk ((n % 64) / 8) ^ (i & 7), 2 bytes
+        const int kk = n & 63;
+        const uint32_t act_hi = smem_u32(S.act[0][0]) + (uint32_t)((n >> 6) * kActBlockBytes + (kk & 7) * 2);
+        const uint32_t act_lo_off = (uint32_t)(2 * kActBlockBytes);       // S.act[1] - S.act[0]
+        uint32_t act_x[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) act_x[v] = act_hi + ((uint32_t)((kk >> 3) ^ v) << 4);
+        auto store_act = [&](int i0, int j, float h) {        // row i0 + j; j compile-time after unrolling
+            const uint32_t addr = act_x[j & 7] + (uint32_t)(i0 + j) * 128;
+            unsigned short hi, lo;
+            split16<kBf16>(h, hi, lo);
+            sts_u16(addr, hi);
+            if (PARTS == 2) sts_u16(addr + act_lo_off, lo);
+        };
+
+#ifdef FLUXGNN_TC_TIMING
+        long long tc_last__ = clock64();
+#endif
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            TC_TICK(0);
+            // ---- row bookkeeping + state load (as in the FP32-pipe kernel) ----------------
+            if (tid < kRows) {
+                const int j = tid;
+                int ic, cell, prev = (j - 1) & (kRows - 1), next = (j + 1) & (kRows - 1);
+                bool live, owned;
+                int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
+                if (a.whole_ic) {
+                    const int slot = j / nx;
+                    cell = j - slot * nx;
+                    ic = tile * a.ics_per_tile + slot;
+                    live = ic < a.B;
+                    owned = live;
+                    prev = (cell == 0) ? j + nx - 1 : j - 1;
+                    next = (cell == nx - 1) ? j - nx + 1 : j + 1;
+                } else {
+                    ic = tile / a.tiles_per_ic;
+                    const int t = tile - ic * a.tiles_per_ic;
+                    const long long gcell = (long long)t * a.valid - a.halo + j;
+                    cell = (int)(((gcell % nx) + nx) % nx);
+                    live = true;
+                    owned = (j >= a.halo) && (j < a.halo + a.valid) && ((long long)t * a.valid + (j - a.halo) < nx);
+                    if (a.slab) {                       // ghost cells instead of the periodic wrap
+                        long long s = gcell + a.halo;
+                        s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
+                        src = (int)s;
+                        ld = a.ld_in;
+                        cell = (int)(gcell < 0 ? 0 : (gcell >= nx ? nx - 1 : gcell));
+                    }
+                }
+                S.rowIC[j] = owned ? ic : -1;
+                S.rowCell[j] = cell;
+                S.prevRow[j] = (short)prev;
+                S.nextRow[j] = (short)next;
+                float vn = 0.f, vu = 0.f, ve = 0.f, vx = 0.f;
+                if (live) {
+                    if (src < 0) src = cell;
+                    const float* st = a.state_in + (size_t)ic * 3 * ld + src;
+                    vn = __ldg(st);
+                    vu = __ldg(st + ld);
+                    ve = __ldg(st + 2 * (size_t)ld);
+                    vx = __ldg(a.x + src);
+                }
+                S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
+            }
+            named_sync(1, kEpiThreads);
+            TC_TICK(1);
+
+            for (int step = 0; step < a.steps; ++step) {
+                // ---- input MLP (src/flux_gnn.py:49): feature n, this warp's two row chunks ----
+                {
+                    const float w0 = S.small[SmallParams::w_in + 0 * kH + n];
+                    const float w1 = S.small[SmallParams::w_in + 1 * kH + n];
+                    const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
+                    const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
+                    const float b = S.small[SmallParams::b_in + n];
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        const int i0 = 32 * (cw + 4 * half);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int i = i0 + j;
+                            float v = fmaf(w0, S.sN[i], b);
+                            v = fmaf(w1, S.sU[i], v);
+                            v = fmaf(w2, S.sE[i], v);
+                            v = fmaf(w3, S.sX[i], v);
+                            store_act(i0, j, fmaxf(v, 0.f));
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(&S.act_ready);
+                TC_TICK(2);
+
+                for (int layer = 0; layer < layers; ++layer) {
+                    mbar_wait(&S.acc_ready, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                    TC_TICK(3);
+                    const bool is_edge = (layer == a.L);
+                    const float bias = S.small[(is_edge ? SmallParams::b_e1 : SmallParams::b_upd + layer * kH) + n];
+                    const float w_out = S.small[SmallParams::w_e2 + n];
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        const int i0 = 32 * (cw + 4 * half);
+                        const int seg0 = (i0 / seg) * seg;
+                        const int cl = (i0 == seg0) ? i0 - 4 + seg : i0 - 4;
+                        const int cr = (i0 + 32 == seg0 + seg) ? i0 + 32 - seg : i0 + 32;
+                        float y[32], zc[32], zl[4], zr[4];
+                        tmem_ld32(tlane + kColY + i0, y);
+                        tmem_ld32(tlane + kColZ + i0, zc);
+                        tmem_ld4(tlane + kColZ + cl, zl);
+                        tmem_ld4(tlane + kColZ + cr, zr);
+                        tc_wait_ld();
+                        float zw[40];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { zw[t] = zl[t]; zw[36 + t] = zr[t]; }
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) zw[4 + t] = zc[t];
+                        if (!is_edge) {
+                            // h'_i = relu(Y_i + b + mean_{0<|k|<=R} Z_{i+k})   (src/flux_gnn.py:55-60)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float s = zw[4 + j + 1] + zw[4 + j - 1];
+#pragma unroll
+                                for (int k = 2; k <= R; ++k) { s += zw[4 + j + k]; s += zw[4 + j - k]; }
+                                store_act(i0, j, fmaxf(fmaf(s, inv_deg, fmaf(y[j], kUnscale, bias)), 0.f));
+                            }
+                        } else {
+                            // edge readout (src/flux_gnn.py:63-66): this feature's term of the two dot products of
+                            // row i -- fwd (row i, col i+1): w2[n] relu(P_i + b1 + Q_{i+1});  bwd (row i, col i-1) --
+                            // summed over the warp's 32 features in registers, over the 4 quadrants in shared memory
+                            float f[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                y[j] = fmaf(y[j], kUnscale, bias);
+                                f[j] = w_out * fmaxf(fmaf(zw[4 + j + 1], kUnscale, y[j]), 0.f);
+                            }
+                            S.edgeP[q][0][i0 + lane] = lane_transpose_sum(f, lane);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = w_out * fmaxf(fmaf(zw[4 + j - 1], kUnscale, y[j]), 0.f);
+                            S.edgeP[q][1][i0 + lane] = lane_transpose_sum(f, lane);
+                        }
+                    }
+                    if (!is_edge) {
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(&S.act_ready);
+                    }
+                    TC_TICK(is_edge ? 5 : 4);
+                }
+                named_sync(1, kEpiThreads);
+                TC_TICK(6);
+
+                // ---- per row: face flux (src/hybrid_solver.py:45-48) ----------------------------
+                float n_new = 0.f, u_new = 0.f;
+                if (tid < kRows) {
+                    const int j = tid, jn = S.nextRow[j];
+                    const float b2 = S.small[SmallParams::b_e2];
+                    const float fwd = ((S.edgeP[0][0][j] + S.edgeP[1][0][j]) + (S.edgeP[2][0][j] + S.edgeP[3][0][j])) + b2;
+                    const float bwd = ((S.edgeP[0][1][jn] + S.edgeP[1][1][jn]) + (S.edgeP[2][1][jn] + S.edgeP[3][1][jn])) + b2;
+                    const float face = 0.5f * (fwd + bwd);       // edges (row j, col j+1) and (row j+1, col j)
+                    const int ic = S.rowIC[j], cell = S.rowCell[j];
+                    if (a.flux_edges != nullptr && ic >= 0) {
+                        float* fe = a.flux_edges + (size_t)ic * 2 * nx + cell;
+                        fe[0] = fwd;
+                        fe[nx] = bwd;
+                    }
+                    if (a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
+                    S.sF[j] = face;
+                }
+                if (!a.do_update) continue;
+                named_sync(1, kEpiThreads);
+                TC_TICK(7);
+
+                // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
+                if (tid < kRows) {
+                    const int j = tid, p = S.prevRow[j];
+                    const float u = S.sU[j], up = S.sU[p];
+                    n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
+                    const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
+                    const float fup = __fmul_rn(__fmul_rn(0.5f, up), up);
+                    const float u_adv = __fsub_rn(u, __fmul_rn(a.c, __fsub_rn(fu, fup)));
+                    u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, S.sE[j]));
+                }
+                if (!a.whole_ic) {
+                    if (tid < kRows && S.rowIC[tid] >= 0) {
+                        float* so = a.state_out + (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+                        so[0] = n_new;
+                        so[nx] = u_new;
+                    }
+                    continue;
+                }
+                named_sync(1, kEpiThreads);
+                if (tid < kRows) {
+                    S.sN[tid] = n_new;
+                    S.sU[tid] = u_new;
+                    S.sRho[tid] = __fsub_rn(n_new, 1.0f);
+                }
+                named_sync(1, kEpiThreads);
+                TC_TICK(8);
+                // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
+                {
+                    const int row = tid >> 1, part = tid & 1;
+                    const int cell = S.rowCell[row], base = row - cell;
+                    double e = 0.0;
+                    for (int i = part; i < nx; i += 2) {
+                        int d = cell - i;
+                        if (d < 0) d += nx;
+                        e = fma(S.gtab[d], (double)S.sRho[base + i], e);
+                    }
+                    e += __shfl_xor_sync(0xffffffffu, e, 1);
+                    if (part == 0) S.sE[row] = (float)e;
+                }
+                named_sync(1, kEpiThreads);
+                TC_TICK(9);
+                if (tid < kRows && S.rowIC[tid] >= 0) {
+                    const size_t off = (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+                    if (step == a.steps - 1) {
+                        a.state_out[off] = S.sN[tid];
+                        a.state_out[off + nx] = S.sU[tid];
+                        a.state_out[off + 2 * (size_t)nx] = S.sE[tid];
+                    }
+                    if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
+                        float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
+                        tr[0] = S.sN[tid];
+                        tr[nx] = S.sU[tid];
+                        tr[2 * (size_t)nx] = S.sE[tid];
+                    }
+                }
+                TC_TICK(10);
+            }   // steps
+            named_sync(1, kEpiThreads);
+        }       // tiles
+    }
+
+    tc_fence_before();
+    __syncthreads();
+#ifdef FLUXGNN_TC_TIMING
+    if (blockIdx.x == 0 && tid < 16) g_tc16_timing[tid] += S.timing[tid];
+#endif
+    if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+}
+
+#ifdef FLUXGNN_TC_TIMING
+extern "C" int fluxgnn_debug_tc_timing(long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, g_tc16_timing, sizeof(g_tc16_timing)) != cudaSuccess) return -1;
+    if (reset) {
+        long long zero[16] = {0};
+        if (cudaMemcpyToSymbol(g_tc16_timing, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
+
+template <int R, int PARTS, bool kBf16>
+static cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream) {
+    const int smem = (int)sizeof(Smem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tc16_kernel<R, PARTS, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    hybrid_tc16_kernel<R, PARTS, kBf16><<<grid, kThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_radius(const HybridArgs& a, int grid, cudaStream_t stream) {
+    if (a.tc_format == 1) return launch_one<R, 1, true>(a, grid, stream);            // bf16
+    if (a.tc_parts == 2) return launch_one<R, 2, false>(a, grid, stream);             // fp16x3
+    return launch_one<R, 1, false>(a, grid, stream);                                  // fp16
+}
+
+cudaError_t launch_hybrid_tc16_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream) {
+    switch (radius) {
+        case 1: return launch_radius<1>(a, grid, stream);
+        case 2: return launch_radius<2>(a, grid, stream);
+        case 3: return launch_radius<3>(a, grid, stream);
+        case 4: return launch_radius<4>(a, grid, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace fluxgnn

@@ -75,7 +75,7 @@ class DomainDecomposedHybridSolver:
         if self.owned < self.halo:
             raise ValueError(f"a slab of {self.owned} cells is narrower than the halo of {self.halo}")
         if precision != "fp32" and precision not in _lib.TC_PRECISIONS:
-            raise ValueError(f"precision must be 'fp32', 'tf32x3' or 'tf32', got {precision!r}")
+            raise ValueError(f"precision must be 'fp32' or one of {sorted(_lib.TC_PRECISIONS)}, got {precision!r}")
         self.precision = precision
         self.grid = PeriodicGrid(self.nx, self.length)
         idx = (rank * self.owned - self.halo + np.arange(self.owned + 2 * self.halo)) % self.nx
@@ -87,7 +87,7 @@ class DomainDecomposedHybridSolver:
     # ---- local pieces -------------------------------------------------------------------
     def _cuda_slab(self, ext: torch.Tensor) -> torch.Tensor:
         tensor_path = self.precision != "fp32"
-        packed = self.model.packed_weights("tc" if tensor_path else "fp32")
+        packed = self.model.packed_weights(_lib.weight_layout(self.precision))
         B = ext.shape[0]
         with torch.cuda.device(self.device):
             out = torch.empty(B, 3, self.owned, dtype=torch.float32, device=self.device)

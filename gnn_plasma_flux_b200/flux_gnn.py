@@ -48,7 +48,8 @@ class FluxGNN(nn.Module):
     def packed_weights(self, layout: str = "fp32") -> torch.Tensor:
         """Weights in a kernel's streaming layout (device float32), repacked only when a
         parameter was replaced, moved or modified in place.  layout "fp32": K-major halves
-        for the FP32-pipe kernel; "tc": pre-swizzled TF32 hi/lo UMMA operand images."""
+        for the FP32-pipe kernel; "tc": pre-swizzled TF32 hi/lo UMMA operand images; "tc16" /
+        "tc16_bf16": the 16-bit (fp16 / bfloat16) operand images of the 256-row tensor kernel."""
         self._check_supported()
         params = list(self.parameters())
         dev = params[0].device
@@ -65,13 +66,21 @@ class FluxGNN(nn.Module):
                 small = [f32(self.input_mlp[0].weight), f32(self.input_mlp[0].bias), w_upd, b_upd,
                          f32(self.edge_mlp[0].weight), f32(self.edge_mlp[0].bias),
                          f32(self.edge_mlp[2].weight), f32(self.edge_mlp[2].bias)]
-                size_fn, pack_fn = ((_lib.lib().fluxgnn_packed_tc_weight_bytes, _lib.lib().fluxgnn_pack_weights_tc)
-                                    if layout == "tc" else
-                                    (_lib.lib().fluxgnn_packed_weight_bytes, _lib.lib().fluxgnn_pack_weights))
-                packed = torch.empty(size_fn(self.num_layers) // 4, dtype=torch.float32, device=dev)
+                L = _lib.lib()
                 stream = torch.cuda.current_stream(dev).cuda_stream
-                _lib.check(pack_fn(*[t.data_ptr() for t in small], self.num_layers, packed.data_ptr(), stream),
-                           "fluxgnn_pack_weights" + ("_tc" if layout == "tc" else ""))
+                ptrs = [t.data_ptr() for t in small]
+                if layout in ("tc16", "tc16_bf16"):
+                    packed = torch.empty(L.fluxgnn_packed_tc16_weight_bytes(self.num_layers) // 4, dtype=torch.float32,
+                                         device=dev)
+                    code = _lib.TC_PRECISIONS["bf16" if layout == "tc16_bf16" else "fp16x3"]
+                    _lib.check(L.fluxgnn_pack_weights_tc16(*ptrs, self.num_layers, code, packed.data_ptr(), stream),
+                               "fluxgnn_pack_weights_tc16")
+                else:
+                    size_fn, pack_fn = ((L.fluxgnn_packed_tc_weight_bytes, L.fluxgnn_pack_weights_tc) if layout == "tc"
+                                        else (L.fluxgnn_packed_weight_bytes, L.fluxgnn_pack_weights))
+                    packed = torch.empty(size_fn(self.num_layers) // 4, dtype=torch.float32, device=dev)
+                    _lib.check(pack_fn(*ptrs, self.num_layers, packed.data_ptr(), stream),
+                               "fluxgnn_pack_weights" + ("_tc" if layout == "tc" else ""))
                 # `small` must outlive the (asynchronous) packing kernel: same-stream
                 # allocator reuse is ordered after it, so dropping the references is safe.
             hit = (key, packed)
@@ -82,13 +91,13 @@ class FluxGNN(nn.Module):
     def ring_fluxes(self, state: torch.Tensor, x: torch.Tensor, radius: int = 1, hops: int | None = None,
                     want_edges: bool = True, want_face: bool = False, precision: str = "fp32"):
         """state [B,3,nx] (CUDA float32), x [nx] -> (flux_edges [B, 2*hops*nx] | None, face_flux [B,nx] | None).
-        precision 'tf32x3' / 'tf32' runs the tensor-core kernel (hop 1 only)."""
+        precision 'fp16x3' / 'fp16' / 'bf16' / 'tf32x3' / 'tf32' runs a tensor-core kernel (hop 1 only)."""
         if state.dim() != 3 or state.shape[1] != 3:
             raise ValueError(f"state must be [B,3,nx], got {tuple(state.shape)}")
         tensor_path = precision != "fp32"
         if tensor_path and precision not in _lib.TC_PRECISIONS:
-            raise ValueError(f"precision must be 'fp32', 'tf32x3' or 'tf32', got {precision!r}")
-        packed = self.packed_weights("tc" if tensor_path else "fp32")
+            raise ValueError(f"precision must be 'fp32' or one of {sorted(_lib.TC_PRECISIONS)}, got {precision!r}")
+        packed = self.packed_weights(_lib.weight_layout(precision))
         state = state.to(device=packed.device, dtype=torch.float32).contiguous()
         x = x.to(device=packed.device, dtype=torch.float32).contiguous()
         B, _, nx = state.shape

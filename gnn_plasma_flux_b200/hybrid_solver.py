@@ -42,7 +42,7 @@ class HybridSolver:
         self.radius = radius
         self.graph_radius = 1 if graph_radius is None else int(graph_radius)
         if precision != "fp32" and precision not in _lib.TC_PRECISIONS:
-            raise ValueError(f"precision must be 'fp32', 'tf32x3' or 'tf32', got {precision!r}")
+            raise ValueError(f"precision must be 'fp32' or one of {sorted(_lib.TC_PRECISIONS)}, got {precision!r}")
         self.precision = precision
         self._pinned = {}
 
@@ -54,7 +54,7 @@ class HybridSolver:
         if state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != base.nx:
             raise ValueError(f"state must be [B,3,{base.nx}], got {tuple(state.shape)}")
         tensor_path = self.precision != "fp32"
-        packed = self.model.packed_weights("tc" if tensor_path else "fp32")
+        packed = self.model.packed_weights(_lib.weight_layout(self.precision))
         dev = packed.device
         if state.device != dev or state.dtype != torch.float32 or not state.is_contiguous():
             state = state.to(device=dev, dtype=torch.float32).contiguous()
@@ -109,7 +109,7 @@ class HybridSolver:
         """fluxgnn_hybrid_rollout[_tc] on caller-provided device-addressable buffers (no checks, nx <= 128)."""
         base = self.baseline
         tensor_path = self.precision != "fp32"
-        packed = self.model.packed_weights("tc" if tensor_path else "fp32")
+        packed = self.model.packed_weights(_lib.weight_layout(self.precision))
         x_dev, gtab = base.grid.tables(dev)
         B, _, nx = src.shape
         with torch.cuda.device(dev):

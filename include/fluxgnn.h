@@ -143,9 +143,28 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers,
  * packed_tc comes from fluxgnn_pack_weights_tc (same inputs as fluxgnn_pack_weights;
  * the stream holds pre-swizzled UMMA operand images, hi and lo parts).
  * Supported: radius <= 4; nx in {32, 64, 128} or nx > 128; other shapes -> FLUXGNN_EUNSUP
- * (the caller decides to use the fp32 entry point; there is no silent fallback). */
+ * (the caller decides to use the fp32 entry point; there is no silent fallback).
+ *
+ * 16-bit operand modes (tcgen05 kind::f16, 256-cell tiles; twice the TF32 rate per product):
+ *   FLUXGNN_TC_FP16X3  h and 2^8 W are split into two fp16 parts each (22 significant bits
+ *                      together, as in the TF32 split), three products accumulated in fp32 and
+ *                      rescaled: fp32-level accuracy, same parity gates as fluxgnn_hybrid_rollout.
+ *   FLUXGNN_TC_FP16    one fp16 product (11-bit operands like plain TF32; activations beyond
+ *                      65504 overflow).
+ *   FLUXGNN_TC_BF16    one bfloat16 product (8-bit operands): loosest tolerance, fp32 range.
+ * Their packed_tc comes from fluxgnn_pack_weights_tc16(..., precision, ...): the fp16 image
+ * serves FP16X3 and FP16, the bf16 image serves BF16. */
 #define FLUXGNN_TC_TF32X3 1
 #define FLUXGNN_TC_TF32   2
+#define FLUXGNN_TC_FP16X3 3
+#define FLUXGNN_TC_FP16   4
+#define FLUXGNN_TC_BF16   5
+size_t fluxgnn_packed_tc16_weight_bytes(int num_layers);
+int fluxgnn_pack_weights_tc16(const float* w_in, const float* b_in,
+                              const float* w_upd, const float* b_upd,
+                              const float* w_e1, const float* b_e1,
+                              const float* w_e2, const float* b_e2,
+                              int num_layers, int precision, void* packed_tc, void* stream);
 size_t fluxgnn_packed_tc_weight_bytes(int num_layers);
 int fluxgnn_pack_weights_tc(const float* w_in, const float* b_in,
                             const float* w_upd, const float* b_upd,
