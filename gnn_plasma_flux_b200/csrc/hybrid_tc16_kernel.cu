@@ -102,13 +102,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         : "memory");
 }
 
-__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+// store the low 16 bits of a 32-bit register (no repacking instruction)
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(addr), "r"(v) : "memory");
 }
 
 // value -> (hi, lo) 16-bit parts.  kBf16 = false: fp16, true: bfloat16.
 template <bool kBf16>
-__device__ __forceinline__ void split16(float h, unsigned short& hi, unsigned short& lo) {
+__device__ __forceinline__ void split16(float h, uint32_t& hi, uint32_t& lo) {
     if constexpr (kBf16) {
         const __nv_bfloat16 a = __float2bfloat16_rn(h);
         hi = __bfloat16_as_ushort(a);
@@ -141,8 +142,11 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
 // PARTS: 2 = x3 split (hi + lo parts), 1 = one product.
 template <int R, int PARTS, bool kBf16>
 __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte aligned as declared (the 128-byte swizzle needs it; checked below).  Indexing the array
+    // itself -- not a re-aligned generic pointer -- keeps every access in the shared address space (LDS/STS).
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int nx = a.nx;
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         for (int v = 0; v < 8; ++v) act_x[v] = act_hi + ((uint32_t)((kk >> 3) ^ v) << 4);
         auto store_act = [&](int i0, int j, float h) {        // row i0 + j; j compile-time after unrolling
             const uint32_t addr = act_x[j & 7] + (uint32_t)(i0 + j) * 128;
-            unsigned short hi, lo;
+            uint32_t hi, lo;
             split16<kBf16>(h, hi, lo);
             sts_u16(addr, hi);
             if (PARTS == 2) sts_u16(addr + act_lo_off, lo);
@@ -323,13 +327,15 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     for (int half = 0; half < 2; ++half) {
                         const int i0 = 32 * (cw + 4 * half);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int i = i0 + j;
-                            float v = fmaf(w0, S.sN[i], b);
-                            v = fmaf(w1, S.sU[i], v);
-                            v = fmaf(w2, S.sE[i], v);
-                            v = fmaf(w3, S.sX[i], v);
-                            store_act(i0, j, fmaxf(v, 0.f));
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 vn = *reinterpret_cast<const float4*>(&S.sN[i0 + j]);
+                            const float4 vu = *reinterpret_cast<const float4*>(&S.sU[i0 + j]);
+                            const float4 ve = *reinterpret_cast<const float4*>(&S.sE[i0 + j]);
+                            const float4 vx = *reinterpret_cast<const float4*>(&S.sX[i0 + j]);
+                            store_act(i0, j + 0, fmaxf(fmaf(w3, vx.x, fmaf(w2, ve.x, fmaf(w1, vu.x, fmaf(w0, vn.x, b)))), 0.f));
+                            store_act(i0, j + 1, fmaxf(fmaf(w3, vx.y, fmaf(w2, ve.y, fmaf(w1, vu.y, fmaf(w0, vn.y, b)))), 0.f));
+                            store_act(i0, j + 2, fmaxf(fmaf(w3, vx.z, fmaf(w2, ve.z, fmaf(w1, vu.z, fmaf(w0, vn.z, b)))), 0.f));
+                            store_act(i0, j + 3, fmaxf(fmaf(w3, vx.w, fmaf(w2, ve.w, fmaf(w1, vu.w, fmaf(w0, vn.w, b)))), 0.f));
                         }
                     }
                 }
@@ -365,11 +371,20 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                         for (int t = 0; t < 32; ++t) zw[4 + t] = zc[t];
                         if (!is_edge) {
                             // h'_i = relu(Y_i + b + mean_{0<|k|<=R} Z_{i+k})   (src/flux_gnn.py:55-60)
+                            // the window sum shares the pair sums pz[t] = Z[t] + Z[t+1] between neighbouring rows
+                            float pz[39];
+                            if constexpr (R >= 2) {
+#pragma unroll
+                                for (int t = 0; t < 39; ++t) pz[t] = zw[t] + zw[t + 1];
+                            }
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                float s = zw[4 + j + 1] + zw[4 + j - 1];
-#pragma unroll
-                                for (int k = 2; k <= R; ++k) { s += zw[4 + j + k]; s += zw[4 + j - k]; }
+                                const int c = 4 + j;                  // window centre in zw
+                                float s;
+                                if constexpr (R == 1) s = zw[c - 1] + zw[c + 1];
+                                else if constexpr (R == 2) s = pz[c - 2] + pz[c + 1];
+                                else if constexpr (R == 3) s = (pz[c - 3] + pz[c + 2]) + (zw[c - 1] + zw[c + 1]);
+                                else s = (pz[c - 4] + pz[c + 3]) + (pz[c - 2] + pz[c + 1]);
                                 store_act(i0, j, fmaxf(fmaf(s, inv_deg, fmaf(y[j], kUnscale, bias)), 0.f));
                             }
                         } else {
