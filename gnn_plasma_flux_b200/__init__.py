@@ -8,6 +8,7 @@ libfluxgnn.so (C ABI: include/fluxgnn.h).  Build the library first:
     python -m gnn_plasma_flux_b200.build
 """
 from .baseline_solver import BaselineSolver
+from .comparison_models import PINN, PureGNN
 from .config import DATASET_CONFIG, EVAL_CONFIG, MODEL_CONFIG, STENCIL_RADII
 from .flux_gnn import FluxGNN
 from .graph_constructor import build_chain_graph, ring_edge_index
@@ -16,5 +17,5 @@ from .datagen import generate_dataset
 from .metrics import compute_metrics, first_nonfinite_step, rollout_metrics
 
 __all__ = ["BaselineSolver", "FluxGNN", "HybridSolver", "build_chain_graph", "ring_edge_index",
-           "generate_dataset", "compute_metrics", "rollout_metrics", "first_nonfinite_step",
+           "generate_dataset", "PureGNN", "PINN", "compute_metrics", "rollout_metrics", "first_nonfinite_step",
            "DATASET_CONFIG", "EVAL_CONFIG", "MODEL_CONFIG", "STENCIL_RADII"]

@@ -59,6 +59,10 @@ SIGNATURES = {
     "fluxgnn_rollout_metrics": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     "fluxgnn_hybrid_slab_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                          c_float, c_float, c_void_p]),
+    "fluxgnn_pure_gnn_packed_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_pure_gnn_pack": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p, c_void_p]),
+    "fluxgnn_pure_gnn_rollout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fluxgnn_dense_layer": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "fluxgnn_baseline_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float,
                                          c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

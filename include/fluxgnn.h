@@ -244,6 +244,24 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out,
                              int steps, int record_every, float* traj,
                              float* flux_n, void* workspace, void* stream);
 
+/* ---- the reference's comparison models ---------------------------------------
+ * PureGNN (scripts/training/train_pure_gnn.py:35-76), rolled out as in
+ * scripts/evaluation/benchmark_timing.py:129-143: per step  state += PureGNN([n,u,E,x], ring edges).
+ * Weights: input_mlp.0 [H][4], update_mlps.l.0 stacked [L][H][2H] / [L][H], output_mlp.0 [H][H],
+ * output_mlp.2 [3][H] / [3] (nn.Linear layouts), H in {64, 128}; nx <= 128; one launch per rollout.
+ * PINN (scripts/training/train_pinn.py:36-61) is a chain of fluxgnn_dense_layer calls:
+ *   out[r][n] = act(sum_k in[r][k] weight[n][k] + bias[n]) (+ residual[r][n]),  activation 0 = none, 1 = tanh. */
+size_t fluxgnn_pure_gnn_packed_bytes(int hidden, int num_layers);
+int fluxgnn_pure_gnn_pack(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
+                          const float* w_o1, const float* b_o1, const float* w_o2, const float* b_o2,
+                          int hidden, int num_layers, void* packed, void* stream);
+int fluxgnn_pure_gnn_rollout(const void* packed, int hidden, int num_layers,
+                             const float* state_in /* [B][3][nx] */, float* state_out,
+                             const float* x, int B, int nx, int steps, void* stream);
+int fluxgnn_dense_layer(const float* in, const float* weight, const float* bias,
+                        const float* residual /* nullable */, float* out,
+                        int rows, int in_features, int out_features, int activation, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

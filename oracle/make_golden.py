@@ -236,6 +236,8 @@ def main():
     g8["state"] = state
     np.savez_compressed(os.path.join(OUT, "g8_gradients.npz"), **g8)
 
+    comparison_goldens()
+
     manifest = {
         "generated_by": "oracle/make_golden.py",
         "reference": "/root/reference (shanedirksen/gnn-plasma-flux, unmodified)",
@@ -249,5 +251,61 @@ def main():
     print("goldens written to", OUT)
 
 
+def comparison_goldens():
+    """G9: the reference's PureGNN and PINN classes, seeded, against the port; their
+    outputs frozen.  `python -m oracle.make_golden --only-g9` regenerates just this file."""
+    sys.path.insert(0, os.path.join(REF, "scripts", "training"))
+    from train_pinn import PINN                               # noqa: E402  (reference)
+    from train_pure_gnn import PureGNN                        # noqa: E402  (reference)
+    torch.set_num_threads(1)
+    g9 = {}
+    base = BaselineSolver(nx=64)
+    ics = np.stack([base.initial_condition(seed=s) for s in range(4)])
+    x32 = base.x.astype(np.float32)
+    for hidden, layers in ((64, 3), (128, 4)):                # class default / the timing benchmark's size
+        torch.manual_seed(7)
+        ref_model = PureGNN(input_dim=4, hidden_dim=hidden, num_layers=layers).eval()
+        w = {k: v.numpy().copy() for k, v in ref_model.state_dict().items()}
+        mine = P.init_pure_gnn_weights(7, 4, hidden, layers)
+        for key in w:
+            same(mine[key], w[key], f"init_pure_gnn_weights[{hidden}][{key}]")
+        tag = f"pgnn{hidden}"
+        with torch.no_grad():
+            feats, ei = build_chain_graph(ics[0], base.x, "cpu")
+            delta = ref_model(feats, ei).numpy()
+            same(P.pure_gnn_forward(w, feats.numpy(), ei.numpy()), delta, f"{tag} forward")
+            g9[f"{tag}_delta"] = delta
+            finals = []
+            for ic in ics:                                    # the loop of benchmark_timing.py:129-143, 10 steps
+                state = ic.copy()
+                for _ in range(10):
+                    _, ei = build_chain_graph(state, base.x, "cpu")
+                    nf = torch.cat([torch.FloatTensor(state).permute(1, 0), torch.FloatTensor(x32).unsqueeze(1)], dim=1)
+                    state = (torch.FloatTensor(state).permute(1, 0) + ref_model(nf, ei)).permute(1, 0).numpy()
+                finals.append(state)
+            same(P.pure_gnn_rollout(w, ics[0], x32, 10), finals[0], f"{tag} 10-step rollout")
+            g9[f"{tag}_rollout10"] = np.stack(finals)
+    torch.manual_seed(11)
+    ref_pinn = PINN(input_dim=3 * 64, hidden_dim=256, num_layers=4).eval()
+    wp = {k: v.numpy().copy() for k, v in ref_pinn.state_dict().items()}
+    mine = P.init_pinn_weights(11, 192, 256, 4)
+    for key in wp:
+        same(mine[key], wp[key], f"init_pinn_weights[{key}]")
+    with torch.no_grad():
+        out = ref_pinn(torch.from_numpy(ics)).numpy()
+        same(P.pinn_forward(wp, ics), out, "pinn forward")
+        g9["pinn_step"] = out
+        state = torch.from_numpy(ics[:1])
+        for _ in range(10):                                   # benchmark_timing.py:186-189
+            state = ref_pinn(state)
+        g9["pinn_rollout10"] = state.numpy()
+    g9["ics"] = ics
+    np.savez_compressed(os.path.join(OUT, "g9_comparison_models.npz"), **g9)
+    print("  wrote g9_comparison_models.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-g9" in sys.argv:
+        comparison_goldens()
+    else:
+        main()

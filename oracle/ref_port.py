@@ -327,3 +327,67 @@ def generate_dataset(nx=64, num_initial_conditions=20, steps_per_ic=30, dt=5e-3,
         states, fluxes = baseline_run(initial_condition(g, seed=ic), g, n_steps=steps_per_ic)
         st.append(states[:-1]); fl.append(fluxes); nxt.append(states[1:])
     return np.concatenate(st), np.concatenate(fl), np.concatenate(nxt)
+
+
+# --------------------------------------------------------------------------
+# the reference's comparison models
+# --------------------------------------------------------------------------
+def init_pure_gnn_weights(seed: int = 0, input_dim: int = 4, hidden: int = 64, layers: int = 3) -> dict:
+    """``torch.manual_seed(seed); PureGNN(input_dim, hidden, layers).state_dict()`` in the reference's
+    construction order (scripts/training/train_pure_gnn.py:37-58)."""
+    torch.manual_seed(seed)
+    mods = [("input_mlp.0", torch.nn.Linear(input_dim, hidden))]
+    mods += [(f"update_mlps.{l}.0", torch.nn.Linear(2 * hidden, hidden)) for l in range(layers)]
+    mods += [("output_mlp.0", torch.nn.Linear(hidden, hidden)), ("output_mlp.2", torch.nn.Linear(hidden, 3))]
+    return {f"{name}.{p}": getattr(m, p).detach().numpy().copy() for name, m in mods for p in ("weight", "bias")}
+
+
+def pure_gnn_forward(w: dict, feats, edge_index, dtype=torch.float32) -> np.ndarray:
+    """PureGNN.forward, scripts/training/train_pure_gnn.py:60-76: delta_state [N,3]."""
+    lin = lambda name, v: torch.nn.functional.linear(v, _t(w[name + ".weight"], dtype), _t(w[name + ".bias"], dtype))
+    h = torch.tanh(lin("input_mlp.0", _t(feats, dtype)))
+    ei = torch.as_tensor(np.asarray(edge_index), dtype=torch.long)
+    src, dst = ei[0], ei[1]
+    layers = sum(1 for k in w if k.startswith("update_mlps.") and k.endswith(".weight"))
+    for l in range(layers):
+        upd = torch.tanh(lin(f"update_mlps.{l}.0", torch.cat([h[src], h[dst]], dim=-1)))
+        agg = torch.zeros_like(h)
+        agg.index_add_(0, dst, upd)
+        h = h + agg
+    return lin("output_mlp.2", torch.tanh(lin("output_mlp.0", h))).numpy()
+
+
+def pure_gnn_rollout(w: dict, state0: np.ndarray, x: np.ndarray, n_steps: int, dtype=torch.float32) -> np.ndarray:
+    """The PureGNN loop of scripts/evaluation/benchmark_timing.py:129-143 for one IC: final [3,nx]."""
+    state = np.asarray(state0, dtype=np.float32)
+    ei = ring_edges(state.shape[1], 1)
+    for _ in range(n_steps):
+        feats = np.concatenate([state.T, np.asarray(x, dtype=np.float32)[:, None]], axis=1)
+        delta = pure_gnn_forward(w, feats, ei, dtype)
+        state = (state.T.astype(delta.dtype) + delta).T.astype(np.float32) if dtype == torch.float32 else (state.T + delta).T
+    return state
+
+
+def init_pinn_weights(seed: int = 0, input_dim: int = 192, hidden: int = 256, layers: int = 4) -> dict:
+    """``torch.manual_seed(seed); PINN(input_dim, hidden, layers).state_dict()`` (scripts/training/train_pinn.py:38-48)."""
+    torch.manual_seed(seed)
+    dims = [input_dim] + [hidden] * (layers - 1) + [input_dim]
+    w = {}
+    for i in range(layers):
+        m = torch.nn.Linear(dims[i], dims[i + 1])
+        w[f"net.{2 * i}.weight"] = m.weight.detach().numpy().copy()
+        w[f"net.{2 * i}.bias"] = m.bias.detach().numpy().copy()
+    return w
+
+
+def pinn_forward(w: dict, state, dtype=torch.float32) -> np.ndarray:
+    """PINN.forward, scripts/training/train_pinn.py:50-61: state + net(flatten(state))."""
+    s = _t(state, dtype)
+    flat = s.reshape(*s.shape[:-2], -1)
+    n = sum(1 for k in w if k.endswith(".weight"))
+    v = flat
+    for i in range(n):
+        v = torch.nn.functional.linear(v, _t(w[f"net.{2 * i}.weight"], dtype), _t(w[f"net.{2 * i}.bias"], dtype))
+        if i < n - 1:
+            v = torch.tanh(v)
+    return (s + v.reshape(s.shape)).numpy()

@@ -636,3 +636,50 @@ def test_training_loop_reduces_flux_loss(weights, built_lib):
         opt.step()
         losses.append(float(loss))
     assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], losses[::6]
+
+
+# ----------------------------------------------------------------------------- comparison models
+@pytest.mark.parametrize("hidden,layers", [(64, 3), (128, 4)])
+def test_pure_gnn_vs_reference(built_lib, hidden, layers):
+    """PureGNN kernel vs the reference class's frozen outputs: one forward, 10-step rollouts of 4 ICs,
+    ragged grid sizes against the port."""
+    from gnn_plasma_flux_b200 import PureGNN, build_chain_graph
+    g = load_golden("g9_comparison_models.npz")
+    w = P.init_pure_gnn_weights(7, 4, hidden, layers)
+    model = PureGNN(4, hidden, layers)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    model = model.cuda()
+    grid = P.Grid(nx=64)
+    feats, ei = build_chain_graph(g["ics"][0], grid.x, "cuda")
+    delta = model(feats, ei).cpu().numpy()
+    ref = g[f"pgnn{hidden}_delta"]
+    assert np.abs(delta - ref).max() <= 1e-5 * np.abs(ref).max()
+    x = torch.from_numpy(grid.x.astype(np.float32)).cuda()
+    out = model.rollout(torch.from_numpy(g["ics"]).cuda(), x, 10).cpu().numpy()
+    assert P.rel_err(out, g[f"pgnn{hidden}_rollout10"]).max() <= 1e-5
+    with pytest.raises(NotImplementedError):
+        model(feats, torch.randint(0, 64, (2, 128), device="cuda"))
+    for nx in (7, 40, 100, 128):                                               # ragged sizes, padding rows
+        gr = P.Grid(nx=nx)
+        ics = np.stack([P.initial_condition(gr, seed=s) for s in range(3)])
+        got = model.rollout(torch.from_numpy(ics).cuda(), torch.from_numpy(gr.x.astype(np.float32)).cuda(), 3).cpu().numpy()
+        want = np.stack([P.pure_gnn_rollout(w, ic, gr.x.astype(np.float32), 3) for ic in ics])
+        assert P.rel_err(got, want).max() <= 1e-5, nx
+
+
+def test_pinn_vs_reference(built_lib):
+    from gnn_plasma_flux_b200 import PINN
+    g = load_golden("g9_comparison_models.npz")
+    w = P.init_pinn_weights(11, 192, 256, 4)
+    model = PINN(192, 256, 4)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    model = model.cuda()
+    out = model(torch.from_numpy(g["ics"]).cuda())
+    assert out.shape == (4, 3, 64)
+    assert P.rel_err(out.cpu().numpy(), g["pinn_step"]).max() <= 1e-5
+    state = torch.from_numpy(g["ics"][:1]).cuda()
+    for _ in range(10):
+        state = model(state)
+    assert P.rel_err(state.cpu().numpy(), g["pinn_rollout10"]).max() <= 1e-4
+    single = model(torch.from_numpy(g["ics"][2]).cuda())                       # unbatched [3,nx], as the reference allows
+    assert P.rel_err(single.cpu().numpy(), g["pinn_step"][2]).max() <= 1e-5

@@ -127,3 +127,17 @@ def test_metrics_and_datagen_golden():
     np.testing.assert_array_equal(st, g7["ds_state_t"])
     np.testing.assert_array_equal(fl, g7["ds_flux_t"])
     np.testing.assert_array_equal(nxt, g7["ds_state_next"])
+
+
+def test_comparison_models_golden():
+    """the PureGNN / PINN restatements against the reference classes' frozen outputs."""
+    g = load_golden("g9_comparison_models.npz")
+    grid = P.Grid(nx=64)
+    x32 = grid.x.astype(np.float32)
+    for hidden, layers in ((64, 3), (128, 4)):
+        w = P.init_pure_gnn_weights(7, 4, hidden, layers)
+        feats = P.node_features(g["ics"][0], grid.x)
+        np.testing.assert_array_equal(P.pure_gnn_forward(w, feats, P.ring_edges(64, 1)), g[f"pgnn{hidden}_delta"])
+        np.testing.assert_array_equal(P.pure_gnn_rollout(w, g["ics"][1], x32, 10), g[f"pgnn{hidden}_rollout10"][1])
+    wp = P.init_pinn_weights(11, 192, 256, 4)
+    np.testing.assert_array_equal(P.pinn_forward(wp, g["ics"]), g["pinn_step"])
