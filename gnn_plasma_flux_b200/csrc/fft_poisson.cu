@@ -29,6 +29,9 @@ namespace {
 
 constexpr int kFftThreads = 512;       // whole-transform kernel (upper bound; it launches nx/16)
 constexpr int kFftStepThreads = 256;   // four-step kernels
+#ifndef FLUXGNN_FFT_ROW_CTAS
+#define FLUXGNN_FFT_ROW_CTAS 2         // row kernel: CTAs per SM the register budget is set for
+#endif
 #define FLUXGNN_FFT_COL_CTAS 2         // column kernels: CTAs per SM the register budget is set for (3 measured slower:
                                        // the L1 data pipe, not occupancy, limits them -- 32-byte segments cost a wavefront each)
 
@@ -571,7 +574,7 @@ __device__ __forceinline__ float2 root32_conj(int c) {
 
 // pass B: row pairs.  grid = (N1/2 + 1, B): pair q -> the rows holding k1 = q and k1 = N1 - q
 // (rows 0 and N1/2 pair with themselves and take the shared-memory spectral step).
-__global__ void __launch_bounds__(kFftStepThreads, 2) poisson_fft_rows_kernel(float2* __restrict__ Y, int bits1,
+__global__ void __launch_bounds__(kFftStepThreads, FLUXGNN_FFT_ROW_CTAS) poisson_fft_rows_kernel(float2* __restrict__ Y, int bits1,
                                                                               float scale) {
     extern __shared__ float2 sfft[];
     const int N1 = 1 << bits1, M = N1 << kRowBits;
