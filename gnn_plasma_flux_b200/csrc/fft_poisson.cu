@@ -421,7 +421,7 @@ __device__ __forceinline__ int rpad(int i) { return i + (i >> 4); }             
 // ---- kernel A / C: column passes -------------------------------------------------------------
 // One pass over blocks of 2^LB rows (j1 units) of a tile of N1 x T elements held at s[cpad(j1*T + t)].
 // kInv = false: DIF, forward, natural j1 in -> position order out;  kInv = true: the transposed DIT pass.
-template <int BITS1, int TILE_BITS, int LB, bool kInv>
+template <int BITS1, int TILE_BITS, int LB, bool kInv, int THREADS>
 __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s,
                                             int j2_0) {
     constexpr int RB = LB >= 4 ? 4 : LB, R = 1 << RB, SUBB = LB - RB, SUB = 1 << SUBB;
@@ -430,9 +430,9 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
     constexpr bool kGlobalIn = kInv ? (SUBB == 0) : (LB == BITS1);
     constexpr bool kGlobalOut = kInv ? (LB == BITS1) : (SUBB == 0);
     constexpr int ITEMS = (1 << TILE_BITS) >> RB;
-    static_assert(ITEMS % kFftStepThreads == 0, "tile too small for the CTA");
-    constexpr int ITERS = ITEMS / kFftStepThreads;
-    constexpr bool kSharedTw = (SUB * T <= kFftStepThreads);   // (t, base) do not depend on the iteration
+    static_assert(ITEMS % THREADS == 0, "tile too small for the CTA");
+    constexpr int ITERS = ITEMS / THREADS;
+    constexpr bool kSharedTw = (SUB * T <= THREADS);   // (t, base) do not depend on the iteration
     // forward: density in (streamed), spectrum out (kept);  inverse: spectrum in (consumed), field out
     constexpr Hint kHin = Hint::kFirst, kHout = kInv ? Hint::kNone : Hint::kLast;
     const uint64_t pol_in = kGlobalIn ? make_policy<kHin>() : 0, pol_out = kGlobalOut ? make_policy<kHout>() : 0;
@@ -444,7 +444,7 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
     }
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-        const int w = threadIdx.x + it * kFftStepThreads;
+        const int w = threadIdx.x + it * THREADS;
         const int t = w & (T - 1), q = w >> TB, base = q & (SUB - 1), blk = q >> SUBB;
         const int j1_0 = (blk << LB) + base;
         float2 v[R];
@@ -480,46 +480,48 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
     if constexpr (!kGlobalOut) __syncthreads();
 }
 
-template <int BITS1, int TILE_BITS, int LB>
+template <int BITS1, int TILE_BITS, int LB, int THREADS>
 __device__ __forceinline__ void columns_forward(const float2* gin, float2* gout, float2* s, int j2_0) {
-    column_pass<BITS1, TILE_BITS, LB, false>(gin, gout, s, j2_0);
+    column_pass<BITS1, TILE_BITS, LB, false, THREADS>(gin, gout, s, j2_0);
     constexpr int SUBB = LB - (LB >= 4 ? 4 : LB);
-    if constexpr (SUBB > 0) columns_forward<BITS1, TILE_BITS, SUBB>(gin, gout, s, j2_0);
+    if constexpr (SUBB > 0) columns_forward<BITS1, TILE_BITS, SUBB, THREADS>(gin, gout, s, j2_0);
 }
-template <int BITS1, int TILE_BITS, int LB>
+template <int BITS1, int TILE_BITS, int LB, int THREADS>
 __device__ __forceinline__ void columns_inverse(const float2* gin, float2* gout, float2* s, int j2_0) {
-    column_pass<BITS1, TILE_BITS, LB, true>(gin, gout, s, j2_0);
-    if constexpr (LB < BITS1) columns_inverse<BITS1, TILE_BITS, LB + 4>(gin, gout, s, j2_0);
+    column_pass<BITS1, TILE_BITS, LB, true, THREADS>(gin, gout, s, j2_0);
+    if constexpr (LB < BITS1) columns_inverse<BITS1, TILE_BITS, LB + 4, THREADS>(gin, gout, s, j2_0);
 }
 __host__ __device__ constexpr int first_inverse_lb(int bits1) { return bits1 < 4 ? bits1 : ((bits1 & 3) ? (bits1 & 3) : 4); }
 __host__ __device__ constexpr int column_tile_bits(int bits1) {
     return bits1 + 2 > FLUXGNN_FFT_STEP_COL_BITS ? bits1 + 2 : FLUXGNN_FFT_STEP_COL_BITS;    // at least 4 columns per tile
 }
+// a 2^14 tile (one CTA per SM by shared memory) runs 512 threads, a 2^13 tile 256 at FLUXGNN_FFT_COL_CTAS per SM
+__host__ __device__ constexpr int column_threads(int bits1) { return column_tile_bits(bits1) <= 13 ? kFftStepThreads : 512; }
 
 }  // namespace
 
 // pass A: forward column stages.  grid = (N2 / T, B)
 template <int BITS1>
-__global__ void __launch_bounds__(kFftStepThreads, column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
+__global__ void __launch_bounds__(column_threads(BITS1), column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
 poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride, float2* __restrict__ Y) {
     extern __shared__ float2 sfft[];
     constexpr int TILE_BITS = column_tile_bits(BITS1);
     const int j2_0 = blockIdx.x << (TILE_BITS - BITS1);
     const float2* src = reinterpret_cast<const float2*>(n + (size_t)blockIdx.y * n_stride);
     float2* dst = Y + ((size_t)blockIdx.y << (BITS1 + kRowBits));
-    columns_forward<BITS1, TILE_BITS, BITS1>(src, dst, sfft, j2_0);
+    columns_forward<BITS1, TILE_BITS, BITS1, column_threads(BITS1)>(src, dst, sfft, j2_0);
 }
 
 // pass C: inverse column stages, (E_2j, E_2j+1) out.  grid = (N2 / T, B)
 template <int BITS1>
-__global__ void __launch_bounds__(kFftStepThreads, column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
+__global__ void __launch_bounds__(column_threads(BITS1), column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
 poisson_fft_cols_inv_kernel(const float2* __restrict__ Y, float* __restrict__ E, long long e_stride) {
     extern __shared__ float2 sfft[];
     constexpr int TILE_BITS = column_tile_bits(BITS1);
     const int j2_0 = blockIdx.x << (TILE_BITS - BITS1);
     const float2* src = Y + ((size_t)blockIdx.y << (BITS1 + kRowBits));
     float2* dst = reinterpret_cast<float2*>(E + (size_t)blockIdx.y * e_stride);
-    columns_inverse<BITS1, TILE_BITS, first_inverse_lb(BITS1)>(src, dst, sfft, j2_0);
+    columns_inverse<BITS1, TILE_BITS, first_inverse_lb(BITS1), column_threads(BITS1)>(src, dst, sfft, j2_0);
 }
 
 namespace {
@@ -749,7 +751,7 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
 #define FLUXGNN_FFT_COLS(BITS1, WHICH, ...)                                                                          \
     case BITS1:                                                                                                     \
         FLUXGNN_CUDA_OK(cudaFuncSetAttribute(WHICH<BITS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        WHICH<BITS1><<<gcol, kFftStepThreads, smem, stream>>>(__VA_ARGS__);                                          \
+        WHICH<BITS1><<<gcol, column_threads(BITS1), smem, stream>>>(__VA_ARGS__);                                          \
         break;
 #define FLUXGNN_FFT_COLS_ALL(WHICH, ...)                                                       \
     switch (bits1) {                                                                          \

@@ -355,6 +355,32 @@ def test_full_size_c2_properties(model, weights):
     assert np.abs(mT - m0).max() <= 50 * nx * np.finfo(np.float32).eps
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_full_size_c3_per_gpu_properties(model, weights, precision):
+    """BASELINE.json configs[2] at its 8-GPU per-GPU size: 8192 ICs x 1024 cells, radius 2 (window tiles +
+    FFT field solve).  Three steps: a sample of ICs against the batched oracle, IC-permutation
+    equivariance (bit-exact), mass conservation to round-off on every IC, and the fp32-accurate tensor
+    mode under the same gates."""
+    nx, B, dt, r = 1024, 8192, 3e-4, 2
+    grid = P.Grid(nx=nx, dt=dt)
+    base = np.stack([P.stable_initial_condition(grid, s) for s in range(32)])
+    ics = np.tile(base, (B // 32, 1, 1))
+    ics += (np.random.RandomState(0).randn(B, 1, 1) * 1e-3).astype(np.float32) * np.array([0, 1, 0], np.float32)[None, :, None]
+    sol = make_solver(model, nx, dt, graph_radius=r, precision=precision)
+    dev = torch.from_numpy(ics).cuda()
+    out, _ = sol.rollout(dev, 3)
+    assert torch.isfinite(out).all()
+    pick = np.array([0, 1, 33, 4097, 8191])
+    ref = batched.hybrid_run(weights, torch.from_numpy(ics[pick]), grid.x, grid.k, grid.dt, grid.dx, 3, radius=r).numpy()
+    assert P.rel_err(out[pick].cpu().numpy(), ref).max() <= 3 * STEP_TOL
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(2)).cuda()
+    out_p, _ = sol.rollout(dev[perm].contiguous(), 3)
+    assert torch.equal(out_p, out[perm])
+    m0 = ics[:, 0].astype(np.float64).sum(-1)
+    mT = out[:, 0].double().sum(-1).cpu().numpy()
+    assert np.abs(mT - m0).max() <= 3 * nx * np.finfo(np.float32).eps
+
+
 # ----------------------------------------------------------------------------- tensor-core path
 TF32_STEP_TOL = 1e-5          # plain TF32: state-level tolerance per step (flux error ~1e-3 enters as c*dF)
 TF32_FLUX_TOL = 2e-2          # plain TF32: relative error of the GNN flux itself
