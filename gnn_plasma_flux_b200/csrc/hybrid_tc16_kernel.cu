@@ -21,10 +21,19 @@
 //   "fp16"  : D = w0 h0 (one product, 2x the TF32 rate; same 11-bit operands as plain tf32)
 //   "bf16"  : one product with bfloat16 operands (8 significant bits; loosest tolerance, widest range)
 //
-// Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quadrant = warp % 4, row chunks warp / 4
-// and warp / 4 + 4 of 32 rows each), warp 16 weight producer, warp 17 TMEM allocator + UMMA issuer.
+// Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quadrant = warp % 4, two 32-row chunks each),
+// warp 16 weight producer, warp 17 TMEM allocator + UMMA issuer.
+//
+// kSplit (whole-IC tiles, nx <= 128: the two 128-row halves of a tile hold different ICs and never
+// exchange data): the halves run as two independent groups of 8 epilogue warps, each with its own
+// barriers, and the issuer alternates between them with N = 128 instructions -- while one half is in
+// its epilogue (or in the finite-volume / field-solve tail) the tensor pipe works on the other half.
+// An N = 128 instruction costs 136 clk against 172 for N = 256, i.e. 1.6x more tensor time per row,
+// but that time is now hidden behind the epilogues instead of added to them.  Window tiles (nx > 128)
+// keep the single 256-row group.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
@@ -55,7 +64,7 @@ struct __align__(1024) Smem {
     int rowCell[kRows];
     short prevRow[kRows], nextRow[kRows];
     uint64_t full[kStages], empty[kStages];
-    uint64_t act_ready, acc_ready;
+    uint64_t act_ready[2], acc_ready[2];          // per group (kSplit: the two 128-row halves)
     uint32_t tmem_base;
 #ifdef FLUXGNN_TC_TIMING
     long long timing[16];
@@ -139,9 +148,12 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[32], int lane) {
 
 }  // namespace
 
-// PARTS: 2 = x3 split (hi + lo parts), 1 = one product.
-template <int R, int PARTS, bool kBf16>
+// PARTS: 2 = x3 split (hi + lo parts), 1 = one product.  kSplit: two independent 128-row groups (see above).
+template <int R, int PARTS, bool kBf16, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridArgs a) {
+    constexpr int kGroups = kSplit ? 2 : 1;
+    constexpr int kGroupRows = kRows / kGroups;              // rows of a group = UMMA N
+    constexpr int kGroupThreads = kEpiThreads / kGroups;
     // 1024-byte aligned as declared (the 128-byte swizzle needs it; checked below).  Indexing the array
     // itself -- not a re-aligned generic pointer -- keeps every access in the shared address space (LDS/STS).
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -159,8 +171,10 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
             mbar_init(&S.full[s], 1);
             mbar_init(&S.empty[s], 1);
         }
-        mbar_init(&S.act_ready, kEpiThreads);
-        mbar_init(&S.acc_ready, 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&S.act_ready[g], kGroupThreads);
+            mbar_init(&S.acc_ready[g], 1);
+        }
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&S.tmem_base, kTmemCols);
@@ -181,7 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
             const unsigned char* stream = reinterpret_cast<const unsigned char*>(a.packed + SmallParams::count);
             Ring r;
             for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
-                for (int layer = 0; layer < layers; ++layer) {
+                for (int lg = 0; lg < layers * kGroups; ++lg) {      // every group consumes the whole layer
+                    const int layer = lg / kGroups;
                     for (int u = 0; u < kTc16UnitsPerLayer; ++u) {
                         if (PARTS == 1 && (u & 1)) continue;          // one product: no lo units
                         mbar_wait(&S.empty[r.stage], r.phase ^ 1);
@@ -196,18 +211,21 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
     } else if (warp == kMmaWarp) {
         // ---------------- UMMA issuer (one thread) ---------------------------------------
         if (lane == 0) {
-            const uint32_t idesc = idesc_f16(128, kRows, kBf16 ? 1 : 0);
-            const uint32_t bhi = smem_u32(S.act[0][0]), blo = smem_u32(S.act[1][0]);
+            const uint32_t idesc = idesc_f16(128, kGroupRows, kBf16 ? 1 : 0);
             Ring r;
             uint32_t act_phase = 0;
             for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
-                for (int layer = 0; layer < layers; ++layer) {
-                    mbar_wait(&S.act_ready, act_phase);
-                    act_phase ^= 1;
+                for (int lg = 0; lg < layers * kGroups; ++lg) {
+                    const int grp = lg % kGroups;                 // kSplit: the halves alternate
+                    // the group's rows of the B operand and its columns of the accumulators
+                    const uint32_t bhi = smem_u32(S.act[0][0]) + grp * kGroupRows * 128;
+                    const uint32_t blo = smem_u32(S.act[1][0]) + grp * kGroupRows * 128;
+                    mbar_wait(&S.act_ready[grp], act_phase);
+                    if (grp == kGroups - 1) act_phase ^= 1;
                     tc_fence_after();
                     for (int kb = 0; kb < 2; ++kb) {
                         for (int blk = 0; blk < 2; ++blk) {
-                            const uint32_t d = tmem + (blk == 0 ? kColZ : kColY);
+                            const uint32_t d = tmem + (blk == 0 ? kColZ : kColY) + grp * kGroupRows;
                             // hi weights x (hi [+ lo] activations)
                             mbar_wait(&S.full[r.stage], r.phase);
                             tc_fence_after();
@@ -235,13 +253,21 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                             }
                         }
                     }
-                    umma_commit(&S.acc_ready);
+                    umma_commit(&S.acc_ready[grp]);
                 }
             }
         }
     } else {
         // ---------------- epilogue / compute warps ---------------------------------------
-        const int q = warp & 3, cw = warp >> 2;               // TMEM lane quadrant; row chunks cw and cw + 4
+        const int q = warp & 3;                               // TMEM lane quadrant
+        const int grp = kSplit ? (warp >> 3) : 0;             // group = 128-row half (kSplit) or the whole tile
+        const int lt = tid - grp * kGroupThreads;             // thread index inside the group
+        const int row0 = grp * kGroupRows;
+        const int bar = 1 + grp;                              // named barrier of the group
+        // the warp's two 32-row chunks start at row0 + 32 * (cw + kChunkStep * half)
+        const int cw = (warp >> 2) & (kSplit ? 1 : 3);
+        constexpr int kChunkStep = kSplit ? 2 : 4;
+        const int myrow = (lt < kGroupRows) ? row0 + lt : -1; // the row this thread looks after in per-row phases
         const int n = 32 * q + lane;                          // this thread's feature = TMEM lane
         const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
         const float inv_deg = kUnscale / (float)(2 * R);
@@ -269,8 +295,8 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             TC_TICK(0);
             // ---- row bookkeeping + state load (as in the FP32-pipe kernel) ----------------
-            if (tid < kRows) {
-                const int j = tid;
+            if (myrow >= 0) {
+                const int j = myrow;
                 int ic, cell, prev = (j - 1) & (kRows - 1), next = (j + 1) & (kRows - 1);
                 bool live, owned;
                 int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
@@ -312,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                 }
                 S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
             }
-            named_sync(1, kEpiThreads);
+            named_sync(bar, kGroupThreads);
             TC_TICK(1);
 
             for (int step = 0; step < a.steps; ++step) {
@@ -325,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     const float b = S.small[SmallParams::b_in + n];
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
-                        const int i0 = 32 * (cw + 4 * half);
+                        const int i0 = row0 + 32 * (cw + kChunkStep * half);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 vn = *reinterpret_cast<const float4*>(&S.sN[i0 + j]);
@@ -341,11 +367,11 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                 }
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&S.act_ready);
+                mbar_arrive(&S.act_ready[grp]);
                 TC_TICK(2);
 
                 for (int layer = 0; layer < layers; ++layer) {
-                    mbar_wait(&S.acc_ready, acc_phase);
+                    mbar_wait(&S.acc_ready[grp], acc_phase);
                     acc_phase ^= 1;
                     tc_fence_after();
                     TC_TICK(3);
@@ -354,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     const float w_out = S.small[SmallParams::w_e2 + n];
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
-                        const int i0 = 32 * (cw + 4 * half);
+                        const int i0 = row0 + 32 * (cw + kChunkStep * half);
                         const int seg0 = (i0 / seg) * seg;
                         const int cl = (i0 == seg0) ? i0 - 4 + seg : i0 - 4;
                         const int cr = (i0 + 32 == seg0 + seg) ? i0 + 32 - seg : i0 + 32;
@@ -406,17 +432,17 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     if (!is_edge) {
                         tc_fence_before();
                         fence_proxy_async();
-                        mbar_arrive(&S.act_ready);
+                        mbar_arrive(&S.act_ready[grp]);
                     }
                     TC_TICK(is_edge ? 5 : 4);
                 }
-                named_sync(1, kEpiThreads);
+                named_sync(bar, kGroupThreads);
                 TC_TICK(6);
 
                 // ---- per row: face flux (src/hybrid_solver.py:45-48) ----------------------------
                 float n_new = 0.f, u_new = 0.f;
-                if (tid < kRows) {
-                    const int j = tid, jn = S.nextRow[j];
+                if (myrow >= 0) {
+                    const int j = myrow, jn = S.nextRow[j];
                     const float b2 = S.small[SmallParams::b_e2];
                     const float fwd = ((S.edgeP[0][0][j] + S.edgeP[1][0][j]) + (S.edgeP[2][0][j] + S.edgeP[3][0][j])) + b2;
                     const float bwd = ((S.edgeP[0][1][jn] + S.edgeP[1][1][jn]) + (S.edgeP[2][1][jn] + S.edgeP[3][1][jn])) + b2;
@@ -431,12 +457,12 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     S.sF[j] = face;
                 }
                 if (!a.do_update) continue;
-                named_sync(1, kEpiThreads);
+                named_sync(bar, kGroupThreads);
                 TC_TICK(7);
 
                 // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
-                if (tid < kRows) {
-                    const int j = tid, p = S.prevRow[j];
+                if (myrow >= 0) {
+                    const int j = myrow, p = S.prevRow[j];
                     const float u = S.sU[j], up = S.sU[p];
                     n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
                     const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
@@ -445,24 +471,24 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, S.sE[j]));
                 }
                 if (!a.whole_ic) {
-                    if (tid < kRows && S.rowIC[tid] >= 0) {
-                        float* so = a.state_out + (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+                    if (myrow >= 0 && S.rowIC[myrow] >= 0) {
+                        float* so = a.state_out + (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
                         so[0] = n_new;
                         so[nx] = u_new;
                     }
                     continue;
                 }
-                named_sync(1, kEpiThreads);
-                if (tid < kRows) {
-                    S.sN[tid] = n_new;
-                    S.sU[tid] = u_new;
-                    S.sRho[tid] = __fsub_rn(n_new, 1.0f);
+                named_sync(bar, kGroupThreads);
+                if (myrow >= 0) {
+                    S.sN[myrow] = n_new;
+                    S.sU[myrow] = u_new;
+                    S.sRho[myrow] = __fsub_rn(n_new, 1.0f);
                 }
-                named_sync(1, kEpiThreads);
+                named_sync(bar, kGroupThreads);
                 TC_TICK(8);
                 // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
                 {
-                    const int row = tid >> 1, part = tid & 1;
+                    const int row = row0 + (lt >> 1), part = lt & 1;
                     const int cell = S.rowCell[row], base = row - cell;
                     double e = 0.0;
                     for (int i = part; i < nx; i += 2) {
@@ -473,25 +499,25 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     e += __shfl_xor_sync(0xffffffffu, e, 1);
                     if (part == 0) S.sE[row] = (float)e;
                 }
-                named_sync(1, kEpiThreads);
+                named_sync(bar, kGroupThreads);
                 TC_TICK(9);
-                if (tid < kRows && S.rowIC[tid] >= 0) {
-                    const size_t off = (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
+                if (myrow >= 0 && S.rowIC[myrow] >= 0) {
+                    const size_t off = (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
                     if (step == a.steps - 1) {
-                        a.state_out[off] = S.sN[tid];
-                        a.state_out[off + nx] = S.sU[tid];
-                        a.state_out[off + 2 * (size_t)nx] = S.sE[tid];
+                        a.state_out[off] = S.sN[myrow];
+                        a.state_out[off + nx] = S.sU[myrow];
+                        a.state_out[off + 2 * (size_t)nx] = S.sE[myrow];
                     }
                     if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
                         float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
-                        tr[0] = S.sN[tid];
-                        tr[nx] = S.sU[tid];
-                        tr[2 * (size_t)nx] = S.sE[tid];
+                        tr[0] = S.sN[myrow];
+                        tr[nx] = S.sU[myrow];
+                        tr[2 * (size_t)nx] = S.sE[myrow];
                     }
                 }
                 TC_TICK(10);
             }   // steps
-            named_sync(1, kEpiThreads);
+            named_sync(bar, kGroupThreads);
         }       // tiles
     }
 
@@ -514,20 +540,30 @@ extern "C" int fluxgnn_debug_tc_timing(long long* out16, int reset) {
 }
 #endif
 
-template <int R, int PARTS, bool kBf16>
+template <int R, int PARTS, bool kBf16, bool kSplit>
 static cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream) {
-    const int smem = (int)sizeof(Smem) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(hybrid_tc16_kernel<R, PARTS, kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)sizeof(Smem);
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tc16_kernel<R, PARTS, kBf16, kSplit>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    hybrid_tc16_kernel<R, PARTS, kBf16><<<grid, kThreads, smem, stream>>>(a);
+    hybrid_tc16_kernel<R, PARTS, kBf16, kSplit><<<grid, kThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
+template <int R, bool kSplit>
+static cudaError_t launch_mode(const HybridArgs& a, int grid, cudaStream_t stream) {
+    if (a.tc_format == 1) return launch_one<R, 1, true, kSplit>(a, grid, stream);            // bf16
+    if (a.tc_parts == 2) return launch_one<R, 2, false, kSplit>(a, grid, stream);             // fp16x3
+    return launch_one<R, 1, false, kSplit>(a, grid, stream);                                  // fp16
+}
+
+// whole-IC tiles (nx in {32, 64, 128}): the two halves of a tile are independent -> ping-pong groups
+// (FLUXGNN_TC16_NO_SPLIT=1: test hook that keeps the single 256-row group)
 template <int R>
 static cudaError_t launch_radius(const HybridArgs& a, int grid, cudaStream_t stream) {
-    if (a.tc_format == 1) return launch_one<R, 1, true>(a, grid, stream);            // bf16
-    if (a.tc_parts == 2) return launch_one<R, 2, false>(a, grid, stream);             // fp16x3
-    return launch_one<R, 1, false>(a, grid, stream);                                  // fp16
+    const char* nosplit = getenv("FLUXGNN_TC16_NO_SPLIT");
+    const bool split = a.whole_ic && !(nosplit != nullptr && nosplit[0] == '1');
+    return split ? launch_mode<R, true>(a, grid, stream) : launch_mode<R, false>(a, grid, stream);
 }
 
 cudaError_t launch_hybrid_tc16_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream) {
