@@ -112,6 +112,19 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 
 // store the low 16 bits of a 32-bit register (no repacking instruction)
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(addr), "r"(v) : "memory");
 }
@@ -209,52 +222,65 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
             }
         }
     } else if (warp == kMmaWarp) {
-        // ---------------- UMMA issuer (one thread) ---------------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = idesc_f16(128, kGroupRows, kBf16 ? 1 : 0);
-            Ring r;
-            uint32_t act_phase = 0;
-            for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
-                for (int lg = 0; lg < layers * kGroups; ++lg) {
-                    const int grp = lg % kGroups;                 // kSplit: the halves alternate
-                    // the group's rows of the B operand and its columns of the accumulators
-                    const uint32_t bhi = smem_u32(S.act[0][0]) + grp * kGroupRows * 128;
-                    const uint32_t blo = smem_u32(S.act[1][0]) + grp * kGroupRows * 128;
-                    mbar_wait(&S.act_ready[grp], act_phase);
-                    if (grp == kGroups - 1) act_phase ^= 1;
-                    tc_fence_after();
-                    for (int kb = 0; kb < 2; ++kb) {
-                        for (int blk = 0; blk < 2; ++blk) {
-                            const uint32_t d = tmem + (blk == 0 ? kColZ : kColY) + grp * kGroupRows;
-                            // hi weights x (hi [+ lo] activations)
-                            mbar_wait(&S.full[r.stage], r.phase);
-                            tc_fence_after();
-                            uint32_t wbase = smem_u32(S.Ws[r.stage]);
+        // ---------------- UMMA issuer ------------------------------------------------------
+        // The WHOLE warp walks the loop in uniform control flow and one elected lane issues.  With a
+        // `lane == 0` branch around everything the compiler cannot prove the descriptors warp-uniform
+        // and wraps every UTCHMMA in R2UR moves and an ELECT / BRA.U.ANY serialisation loop: ~15
+        // dependent instructions of a lone warp per UMMA (~136 clk), which -- not the tensor pipe --
+        // was the cost of an N <= 128 instruction measured by scripts/probes/umma_probe.cu.
+        const uint32_t idesc = idesc_f16(128, kGroupRows, kBf16 ? 1 : 0);
+        const bool leader = elect_one();
+        const uint64_t ws_desc0 = umma_desc_sw128(smem_u32(S.Ws[0]));
+        const uint64_t hi_desc0 = umma_desc_sw128(smem_u32(S.act[0][0]));
+        const uint64_t lo_desc0 = umma_desc_sw128(smem_u32(S.act[1][0]));
+        constexpr uint64_t kStageStep = kTc16UnitBytes >> 4;          // descriptor address field counts 16-byte units
+        constexpr uint64_t kKbStep = kActBlockBytes >> 4;
+        constexpr uint64_t kGroupStep = (uint64_t)(kGroupRows * 128) >> 4;
+        Ring r;
+        uint32_t act_phase = 0;
+        for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
+            for (int lg = 0; lg < layers * kGroups; ++lg) {
+                const int grp = lg % kGroups;                         // kSplit: the halves alternate
+                // the group's rows of the B operand and its columns of the accumulators
+                const uint64_t bhi = hi_desc0 + grp * kGroupStep, blo = lo_desc0 + grp * kGroupStep;
+                mbar_wait(&S.act_ready[grp], act_phase);
+                if (grp == kGroups - 1) act_phase ^= 1;
+                tc_fence_after();
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = umma_desc_sw128(wbase + ks * 32);
-                                umma_f16(d, ad, umma_desc_sw128(bhi + kb * kActBlockBytes + ks * 32), idesc, (kb | ks) != 0);
-                                if (PARTS == 2)
-                                    umma_f16(d, ad, umma_desc_sw128(blo + kb * kActBlockBytes + ks * 32), idesc, 1);
+                for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const uint32_t d = tmem + (blk == 0 ? kColZ : kColY) + grp * kGroupRows;
+                        // hi weights x (hi [+ lo] activations)
+                        mbar_wait(&S.full[r.stage], r.phase);
+                        tc_fence_after();
+                        uint64_t wd = ws_desc0 + r.stage * kStageStep;
+                        if (leader) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {          // 32 bytes of K per instruction = 2 address units
+                                umma_f16(d, wd + 2 * ks, bhi + kb * kKbStep + 2 * ks, idesc, (kb | ks) != 0);
+                                if (PARTS == 2) umma_f16(d, wd + 2 * ks, blo + kb * kKbStep + 2 * ks, idesc, 1);
                             }
                             umma_commit(&S.empty[r.stage]);
-                            r.advance();
-                            if (PARTS == 2) {
-                                // lo weights x hi activations
-                                mbar_wait(&S.full[r.stage], r.phase);
-                                tc_fence_after();
-                                wbase = smem_u32(S.Ws[r.stage]);
+                        }
+                        r.advance();
+                        if (PARTS == 2) {
+                            // lo weights x hi activations
+                            mbar_wait(&S.full[r.stage], r.phase);
+                            tc_fence_after();
+                            wd = ws_desc0 + r.stage * kStageStep;
+                            if (leader) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)
-                                    umma_f16(d, umma_desc_sw128(wbase + ks * 32),
-                                             umma_desc_sw128(bhi + kb * kActBlockBytes + ks * 32), idesc, 1);
+                                    umma_f16(d, wd + 2 * ks, bhi + kb * kKbStep + 2 * ks, idesc, 1);
                                 umma_commit(&S.empty[r.stage]);
-                                r.advance();
                             }
+                            r.advance();
                         }
                     }
-                    umma_commit(&S.acc_ready[grp]);
                 }
+                if (leader) umma_commit(&S.acc_ready[grp]);
+                __syncwarp();
             }
         }
     } else {

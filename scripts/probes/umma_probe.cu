@@ -11,9 +11,16 @@ __device__ __forceinline__ void umma_f16(uint32_t d, uint64_t a, uint64_t b, uin
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 // kind::f16 instruction descriptor: fp16 A/B (format 0), fp32 accumulate
+// descriptor with a chosen layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 0 = none (LBO/SBO for 8x16B core matrices)
+__device__ __forceinline__ uint64_t desc_layout(uint32_t addr, int layout) {
+    if (layout == 2) return umma_desc_sw128(addr);
+    const uint64_t sbo = layout == 4 ? 512 : layout == 6 ? 256 : 128;     // 8-row group pitch
+    const uint64_t lbo = layout == 0 ? 4096 : 16;                          // none: next K core matrix far away
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
-struct Params { int kind16, N, nacc, per_commit, same_a, reps; };
+struct Params { int kind16, N, nacc, per_commit, same_a, reps, M = 128, layout = 2, kstep = 32; };
 
 __global__ void __launch_bounds__(128, 1) probe(Params p, long long* out) {
     extern __shared__ __align__(1024) unsigned char raw[];
@@ -28,7 +35,7 @@ __global__ void __launch_bounds__(128, 1) probe(Params p, long long* out) {
     if (threadIdx.x == 0) {
         const uint32_t tm = tmem_base;
         const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm + 64 * 1024);     // A: 4 units of 16 KiB; B: up to 256 rows x 128 B x 2
-        const uint32_t idesc = p.kind16 ? idesc_f16(128, p.N) : umma_idesc_tf32(128, p.N);
+        const uint32_t idesc = p.kind16 ? idesc_f16(p.M, p.N) : umma_idesc_tf32(p.M, p.N);
         uint32_t phase = 0;
         long long t0 = clock64();
         int n = 0;
@@ -37,7 +44,7 @@ __global__ void __launch_bounds__(128, 1) probe(Params p, long long* out) {
                 const uint32_t d = tm + (uint32_t)((u % p.nacc) * p.N);
                 const uint32_t wa = a0 + (p.same_a ? 0 : (u & 3) * 16384);
                 for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = umma_desc_sw128(wa + ks * 32), bd = umma_desc_sw128(b0 + ks * 32);
+                    const uint64_t ad = desc_layout(wa + ks * p.kstep, p.layout), bd = desc_layout(b0 + ks * p.kstep, p.layout);
                     if (p.kind16) umma_f16(d, ad, bd, idesc, 1); else umma_tf32(d, ad, bd, idesc, 1);
                     ++n;
                 }
@@ -73,9 +80,20 @@ int main() {
         {"f16 N=128, 2 accumulators, commit per unit", {1, 128, 2, 1, 0, 8}},
         {"f16 N=256, 2 accumulators", {1, 256, 2, 0, 0, 8}},
         {"f16 N=64, 2 accumulators", {1, 64, 2, 0, 0, 8}},
+        {"f16 N=32, 2 accumulators", {1, 32, 2, 0, 0, 8}},
+        {"f16 N=160, 2 accumulators", {1, 160, 2, 0, 0, 8}},
+        {"f16 N=192, 2 accumulators", {1, 192, 2, 0, 0, 8}},
+        {"f16 N=224, 2 accumulators", {1, 224, 2, 0, 0, 8}},
+        {"f16 M=64 N=128, 2 accumulators", {1, 128, 2, 0, 0, 8, 64}},
+        {"f16 M=64 N=256, 2 accumulators", {1, 256, 2, 0, 0, 8, 64}},
+        {"f16 N=128, SWIZZLE_64B", {1, 128, 2, 0, 0, 8, 128, 4}},
+        {"f16 N=128, SWIZZLE_32B", {1, 128, 2, 0, 0, 8, 128, 6}},
+        {"f16 N=128, no swizzle", {1, 128, 2, 0, 0, 8, 128, 0, 256}},
+        {"f16 N=256, SWIZZLE_32B", {1, 256, 2, 0, 0, 8, 128, 6}},
+        {"f16 N=256, no swizzle", {1, 256, 2, 0, 0, 8, 128, 0, 256}},
     };
     for (auto& c : cases) {
-        for (int grid : {1, 148}) {
+        for (int grid : {148}) {
             cudaMemset(out, 0, 16);
             probe<<<grid, 128, 200 * 1024>>>(c.p, out);
             cudaError_t e = cudaDeviceSynchronize();
