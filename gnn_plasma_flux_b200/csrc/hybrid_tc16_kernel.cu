@@ -112,6 +112,7 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 
 // store the low 16 bits of a 32-bit register (no repacking instruction)
+// store the low 16 bits of a 32-bit register (no repacking instruction)
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         // dependent instructions of a lone warp per UMMA (~136 clk), which -- not the tensor pipe --
         // was the cost of an N <= 128 instruction measured by scripts/probes/umma_probe.cu.
         const uint32_t idesc = idesc_f16(128, kGroupRows, kBf16 ? 1 : 0);
-        const bool leader = elect_one();
+        const bool leader = elect_one_lane();
         const uint64_t ws_desc0 = umma_desc_sw128(smem_u32(S.Ws[0]));
         const uint64_t hi_desc0 = umma_desc_sw128(smem_u32(S.act[0][0]));
         const uint64_t lo_desc0 = umma_desc_sw128(smem_u32(S.act[1][0]));

@@ -64,8 +64,10 @@ struct Ring {
 
 template <int R>
 __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // declared 1024-byte aligned (128-byte swizzle); indexing the array itself keeps accesses in the shared space
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int nx = a.nx;
@@ -111,50 +113,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
             }
         }
     } else if (warp == kMmaWarp) {
-        // ---------------- UMMA issuer (one thread) ---------------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(128, 128);
-            const uint32_t bhi = smem_u32(S.Bhi), blo = smem_u32(S.Blo);
-            Ring r;
-            uint32_t act_phase = 0;
-            for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
-                for (int layer = 0; layer < layers; ++layer) {
-                    mbar_wait(&S.act_ready, act_phase);
-                    act_phase ^= 1;
-                    tc_fence_after();
-                    for (int kb = 0; kb < 4; ++kb) {
-                        for (int blk = 0; blk < 2; ++blk) {
-                            const uint32_t d = tmem + (blk == 0 ? kColZ : kColY);
-                            // hi weights x (hi [+ lo] activations)
-                            mbar_wait(&S.full[r.stage], r.phase);
-                            tc_fence_after();
-                            uint32_t wbase = smem_u32(S.Ws[r.stage]);
+        // ---------------- UMMA issuer ------------------------------------------------------
+        // The whole warp walks the loop in uniform control flow, one elected lane issues (see
+        // hybrid_tc16_kernel.cu: with a `lane == 0` branch around the loop every UTCHMMA was wrapped in
+        // R2UR moves and an ELECT serialisation loop, ~136 clk of a lone warp per instruction).
+        const uint32_t idesc = umma_idesc_tf32(128, 128);
+        const bool leader = elect_one_lane();
+        const uint64_t ws_desc0 = umma_desc_sw128(smem_u32(S.Ws[0]));
+        const uint64_t bhi = umma_desc_sw128(smem_u32(S.Bhi)), blo = umma_desc_sw128(smem_u32(S.Blo));
+        constexpr uint64_t kStageStep = (uint64_t)(kTcUnitFloats * 4) >> 4;     // address field counts 16-byte units
+        constexpr uint64_t kKbStep = (uint64_t)(kTileRows * 128) >> 4;
+        Ring r;
+        uint32_t act_phase = 0;
+        for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
+            for (int layer = 0; layer < layers; ++layer) {
+                mbar_wait(&S.act_ready, act_phase);
+                act_phase ^= 1;
+                tc_fence_after();
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = umma_desc_sw128(wbase + ks * 32);
-                                umma_tf32(d, ad, umma_desc_sw128(bhi + kb * (kTileRows * 128) + ks * 32), idesc,
-                                          (kb | ks) != 0);
-                                if (parts == 2)
-                                    umma_tf32(d, ad, umma_desc_sw128(blo + kb * (kTileRows * 128) + ks * 32), idesc, 1);
+                for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const uint32_t d = tmem + (blk == 0 ? kColZ : kColY);
+                        // hi weights x (hi [+ lo] activations)
+                        mbar_wait(&S.full[r.stage], r.phase);
+                        tc_fence_after();
+                        uint64_t wd = ws_desc0 + r.stage * kStageStep;
+                        if (leader) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {            // 32 bytes of K per instruction = 2 address units
+                                umma_tf32(d, wd + 2 * ks, bhi + kb * kKbStep + 2 * ks, idesc, (kb | ks) != 0);
+                                if (parts == 2) umma_tf32(d, wd + 2 * ks, blo + kb * kKbStep + 2 * ks, idesc, 1);
                             }
                             umma_commit(&S.empty[r.stage]);
-                            r.advance();
-                            if (parts == 2) {
-                                // lo weights x hi activations
-                                mbar_wait(&S.full[r.stage], r.phase);
-                                tc_fence_after();
-                                wbase = smem_u32(S.Ws[r.stage]);
+                        }
+                        r.advance();
+                        if (parts == 2) {
+                            // lo weights x hi activations
+                            mbar_wait(&S.full[r.stage], r.phase);
+                            tc_fence_after();
+                            wd = ws_desc0 + r.stage * kStageStep;
+                            if (leader) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)
-                                    umma_tf32(d, umma_desc_sw128(wbase + ks * 32),
-                                              umma_desc_sw128(bhi + kb * (kTileRows * 128) + ks * 32), idesc, 1);
+                                    umma_tf32(d, wd + 2 * ks, bhi + kb * kKbStep + 2 * ks, idesc, 1);
                                 umma_commit(&S.empty[r.stage]);
-                                r.advance();
                             }
+                            r.advance();
                         }
                     }
-                    umma_commit(&S.acc_ready);
                 }
+                if (leader) umma_commit(&S.acc_ready);
+                __syncwarp();
             }
         }
     } else {
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
 
 template <int R>
 static cudaError_t launch_tc_one(const HybridArgs& a, int grid, cudaStream_t stream) {
-    const int smem = (int)sizeof(TcSmem) + 1024;
+    const int smem = (int)sizeof(TcSmem);
     cudaError_t e = cudaFuncSetAttribute(hybrid_tc_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     hybrid_tc_kernel<R><<<grid, kTcThreads, smem, stream>>>(a);
