@@ -1,11 +1,13 @@
 // Tensor-core variant of the fused hybrid step with 16-bit operands and 256-row tiles
 // (sm_100a: tcgen05.mma kind::f16 + TMEM + bulk-copy TMA).
 //
-// Why this shape (measured with scripts/probes/umma_probe.cu on B200): one tcgen05.mma with
-// M = 128 costs ~136 clk for any N <= 128 and ~172 clk for N = 256, for a 32-byte K step of either
-// operand type.  Per flop an N = 256 instruction is therefore 1.6x cheaper than N = 128, and a
-// 16-bit operand (K = 16 per instruction) twice as cheap as TF32 (K = 8).  The tile is 256 rows
-// (cells) so that every instruction is M = 128 output features x N = 256 rows.
+// Shape (scripts/probes/umma_probe.cu, profiles/r1_n_umma_probe.txt): with a tight, warp-uniform issue
+// loop one tcgen05.mma of M = 128 costs 128 clk at N = 256 and 64 clk at N = 128 for a 32-byte K step
+// -- both at the pipe's peak (8.1 kflop/clk/SM for 16-bit operands, half of that for TF32) -- but
+// 48 clk at N = 64 (66 %) and the same time at M = 64 (50 %).  So 16-bit operands (K = 16 per
+// instruction) halve the tensor time of TF32, and N >= 128 keeps the pipe efficient.  The tile is 256
+// rows: one N = 256 group for window tiles (less halo: 93 % useful rows at the C3 shape instead of
+// 86 %), two independent N = 128 groups for whole-IC tiles (kSplit below).
 //
 // The product is issued TRANSPOSED as in hybrid_tc_kernel.cu: D^T[n][i] = sum_k W[n][k] h[i][k];
 // the accumulator has TMEM lane = feature, column = row, so the +-r window of the message-passing
@@ -28,9 +30,8 @@
 // exchange data): the halves run as two independent groups of 8 epilogue warps, each with its own
 // barriers, and the issuer alternates between them with N = 128 instructions -- while one half is in
 // its epilogue (or in the finite-volume / field-solve tail) the tensor pipe works on the other half.
-// An N = 128 instruction costs 136 clk against 172 for N = 256, i.e. 1.6x more tensor time per row,
-// but that time is now hidden behind the epilogues instead of added to them.  Window tiles (nx > 128)
-// keep the single 256-row group.
+// N = 128 instructions are as efficient as N = 256 ones, so the split costs no tensor time.  Window
+// tiles (nx > 128) keep the single 256-row group.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -226,9 +227,9 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         // ---------------- UMMA issuer ------------------------------------------------------
         // The WHOLE warp walks the loop in uniform control flow and one elected lane issues.  With a
         // `lane == 0` branch around everything the compiler cannot prove the descriptors warp-uniform
-        // and wraps every UTCHMMA in R2UR moves and an ELECT / BRA.U.ANY serialisation loop: ~15
-        // dependent instructions of a lone warp per UMMA (~136 clk), which -- not the tensor pipe --
-        // was the cost of an N <= 128 instruction measured by scripts/probes/umma_probe.cu.
+        // (ring stage, group) and wraps every UTCHMMA in R2UR moves and an ELECT / BRA.U.ANY
+        // serialisation loop: ~15 dependent instructions of a lone warp per UMMA, ~136 clk against the
+        // 64 clk the tensor pipe needs for an N = 128 instruction.
         const uint32_t idesc = idesc_f16(128, kGroupRows, kBf16 ? 1 : 0);
         const bool leader = elect_one_lane();
         const uint64_t ws_desc0 = umma_desc_sw128(smem_u32(S.Ws[0]));
