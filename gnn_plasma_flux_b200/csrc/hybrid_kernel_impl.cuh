@@ -30,6 +30,8 @@
 // mbarrier ring; 8 consumer warps run an 8x8 register-tile FFMA kernel.
 #pragma once
 
+#include <cstdio>
+
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
 
@@ -75,6 +77,9 @@ struct Pipe {
     int stage = 0;
     uint32_t phase = 0;
     int consumed = 0;                    // chunks this warp has finished (only compared with kSkewChunks)
+#ifdef FLUXGNN_FFMA_TIMING
+    long long t_wait = 0, t_gemm = 0, t_bar = 0;
+#endif
     __device__ __forceinline__ void advance() {
         if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
@@ -113,8 +118,17 @@ __device__ __forceinline__ void gemm_pass(float (&acc)[8][8], TileSmem& S, Pipe&
         }
 #endif
 #pragma unroll 1
+#ifdef FLUXGNN_FFMA_TIMING
+    const long long tg0 = clock64();
+#endif
     for (int kc = 0; kc < kChunksPerHalf; ++kc) {
+#ifdef FLUXGNN_FFMA_TIMING
+        const long long tw0 = clock64();
         mbar_wait(&S.full[pipe.stage], pipe.phase);
+        pipe.t_wait += clock64() - tw0;
+#else
+        mbar_wait(&S.full[pipe.stage], pipe.phase);
+#endif
         const float* __restrict__ wst = S.Ws[pipe.stage];
         const float* __restrict__ hk = S.Hs + kc * kChunkK * kTileRows;
 #pragma unroll
@@ -154,6 +168,9 @@ __device__ __forceinline__ void gemm_pass(float (&acc)[8][8], TileSmem& S, Pipe&
         }
         pipe.advance();
     }
+#ifdef FLUXGNN_FFMA_TIMING
+    pipe.t_gemm += clock64() - tg0;
+#endif
 #if FLUXGNN_FFMA2
 #pragma unroll
     for (int p = 0; p < 4; ++p)
@@ -276,6 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
     const int bar = 1 + grp;
     const bool leads_skew = a.split && grp == 0;
     if (a.split && grp == 1) mbar_wait(&S.skew, 0);
+#ifdef FLUXGNN_FFMA_TIMING
+    const long long t_start = clock64();
+#endif
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         // ---- row bookkeeping + state load -----------------------------------------
@@ -573,6 +593,11 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
         }   // steps
         named_sync(bar, gthreads);   // state arrays are rewritten by the next tile's load
     }       // tiles
+#ifdef FLUXGNN_FFMA_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
+        printf("[ffma timing] warp %d (group %d): total %lld clk, in GEMM passes %lld, of which waiting for weights %lld\n",
+               warp, grp, clock64() - t_start, pipe.t_gemm, pipe.t_wait);
+#endif
 }
 
 // ---------------------------------------------------------------------------
