@@ -41,7 +41,16 @@ static int sm_count(int* out) {
 static int plan_tiles(HybridArgs& a, int* fast_radius) {
     const int nx = a.nx;
     if (a.tile_rows == 0) a.tile_rows = kTileRows;
-    const int rows = a.tile_rows;                  // 128, or 256 for the 16-bit tensor kernel
+    // height of a logical tile: 128; the 16-bit tensor kernel packs two 128-row groups (or one 256-row group) per CTA
+    if (a.tile_rows == kTc16TileRows && a.tc_group_rows == 0) {
+        // two independent 128-row groups overlap their epilogues with each other's products (1.36x per tile);
+        // as windows they carry twice the halo, which pays up to a receptive field of 24 cells
+        const char* nosplit = getenv("FLUXGNN_TC16_NO_SPLIT");         // test hook
+        const bool forced_single = nosplit != nullptr && nosplit[0] == '1';
+        const int halo = a.L * a.radius + a.hops;
+        a.tc_group_rows = (!forced_single && (nx <= kTileRows || halo <= 24)) ? 128 : kTc16TileRows;
+    }
+    const int rows = a.tc_group_rows ? a.tc_group_rows : a.tile_rows;
     if (nx <= kTileRows) {                         // whole ICs (the API's workspace / gtab rules key on 128)
         a.whole_ic = 1;
         a.ics_per_tile = rows / nx;
@@ -86,7 +95,9 @@ static int launch_tiles(const HybridArgs& a, int fast_radius, cudaStream_t strea
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc != FLUXGNN_OK) return rc;
-    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    const int groups = a.tc_group_rows ? a.tile_rows / a.tc_group_rows : 1;       // logical tiles per CTA tile
+    const int cta_tiles = (a.num_tiles + groups - 1) / groups;
+    const int grid = cta_tiles < sms ? cta_tiles : sms;
     if (fast_radius < 0 && a.tile_rows == kTc16TileRows)
         FLUXGNN_CUDA_OK(launch_hybrid_tc16_tiles(a, -fast_radius, grid, stream));
     else if (fast_radius < 0)
@@ -501,12 +512,18 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, 
     a.c = c; a.dt = dt;
     a.tile_rows = kTileRows;
     if (precision != 0) tc_configure(a, precision);
+    int rows = a.tile_rows;
+    if (a.tile_rows == kTc16TileRows) {                                  // as in plan_tiles
+        const char* nosplit = getenv("FLUXGNN_TC16_NO_SPLIT");
+        a.tc_group_rows = (!(nosplit != nullptr && nosplit[0] == '1') && halo <= 24) ? 128 : kTc16TileRows;
+        rows = a.tc_group_rows;
+    }
     // always window tiles: the receptive field is served by the ghost cells
     a.whole_ic = 0;
     a.halo = halo;
-    a.valid = a.tile_rows - 2 * halo;
+    a.valid = rows - 2 * halo;
     if (a.valid < 8)
-        return set_error(FLUXGNN_EUNSUP, "receptive field of %d cells does not fit a %d-cell tile", halo, a.tile_rows);
+        return set_error(FLUXGNN_EUNSUP, "receptive field of %d cells does not fit a %d-cell tile", halo, rows);
     a.tiles_per_ic = (owned + a.valid - 1) / a.valid;
     const long long tiles = (long long)B * a.tiles_per_ic;
     if (tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");

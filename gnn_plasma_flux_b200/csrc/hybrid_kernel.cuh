@@ -27,7 +27,10 @@ struct HybridArgs {
     float c, dt;               // float32(dt/dx), float32(dt)
     int tc_parts;              // tensor path only: 2 = x3 split (hi/lo parts, three products), 1 = one product
     int tc_format;             // 16-bit tensor path: 0 = fp16, 1 = bf16 operands
-    int tile_rows;             // cells per tile: 128 (kTileRows) or 256 (16-bit tensor path)
+    int tile_rows;             // cells per CTA tile: 128 (kTileRows) or 256 (16-bit tensor path)
+    int tc_group_rows;         // 16-bit tensor path: rows of one independent group = height of a LOGICAL tile
+                               //   (128: two groups per CTA tile, 256: one); num_tiles, valid, tiles_per_ic and
+                               //   ics_per_tile count logical tiles.  0 elsewhere (logical tile = CTA tile).
     float* acts;               // nullable (FP32-pipe kernel, training forward): saved activations, row-major
     long long acts_stride;     //   [L+3][B*nx][128]: h^0..h^L, then P + b1 and Q of the edge readout
     int split;                 // FP32-pipe kernel: two skewed 64-row groups per tile (whole-IC tiles, nx | 64)

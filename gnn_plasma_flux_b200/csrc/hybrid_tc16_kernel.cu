@@ -6,8 +6,7 @@
 // -- both at the pipe's peak (8.1 kflop/clk/SM for 16-bit operands, half of that for TF32) -- but
 // 48 clk at N = 64 (66 %) and the same time at M = 64 (50 %).  So 16-bit operands (K = 16 per
 // instruction) halve the tensor time of TF32, and N >= 128 keeps the pipe efficient.  The tile is 256
-// rows: one N = 256 group for window tiles (less halo: 93 % useful rows at the C3 shape instead of
-// 86 %), two independent N = 128 groups for whole-IC tiles (kSplit below).
+// rows, normally run as two independent N = 128 groups (kSplit below).
 //
 // The product is issued TRANSPOSED as in hybrid_tc_kernel.cu: D^T[n][i] = sum_k W[n][k] h[i][k];
 // the accumulator has TMEM lane = feature, column = row, so the +-r window of the message-passing
@@ -26,12 +25,12 @@
 // Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quadrant = warp % 4, two 32-row chunks each),
 // warp 16 weight producer, warp 17 TMEM allocator + UMMA issuer.
 //
-// kSplit (whole-IC tiles, nx <= 128: the two 128-row halves of a tile hold different ICs and never
-// exchange data): the halves run as two independent groups of 8 epilogue warps, each with its own
-// barriers, and the issuer alternates between them with N = 128 instructions -- while one half is in
-// its epilogue (or in the finite-volume / field-solve tail) the tensor pipe works on the other half.
-// N = 128 instructions are as efficient as N = 256 ones, so the split costs no tensor time.  Window
-// tiles (nx > 128) keep the single 256-row group.
+// kSplit: the two 128-row halves of a CTA tile are independent LOGICAL tiles -- different ICs (nx <= 128)
+// or two windows with their own halos (nx > 128) -- and run as two groups of 8 epilogue warps, each
+// with its own barriers; the issuer alternates between them with N = 128 instructions, so while one
+// half is in its epilogue (or in the finite-volume / field-solve tail) the tensor pipe works on the
+// other.  N = 128 instructions are as efficient as N = 256 ones, so the split costs no tensor time.
+// Only very wide receptive fields (halo > 24 cells) keep one 256-row window per CTA (api.cu, plan_tiles).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -201,7 +200,9 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
 
-    const int my_tiles = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // a.num_tiles counts LOGICAL tiles (one per group); a CTA tile holds kGroups of them
+    const int cta_tiles = (a.num_tiles + kGroups - 1) / kGroups;
+    const int my_tiles = (cta_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int layers = a.L + 1;
 
     if (warp == kProducerWarp) {
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         const int n = 32 * q + lane;                          // this thread's feature = TMEM lane
         const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
         const float inv_deg = kUnscale / (float)(2 * R);
-        const int seg = a.whole_ic ? nx : kRows;              // periodic segment inside the tile (multiple of 32)
+        const int seg = a.whole_ic ? nx : kGroupRows;         // periodic segment inside the group (multiple of 32)
         uint32_t acc_phase = 0;
 
         // activation element (row i, feature n): k-block n / 64, 16-byte chunk ((n % 64) / 8) ^ (i & 7), 2 bytes
@@ -320,29 +321,31 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
 #ifdef FLUXGNN_TC_TIMING
         long long tc_last__ = clock64();
 #endif
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        for (int cta_tile = blockIdx.x; cta_tile < cta_tiles; cta_tile += gridDim.x) {
+            const int tile = cta_tile * kGroups + grp;                 // this group's logical tile
+            const bool tile_ok = tile < a.num_tiles;                   // the last CTA tile may be half empty
             TC_TICK(0);
             // ---- row bookkeeping + state load (as in the FP32-pipe kernel) ----------------
             if (myrow >= 0) {
-                const int j = myrow;
-                int ic, cell, prev = (j - 1) & (kRows - 1), next = (j + 1) & (kRows - 1);
+                const int j = myrow, jl = lt;                          // row in the CTA tile / in the group
+                int ic, cell, prev = row0 + ((jl - 1) & (kGroupRows - 1)), next = row0 + ((jl + 1) & (kGroupRows - 1));
                 bool live, owned;
                 int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
                 if (a.whole_ic) {
-                    const int slot = j / nx;
-                    cell = j - slot * nx;
+                    const int slot = jl / nx;
+                    cell = jl - slot * nx;
                     ic = tile * a.ics_per_tile + slot;
-                    live = ic < a.B;
+                    live = tile_ok && ic < a.B;
                     owned = live;
                     prev = (cell == 0) ? j + nx - 1 : j - 1;
                     next = (cell == nx - 1) ? j - nx + 1 : j + 1;
                 } else {
                     ic = tile / a.tiles_per_ic;
                     const int t = tile - ic * a.tiles_per_ic;
-                    const long long gcell = (long long)t * a.valid - a.halo + j;
+                    const long long gcell = (long long)t * a.valid - a.halo + jl;
                     cell = (int)(((gcell % nx) + nx) % nx);
-                    live = true;
-                    owned = (j >= a.halo) && (j < a.halo + a.valid) && ((long long)t * a.valid + (j - a.halo) < nx);
+                    live = tile_ok;
+                    owned = tile_ok && (jl >= a.halo) && (jl < a.halo + a.valid) && ((long long)t * a.valid + (jl - a.halo) < nx);
                     if (a.slab) {                       // ghost cells instead of the periodic wrap
                         long long s = gcell + a.halo;
                         s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
@@ -585,13 +588,10 @@ static cudaError_t launch_mode(const HybridArgs& a, int grid, cudaStream_t strea
     return launch_one<R, 1, false, kSplit>(a, grid, stream);                                  // fp16
 }
 
-// whole-IC tiles (nx in {32, 64, 128}): the two halves of a tile are independent -> ping-pong groups
-// (FLUXGNN_TC16_NO_SPLIT=1: test hook that keeps the single 256-row group)
+// a.tc_group_rows (api.cu, plan_tiles): 128 = two independent groups per CTA tile, 256 = one group
 template <int R>
 static cudaError_t launch_radius(const HybridArgs& a, int grid, cudaStream_t stream) {
-    const char* nosplit = getenv("FLUXGNN_TC16_NO_SPLIT");
-    const bool split = a.whole_ic && !(nosplit != nullptr && nosplit[0] == '1');
-    return split ? launch_mode<R, true>(a, grid, stream) : launch_mode<R, false>(a, grid, stream);
+    return a.tc_group_rows == 128 ? launch_mode<R, true>(a, grid, stream) : launch_mode<R, false>(a, grid, stream);
 }
 
 cudaError_t launch_hybrid_tc16_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream) {

@@ -463,6 +463,23 @@ def test_tc_long_rollout_1000_steps(model):
         assert np.abs(final[:, 0].astype(np.float64).sum(-1) - mass0).max() <= 1000 * 64 * np.finfo(np.float32).eps
 
 
+@pytest.mark.parametrize("nx,radius", [(64, 3), (1024, 2)])
+def test_tc16_single_group_path(model, weights, monkeypatch, nx, radius):
+    """The 16-bit kernel normally runs two 128-row groups per CTA tile; FLUXGNN_TC16_NO_SPLIT=1 keeps the
+    one-group 256-row variant (used for very wide receptive fields) under test: same gates."""
+    dt = 1e-3 if nx == 64 else 3e-4
+    grid = P.Grid(nx=nx, dt=dt)
+    ics = np.stack([P.stable_initial_condition(grid, s) for s in range(5)])
+    ref = batched.hybrid_run(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, 3, radius=radius).numpy()
+    sol = make_solver(model, nx, dt, graph_radius=radius, precision="fp16x3")
+    two, _ = sol.rollout(torch.from_numpy(ics).cuda(), 3)
+    monkeypatch.setenv("FLUXGNN_TC16_NO_SPLIT", "1")
+    one, _ = sol.rollout(torch.from_numpy(ics).cuda(), 3)
+    assert P.rel_err(one.cpu().numpy(), ref).max() <= 3 * STEP_TOL
+    assert P.rel_err(two.cpu().numpy(), ref).max() <= 3 * STEP_TOL
+    assert torch.equal(one, two)                 # same arithmetic per cell, only the tiling differs
+
+
 def test_tc_rejects_unsupported_shapes(model):
     from gnn_plasma_flux_b200 import _lib
     with pytest.raises(_lib.FluxGNNError):                                       # nx=40: no silent fallback
