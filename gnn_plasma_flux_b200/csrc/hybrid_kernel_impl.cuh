@@ -34,6 +34,7 @@
 
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
+#include "tile_common.cuh"
 
 namespace fluxgnn {
 
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
     const int myrow = (lt < nrows) ? row0 + lt : -1;                   // the row this thread looks after
     const int bar = 1 + grp;
     const bool leads_skew = a.split && grp == 0;
+    const TileRows T{S.sN, S.sU, S.sE, S.sX, S.sF, S.sRho, S.gtab, S.rowIC, S.rowCell, S.prevRow, S.nextRow};
     if (a.split && grp == 1) mbar_wait(&S.skew, 0);
 #ifdef FLUXGNN_FFMA_TIMING
     const long long t_start = clock64();
@@ -299,51 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         // ---- row bookkeeping + state load -----------------------------------------
-        if (myrow >= 0) {
-            const int j = myrow;
-            int ic, cell, prev = (j - 1) & (kTileRows - 1), next = (j + 1) & (kTileRows - 1);
-            bool live, owned;
-            int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
-            if (a.whole_ic) {
-                const int slot = j / nx;
-                cell = j - slot * nx;
-                ic = tile * a.ics_per_tile + slot;
-                live = (slot < a.ics_per_tile) && (ic < a.B);
-                owned = live;
-                if (slot < a.ics_per_tile) {
-                    prev = (cell == 0) ? j + nx - 1 : j - 1;
-                    next = (cell == nx - 1) ? j - nx + 1 : j + 1;
-                }
-            } else {
-                ic = tile / a.tiles_per_ic;
-                const int t = tile - ic * a.tiles_per_ic;
-                const long long gcell = (long long)t * a.valid - a.halo + j;
-                cell = (int)(((gcell % nx) + nx) % nx);
-                live = true;
-                owned = (j >= a.halo) && (j < a.halo + a.valid) && ((long long)t * a.valid + (j - a.halo) < nx);
-                if (a.slab) {                       // ghost cells instead of the periodic wrap
-                    long long s = gcell + a.halo;
-                    s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
-                    src = (int)s;
-                    ld = a.ld_in;
-                    cell = (int)(gcell < 0 ? 0 : (gcell >= nx ? nx - 1 : gcell));
-                }
-            }
-            S.rowIC[j] = owned ? ic : -1;
-            S.rowCell[j] = cell;
-            S.prevRow[j] = (short)prev;
-            S.nextRow[j] = (short)next;
-            float vn = 0.f, vu = 0.f, ve = 0.f, vx = 0.f;
-            if (live) {
-                if (src < 0) src = cell;
-                const float* st = a.state_in + (size_t)ic * 3 * ld + src;
-                vn = __ldg(st);
-                vu = __ldg(st + ld);
-                ve = __ldg(st + 2 * (size_t)ld);
-                vx = __ldg(a.x + src);
-            }
-            S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
-        }
+        if (myrow >= 0) tile_load_row(a, T, tile, true, myrow, myrow, 0, kTileRows);
         named_sync(bar, gthreads);
 
         for (int step = 0; step < a.steps; ++step) {
@@ -533,63 +491,26 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
             if (!a.do_update) continue;          // forward only (steps == 1)
             named_sync(bar, gthreads);
 
-            // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
-            if (myrow >= 0) {
-                const int j = myrow, p = S.prevRow[j];
-                const float u = S.sU[j], up = S.sU[p];
-                n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
-                const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
-                const float fup = __fmul_rn(__fmul_rn(0.5f, up), up);
-                const float u_adv = __fsub_rn(u, __fmul_rn(a.c, __fsub_rn(fu, fup)));
-                u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, S.sE[j]));
-            }
+            // ---- finite-volume update (src/hybrid_solver.py:51-58) ----
+            if (myrow >= 0) tile_fv_update(a, T, myrow, n_new, u_new);
             if (!a.whole_ic) {
                 // window tiles: E' comes from the separate field-solve kernel
-                if (myrow >= 0 && S.rowIC[myrow] >= 0) {
-                    float* so = a.state_out + (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
-                    so[0] = n_new;
-                    so[nx] = u_new;
-                }
+                if (myrow >= 0) tile_store_window_row(a, T, myrow, n_new, u_new);
                 continue;
             }
             named_sync(bar, gthreads);           // everyone has read the old n, u
-            if (myrow >= 0) {
-                S.sN[myrow] = n_new;
-                S.sU[myrow] = u_new;
-                S.sRho[myrow] = __fsub_rn(n_new, 1.0f);        // rho = n - n0  (src/baseline_solver.py:60)
-            }
+            if (myrow >= 0) tile_keep_row(T, myrow, n_new, u_new);
             named_sync(bar, gthreads);
-            // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
+            // ---- field solve: E = g (*) rho, two threads per row (src/baseline_solver.py:59-68) ----
             {
                 const int row = row0 + (lt >> 1), half = lt & 1;
-                double e = 0.0;
-                if (row < used_rows) {
-                    const int cell = S.rowCell[row], base = row - cell;
-                    for (int i = half; i < nx; i += 2) {
-                        int d = cell - i;
-                        if (d < 0) d += nx;
-                        e = fma(S.gtab[d], (double)S.sRho[base + i], e);
-                    }
-                }
+                double e = (row < used_rows) ? tile_field_partial(T, row, half, 2, nx) : 0.0;
                 e += __shfl_xor_sync(0xffffffffu, e, 1);
                 if (half == 0) S.sE[row] = (float)e;
             }
             named_sync(bar, gthreads);
             // ---- write-out: last step and recorded steps ---------------------------------
-            if (myrow >= 0 && S.rowIC[myrow] >= 0) {
-                const size_t off = (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
-                if (step == a.steps - 1) {
-                    a.state_out[off] = S.sN[myrow];
-                    a.state_out[off + nx] = S.sU[myrow];
-                    a.state_out[off + 2 * (size_t)nx] = S.sE[myrow];
-                }
-                if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
-                    float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
-                    tr[0] = S.sN[myrow];
-                    tr[nx] = S.sU[myrow];
-                    tr[2 * (size_t)nx] = S.sE[myrow];
-                }
-            }
+            if (myrow >= 0) tile_write_out_row(a, T, myrow, step);
         }   // steps
         named_sync(bar, gthreads);   // state arrays are rewritten by the next tile's load
     }       // tiles

@@ -37,6 +37,7 @@
 
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
+#include "tile_common.cuh"
 
 namespace fluxgnn {
 
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         const int cw = (warp >> 2) & (kSplit ? 1 : 3);
         constexpr int kChunkStep = kSplit ? 2 : 4;
         const int myrow = (lt < kGroupRows) ? row0 + lt : -1; // the row this thread looks after in per-row phases
+        const TileRows T{S.sN, S.sU, S.sE, S.sX, S.sF, S.sRho, S.gtab, S.rowIC, S.rowCell, S.prevRow, S.nextRow};
         const int n = 32 * q + lane;                          // this thread's feature = TMEM lane
         const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
         const float inv_deg = kUnscale / (float)(2 * R);
@@ -326,49 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
             const bool tile_ok = tile < a.num_tiles;                   // the last CTA tile may be half empty
             TC_TICK(0);
             // ---- row bookkeeping + state load (as in the FP32-pipe kernel) ----------------
-            if (myrow >= 0) {
-                const int j = myrow, jl = lt;                          // row in the CTA tile / in the group
-                int ic, cell, prev = row0 + ((jl - 1) & (kGroupRows - 1)), next = row0 + ((jl + 1) & (kGroupRows - 1));
-                bool live, owned;
-                int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
-                if (a.whole_ic) {
-                    const int slot = jl / nx;
-                    cell = jl - slot * nx;
-                    ic = tile * a.ics_per_tile + slot;
-                    live = tile_ok && ic < a.B;
-                    owned = live;
-                    prev = (cell == 0) ? j + nx - 1 : j - 1;
-                    next = (cell == nx - 1) ? j - nx + 1 : j + 1;
-                } else {
-                    ic = tile / a.tiles_per_ic;
-                    const int t = tile - ic * a.tiles_per_ic;
-                    const long long gcell = (long long)t * a.valid - a.halo + jl;
-                    cell = (int)(((gcell % nx) + nx) % nx);
-                    live = tile_ok;
-                    owned = tile_ok && (jl >= a.halo) && (jl < a.halo + a.valid) && ((long long)t * a.valid + (jl - a.halo) < nx);
-                    if (a.slab) {                       // ghost cells instead of the periodic wrap
-                        long long s = gcell + a.halo;
-                        s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
-                        src = (int)s;
-                        ld = a.ld_in;
-                        cell = (int)(gcell < 0 ? 0 : (gcell >= nx ? nx - 1 : gcell));
-                    }
-                }
-                S.rowIC[j] = owned ? ic : -1;
-                S.rowCell[j] = cell;
-                S.prevRow[j] = (short)prev;
-                S.nextRow[j] = (short)next;
-                float vn = 0.f, vu = 0.f, ve = 0.f, vx = 0.f;
-                if (live) {
-                    if (src < 0) src = cell;
-                    const float* st = a.state_in + (size_t)ic * 3 * ld + src;
-                    vn = __ldg(st);
-                    vu = __ldg(st + ld);
-                    ve = __ldg(st + 2 * (size_t)ld);
-                    vx = __ldg(a.x + src);
-                }
-                S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
-            }
+            if (myrow >= 0) tile_load_row(a, T, tile, tile_ok, myrow, lt, row0, kGroupRows);
             named_sync(bar, kGroupThreads);
             TC_TICK(1);
 
@@ -491,61 +451,26 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                 named_sync(bar, kGroupThreads);
                 TC_TICK(7);
 
-                // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
-                if (myrow >= 0) {
-                    const int j = myrow, p = S.prevRow[j];
-                    const float u = S.sU[j], up = S.sU[p];
-                    n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
-                    const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
-                    const float fup = __fmul_rn(__fmul_rn(0.5f, up), up);
-                    const float u_adv = __fsub_rn(u, __fmul_rn(a.c, __fsub_rn(fu, fup)));
-                    u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, S.sE[j]));
-                }
+                // ---- finite-volume update (src/hybrid_solver.py:51-58) ----
+                if (myrow >= 0) tile_fv_update(a, T, myrow, n_new, u_new);
                 if (!a.whole_ic) {
-                    if (myrow >= 0 && S.rowIC[myrow] >= 0) {
-                        float* so = a.state_out + (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
-                        so[0] = n_new;
-                        so[nx] = u_new;
-                    }
+                    if (myrow >= 0) tile_store_window_row(a, T, myrow, n_new, u_new);
                     continue;
                 }
                 named_sync(bar, kGroupThreads);
-                if (myrow >= 0) {
-                    S.sN[myrow] = n_new;
-                    S.sU[myrow] = u_new;
-                    S.sRho[myrow] = __fsub_rn(n_new, 1.0f);
-                }
+                if (myrow >= 0) tile_keep_row(T, myrow, n_new, u_new);
                 named_sync(bar, kGroupThreads);
                 TC_TICK(8);
-                // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
+                // ---- field solve: E = g (*) rho, two threads per row (src/baseline_solver.py:59-68) ----
                 {
                     const int row = row0 + (lt >> 1), part = lt & 1;
-                    const int cell = S.rowCell[row], base = row - cell;
-                    double e = 0.0;
-                    for (int i = part; i < nx; i += 2) {
-                        int d = cell - i;
-                        if (d < 0) d += nx;
-                        e = fma(S.gtab[d], (double)S.sRho[base + i], e);
-                    }
+                    double e = tile_field_partial(T, row, part, 2, nx);
                     e += __shfl_xor_sync(0xffffffffu, e, 1);
                     if (part == 0) S.sE[row] = (float)e;
                 }
                 named_sync(bar, kGroupThreads);
                 TC_TICK(9);
-                if (myrow >= 0 && S.rowIC[myrow] >= 0) {
-                    const size_t off = (size_t)S.rowIC[myrow] * 3 * nx + S.rowCell[myrow];
-                    if (step == a.steps - 1) {
-                        a.state_out[off] = S.sN[myrow];
-                        a.state_out[off + nx] = S.sU[myrow];
-                        a.state_out[off + 2 * (size_t)nx] = S.sE[myrow];
-                    }
-                    if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
-                        float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
-                        tr[0] = S.sN[myrow];
-                        tr[nx] = S.sU[myrow];
-                        tr[2 * (size_t)nx] = S.sE[myrow];
-                    }
-                }
+                if (myrow >= 0) tile_write_out_row(a, T, myrow, step);
                 TC_TICK(10);
             }   // steps
             named_sync(bar, kGroupThreads);

@@ -22,6 +22,7 @@
 // operand images), warp 17 TMEM allocator + single-thread UMMA issuer.
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
+#include "tile_common.cuh"
 
 namespace fluxgnn {
 
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
         const float inv_deg = 1.0f / (float)(2 * R);
         const int seg = a.whole_ic ? nx : kTileRows;          // periodic segment inside the tile (multiple of 32)
         uint32_t acc_phase = 0;
+        const TileRows T{S.sN, S.sU, S.sE, S.sX, S.sF, S.sRho, S.gtab, S.rowIC, S.rowCell, S.prevRow, S.nextRow};
 
         // activation element (row i0 + j, feature n): K-block q, 16-byte chunk (lane/4) ^ (j & 7)
         const uint32_t act_base = (uint32_t)(q * (kTileRows * 128) + i0 * 128 + ((lane & 3) << 2));
@@ -193,49 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
 
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             // ---- row bookkeeping + state load (as in the FP32-pipe kernel) ----------------
-            if (tid < kTileRows) {
-                const int j = tid;
-                int ic, cell, prev = (j - 1) & (kTileRows - 1), next = (j + 1) & (kTileRows - 1);
-                bool live, owned;
-                int src = -1, ld = nx;                  // source index / row length when they differ from (cell, nx)
-                if (a.whole_ic) {
-                    const int slot = j / nx;
-                    cell = j - slot * nx;
-                    ic = tile * a.ics_per_tile + slot;
-                    live = ic < a.B;
-                    owned = live;
-                    prev = (cell == 0) ? j + nx - 1 : j - 1;
-                    next = (cell == nx - 1) ? j - nx + 1 : j + 1;
-                } else {
-                    ic = tile / a.tiles_per_ic;
-                    const int t = tile - ic * a.tiles_per_ic;
-                    const long long gcell = (long long)t * a.valid - a.halo + j;
-                    cell = (int)(((gcell % nx) + nx) % nx);
-                    live = true;
-                    owned = (j >= a.halo) && (j < a.halo + a.valid) && ((long long)t * a.valid + (j - a.halo) < nx);
-                    if (a.slab) {                       // ghost cells instead of the periodic wrap
-                        long long s = gcell + a.halo;
-                        s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
-                        src = (int)s;
-                        ld = a.ld_in;
-                        cell = (int)(gcell < 0 ? 0 : (gcell >= nx ? nx - 1 : gcell));
-                    }
-                }
-                S.rowIC[j] = owned ? ic : -1;
-                S.rowCell[j] = cell;
-                S.prevRow[j] = (short)prev;
-                S.nextRow[j] = (short)next;
-                float vn = 0.f, vu = 0.f, ve = 0.f, vx = 0.f;
-                if (live) {
-                    if (src < 0) src = cell;
-                    const float* st = a.state_in + (size_t)ic * 3 * ld + src;
-                    vn = __ldg(st);
-                    vu = __ldg(st + ld);
-                    ve = __ldg(st + 2 * (size_t)ld);
-                    vx = __ldg(a.x + src);
-                }
-                S.sN[j] = vn; S.sU[j] = vu; S.sE[j] = ve; S.sX[j] = vx;
-            }
+            if (tid < kTileRows) tile_load_row(a, T, tile, true, tid, tid, 0, kTileRows);
             named_sync(1, kEpiThreads);
 
             for (int step = 0; step < a.steps; ++step) {
@@ -350,60 +310,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) hybrid_tc_kernel(const HybridAr
                 if (!a.do_update) continue;
                 named_sync(1, kEpiThreads);
 
-                // ---- finite-volume update, numpy's fp32 operation order (src/hybrid_solver.py:51-58) ----
-                if (tid < kTileRows) {
-                    const int j = tid, p = S.prevRow[j];
-                    const float u = S.sU[j], up = S.sU[p];
-                    n_new = __fsub_rn(S.sN[j], __fmul_rn(a.c, __fsub_rn(S.sF[j], S.sF[p])));
-                    const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
-                    const float fup = __fmul_rn(__fmul_rn(0.5f, up), up);
-                    const float u_adv = __fsub_rn(u, __fmul_rn(a.c, __fsub_rn(fu, fup)));
-                    u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, S.sE[j]));
-                }
+                // ---- finite-volume update (src/hybrid_solver.py:51-58) ----
+                if (tid < kTileRows) tile_fv_update(a, T, tid, n_new, u_new);
                 if (!a.whole_ic) {
-                    if (tid < kTileRows && S.rowIC[tid] >= 0) {
-                        float* so = a.state_out + (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
-                        so[0] = n_new;
-                        so[nx] = u_new;
-                    }
+                    if (tid < kTileRows) tile_store_window_row(a, T, tid, n_new, u_new);
                     continue;
                 }
                 named_sync(1, kEpiThreads);
-                if (tid < kTileRows) {
-                    S.sN[tid] = n_new;
-                    S.sU[tid] = u_new;
-                    S.sRho[tid] = __fsub_rn(n_new, 1.0f);
-                }
+                if (tid < kTileRows) tile_keep_row(T, tid, n_new, u_new);
                 named_sync(1, kEpiThreads);
-                // ---- field solve: E = g (*) rho, fp64 accumulation (src/baseline_solver.py:59-68) ----
+                // ---- field solve: E = g (*) rho, four threads per row (src/baseline_solver.py:59-68) ----
                 {
                     const int row = tid >> 2, part = tid & 3;
-                    const int cell = S.rowCell[row], base = row - cell;
-                    double e = 0.0;
-                    for (int i = part; i < nx; i += 4) {
-                        int d = cell - i;
-                        if (d < 0) d += nx;
-                        e = fma(S.gtab[d], (double)S.sRho[base + i], e);
-                    }
+                    double e = tile_field_partial(T, row, part, 4, nx);
                     e += __shfl_xor_sync(0xffffffffu, e, 1);
                     e += __shfl_xor_sync(0xffffffffu, e, 2);
                     if (part == 0) S.sE[row] = (float)e;
                 }
                 named_sync(1, kEpiThreads);
-                if (tid < kTileRows && S.rowIC[tid] >= 0) {
-                    const size_t off = (size_t)S.rowIC[tid] * 3 * nx + S.rowCell[tid];
-                    if (step == a.steps - 1) {
-                        a.state_out[off] = S.sN[tid];
-                        a.state_out[off + nx] = S.sU[tid];
-                        a.state_out[off + 2 * (size_t)nx] = S.sE[tid];
-                    }
-                    if (a.traj != nullptr && (step + 1) % a.record_every == 0) {
-                        float* tr = a.traj + (size_t)((step + 1) / a.record_every - 1) * a.B * 3 * nx + off;
-                        tr[0] = S.sN[tid];
-                        tr[nx] = S.sU[tid];
-                        tr[2 * (size_t)nx] = S.sE[tid];
-                    }
-                }
+                if (tid < kTileRows) tile_write_out_row(a, T, tid, step);
             }   // steps
             named_sync(1, kEpiThreads);
         }       // tiles
