@@ -168,7 +168,6 @@ template <int R, int PARTS, bool kBf16, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridArgs a) {
     constexpr int kGroups = kSplit ? 2 : 1;
     constexpr int kGroupRows = kRows / kGroups;              // rows of a group = UMMA N
-    constexpr int kGroupThreads = kEpiThreads / kGroups;
     // 1024-byte aligned as declared (the 128-byte swizzle needs it; checked below).  Indexing the array
     // itself -- not a re-aligned generic pointer -- keeps every access in the shared address space (LDS/STS).
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
             mbar_init(&S.empty[s], 1);
         }
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&S.act_ready[g], kGroupThreads);
+            mbar_init(&S.act_ready[g], kEpiThreads);          // all 16 epilogue warps publish every group
             mbar_init(&S.acc_ready[g], 1);
         }
         mbar_fence_init();
@@ -289,15 +288,14 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         }
     } else {
         // ---------------- epilogue / compute warps ---------------------------------------
-        const int q = warp & 3;                               // TMEM lane quadrant
-        const int grp = kSplit ? (warp >> 3) : 0;             // group = 128-row half (kSplit) or the whole tile
-        const int lt = tid - grp * kGroupThreads;             // thread index inside the group
-        const int row0 = grp * kGroupRows;
-        const int bar = 1 + grp;                              // named barrier of the group
-        // the warp's two 32-row chunks start at row0 + 32 * (cw + kChunkStep * half)
-        const int cw = (warp >> 2) & (kSplit ? 1 : 3);
-        constexpr int kChunkStep = kSplit ? 2 : 4;
-        const int myrow = (lt < kGroupRows) ? row0 + lt : -1; // the row this thread looks after in per-row phases
+        // All 16 warps serve whichever group's accumulators are ready: per layer they finish group 0 while
+        // the tensor pipe works on group 1, then group 1 while it works on group 0's next layer.  The
+        // finite-volume tail of a group and the input layer of its NEXT step (or next tile) run right after
+        // its edge readout, so that the issuer always has the other group's products to go on with.
+        const int q = warp & 3;                               // TMEM lane quadrant = feature quadrant
+        const int cw = warp >> 2;                             // 0..3: the warp's 32-row chunk(s) inside a group
+        constexpr int kChunksPerWarp = kGroupRows / 128;      // 1 (two groups) or 2 (one 256-row group)
+        constexpr int kRowThreads = kEpiThreads / kGroupRows; // threads per row in the field solve: 4 or 2
         const TileRows T{S.sN, S.sU, S.sE, S.sX, S.sF, S.sRho, S.gtab, S.rowIC, S.rowCell, S.prevRow, S.nextRow};
         const int n = 32 * q + lane;                          // this thread's feature = TMEM lane
         const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
@@ -319,162 +317,184 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
             sts_u16(addr, hi);
             if (PARTS == 2) sts_u16(addr + act_lo_off, lo);
         };
+        auto publish_activations = [&](int g) {               // generic-proxy stores -> visible to the UMMAs of group g
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(&S.act_ready[g]);
+        };
+
+        // ---- row bookkeeping + state load of group g's logical tile (tile_common.cuh) ----
+        auto load_rows = [&](int g, int cta_tile) {
+            const int tile = cta_tile * kGroups + g;
+            if (tid < kGroupRows)
+                tile_load_row(a, T, tile, tile < a.num_tiles, g * kGroupRows + tid, tid, g * kGroupRows, kGroupRows);
+        };
+
+        // ---- input MLP (src/flux_gnn.py:49): feature n, the warp's chunk(s) of group g ----
+        auto input_layer = [&](int g) {
+            const float w0 = S.small[SmallParams::w_in + 0 * kH + n];
+            const float w1 = S.small[SmallParams::w_in + 1 * kH + n];
+            const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
+            const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
+            const float b = S.small[SmallParams::b_in + n];
+#pragma unroll 1
+            for (int half = 0; half < kChunksPerWarp; ++half) {
+                const int i0 = g * kGroupRows + 32 * (cw + 4 * half);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 vn = *reinterpret_cast<const float4*>(&S.sN[i0 + j]);
+                    const float4 vu = *reinterpret_cast<const float4*>(&S.sU[i0 + j]);
+                    const float4 ve = *reinterpret_cast<const float4*>(&S.sE[i0 + j]);
+                    const float4 vx = *reinterpret_cast<const float4*>(&S.sX[i0 + j]);
+                    store_act(i0, j + 0, fmaxf(fmaf(w3, vx.x, fmaf(w2, ve.x, fmaf(w1, vu.x, fmaf(w0, vn.x, b)))), 0.f));
+                    store_act(i0, j + 1, fmaxf(fmaf(w3, vx.y, fmaf(w2, ve.y, fmaf(w1, vu.y, fmaf(w0, vn.y, b)))), 0.f));
+                    store_act(i0, j + 2, fmaxf(fmaf(w3, vx.z, fmaf(w2, ve.z, fmaf(w1, vu.z, fmaf(w0, vn.z, b)))), 0.f));
+                    store_act(i0, j + 3, fmaxf(fmaf(w3, vx.w, fmaf(w2, ve.w, fmaf(w1, vu.w, fmaf(w0, vn.w, b)))), 0.f));
+                }
+            }
+            publish_activations(g);
+        };
+
+        // ---- one layer's epilogue for group g: message passing (layer < L) or edge readout (layer == L) ----
+        auto layer_epilogue = [&](int g, int layer) {
+            const bool is_edge = (layer == a.L);
+            const float bias = S.small[(is_edge ? SmallParams::b_e1 : SmallParams::b_upd + layer * kH) + n];
+            const float w_out = S.small[SmallParams::w_e2 + n];
+#pragma unroll 1
+            for (int half = 0; half < kChunksPerWarp; ++half) {
+                const int i0 = g * kGroupRows + 32 * (cw + 4 * half);
+                const int seg0 = (i0 / seg) * seg;
+                const int cl = (i0 == seg0) ? i0 - 4 + seg : i0 - 4;
+                const int cr = (i0 + 32 == seg0 + seg) ? i0 + 32 - seg : i0 + 32;
+                float y[32], zc[32], zl[4], zr[4];
+                tmem_ld32(tlane + kColY + i0, y);
+                tmem_ld32(tlane + kColZ + i0, zc);
+                tmem_ld4(tlane + kColZ + cl, zl);
+                tmem_ld4(tlane + kColZ + cr, zr);
+                tc_wait_ld();
+                float zw[40];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { zw[t] = zl[t]; zw[36 + t] = zr[t]; }
+#pragma unroll
+                for (int t = 0; t < 32; ++t) zw[4 + t] = zc[t];
+                if (!is_edge) {
+                    // h'_i = relu(Y_i + b + mean_{0<|k|<=R} Z_{i+k})   (src/flux_gnn.py:55-60)
+                    // the window sum shares the pair sums pz[t] = Z[t] + Z[t+1] between neighbouring rows
+                    float pz[39];
+                    if constexpr (R >= 2) {
+#pragma unroll
+                        for (int t = 0; t < 39; ++t) pz[t] = zw[t] + zw[t + 1];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int c = 4 + j;                  // window centre in zw
+                        float sum;
+                        if constexpr (R == 1) sum = zw[c - 1] + zw[c + 1];
+                        else if constexpr (R == 2) sum = pz[c - 2] + pz[c + 1];
+                        else if constexpr (R == 3) sum = (pz[c - 3] + pz[c + 2]) + (zw[c - 1] + zw[c + 1]);
+                        else sum = (pz[c - 4] + pz[c + 3]) + (pz[c - 2] + pz[c + 1]);
+                        store_act(i0, j, fmaxf(fmaf(sum, inv_deg, fmaf(y[j], kUnscale, bias)), 0.f));
+                    }
+                } else {
+                    // edge readout (src/flux_gnn.py:63-66): this feature's term of the two dot products of
+                    // row i -- fwd (row i, col i+1): w2[n] relu(P_i + b1 + Q_{i+1});  bwd (row i, col i-1) --
+                    // summed over the warp's 32 features in registers, over the 4 quadrants in shared memory
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        y[j] = fmaf(y[j], kUnscale, bias);
+                        f[j] = w_out * fmaxf(fmaf(zw[4 + j + 1], kUnscale, y[j]), 0.f);
+                    }
+                    S.edgeP[q][0][i0 + lane] = lane_transpose_sum(f, lane);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = w_out * fmaxf(fmaf(zw[4 + j - 1], kUnscale, y[j]), 0.f);
+                    S.edgeP[q][1][i0 + lane] = lane_transpose_sum(f, lane);
+                }
+            }
+            if (!is_edge) publish_activations(g);
+        };
+
+        // ---- after the edge readout of group g: face flux, finite-volume update, field solve, write-out ----
+        auto finish_step = [&](int g, int step) {
+            const int myrow = (tid < kGroupRows) ? g * kGroupRows + tid : -1;
+            named_sync(1, kEpiThreads);                        // edgeP of this group complete
+            float n_new = 0.f, u_new = 0.f;
+            if (myrow >= 0) {
+                // face flux (src/hybrid_solver.py:45-48): edges (row j, col j+1) and (row j+1, col j)
+                const int j = myrow, jn = S.nextRow[j];
+                const float b2 = S.small[SmallParams::b_e2];
+                const float fwd = ((S.edgeP[0][0][j] + S.edgeP[1][0][j]) + (S.edgeP[2][0][j] + S.edgeP[3][0][j])) + b2;
+                const float bwd = ((S.edgeP[0][1][jn] + S.edgeP[1][1][jn]) + (S.edgeP[2][1][jn] + S.edgeP[3][1][jn])) + b2;
+                const float face = 0.5f * (fwd + bwd);
+                const int ic = S.rowIC[j], cell = S.rowCell[j];
+                if (a.flux_edges != nullptr && ic >= 0) {
+                    float* fe = a.flux_edges + (size_t)ic * 2 * nx + cell;
+                    fe[0] = fwd;
+                    fe[nx] = bwd;
+                }
+                if (a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
+                S.sF[j] = face;
+            }
+            if (!a.do_update) return;                          // forward only
+            named_sync(1, kEpiThreads);
+            // finite-volume update (src/hybrid_solver.py:51-58)
+            if (myrow >= 0) tile_fv_update(a, T, myrow, n_new, u_new);
+            if (!a.whole_ic) {
+                if (myrow >= 0) tile_store_window_row(a, T, myrow, n_new, u_new);
+                return;
+            }
+            named_sync(1, kEpiThreads);
+            if (myrow >= 0) tile_keep_row(T, myrow, n_new, u_new);
+            named_sync(1, kEpiThreads);
+            // field solve: E = g (*) rho, kRowThreads threads per row (src/baseline_solver.py:59-68)
+            {
+                const int row = g * kGroupRows + tid / kRowThreads, part = tid % kRowThreads;
+                double e = tile_field_partial(T, row, part, kRowThreads, nx);
+#pragma unroll
+                for (int m = 1; m < kRowThreads; m <<= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+                if (part == 0) S.sE[row] = (float)e;
+            }
+            named_sync(1, kEpiThreads);
+            if (myrow >= 0) tile_write_out_row(a, T, myrow, step);
+        };
 
 #ifdef FLUXGNN_TC_TIMING
         long long tc_last__ = clock64();
 #endif
+        // prologue: first tile of both groups
+        for (int g = 0; g < kGroups; ++g) load_rows(g, blockIdx.x);
+        named_sync(1, kEpiThreads);
+        for (int g = 0; g < kGroups; ++g) input_layer(g);
+        TC_TICK(2);
         for (int cta_tile = blockIdx.x; cta_tile < cta_tiles; cta_tile += gridDim.x) {
-            const int tile = cta_tile * kGroups + grp;                 // this group's logical tile
-            const bool tile_ok = tile < a.num_tiles;                   // the last CTA tile may be half empty
-            TC_TICK(0);
-            // ---- row bookkeeping + state load (as in the FP32-pipe kernel) ----------------
-            if (myrow >= 0) tile_load_row(a, T, tile, tile_ok, myrow, lt, row0, kGroupRows);
-            named_sync(bar, kGroupThreads);
-            TC_TICK(1);
-
+            const int next_tile = cta_tile + (int)gridDim.x;
             for (int step = 0; step < a.steps; ++step) {
-                // ---- input MLP (src/flux_gnn.py:49): feature n, this warp's two row chunks ----
-                {
-                    const float w0 = S.small[SmallParams::w_in + 0 * kH + n];
-                    const float w1 = S.small[SmallParams::w_in + 1 * kH + n];
-                    const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
-                    const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
-                    const float b = S.small[SmallParams::b_in + n];
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        const int i0 = row0 + 32 * (cw + kChunkStep * half);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 vn = *reinterpret_cast<const float4*>(&S.sN[i0 + j]);
-                            const float4 vu = *reinterpret_cast<const float4*>(&S.sU[i0 + j]);
-                            const float4 ve = *reinterpret_cast<const float4*>(&S.sE[i0 + j]);
-                            const float4 vx = *reinterpret_cast<const float4*>(&S.sX[i0 + j]);
-                            store_act(i0, j + 0, fmaxf(fmaf(w3, vx.x, fmaf(w2, ve.x, fmaf(w1, vu.x, fmaf(w0, vn.x, b)))), 0.f));
-                            store_act(i0, j + 1, fmaxf(fmaf(w3, vx.y, fmaf(w2, ve.y, fmaf(w1, vu.y, fmaf(w0, vn.y, b)))), 0.f));
-                            store_act(i0, j + 2, fmaxf(fmaf(w3, vx.z, fmaf(w2, ve.z, fmaf(w1, vu.z, fmaf(w0, vn.z, b)))), 0.f));
-                            store_act(i0, j + 3, fmaxf(fmaf(w3, vx.w, fmaf(w2, ve.w, fmaf(w1, vu.w, fmaf(w0, vn.w, b)))), 0.f));
-                        }
-                    }
-                }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(&S.act_ready[grp]);
-                TC_TICK(2);
-
                 for (int layer = 0; layer < layers; ++layer) {
-                    mbar_wait(&S.acc_ready[grp], acc_phase);
-                    acc_phase ^= 1;
-                    tc_fence_after();
-                    TC_TICK(3);
-                    const bool is_edge = (layer == a.L);
-                    const float bias = S.small[(is_edge ? SmallParams::b_e1 : SmallParams::b_upd + layer * kH) + n];
-                    const float w_out = S.small[SmallParams::w_e2 + n];
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        const int i0 = row0 + 32 * (cw + kChunkStep * half);
-                        const int seg0 = (i0 / seg) * seg;
-                        const int cl = (i0 == seg0) ? i0 - 4 + seg : i0 - 4;
-                        const int cr = (i0 + 32 == seg0 + seg) ? i0 + 32 - seg : i0 + 32;
-                        float y[32], zc[32], zl[4], zr[4];
-                        tmem_ld32(tlane + kColY + i0, y);
-                        tmem_ld32(tlane + kColZ + i0, zc);
-                        tmem_ld4(tlane + kColZ + cl, zl);
-                        tmem_ld4(tlane + kColZ + cr, zr);
-                        tc_wait_ld();
-                        float zw[40];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) { zw[t] = zl[t]; zw[36 + t] = zr[t]; }
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) zw[4 + t] = zc[t];
-                        if (!is_edge) {
-                            // h'_i = relu(Y_i + b + mean_{0<|k|<=R} Z_{i+k})   (src/flux_gnn.py:55-60)
-                            // the window sum shares the pair sums pz[t] = Z[t] + Z[t+1] between neighbouring rows
-                            float pz[39];
-                            if constexpr (R >= 2) {
-#pragma unroll
-                                for (int t = 0; t < 39; ++t) pz[t] = zw[t] + zw[t + 1];
-                            }
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int c = 4 + j;                  // window centre in zw
-                                float s;
-                                if constexpr (R == 1) s = zw[c - 1] + zw[c + 1];
-                                else if constexpr (R == 2) s = pz[c - 2] + pz[c + 1];
-                                else if constexpr (R == 3) s = (pz[c - 3] + pz[c + 2]) + (zw[c - 1] + zw[c + 1]);
-                                else s = (pz[c - 4] + pz[c + 3]) + (pz[c - 2] + pz[c + 1]);
-                                store_act(i0, j, fmaxf(fmaf(s, inv_deg, fmaf(y[j], kUnscale, bias)), 0.f));
-                            }
-                        } else {
-                            // edge readout (src/flux_gnn.py:63-66): this feature's term of the two dot products of
-                            // row i -- fwd (row i, col i+1): w2[n] relu(P_i + b1 + Q_{i+1});  bwd (row i, col i-1) --
-                            // summed over the warp's 32 features in registers, over the 4 quadrants in shared memory
-                            float f[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                y[j] = fmaf(y[j], kUnscale, bias);
-                                f[j] = w_out * fmaxf(fmaf(zw[4 + j + 1], kUnscale, y[j]), 0.f);
-                            }
-                            S.edgeP[q][0][i0 + lane] = lane_transpose_sum(f, lane);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = w_out * fmaxf(fmaf(zw[4 + j - 1], kUnscale, y[j]), 0.f);
-                            S.edgeP[q][1][i0 + lane] = lane_transpose_sum(f, lane);
+                    for (int g = 0; g < kGroups; ++g) {
+                        mbar_wait(&S.acc_ready[g], acc_phase);
+                        tc_fence_after();
+                        TC_TICK(3);
+                        layer_epilogue(g, layer);
+                        TC_TICK(layer < a.L ? 4 : 5);
+                        if (layer < a.L) continue;
+                        finish_step(g, step);
+                        TC_TICK(8);
+                        // group g moves on to its next step / next tile while the other group's products run
+                        if (step + 1 < a.steps) {
+                            named_sync(1, kEpiThreads);        // the new state of every row is in shared memory
+                            input_layer(g);
+                        } else if (next_tile < cta_tiles) {
+                            named_sync(1, kEpiThreads);        // nobody reads this group's rows any more
+                            load_rows(g, next_tile);
+                            named_sync(1, kEpiThreads);
+                            input_layer(g);
                         }
+                        TC_TICK(2);
                     }
-                    if (!is_edge) {
-                        tc_fence_before();
-                        fence_proxy_async();
-                        mbar_arrive(&S.act_ready[grp]);
-                    }
-                    TC_TICK(is_edge ? 5 : 4);
+                    acc_phase ^= 1;
                 }
-                named_sync(bar, kGroupThreads);
-                TC_TICK(6);
-
-                // ---- per row: face flux (src/hybrid_solver.py:45-48) ----------------------------
-                float n_new = 0.f, u_new = 0.f;
-                if (myrow >= 0) {
-                    const int j = myrow, jn = S.nextRow[j];
-                    const float b2 = S.small[SmallParams::b_e2];
-                    const float fwd = ((S.edgeP[0][0][j] + S.edgeP[1][0][j]) + (S.edgeP[2][0][j] + S.edgeP[3][0][j])) + b2;
-                    const float bwd = ((S.edgeP[0][1][jn] + S.edgeP[1][1][jn]) + (S.edgeP[2][1][jn] + S.edgeP[3][1][jn])) + b2;
-                    const float face = 0.5f * (fwd + bwd);       // edges (row j, col j+1) and (row j+1, col j)
-                    const int ic = S.rowIC[j], cell = S.rowCell[j];
-                    if (a.flux_edges != nullptr && ic >= 0) {
-                        float* fe = a.flux_edges + (size_t)ic * 2 * nx + cell;
-                        fe[0] = fwd;
-                        fe[nx] = bwd;
-                    }
-                    if (a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
-                    S.sF[j] = face;
-                }
-                if (!a.do_update) continue;
-                named_sync(bar, kGroupThreads);
-                TC_TICK(7);
-
-                // ---- finite-volume update (src/hybrid_solver.py:51-58) ----
-                if (myrow >= 0) tile_fv_update(a, T, myrow, n_new, u_new);
-                if (!a.whole_ic) {
-                    if (myrow >= 0) tile_store_window_row(a, T, myrow, n_new, u_new);
-                    continue;
-                }
-                named_sync(bar, kGroupThreads);
-                if (myrow >= 0) tile_keep_row(T, myrow, n_new, u_new);
-                named_sync(bar, kGroupThreads);
-                TC_TICK(8);
-                // ---- field solve: E = g (*) rho, two threads per row (src/baseline_solver.py:59-68) ----
-                {
-                    const int row = row0 + (lt >> 1), part = lt & 1;
-                    double e = tile_field_partial(T, row, part, 2, nx);
-                    e += __shfl_xor_sync(0xffffffffu, e, 1);
-                    if (part == 0) S.sE[row] = (float)e;
-                }
-                named_sync(bar, kGroupThreads);
-                TC_TICK(9);
-                if (myrow >= 0) tile_write_out_row(a, T, myrow, step);
-                TC_TICK(10);
-            }   // steps
-            named_sync(bar, kGroupThreads);
-        }       // tiles
+            }
+        }
     }
 
     tc_fence_before();
