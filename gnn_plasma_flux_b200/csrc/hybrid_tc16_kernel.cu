@@ -50,11 +50,12 @@ constexpr int kProducerWarp = 16, kMmaWarp = 17;
 constexpr int kThreads = kEpiThreads + 64;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColZ = 0, kColY = 256;
-constexpr int kActBlockBytes = kRows * 128;       // [256 rows][64 k] 16-bit, K-major SW128: 32 KiB
+constexpr int kActBlockBytes = kRows * 128;       // half of one part of the activations: 32 KiB
 constexpr float kUnscale = 1.0f / kTc16WeightScale;
 
 struct __align__(1024) Smem {
-    unsigned char act[2][2][kActBlockBytes];      // [part][k-block]: the UMMA B operand (activations)
+    unsigned char act[2][2][kActBlockBytes];      // [part]: 64 KiB of activations, the MN-major UMMA B operand
+                                                  //   ([64-row block][k atom][1024 B], see umma_desc_b_mn)
     unsigned char Ws[kStages][kTc16UnitBytes];    // streamed weight operand images (UMMA A operand)
     float small[SmallParams::count];
     float sN[kRows], sU[kRows], sE[kRows], sX[kRows];
@@ -95,9 +96,23 @@ struct Ring {
     }
 };
 
-// kind::f16 instruction descriptor: fp32 accumulate, A and B K-major, fmt 0 = fp16, 1 = bf16.
+// kind::f16 instruction descriptor: fp32 accumulate, A (weights) K-major, B (activations) MN-major (bit 16),
+// fmt 0 = fp16, 1 = bf16.
 __device__ __forceinline__ uint32_t idesc_f16(int M, int N, int fmt) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// The activations are the MN-major B operand: for one k the rows (N) are contiguous, so the thread that owns
+// feature k = TMEM lane k stores 8 consecutive rows of it with ONE 16-byte store (K-major needed 2-byte
+// stores 128 bytes apart: 64 per 32 rows and part, and the MIO queue throttled the epilogue).
+// Canonical MN-major SWIZZLE_128B layout: atoms of [8 k][64 rows] 16-bit = 1024 bytes (k row = 128 bytes, its
+// eight 16-byte chunks XOR-swizzled with k % 8); atoms of consecutive k groups 1024 bytes apart (SBO), 64-row
+// blocks kActRowBlockBytes apart (LBO).  [part][64-row block (4)][k atom (16)][1024 B].
+constexpr int kActRowBlockBytes = 16 * 1024;      // one 64-row block: 128 k x 64 rows x 2 bytes
+__device__ __forceinline__ uint64_t umma_desc_b_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(kActRowBlockBytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -112,36 +127,24 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         : "memory");
 }
 
-// store the low 16 bits of a 32-bit register (no repacking instruction)
-// store the low 16 bits of a 32-bit register (no repacking instruction)
-// one lane of the (converged) warp
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(pred));
-    return pred != 0;
+// 8 consecutive rows of one feature -> one 16-byte chunk of hi parts (and one of lo parts)
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
-    asm volatile("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(addr), "r"(v) : "memory");
-}
-
-// value -> (hi, lo) 16-bit parts.  kBf16 = false: fp16, true: bfloat16.
 template <bool kBf16>
-__device__ __forceinline__ void split16(float h, uint32_t& hi, uint32_t& lo) {
+__device__ __forceinline__ void pack_pair(float h0, float h1, uint32_t& hi, uint32_t& lo) {
     if constexpr (kBf16) {
-        const __nv_bfloat16 a = __float2bfloat16_rn(h);
-        hi = __bfloat16_as_ushort(a);
-        lo = __bfloat16_as_ushort(__float2bfloat16_rn(h - __bfloat162float(a)));
+        const __nv_bfloat162 a = __floats2bfloat162_rn(h0, h1);
+        const float2 af = __bfloat1622float2(a);
+        const __nv_bfloat162 b = __floats2bfloat162_rn(h0 - af.x, h1 - af.y);
+        hi = *reinterpret_cast<const uint32_t*>(&a);
+        lo = *reinterpret_cast<const uint32_t*>(&b);
     } else {
-        const __half a = __float2half_rn(h);
-        hi = __half_as_ushort(a);
-        lo = __half_as_ushort(__float2half_rn(h - __half2float(a)));
+        const __half2 a = __floats2half2_rn(h0, h1);
+        const float2 af = __half22float2(a);
+        const __half2 b = __floats2half2_rn(h0 - af.x, h1 - af.y);
+        hi = *reinterpret_cast<const uint32_t*>(&a);
+        lo = *reinterpret_cast<const uint32_t*>(&b);
     }
 }
 
@@ -234,11 +237,12 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         const uint32_t idesc = idesc_f16(128, kGroupRows, kBf16 ? 1 : 0);
         const bool leader = elect_one_lane();
         const uint64_t ws_desc0 = umma_desc_sw128(smem_u32(S.Ws[0]));
-        const uint64_t hi_desc0 = umma_desc_sw128(smem_u32(S.act[0][0]));
-        const uint64_t lo_desc0 = umma_desc_sw128(smem_u32(S.act[1][0]));
+        const uint64_t hi_desc0 = umma_desc_b_mn(smem_u32(S.act[0][0]));
+        const uint64_t lo_desc0 = umma_desc_b_mn(smem_u32(S.act[1][0]));
         constexpr uint64_t kStageStep = kTc16UnitBytes >> 4;          // descriptor address field counts 16-byte units
-        constexpr uint64_t kKbStep = kActBlockBytes >> 4;
-        constexpr uint64_t kGroupStep = (uint64_t)(kGroupRows * 128) >> 4;
+        constexpr uint64_t kKbStep = (uint64_t)(8 * 1024) >> 4;        // 64 k = 8 atoms
+        constexpr uint64_t kKsStep = (uint64_t)(2 * 1024) >> 4;        // 16 k = 2 atoms per instruction
+        constexpr uint64_t kGroupStep = (uint64_t)((kGroupRows / 64) * kActRowBlockBytes) >> 4;
         Ring r;
         uint32_t act_phase = 0;
         for (long long rep = 0; rep < (long long)my_tiles * a.steps; ++rep) {
@@ -261,8 +265,8 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                         if (leader) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {          // 32 bytes of K per instruction = 2 address units
-                                umma_f16(d, wd + 2 * ks, bhi + kb * kKbStep + 2 * ks, idesc, (kb | ks) != 0);
-                                if (PARTS == 2) umma_f16(d, wd + 2 * ks, blo + kb * kKbStep + 2 * ks, idesc, 1);
+                                umma_f16(d, wd + 2 * ks, bhi + kb * kKbStep + ks * kKsStep, idesc, (kb | ks) != 0);
+                                if (PARTS == 2) umma_f16(d, wd + 2 * ks, blo + kb * kKbStep + ks * kKsStep, idesc, 1);
                             }
                             umma_commit(&S.empty[r.stage]);
                         }
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                             if (leader) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)
-                                    umma_f16(d, wd + 2 * ks, bhi + kb * kKbStep + 2 * ks, idesc, 1);
+                                    umma_f16(d, wd + 2 * ks, bhi + kb * kKbStep + ks * kKsStep, idesc, 1);
                                 umma_commit(&S.empty[r.stage]);
                             }
                             r.advance();
@@ -303,19 +307,19 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         const int seg = a.whole_ic ? nx : kGroupRows;         // periodic segment inside the group (multiple of 32)
         uint32_t acc_phase = 0;
 
-        // activation element (row i, feature n): k-block n / 64, 16-byte chunk ((n % 64) / 8) ^ (i & 7), 2 bytes
-        const int kk = n & 63;
-        const uint32_t act_hi = smem_u32(S.act[0][0]) + (uint32_t)((n >> 6) * kActBlockBytes + (kk & 7) * 2);
+        // rows 8c .. 8c+7 (c = chunk inside a 64-row block) of feature n: one 16-byte chunk at
+        //   (row block) * kActRowBlockBytes + (n / 8) * 1024 + (n % 8) * 128 + ((c ^ (n % 8)) << 4)
+        const uint32_t act_feat = smem_u32(S.act[0][0]) + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128);
         const uint32_t act_lo_off = (uint32_t)(2 * kActBlockBytes);       // S.act[1] - S.act[0]
-        uint32_t act_x[8];
+        // store_rows8: h[0..7] = rows i0 + 8c .. of this feature (i0 a multiple of 32, c = 0..3)
+        auto store_rows8 = [&](int i0, int c, const float (&h)[8]) {
+            const uint32_t chunk = (uint32_t)(((i0 >> 5) & 1) * 4 + c);
+            const uint32_t addr = act_feat + (uint32_t)(i0 >> 6) * kActRowBlockBytes + ((chunk ^ (uint32_t)(n & 7)) << 4);
+            uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) act_x[v] = act_hi + ((uint32_t)((kk >> 3) ^ v) << 4);
-        auto store_act = [&](int i0, int j, float h) {        // row i0 + j; j compile-time after unrolling
-            const uint32_t addr = act_x[j & 7] + (uint32_t)(i0 + j) * 128;
-            uint32_t hi, lo;
-            split16<kBf16>(h, hi, lo);
-            sts_u16(addr, hi);
-            if (PARTS == 2) sts_u16(addr + act_lo_off, lo);
+            for (int t = 0; t < 4; ++t) pack_pair<kBf16>(h[2 * t], h[2 * t + 1], hi[t], lo[t]);
+            sts_u128(addr, hi[0], hi[1], hi[2], hi[3]);
+            if (PARTS == 2) sts_u128(addr + act_lo_off, lo[0], lo[1], lo[2], lo[3]);
         };
         auto publish_activations = [&](int g) {               // generic-proxy stores -> visible to the UMMAs of group g
             tc_fence_before();
@@ -341,15 +345,20 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
             for (int half = 0; half < kChunksPerWarp; ++half) {
                 const int i0 = g * kGroupRows + 32 * (cw + 4 * half);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 vn = *reinterpret_cast<const float4*>(&S.sN[i0 + j]);
-                    const float4 vu = *reinterpret_cast<const float4*>(&S.sU[i0 + j]);
-                    const float4 ve = *reinterpret_cast<const float4*>(&S.sE[i0 + j]);
-                    const float4 vx = *reinterpret_cast<const float4*>(&S.sX[i0 + j]);
-                    store_act(i0, j + 0, fmaxf(fmaf(w3, vx.x, fmaf(w2, ve.x, fmaf(w1, vu.x, fmaf(w0, vn.x, b)))), 0.f));
-                    store_act(i0, j + 1, fmaxf(fmaf(w3, vx.y, fmaf(w2, ve.y, fmaf(w1, vu.y, fmaf(w0, vn.y, b)))), 0.f));
-                    store_act(i0, j + 2, fmaxf(fmaf(w3, vx.z, fmaf(w2, ve.z, fmaf(w1, vu.z, fmaf(w0, vn.z, b)))), 0.f));
-                    store_act(i0, j + 3, fmaxf(fmaf(w3, vx.w, fmaf(w2, ve.w, fmaf(w1, vu.w, fmaf(w0, vn.w, b)))), 0.f));
+                for (int c = 0; c < 4; ++c) {
+                    float h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 4) {
+                        const float4 vn = *reinterpret_cast<const float4*>(&S.sN[i0 + 8 * c + j]);
+                        const float4 vu = *reinterpret_cast<const float4*>(&S.sU[i0 + 8 * c + j]);
+                        const float4 ve = *reinterpret_cast<const float4*>(&S.sE[i0 + 8 * c + j]);
+                        const float4 vx = *reinterpret_cast<const float4*>(&S.sX[i0 + 8 * c + j]);
+                        h[j + 0] = fmaxf(fmaf(w3, vx.x, fmaf(w2, ve.x, fmaf(w1, vu.x, fmaf(w0, vn.x, b)))), 0.f);
+                        h[j + 1] = fmaxf(fmaf(w3, vx.y, fmaf(w2, ve.y, fmaf(w1, vu.y, fmaf(w0, vn.y, b)))), 0.f);
+                        h[j + 2] = fmaxf(fmaf(w3, vx.z, fmaf(w2, ve.z, fmaf(w1, vu.z, fmaf(w0, vn.z, b)))), 0.f);
+                        h[j + 3] = fmaxf(fmaf(w3, vx.w, fmaf(w2, ve.w, fmaf(w1, vu.w, fmaf(w0, vn.w, b)))), 0.f);
+                    }
+                    store_rows8(i0, c, h);
                 }
             }
             publish_activations(g);
@@ -386,14 +395,19 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                         for (int t = 0; t < 39; ++t) pz[t] = zw[t] + zw[t + 1];
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = 4 + j;                  // window centre in zw
-                        float sum;
-                        if constexpr (R == 1) sum = zw[c - 1] + zw[c + 1];
-                        else if constexpr (R == 2) sum = pz[c - 2] + pz[c + 1];
-                        else if constexpr (R == 3) sum = (pz[c - 3] + pz[c + 2]) + (zw[c - 1] + zw[c + 1]);
-                        else sum = (pz[c - 4] + pz[c + 3]) + (pz[c - 2] + pz[c + 1]);
-                        store_act(i0, j, fmaxf(fmaf(sum, inv_deg, fmaf(y[j], kUnscale, bias)), 0.f));
+                    for (int ch = 0; ch < 4; ++ch) {
+                        float h[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int j = 8 * ch + jj, c = 4 + j;     // window centre in zw
+                            float sum;
+                            if constexpr (R == 1) sum = zw[c - 1] + zw[c + 1];
+                            else if constexpr (R == 2) sum = pz[c - 2] + pz[c + 1];
+                            else if constexpr (R == 3) sum = (pz[c - 3] + pz[c + 2]) + (zw[c - 1] + zw[c + 1]);
+                            else sum = (pz[c - 4] + pz[c + 3]) + (pz[c - 2] + pz[c + 1]);
+                            h[jj] = fmaxf(fmaf(sum, inv_deg, fmaf(y[j], kUnscale, bias)), 0.f);
+                        }
+                        store_rows8(i0, ch, h);
                     }
                 } else {
                     // edge readout (src/flux_gnn.py:63-66): this feature's term of the two dot products of

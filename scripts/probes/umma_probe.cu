@@ -20,7 +20,7 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) { return (1u << 4
 
 constexpr int kReps = 8, kUnits = 16;      // 16 units of 4 k-steps per repetition (the tile kernel's weight units)
 
-template <bool kF16, int M, int N, int kAcc, bool kCommitPerUnit, bool kUniform>
+template <bool kF16, int M, int N, int kAcc, bool kCommitPerUnit, bool kUniform, bool kBmn = false>
 __global__ void __launch_bounds__(128, 1) probe(long long* out) {
     extern __shared__ __align__(1024) unsigned char sm[];
     __shared__ uint64_t bar, bar2;
@@ -30,8 +30,14 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out) {
     if (threadIdx.x < 32) tmem_alloc(&tmem_base, 512);
     tc_fence_before(); __syncthreads(); tc_fence_after();
     fence_proxy_async();
-    const uint32_t idesc = kF16 ? idesc_f16(M, N) : umma_idesc_tf32(M, N);
-    const uint64_t a0 = umma_desc_sw128(smem_u32(sm)), b0 = umma_desc_sw128(smem_u32(sm + 64 * 1024));
+    const uint32_t idesc = (kF16 ? idesc_f16(M, N) : umma_idesc_tf32(M, N)) | (kBmn ? (1u << 16) : 0u);
+    // kBmn: B operand MN-major (rows contiguous), SWIZZLE_128B atoms of [8 k][64 rows], LBO 16 KiB, SBO 1 KiB
+    const uint32_t baddr = smem_u32(sm + 64 * 1024);
+    const uint64_t a0 = umma_desc_sw128(smem_u32(sm));
+    const uint64_t b0 = kBmn ? ((uint64_t)((baddr & 0x3FFFF) >> 4) | ((uint64_t)(16384 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+                                ((uint64_t)1 << 46) | ((uint64_t)2 << 61))
+                             : umma_desc_sw128(baddr);
+    constexpr uint64_t kBStep = kBmn ? (2048 >> 4) : 2;
     auto body = [&](bool leader) {
         const uint32_t tm = tmem_base;
         for (int r = 0; r < kReps; ++r) {
@@ -42,8 +48,8 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out) {
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        if (kF16) umma_f16(d, ad + 2 * ks, b0 + 2 * ks, idesc, 1);
-                        else umma_tf32(d, ad + 2 * ks, b0 + 2 * ks, idesc, 1);
+                        if (kF16) umma_f16(d, ad + 2 * ks, b0 + kBStep * ks, idesc, 1);
+                        else umma_tf32(d, ad + 2 * ks, b0 + kBStep * ks, idesc, 1);
                     }
                     if (kCommitPerUnit) umma_commit(&bar2);          // stage-release style commit nobody waits on
                 }
@@ -70,9 +76,9 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out) {
     if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
 }
 
-template <bool kF16, int M, int N, int kAcc, bool kCommitPerUnit, bool kUniform>
+template <bool kF16, int M, int N, int kAcc, bool kCommitPerUnit, bool kUniform, bool kBmn = false>
 static void run(const char* name, long long* out) {
-    auto k = probe<kF16, M, N, kAcc, kCommitPerUnit, kUniform>;
+    auto k = probe<kF16, M, N, kAcc, kCommitPerUnit, kUniform, kBmn>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaMemset(out, 0, 8);
     k<<<148, 128, 200 * 1024>>>(out);
@@ -95,6 +101,8 @@ int main() {
     run<true, 128, 128, 1, false, true>("f16  M=128 N=128, one accumulator chain", out);
     run<true, 128, 128, 2, true, true>("f16  M=128 N=128, commit after every 4 UMMAs", out);
     run<true, 128, 256, 2, true, true>("f16  M=128 N=256, commit after every 4 UMMAs", out);
+    run<true, 128, 128, 2, false, true, true>("f16  M=128 N=128, B operand MN-major", out);
+    run<true, 128, 256, 2, false, true, true>("f16  M=128 N=256, B operand MN-major", out);
     run<false, 128, 256, 2, false, true>("tf32 M=128 N=256, uniform issue", out);
     run<false, 128, 128, 2, false, true>("tf32 M=128 N=128, uniform issue", out);
     run<true, 128, 256, 2, false, false>("f16  M=128 N=256, issued inside `if (threadIdx.x == 0)`", out);
