@@ -20,11 +20,11 @@ L.fluxgnn_debug_tc_timing(None, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); sol.rollout(st, steps); e1.record(); torch.cuda.synchronize()
 L.fluxgnn_debug_tc_timing(buf, 0)
-names = ["tile loop", "state load", "input MLP", "wait UMMA", "layer epilogue", "edge epilogue", "edge reduce", "face flux",
-         "FV update", "field solve", "stores"]
+# slots used by hybrid_tc16_kernel.cu (TC_TICK): 2 input layer (incl. next-tile load), 3 waiting for a group's UMMAs,
+# 4 message-passing epilogues, 5 edge-readout epilogues, 8 finite-volume tail (face flux, update, field solve, write-out)
+names = {2: "input layer", 3: "wait UMMA", 4: "layer epilogues", 5: "edge readout", 8: "finite-volume tail"}
 tiles = (B * nx // 256 + 147) // 148     # assumes a 148-CTA grid
-tot = sum(buf[:11])
+tot = sum(buf[i] for i in names)
 print(f"{prec}: {e0.elapsed_time(e1) / steps:.3f} ms/step; CTA 0: {tiles} tiles x {steps} steps, {tot / (tiles * steps):.0f} clk per tile-step")
-for i, n in enumerate(names):
-    if i == 11: print('  -- UMMA issuer thread --')
+for i, n in names.items():
     print(f"  {n:16s} {buf[i] / (tiles * steps):9.0f} clk/tile-step  {100 * buf[i] / tot:5.1f} %")
