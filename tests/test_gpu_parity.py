@@ -480,6 +480,20 @@ def test_tc16_single_group_path(model, weights, monkeypatch, nx, radius):
     assert torch.equal(one, two)                 # same arithmetic per cell, only the tiling differs
 
 
+@pytest.mark.parametrize("B,nx", [(1, 64), (3, 64), (5, 32), (1, 128), (3, 128), (1, 1024)])
+def test_tc16_ragged_batches(model, weights, B, nx):
+    """Batches that leave a CTA tile partly (or its second group entirely) empty: 1 or 3 ICs of 64 cells
+    in a 256-row tile, one 128-cell IC, a single IC in window mode."""
+    dt = 3e-4 if nx > 128 else 1e-3
+    grid = P.Grid(nx=nx, dt=dt)
+    ics = np.stack([P.stable_initial_condition(grid, s) for s in range(B)])
+    ref = batched.hybrid_run(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, 2, radius=2).numpy()
+    sol = make_solver(model, nx, dt, graph_radius=2, precision="fp16x3")
+    out, traj = sol.rollout(torch.from_numpy(ics).cuda(), 2, record_every=1)
+    assert P.rel_err(out.cpu().numpy(), ref).max() <= 2 * STEP_TOL
+    assert torch.equal(traj[-1], out)
+
+
 def test_tc_rejects_unsupported_shapes(model):
     from gnn_plasma_flux_b200 import _lib
     with pytest.raises(_lib.FluxGNNError):                                       # nx=40: no silent fallback
