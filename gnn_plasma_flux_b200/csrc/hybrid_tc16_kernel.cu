@@ -1,7 +1,7 @@
 // Tensor-core variant of the fused hybrid step with 16-bit operands and 256-row tiles
 // (sm_100a: tcgen05.mma kind::f16 + TMEM + bulk-copy TMA).
 //
-// Shape (scripts/probes/umma_probe.cu, profiles/r1_n_umma_probe.txt): with a tight, warp-uniform issue
+// Shape (scripts/probes/umma_probe.cu, profiles/r1_p_umma_probe.txt): with a tight, warp-uniform issue
 // loop one tcgen05.mma of M = 128 costs 128 clk at N = 256 and 64 clk at N = 128 for a 32-byte K step
 // -- both at the pipe's peak (8.1 kflop/clk/SM for 16-bit operands, half of that for TF32) -- but
 // 48 clk at N = 64 (66 %) and the same time at M = 64 (50 %).  So 16-bit operands (K = 16 per
@@ -22,15 +22,16 @@
 //   "fp16"  : D = w0 h0 (one product, 2x the TF32 rate; same 11-bit operands as plain tf32)
 //   "bf16"  : one product with bfloat16 operands (8 significant bits; loosest tolerance, widest range)
 //
-// Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quadrant = warp % 4, two 32-row chunks each),
+// Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quadrant = warp % 4, 32-row chunk = warp / 4),
 // warp 16 weight producer, warp 17 TMEM allocator + UMMA issuer.
 //
 // kSplit: the two 128-row halves of a CTA tile are independent LOGICAL tiles -- different ICs (nx <= 128)
-// or two windows with their own halos (nx > 128) -- and run as two groups of 8 epilogue warps, each
-// with its own barriers; the issuer alternates between them with N = 128 instructions, so while one
-// half is in its epilogue (or in the finite-volume / field-solve tail) the tensor pipe works on the
-// other.  N = 128 instructions are as efficient as N = 256 ones, so the split costs no tensor time.
-// Only very wide receptive fields (halo > 24 cells) keep one 256-row window per CTA (api.cu, plan_tiles).
+// or two windows with their own halos (nx > 128) -- i.e. two GROUPS with their own barriers and their
+// own columns of the accumulators.  The issuer alternates between them with N = 128 instructions and
+// the 16 epilogue warps serve whichever group is ready, so while one half is in its epilogue (or in
+// the finite-volume / field-solve tail) the tensor pipe works on the other.  N = 128 instructions are
+// as efficient as N = 256 ones, so the split costs no tensor time.  Only very wide receptive fields
+// (halo > 24 cells) keep one 256-row window per CTA (api.cu, plan_tiles).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -50,11 +51,11 @@ constexpr int kProducerWarp = 16, kMmaWarp = 17;
 constexpr int kThreads = kEpiThreads + 64;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColZ = 0, kColY = 256;
-constexpr int kActBlockBytes = kRows * 128;       // half of one part of the activations: 32 KiB
+constexpr int kActPartBytes = kRows * 128 * 2;    // one part (hi or lo) of the activations: 256 rows x 128 k x 2 B
 constexpr float kUnscale = 1.0f / kTc16WeightScale;
 
 struct __align__(1024) Smem {
-    unsigned char act[2][2][kActBlockBytes];      // [part]: 64 KiB of activations, the MN-major UMMA B operand
+    unsigned char act[2][kActPartBytes];          // [part]: 64 KiB of activations, the MN-major UMMA B operand
                                                   //   ([64-row block][k atom][1024 B], see umma_desc_b_mn)
     unsigned char Ws[kStages][kTc16UnitBytes];    // streamed weight operand images (UMMA A operand)
     float small[SmallParams::count];
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         const uint32_t idesc = idesc_f16(128, kGroupRows, kBf16 ? 1 : 0);
         const bool leader = elect_one_lane();
         const uint64_t ws_desc0 = umma_desc_sw128(smem_u32(S.Ws[0]));
-        const uint64_t hi_desc0 = umma_desc_b_mn(smem_u32(S.act[0][0]));
-        const uint64_t lo_desc0 = umma_desc_b_mn(smem_u32(S.act[1][0]));
+        const uint64_t hi_desc0 = umma_desc_b_mn(smem_u32(S.act[0]));
+        const uint64_t lo_desc0 = umma_desc_b_mn(smem_u32(S.act[1]));
         constexpr uint64_t kStageStep = kTc16UnitBytes >> 4;          // descriptor address field counts 16-byte units
         constexpr uint64_t kKbStep = (uint64_t)(8 * 1024) >> 4;        // 64 k = 8 atoms
         constexpr uint64_t kKsStep = (uint64_t)(2 * 1024) >> 4;        // 16 k = 2 atoms per instruction
@@ -309,8 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
 
         // rows 8c .. 8c+7 (c = chunk inside a 64-row block) of feature n: one 16-byte chunk at
         //   (row block) * kActRowBlockBytes + (n / 8) * 1024 + (n % 8) * 128 + ((c ^ (n % 8)) << 4)
-        const uint32_t act_feat = smem_u32(S.act[0][0]) + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128);
-        const uint32_t act_lo_off = (uint32_t)(2 * kActBlockBytes);       // S.act[1] - S.act[0]
+        const uint32_t act_feat = smem_u32(S.act[0]) + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128);
+        const uint32_t act_lo_off = (uint32_t)kActPartBytes;              // S.act[1] - S.act[0]
         // store_rows8: h[0..7] = rows i0 + 8c .. of this feature (i0 a multiple of 32, c = 0..3)
         auto store_rows8 = [&](int i0, int c, const float (&h)[8]) {
             const uint32_t chunk = (uint32_t)(((i0 >> 5) & 1) * 4 + c);
