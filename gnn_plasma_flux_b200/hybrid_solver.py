@@ -93,9 +93,11 @@ class HybridSolver:
         dev = torch.device(self.device)
         state = state.to(device=dev, dtype=torch.float32).contiguous()
         key = (tuple(state.shape), chunk, self.precision, self.graph_radius)
+        packed = self.model.packed_weights(_lib.weight_layout(self.precision))  # pack outside the capture
         entry = self._graphs.get(key)
+        if entry is not None and entry[3] is not packed:
+            entry = None                    # the weights were repacked: the captured graphs point at the old buffer
         if entry is None:
-            self.model.packed_weights(_lib.weight_layout(self.precision))      # pack outside the capture
             base.grid.tables(dev)
             with torch.cuda.device(dev):
                 a, b = torch.empty_like(state), torch.empty_like(state)
@@ -111,9 +113,9 @@ class HybridSolver:
                             self.rollout(src, chunk, out=dst)
                         graphs.append(g)
                 torch.cuda.current_stream(dev).wait_stream(side)
-            entry = (a, b, graphs)
+            entry = (a, b, graphs, packed)  # keeps the packed weights the graphs read alive
             self._graphs[key] = entry
-        a, b, graphs = entry
+        a, b, graphs, _ = entry
         a.copy_(state)
         reps, rest = divmod(n_steps, chunk)
         for i in range(reps):

@@ -264,6 +264,18 @@ def test_graphed_window_rollout_is_bit_identical(model, precision):
         got = sol.rollout_graphed(ics, 47, chunk=10)
         assert torch.equal(got, ref)
     assert torch.isfinite(got).all()
+    if precision == "fp32":
+        # changing a parameter repacks the weights: the cached graphs must be re-captured, not replayed
+        saved = model.edge_mlp[2].bias.detach().clone()
+        with torch.no_grad():
+            model.edge_mlp[2].bias.add_(0.25)
+        try:
+            ref2, _ = sol.rollout(ics, 47)
+            got2 = sol.rollout_graphed(ics, 47, chunk=10)
+            assert torch.equal(got2, ref2) and not torch.equal(got2, got)
+        finally:
+            with torch.no_grad():
+                model.edge_mlp[2].bias.copy_(saved)             # bit-exact restore for the tests that follow
 
 
 def test_synthetic_inputs_match_oracle_recipe(weights, built_lib):
