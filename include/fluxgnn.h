@@ -138,8 +138,8 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers,
  *   FLUXGNN_TC_TF32X3  h and W are split into two TF32 parts and three products are
  *                      accumulated in fp32: fp32-level accuracy (same parity gates as
  *                      fluxgnn_hybrid_rollout).
- *   FLUXGNN_TC_TF32    one TF32 product: ~1e-3 relative flux error, for throughput
- *                      studies only (tolerance stated in DESIGN.md).
+ *   FLUXGNN_TC_TF32    one TF32 product: ~3e-4 relative flux error (tolerances and measured
+ *                      values in DESIGN.md section 6).
  * packed_tc comes from fluxgnn_pack_weights_tc (same inputs as fluxgnn_pack_weights;
  * the stream holds pre-swizzled UMMA operand images, hi and lo parts).
  * Supported: radius <= 4; nx in {32, 64, 128} or nx > 128; other shapes -> FLUXGNN_EUNSUP

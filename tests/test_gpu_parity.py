@@ -395,10 +395,10 @@ def test_full_size_c3_per_gpu_properties(model, weights, precision):
 
 # ----------------------------------------------------------------------------- tensor-core path
 TF32_STEP_TOL = 1e-5          # plain TF32: state-level tolerance per step (flux error ~1e-3 enters as c*dF)
-TF32_FLUX_TOL = 2e-2          # plain TF32: relative error of the GNN flux itself
+TF32_FLUX_TOL = 2e-3          # plain TF32 / fp16 (11-bit operands): relative error of the GNN flux itself (measured 2-3e-4)
 TF32X3_FLUX_TOL = 2e-5        # 3xTF32 / 3xFP16 split: flux error at fp32 rounding level
 BF16_STEP_TOL = 1e-4          # plain bf16 (8-bit operands): state-level tolerance per step
-BF16_FLUX_TOL = 1e-1          # plain bf16: relative error of the GNN flux itself
+BF16_FLUX_TOL = 1e-2          # plain bf16: relative error of the GNN flux itself (measured ~2e-3)
 SPLIT_MODES = ("tf32x3", "fp16x3")                      # fp32-accurate: same gates as the fp32 kernel
 TC_MODES = ["fp16x3", "fp16", "bf16", "tf32x3", "tf32"]
 
@@ -470,7 +470,7 @@ def test_tc_long_rollout_1000_steps(model):
             assert (vs64 <= np.maximum(1e-4, 2.0 * floor)).all()
             assert (vs32 <= np.maximum(1e-4, 3.0 * floor)).all()
         else:
-            assert (vs32 <= (2e-2 if precision == "bf16" else 2e-3)).all()       # documented looser tolerances
+            assert (vs32 <= (2e-3 if precision == "bf16" else 1e-3)).all()       # documented looser tolerances (measured 4e-4 / 1.3e-4)
         mass0 = g6["ics"][:, 0].astype(np.float64).sum(-1)
         assert np.abs(final[:, 0].astype(np.float64).sum(-1) - mass0).max() <= 1000 * 64 * np.finfo(np.float32).eps
 
