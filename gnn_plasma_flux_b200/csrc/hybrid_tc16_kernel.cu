@@ -219,6 +219,9 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     const int layer = lg / kGroups;
                     for (int u = 0; u < kTc16UnitsPerLayer; ++u) {
                         if (PARTS == 1 && (u & 1)) continue;          // one product: no lo units
+#ifdef FLUXGNN_TC_DEBUG_NOSTREAM                              // timing experiment: UMMAs on stale weights, no stream
+                        continue;
+#endif
                         mbar_wait(&S.empty[r.stage], r.phase ^ 1);
                         mbar_arrive_expect_tx(&S.full[r.stage], kTc16UnitBytes);
                         bulk_g2s(S.Ws[r.stage], stream + ((size_t)layer * kTc16UnitsPerLayer + u) * kTc16UnitBytes,
@@ -260,7 +263,9 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     for (int blk = 0; blk < 2; ++blk) {
                         const uint32_t d = tmem + (blk == 0 ? kColZ : kColY) + grp * kGroupRows;
                         // hi weights x (hi [+ lo] activations)
+#ifndef FLUXGNN_TC_DEBUG_NOSTREAM
                         mbar_wait(&S.full[r.stage], r.phase);
+#endif
                         tc_fence_after();
                         uint64_t wd = ws_desc0 + r.stage * kStageStep;
                         if (leader) {
@@ -274,7 +279,9 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                         r.advance();
                         if (PARTS == 2) {
                             // lo weights x hi activations
+#ifndef FLUXGNN_TC_DEBUG_NOSTREAM
                             mbar_wait(&S.full[r.stage], r.phase);
+#endif
                             tc_fence_after();
                             wd = ws_desc0 + r.stage * kStageStep;
                             if (leader) {
