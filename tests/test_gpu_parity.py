@@ -344,7 +344,8 @@ def test_long_rollout_1000_steps(model):
     assert np.abs(massT - mass0).max() <= 1000 * 64 * np.finfo(np.float32).eps
 
 
-def test_full_size_c2_properties(model, weights):
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_full_size_c2_properties(model, weights, precision):
     """BASELINE.json configs[1] shape: 4096 ICs x 64 cells, radius 3.  One step vs the batched
     oracle on every IC, plus size-independent properties: IC-permutation equivariance,
     translation equivariance along the periodic grid is NOT expected (x is a feature), mass conservation."""
@@ -353,7 +354,7 @@ def test_full_size_c2_properties(model, weights):
     base = np.stack([P.stable_initial_condition(grid, s) for s in range(64)])
     ics = np.tile(base, (B // 64, 1, 1))
     ics += (np.random.RandomState(0).randn(B, 1, 1) * 1e-3).astype(np.float32) * np.array([0, 1, 0], np.float32)[None, :, None]
-    sol = make_solver(model, nx, 1e-3, graph_radius=3)
+    sol = make_solver(model, nx, 1e-3, graph_radius=3, precision=precision)
     dev = torch.from_numpy(ics).cuda()
     out, _ = sol.rollout(dev, 1)
     ref = batched.hybrid_step(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, radius=3).numpy()
