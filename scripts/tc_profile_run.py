@@ -1,24 +1,19 @@
-"""Small driver for ncu: a few launches of the tensor-core hybrid step at the C2 shape."""
+"""Small driver for ncu: a few launches of a tensor-core hybrid step at the C2 shape (4096 ICs x 64 cells, radius 3).
+usage: python scripts/tc_profile_run.py [fp16x3|fp16|bf16|tf32x3|tf32]"""
 import os
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gnn_plasma_flux_b200 import FluxGNN, HybridSolver, MODEL_CONFIG   # noqa: E402
-from oracle import ref_port as P                                        # noqa: E402  (inputs only)
+from gnn_plasma_flux_b200 import HybridSolver                                               # noqa: E402
+from gnn_plasma_flux_b200.synthetic import seeded_model, stable_initial_conditions          # noqa: E402
 
-prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
-weights = P.init_weights(0)
-model = FluxGNN(**MODEL_CONFIG)
-model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
-nx, B, r = 64, 4096, 3
-grid = P.Grid(nx=nx, dt=1e-3)
-ics = np.stack([P.stable_initial_condition(grid, s % 50) for s in range(B)])
-sol = HybridSolver(None, r, nx=nx, dt=1e-3, graph_radius=r, model=model.cuda(), precision=prec)
-dev = torch.from_numpy(ics).cuda()
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
+dev = torch.device("cuda", 0)
+sol = HybridSolver(None, 3, nx=64, dt=1e-3, device=dev, graph_radius=3, model=seeded_model(0, dev), precision=prec)
+state = stable_initial_conditions(sol.baseline, 4096, distinct=64)
 for _ in range(5):
-    dev, _ = sol.rollout(dev, 1)
+    state, _ = sol.rollout(state, 1)
 torch.cuda.synchronize()
-print("ok", float(dev.abs().max()))
+print("ok", float(state.abs().max()))
