@@ -29,6 +29,24 @@ def test_header_symbols_exported(built_lib):
     assert built_lib.fluxgnn_abi_version() == _lib.ABI_VERSION
 
 
+def test_precision_codes_match_header(built_lib):
+    """FLUXGNN_TC_* in the header == the precision names the Python classes accept; every mode has a
+    packed-weight layout and a size query that answers without a GPU."""
+    from gnn_plasma_flux_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "fluxgnn.h")).read()
+    codes = {name.lower(): int(val) for name, val in re.findall(r"#define\s+FLUXGNN_TC_([A-Z0-9]+)\s+(\d+)", text)}
+    assert codes == _lib.TC_PRECISIONS
+    for name in ["fp32", *codes]:
+        assert _lib.weight_layout(name) in ("fp32", "tc", "tc16", "tc16_bf16")
+    small = 2048 * 4
+    assert built_lib.fluxgnn_packed_tc16_weight_bytes(4) == small + 5 * 8 * 16384           # 8 units of 16 KiB per layer
+    assert built_lib.fluxgnn_packed_tc_weight_bytes(4) == small + 5 * 16 * 16384
+    assert built_lib.fluxgnn_packed_tc16_weight_bytes(0) == 0
+    rc = built_lib.fluxgnn_pack_weights_tc16(None, None, None, None, None, None, None, None, 4, 2, None, None)
+    assert rc == -1                                               # precision 2 (tf32) has no 16-bit image
+    assert built_lib.fluxgnn_pure_gnn_packed_bytes(64, 3) > 0 and built_lib.fluxgnn_pure_gnn_packed_bytes(48, 3) == 0
+
+
 def test_size_queries(built_lib):
     small, layer = 2048, 2 * 128 * 128
     for L in (1, 4, 8):
