@@ -753,3 +753,28 @@ def test_pinn_vs_reference(built_lib):
     assert P.rel_err(state.cpu().numpy(), g["pinn_rollout10"]).max() <= 1e-4
     single = model(torch.from_numpy(g["ics"][2]).cuda())                       # unbatched [3,nx], as the reference allows
     assert P.rel_err(single.cpu().numpy(), g["pinn_step"][2]).max() <= 1e-5
+
+
+# ----------------------------------------------------------------------------- documentation
+def test_integration_md_stub_runs(model, tmp_path):
+    """The ctypes stub printed in INTEGRATION.md is executable as written and reproduces the package's
+    HybridSolver.run on a reference-style call (numpy [3,64] in, [T+1,3,64] out)."""
+    import os
+    import re
+    from conftest import ROOT
+    from gnn_plasma_flux_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "ctypes.CDLL" in b)
+    stub = stub.replace('ctypes.CDLL("libfluxgnn.so")', f'ctypes.CDLL({_lib.LIB_PATH!r})')
+    ckpt = tmp_path / "hybrid.pt"
+    torch.save({k: v.cpu() for k, v in model.state_dict().items()}, ckpt)
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    theirs = ns["HybridSolver"](str(ckpt), radius=1)
+    grid = P.Grid(nx=64, dt=5e-3)
+    ic = P.initial_condition(grid, seed=3)
+    got = theirs.run(ic, n_steps=12)
+    ours = make_solver(model, 64, 5e-3).run(ic, n_steps=12)
+    assert got.shape == (13, 3, 64) and got.dtype == np.float32
+    np.testing.assert_array_equal(got, ours)
