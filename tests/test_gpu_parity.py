@@ -368,6 +368,29 @@ def test_full_size_c2_properties(model, weights, precision):
     assert np.abs(mT - m0).max() <= 50 * nx * np.finfo(np.float32).eps
 
 
+def test_full_size_c2_thousand_steps_fp32_vs_fp16x3(model):
+    """BASELINE.json configs[1] in full: 4096 ICs x 64 cells, radius 3, 1000 steps (one persistent launch
+    per kernel).  The FP32-pipe kernel and the fp32-accurate tensor kernel must stay within the
+    1000-step tolerance of each other on every IC, stay finite and conserve mass to round-off."""
+    nx, B, T = 64, 4096, 1000
+    grid = P.Grid(nx=nx, dt=1e-3)
+    base = np.stack([P.stable_initial_condition(grid, s) for s in range(64)])
+    ics = np.tile(base, (B // 64, 1, 1))
+    ics += (np.random.RandomState(1).randn(B, 1, 1) * 1e-3).astype(np.float32) * np.array([0, 1, 0], np.float32)[None, :, None]
+    dev = torch.from_numpy(ics).cuda()
+    finals = {}
+    for precision in ("fp32", "fp16x3"):
+        out, _ = make_solver(model, nx, 1e-3, graph_radius=3, precision=precision).rollout(dev, T)
+        assert torch.isfinite(out).all(), precision
+        m0 = ics[:, 0].astype(np.float64).sum(-1)
+        mT = out[:, 0].double().sum(-1).cpu().numpy()
+        assert np.abs(mT - m0).max() <= T * nx * np.finfo(np.float32).eps, precision
+        finals[precision] = out.cpu().numpy()
+    err = P.rel_err(finals["fp16x3"], finals["fp32"])
+    print("1000 steps, 4096 ICs: fp16x3 vs fp32 kernel", err)
+    assert err.max() <= 1e-4
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_full_size_c3_per_gpu_properties(model, weights, precision):
     """BASELINE.json configs[2] at its 8-GPU per-GPU size: 8192 ICs x 1024 cells, radius 2 (window tiles +
