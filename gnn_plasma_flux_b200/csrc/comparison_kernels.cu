@@ -65,11 +65,15 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ in, const f
                                            int nx, int n, int rgroup, int ngroups) {
     for (int r0 = rgroup * 8; r0 < nx; r0 += ngroups * 8) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int k = 0; k < H; ++k) {
-            const float w = __ldg(Wt + (size_t)k * H + n);
+#pragma unroll 2
+        for (int k = 0; k < H; k += 4) {                            // 128-bit broadcast reads of the activations
+            const float w0 = __ldg(Wt + (size_t)(k + 0) * H + n), w1 = __ldg(Wt + (size_t)(k + 1) * H + n);
+            const float w2 = __ldg(Wt + (size_t)(k + 2) * H + n), w3 = __ldg(Wt + (size_t)(k + 3) * H + n);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(in[(r0 + i) * H + k], w, acc[i]);
+            for (int i = 0; i < 8; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(in + (r0 + i) * H + k);
+                acc[i] = fmaf(a.w, w3, fmaf(a.z, w2, fmaf(a.y, w1, fmaf(a.x, w0, acc[i]))));
+            }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
