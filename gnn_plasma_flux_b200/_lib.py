@@ -43,6 +43,8 @@ SIGNATURES = {
     "fluxgnn_hybrid_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_hybrid_rollout": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double,
                                        c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_hybrid_rollout_diag": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                            c_double, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
     "fluxgnn_packed_tc_weight_bytes": (c_size_t, [c_int]),
     "fluxgnn_pack_weights_tc": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
     "fluxgnn_packed_tc16_weight_bytes": (c_size_t, [c_int]),

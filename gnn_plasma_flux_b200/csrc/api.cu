@@ -328,7 +328,7 @@ size_t fluxgnn_baseline_workspace_bytes(int B, int nx) {
 static int hybrid_rollout_impl(int precision, const void* packed, int num_layers, const float* state_in,
                                float* state_out, const float* x, const double* gtab, int B, int nx, double length,
                                int radius, float c, float dt, int steps, int record_every, float* traj,
-                               void* workspace, void* stream_) {
+                               void* workspace, void* stream_, float* diag = nullptr) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_model(packed, num_layers, B, nx, radius);
     if (rc != FLUXGNN_OK) return rc;
@@ -361,9 +361,13 @@ static int hybrid_rollout_impl(int precision, const void* packed, int num_layers
         a.state_in = state_in;
         a.state_out = state_out;
         a.traj = traj;
+        a.diag = diag;
         a.steps = steps;
         return launch_tiles(a, fast, stream);
     }
+    if (diag != nullptr)
+        return set_error(FLUXGNN_EUNSUP, "in-kernel diagnostics need whole-IC tiles (nx <= %d), got nx=%d; reduce a "
+                                         "recorded trajectory with fluxgnn_rollout_metrics instead", kTileRows, nx);
     // window tiles: per step  tile kernel (n', u')  ->  field-solve kernel (E')
     const size_t state_floats = (size_t)B * 3 * nx;
     const bool need_ws = steps > 1 || fluxgnn_poisson_workspace_bytes(B, nx) > 0;
@@ -398,6 +402,16 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers, const float* stat
                            void* stream) {
     return hybrid_rollout_impl(0, packed, num_layers, state_in, state_out, x, gtab, B, nx, length, radius, c, dt,
                                steps, record_every, traj, workspace, stream);
+}
+
+int fluxgnn_hybrid_rollout_diag(const void* packed, int num_layers, int precision, const float* state_in,
+                                float* state_out, const float* x, const double* gtab, int B, int nx, double length,
+                                int radius, float c, float dt, int steps, float* diag, void* stream) {
+    if (precision != 0 && !tc_precision_known(precision))
+        return set_error(FLUXGNN_EINVAL, "hybrid_rollout_diag: precision must be 0 (fp32 kernel) or one of FLUXGNN_TC_*");
+    if (!diag) return set_error(FLUXGNN_EINVAL, "hybrid_rollout_diag: null diagnostics buffer");
+    return hybrid_rollout_impl(precision, packed, num_layers, state_in, state_out, x, gtab, B, nx, length, radius, c, dt,
+                               steps, 1, nullptr, nullptr, stream, diag);
 }
 
 int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precision, const float* state_in,

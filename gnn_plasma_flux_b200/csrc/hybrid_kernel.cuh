@@ -17,6 +17,8 @@ struct HybridArgs {
     float* flux_edges;         // nullable [B][2*hops*nx]
     float* face_flux;          // nullable [B][nx]
     float* traj;               // nullable [steps/record_every][B][3][nx]
+    float* diag;               // nullable [steps][B][4], whole-IC tiles: energy 0.5 mean(u^2+E^2), charge mean(n),
+                               //   number of non-finite values, 0 -- after EVERY step, reduced inside the kernel
     int B, nx, radius, L, hops;
     int whole_ic;              // 1: tile = floor(128/nx) complete ICs; 0: window of one IC + halo
     int ics_per_tile;          // whole-IC tiles

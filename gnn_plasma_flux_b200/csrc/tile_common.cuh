@@ -125,6 +125,23 @@ __device__ __forceinline__ void tile_write_out_row(const HybridArgs& a, const Ti
         tr[nx] = T.sU[j];
         tr[2 * (size_t)nx] = T.sE[j];
     }
+    // Per-step diagnostics of the IC whose first cell this row is (scripts/evaluation/evaluate_all.py:134-141,
+    // evaluate_long_rollout.py:53-66): one thread walks the IC's rows in order, fp64 sums -> deterministic.
+    if (a.diag != nullptr && T.rowCell[j] == 0) {
+        double e = 0.0, c = 0.0;
+        int bad = 0;
+        for (int i = 0; i < nx; ++i) {
+            const float n = T.sN[j + i], u = T.sU[j + i], f = T.sE[j + i];
+            e += (double)u * u + (double)f * f;
+            c += n;
+            bad += (isfinite(n) ? 0 : 1) + (isfinite(u) ? 0 : 1) + (isfinite(f) ? 0 : 1);
+        }
+        float* d = a.diag + ((size_t)step * a.B + T.rowIC[j]) * 4;
+        d[0] = (float)(0.5 * e / nx);
+        d[1] = (float)(c / nx);
+        d[2] = (float)bad;
+        d[3] = 0.f;
+    }
 }
 
 }  // namespace fluxgnn

@@ -81,6 +81,31 @@ class HybridSolver:
                 work.data_ptr() if work is not None else None, stream), "fluxgnn_hybrid_rollout")
         return out, traj
 
+    def rollout_diagnostics(self, state: torch.Tensor, n_steps: int):
+        """Advance state [B,3,nx] (nx <= 128) by n_steps in one persistent launch and reduce the per-step
+        diagnostics of the reference's evaluation scripts inside the kernel (no trajectory is stored):
+        returns (final [B,3,nx], {"energy": [T,B], "charge": [T,B], "nonfinite": [T,B]}) -- energy
+        0.5*mean(u^2+E^2), charge mean(n) (scripts/evaluation/evaluate_all.py:134-141), count of
+        non-finite values (the `exploded_at` test of evaluate_long_rollout.py:53-66)."""
+        base = self.baseline
+        if state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != base.nx:
+            raise ValueError(f"state must be [B,3,{base.nx}], got {tuple(state.shape)}")
+        packed = self.model.packed_weights(_lib.weight_layout(self.precision))
+        dev = packed.device
+        state = state.to(device=dev, dtype=torch.float32).contiguous()
+        B, _, nx = state.shape
+        x_dev, gtab = base.grid.tables(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty_like(state)
+            diag = torch.empty(n_steps, B, 4, dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().fluxgnn_hybrid_rollout_diag(
+                packed.data_ptr(), self.model.num_layers,
+                _lib.TC_PRECISIONS[self.precision] if self.precision != "fp32" else 0,
+                state.data_ptr(), out.data_ptr(), x_dev.data_ptr(), gtab.data_ptr() if gtab is not None else None,
+                B, nx, base.length, self.graph_radius, float(np.float32(base.dt / base.dx)), float(np.float32(base.dt)),
+                n_steps, diag.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "fluxgnn_hybrid_rollout_diag")
+        return out, {"energy": diag[..., 0], "charge": diag[..., 1], "nonfinite": diag[..., 2]}
+
     def rollout_graphed(self, state: torch.Tensor, n_steps: int, chunk: int = 10):
         """rollout() for grids above 128 cells, where a step is several kernel launches (tile kernel +
         field-solve kernels): `chunk` steps are captured once into a CUDA graph (A -> B and B -> A variants

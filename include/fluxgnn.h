@@ -182,6 +182,19 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                               int steps, int record_every, float* traj,
                               void* workspace, void* stream);
 
+/* ---- rollout with in-kernel diagnostics -----------------------------------
+ * fluxgnn_hybrid_rollout for grids of up to 128 cells that also reduces, inside the persistent kernel
+ * and after EVERY step, what scripts/evaluation/evaluate_all.py:134-141 and
+ * evaluate_long_rollout.py:53-66 compute from host copies of the trajectory:
+ *   diag[step][ic] = { 0.5*mean(u^2 + E^2), mean(n), number of non-finite values, 0 }   (4 floats)
+ * so a 1000-step sweep over 65536 ICs returns 1 GB of diagnostics instead of 800 GB of states.
+ * precision 0 = fp32 kernel (packed from fluxgnn_pack_weights), FLUXGNN_TC_* = tensor kernels. */
+int fluxgnn_hybrid_rollout_diag(const void* packed, int num_layers, int precision,
+                                const float* state_in, float* state_out,
+                                const float* x, const double* gtab,
+                                int B, int nx, double length, int radius, float c, float dt,
+                                int steps, float* diag /* [steps][B][4] */, void* stream);
+
 /* ---- training: FluxGNN.forward with saved activations and its backward pass --
  * What scripts/training/train_ablation.py:128-206 needs from the model: the edge fluxes of
  * src/flux_gnn.py:40-67 on the ring, differentiable w.r.t. every parameter and the node features.

@@ -778,6 +778,29 @@ def test_pinn_vs_reference(built_lib):
     assert P.rel_err(single.cpu().numpy(), g["pinn_step"][2]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("precision,nx", [("fp32", 64), ("fp32", 40), ("fp16x3", 64), ("tf32x3", 128)])
+def test_in_kernel_diagnostics(model, precision, nx):
+    """Per-step energy / charge / non-finite counts reduced inside the persistent kernel equal the
+    reduction of the recorded trajectory (fluxgnn_rollout_metrics), and the final state is unchanged."""
+    from gnn_plasma_flux_b200 import _lib, rollout_metrics
+    grid = P.Grid(nx=nx, dt=1e-3)
+    ics = torch.from_numpy(np.stack([P.stable_initial_condition(grid, s) for s in range(7)])).cuda()
+    ics[3, 1, 5] = float("inf")                                      # one IC blows up at once
+    sol = make_solver(model, nx, 1e-3, graph_radius=2, precision=precision)
+    final, traj = sol.rollout(ics, 25, record_every=1)
+    final_d, diag = sol.rollout_diagnostics(ics, 25)
+    keep = [0, 1, 2, 4, 5, 6]
+    assert torch.equal(final_d[keep], final[keep])
+    ref = rollout_metrics(traj)
+    for key in ("energy", "charge"):
+        a, b = diag[key][:, keep], ref[key][:, keep]
+        assert (a - b).abs().max() <= 1e-6 * b.abs().max(), key
+    assert torch.equal(diag["nonfinite"][:, keep], torch.zeros_like(diag["nonfinite"][:, keep]))
+    assert (diag["nonfinite"][:, 3] > 0).all()
+    with pytest.raises(_lib.FluxGNNError):                            # window tiles: reduce a recorded trajectory instead
+        make_solver(model, 1024, 3e-4, precision=precision).rollout_diagnostics(torch.zeros(2, 3, 1024, device="cuda"), 2)
+
+
 # ----------------------------------------------------------------------------- documentation
 def test_integration_md_stub_runs(model, tmp_path):
     """The ctypes stub printed in INTEGRATION.md is executable as written and reproduces the package's
