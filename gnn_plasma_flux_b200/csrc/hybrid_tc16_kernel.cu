@@ -134,20 +134,29 @@ __device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t a, uint32_t b, 
 }
 template <bool kBf16>
 __device__ __forceinline__ void pack_pair(float h0, float h1, uint32_t& hi, uint32_t& lo) {
+    // hi = rn16(h), lo = rn16(h - hi).  The residual is one mixed-precision FMA per element
+    // (fma.rn.f32.f16: -1 * hi + h, exact), so that a pair costs F2FP + 2 FHFMA + F2FP.
+    float r0, r1;
     if constexpr (kBf16) {
         const __nv_bfloat162 a = __floats2bfloat162_rn(h0, h1);
-        const float2 af = __bfloat1622float2(a);
-        const __nv_bfloat162 b = __floats2bfloat162_rn(h0 - af.x, h1 - af.y);
         hi = *reinterpret_cast<const uint32_t*>(&a);
+        const unsigned short a0 = (unsigned short)(hi & 0xffffu), a1 = (unsigned short)(hi >> 16), m1 = 0xbf80;
+        asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(r0) : "h"(a0), "h"(m1), "f"(h0));
+        asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(r1) : "h"(a1), "h"(m1), "f"(h1));
+        const __nv_bfloat162 b = __floats2bfloat162_rn(r0, r1);
         lo = *reinterpret_cast<const uint32_t*>(&b);
     } else {
         const __half2 a = __floats2half2_rn(h0, h1);
-        const float2 af = __half22float2(a);
-        const __half2 b = __floats2half2_rn(h0 - af.x, h1 - af.y);
         hi = *reinterpret_cast<const uint32_t*>(&a);
+        const unsigned short a0 = (unsigned short)(hi & 0xffffu), a1 = (unsigned short)(hi >> 16), m1 = 0xbc00;
+        asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r0) : "h"(a0), "h"(m1), "f"(h0));
+        asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r1) : "h"(a1), "h"(m1), "f"(h1));
+        const __half2 b = __floats2half2_rn(r0, r1);
         lo = *reinterpret_cast<const uint32_t*>(&b);
     }
 }
+
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 
 // Sum over the 32 lanes of v[r] for every r, result for r = lane (butterfly transpose-reduce:
 // 31 shuffles instead of 32 x 5).
@@ -344,11 +353,11 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
 
         // ---- input MLP (src/flux_gnn.py:49): feature n, the warp's chunk(s) of group g ----
         auto input_layer = [&](int g) {
-            const float w0 = S.small[SmallParams::w_in + 0 * kH + n];
-            const float w1 = S.small[SmallParams::w_in + 1 * kH + n];
-            const float w2 = S.small[SmallParams::w_in + 2 * kH + n];
-            const float w3 = S.small[SmallParams::w_in + 3 * kH + n];
-            const float b = S.small[SmallParams::b_in + n];
+            const float2 w0 = dup2(S.small[SmallParams::w_in + 0 * kH + n]);
+            const float2 w1 = dup2(S.small[SmallParams::w_in + 1 * kH + n]);
+            const float2 w2 = dup2(S.small[SmallParams::w_in + 2 * kH + n]);
+            const float2 w3 = dup2(S.small[SmallParams::w_in + 3 * kH + n]);
+            const float2 b = dup2(S.small[SmallParams::b_in + n]);
 #pragma unroll 1
             for (int half = 0; half < kChunksPerWarp; ++half) {
                 const int i0 = g * kGroupRows + 32 * (cw + 4 * half);
@@ -361,10 +370,15 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                         const float4 vu = *reinterpret_cast<const float4*>(&S.sU[i0 + 8 * c + j]);
                         const float4 ve = *reinterpret_cast<const float4*>(&S.sE[i0 + 8 * c + j]);
                         const float4 vx = *reinterpret_cast<const float4*>(&S.sX[i0 + 8 * c + j]);
-                        h[j + 0] = fmaxf(fmaf(w3, vx.x, fmaf(w2, ve.x, fmaf(w1, vu.x, fmaf(w0, vn.x, b)))), 0.f);
-                        h[j + 1] = fmaxf(fmaf(w3, vx.y, fmaf(w2, ve.y, fmaf(w1, vu.y, fmaf(w0, vn.y, b)))), 0.f);
-                        h[j + 2] = fmaxf(fmaf(w3, vx.z, fmaf(w2, ve.z, fmaf(w1, vu.z, fmaf(w0, vn.z, b)))), 0.f);
-                        h[j + 3] = fmaxf(fmaf(w3, vx.w, fmaf(w2, ve.w, fmaf(w1, vu.w, fmaf(w0, vn.w, b)))), 0.f);
+                        // two cells per packed FMA, same order of operations per cell as the scalar chain
+                        const float2 lo2 = __ffma2_rn(w3, make_float2(vx.x, vx.y), __ffma2_rn(w2, make_float2(ve.x, ve.y),
+                                           __ffma2_rn(w1, make_float2(vu.x, vu.y), __ffma2_rn(w0, make_float2(vn.x, vn.y), b))));
+                        const float2 hi2 = __ffma2_rn(w3, make_float2(vx.z, vx.w), __ffma2_rn(w2, make_float2(ve.z, ve.w),
+                                           __ffma2_rn(w1, make_float2(vu.z, vu.w), __ffma2_rn(w0, make_float2(vn.z, vn.w), b))));
+                        h[j + 0] = fmaxf(lo2.x, 0.f);
+                        h[j + 1] = fmaxf(lo2.y, 0.f);
+                        h[j + 2] = fmaxf(hi2.x, 0.f);
+                        h[j + 3] = fmaxf(hi2.y, 0.f);
                     }
                     store_rows8(i0, c, h);
                 }
@@ -394,7 +408,40 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                 for (int t = 0; t < 4; ++t) { zw[t] = zl[t]; zw[36 + t] = zr[t]; }
 #pragma unroll
                 for (int t = 0; t < 32; ++t) zw[4 + t] = zc[t];
-                if (!is_edge) {
+                if (!is_edge && R == 3) {
+                    // h'_i = relu(Y_i + b + mean_{0<|k|<=3} Z_{i+k})   (src/flux_gnn.py:55-60), two rows per packed
+                    // instruction.  Window w[0..39] = rows i0-4 .. i0+35 as aligned pairs P[m] = (w[2m], w[2m+1]);
+                    // with hs[m] = w[2m] + w[2m+1] and G[k] = P[k-1] + P[k+1] (packed) the sums of the rows of pair m are
+                    //   S(2m) = hs[m-1] + hs[m+1] + G[m-1].y,   S(2m+1) = hs[m-1] + hs[m+1] + G[m+1].x
+                    float2 P[20], G[20];
+                    float hs[20];
+                    P[0] = make_float2(zl[0], zl[1]);
+                    P[1] = make_float2(zl[2], zl[3]);
+                    P[18] = make_float2(zr[0], zr[1]);
+                    P[19] = make_float2(zr[2], zr[3]);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) P[2 + m] = make_float2(zc[2 * m], zc[2 * m + 1]);
+#pragma unroll
+                    for (int m = 1; m < 19; ++m) {
+                        hs[m] = P[m].x + P[m].y;
+                        G[m] = __fadd2_rn(P[m - 1], P[m + 1]);
+                    }
+                    const float2 us2 = dup2(kUnscale), bias2 = dup2(bias), inv2 = dup2(inv_deg);
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        float h[8];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int m = 4 * ch + t, mc = m + 2;
+                            const float tm = hs[mc - 1] + hs[mc + 1];
+                            const float2 sum = make_float2(tm + G[mc - 1].y, tm + G[mc + 1].x);
+                            const float2 r = __ffma2_rn(sum, inv2, __ffma2_rn(make_float2(y[2 * m], y[2 * m + 1]), us2, bias2));
+                            h[2 * t] = fmaxf(r.x, 0.f);
+                            h[2 * t + 1] = fmaxf(r.y, 0.f);
+                        }
+                        store_rows8(i0, ch, h);
+                    }
+                } else if (!is_edge) {
                     // h'_i = relu(Y_i + b + mean_{0<|k|<=R} Z_{i+k})   (src/flux_gnn.py:55-60)
                     // the window sum shares the pair sums pz[t] = Z[t] + Z[t+1] between neighbouring rows
                     float pz[39];
