@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         const float inv_deg = kUnscale / (float)(2 * R);
         const int seg = a.whole_ic ? nx : kGroupRows;         // periodic segment inside the group (multiple of 32)
         uint32_t acc_phase = 0;
+        const bool fuse_faces = (a.flux_edges == nullptr);    // no per-edge output: one feature reduction per face
 
         // rows 8c .. 8c+7 (c = chunk inside a 64-row block) of feature n: one 16-byte chunk at
         //   (row block) * kActRowBlockBytes + (n / 8) * 1024 + (n % 8) * 128 + ((c ^ (n % 8)) << 4)
@@ -469,15 +470,45 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     // row i -- fwd (row i, col i+1): w2[n] relu(P_i + b1 + Q_{i+1});  bwd (row i, col i-1) --
                     // summed over the warp's 32 features in registers, over the 4 quadrants in shared memory
                     float f[32];
+                    if (fuse_faces) {
+                        // Rollouts only need the face flux 0.5 (fwd_i + bwd_{i+1}) (src/hybrid_solver.py:45-48): add
+                        // the two terms of face i + 1/2 per feature and reduce once.  P + b1 of row i0 + 32 (the
+                        // periodic right neighbour of the chunk) comes from one more accumulator column.
+                        float yr[4];
+                        tmem_ld4(tlane + kColY + cr, yr);
+                        tc_wait_ld();
+                        const float2 us2 = dup2(kUnscale), bias2 = dup2(bias), w2 = dup2(w_out);
+                        float yb[34];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        y[j] = fmaf(y[j], kUnscale, bias);
-                        f[j] = w_out * fmaxf(fmaf(zw[4 + j + 1], kUnscale, y[j]), 0.f);
+                        for (int m = 0; m < 16; ++m) {
+                            const float2 t = __ffma2_rn(make_float2(y[2 * m], y[2 * m + 1]), us2, bias2);
+                            yb[2 * m] = t.x;
+                            yb[2 * m + 1] = t.y;
+                        }
+                        yb[32] = fmaf(yr[0], kUnscale, bias);
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            const int j = 2 * m;
+                            const float2 fw = make_float2(fmaxf(fmaf(zw[4 + j + 1], kUnscale, yb[j]), 0.f),
+                                                          fmaxf(fmaf(zw[4 + j + 2], kUnscale, yb[j + 1]), 0.f));
+                            const float2 bw = make_float2(fmaxf(fmaf(zw[4 + j], kUnscale, yb[j + 1]), 0.f),
+                                                          fmaxf(fmaf(zw[4 + j + 1], kUnscale, yb[j + 2]), 0.f));
+                            const float2 t = __fmul2_rn(w2, __fadd2_rn(fw, bw));
+                            f[j] = t.x;
+                            f[j + 1] = t.y;
+                        }
+                        S.edgeP[q][0][i0 + lane] = lane_transpose_sum(f, lane);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            y[j] = fmaf(y[j], kUnscale, bias);
+                            f[j] = w_out * fmaxf(fmaf(zw[4 + j + 1], kUnscale, y[j]), 0.f);
+                        }
+                        S.edgeP[q][0][i0 + lane] = lane_transpose_sum(f, lane);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = w_out * fmaxf(fmaf(zw[4 + j - 1], kUnscale, y[j]), 0.f);
+                        S.edgeP[q][1][i0 + lane] = lane_transpose_sum(f, lane);
                     }
-                    S.edgeP[q][0][i0 + lane] = lane_transpose_sum(f, lane);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = w_out * fmaxf(fmaf(zw[4 + j - 1], kUnscale, y[j]), 0.f);
-                    S.edgeP[q][1][i0 + lane] = lane_transpose_sum(f, lane);
                 }
             }
             if (!is_edge) publish_activations(g);
@@ -492,14 +523,20 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                 // face flux (src/hybrid_solver.py:45-48): edges (row j, col j+1) and (row j+1, col j)
                 const int j = myrow, jn = S.nextRow[j];
                 const float b2 = S.small[SmallParams::b_e2];
-                const float fwd = ((S.edgeP[0][0][j] + S.edgeP[1][0][j]) + (S.edgeP[2][0][j] + S.edgeP[3][0][j])) + b2;
-                const float bwd = ((S.edgeP[0][1][jn] + S.edgeP[1][1][jn]) + (S.edgeP[2][1][jn] + S.edgeP[3][1][jn])) + b2;
-                const float face = 0.5f * (fwd + bwd);
+                const float sum0 = (S.edgeP[0][0][j] + S.edgeP[1][0][j]) + (S.edgeP[2][0][j] + S.edgeP[3][0][j]);
                 const int ic = S.rowIC[j], cell = S.rowCell[j];
-                if (a.flux_edges != nullptr && ic >= 0) {
-                    float* fe = a.flux_edges + (size_t)ic * 2 * nx + cell;
-                    fe[0] = fwd;
-                    fe[nx] = bwd;
+                float face;
+                if (fuse_faces) {                              // sum0 = fwd_j + bwd_{j+1} without the biases
+                    face = fmaf(0.5f, sum0, b2);
+                } else {
+                    const float fwd = sum0 + b2;
+                    const float bwd = ((S.edgeP[0][1][jn] + S.edgeP[1][1][jn]) + (S.edgeP[2][1][jn] + S.edgeP[3][1][jn])) + b2;
+                    face = 0.5f * (fwd + bwd);
+                    if (ic >= 0) {
+                        float* fe = a.flux_edges + (size_t)ic * 2 * nx + cell;
+                        fe[0] = fwd;
+                        fe[nx] = bwd;
+                    }
                 }
                 if (a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
                 S.sF[j] = face;
