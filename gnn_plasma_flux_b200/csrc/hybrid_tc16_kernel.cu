@@ -517,21 +517,31 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
         // ---- after the edge readout of group g: face flux, finite-volume update, field solve, write-out ----
         auto finish_step = [&](int g, int step) {
             const int myrow = (tid < kGroupRows) ? g * kGroupRows + tid : -1;
+            // u of the left neighbour is read BEFORE the barrier: below every row overwrites its own state as
+            // soon as it has its update, without a barrier between the reads and the writes
+            int prow = 0;
+            float u_prev = 0.f;
+            if (a.do_update && myrow >= 0) {
+                prow = S.prevRow[myrow];
+                u_prev = S.sU[prow];
+            }
             named_sync(1, kEpiThreads);                        // edgeP of this group complete
-            float n_new = 0.f, u_new = 0.f;
             if (myrow >= 0) {
                 // face flux (src/hybrid_solver.py:45-48): edges (row j, col j+1) and (row j+1, col j)
-                const int j = myrow, jn = S.nextRow[j];
+                const int j = myrow;
                 const float b2 = S.small[SmallParams::b_e2];
-                const float sum0 = (S.edgeP[0][0][j] + S.edgeP[1][0][j]) + (S.edgeP[2][0][j] + S.edgeP[3][0][j]);
+                auto edge_sum = [&](int dir, int row) {
+                    return (S.edgeP[0][dir][row] + S.edgeP[1][dir][row]) + (S.edgeP[2][dir][row] + S.edgeP[3][dir][row]);
+                };
                 const int ic = S.rowIC[j], cell = S.rowCell[j];
-                float face;
-                if (fuse_faces) {                              // sum0 = fwd_j + bwd_{j+1} without the biases
-                    face = fmaf(0.5f, sum0, b2);
+                float face, face_prev = 0.f;
+                if (fuse_faces) {                              // edgeP[.][0] = fwd_j + bwd_{j+1} without the biases
+                    face = fmaf(0.5f, edge_sum(0, j), b2);
+                    if (a.do_update) face_prev = fmaf(0.5f, edge_sum(0, prow), b2);   // same bits as row prow's own face
                 } else {
-                    const float fwd = sum0 + b2;
-                    const float bwd = ((S.edgeP[0][1][jn] + S.edgeP[1][1][jn]) + (S.edgeP[2][1][jn] + S.edgeP[3][1][jn])) + b2;
+                    const float fwd = edge_sum(0, j) + b2, bwd = edge_sum(1, S.nextRow[j]) + b2;
                     face = 0.5f * (fwd + bwd);
+                    if (a.do_update) face_prev = 0.5f * ((edge_sum(0, prow) + b2) + (edge_sum(1, j) + b2));
                     if (ic >= 0) {
                         float* fe = a.flux_edges + (size_t)ic * 2 * nx + cell;
                         fe[0] = fwd;
@@ -539,19 +549,16 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                     }
                 }
                 if (a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
-                S.sF[j] = face;
+                if (a.do_update) {
+                    // finite-volume update (src/hybrid_solver.py:51-58)
+                    float n_new, u_new;
+                    tile_fv_update_values(a, S.sN[j], S.sU[j], u_prev, S.sE[j], face, face_prev, n_new, u_new);
+                    if (a.whole_ic) tile_keep_row(T, j, n_new, u_new);
+                    else tile_store_window_row(a, T, j, n_new, u_new);
+                }
             }
-            if (!a.do_update) return;                          // forward only
-            named_sync(1, kEpiThreads);
-            // finite-volume update (src/hybrid_solver.py:51-58)
-            if (myrow >= 0) tile_fv_update(a, T, myrow, n_new, u_new);
-            if (!a.whole_ic) {
-                if (myrow >= 0) tile_store_window_row(a, T, myrow, n_new, u_new);
-                return;
-            }
-            named_sync(1, kEpiThreads);
-            if (myrow >= 0) tile_keep_row(T, myrow, n_new, u_new);
-            named_sync(1, kEpiThreads);
+            if (!a.do_update || !a.whole_ic) return;
+            named_sync(1, kEpiThreads);                        // rho of every row
             // field solve: E = g (*) rho, kRowThreads threads per row (src/baseline_solver.py:59-68)
             {
                 const int row = g * kGroupRows + tid / kRowThreads, part = tid % kRowThreads;
@@ -560,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                 for (int m = 1; m < kRowThreads; m <<= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
                 if (part == 0) S.sE[row] = (float)e;
             }
-            named_sync(1, kEpiThreads);
+            named_sync(1, kEpiThreads);                        // the new state of every row is in shared memory
             if (myrow >= 0) tile_write_out_row(a, T, myrow, step);
         };
 
@@ -586,8 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
                         finish_step(g, step);
                         TC_TICK(8);
                         // group g moves on to its next step / next tile while the other group's products run
-                        if (step + 1 < a.steps) {
-                            named_sync(1, kEpiThreads);        // the new state of every row is in shared memory
+                        if (step + 1 < a.steps) {                // whole-IC tiles: finish_step ended on a barrier
                             input_layer(g);
                         } else if (next_tile < cta_tiles) {
                             named_sync(1, kEpiThreads);        // nobody reads this group's rows any more

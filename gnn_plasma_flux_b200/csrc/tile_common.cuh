@@ -71,14 +71,17 @@ __device__ __forceinline__ void tile_load_row(const HybridArgs& a, const TileRow
 
 // Finite-volume update of row j, numpy's fp32 operation order (src/hybrid_solver.py:51-58; no viscosity):
 //   n' = n - c (F_j - F_{j-1}),   u' = u - c (u_j^2/2 - u_{j-1}^2/2) + dt E
-__device__ __forceinline__ void tile_fv_update(const HybridArgs& a, const TileRows& T, int j, float& n_new, float& u_new) {
-    const int p = T.prevRow[j];
-    const float u = T.sU[j], up = T.sU[p];
-    n_new = __fsub_rn(T.sN[j], __fmul_rn(a.c, __fsub_rn(T.sF[j], T.sF[p])));
+__device__ __forceinline__ void tile_fv_update_values(const HybridArgs& a, float n, float u, float up, float e, float face,
+                                                      float face_prev, float& n_new, float& u_new) {
+    n_new = __fsub_rn(n, __fmul_rn(a.c, __fsub_rn(face, face_prev)));
     const float fu = __fmul_rn(__fmul_rn(0.5f, u), u);
     const float fup = __fmul_rn(__fmul_rn(0.5f, up), up);
     const float u_adv = __fsub_rn(u, __fmul_rn(a.c, __fsub_rn(fu, fup)));
-    u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, T.sE[j]));
+    u_new = __fadd_rn(u_adv, __fmul_rn(a.dt, e));
+}
+__device__ __forceinline__ void tile_fv_update(const HybridArgs& a, const TileRows& T, int j, float& n_new, float& u_new) {
+    const int p = T.prevRow[j];
+    tile_fv_update_values(a, T.sN[j], T.sU[j], T.sU[p], T.sE[j], T.sF[j], T.sF[p], n_new, u_new);
 }
 
 // Window tiles: n', u' of an owned row go straight to state_out (E' comes from the field-solve kernel).
