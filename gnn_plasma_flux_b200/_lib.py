@@ -17,6 +17,9 @@ MAX_HOPS = 4
 MAX_LAYERS = 8
 HIDDEN = 128
 INPUT_DIM = 4
+# fp16 / fp16x3 operand images store 2^8 * W (kTc16WeightScale, csrc/common.cuh): fp16's largest finite value / 2^8
+FP16_WEIGHT_LIMIT = 65504.0 / 256.0
+
 TC_PRECISIONS = {"tf32x3": 1, "tf32": 2, "fp16x3": 3, "fp16": 4, "bf16": 5}     # FLUXGNN_TC_* of include/fluxgnn.h
 
 

@@ -69,6 +69,13 @@ class FluxGNN(nn.Module):
                 L = _lib.lib()
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 ptrs = [t.data_ptr() for t in small]
+                if layout == "tc16":
+                    # fp16 operand images hold 2^8 * W: fail here rather than stream inf into the tensor cores
+                    w_max = float(torch.maximum(w_upd.abs().max(), small[4].abs().max()))
+                    if not w_max < _lib.FP16_WEIGHT_LIMIT:
+                        raise _lib.FluxGNNError(
+                            f"fp16 tensor-core layouts need |W| < {_lib.FP16_WEIGHT_LIMIT:g} in the update and edge "
+                            f"layers (largest entry {w_max:g}); use precision='bf16', 'tf32x3' or 'fp32' for this model")
                 if layout in ("tc16", "tc16_bf16"):
                     packed = torch.empty(L.fluxgnn_packed_tc16_weight_bytes(self.num_layers) // 4, dtype=torch.float32,
                                          device=dev)

@@ -153,7 +153,12 @@ int fluxgnn_hybrid_rollout(const void* packed, int num_layers,
  *                      65504 overflow).
  *   FLUXGNN_TC_BF16    one bfloat16 product (8-bit operands): loosest tolerance, fp32 range.
  * Their packed_tc comes from fluxgnn_pack_weights_tc16(..., precision, ...): the fp16 image
- * serves FP16X3 and FP16, the bf16 image serves BF16. */
+ * serves FP16X3 and FP16, the bf16 image serves BF16.
+ * Range of the fp16 modes: the image stores 2^8 W, so the update- and edge-layer weights must stay
+ * below 65504 / 2^8 = 255.875 in magnitude, and hidden activations below 65504; beyond that the
+ * operands are inf and the outputs non-finite (fluxgnn_hybrid_rollout_diag / fluxgnn_rollout_metrics
+ * count them).  The packing call is asynchronous and cannot report it: the Python mirror checks the
+ * weights before packing (FluxGNN.packed_weights) and raises; C callers check max|W| themselves. */
 #define FLUXGNN_TC_TF32X3 1
 #define FLUXGNN_TC_TF32   2
 #define FLUXGNN_TC_FP16X3 3

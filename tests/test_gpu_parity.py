@@ -778,6 +778,25 @@ def test_pinn_vs_reference(built_lib):
     assert P.rel_err(single.cpu().numpy(), g["pinn_step"][2]).max() <= 1e-5
 
 
+def test_fp16_layout_rejects_out_of_range_weights(model):
+    """fp16 operand images hold 2^8 W: weights of 256 or more must fail at packing time, loudly, and the
+    bf16 / tf32 / fp32 layouts of the same model must keep working."""
+    from gnn_plasma_flux_b200 import _lib
+    w = model.update_mlps[1][0].weight
+    saved = w.detach().clone()
+    try:
+        with torch.no_grad():
+            w[3, 5] = 300.0
+        with pytest.raises(_lib.FluxGNNError, match="fp16 tensor-core layouts"):
+            model.packed_weights("tc16")
+        for layout in ("tc16_bf16", "tc", "fp32"):
+            assert torch.isfinite(model.packed_weights(layout)).all()
+    finally:
+        with torch.no_grad():
+            w.copy_(saved)
+    assert torch.isfinite(model.packed_weights("tc16")).all()
+
+
 @pytest.mark.parametrize("precision,nx", [("fp32", 64), ("fp32", 40), ("fp16x3", 64), ("tf32x3", 128)])
 def test_in_kernel_diagnostics(model, precision, nx):
     """Per-step energy / charge / non-finite counts reduced inside the persistent kernel equal the
