@@ -455,6 +455,10 @@ def test_tc_flux_vs_fp64_oracle(model, weights, precision, nx, radius):
     assert err_tc <= tc_tols(precision)[0]
     face_ref = 0.5 * (ref[:, :nx] + ref[:, nx:])
     assert np.abs(f_tc.cpu().numpy() - face_ref).max() / scale <= tc_tols(precision)[0]
+    # face flux alone: the 16-bit kernel then reduces fwd_i + bwd_{i+1} in one pass (the rollout's code path)
+    none, f_only = model.ring_fluxes(dev, xd, radius=radius, want_edges=False, want_face=True, precision=precision)
+    assert none is None
+    assert np.abs(f_only.cpu().numpy() - face_ref).max() / scale <= tc_tols(precision)[0]
 
 
 @pytest.mark.parametrize("precision", TC_MODES)
