@@ -450,18 +450,23 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tc16_kernel(const HybridAr
 #pragma unroll
                         for (int t = 0; t < 39; ++t) pz[t] = zw[t] + zw[t + 1];
                     }
+                    auto window_sum = [&](int c) {                      // c = window centre in zw
+                        if constexpr (R == 1) return zw[c - 1] + zw[c + 1];
+                        else if constexpr (R == 2) return pz[c - 2] + pz[c + 1];
+                        else if constexpr (R == 3) return (pz[c - 3] + pz[c + 2]) + (zw[c - 1] + zw[c + 1]);
+                        else return (pz[c - 4] + pz[c + 3]) + (pz[c - 2] + pz[c + 1]);
+                    };
+                    const float2 us2 = dup2(kUnscale), bias2 = dup2(bias), inv2 = dup2(inv_deg);
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         float h[8];
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int j = 8 * ch + jj, c = 4 + j;     // window centre in zw
-                            float sum;
-                            if constexpr (R == 1) sum = zw[c - 1] + zw[c + 1];
-                            else if constexpr (R == 2) sum = pz[c - 2] + pz[c + 1];
-                            else if constexpr (R == 3) sum = (pz[c - 3] + pz[c + 2]) + (zw[c - 1] + zw[c + 1]);
-                            else sum = (pz[c - 4] + pz[c + 3]) + (pz[c - 2] + pz[c + 1]);
-                            h[jj] = fmaxf(fmaf(sum, inv_deg, fmaf(y[j], kUnscale, bias)), 0.f);
+                        for (int t = 0; t < 4; ++t) {                   // bias, unscale and mean: two rows per FFMA2
+                            const int j = 8 * ch + 2 * t;
+                            const float2 sum = make_float2(window_sum(4 + j), window_sum(5 + j));
+                            const float2 r = __ffma2_rn(sum, inv2, __ffma2_rn(make_float2(y[j], y[j + 1]), us2, bias2));
+                            h[2 * t] = fmaxf(r.x, 0.f);
+                            h[2 * t + 1] = fmaxf(r.y, 0.f);
                         }
                         store_rows8(i0, ch, h);
                     }
