@@ -175,6 +175,41 @@ class HybridSolver:
         torch.cuda.current_stream(dev).synchronize()
         return host_out
 
+    def stream_pinned(self, host_in, host_out, n_steps: int = 1, depth: int = 2):
+        """INDEPENDENT batches on HOST buffers, pipelined: host_in / host_out are equally long sequences of
+        pinned [B,3,nx] float32 tensors; batch i is copied in, advanced n_steps and copied out on CUDA
+        stream i % depth, so that the H2D copy of batch i+1 and the D2H copy of batch i-1 overlap the
+        kernel of batch i (ensembles larger than one launch; the reference loops such batches one IC at
+        a time, scripts/evaluation/evaluate_multi_ic.py:124-126).  Returns after every result is
+        readable on the host."""
+        if len(host_in) != len(host_out):
+            raise ValueError("host_in and host_out must have the same length")
+        if not all(t.is_pinned() for t in host_in) or not all(t.is_pinned() for t in host_out):
+            raise ValueError("stream_pinned needs pinned host tensors")
+        dev = torch.device(self.device)
+        self.model.packed_weights(_lib.weight_layout(self.precision))        # packed once, before the streams fork
+        self.baseline.grid.tables(dev)
+        main = torch.cuda.current_stream(dev)
+        lanes = self._pinned.setdefault(("streams", depth), [torch.cuda.Stream(dev) for _ in range(depth)])
+        for s in lanes:
+            s.wait_stream(main)
+        for i, (h_in, h_out) in enumerate(zip(host_in, host_out)):
+            slot = i % depth
+            key = ("lane", slot, tuple(h_in.shape))
+            bufs = self._pinned.get(key)
+            with torch.cuda.stream(lanes[slot]):
+                if bufs is None:
+                    bufs = (torch.empty(h_in.shape, dtype=torch.float32, device=dev),
+                            torch.empty(h_in.shape, dtype=torch.float32, device=dev))
+                    self._pinned[key] = bufs
+                bufs[0].copy_(h_in, non_blocking=True)
+                self.rollout(bufs[0], n_steps, out=bufs[1])
+                h_out.copy_(bufs[1], non_blocking=True)
+        for s in lanes:
+            main.wait_stream(s)
+        main.synchronize()
+        return host_out
+
     def _rollout_raw(self, src: torch.Tensor, dst: torch.Tensor, n_steps: int, dev):
         """fluxgnn_hybrid_rollout[_tc] on caller-provided device-addressable buffers (no checks, nx <= 128)."""
         base = self.baseline
