@@ -32,6 +32,14 @@
 // the finite-volume / field-solve tail) the tensor pipe works on the other.  N = 128 instructions are
 // as efficient as N = 256 ones, so the split costs no tensor time.  Only very wide receptive fields
 // (halo > 24 cells) keep one 256-row window per CTA (api.cu, plan_tiles).
+//
+// Epilogue arithmetic.  The epilogue warps are issue-bound, so their FP32 work is packed two rows per
+// instruction where the register pairs line up: window sums from aligned pairs (FADD2), bias / unscale /
+// mean as FFMA2, the hi/lo residual of the operand split as one mixed-precision FMA per element
+// (fma.rn.f32.f16, SASS FHFMA).  Rollouts (no per-edge output) add the two terms of a face per feature
+// before the warp transpose-sum, i.e. one feature reduction per face instead of two, and the
+// finite-volume tail needs three barriers: a row reads its left neighbour's u before the first one and
+// forms both of its faces itself.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
