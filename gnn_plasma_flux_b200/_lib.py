@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLUXGNN_LIB") or os.path.join(_HERE, "libfluxgnn.so")   # FLUXGNN_LIB: experiment builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_HOPS = 4
 MAX_LAYERS = 8
 HIDDEN = 128
@@ -64,9 +64,18 @@ SIGNATURES = {
     "fluxgnn_rollout_metrics": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     "fluxgnn_hybrid_slab_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                          c_float, c_float, c_void_p]),
+    "fluxgnn_hybrid_slab_step_ld": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                            c_int, c_int, c_float, c_float, c_void_p]),
+    "fluxgnn_baseline_slab_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                           c_float, c_float, c_float, c_float, c_void_p]),
+    "fluxgnn_poisson_dist_pack": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "fluxgnn_poisson_dist_unpack": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "fluxgnn_poisson_dist_rank_dft": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_int, c_int, c_void_p]),
+    "fluxgnn_poisson_dist_local": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
     "fluxgnn_pure_gnn_packed_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_pure_gnn_pack": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p, c_void_p]),
     "fluxgnn_pure_gnn_rollout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fluxgnn_pure_gnn_delta": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "fluxgnn_dense_layer": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "fluxgnn_baseline_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float,

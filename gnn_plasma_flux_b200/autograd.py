@@ -32,21 +32,25 @@ class RingFluxes(torch.autograd.Function):
                                                              radius, hops, edges.data_ptr(), acts.data_ptr(), stream),
                        "fluxgnn_forward_ring_train")
         ctx.model, ctx.radius, ctx.hops = model, radius, hops
-        ctx.save_for_backward(state, x, acts)
+        # the parameters go through save_for_backward so that autograd's version check fires when one of
+        # them is modified in place between this forward and the backward (optimizer.step() on a retained
+        # graph, load_state_dict): stock autograd raises there, and so does this function
+        ctx.save_for_backward(state, x, acts, *params)
         return edges
 
     @staticmethod
     def backward(ctx, dflux):
         model, radius, hops = ctx.model, ctx.radius, ctx.hops
-        state, x, acts = ctx.saved_tensors
+        state, x, acts, *params = ctx.saved_tensors        # raises if a saved parameter changed in place
         dev = state.device
         B, _, nx = state.shape
         L, H = model.num_layers, model.hidden_dim
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        # model.parameters() order: input_mlp.0.{weight,bias}, update_mlps.l.0.{weight,bias}, edge_mlp.0.*, edge_mlp.2.*
         with torch.cuda.device(dev), torch.no_grad():
-            w_in = f32(model.input_mlp[0].weight)
-            w_upd = torch.stack([f32(m[0].weight) for m in model.update_mlps]).contiguous()
-            w_e1, w_e2 = f32(model.edge_mlp[0].weight), f32(model.edge_mlp[2].weight)
+            w_in = f32(params[0])
+            w_upd = torch.stack([f32(params[2 + 2 * l]) for l in range(L)]).contiguous()
+            w_e1, w_e2 = f32(params[2 + 2 * L]), f32(params[4 + 2 * L])
             z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
             g_w_in, g_b_in = z(H, model.input_dim), z(H)
             g_w_upd, g_b_upd = z(L, H, 2 * H), z(L, H)

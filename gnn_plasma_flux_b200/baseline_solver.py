@@ -119,15 +119,24 @@ class BaselineSolver:
     def rollout(self, state: torch.Tensor, n_steps: int, record_every: int = 0, record_flux: bool = False):
         """Device-resident rollout of state [B,3,nx] (CUDA float32).
         Returns (final [B,3,nx], traj [n_steps//record_every, B,3,nx] | None, flux_n [n_steps,B,nx] | None)."""
-        B, _, nx = state.shape
-        if nx != self.nx:
-            raise ValueError(f"state has nx={nx}, solver has nx={self.nx}")
+        if not torch.is_tensor(state) or state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != self.nx:
+            raise ValueError(f"state must be a tensor [B,3,{self.nx}], got {tuple(getattr(state, 'shape', ()))}")
         dev = self.device
+        if dev.type != "cuda":
+            raise _lib.FluxGNNError(f"BaselineSolver(device={dev}): the step runs in libfluxgnn.so on a CUDA device "
+                                    "(there is no CPU fallback)")
+        state = state.to(device=dev, dtype=torch.float32).contiguous()
+        B, _, nx = state.shape
+        if n_steps < 0:
+            raise ValueError(f"n_steps must be >= 0, got {n_steps}")
+        if n_steps == 0:                      # the reference's loops simply do not run (src/baseline_solver.py:106-116)
+            return (state.clone(), state.new_empty((0, B, 3, nx)) if record_every else None,
+                    state.new_empty((0, B, nx)) if record_flux else None)
         _, gtab = self.grid.tables(dev)
         with torch.cuda.device(dev):
             out = torch.empty_like(state)
             ws_bytes = _lib.lib().fluxgnn_baseline_workspace_bytes(B, nx)
-            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
             traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
                     if record_every else None)
             flux = torch.empty(n_steps, B, nx, dtype=torch.float32, device=dev) if record_flux else None
@@ -137,7 +146,7 @@ class BaselineSolver:
                 self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)),
                 n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
                 flux.data_ptr() if flux is not None else None,
-                work.data_ptr(), stream), "fluxgnn_baseline_rollout")
+                work.data_ptr() if work is not None else None, stream), "fluxgnn_baseline_rollout")
         return out, traj, flux
 
     def step(self, state, return_flux=False):

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -507,6 +508,13 @@ int fluxgnn_rollout_metrics(const float* pred, const float* truth, long long num
 int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, const float* state_ext,
                              const float* x_ext, float* state_out, int B, int owned, int halo, int radius,
                              float c, float dt, void* stream) {
+    return fluxgnn_hybrid_slab_step_ld(packed, num_layers, precision, state_ext, x_ext, state_out, owned, 0, B, owned,
+                                       halo, radius, c, dt, stream);
+}
+
+int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precision, const float* state_ext,
+                                const float* x_ext, float* state_out, int out_ld, int out_off, int B, int owned,
+                                int halo, int radius, float c, float dt, void* stream) {
     int rc = check_model(packed, num_layers, B, owned, radius);
     if (rc != FLUXGNN_OK) return rc;
     if (!state_ext || !x_ext || !state_out) return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: null pointer");
@@ -544,6 +552,11 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, 
     a.num_tiles = (int)tiles;
     a.slab = 1;
     a.ld_in = owned + 2 * halo;
+    if (out_off < 0 || out_ld < out_off + owned)
+        return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: output row of %d floats cannot hold %d cells at offset %d",
+                         out_ld, owned, out_off);
+    a.ld_out = out_ld;
+    a.out_off = out_off;
     int fast = (radius <= 4) ? radius : 0;
     if (precision != 0) {
         rc = tc_shape_ok(0, owned, radius);
@@ -551,6 +564,50 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, 
         fast = -radius;
     }
     return launch_tiles(a, fast, (cudaStream_t)stream);
+}
+
+int fluxgnn_poisson_dist_pack(const float* n, long long ic_stride, int B, int S, void* z, void* stream) {
+    if (!n || !z || B < 1 || S < 1 || ic_stride < S) return set_error(FLUXGNN_EINVAL, "poisson_dist_pack: bad argument");
+    return launch_poisson_dist_pack(n, ic_stride, B, S, (float2*)z, 0, nullptr, (cudaStream_t)stream);
+}
+
+int fluxgnn_poisson_dist_unpack(const void* e, float* E, long long ic_stride, int B, int S, void* stream) {
+    if (!e || !E || B < 1 || S < 1 || ic_stride < S) return set_error(FLUXGNN_EINVAL, "poisson_dist_unpack: bad argument");
+    return launch_poisson_dist_pack(nullptr, ic_stride, B, S, (float2*)const_cast<void*>(e), 1, E, (cudaStream_t)stream);
+}
+
+int fluxgnn_poisson_dist_rank_dft(const void* in, void* out, int G, long long chunk, long long flat0, int S, int inverse,
+                                  void* stream) {
+    if (!in || !out || in == out || chunk < 1 || flat0 < 0)
+        return set_error(FLUXGNN_EINVAL, "poisson_dist_rank_dft: bad argument (chunk=%lld)", chunk);
+    return launch_poisson_rank_dft((const float2*)in, (float2*)out, G, chunk, flat0, S, inverse ? 1 : 0, (cudaStream_t)stream);
+}
+
+int fluxgnn_poisson_dist_local(void* y, void* scratch, int P, int S, int G, int rank, double length, void* stream) {
+    if (!y || !(length > 0.0)) return set_error(FLUXGNN_EINVAL, "poisson_dist_local: bad argument");
+    return launch_poisson_dist_local((float2*)y, (float2*)scratch, P, S, G, rank, length, (cudaStream_t)stream);
+}
+
+int fluxgnn_baseline_slab_step(const float* state_ext, float* state_out, int out_ld, int out_off, float* flux_n,
+                               int B, int owned, int halo, float c, float dt, float nu, float dx2, void* stream) {
+    if (!state_ext || !state_out || B < 1 || owned < 1 || halo < 1)
+        return set_error(FLUXGNN_EINVAL, "baseline_slab_step: bad argument (B=%d owned=%d halo=%d)", B, owned, halo);
+    if (out_off < 0 || out_ld < out_off + owned)
+        return set_error(FLUXGNN_EINVAL, "baseline_slab_step: output row of %d floats cannot hold %d cells at offset %d",
+                         out_ld, owned, out_off);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    const bool vec = ((owned | halo | out_ld | out_off) & 3) == 0 && (((uintptr_t)state_ext | (uintptr_t)state_out) & 15) == 0 &&
+                     (flux_n == nullptr || ((uintptr_t)flux_n & 15) == 0);
+    const long long cells = (long long)B * owned;
+    long long blocks = ((vec ? cells / 4 : cells) + 255) / 256;
+    if (blocks > (long long)sms * 64) blocks = (long long)sms * 64;
+    baseline_fv_slab_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(state_ext, state_out, flux_n, B, owned, halo,
+                                                                              out_ld, out_off, vec ? 1 : 0, c, dt, nu, dx2);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
 }
 
 int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const double* gtab, int B, int nx,

@@ -86,7 +86,8 @@ template <int H>
 __global__ void __launch_bounds__(kCmpThreads) pure_gnn_rollout_kernel(const float* __restrict__ packed,
                                                                       const float* __restrict__ state_in,
                                                                       float* __restrict__ state_out,
-                                                                      const float* __restrict__ x, int nx, int L, int steps) {
+                                                                      const float* __restrict__ x, int nx, int L, int steps,
+                                                                      int delta_only) {
     extern __shared__ float cmp_smem[];
     const int rows = (nx + 7) & ~7;
     float* h = cmp_smem;                        // [rows][H]
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(kCmpThreads) pure_gnn_rollout_kernel(const flo
             const int c = w / nx, r = w % nx;
             float acc = 0.f;
             for (int k = 0; k < H; ++k) acc = fmaf(P[r * H + k], __ldg(w_o2 + k * 4 + c), acc);
-            st[c * rows + r] += acc + __ldg(b_o2 + c);
+            const float delta = acc + __ldg(b_o2 + c);
+            st[c * rows + r] = delta_only ? delta : st[c * rows + r] + delta;      // delta_only: PureGNN.forward's own output
         }
         __syncthreads();
     }
@@ -219,8 +221,8 @@ int fluxgnn_pure_gnn_pack(const float* w_in, const float* b_in, const float* w_u
     return FLUXGNN_OK;
 }
 
-int fluxgnn_pure_gnn_rollout(const void* packed, int hidden, int num_layers, const float* state_in, float* state_out,
-                             const float* x, int B, int nx, int steps, void* stream) {
+static int pure_gnn_launch(const void* packed, int hidden, int num_layers, const float* state_in, float* state_out,
+                           const float* x, int B, int nx, int steps, int delta_only, void* stream) {
     if (!packed || !state_in || !state_out || !x) return set_error(FLUXGNN_EINVAL, "pure_gnn_rollout: null pointer");
     if ((hidden != 64 && hidden != 128) || num_layers < 1 || num_layers > 8)
         return set_error(FLUXGNN_EUNSUP, "pure_gnn_rollout: hidden must be 64 or 128 and num_layers 1..8");
@@ -231,15 +233,25 @@ int fluxgnn_pure_gnn_rollout(const void* packed, int hidden, int num_layers, con
     if (hidden == 128) {
         FLUXGNN_CUDA_OK(cudaFuncSetAttribute(pure_gnn_rollout_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pure_gnn_rollout_kernel<128><<<B, kCmpThreads, smem, (cudaStream_t)stream>>>((const float*)packed, state_in, state_out,
-                                                                                   x, nx, num_layers, steps);
+                                                                                   x, nx, num_layers, steps, delta_only);
     } else {
         FLUXGNN_CUDA_OK(cudaFuncSetAttribute(pure_gnn_rollout_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pure_gnn_rollout_kernel<64><<<B, kCmpThreads, smem, (cudaStream_t)stream>>>((const float*)packed, state_in, state_out, x,
-                                                                                  nx, num_layers, steps);
+                                                                                  nx, num_layers, steps, delta_only);
     }
     FLUXGNN_CUDA_OK(cudaGetLastError());
     count_launch();
     return FLUXGNN_OK;
+}
+
+int fluxgnn_pure_gnn_rollout(const void* packed, int hidden, int num_layers, const float* state_in, float* state_out,
+                             const float* x, int B, int nx, int steps, void* stream) {
+    return pure_gnn_launch(packed, hidden, num_layers, state_in, state_out, x, B, nx, steps, 0, stream);
+}
+
+int fluxgnn_pure_gnn_delta(const void* packed, int hidden, int num_layers, const float* state, float* delta_out,
+                           const float* x, int B, int nx, void* stream) {
+    return pure_gnn_launch(packed, hidden, num_layers, state, delta_out, x, B, nx, 1, 1, stream);
 }
 
 int fluxgnn_dense_layer(const float* in, const float* weight, const float* bias, const float* residual, float* out,

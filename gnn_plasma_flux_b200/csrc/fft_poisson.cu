@@ -291,19 +291,41 @@ __device__ __forceinline__ void spectral_self_row(float2* s, int bits2, int k1, 
 // ---------------------------------------------------------------------------
 // whole transform in one CTA (M = nx/2 = 2^bits <= 2^14 complex points)
 // ---------------------------------------------------------------------------
+// The diagonal spectral multiplier of the distributed solve (see launch_poisson_dist_local): the local bin kl of rank
+// kr is the global bin k = kr + G kl of an nx-point COMPLEX transform; E_hat = i rho_hat / k_phys with the signed
+// wavenumber (k > nx/2 -> k - nx), zero for k = 0 and for the Nyquist bin (src/baseline_solver.py:62-66: the real
+// part drops it; here two real signals share one complex transform, so it must be removed explicitly).
+__device__ __forceinline__ float2 spectral_diag(float2 z, long long k, long long nx, float scale) {
+    if (k == 0 || 2 * k == nx) return make_float2(0.f, 0.f);
+    const float kk = (float)(2 * k < nx ? k : k - nx);            // |kk| < 2^24: exact
+    const float f = __fdividef(scale, kk);
+    return make_float2(-f * z.y, f * z.x);
+}
+
+// kDist = false: the real-input half-length solve of one IC.  kDist = true: in-place complex transform of one of the
+// P signals of a rank (no n0 subtraction, diagonal multiplier of global bins kr + G kl).
+template <bool kDist>
 __global__ void __launch_bounds__(kFftThreads) poisson_fft_small_kernel(const float* __restrict__ n, long long n_stride,
                                                                         float* __restrict__ E, long long e_stride,
-                                                                        int bits, double length) {
+                                                                        int bits, double length, int G, int kr) {
     extern __shared__ float2 sfft[];
     const int M = 1 << bits;
     const float2* src = reinterpret_cast<const float2*>(n + (size_t)blockIdx.x * n_stride);
     for (int j = threadIdx.x; j < M; j += blockDim.x) {
         const float2 v = src[j];
-        sfft[saddr(j, 0, 1)] = make_float2(__fsub_rn(v.x, 1.0f), __fsub_rn(v.y, 1.0f));
+        sfft[saddr(j, 0, 1)] = kDist ? v : make_float2(__fsub_rn(v.x, 1.0f), __fsub_rn(v.y, 1.0f));
     }
     __syncthreads();
     fft_dif(sfft, bits, 1, -1.f);
-    spectral_self_row(sfft, bits, 0, 1, M, 2LL * M, (float)(length / (6.283185307179586476925 * (double)M)));
+    if constexpr (kDist) {
+        const long long nx = (long long)M * G;
+        const float scale = (float)(length / (6.283185307179586476925 * (double)M));     // carries the 1/M of the local inverse
+        for (int p = threadIdx.x; p < M; p += blockDim.x)
+            sfft[saddr(p, 0, 1)] = spectral_diag(sfft[saddr(p, 0, 1)], (long long)kr + (long long)G * bitrev(p, bits), nx, scale);
+        __syncthreads();
+    } else {
+        spectral_self_row(sfft, bits, 0, 1, M, 2LL * M, (float)(length / (6.283185307179586476925 * (double)M)));
+    }
     fft_dit(sfft, bits, 1, +1.f);
     float2* dst = reinterpret_cast<float2*>(E + (size_t)blockIdx.x * e_stride);
     for (int j = threadIdx.x; j < M; j += blockDim.x) dst[j] = sfft[saddr(j, 0, 1)];
@@ -421,7 +443,7 @@ __device__ __forceinline__ int rpad(int i) { return i + (i >> 4); }             
 // ---- kernel A / C: column passes -------------------------------------------------------------
 // One pass over blocks of 2^LB rows (j1 units) of a tile of N1 x T elements held at s[cpad(j1*T + t)].
 // kInv = false: DIF, forward, natural j1 in -> position order out;  kInv = true: the transposed DIT pass.
-template <int BITS1, int TILE_BITS, int LB, bool kInv, int THREADS>
+template <int BITS1, int TILE_BITS, int LB, bool kInv, int THREADS, bool kSub1 = true>
 __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s,
                                             int j2_0) {
     constexpr int RB = LB >= 4 ? 4 : LB, R = 1 << RB, SUBB = LB - RB, SUB = 1 << SUBB;
@@ -452,7 +474,7 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
 #pragma unroll
             for (int m = 0; m < R; ++m)
                 v[m] = gload<kHin>(gin + (((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t), pol_in);
-            if constexpr (!kInv) {
+            if constexpr (!kInv && kSub1) {          // rho = n - n0 (src/baseline_solver.py:60)
 #pragma unroll
                 for (int m = 0; m < R; ++m) v[m] = make_float2(__fsub_rn(v[m].x, 1.0f), __fsub_rn(v[m].y, 1.0f));
             }
@@ -480,11 +502,11 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
     if constexpr (!kGlobalOut) __syncthreads();
 }
 
-template <int BITS1, int TILE_BITS, int LB, int THREADS>
+template <int BITS1, int TILE_BITS, int LB, int THREADS, bool kSub1 = true>
 __device__ __forceinline__ void columns_forward(const float2* gin, float2* gout, float2* s, int j2_0) {
-    column_pass<BITS1, TILE_BITS, LB, false, THREADS>(gin, gout, s, j2_0);
+    column_pass<BITS1, TILE_BITS, LB, false, THREADS, kSub1>(gin, gout, s, j2_0);
     constexpr int SUBB = LB - (LB >= 4 ? 4 : LB);
-    if constexpr (SUBB > 0) columns_forward<BITS1, TILE_BITS, SUBB, THREADS>(gin, gout, s, j2_0);
+    if constexpr (SUBB > 0) columns_forward<BITS1, TILE_BITS, SUBB, THREADS, kSub1>(gin, gout, s, j2_0);
 }
 template <int BITS1, int TILE_BITS, int LB, int THREADS>
 __device__ __forceinline__ void columns_inverse(const float2* gin, float2* gout, float2* s, int j2_0) {
@@ -500,8 +522,9 @@ __host__ __device__ constexpr int column_threads(int bits1) { return column_tile
 
 }  // namespace
 
-// pass A: forward column stages.  grid = (N2 / T, B)
-template <int BITS1>
+// pass A: forward column stages.  grid = (N2 / T, B).  kSub1: the input is the density (rho = n - 1 is formed
+// on the fly); otherwise it is taken as it is (the complex signals of the distributed solve).
+template <int BITS1, bool kSub1 = true>
 __global__ void __launch_bounds__(column_threads(BITS1), column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
 poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride, float2* __restrict__ Y) {
     extern __shared__ float2 sfft[];
@@ -509,7 +532,7 @@ poisson_fft_cols_fwd_kernel(const float* __restrict__ n, long long n_stride, flo
     const int j2_0 = blockIdx.x << (TILE_BITS - BITS1);
     const float2* src = reinterpret_cast<const float2*>(n + (size_t)blockIdx.y * n_stride);
     float2* dst = Y + ((size_t)blockIdx.y << (BITS1 + kRowBits));
-    columns_forward<BITS1, TILE_BITS, BITS1, column_threads(BITS1)>(src, dst, sfft, j2_0);
+    columns_forward<BITS1, TILE_BITS, BITS1, column_threads(BITS1), kSub1>(src, dst, sfft, j2_0);
 }
 
 // pass C: inverse column stages, (E_2j, E_2j+1) out.  grid = (N2 / T, B)
@@ -696,6 +719,179 @@ __global__ void __launch_bounds__(kFftStepThreads, FLUXGNN_FFT_ROW_CTAS) poisson
     }
 }
 
+// pass B of the distributed solve: two INDEPENDENT rows per CTA (positions 2 bx, 2 bx + 1; they share every
+// twiddle set), forward row stages, diagonal multiplier, inverse row stages, in place.  grid = (N1/2, P).
+__global__ void __launch_bounds__(kFftStepThreads, FLUXGNN_FFT_ROW_CTAS) poisson_fft_rows_diag_kernel(
+    float2* __restrict__ Y, int bits1, float scale, int G, int kr) {
+    extern __shared__ float2 sfft[];
+    const int tid = threadIdx.x;
+    const long long Ml = 1LL << (bits1 + kRowBits), nx = Ml * G;
+    float2* base = Y + ((size_t)blockIdx.y << (bits1 + kRowBits));
+    float2* rowa = base + ((size_t)(2 * blockIdx.x) << kRowBits);
+    float2* rowb = rowa + kRowLen;
+    const int k1a = bitrev(2 * blockIdx.x, bits1), k1b = bitrev(2 * blockIdx.x + 1, bits1);
+    float2* sa = sfft;
+    float2* sb = sfft + kRowPad;
+    float2 va[16], vb[16], pw[16];
+    const uint64_t pol = make_policy<Hint::kLast>();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = gload<Hint::kLast>(rowa + tid + 256 * m, pol);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) vb[m] = gload<Hint::kLast>(rowb + tid + 256 * m, pol);
+    twiddle_powers<16>(unit_root(tid, kRowBits, -1.f), pw);
+    row_butterfly<false>(va, pw, true);
+    row_butterfly<false>(vb, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sa[rpad(tid + 256 * m)] = va[m];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sb[rpad(tid + 256 * m)] = vb[m];
+    __syncthreads();
+    const int e2 = (tid >> 4) * 256 + (tid & 15);
+    twiddle_powers<16>(unit_root(tid & 15, 8, -1.f), pw);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = sa[rpad(e2 + 16 * m)];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(e2 + 16 * m)];
+    row_butterfly<false>(va, pw, true);
+    row_butterfly<false>(vb, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sa[rpad(e2 + 16 * m)] = va[m];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sb[rpad(e2 + 16 * m)] = vb[m];
+    __syncthreads();
+    // forward pass 3 (blocks of 16), multiplier, inverse pass 3: block tid of both rows stays in registers
+    const int e3 = tid * 16;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = sa[rpad(e3 + m)];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(e3 + m)];
+    row_butterfly<false>(va, pw, false);
+    row_butterfly<false>(vb, pw, false);
+    // register m holds local bin kl = k1 + N1 (bitrev8(tid) + 256 bitrev4(m)) = kl0 + bitrev4(m) Ml/16
+    const long long kl0a = (long long)k1a + ((long long)bitrev(tid, 8) << bits1);
+    const long long kl0b = (long long)k1b + ((long long)bitrev(tid, 8) << bits1);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const long long step = (long long)brev_bits(m, 4) * (Ml >> 4);
+        va[m] = spectral_diag(va[m], (long long)kr + (long long)G * (kl0a + step), nx, scale);
+        vb[m] = spectral_diag(vb[m], (long long)kr + (long long)G * (kl0b + step), nx, scale);
+    }
+    row_butterfly<true>(va, pw, false);
+    row_butterfly<true>(vb, pw, false);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sa[rpad(e3 + m)] = va[m];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sb[rpad(e3 + m)] = vb[m];
+    __syncthreads();
+    twiddle_powers<16>(unit_root(tid & 15, 8, +1.f), pw);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = sa[rpad(e2 + 16 * m)];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(e2 + 16 * m)];
+    row_butterfly<true>(va, pw, true);
+    row_butterfly<true>(vb, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sa[rpad(e2 + 16 * m)] = va[m];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) sb[rpad(e2 + 16 * m)] = vb[m];
+    __syncthreads();
+    twiddle_powers<16>(unit_root(tid, kRowBits, +1.f), pw);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) va[m] = sa[rpad(tid + 256 * m)];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) vb[m] = sb[rpad(tid + 256 * m)];
+    row_butterfly<true>(va, pw, true);
+    row_butterfly<true>(vb, pw, true);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) gstore<Hint::kLast>(rowa + tid + 256 * m, va[m], pol);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) gstore<Hint::kLast>(rowb + tid + 256 * m, vb[m], pol);
+}
+
+// ---------------------------------------------------------------------------
+// Distributed field solve (one grid of nx cells split over G ranks, S = nx/G cells each).
+// Two density rows (ICs 2p, 2p+1) share one COMPLEX signal z = rho_a + i rho_b, so the multiplier i/k is diagonal
+// (no k <-> nx-k pairing across ranks) and the solve returns E_a + i E_b.  The nx-point transform is decimated in
+// frequency over the rank index: element (jr, jl) = jr S + jl, bin k = kr + G kl,
+//   y[kr][jl]  = W_nx^(jl kr) sum_jr W_G^(jr kr) z[jr][jl]        poisson_rank_dft_kernel (between two all-to-alls)
+//   Z[kr+G kl] = FFT_S(y[kr])[kl]                                  local: passes A, B, C above with the diagonal multiplier
+// and the inverse runs the same steps backwards.  Every exchanged buffer is a flat array cut into G equal chunks.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) poisson_pack_pairs_kernel(const float* __restrict__ n, long long ic_stride,
+                                                                 float2* __restrict__ z, int B, int S) {
+    const long long total = (long long)((B + 1) / 2) * S;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(idx / S), j = (int)(idx - (long long)p * S);
+        const float a = __fsub_rn(__ldg(n + (size_t)(2 * p) * ic_stride + j), 1.0f);
+        const float b = (2 * p + 1 < B) ? __fsub_rn(__ldg(n + (size_t)(2 * p + 1) * ic_stride + j), 1.0f) : 0.f;
+        z[idx] = make_float2(a, b);
+    }
+}
+
+__global__ void __launch_bounds__(256) poisson_unpack_pairs_kernel(const float2* __restrict__ e, float* __restrict__ E,
+                                                                   long long ic_stride, int B, int S) {
+    const long long total = (long long)((B + 1) / 2) * S;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(idx / S), j = (int)(idx - (long long)p * S);
+        const float2 v = e[idx];
+        E[(size_t)(2 * p) * ic_stride + j] = v.x;
+        if (2 * p + 1 < B) E[(size_t)(2 * p + 1) * ic_stride + j] = v.y;
+    }
+}
+
+// in[q][e], out[r][e], e < chunk; flat index of element e = flat0 + e, jl = flat index mod S.
+//   forward: out[kr][e] = W_nx^-(jl kr) sum_q W_G^-(q kr) in[q][e]
+//   inverse: out[jr][e] = (1/G) sum_kr W_G^+(jr kr) W_nx^+(jl kr) in[kr][e]
+template <int G>
+__global__ void __launch_bounds__(256) poisson_rank_dft_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                               long long chunk, long long flat0, int S, long long nx,
+                                                               int inverse) {
+    const float sign = inverse ? 1.f : -1.f;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < chunk; e += (long long)gridDim.x * blockDim.x) {
+        const long long jl = (flat0 + e) & (long long)(S - 1);
+        float2 v[G], pw[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) v[q] = in[(size_t)q * chunk + e];
+        twiddle_powers<G>(big_twiddle(jl, nx, sign), pw);             // pw[r] = W_nx^(sign jl r)
+        if (inverse) {
+#pragma unroll
+            for (int q = 1; q < G; ++q) v[q] = pmul(v[q], pw[q]);
+        }
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            float2 acc = v[0];
+#pragma unroll
+            for (int q = 1; q < G; ++q) {
+                // W_G^(sign q r): eighth turns at most for G <= 8, sixteenth turns for G = 16
+                constexpr int kTurn = 16 / G;
+                float2 t;
+                switch (((q * r) & (G - 1)) * kTurn) {
+                    case 0: t = v[q]; break;
+                    case 1: t = mul_root16<1>(v[q], sign); break;
+                    case 2: t = mul_root16<2>(v[q], sign); break;
+                    case 3: t = mul_root16<3>(v[q], sign); break;
+                    case 4: t = mul_root16<4>(v[q], sign); break;
+                    case 5: t = mul_root16<5>(v[q], sign); break;
+                    case 6: t = mul_root16<6>(v[q], sign); break;
+                    case 7: t = mul_root16<7>(v[q], sign); break;
+                    case 8: t = mul_root16<8>(v[q], sign); break;
+                    case 9: t = mul_root16<9>(v[q], sign); break;
+                    case 10: t = mul_root16<10>(v[q], sign); break;
+                    case 11: t = mul_root16<11>(v[q], sign); break;
+                    case 12: t = mul_root16<12>(v[q], sign); break;
+                    case 13: t = mul_root16<13>(v[q], sign); break;
+                    case 14: t = mul_root16<14>(v[q], sign); break;
+                    default: t = mul_root16<15>(v[q], sign); break;
+                }
+                acc = __fadd2_rn(acc, t);
+            }
+            if (inverse) acc = make_float2(acc.x * (1.0f / G), acc.y * (1.0f / G));
+            else if (r > 0) acc = pmul(acc, pw[r]);
+            out[(size_t)r * chunk + e] = acc;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------
@@ -727,10 +923,10 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     if (mbits <= kFftRowBits) {
         const int M = 1 << mbits;
         const size_t smem = (size_t)(M + M / 16) * sizeof(float2);
-        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
         const int threads = M / 16 < kFftThreads ? (M / 16 < 64 ? 64 : M / 16) : kFftThreads;
-        poisson_fft_small_kernel<<<B, threads, smem, stream>>>(n, n_stride, E, e_stride, mbits, length);
+        poisson_fft_small_kernel<false><<<B, threads, smem, stream>>>(n, n_stride, E, e_stride, mbits, length, 1, 0);
         FLUXGNN_CUDA_OK(cudaGetLastError());
         count_launch();
         return FLUXGNN_OK;
@@ -770,6 +966,92 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     FLUXGNN_CUDA_OK(cudaGetLastError());
 #undef FLUXGNN_FFT_COLS_ALL
 #undef FLUXGNN_FFT_COLS
+    count_launch(3);
+    return FLUXGNN_OK;
+}
+
+// ---- distributed solve: host side ------------------------------------------------------------------------
+static int dist_shape_ok(int S, int G) {
+    const int sbits = ilog2_exact(S), gbits = ilog2_exact(G);
+    if (sbits < 8 || sbits > kFftMaxBits - 1 || gbits < 0 || G > 16 || sbits + gbits > 27)
+        return set_error(FLUXGNN_EUNSUP, "distributed field solve: slab of %d cells over %d ranks (need powers of two, "
+                                         "slab >= 256 cells, <= 16 ranks, grid <= 2^27 cells)", S, G);
+    return FLUXGNN_OK;
+}
+
+int launch_poisson_dist_pack(const float* n, long long ic_stride, int B, int S, float2* z, int unpack, float* E,
+                             cudaStream_t stream) {
+    const long long total = (long long)((B + 1) / 2) * S;
+    const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (unpack) poisson_unpack_pairs_kernel<<<blocks, 256, 0, stream>>>(z, E, ic_stride, B, S);
+    else poisson_pack_pairs_kernel<<<blocks, 256, 0, stream>>>(n, ic_stride, z, B, S);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+int launch_poisson_rank_dft(const float2* in, float2* out, int G, long long chunk, long long flat0, int S, int inverse,
+                            cudaStream_t stream) {
+    int rc = dist_shape_ok(S, G);
+    if (rc != FLUXGNN_OK) return rc;
+    const long long nx = (long long)S * G;
+    const unsigned blocks = (unsigned)((chunk + 255) / 256 < 148 * 16 ? (chunk + 255) / 256 : 148 * 16);
+    switch (G) {
+        case 1: poisson_rank_dft_kernel<1><<<blocks, 256, 0, stream>>>(in, out, chunk, flat0, S, nx, inverse); break;
+        case 2: poisson_rank_dft_kernel<2><<<blocks, 256, 0, stream>>>(in, out, chunk, flat0, S, nx, inverse); break;
+        case 4: poisson_rank_dft_kernel<4><<<blocks, 256, 0, stream>>>(in, out, chunk, flat0, S, nx, inverse); break;
+        case 8: poisson_rank_dft_kernel<8><<<blocks, 256, 0, stream>>>(in, out, chunk, flat0, S, nx, inverse); break;
+        default: poisson_rank_dft_kernel<16><<<blocks, 256, 0, stream>>>(in, out, chunk, flat0, S, nx, inverse); break;
+    }
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+// In-place solve of the P complex signals y[P][S] of rank kr (local bins kl <-> global bins kr + G kl); `scratch`
+// holds another P*S complex numbers (unused for S <= 2^14).
+int launch_poisson_dist_local(float2* y, float2* scratch, int P, int S, int G, int kr, double length, cudaStream_t stream) {
+    int rc = dist_shape_ok(S, G);
+    if (rc != FLUXGNN_OK) return rc;
+    if (P < 1 || P > 65535 || kr < 0 || kr >= G) return set_error(FLUXGNN_EINVAL, "distributed field solve: P=%d rank=%d of %d", P, kr, G);
+    const int mbits = ilog2_exact(S);
+    if (mbits <= kFftRowBits) {
+        const int M = 1 << mbits;
+        const size_t smem = (size_t)(M + M / 16) * sizeof(float2);
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int threads = M / 16 < kFftThreads ? (M / 16 < 64 ? 64 : M / 16) : kFftThreads;
+        poisson_fft_small_kernel<true><<<P, threads, smem, stream>>>((const float*)y, 2LL * S, (float*)y, 2LL * S, mbits, length, G, kr);
+        FLUXGNN_CUDA_OK(cudaGetLastError());
+        count_launch();
+        return FLUXGNN_OK;
+    }
+    if (scratch == nullptr) return set_error(FLUXGNN_EINVAL, "distributed field solve: scratch required for slabs above 2^14 cells");
+    const int bits1 = mbits - kRowBits;
+    const int tile_bits = column_tile_bits(bits1);
+    const int T = 1 << (tile_bits - bits1);
+    const size_t tile = (size_t)1 << tile_bits;
+    const size_t smem = (tile + (tile >> 5) * 4) * sizeof(float2);
+    const size_t smem_row = (size_t)2 * kRowPad * sizeof(float2);
+    const float scale = (float)(length / (6.283185307179586476925 * (double)S));
+    dim3 gcol((unsigned)(kRowLen / T), (unsigned)P), grow((unsigned)((1 << bits1) / 2), (unsigned)P);
+    FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+#define FLUXGNN_DIST_COLS(BITS1)                                                                                         \
+    case BITS1:                                                                                                          \
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_fwd_kernel<BITS1, false>,                                  \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_inv_kernel<BITS1>,                                         \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        poisson_fft_cols_fwd_kernel<BITS1, false><<<gcol, column_threads(BITS1), smem, stream>>>((const float*)y, 2LL * S, scratch); \
+        poisson_fft_rows_diag_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(scratch, bits1, scale, G, kr);         \
+        poisson_fft_cols_inv_kernel<BITS1><<<gcol, column_threads(BITS1), smem, stream>>>(scratch, (float*)y, 2LL * S);  \
+        break;
+    switch (bits1) {
+        FLUXGNN_DIST_COLS(3) FLUXGNN_DIST_COLS(4) FLUXGNN_DIST_COLS(5) FLUXGNN_DIST_COLS(6) FLUXGNN_DIST_COLS(7)
+        FLUXGNN_DIST_COLS(8) FLUXGNN_DIST_COLS(9) FLUXGNN_DIST_COLS(10) FLUXGNN_DIST_COLS(11) FLUXGNN_DIST_COLS(12)
+        default: return set_error(FLUXGNN_EUNSUP, "distributed field solve: unsupported column length 2^%d", bits1);
+    }
+#undef FLUXGNN_DIST_COLS
+    FLUXGNN_CUDA_OK(cudaGetLastError());
     count_launch(3);
     return FLUXGNN_OK;
 }

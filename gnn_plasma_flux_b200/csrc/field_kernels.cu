@@ -130,6 +130,55 @@ __global__ void __launch_bounds__(256) baseline_fv_kernel(const float* __restric
     }
 }
 
+// The same update for one slab of a domain-decomposed grid (baseline-only row): `in` is the extended
+// state [B][3][owned + 2*halo] whose ghost cells replace the periodic wrap (halo >= 1; the stencil needs one cell);
+// n', u' go to out[B][3][out_ld] at column out_off + cell (E' comes from the distributed field solve).
+__global__ void __launch_bounds__(256) baseline_fv_slab_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                               float* __restrict__ flux_n, int B, int owned, int halo,
+                                                               int out_ld, int out_off, int vec,
+                                                               float c, float dt, float nu, float dx2) {
+    const int ld = owned + 2 * halo;
+    if (vec) {
+        const int quads = owned >> 2;
+        const long long total = (long long)B * quads;
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+             idx += (long long)gridDim.x * blockDim.x) {
+            const int ic = (int)(idx / quads);
+            const int i = (int)(idx - (long long)ic * quads) << 2;
+            const float* pn = in + (size_t)ic * 3 * ld + halo + i;
+            const float* pu = pn + ld;
+            const float* pe = pu + ld;
+            const float4 n4 = *reinterpret_cast<const float4*>(pn);
+            const float4 u4 = *reinterpret_cast<const float4*>(pu);
+            const float4 e4 = *reinterpret_cast<const float4*>(pe);
+            const float nm = __ldg(pn - 1), um = __ldg(pu - 1), up = __ldg(pu + 4);
+            const FvOut a = fv_cell(nm, n4.x, um, u4.x, u4.y, e4.x, c, dt, nu, dx2);
+            const FvOut b = fv_cell(n4.x, n4.y, u4.x, u4.y, u4.z, e4.y, c, dt, nu, dx2);
+            const FvOut d = fv_cell(n4.y, n4.z, u4.y, u4.z, u4.w, e4.z, c, dt, nu, dx2);
+            const FvOut e = fv_cell(n4.z, n4.w, u4.z, u4.w, up, e4.w, c, dt, nu, dx2);
+            float* po = out + (size_t)ic * 3 * out_ld + out_off + i;
+            *reinterpret_cast<float4*>(po) = make_float4(a.n, b.n, d.n, e.n);
+            *reinterpret_cast<float4*>(po + out_ld) = make_float4(a.u, b.u, d.u, e.u);
+            if (flux_n != nullptr)
+                *reinterpret_cast<float4*>(flux_n + (size_t)ic * owned + i) = make_float4(a.fn, b.fn, d.fn, e.fn);
+        }
+        return;
+    }
+    const long long total = (long long)B * owned;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int ic = (int)(idx / owned);
+        const int i = (int)(idx - (long long)ic * owned);
+        const float* pn = in + (size_t)ic * 3 * ld + halo + i;
+        const float* pu = pn + ld;
+        const FvOut o = fv_cell(pn[-1], pn[0], pu[-1], pu[0], pu[1], pu[ld], c, dt, nu, dx2);
+        float* po = out + (size_t)ic * 3 * out_ld + out_off + i;
+        po[0] = o.n;
+        po[out_ld] = o.u;
+        if (flux_n != nullptr) flux_n[idx] = o.fn;
+    }
+}
+
 // FP32 pipe probe: 16 independent FFMA chains per thread, register operands only.
 // Used by bench.py to measure the FFMA roofline of the box it runs on.
 __global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ out, int iters, float a, float b) {

@@ -10,6 +10,8 @@ __global__ void poisson_direct_kernel(const float* n, long long n_stride, float*
                                       const double* gtab, int nx);
 __global__ void baseline_fv_kernel(const float* in, float* out, float* flux_n, int B, int nx,
                                    float c, float dt, float nu, float dx2);
+__global__ void baseline_fv_slab_kernel(const float* in, float* out, float* flux_n, int B, int owned, int halo,
+                                        int out_ld, int out_off, int vec, float c, float dt, float nu, float dx2);
 __global__ void pack_weights_kernel(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
                                     const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
                                     int L, float* packed);
@@ -41,5 +43,12 @@ bool poisson_fft_supported(int nx);
 size_t poisson_fft_workspace_bytes(int B, int nx);
 int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e_stride, int B, int nx,
                        double length, void* workspace, cudaStream_t stream);
+
+// distributed field solve (fft_poisson.cu): pack / unpack pairs of ICs, the cross-rank DFT stage, the local solve
+int launch_poisson_dist_pack(const float* n, long long ic_stride, int B, int S, float2* z, int unpack, float* E,
+                             cudaStream_t stream);
+int launch_poisson_rank_dft(const float2* in, float2* out, int G, long long chunk, long long flat0, int S, int inverse,
+                            cudaStream_t stream);
+int launch_poisson_dist_local(float2* y, float2* scratch, int P, int S, int G, int kr, double length, cudaStream_t stream);
 
 }  // namespace fluxgnn

@@ -39,6 +39,9 @@ struct HybridArgs {
     int slab;                  // 1: one slab of a domain-decomposed grid.  state_in and x are
     int ld_in;                 //    [..][ld_in] = nx owned cells + `halo` ghost cells per side, no
                                //    periodic wrap; nx counts the OWNED cells; outputs are [..][nx]
+    int ld_out, out_off;       // window / slab outputs: row length of state_out and offset of cell 0 in it
+                               //    (0, 0 = [..][nx]; a slab that writes the interior of the next extended state
+                               //    passes ld_out = nx + 2*halo, out_off = halo)
 };
 
 // fast_radius 1..4 selects the compile-time-radius window path; 0 the generic path.

@@ -87,9 +87,10 @@ __device__ __forceinline__ void tile_fv_update(const HybridArgs& a, const TileRo
 // Window tiles: n', u' of an owned row go straight to state_out (E' comes from the field-solve kernel).
 __device__ __forceinline__ void tile_store_window_row(const HybridArgs& a, const TileRows& T, int j, float n_new, float u_new) {
     if (T.rowIC[j] < 0) return;
-    float* so = a.state_out + (size_t)T.rowIC[j] * 3 * a.nx + T.rowCell[j];
+    const int ld = a.ld_out ? a.ld_out : a.nx;
+    float* so = a.state_out + (size_t)T.rowIC[j] * 3 * ld + a.out_off + T.rowCell[j];
     so[0] = n_new;
-    so[a.nx] = u_new;
+    so[ld] = u_new;
 }
 
 // Whole-IC tiles: the new state stays in shared memory; rho = n' - n0 (src/baseline_solver.py:60).

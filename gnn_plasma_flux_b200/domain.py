@@ -1,22 +1,27 @@
-"""Domain decomposition of ONE large periodic grid across GPUs (BASELINE.json configs[3]).
+"""Domain decomposition of ONE large periodic grid across GPUs (BASELINE.json configs[3] and the
+baseline-only row).
 
 The reference has no distributed code; this is new work behind the same step arithmetic
-(src/hybrid_solver.py:34-64).  Rank r of G owns the contiguous slab of S = nx/G cells
-[r*S, (r+1)*S).  Per time step:
+(src/hybrid_solver.py:34-64, src/baseline_solver.py:80-101).  Rank r of G owns the contiguous slab of
+S = nx/G cells [r*S, (r+1)*S) and keeps it permanently in the EXTENDED layout [B][3][S + 2H] (H ghost
+cells per side), in two ping-pong buffers.  Per time step:
 
-  1. ring halo exchange of raw state: H = L*radius + 1 cells per side (the receptive field of
-     one step), 12 bytes per cell, two small point-to-point messages per neighbour
-     -- instead of exchanging 512-byte hidden states after every layer;
-  2. the fused tile kernel on the slab + ghost cells (fluxgnn_hybrid_slab_step): n', u';
-  3. the field solve is global: all-gather n' (4 B/cell), every rank runs the same FFT solve
-     and keeps its slab of E'.  The solve is replicated on purpose: at these sizes it costs
-     well under 2 % of the GNN work of the step, and an all-gather is one collective instead of
-     the four all-to-all transposes of a distributed FFT.
+  1. ring halo exchange of raw state: H = L*radius + 1 cells per side for the hybrid step (the receptive
+     field of one step; 12 bytes per cell instead of 512-byte hidden states after every layer), H = 4 for
+     the classical step (its stencil needs 1; 4 keeps 128-bit loads aligned).  The two edges travel as one
+     small message per neighbour and land in the ghost zones of the current buffer;
+  2. the slab kernel (fluxgnn_hybrid_slab_step_ld / fluxgnn_baseline_slab_step) writes n', u' straight into
+     the interior of the other buffer -- no concatenation, no slicing on the step path;
+  3. the field solve is distributed (`field_solve="alltoall"`, the default wherever slabs and rank count are
+     powers of two): two ICs travel as one complex
+     signal, the nx-point transform is decimated in frequency over the rank index, four all-to-alls of
+     4 bytes per cell each (include/fluxgnn.h, "distributed field solve"); every rank transforms only its own
+     1/G of the spectrum.  `field_solve="allgather"` keeps round 1's variant (all-gather of n', the whole FFT
+     replicated on every rank: G times the bytes and the arithmetic) as a cross-check.
 
-One process per GPU; `TorchDistComm` speaks torch.distributed (NCCL on GPUs, gloo in the CPU
-tests).  `step_emulated` runs G virtual ranks inside one process on one GPU -- the way to
-exercise the decomposition without G devices (separate processes that wait on one another
-must not share a GPU).
+One process per GPU; `TorchDistComm` speaks torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+`step_emulated` runs G virtual ranks inside one process on one GPU -- the way to exercise the
+decomposition without G devices (separate processes that wait on one another must not share a GPU).
 """
 from __future__ import annotations
 
@@ -30,7 +35,7 @@ from .grid import PeriodicGrid
 
 
 class TorchDistComm:
-    """Ring neighbours + all-gather over a torch.distributed process group."""
+    """Ring neighbours, all-to-all and all-gather over a torch.distributed process group."""
 
     def __init__(self, group=None):
         self.group = group
@@ -51,8 +56,15 @@ class TorchDistComm:
                dist.P2POp(dist.irecv, left_ghost, left, self.group),
                dist.P2POp(dist.irecv, right_ghost, right, self.group)]
         for req in dist.batch_isend_irecv(ops):
-            req.wait()
+            req.wait()               # NCCL: orders the current stream after the transfer, the host does not block
         return left_ghost, right_ghost
+
+    def all_to_all(self, recv: torch.Tensor, send: torch.Tensor):
+        """Flat buffers cut into `world` equal chunks: chunk q of `send` goes to rank q."""
+        if self.world == 1:
+            recv.copy_(send)
+        else:
+            dist.all_to_all_single(recv, send, group=self.group)
 
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
@@ -60,51 +72,204 @@ class TorchDistComm:
         return out
 
 
-class DomainDecomposedHybridSolver:
-    """The hybrid step on one slab of a grid of `nx` cells split over `world` ranks."""
+# ------------------------------------------------------------------------------------------- field solve
+class DistributedFieldSolve:
+    """Per-rank stages of the distributed spectral field solve (include/fluxgnn.h, fluxgnn_poisson_dist_*).
+    Buffers: two flat complex arrays of P*S elements (P = ceil(B/2) complex signals of S cells) that alternate
+    as send / receive buffer of the four all-to-alls, plus the FFT scratch."""
 
-    def __init__(self, model, nx, length=2 * np.pi, dt=5e-3, graph_radius=1, rank=0, world=1, device="cuda",
-                 precision="fp32", slab_fn=None, field_fn=None):
+    def __init__(self, nx: int, length: float, rank: int, world: int, device, cuda_stages=None):
+        if world & (world - 1) or world > 16:
+            raise ValueError(f"the distributed field solve needs a power-of-two number of ranks <= 16, got {world}")
+        self.nx, self.length, self.rank, self.world = int(nx), float(length), rank, world
+        self.S = self.nx // world
+        if self.S & (self.S - 1) or self.S < 256:
+            raise ValueError(f"the distributed field solve needs power-of-two slabs of >= 256 cells, got {self.S}")
+        self.device = torch.device(device)
+        self._bufs = {}
+        self._stages = cuda_stages          # test hook: CPU stand-ins for the four CUDA stages
+
+    def buffers(self, B: int):
+        P = (B + 1) // 2
+        hit = self._bufs.get(P)
+        if hit is None:
+            n = P * self.S * 2
+            hit = tuple(torch.empty(n, dtype=torch.float32, device=self.device) for _ in range(3))
+            self._bufs[P] = hit
+        return hit
+
+    # ---- the four local stages (CUDA; `self._stages` replaces them in the CPU tests) ----
+    def pack(self, n_rows: torch.Tensor, z: torch.Tensor):
+        """n_rows: [B, S] view (row stride arbitrary, unit column stride) -> z flat [P*S*2] = (n_a - 1, n_b - 1)."""
+        if self._stages:
+            return self._stages["pack"](n_rows, z)
+        B = n_rows.shape[0]
+        _lib.check(_lib.lib().fluxgnn_poisson_dist_pack(n_rows.data_ptr(), n_rows.stride(0) if B > 1 else self.S, B, self.S,
+                                                        z.data_ptr(), _stream(self.device)), "fluxgnn_poisson_dist_pack")
+
+    def rank_dft(self, src: torch.Tensor, dst: torch.Tensor, inverse: bool):
+        if self._stages:
+            return self._stages["rank_dft"](self, src, dst, inverse)
+        chunk = src.numel() // 2 // self.world
+        _lib.check(_lib.lib().fluxgnn_poisson_dist_rank_dft(src.data_ptr(), dst.data_ptr(), self.world, chunk,
+                                                            self.rank * chunk, self.S, int(inverse), _stream(self.device)),
+                   "fluxgnn_poisson_dist_rank_dft")
+
+    def local(self, y: torch.Tensor, scratch: torch.Tensor):
+        if self._stages:
+            return self._stages["local"](self, y)
+        P = y.numel() // 2 // self.S
+        _lib.check(_lib.lib().fluxgnn_poisson_dist_local(y.data_ptr(), scratch.data_ptr(), P, self.S, self.world, self.rank,
+                                                         self.length, _stream(self.device)), "fluxgnn_poisson_dist_local")
+
+    def unpack(self, e: torch.Tensor, E_rows: torch.Tensor):
+        if self._stages:
+            return self._stages["unpack"](e, E_rows)
+        B = E_rows.shape[0]
+        _lib.check(_lib.lib().fluxgnn_poisson_dist_unpack(e.data_ptr(), E_rows.data_ptr(), E_rows.stride(0) if B > 1 else self.S,
+                                                          B, self.S, _stream(self.device)), "fluxgnn_poisson_dist_unpack")
+
+    # ---- one solve on one rank ----
+    def solve(self, n_rows: torch.Tensor, E_rows: torch.Tensor, comm):
+        """E_rows[B,S] <- field of the global density whose slab is n_rows[B,S] (both may be strided row views)."""
+        a, b, scratch = self.buffers(n_rows.shape[0])
+        with torch.cuda.device(self.device) if self.device.type == "cuda" else _nullctx():
+            self.pack(n_rows, a)
+            if self.world > 1:
+                comm.all_to_all(b, a)
+                self.rank_dft(b, a, False)
+                comm.all_to_all(b, a)
+            else:
+                a, b = b, a
+            self.local(b, scratch)
+            if self.world > 1:
+                comm.all_to_all(a, b)
+                self.rank_dft(a, b, True)
+                comm.all_to_all(a, b)
+            else:
+                a, b = b, a
+            self.unpack(a, E_rows)
+
+
+def solve_emulated(solvers, n_rows, E_rows):
+    """The same solve for G virtual ranks in one process: every all-to-all becomes chunk copies."""
+    G = len(solvers)
+    bufs = [s.buffers(n_rows[0].shape[0]) for s in solvers]
+    a = [bf[0] for bf in bufs]
+    b = [bf[1] for bf in bufs]
+
+    def exchange(dst, src):
+        chunk = src[0].numel() // G
+        for r in range(G):
+            for q in range(G):
+                dst[r][q * chunk:(q + 1) * chunk].copy_(src[q][r * chunk:(r + 1) * chunk])
+
+    for r in range(G):
+        solvers[r].pack(n_rows[r], a[r])
+    if G > 1:
+        exchange(b, a)
+        for r in range(G):
+            solvers[r].rank_dft(b[r], a[r], False)
+        exchange(b, a)
+    else:
+        a, b = b, a
+    for r in range(G):
+        solvers[r].local(b[r], bufs[r][2])
+    if G > 1:
+        exchange(a, b)
+        for r in range(G):
+            solvers[r].rank_dft(a[r], b[r], True)
+        exchange(a, b)
+    else:
+        a, b = b, a
+    for r in range(G):
+        solvers[r].unpack(a[r], E_rows[r])
+
+
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# ------------------------------------------------------------------------------------------- slab solvers
+class _DomainDecomposedSolver:
+    """Shared host logic: extended ping-pong state, halo exchange, field solve, step orchestration."""
+
+    def __init__(self, nx, length, dt, halo, rank, world, device, field_solve, slab_fn=None, field_fn=None,
+                 field_stages=None):
         if nx % world:
             raise ValueError(f"nx={nx} is not divisible by the number of ranks {world}")
-        self.model, self.nx, self.length, self.dt = model, int(nx), float(length), float(dt)
+        self.nx, self.length, self.dt = int(nx), float(length), float(dt)
         self.rank, self.world, self.device = rank, world, torch.device(device)
-        self.radius = int(graph_radius)
         self.owned = self.nx // world
-        self.halo = model.num_layers * self.radius + 1
+        self.halo = int(halo)
         if self.owned < self.halo:
             raise ValueError(f"a slab of {self.owned} cells is narrower than the halo of {self.halo}")
-        if precision != "fp32" and precision not in _lib.TC_PRECISIONS:
-            raise ValueError(f"precision must be 'fp32' or one of {sorted(_lib.TC_PRECISIONS)}, got {precision!r}")
-        self.precision = precision
+        if field_solve not in ("auto", "alltoall", "allgather"):
+            raise ValueError("field_solve must be 'auto', 'alltoall' or 'allgather'")
+        if field_solve == "auto":            # the distributed solve needs power-of-two slabs and rank counts
+            ok = not (self.owned & (self.owned - 1)) and self.owned >= 256 and not (world & (world - 1)) and world <= 16
+            field_solve = "alltoall" if ok else "allgather"
+        self.field_mode = field_solve
         self.grid = PeriodicGrid(self.nx, self.length)
-        idx = (rank * self.owned - self.halo + np.arange(self.owned + 2 * self.halo)) % self.nx
+        self.ld = self.owned + 2 * self.halo
+        idx = (rank * self.owned - self.halo + np.arange(self.ld)) % self.nx
         self.x_ext = torch.as_tensor(self.grid.x[idx], dtype=torch.float32).to(self.device)   # GLOBAL positions
         self._slab_fn = slab_fn or self._cuda_slab
         self._field_fn = field_fn
         self._baseline = None
+        self._ext = {}                       # batch -> [buffer 0, buffer 1]
+        self._cur = {}                       # batch -> index of the buffer holding the current state
+        self._edges = {}
+        self._dist = (DistributedFieldSolve(self.nx, self.length, rank, world, self.device, field_stages)
+                      if field_solve == "alltoall" else None)
 
-    # ---- local pieces -------------------------------------------------------------------
-    def _cuda_slab(self, ext: torch.Tensor) -> torch.Tensor:
-        tensor_path = self.precision != "fp32"
-        packed = self.model.packed_weights(_lib.weight_layout(self.precision))
+    # ---- extended state ----
+    def _buffers(self, B: int):
+        hit = self._ext.get(B)
+        if hit is None:
+            hit = [torch.zeros(B, 3, self.ld, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._ext[B] = hit
+            self._cur[B] = 0
+            H = self.halo
+            self._edges[B] = (torch.empty(2, B, 3, H, dtype=torch.float32, device=self.device),
+                              torch.empty(2, B, 3, H, dtype=torch.float32, device=self.device))
+        return hit
+
+    def interior(self, ext: torch.Tensor) -> torch.Tensor:
+        return ext[..., self.halo:self.halo + self.owned]
+
+    def _adopt(self, local: torch.Tensor) -> torch.Tensor:
+        """The extended buffer that holds `local`: the current one if `local` is its interior view (the value the
+        previous step returned), otherwise the state is copied in."""
+        if local.dim() != 3 or local.shape[1] != 3 or local.shape[2] != self.owned:
+            raise ValueError(f"local state must be [B,3,{self.owned}], got {tuple(local.shape)}")
+        B = local.shape[0]
+        bufs = self._buffers(B)
+        cur = bufs[self._cur[B]]
+        mine = self.interior(cur)
+        if not (local.data_ptr() == mine.data_ptr() and local.stride() == mine.stride()):
+            mine.copy_(local.to(device=self.device, dtype=torch.float32))
+        return cur
+
+    def _fill_ghosts(self, ext: torch.Tensor, comm):
+        H, S = self.halo, self.owned
         B = ext.shape[0]
-        with torch.cuda.device(self.device):
-            out = torch.empty(B, 3, self.owned, dtype=torch.float32, device=self.device)
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            dx = self.length / self.nx
-            _lib.check(_lib.lib().fluxgnn_hybrid_slab_step(
-                packed.data_ptr(), self.model.num_layers, _lib.TC_PRECISIONS[self.precision] if tensor_path else 0,
-                ext.data_ptr(), self.x_ext.data_ptr(), out.data_ptr(), B, self.owned, self.halo, self.radius,
-                float(np.float32(self.dt / dx)), float(np.float32(self.dt)), stream), "fluxgnn_hybrid_slab_step")
-        return out
+        send, recv = self._edges[B]
+        send[0].copy_(ext[..., H:2 * H])             # my first H cells -> left neighbour's right ghosts
+        send[1].copy_(ext[..., S:S + H])             # my last H cells  -> right neighbour's left ghosts
+        left_ghost, right_ghost = comm.exchange_halos(send[0], send[1])
+        ext[..., :H].copy_(left_ghost)
+        ext[..., H + S:].copy_(right_ghost)
 
-    def advance_slab(self, ext: torch.Tensor) -> torch.Tensor:
-        """ext [B,3,owned+2*halo] (ghosts included) -> [B,3,owned] with n', u' (E' not yet)."""
-        if ext.shape[1:] != (3, self.owned + 2 * self.halo):
-            raise ValueError(f"ext must be [B,3,{self.owned + 2 * self.halo}], got {tuple(ext.shape)}")
-        return self._slab_fn(ext.to(torch.float32).contiguous())
-
+    # ---- field solve ----
     def field(self, n_full: torch.Tensor) -> torch.Tensor:
         """Global field solve E[B,nx] from the gathered density (src/baseline_solver.py:59-68)."""
         if self._field_fn is not None:
@@ -113,16 +278,103 @@ class DomainDecomposedHybridSolver:
             self._baseline = BaselineSolver(nx=self.nx, length=self.length, dt=self.dt, device=self.device)
         return self._baseline.solve_poisson(n_full.contiguous())
 
-    # ---- one step, one process per rank ----------------------------------------------------
+    def _solve_field(self, nxt: torch.Tensor, comm):
+        """E' of the new density (channel 0 of `nxt`'s interior) into channel 2 of `nxt`'s interior."""
+        inner = self.interior(nxt)
+        if self._dist is not None:
+            self._dist.solve(inner[:, 0], inner[:, 2], comm)
+            return
+        S = self.owned
+        gathered = comm.all_gather(inner[:, 0].contiguous())                    # [world,B,S]
+        n_full = gathered.permute(1, 0, 2).reshape(nxt.shape[0], self.nx)
+        inner[:, 2].copy_(self.field(n_full)[:, self.rank * S:(self.rank + 1) * S])
+
+    # ---- one step, one process per rank ----
     def step(self, local: torch.Tensor, comm) -> torch.Tensor:
-        """local [B,3,owned] -> new local state; `comm` provides exchange_halos / all_gather."""
-        H, S = self.halo, self.owned
-        left_ghost, right_ghost = comm.exchange_halos(local[..., :H].contiguous(), local[..., S - H:].contiguous())
-        out = self.advance_slab(torch.cat([left_ghost, local, right_ghost], dim=-1))
-        gathered = comm.all_gather(out[:, 0, :].contiguous())                    # [world,B,S]
-        n_full = gathered.permute(1, 0, 2).reshape(local.shape[0], self.nx)
-        out[:, 2, :] = self.field(n_full)[:, self.rank * S:(self.rank + 1) * S]
-        return out
+        """local [B,3,owned] -> new local state (the interior VIEW of this solver's extended buffer; pass it back
+        to step() and no copy is made).  `comm` provides exchange_halos / all_to_all / all_gather."""
+        cur = self._adopt(local)
+        B = cur.shape[0]
+        nxt = self._ext[B][1 - self._cur[B]]
+        self._fill_ghosts(cur, comm)
+        self._slab_fn(cur, nxt)
+        self._solve_field(nxt, comm)
+        self._cur[B] = 1 - self._cur[B]
+        return self.interior(nxt)
+
+    def time_shares(self, local: torch.Tensor, comm, reps: int = 3):
+        """Device time of a full step against the slab kernel alone (all ranks call this together):
+        {"step_ms", "slab_kernel_ms", "exchange_and_solve_share"}."""
+        cur = self._adopt(local)
+        B = cur.shape[0]
+        nxt = self._ext[B][1 - self._cur[B]]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.synchronize(self.device)
+        ev[0].record()
+        for _ in range(reps):
+            self._slab_fn(cur, nxt)
+        ev[1].record()
+        state = local
+        ev[2].record()
+        for _ in range(reps):
+            state = self.step(state, comm)
+        ev[3].record()
+        torch.cuda.synchronize(self.device)
+        slab, full = ev[0].elapsed_time(ev[1]) / reps, ev[2].elapsed_time(ev[3]) / reps
+        return {"step_ms": full, "slab_kernel_ms": slab, "exchange_and_solve_share": max(0.0, 1.0 - slab / full)}
+
+
+class DomainDecomposedHybridSolver(_DomainDecomposedSolver):
+    """The hybrid step on one slab of a grid of `nx` cells split over `world` ranks."""
+
+    def __init__(self, model, nx, length=2 * np.pi, dt=5e-3, graph_radius=1, rank=0, world=1, device="cuda",
+                 precision="fp32", slab_fn=None, field_fn=None, field_solve="auto", field_stages=None):
+        self.model = model
+        self.radius = int(graph_radius)
+        if precision != "fp32" and precision not in _lib.TC_PRECISIONS:
+            raise ValueError(f"precision must be 'fp32' or one of {sorted(_lib.TC_PRECISIONS)}, got {precision!r}")
+        self.precision = precision
+        super().__init__(nx, length, dt, model.num_layers * self.radius + 1, rank, world, device, field_solve,
+                         slab_fn, field_fn, field_stages)
+
+    def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor):
+        tensor_path = self.precision != "fp32"
+        packed = self.model.packed_weights(_lib.weight_layout(self.precision))
+        B = ext.shape[0]
+        with torch.cuda.device(self.device):
+            dx = self.length / self.nx
+            _lib.check(_lib.lib().fluxgnn_hybrid_slab_step_ld(
+                packed.data_ptr(), self.model.num_layers, _lib.TC_PRECISIONS[self.precision] if tensor_path else 0,
+                ext.data_ptr(), self.x_ext.data_ptr(), nxt.data_ptr(), self.ld, self.halo, B, self.owned, self.halo,
+                self.radius, float(np.float32(self.dt / dx)), float(np.float32(self.dt)), _stream(self.device)),
+                "fluxgnn_hybrid_slab_step_ld")
+
+    def advance_slab(self, ext: torch.Tensor) -> torch.Tensor:
+        """ext [B,3,owned+2*halo] (ghosts included) -> [B,3,owned] with n', u' (E' not yet)."""
+        if ext.shape[1:] != (3, self.ld):
+            raise ValueError(f"ext must be [B,3,{self.ld}], got {tuple(ext.shape)}")
+        nxt = torch.zeros_like(ext)
+        self._slab_fn(ext.to(torch.float32).contiguous(), nxt)
+        return self.interior(nxt).contiguous()
+
+
+class DomainDecomposedBaselineSolver(_DomainDecomposedSolver):
+    """The classical step (src/baseline_solver.py:80-101) on one slab: halo exchange of 4 cells (1 is read),
+    fluxgnn_baseline_slab_step, distributed field solve."""
+
+    def __init__(self, nx, length=2 * np.pi, dt=5e-3, nu=1e-3, rank=0, world=1, device="cuda", slab_fn=None,
+                 field_fn=None, field_solve="auto", field_stages=None):
+        self.nu = float(nu)
+        super().__init__(nx, length, dt, 4, rank, world, device, field_solve, slab_fn, field_fn, field_stages)
+
+    def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor):
+        B = ext.shape[0]
+        dx = self.length / self.nx
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fluxgnn_baseline_slab_step(
+                ext.data_ptr(), nxt.data_ptr(), self.ld, self.halo, None, B, self.owned, self.halo,
+                float(np.float32(self.dt / dx)), float(np.float32(self.dt)), float(np.float32(self.nu)),
+                float(np.float32(dx ** 2)), _stream(self.device)), "fluxgnn_baseline_slab_step")
 
 
 def split_slabs(state: torch.Tensor, world: int):
@@ -132,13 +384,24 @@ def split_slabs(state: torch.Tensor, world: int):
 
 def step_emulated(solvers, locals_):
     """One decomposed step of G virtual ranks inside this process (solvers[r] built with rank=r,
-    world=G): the halo exchange and the all-gather become tensor copies.  For single-GPU tests."""
+    world=G): the halo exchange and the collectives become tensor copies.  For single-GPU tests."""
     G = len(solvers)
     H, S = solvers[0].halo, solvers[0].owned
-    exts = [torch.cat([locals_[(r - 1) % G][..., S - H:], locals_[r], locals_[(r + 1) % G][..., :H]], dim=-1)
-            for r in range(G)]
-    outs = [solvers[r].advance_slab(exts[r]) for r in range(G)]
-    n_full = torch.cat([o[:, 0, :] for o in outs], dim=-1)
+    curs = [solvers[r]._adopt(locals_[r]) for r in range(G)]
+    B = curs[0].shape[0]
+    nxts = [solvers[r]._ext[B][1 - solvers[r]._cur[B]] for r in range(G)]
     for r in range(G):
-        outs[r][:, 2, :] = solvers[r].field(n_full)[:, r * S:(r + 1) * S]
-    return outs
+        curs[r][..., :H].copy_(curs[(r - 1) % G][..., S:S + H])
+        curs[r][..., H + S:].copy_(curs[(r + 1) % G][..., H:2 * H])
+    for r in range(G):
+        solvers[r]._slab_fn(curs[r], nxts[r])
+    inner = [solvers[r].interior(nxts[r]) for r in range(G)]
+    if solvers[0]._dist is not None:
+        solve_emulated([s._dist for s in solvers], [i[:, 0] for i in inner], [i[:, 2] for i in inner])
+    else:
+        n_full = torch.cat([i[:, 0] for i in inner], dim=-1)
+        for r in range(G):
+            inner[r][:, 2].copy_(solvers[r].field(n_full)[:, r * S:(r + 1) * S])
+    for r in range(G):
+        solvers[r]._cur[B] = 1 - solvers[r]._cur[B]
+    return inner

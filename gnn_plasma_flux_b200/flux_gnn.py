@@ -36,7 +36,30 @@ class FluxGNN(nn.Module):
         self.input_mlp = _linear_relu(input_dim, hidden_dim)
         self.update_mlps = nn.ModuleList(_linear_relu(2 * hidden_dim, hidden_dim) for _ in range(num_layers))
         self.edge_mlp = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, 1))
-        self._packed = {}            # layout name -> (key, tensor)
+        self._packed = {}            # layout name -> (key, tensor, ready event)
+
+    # ------------------------------------------------------------------ cache control
+    def invalidate_packed(self):
+        """Drop the packed-weight caches so that the next call repacks from the live parameters.
+        The cache key is (data_ptr, version counter) of every parameter, which in-place edits through
+        autograd-visible ops (optimizer.step(), p.add_(), p.copy_() under no_grad) and replaced or moved
+        tensors all change.  Edits made through `p.data` (p.data.copy_(), p.data.mul_(), EMA swaps, hand-written
+        SGD) do NOT bump the version counter: call invalidate_packed() after them.  load_state_dict(), train(),
+        eval() and .to()/.cuda()/.float() invalidate automatically."""
+        self._packed.clear()
+        return self
+
+    def load_state_dict(self, *args, **kwargs):
+        self._packed.clear()
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode: bool = True):
+        self._packed.clear()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed.clear()
+        return super()._apply(fn, *args, **kwargs)
 
     # ------------------------------------------------------------------ weights
     def _check_supported(self):
@@ -90,8 +113,15 @@ class FluxGNN(nn.Module):
                                "fluxgnn_pack_weights" + ("_tc" if layout == "tc" else ""))
                 # `small` must outlive the (asynchronous) packing kernel: same-stream
                 # allocator reuse is ordered after it, so dropping the references is safe.
-            hit = (key, packed)
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(dev))
+            hit = (key, packed, ready, stream)
             self._packed[layout] = hit
+        # a consumer on another stream must not read the buffer before the packing kernel has run
+        # (inside a graph capture an outside event cannot be waited on: pack before capturing)
+        cur = torch.cuda.current_stream(dev)
+        if cur.cuda_stream != hit[3] and not torch.cuda.is_current_stream_capturing():
+            cur.wait_event(hit[2])
         return hit[1]
 
     # ------------------------------------------------------------------ structured entry points

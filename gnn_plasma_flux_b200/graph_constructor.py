@@ -27,16 +27,18 @@ def ring_edge_index(nx: int, radius: int = 1, device=None) -> torch.Tensor:
         rows.extend((base, shifted))
         cols.extend((shifted, base))
     edge_index = torch.stack((torch.cat(rows), torch.cat(cols)))
-    edge_index._fluxgnn_ring = (int(nx), int(radius))
+    edge_index._fluxgnn_ring = (int(nx), int(radius), edge_index._version)
     return edge_index
 
 
 def is_ring(edge_index: torch.Tensor, num_nodes: int):
     """Return the radius if `edge_index` is the canonical ring of `num_nodes`
-    nodes, else None.  Tagged tensors are trusted; others are compared on their
+    nodes, else None.  Tagged tensors are trusted as long as they were not written
+    in place since the tag was set (version counter); others are compared on their
     own device (one small kernel + one scalar read-back)."""
     tag = getattr(edge_index, "_fluxgnn_ring", None)
-    if tag is not None and tag[0] == num_nodes and edge_index.shape[1] == 2 * tag[1] * num_nodes:
+    if (tag is not None and tag[0] == num_nodes and edge_index.shape[1] == 2 * tag[1] * num_nodes
+            and tag[2] == edge_index._version):
         return tag[1]
     if edge_index.dim() != 2 or edge_index.shape[0] != 2 or num_nodes < 1:
         return None
@@ -46,7 +48,7 @@ def is_ring(edge_index: torch.Tensor, num_nodes: int):
     radius = n_edges // (2 * num_nodes)
     want = ring_edge_index(num_nodes, radius, device=edge_index.device)
     if bool(torch.equal(edge_index.to(torch.long), want)):
-        edge_index._fluxgnn_ring = (int(num_nodes), int(radius))
+        edge_index._fluxgnn_ring = (int(num_nodes), int(radius), edge_index._version)
         return radius
     return None
 

@@ -40,6 +40,13 @@ class PeriodicGrid:
                     stream = torch.cuda.current_stream(device).cuda_stream
                     _lib.check(_lib.lib().fluxgnn_poisson_table(self.nx, self.length, gtab.data_ptr(), stream),
                                "fluxgnn_poisson_table")
-            hit = (x_dev, gtab)
+                stream = torch.cuda.current_stream(device)
+                ready = torch.cuda.Event()
+                ready.record(stream)
+            hit = (x_dev, gtab, ready, stream.cuda_stream)
             self._dev[key] = hit
-        return hit
+        # a consumer on another stream waits for the table kernel / H2D copy of the first call
+        cur = torch.cuda.current_stream(device)
+        if cur.cuda_stream != hit[3] and not torch.cuda.is_current_stream_capturing():
+            cur.wait_event(hit[2])
+        return hit[0], hit[1]

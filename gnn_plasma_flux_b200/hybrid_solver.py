@@ -60,6 +60,11 @@ class HybridSolver:
         if state.device != dev or state.dtype != torch.float32 or not state.is_contiguous():
             state = state.to(device=dev, dtype=torch.float32).contiguous()
         B, _, nx = state.shape
+        if n_steps < 0:
+            raise ValueError(f"n_steps must be >= 0, got {n_steps}")
+        if n_steps == 0:                      # the reference's loop does not run (src/hybrid_solver.py:69): [state0]
+            final = state.clone() if out is None else out.copy_(state)
+            return final, (state.new_empty((0, B, 3, nx)) if record_every else None)
         x_dev, gtab = base.grid.tables(dev)
         with torch.cuda.device(dev):
             if out is None:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FLUXGNN_ABI_VERSION 1
+#define FLUXGNN_ABI_VERSION 2
 
 #define FLUXGNN_OK        0
 #define FLUXGNN_EINVAL   -1   /* bad argument (shape, null pointer, unsupported size) */
@@ -246,6 +246,47 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision,
                              const float* state_ext, const float* x_ext, float* state_out,
                              int B, int owned, int halo, int radius, float c, float dt, void* stream);
 
+/* The same slab step writing into a row-strided output: n' and u' of cell i go to
+ * state_out[ic][0..1][out_off + i] of an array [B][3][out_ld].  With out_ld = owned + 2*halo and
+ * out_off = halo the slab writes the interior of the NEXT extended state directly (the ghost cells
+ * are then filled by the neighbours' halo stores / sends): no concatenation on the step path. */
+int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precision,
+                                const float* state_ext, const float* x_ext, float* state_out,
+                                int out_ld, int out_off, int B, int owned, int halo, int radius,
+                                float c, float dt, void* stream);
+
+/* ---- one slab of the classical solver (baseline-only domain decomposition) ------
+ * src/baseline_solver.py:80-94 (upwind fluxes, viscous Laplacian, forward Euler) for `owned`
+ * consecutive cells of a longer periodic grid:  state_ext[B][3][owned + 2*halo] carries `halo` >= 1
+ * ghost cells per side (the stencil reads one; halo = 4 keeps 128-bit loads aligned).  n', u' are
+ * written as in fluxgnn_hybrid_slab_step_ld; E' comes from the distributed field solve.
+ * flux_n: nullable [B][owned], the continuity flux F_n. */
+int fluxgnn_baseline_slab_step(const float* state_ext, float* state_out, int out_ld, int out_off,
+                               float* flux_n, int B, int owned, int halo,
+                               float c, float dt, float nu, float dx2, void* stream);
+
+/* ---- distributed field solve ("distributed FFT via all-to-all") --------------------------
+ * The operator of src/baseline_solver.py:59-68 for ONE periodic grid of nx = G*S cells whose rank r
+ * (r < G, G and S powers of two, S >= 256, G <= 16) holds cells [r*S, (r+1)*S) of B density rows.
+ * Two rows (ICs 2p, 2p+1) travel as one complex signal z = (n_a - 1) + i (n_b - 1): the multiplier
+ * i/k is then diagonal and the result is E_a + i E_b.  P = ceil(B/2).  The nx-point transform is
+ * decimated in frequency over the rank index (element jr*S + jl, bin kr + G*kl).  Per step and rank:
+ *   1. fluxgnn_poisson_dist_pack      n[B][S] (row stride ic_stride) -> z[P][S]
+ *   2. all-to-all (the caller's; NCCL): flat z cut into G equal chunks, chunk q -> rank q
+ *   3. fluxgnn_poisson_dist_rank_dft  in[G][chunk] (chunk of every rank) -> out[G][chunk] (for every rank),
+ *                                     flat0 = rank*chunk is the flat index of the chunk's first element
+ *   4. all-to-all -> y[P][S], the rank's own share of the spectrum's input
+ *   5. fluxgnn_poisson_dist_local     y in place: FFT_S, diagonal multiplier of bins rank + G*kl, inverse FFT_S
+ *                                     (scratch: P*S complex numbers, needed above S = 2^14)
+ *   6. all-to-all, fluxgnn_poisson_dist_rank_dft(inverse = 1), all-to-all -> e[P][S] = E_a + i E_b
+ *   7. fluxgnn_poisson_dist_unpack    e -> E[B][S] (row stride ic_stride, e.g. the E channel of an extended state)
+ * With G = 1 steps 2-4 and 6 are the identity and the result equals fluxgnn_poisson_spectral to rounding. */
+int fluxgnn_poisson_dist_pack(const float* n, long long ic_stride, int B, int S, void* z, void* stream);
+int fluxgnn_poisson_dist_unpack(const void* e, float* E, long long ic_stride, int B, int S, void* stream);
+int fluxgnn_poisson_dist_rank_dft(const void* in, void* out, int G, long long chunk, long long flat0, int S,
+                                  int inverse, void* stream);
+int fluxgnn_poisson_dist_local(void* y, void* scratch, int P, int S, int G, int rank, double length, void* stream);
+
 /* ---- BaselineSolver.step / .run ------------------------------------------------
  * Replaces src/baseline_solver.py:70-118: upwind continuity flux n*u,
  * left-differenced u^2/2, viscous Laplacian, forward Euler, field solve.
@@ -276,6 +317,10 @@ int fluxgnn_pure_gnn_pack(const float* w_in, const float* b_in, const float* w_u
 int fluxgnn_pure_gnn_rollout(const void* packed, int hidden, int num_layers,
                              const float* state_in /* [B][3][nx] */, float* state_out,
                              const float* x, int B, int nx, int steps, void* stream);
+/* PureGNN.forward itself (train_pure_gnn.py:57-76): delta_out[B][3][nx] = the model output, NOT added to the state. */
+int fluxgnn_pure_gnn_delta(const void* packed, int hidden, int num_layers,
+                           const float* state /* [B][3][nx] */, float* delta_out,
+                           const float* x, int B, int nx, void* stream);
 int fluxgnn_dense_layer(const float* in, const float* weight, const float* bias,
                         const float* residual /* nullable */, float* out,
                         int rows, int in_features, int out_features, int activation, void* stream);

@@ -237,6 +237,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "g8_gradients.npz"), **g8)
 
     comparison_goldens()
+    long_rollout_goldens()
 
     manifest = {
         "generated_by": "oracle/make_golden.py",
@@ -249,6 +250,60 @@ def main():
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1)
     print("goldens written to", OUT)
+
+
+def reference_radius_run(ref_model, ref_base, state0, n_steps, radius, every):
+    """The reference's HybridSolver.step/run arithmetic (src/hybrid_solver.py:34-73) driven with the
+    REFERENCE objects -- its FluxGNN.forward fed the radius-r ring, its BaselineSolver.solve_poisson --
+    for graph radii the reference's own step cannot take (it slices `flux_edge[nx:]`, :46, which only has
+    the right length on the nearest-neighbour ring).  Only hop 1 enters the face flux."""
+    nx = ref_base.nx
+    edges = torch.from_numpy(P.ring_edges(nx, radius))
+    c = ref_base.dt / ref_base.dx
+    state = state0.astype(np.float32)
+    snaps = [state]
+    for t in range(1, n_steps + 1):
+        n, u, E = state
+        nf, _ = build_chain_graph(state, ref_base.x)
+        with torch.no_grad():
+            flux = ref_model(nf, edges).cpu().numpy()
+        face = 0.5 * (flux[:nx] + flux[nx:2 * nx]).astype(np.float32)
+        n_new = n - c * (face - np.roll(face, 1))
+        fu = 0.5 * u * u
+        u_new = (u - c * (fu - np.roll(fu, 1))) + ref_base.dt * E
+        state = np.stack([n_new, u_new, ref_base.solve_poisson(n_new)], axis=0).astype(np.float32)
+        if t % every == 0:
+            snaps.append(state)
+    return np.stack(snaps, axis=0)
+
+
+def long_rollout_goldens():
+    """G6b: the long-rollout gate at the radii BASELINE.json's configs really use -- C2 (nx=64, radius 3,
+    1000 steps) and C3 (nx=1024, radius 2, 300 steps): reference objects in fp32 + the fp64 restatement.
+    `python -m oracle.make_golden --only-g6b` regenerates just this file."""
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    ref_model = FluxGNN(input_dim=4, hidden_dim=128, num_layers=4).eval()
+    weights = {k: v.numpy().copy() for k, v in ref_model.state_dict().items()}
+    out = {}
+    for tag, nx, dt, radius, steps, every, n_ics in (("c2", 64, 1e-3, 3, 1000, 100, 4), ("c3", 1024, 3e-4, 2, 300, 100, 2)):
+        base = BaselineSolver(nx=nx, dt=dt)
+        g = P.Grid(nx=nx, dt=dt)
+        ics = np.stack([P.stable_initial_condition(g, 50 + s) for s in range(n_ics)])
+        s32, s64 = [], []
+        for i, ic in enumerate(ics):
+            r32 = reference_radius_run(ref_model, base, ic, steps, radius, every)
+            assert np.isfinite(r32).all()
+            if i == 0:          # the port walks the same trajectory bit for bit
+                same(P.hybrid_run(weights, ic, g, steps, radius=radius)[::every], r32, f"hybrid_run {tag} r={radius} {steps} steps")
+            s32.append(r32)
+            s64.append(P.hybrid_run(weights, ic, g, steps, radius=radius, dtype=torch.float64)[::every])
+        s32, s64 = np.stack(s32), np.stack(s64)
+        print(f"      {tag}: reference fp32 vs fp64 after {steps} steps (n,u,E):", P.rel_err(s32[:, -1], s64[:, -1]))
+        out.update({f"{tag}_ics": ics, f"{tag}_ref_fp32": s32, f"{tag}_fp64": s64, f"{tag}_dt": dt, f"{tag}_nx": nx,
+                    f"{tag}_radius": radius, f"{tag}_steps": steps, f"{tag}_every": every})
+    np.savez_compressed(os.path.join(OUT, "g6b_long_rollout_radius.npz"), **out)
+    print("  wrote g6b_long_rollout_radius.npz")
 
 
 def comparison_goldens():
@@ -307,5 +362,7 @@ def comparison_goldens():
 if __name__ == "__main__":
     if "--only-g9" in sys.argv:
         comparison_goldens()
+    elif "--only-g6b" in sys.argv:
+        long_rollout_goldens()
     else:
         main()

@@ -16,6 +16,7 @@ from oracle import batched, ref_port as P
 
 pytestmark = pytest.mark.gpu
 STEP_TOL = 1e-5
+LONG_TOL = 1e-4          # north_star: <= 1e-4 over a 1000-step rollout, flat, against the reference's fp32 trajectory
 
 
 @pytest.fixture(scope="module")
@@ -335,13 +336,41 @@ def test_long_rollout_1000_steps(model):
     vs64 = P.rel_err(ours[:, -1], g6["fp64"][:, -1])
     vs32 = P.rel_err(ours[:, -1], g6["ref_fp32"][:, -1])
     print("1000-step rel err: reference-vs-fp64", floor, "ours-vs-fp64", vs64, "ours-vs-reference", vs32)
-    # <= 1e-4, or within 2x of the reference's own distance from the fp64 trajectory where that is larger
-    assert (vs64 <= np.maximum(1e-4, 2.0 * floor)).all()
-    assert (vs32 <= np.maximum(1e-4, 3.0 * floor)).all()
+    # vs the reference's own fp32 trajectory: flat 1e-4 (north_star); vs fp64 the reference itself is up to
+    # 1.8e-4 away (its E channel), so that comparison is gated relative to the reference's own distance
+    assert (vs32 <= LONG_TOL).all()
+    assert (vs64 <= np.maximum(LONG_TOL, 2.0 * floor)).all()
     # total mass conserved to round-off (flux form telescopes)
     mass0 = g6["ics"][:, 0].astype(np.float64).sum(-1)
     massT = ours[:, -1, 0].astype(np.float64).sum(-1)
     assert np.abs(massT - mass0).max() <= 1000 * 64 * np.finfo(np.float32).eps
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "tf32x3"])
+@pytest.mark.parametrize("tag", ["c2", "c3"])
+def test_long_rollout_at_config_radius(model, precision, tag):
+    """The long-rollout gate at the radii BASELINE.json's configs use (golden g6b: the reference's own
+    FluxGNN.forward on the radius-r ring + its FV / field-solve arithmetic): C2 = 64 cells, radius 3,
+    1000 steps; C3 = 1024 cells (window tiles + FFT), radius 2, 300 steps.  Flat 1e-4 against the
+    reference's fp32 trajectory at every recorded snapshot; mass conserved to round-off."""
+    g = load_golden("g6b_long_rollout_radius.npz")
+    nx, dt, r = int(g[f"{tag}_nx"]), float(g[f"{tag}_dt"]), int(g[f"{tag}_radius"])
+    steps, every = int(g[f"{tag}_steps"]), int(g[f"{tag}_every"])
+    ics, ref32, ref64 = g[f"{tag}_ics"], g[f"{tag}_ref_fp32"], g[f"{tag}_fp64"]
+    sol = make_solver(model, nx, dt, graph_radius=r, precision=precision)
+    final, traj = sol.rollout(torch.from_numpy(ics).cuda(), steps, record_every=every)
+    ours = np.moveaxis(traj.cpu().numpy(), 0, 1)                               # [ICs, snaps, 3, nx]
+    assert np.isfinite(ours).all()
+    np.testing.assert_array_equal(ours[:, -1], final.cpu().numpy())
+    for k in range(ours.shape[1]):
+        vs32 = P.rel_err(ours[:, k], ref32[:, k + 1])
+        assert (vs32 <= LONG_TOL).all(), (k, vs32)
+    floor = P.rel_err(ref32[:, -1], ref64[:, -1])
+    vs64 = P.rel_err(ours[:, -1], ref64[:, -1])
+    print(f"{tag} {precision} {steps} steps: ours-vs-reference {vs32}, ours-vs-fp64 {vs64}, reference-vs-fp64 {floor}")
+    assert (vs64 <= np.maximum(LONG_TOL, 2.0 * floor)).all()
+    mass0 = ics[:, 0].astype(np.float64).sum(-1)
+    assert np.abs(ours[:, -1, 0].astype(np.float64).sum(-1) - mass0).max() <= steps * nx * np.finfo(np.float32).eps
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
@@ -495,8 +524,8 @@ def test_tc_long_rollout_1000_steps(model):
         vs32 = P.rel_err(final, g6["ref_fp32"][:, -1])
         print(f"1000 steps {precision}: vs fp64 {vs64}, vs reference fp32 {vs32} (reference-vs-fp64 floor {floor})")
         if precision in SPLIT_MODES:
-            assert (vs64 <= np.maximum(1e-4, 2.0 * floor)).all()
-            assert (vs32 <= np.maximum(1e-4, 3.0 * floor)).all()
+            assert (vs32 <= LONG_TOL).all()
+            assert (vs64 <= np.maximum(LONG_TOL, 2.0 * floor)).all()
         else:
             assert (vs32 <= (2e-3 if precision == "bf16" else 1e-3)).all()       # documented looser tolerances (measured 4e-4 / 1.3e-4)
         mass0 = g6["ics"][:, 0].astype(np.float64).sum(-1)
@@ -548,8 +577,8 @@ def test_tc_rejects_unsupported_shapes(model):
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("world,nx,radius", [(1, 1 << 12, 2), (2, 1 << 12, 3), (4, 1 << 15, 3), (8, 1 << 15, 1), (8, 1000, 2)])
 def test_domain_decomposition_emulated_ranks(model, weights, precision, world, nx, radius):
-    """G virtual ranks on one GPU (slab kernel + ghost cells + global field solve) reproduce the
-    undivided solver bit for bit, and the oracle within the step tolerance."""
+    """G virtual ranks on one GPU (slab kernel + ghost cells + all-gathered density + replicated field solve)
+    reproduce the undivided solver bit for bit, and the oracle within the step tolerance."""
     from gnn_plasma_flux_b200.domain import DomainDecomposedHybridSolver, split_slabs, step_emulated
     if nx % world:
         pytest.skip("grid not divisible")
@@ -559,7 +588,7 @@ def test_domain_decomposition_emulated_ranks(model, weights, precision, world, n
     whole = make_solver(model, nx, dt, graph_radius=radius, precision=precision)
     dev = torch.from_numpy(ics).cuda()
     solvers = [DomainDecomposedHybridSolver(model, nx, dt=dt, graph_radius=radius, rank=r, world=world,
-                                            device="cuda", precision=precision) for r in range(world)]
+                                            device="cuda", precision=precision, field_solve="allgather") for r in range(world)]
     locals_ = split_slabs(dev, world)
     ref = dev
     for _ in range(3):
@@ -570,6 +599,91 @@ def test_domain_decomposition_emulated_ranks(model, weights, precision, world, n
     if nx <= (1 << 12):
         orc = batched.hybrid_run(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, 3, radius=radius).numpy()
         assert P.rel_err(got.cpu().numpy(), orc).max() <= 3 * STEP_TOL
+
+
+@pytest.mark.parametrize("world,nx,batch", [(1, 1 << 10, 2), (2, 1 << 12, 3), (4, 1 << 14, 1), (8, 1 << 16, 4), (2, 1 << 17, 2),
+                                            (16, 1 << 19, 2), (4, 1 << 20, 3)])
+def test_distributed_field_solve_emulated(built_lib, world, nx, batch):
+    """The all-to-all field solve (two ICs per complex signal, transform decimated over the rank index, diagonal
+    multiplier; slabs of 2^8..2^18 cells: one-CTA and four-step local transforms) against the single-GPU
+    solve of this package and the fp64 operator, incl. a Nyquist component and a non-zero mean."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    from gnn_plasma_flux_b200.domain import DistributedFieldSolve, solve_emulated
+    rng = np.random.RandomState(nx % 1000 + world)
+    x = np.linspace(0, 2 * np.pi, nx, endpoint=False)
+    dens = np.stack([1.3 + 0.2 * np.sin((b + 1) * x + b) + 0.05 * np.cos(37 * x) + 0.1 * np.cos(np.pi * np.arange(nx))
+                     + 0.02 * rng.randn(nx) for b in range(batch)]).astype(np.float32)
+    n = torch.from_numpy(dens).cuda()
+    want = BaselineSolver(nx=nx, device="cuda").solve_poisson(n)
+    S = nx // world
+    solvers = [DistributedFieldSolve(nx, 2 * np.pi, r, world, "cuda") for r in range(world)]
+    E = torch.zeros_like(n)
+    solve_emulated(solvers, [n[:, r * S:(r + 1) * S] for r in range(world)], [E[:, r * S:(r + 1) * S] for r in range(world)])
+    scale = float(want.abs().max())
+    assert float((E - want).abs().max()) <= 2e-6 * scale
+    k = 2 * np.pi * np.fft.fftfreq(nx, d=2 * np.pi / nx)
+    spec = np.fft.fft(dens.astype(np.float64) - 1.0, axis=-1)
+    mult = np.zeros(nx, dtype=np.complex128)
+    mult[k != 0] = 1j / k[k != 0]
+    exact = np.real(np.fft.ifft(spec * mult, axis=-1))
+    assert np.abs(E.cpu().numpy() - exact).max() <= 2e-6 * np.abs(exact).max()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("world,nx,radius", [(1, 1 << 12, 2), (2, 1 << 12, 3), (4, 1 << 15, 3), (8, 1 << 15, 1)])
+def test_domain_decomposition_alltoall_emulated_ranks(model, weights, precision, world, nx, radius):
+    """The default decomposition (distributed field solve) on G virtual ranks: n', u' of the first step are
+    bit-identical to the undivided solver (same slab arithmetic, same inputs), E' agrees to rounding, and three
+    steps stay within the step tolerance of the undivided solver and of the oracle."""
+    from gnn_plasma_flux_b200.domain import DomainDecomposedHybridSolver, split_slabs, step_emulated
+    dt = 0.02 * (2 * np.pi / nx)
+    grid = P.Grid(nx=nx, dt=dt)
+    ics = np.stack([P.stable_initial_condition(grid, s) for s in range(3)])
+    whole = make_solver(model, nx, dt, graph_radius=radius, precision=precision)
+    dev = torch.from_numpy(ics).cuda()
+    solvers = [DomainDecomposedHybridSolver(model, nx, dt=dt, graph_radius=radius, rank=r, world=world,
+                                            device="cuda", precision=precision) for r in range(world)]
+    assert solvers[0].field_mode == "alltoall"
+    locals_ = split_slabs(dev, world)
+    ref = dev
+    for t in range(3):
+        locals_ = step_emulated(solvers, locals_)
+        ref, _ = whole.rollout(ref, 1)
+        got = torch.cat(list(locals_), dim=-1)
+        if t == 0:
+            assert torch.equal(got[:, :2], ref[:, :2])
+            assert float((got[:, 2] - ref[:, 2]).abs().max()) <= 2e-6 * float(ref[:, 2].abs().max())
+    assert P.rel_err(got.cpu().numpy(), ref.cpu().numpy()).max() <= STEP_TOL
+    if nx <= (1 << 12):
+        orc = batched.hybrid_run(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, 3, radius=radius).numpy()
+        assert P.rel_err(got.cpu().numpy(), orc).max() <= 3 * STEP_TOL
+
+
+@pytest.mark.parametrize("world,nx,field_solve", [(1, 1 << 12, "alltoall"), (4, 1 << 14, "alltoall"), (8, 1 << 20, "alltoall"),
+                                                  (4, 1000, "allgather"), (2, 1 << 16, "allgather")])
+def test_baseline_domain_decomposition_emulated_ranks(built_lib, world, nx, field_solve):
+    """SURVEY 8e, baseline-only row: the classical step on G virtual ranks (halo exchange, fluxgnn_baseline_slab_step,
+    field solve) against the undivided BaselineSolver: bit-exact with the replicated solve; with the distributed
+    solve n', u' of the first step bit-exact and five steps within the step tolerance."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    from gnn_plasma_flux_b200.domain import DomainDecomposedBaselineSolver, split_slabs, step_emulated
+    dt = 0.2 * (2 * np.pi / nx) ** 2 / 1e-3
+    whole = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device="cuda")
+    grid = P.Grid(nx=nx, dt=dt)
+    dev = torch.from_numpy(np.stack([P.stable_initial_condition(grid, s) for s in range(3)])).cuda()
+    solvers = [DomainDecomposedBaselineSolver(nx, dt=dt, nu=1e-3, rank=r, world=world, device="cuda", field_solve=field_solve)
+               for r in range(world)]
+    locals_ = split_slabs(dev, world)
+    ref = dev
+    for t in range(5):
+        locals_ = step_emulated(solvers, locals_)
+        ref = whole.rollout(ref, 1)[0]
+        got = torch.cat(list(locals_), dim=-1)
+        if field_solve == "allgather":
+            assert torch.equal(got, ref), t
+        elif t == 0:
+            assert torch.equal(got[:, :2], ref[:, :2])
+    assert P.rel_err(got.cpu().numpy(), ref.cpu().numpy()).max() <= STEP_TOL
 
 
 # ----------------------------------------------------------------------------- BaselineSolver

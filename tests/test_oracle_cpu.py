@@ -115,6 +115,28 @@ def test_long_rollout_noise_floor_golden():
     assert np.abs(massT - mass0).max() < 1000 * 64 * np.finfo(np.float32).eps
 
 
+def test_long_rollout_at_config_radius_golden(weights):
+    """g6b: the port walks the reference-object trajectory bit for bit at the radii of C2 / C3
+    (first 100 steps of one IC each), and the frozen fp32 trajectories stay finite and conserve mass."""
+    torch.set_num_threads(1)
+    g = load_golden("g6b_long_rollout_radius.npz")
+    for tag in ("c2", "c3"):
+        nx, dt, r, every = int(g[f"{tag}_nx"]), float(g[f"{tag}_dt"]), int(g[f"{tag}_radius"]), int(g[f"{tag}_every"])
+        grid = P.Grid(nx=nx, dt=dt)
+        ic = g[f"{tag}_ics"][0]
+        np.testing.assert_array_equal(P.stable_initial_condition(grid, 50), ic)
+        steps = every if tag == "c2" else 10
+        run = P.hybrid_run(weights, ic, grid, steps, radius=r)
+        np.testing.assert_array_equal(run[0], g[f"{tag}_ref_fp32"][0, 0])
+        if tag == "c2":
+            np.testing.assert_array_equal(run[every], g[f"{tag}_ref_fp32"][0, 1])
+        ref32 = g[f"{tag}_ref_fp32"]
+        assert np.isfinite(ref32).all()
+        T = int(g[f"{tag}_steps"])
+        mass0 = ref32[:, 0, 0].astype(np.float64).sum(-1)
+        assert np.abs(ref32[:, -1, 0].astype(np.float64).sum(-1) - mass0).max() < T * nx * np.finfo(np.float32).eps
+
+
 def test_metrics_and_datagen_golden():
     """the oracle's restatements of evaluate_all.compute_metrics and
     generate_data.generate_dataset against outputs of the reference's own functions."""
