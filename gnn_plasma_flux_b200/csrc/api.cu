@@ -318,9 +318,11 @@ size_t fluxgnn_hybrid_workspace_bytes(int B, int nx) {
     return (size_t)B * 3 * nx * sizeof(float) + fluxgnn_poisson_workspace_bytes(B, nx);
 }
 
+// workspace = [state ping-pong buffer][FFT scratch][tile-major n, u and halo side arrays of the fused step]
 size_t fluxgnn_baseline_workspace_bytes(int B, int nx) {
     if (B < 1 || nx < 1) return 0;
-    return (size_t)B * 3 * nx * sizeof(float) + fluxgnn_poisson_workspace_bytes(B, nx);
+    return (size_t)B * 3 * nx * sizeof(float) + fluxgnn_poisson_workspace_bytes(B, nx) +
+           baseline_fused_workspace_floats(B, nx) * sizeof(float);
 }
 
 }  // extern "C"
@@ -629,6 +631,33 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const doub
     const long long cells = (long long)B * nx;
     long long blocks = (((nx & 3) == 0 ? cells / 4 : cells) + 255) / 256;
     if (blocks > (long long)sms * 64) blocks = (long long)sms * 64;
+    // Long grids, no recording: after the first step the inverse column stages, the finite-volume update and the
+    // forward column stages of consecutive steps run as one kernel (fft_poisson.cu, "fused classical step"): two
+    // launches and 32 bytes per cell-update instead of four and 44.  FLUXGNN_BASELINE_NO_FUSE=1 is the test hook.
+    const char* nofuse = getenv("FLUXGNN_BASELINE_NO_FUSE");
+    if (steps >= 3 && !traj && !flux_n && baseline_fused_supported(nx) && B <= 65535 &&
+        !(nofuse != nullptr && nofuse[0] == '1')) {
+        float* tmp = (float*)workspace;                                    // natural-layout state after step 1
+        float2* Y = (float2*)fft_ws;
+        float* fused_ws = (float*)fft_ws + fluxgnn_poisson_workspace_bytes(B, nx) / sizeof(float);
+        baseline_fv_kernel<<<(unsigned)blocks, 256, 0, stream>>>(state_in, tmp, nullptr, B, nx, c, dt, nu, dx2);
+        FLUXGNN_CUDA_OK(cudaGetLastError());
+        count_launch();
+        rc = launch_baseline_to_tiles(tmp, fused_ws, 0, B, nx, stream);
+        if (rc != FLUXGNN_OK) return rc;
+        rc = launch_poisson_fft_cols(tmp, 3LL * nx, Y, nullptr, 0, B, nx, 0, stream);
+        if (rc != FLUXGNN_OK) return rc;
+        rc = launch_poisson_fft_rows(Y, B, nx, length, stream);
+        if (rc != FLUXGNN_OK) return rc;
+        for (int t = 1; t < steps; ++t) {
+            rc = launch_baseline_fused_cols(Y, fused_ws, (t - 1) & 1, t == steps - 1 ? state_out : nullptr, B, nx, c, dt, nu,
+                                            dx2, stream);
+            if (rc != FLUXGNN_OK) return rc;
+            rc = launch_poisson_fft_rows(Y, B, nx, length, stream);
+            if (rc != FLUXGNN_OK) return rc;
+        }
+        return launch_poisson_fft_cols(nullptr, 0, Y, state_out + 2 * (size_t)nx, 3LL * nx, B, nx, 1, stream);
+    }
     const float* src = state_in;
     for (int t = 0; t < steps; ++t) {
         float* dst = ((steps - 1 - t) % 2 == 0) ? state_out : (float*)workspace;

@@ -719,6 +719,152 @@ __global__ void __launch_bounds__(kFftStepThreads, FLUXGNN_FFT_ROW_CTAS) poisson
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused classical step for long grids (BASELINE.json configs[4]; src/baseline_solver.py:80-101).
+// Inside a multi-step rollout the field E_s is consumed only by the next finite-volume update, and that update
+// is cell-local except for one neighbour on each side.  So pass C of step s (inverse column stages -> E_s), the
+// finite-volume update s -> s+1 and pass A of step s+1 (forward column stages of rho' = n' - 1) run as ONE column
+// kernel: the thread that ends the inverse network with E of 16 (row, column) positions in registers is the thread
+// that starts the forward network with rho' of the same positions.  Per step and cell the kernel reads the
+// spectrum (4 B), n and u (8 B) and writes n', u' (8 B) and the new spectrum (4 B): 24 B, plus 8 B for the row
+// kernel = 32 B per cell-update instead of 44, in 2 launches instead of 4; E is never written between steps.
+// Between steps n and u live in a TILE-MAJOR private layout P[b][tile][row j1][2T floats] -- the 2T cells a column
+// tile owns in matrix row j1 are contiguous and a whole tile is one contiguous block, so a warp's accesses are
+// 256 contiguous bytes instead of eight 32-byte pieces 32 KiB apart -- and the three neighbour values a tile needs
+// per matrix row travel through side arrays H[b][3][tile][j1] (last n, last u, first u of the tile's row), which
+// the owning tile writes and its neighbours read as contiguous runs.  Both are double-buffered.
+// ---------------------------------------------------------------------------
+struct FusedColsArgs {
+    float2* Y;                       // [B][N1][4096] spectrum, transformed in place tile by tile
+    const float* Pn_in;              // tile-major n, u of the current step
+    const float* Pu_in;
+    float* Pn_out;
+    float* Pu_out;
+    const float* H_in;               // [B][3][tiles][N1]
+    float* H_out;
+    float* nat_out;                  // nullable [B][3][nx]: n', u' also in the natural layout (last step of a rollout)
+    float c, dt, nu, dx2;
+};
+
+template <int BITS1, int TILE_BITS, int LB, int THREADS>
+__device__ __forceinline__ void columns_inverse_to_smem(const float2* gin, float2* s, int j2_0) {
+    if constexpr (LB < BITS1) {
+        column_pass<BITS1, TILE_BITS, LB, true, THREADS>(gin, nullptr, s, j2_0);
+        columns_inverse_to_smem<BITS1, TILE_BITS, LB + 4, THREADS>(gin, s, j2_0);
+    }
+}
+
+template <int BITS1>
+__global__ void __launch_bounds__(column_threads(BITS1), column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
+baseline_fused_cols_kernel(FusedColsArgs a) {
+    extern __shared__ float2 sfft[];
+    constexpr int TILE_BITS = column_tile_bits(BITS1), THREADS = column_threads(BITS1);
+    constexpr int TB = TILE_BITS - BITS1, T = 1 << TB, N1 = 1 << BITS1;
+    constexpr int SUBB = BITS1 - 4;               // the middle pass is the radix-16 pass over whole columns
+    constexpr int ITEMS = (1 << TILE_BITS) >> 4, ITERS = ITEMS / THREADS;
+    static_assert(BITS1 >= 5 && T <= 32 && ITEMS % THREADS == 0, "fused column kernel: unsupported tile");
+    const int tile = blockIdx.x, tiles = gridDim.x, b = blockIdx.y;
+    const int j2_0 = tile << TB;
+    float2* Y = a.Y + ((size_t)b << (BITS1 + kRowBits));
+    // ---- pass C of the previous step, all but its last stage set ----
+    columns_inverse_to_smem<BITS1, TILE_BITS, first_inverse_lb(BITS1), THREADS>(Y, sfft, j2_0);
+    const size_t pcells = (size_t)N1 << (kRowBits + 1);               // cells per IC
+    const float2* Pn = reinterpret_cast<const float2*>(a.Pn_in + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
+    const float2* Pu = reinterpret_cast<const float2*>(a.Pu_in + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
+    float2* Qn = reinterpret_cast<float2*>(a.Pn_out + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
+    float2* Qu = reinterpret_cast<float2*>(a.Pu_out + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
+    const size_t hplane = (size_t)tiles << BITS1;
+    const float* Hin = a.H_in + (size_t)b * 3 * hplane;
+    float* Hout = a.H_out + (size_t)b * 3 * hplane;
+    const int lane_t = threadIdx.x & (T - 1);
+    const uint64_t pol_first = make_policy<Hint::kFirst>();
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int w = threadIdx.x + it * THREADS;
+        const int t = w & (T - 1), base = w >> TB;                    // rows base + m*SUB, column t
+        float2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = sfft[cpad(((base + (m << SUBB)) << TB) + t)];
+        TwiddleSet<16> pw;
+        pw.init(unit_root((base << kRowBits) + j2_0 + t, BITS1 + kRowBits, +1.f));
+        pw.apply(v);
+        DitStages<16>::run(v, +1.f);                                   // v[m] = (E_2j, E_2j+1) at (row base + m*SUB, column t)
+        // ---- finite-volume update of the two cells of every position (src/baseline_solver.py:84-94) ----
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int j1 = base + (m << SUBB);
+            const size_t e = ((size_t)j1 << TB) + t;
+            const float2 n2 = gload<Hint::kFirst>(Pn + e, pol_first), u2 = gload<Hint::kFirst>(Pu + e, pol_first);
+            // neighbours inside the tile row come from the adjacent lanes, across the tile edge from the side arrays
+            float nl = __shfl_up_sync(0xffffffffu, n2.y, 1), ul = __shfl_up_sync(0xffffffffu, u2.y, 1);
+            float ur = __shfl_down_sync(0xffffffffu, u2.x, 1);
+            if (lane_t == 0) {
+                int tl = tile - 1, jl = j1;
+                if (tl < 0) { tl = tiles - 1; jl = (j1 == 0) ? N1 - 1 : j1 - 1; }
+                const size_t h = ((size_t)tl << BITS1) + jl;
+                nl = __ldg(Hin + h);
+                ul = __ldg(Hin + hplane + h);
+            }
+            if (lane_t == T - 1) {
+                int tr = tile + 1, jr = j1;
+                if (tr == tiles) { tr = 0; jr = (j1 == N1 - 1) ? 0 : j1 + 1; }
+                ur = __ldg(Hin + 2 * hplane + ((size_t)tr << BITS1) + jr);
+            }
+            const FvOut c0 = fv_cell(nl, n2.x, ul, u2.x, u2.y, v[m].x, a.c, a.dt, a.nu, a.dx2);
+            const FvOut c1 = fv_cell(n2.x, n2.y, u2.x, u2.y, ur, v[m].y, a.c, a.dt, a.nu, a.dx2);
+            Qn[e] = make_float2(c0.n, c1.n);
+            Qu[e] = make_float2(c0.u, c1.u);
+            const size_t hme = ((size_t)tile << BITS1) + j1;
+            if (lane_t == T - 1) {
+                Hout[hme] = c1.n;
+                Hout[hplane + hme] = c1.u;
+            }
+            if (lane_t == 0) Hout[2 * hplane + hme] = c0.u;
+            if (a.nat_out != nullptr) {
+                float2* so = reinterpret_cast<float2*>(a.nat_out + (size_t)b * 3 * pcells) + ((size_t)j1 << kRowBits) + j2_0 + t;
+                so[0] = make_float2(c0.n, c1.n);
+                so[pcells >> 1] = make_float2(c0.u, c1.u);
+            }
+            v[m] = make_float2(__fsub_rn(c0.n, 1.0f), __fsub_rn(c1.n, 1.0f));      // rho' = n' - n0
+        }
+        // ---- first stage set of pass A of the next step ----
+        DifStages<16>::run(v, -1.f);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pw.pw[q].y = -pw.pw[q].y;         // W^-1 powers = conjugates
+        pw.apply(v);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sfft[cpad(((base + (m << SUBB)) << TB) + t)] = v[m];
+    }
+    __syncthreads();
+    columns_forward<BITS1, TILE_BITS, SUBB, THREADS>(nullptr, Y, sfft, j2_0);
+}
+
+// natural [B][3][nx] -> tile-major n, u and the halo side arrays (once per fused rollout).  TB = log2(columns per tile).
+__global__ void __launch_bounds__(256) baseline_to_tiles_kernel(const float* __restrict__ state, float* __restrict__ Pn,
+                                                                float* __restrict__ Pu, float* __restrict__ H, int bits1,
+                                                                int tb, int B) {
+    const size_t M = (size_t)1 << (bits1 + kRowBits);
+    const int T = 1 << tb, tiles = kRowLen >> tb;
+    const size_t hplane = (size_t)tiles << bits1;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M * B; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx >> (bits1 + kRowBits));
+        const size_t j = idx & (M - 1);
+        const int j1 = (int)(j >> kRowBits), j2 = (int)(j & (kRowLen - 1)), tile = j2 >> tb, t = j2 & (T - 1);
+        const float2 n2 = reinterpret_cast<const float2*>(state + (size_t)b * 6 * M)[j];
+        const float2 u2 = reinterpret_cast<const float2*>(state + (size_t)b * 6 * M + 2 * M)[j];
+        const size_t e = (size_t)b * M + (((size_t)tile << bits1) + j1) * T + t;
+        reinterpret_cast<float2*>(Pn)[e] = n2;
+        reinterpret_cast<float2*>(Pu)[e] = u2;
+        float* Hb = H + (size_t)b * 3 * hplane;
+        const size_t hme = ((size_t)tile << bits1) + j1;
+        if (t == T - 1) {
+            Hb[hme] = n2.y;
+            Hb[hplane + hme] = u2.y;
+        }
+        if (t == 0) Hb[2 * hplane + hme] = u2.x;
+    }
+}
+
 // pass B of the distributed solve: two INDEPENDENT rows per CTA (positions 2 bx, 2 bx + 1; they share every
 // twiddle set), forward row stages, diagonal multiplier, inverse row stages, in place.  grid = (N1/2, P).
 __global__ void __launch_bounds__(kFftStepThreads, FLUXGNN_FFT_ROW_CTAS) poisson_fft_rows_diag_kernel(
@@ -912,6 +1058,54 @@ size_t poisson_fft_workspace_bytes(int B, int nx) {
     return (size_t)B * (size_t)(nx / 2) * sizeof(float2);
 }
 
+// One column pass of the four-step solve: inverse = 0: density n -> Y (pass A); 1: Y -> field E (pass C).
+int launch_poisson_fft_cols(const float* n, long long n_stride, float2* Y, float* E, long long e_stride, int B, int nx,
+                            int inverse, cudaStream_t stream) {
+    const int bits1 = ilog2_exact(nx) - 1 - kRowBits;
+    const int tile_bits = column_tile_bits(bits1);
+    const int T = 1 << (tile_bits - bits1);
+    const size_t tile = (size_t)1 << tile_bits;
+    const size_t smem = (tile + (tile >> 5) * 4) * sizeof(float2);
+    dim3 gcol((unsigned)(kRowLen / T), (unsigned)B);
+#define FLUXGNN_FFT_COLS(BITS1, WHICH, ...)                                                                          \
+    case BITS1:                                                                                                     \
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(WHICH<BITS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        WHICH<BITS1><<<gcol, column_threads(BITS1), smem, stream>>>(__VA_ARGS__);                                          \
+        break;
+#define FLUXGNN_FFT_COLS_ALL(WHICH, ...)                                                       \
+    switch (bits1) {                                                                          \
+        FLUXGNN_FFT_COLS(3, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(4, WHICH, __VA_ARGS__)       \
+        FLUXGNN_FFT_COLS(5, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(6, WHICH, __VA_ARGS__)       \
+        FLUXGNN_FFT_COLS(7, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(8, WHICH, __VA_ARGS__)       \
+        FLUXGNN_FFT_COLS(9, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(10, WHICH, __VA_ARGS__)      \
+        FLUXGNN_FFT_COLS(11, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(12, WHICH, __VA_ARGS__)     \
+        default: return set_error(FLUXGNN_EUNSUP, "four-step FFT: unsupported column length 2^%d", bits1); \
+    }
+    if (!inverse) {
+        FLUXGNN_FFT_COLS_ALL(poisson_fft_cols_fwd_kernel, n, n_stride, Y)
+    } else {
+        FLUXGNN_FFT_COLS_ALL(poisson_fft_cols_inv_kernel, Y, E, e_stride)
+    }
+#undef FLUXGNN_FFT_COLS_ALL
+#undef FLUXGNN_FFT_COLS
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+// Pass B of the four-step solve (row pairs, spectral step), in place on Y.
+int launch_poisson_fft_rows(float2* Y, int B, int nx, double length, cudaStream_t stream) {
+    const int mbits = ilog2_exact(nx) - 1, bits1 = mbits - kRowBits;
+    const size_t smem_row = (size_t)2 * kRowPad * sizeof(float2);
+    const float scale = (float)(length / (6.283185307179586476925 * (double)(1LL << mbits)));
+    dim3 grow((unsigned)((1 << bits1) / 2 + 1), (unsigned)B);
+    FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+    poisson_fft_rows_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(Y, bits1, scale);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e_stride, int B, int nx,
                        double length, void* workspace, cudaStream_t stream) {
     const int bits = ilog2_exact(nx);
@@ -934,39 +1128,88 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
     if (workspace == nullptr)
         return set_error(FLUXGNN_EINVAL, "field solve for nx=%d needs fluxgnn_poisson_workspace_bytes() of scratch", nx);
     if (B > 65535) return set_error(FLUXGNN_EUNSUP, "field solve for nx=%d handles at most 65535 ICs per call", nx);
-    const int bits1 = mbits - kRowBits;                       // 3..12
+    float2* Y = (float2*)workspace;
+    int rc = launch_poisson_fft_cols(n, n_stride, Y, nullptr, 0, B, nx, 0, stream);
+    if (rc != FLUXGNN_OK) return rc;
+    rc = launch_poisson_fft_rows(Y, B, nx, length, stream);
+    if (rc != FLUXGNN_OK) return rc;
+    return launch_poisson_fft_cols(nullptr, 0, Y, E, e_stride, B, nx, 1, stream);
+}
+
+// ---- fused classical step: host side --------------------------------------------------------------------
+bool baseline_fused_supported(int nx) {
+    const int bits = ilog2_exact(nx);
+    if (bits < 0) return false;
+    const int bits1 = bits - 1 - kRowBits;
+    return bits1 >= 8 && bits1 <= 12;                 // column tiles of 4..32 columns; nx = 2^21 .. 2^25
+}
+
+static void fused_geometry(int nx, int* bits1, int* tb, size_t* cells, size_t* hfloats) {
+    const int bits = ilog2_exact(nx);
+    *bits1 = bits - 1 - kRowBits;
+    *tb = column_tile_bits(*bits1) - *bits1;
+    *cells = (size_t)nx;
+    *hfloats = (size_t)3 * (kRowLen >> *tb) << *bits1;     // 3 planes x tiles x N1
+}
+
+size_t baseline_fused_workspace_floats(int B, int nx) {
+    if (!baseline_fused_supported(nx)) return 0;
+    int bits1, tb;
+    size_t cells, hfloats;
+    fused_geometry(nx, &bits1, &tb, &cells, &hfloats);
+    return (size_t)B * 2 * (2 * cells + hfloats);
+}
+
+// fused_ws = [slot 0: Pn | Pu | H][slot 1: Pn | Pu | H]
+static float* fused_slot(float* ws, int slot, int B, size_t cells, size_t hfloats) {
+    return ws + (size_t)slot * B * (2 * cells + hfloats);
+}
+
+int launch_baseline_to_tiles(const float* state, float* fused_ws, int slot, int B, int nx, cudaStream_t stream) {
+    int bits1, tb;
+    size_t cells, hfloats;
+    fused_geometry(nx, &bits1, &tb, &cells, &hfloats);
+    float* base = fused_slot(fused_ws, slot, B, cells, hfloats);
+    baseline_to_tiles_kernel<<<148 * 8, 256, 0, stream>>>(state, base, base + (size_t)B * cells, base + (size_t)2 * B * cells,
+                                                          bits1, tb, B);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+int launch_baseline_fused_cols(float2* Y, float* fused_ws, int slot_in, float* nat_out, int B, int nx,
+                               float c, float dt, float nu, float dx2, cudaStream_t stream) {
+    int bits1, tb;
+    size_t cells, hfloats;
+    fused_geometry(nx, &bits1, &tb, &cells, &hfloats);
+    const float* in = fused_slot(fused_ws, slot_in, B, cells, hfloats);
+    float* out = fused_slot(fused_ws, 1 - slot_in, B, cells, hfloats);
+    FusedColsArgs a;
+    a.Y = Y;
+    a.Pn_in = in;
+    a.Pu_in = in + (size_t)B * cells;
+    a.H_in = in + (size_t)2 * B * cells;
+    a.Pn_out = out;
+    a.Pu_out = out + (size_t)B * cells;
+    a.H_out = out + (size_t)2 * B * cells;
+    a.nat_out = nat_out;
+    a.c = c; a.dt = dt; a.nu = nu; a.dx2 = dx2;
     const int tile_bits = column_tile_bits(bits1);
-    const int T = 1 << (tile_bits - bits1);
     const size_t tile = (size_t)1 << tile_bits;
     const size_t smem = (tile + (tile >> 5) * 4) * sizeof(float2);
-    const size_t smem_row = (size_t)2 * kRowPad * sizeof(float2);
-    const float scale = (float)(length / (6.283185307179586476925 * (double)(1LL << mbits)));
-    float2* Y = (float2*)workspace;
-    dim3 gcol((unsigned)(kRowLen / T), (unsigned)B), grow((unsigned)((1 << bits1) / 2 + 1), (unsigned)B);
-    FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-#define FLUXGNN_FFT_COLS(BITS1, WHICH, ...)                                                                          \
-    case BITS1:                                                                                                     \
-        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(WHICH<BITS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        WHICH<BITS1><<<gcol, column_threads(BITS1), smem, stream>>>(__VA_ARGS__);                                          \
+    dim3 grid((unsigned)(kRowLen >> tb), (unsigned)B);
+#define FLUXGNN_FUSED(BITS1)                                                                                                  \
+    case BITS1:                                                                                                               \
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(baseline_fused_cols_kernel<BITS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        baseline_fused_cols_kernel<BITS1><<<grid, column_threads(BITS1), smem, stream>>>(a);                                  \
         break;
-#define FLUXGNN_FFT_COLS_ALL(WHICH, ...)                                                       \
-    switch (bits1) {                                                                          \
-        FLUXGNN_FFT_COLS(3, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(4, WHICH, __VA_ARGS__)       \
-        FLUXGNN_FFT_COLS(5, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(6, WHICH, __VA_ARGS__)       \
-        FLUXGNN_FFT_COLS(7, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(8, WHICH, __VA_ARGS__)       \
-        FLUXGNN_FFT_COLS(9, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(10, WHICH, __VA_ARGS__)      \
-        FLUXGNN_FFT_COLS(11, WHICH, __VA_ARGS__) FLUXGNN_FFT_COLS(12, WHICH, __VA_ARGS__)     \
-        default: return set_error(FLUXGNN_EUNSUP, "four-step FFT: unsupported column length 2^%d", bits1); \
+    switch (bits1) {
+        FLUXGNN_FUSED(8) FLUXGNN_FUSED(9) FLUXGNN_FUSED(10) FLUXGNN_FUSED(11) FLUXGNN_FUSED(12)
+        default: return set_error(FLUXGNN_EUNSUP, "fused classical step: unsupported column length 2^%d", bits1);
     }
-    FLUXGNN_FFT_COLS_ALL(poisson_fft_cols_fwd_kernel, n, n_stride, Y)
+#undef FLUXGNN_FUSED
     FLUXGNN_CUDA_OK(cudaGetLastError());
-    poisson_fft_rows_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(Y, bits1, scale);
-    FLUXGNN_CUDA_OK(cudaGetLastError());
-    FLUXGNN_FFT_COLS_ALL(poisson_fft_cols_inv_kernel, Y, E, e_stride)
-    FLUXGNN_CUDA_OK(cudaGetLastError());
-#undef FLUXGNN_FFT_COLS_ALL
-#undef FLUXGNN_FFT_COLS
-    count_launch(3);
+    count_launch();
     return FLUXGNN_OK;
 }
 

@@ -62,23 +62,6 @@ __global__ void __launch_bounds__(256) poisson_direct_kernel(const float* __rest
     E[(size_t)ic * e_stride + j] = (float)(acc0 + acc1);
 }
 
-// Every intermediate is rounded to fp32 exactly where numpy rounds it
-// (python-float scalars are weak, so c, dt, nu and dx^2 act as float32).
-struct FvOut { float n, u, fn; };
-__device__ __forceinline__ FvOut fv_cell(float nm, float n0, float um, float u0, float up, float e0,
-                                         float c, float dt, float nu, float dx2) {
-    FvOut o;
-    o.fn = __fmul_rn(n0, u0);                                                          // :70-71
-    const float fnm = __fmul_rn(nm, um);
-    o.n = __fsub_rn(n0, __fmul_rn(c, __fsub_rn(o.fn, fnm)));                           // :85-86
-    const float fu = __fmul_rn(__fmul_rn(0.5f, u0), u0);                               // :73-74
-    const float fum = __fmul_rn(__fmul_rn(0.5f, um), um);
-    const float u_adv = __fsub_rn(u0, __fmul_rn(c, __fsub_rn(fu, fum)));               // :90-91
-    const float lap = __fdiv_rn(__fadd_rn(__fsub_rn(up, __fmul_rn(2.0f, u0)), um), dx2);   // :76-78
-    o.u = __fadd_rn(u_adv, __fmul_rn(dt, __fadd_rn(e0, __fmul_rn(nu, lap))));          // :94
-    return o;
-}
-
 // One thread per 4 consecutive cells when nx % 4 == 0 (128-bit loads/stores, the two halo
 // cells come from the neighbouring quads through the read-only cache); scalar otherwise.
 __global__ void __launch_bounds__(256) baseline_fv_kernel(const float* __restrict__ in, float* __restrict__ out,

@@ -5,6 +5,23 @@
 
 namespace fluxgnn {
 
+// Every intermediate is rounded to fp32 exactly where numpy rounds it
+// (python-float scalars are weak, so c, dt, nu and dx^2 act as float32).
+struct FvOut { float n, u, fn; };
+__device__ __forceinline__ FvOut fv_cell(float nm, float n0, float um, float u0, float up, float e0,
+                                         float c, float dt, float nu, float dx2) {
+    FvOut o;
+    o.fn = __fmul_rn(n0, u0);                                                          // :70-71
+    const float fnm = __fmul_rn(nm, um);
+    o.n = __fsub_rn(n0, __fmul_rn(c, __fsub_rn(o.fn, fnm)));                           // :85-86
+    const float fu = __fmul_rn(__fmul_rn(0.5f, u0), u0);                               // :73-74
+    const float fum = __fmul_rn(__fmul_rn(0.5f, um), um);
+    const float u_adv = __fsub_rn(u0, __fmul_rn(c, __fsub_rn(fu, fum)));               // :90-91
+    const float lap = __fdiv_rn(__fadd_rn(__fsub_rn(up, __fmul_rn(2.0f, u0)), um), dx2);   // :76-78
+    o.u = __fadd_rn(u_adv, __fmul_rn(dt, __fadd_rn(e0, __fmul_rn(nu, lap))));          // :94
+    return o;
+}
+
 __global__ void poisson_table_kernel(int nx, double length, double* gtab);
 __global__ void poisson_direct_kernel(const float* n, long long n_stride, float* E, long long e_stride,
                                       const double* gtab, int nx);
@@ -43,6 +60,18 @@ bool poisson_fft_supported(int nx);
 size_t poisson_fft_workspace_bytes(int B, int nx);
 int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e_stride, int B, int nx,
                        double length, void* workspace, cudaStream_t stream);
+
+// fused classical step (fft_poisson.cu): inverse column stages + finite-volume update + forward column stages in one
+// kernel, n and u in a tile-major private layout.  Available for four-step grids whose column tiles are at most 32
+// columns wide (nx >= 2^21).
+bool baseline_fused_supported(int nx);
+size_t baseline_fused_workspace_floats(int B, int nx);        // 2 x (Pn, Pu) + 2 x H
+int launch_baseline_to_tiles(const float* state, float* fused_ws, int slot, int B, int nx, cudaStream_t stream);
+int launch_baseline_fused_cols(float2* Y, float* fused_ws, int slot_in, float* nat_out, int B, int nx,
+                               float c, float dt, float nu, float dx2, cudaStream_t stream);
+int launch_poisson_fft_rows(float2* Y, int B, int nx, double length, cudaStream_t stream);
+int launch_poisson_fft_cols(const float* n, long long n_stride, float2* Y, float* E, long long e_stride, int B, int nx,
+                            int inverse, cudaStream_t stream);
 
 // distributed field solve (fft_poisson.cu): pack / unpack pairs of ICs, the cross-rank DFT stage, the local solve
 int launch_poisson_dist_pack(const float* n, long long ic_stride, int B, int S, float2* z, int unpack, float* E,

@@ -620,13 +620,13 @@ def test_distributed_field_solve_emulated(built_lib, world, nx, batch):
     E = torch.zeros_like(n)
     solve_emulated(solvers, [n[:, r * S:(r + 1) * S] for r in range(world)], [E[:, r * S:(r + 1) * S] for r in range(world)])
     scale = float(want.abs().max())
-    assert float((E - want).abs().max()) <= 2e-6 * scale
+    assert float((E - want).abs().max()) <= 5e-6 * scale          # two fp32 transforms of up to 2^20 points against each other
     k = 2 * np.pi * np.fft.fftfreq(nx, d=2 * np.pi / nx)
     spec = np.fft.fft(dens.astype(np.float64) - 1.0, axis=-1)
     mult = np.zeros(nx, dtype=np.complex128)
     mult[k != 0] = 1j / k[k != 0]
     exact = np.real(np.fft.ifft(spec * mult, axis=-1))
-    assert np.abs(E.cpu().numpy() - exact).max() <= 2e-6 * np.abs(exact).max()
+    assert np.abs(E.cpu().numpy() - exact).max() <= 3e-6 * np.abs(exact).max()   # the gate of test_poisson_fft_vs_oracle
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
@@ -703,6 +703,33 @@ def test_baseline_golden(built_lib, nx):
     assert P.rel_err(run_s[-1], states[-1]).max() <= STEP_TOL * len(fluxes)
     s2, none = sol.run(states[0], n_steps=3, record_flux=False)
     assert none is None and s2.shape == (4, 3, nx)
+
+
+@pytest.mark.parametrize("log2nx,B,steps", [(21, 2, 3), (22, 1, 4), (23, 2, 5), (24, 1, 6), (24, 2, 3)])
+def test_baseline_fused_rollout_is_bit_identical(built_lib, monkeypatch, log2nx, B, steps):
+    """Multi-step rollouts of long grids run the fused column kernel (inverse column stages + finite-volume update
+    + forward column stages, tile-major private state): same arithmetic per cell, so the result must equal the
+    unfused launch sequence (FLUXGNN_BASELINE_NO_FUSE=1) and a chain of one-step calls bit for bit."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    from gnn_plasma_flux_b200.synthetic import stable_initial_conditions
+    nx = 1 << log2nx
+    dt = 0.2 * (2 * np.pi / nx) ** 2 / 1e-3
+    sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device="cuda")
+    state = stable_initial_conditions(sol, B)
+    state[:, 1] += 1e-3 * torch.randn(B, nx, device="cuda", generator=torch.Generator("cuda").manual_seed(log2nx))
+    before = __import__("gnn_plasma_flux_b200")._lib.launch_count()
+    fused = sol.rollout(state, steps)[0]
+    launches = __import__("gnn_plasma_flux_b200")._lib.launch_count() - before
+    assert launches == 4 + 2 * (steps - 1) + 1                  # FV, to_tiles, A, B; (fused, B) per further step; C
+    monkeypatch.setenv("FLUXGNN_BASELINE_NO_FUSE", "1")
+    plain = sol.rollout(state, steps)[0]
+    monkeypatch.delenv("FLUXGNN_BASELINE_NO_FUSE")
+    assert torch.isfinite(fused).all()
+    assert torch.equal(fused, plain)
+    chain = state
+    for _ in range(steps):
+        chain = sol.rollout(chain, 1)[0]
+    assert torch.equal(fused, chain)
 
 
 def test_error_paths(model):
