@@ -631,12 +631,15 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const doub
     const long long cells = (long long)B * nx;
     long long blocks = (((nx & 3) == 0 ? cells / 4 : cells) + 255) / 256;
     if (blocks > (long long)sms * 64) blocks = (long long)sms * 64;
-    // Long grids, no recording: after the first step the inverse column stages, the finite-volume update and the
-    // forward column stages of consecutive steps run as one kernel (fft_poisson.cu, "fused classical step"): two
-    // launches and 32 bytes per cell-update instead of four and 44.  FLUXGNN_BASELINE_NO_FUSE=1 is the test hook.
-    const char* nofuse = getenv("FLUXGNN_BASELINE_NO_FUSE");
-    if (steps >= 3 && !traj && !flux_n && baseline_fused_supported(nx) && B <= 65535 &&
-        !(nofuse != nullptr && nofuse[0] == '1')) {
+    // Opt-in (FLUXGNN_BASELINE_FUSE=1): after the first step the inverse column stages, the finite-volume update and
+    // the forward column stages of consecutive steps run as one kernel (fft_poisson.cu, "fused classical step"): two
+    // launches and 32 bytes per cell-update instead of four and 44, bit-identical results.  Measured on B200 it is
+    // SLOWER than the four-kernel sequence (0.190 against 0.172 ms per step at 2^24 cells, profiles/r2_c5_fused.md):
+    // one 512-thread CTA per SM serialises its phases, while the stand-alone finite-volume kernel streams at 93 % of
+    // the HBM peak; so the default stays unfused.
+    const char* fuse = getenv("FLUXGNN_BASELINE_FUSE");
+    if (steps >= 3 && !traj && !flux_n && baseline_fused_supported(nx, dx2) && B <= 65535 &&
+        fuse != nullptr && fuse[0] == '1') {
         float* tmp = (float*)workspace;                                    // natural-layout state after step 1
         float2* Y = (float2*)fft_ws;
         float* fused_ws = (float*)fft_ws + fluxgnn_poisson_workspace_bytes(B, nx) / sizeof(float);

@@ -20,6 +20,8 @@
 //                 inverse FFTs, conj twiddle, in place.  Rows 0 and N1/2 pair with themselves.
 //     C  columns: inverse length-N1 FFT over k1 -> (E_2j, E_2j+1)
 // No transposes.  Each shared-memory round trip is a radix-16 transform in registers.
+#include <cstring>
+
 #include "common.cuh"
 #include "field_kernels.cuh"
 
@@ -754,89 +756,141 @@ __device__ __forceinline__ void columns_inverse_to_smem(const float2* gin, float
     }
 }
 
+// One persistent CTA of 512 threads per SM walks the column tiles.  For every tile the n and u blocks (64 KiB each,
+// contiguous in the tile-major layout) and the three neighbour rows (N1 floats each) are fetched by 1-D bulk copies
+// (cp.async.bulk, the TMA unit) that run under the inverse column stages; the next tile's copies are issued as soon
+// as the finite-volume update has read this tile's, and run under the forward column stages.  The spectrum tile (32-byte
+// pieces 32 KiB apart) and the outputs go through ordinary loads / stores.
+constexpr int kFusedThreads = 512;
+constexpr int kFusedTileBits = 13;
+constexpr int kFusedWork = (1 << kFusedTileBits) + ((1 << kFusedTileBits) >> 5) * 4;          // float2 elements, padded
+
 template <int BITS1>
-__global__ void __launch_bounds__(column_threads(BITS1), column_tile_bits(BITS1) <= 13 ? FLUXGNN_FFT_COL_CTAS : 1)
-baseline_fused_cols_kernel(FusedColsArgs a) {
-    extern __shared__ float2 sfft[];
-    constexpr int TILE_BITS = column_tile_bits(BITS1), THREADS = column_threads(BITS1);
+__global__ void __launch_bounds__(kFusedThreads, 1) baseline_fused_cols_kernel(FusedColsArgs a, int tiles, int total) {
+    extern __shared__ __align__(128) float2 sfft[];
+    constexpr int TILE_BITS = kFusedTileBits, THREADS = kFusedThreads;
     constexpr int TB = TILE_BITS - BITS1, T = 1 << TB, N1 = 1 << BITS1;
     constexpr int SUBB = BITS1 - 4;               // the middle pass is the radix-16 pass over whole columns
     constexpr int ITEMS = (1 << TILE_BITS) >> 4, ITERS = ITEMS / THREADS;
-    static_assert(BITS1 >= 5 && T <= 32 && ITEMS % THREADS == 0, "fused column kernel: unsupported tile");
-    const int tile = blockIdx.x, tiles = gridDim.x, b = blockIdx.y;
-    const int j2_0 = tile << TB;
-    float2* Y = a.Y + ((size_t)b << (BITS1 + kRowBits));
-    // ---- pass C of the previous step, all but its last stage set ----
-    columns_inverse_to_smem<BITS1, TILE_BITS, first_inverse_lb(BITS1), THREADS>(Y, sfft, j2_0);
+    static_assert(BITS1 >= 5 && BITS1 <= 11 && ITEMS % THREADS == 0, "fused column kernel: unsupported tile");
+    constexpr uint32_t kTileBytes = (1u << TILE_BITS) * 8u, kHaloBytes = N1 * 4u;
+    float2* sN = sfft + kFusedWork;                                   // [N1][T] float2 = the tile's n block
+    float2* sU = sN + (1 << TILE_BITS);
+    float* sH = reinterpret_cast<float*>(sU + (1 << TILE_BITS));      // [3][N1]: left n, left u, right u
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sH + 3 * N1);
     const size_t pcells = (size_t)N1 << (kRowBits + 1);               // cells per IC
-    const float2* Pn = reinterpret_cast<const float2*>(a.Pn_in + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
-    const float2* Pu = reinterpret_cast<const float2*>(a.Pu_in + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
-    float2* Qn = reinterpret_cast<float2*>(a.Pn_out + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
-    float2* Qu = reinterpret_cast<float2*>(a.Pu_out + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
     const size_t hplane = (size_t)tiles << BITS1;
-    const float* Hin = a.H_in + (size_t)b * 3 * hplane;
-    float* Hout = a.H_out + (size_t)b * 3 * hplane;
-    const int lane_t = threadIdx.x & (T - 1);
-    const uint64_t pol_first = make_policy<Hint::kFirst>();
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const int w = threadIdx.x + it * THREADS;
-        const int t = w & (T - 1), base = w >> TB;                    // rows base + m*SUB, column t
-        float2 v[16];
-#pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = sfft[cpad(((base + (m << SUBB)) << TB) + t)];
-        TwiddleSet<16> pw;
-        pw.init(unit_root((base << kRowBits) + j2_0 + t, BITS1 + kRowBits, +1.f));
-        pw.apply(v);
-        DitStages<16>::run(v, +1.f);                                   // v[m] = (E_2j, E_2j+1) at (row base + m*SUB, column t)
-        // ---- finite-volume update of the two cells of every position (src/baseline_solver.py:84-94) ----
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int j1 = base + (m << SUBB);
-            const size_t e = ((size_t)j1 << TB) + t;
-            const float2 n2 = gload<Hint::kFirst>(Pn + e, pol_first), u2 = gload<Hint::kFirst>(Pu + e, pol_first);
-            // neighbours inside the tile row come from the adjacent lanes, across the tile edge from the side arrays
-            float nl = __shfl_up_sync(0xffffffffu, n2.y, 1), ul = __shfl_up_sync(0xffffffffu, u2.y, 1);
-            float ur = __shfl_down_sync(0xffffffffu, u2.x, 1);
-            if (lane_t == 0) {
-                int tl = tile - 1, jl = j1;
-                if (tl < 0) { tl = tiles - 1; jl = (j1 == 0) ? N1 - 1 : j1 - 1; }
-                const size_t h = ((size_t)tl << BITS1) + jl;
-                nl = __ldg(Hin + h);
-                ul = __ldg(Hin + hplane + h);
-            }
-            if (lane_t == T - 1) {
-                int tr = tile + 1, jr = j1;
-                if (tr == tiles) { tr = 0; jr = (j1 == N1 - 1) ? 0 : j1 + 1; }
-                ur = __ldg(Hin + 2 * hplane + ((size_t)tr << BITS1) + jr);
-            }
-            const FvOut c0 = fv_cell(nl, n2.x, ul, u2.x, u2.y, v[m].x, a.c, a.dt, a.nu, a.dx2);
-            const FvOut c1 = fv_cell(n2.x, n2.y, u2.x, u2.y, ur, v[m].y, a.c, a.dt, a.nu, a.dx2);
-            Qn[e] = make_float2(c0.n, c1.n);
-            Qu[e] = make_float2(c0.u, c1.u);
-            const size_t hme = ((size_t)tile << BITS1) + j1;
-            if (lane_t == T - 1) {
-                Hout[hme] = c1.n;
-                Hout[hplane + hme] = c1.u;
-            }
-            if (lane_t == 0) Hout[2 * hplane + hme] = c0.u;
-            if (a.nat_out != nullptr) {
-                float2* so = reinterpret_cast<float2*>(a.nat_out + (size_t)b * 3 * pcells) + ((size_t)j1 << kRowBits) + j2_0 + t;
-                so[0] = make_float2(c0.n, c1.n);
-                so[pcells >> 1] = make_float2(c0.u, c1.u);
-            }
-            v[m] = make_float2(__fsub_rn(c0.n, 1.0f), __fsub_rn(c1.n, 1.0f));      // rho' = n' - n0
-        }
-        // ---- first stage set of pass A of the next step ----
-        DifStages<16>::run(v, -1.f);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) pw.pw[q].y = -pw.pw[q].y;         // W^-1 powers = conjugates
-        pw.apply(v);
-#pragma unroll
-        for (int m = 0; m < 16; ++m) sfft[cpad(((base + (m << SUBB)) << TB) + t)] = v[m];
+    const int tid = threadIdx.x;
+    const float rdx2 = fv_reciprocal(a.dx2);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
     }
     __syncthreads();
-    columns_forward<BITS1, TILE_BITS, SUBB, THREADS>(nullptr, Y, sfft, j2_0);
+    // thread 0: bulk copies of work item `it` (tile-major n, u blocks; neighbour rows where they are contiguous)
+    auto issue = [&](int it) {
+        const int b = it / tiles, tile = it - b * tiles;
+        const uint32_t bytes = 2 * kTileBytes + (tile > 0 ? 2 * kHaloBytes : 0) + (tile < tiles - 1 ? kHaloBytes : 0);
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(sN, a.Pn_in + (size_t)b * pcells + ((size_t)tile << (TILE_BITS + 1)), kTileBytes, bar);
+        bulk_g2s(sU, a.Pu_in + (size_t)b * pcells + ((size_t)tile << (TILE_BITS + 1)), kTileBytes, bar);
+        const float* Hin = a.H_in + (size_t)b * 3 * hplane;
+        if (tile > 0) {
+            bulk_g2s(sH, Hin + ((size_t)(tile - 1) << BITS1), kHaloBytes, bar);
+            bulk_g2s(sH + N1, Hin + hplane + ((size_t)(tile - 1) << BITS1), kHaloBytes, bar);
+        }
+        if (tile < tiles - 1) bulk_g2s(sH + 2 * N1, Hin + 2 * hplane + ((size_t)(tile + 1) << BITS1), kHaloBytes, bar);
+    };
+    if (tid == 0 && (int)blockIdx.x < total) issue(blockIdx.x);
+    uint32_t parity = 0;
+    for (int it = blockIdx.x; it < total; it += gridDim.x, parity ^= 1) {
+        const int b = it / tiles, tile = it - b * tiles;
+        const int j2_0 = tile << TB;
+        float2* Y = a.Y + ((size_t)b << (BITS1 + kRowBits));
+        const float* Hin = a.H_in + (size_t)b * 3 * hplane;
+        // the grid's first / last tile: its outer neighbours are the far tile's rows shifted by one matrix row
+        // (periodic wrap), which is not 16-byte aligned -> ordinary loads
+        if (tile == 0) {
+            const float* hn = Hin + ((size_t)(tiles - 1) << BITS1);
+            for (int j = tid; j < N1; j += THREADS) {
+                const int jl = (j == 0) ? N1 - 1 : j - 1;
+                sH[j] = __ldg(hn + jl);
+                sH[N1 + j] = __ldg(hn + hplane + jl);
+            }
+        }
+        if (tile == tiles - 1) {
+            const float* hu = Hin + 2 * hplane;
+            for (int j = tid; j < N1; j += THREADS) sH[2 * N1 + j] = __ldg(hu + ((j == N1 - 1) ? 0 : j + 1));
+        }
+        // ---- pass C of the previous step, all but its last stage set ----
+        columns_inverse_to_smem<BITS1, TILE_BITS, first_inverse_lb(BITS1), THREADS>(Y, sfft, j2_0);
+        mbar_wait(bar, parity);
+        float2* Qn = reinterpret_cast<float2*>(a.Pn_out + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
+        float2* Qu = reinterpret_cast<float2*>(a.Pu_out + (size_t)b * pcells) + ((size_t)tile << TILE_BITS);
+        float* Hout = a.H_out + (size_t)b * 3 * hplane + ((size_t)tile << BITS1);
+#pragma unroll
+        for (int rep = 0; rep < ITERS; ++rep) {
+            const int w = tid + rep * THREADS;
+            const int t = w & (T - 1), base = w >> TB;                    // rows base + m*SUB, column t
+            float2 v[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = sfft[cpad(((base + (m << SUBB)) << TB) + t)];
+            TwiddleSet<16> pw;
+            pw.init(unit_root((base << kRowBits) + j2_0 + t, BITS1 + kRowBits, +1.f));
+            pw.apply(v);
+            DitStages<16>::run(v, +1.f);                                   // v[m] = (E_2j, E_2j+1) at (row base + m*SUB, column t)
+            // ---- finite-volume update of the two cells of every position (src/baseline_solver.py:84-94) ----
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int j1 = base + (m << SUBB);
+                const int e = (j1 << TB) + t;
+                const float2 n2 = sN[e], u2 = sU[e];
+                float nl, ul, ur;
+                if (t == 0) {
+                    nl = sH[j1];
+                    ul = sH[N1 + j1];
+                } else {
+                    nl = sN[e - 1].y;
+                    ul = sU[e - 1].y;
+                }
+                ur = (t == T - 1) ? sH[2 * N1 + j1] : sU[e + 1].x;
+                float2 nn, un;
+                fv_pair(nl, n2, ul, u2, ur, v[m], a.c, a.dt, a.nu, a.dx2, rdx2, nn, un);
+                Qn[e] = nn;
+                Qu[e] = un;
+                if (t == T - 1) {
+                    Hout[j1] = nn.y;
+                    Hout[hplane + j1] = un.y;
+                }
+                if (t == 0) Hout[2 * hplane + j1] = un.x;
+                if (a.nat_out != nullptr) {
+                    float2* so = reinterpret_cast<float2*>(a.nat_out + (size_t)b * 3 * pcells) + ((size_t)j1 << kRowBits) + j2_0 + t;
+                    so[0] = nn;
+                    so[pcells >> 1] = un;
+                }
+                v[m] = __fadd2_rn(nn, make_float2(-1.0f, -1.0f));                 // rho' = n' - n0
+            }
+            // ---- first stage set of pass A of the next step ----
+            DifStages<16>::run(v, -1.f);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) pw.pw[q].y = -pw.pw[q].y;         // W^-1 powers = conjugates
+            pw.apply(v);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) sfft[cpad(((base + (m << SUBB)) << TB) + t)] = v[m];
+        }
+        __syncthreads();                              // n, u, neighbour rows are consumed; the work tile is complete
+        if (it + (int)gridDim.x < total) {
+            const int nit = it + gridDim.x;
+            if (tid == 0) issue(nit);
+            // the next tile's spectrum pieces (one 32-byte sector per matrix row) on their way into the L2
+            const int nb = nit / tiles, ntile = nit - nb * tiles;
+            const float2* Yn = a.Y + ((size_t)nb << (BITS1 + kRowBits)) + (ntile << TB);
+            for (int row = tid; row < N1; row += THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Yn + ((size_t)row << kRowBits)));
+        }
+        columns_forward<BITS1, TILE_BITS, SUBB, THREADS>(nullptr, Y, sfft, j2_0);
+        __syncthreads();                              // the work tile is free for the next tile's inverse stages
+    }
 }
 
 // natural [B][3][nx] -> tile-major n, u and the halo side arrays (once per fused rollout).  TB = log2(columns per tile).
@@ -1137,23 +1191,27 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
 }
 
 // ---- fused classical step: host side --------------------------------------------------------------------
-bool baseline_fused_supported(int nx) {
+bool baseline_fused_supported(int nx, float dx2) {
     const int bits = ilog2_exact(nx);
     if (bits < 0) return false;
+    // the fused kernel divides by dx^2 with the FMA sequence of fv_div() only (see fv_reciprocal in field_kernels.cuh)
+    unsigned ubits;
+    memcpy(&ubits, &dx2, sizeof(ubits));
+    if (!(dx2 > 0.f && dx2 < 1.f) || (ubits & 0x7fffffu) == 0x7fffffu || (ubits >> 23) == 0u) return false;
     const int bits1 = bits - 1 - kRowBits;
-    return bits1 >= 8 && bits1 <= 12;                 // column tiles of 4..32 columns; nx = 2^21 .. 2^25
+    return bits1 >= 8 && bits1 <= 11;                 // column tiles of 2^13 points, 4..32 columns; nx = 2^21 .. 2^24
 }
 
 static void fused_geometry(int nx, int* bits1, int* tb, size_t* cells, size_t* hfloats) {
     const int bits = ilog2_exact(nx);
     *bits1 = bits - 1 - kRowBits;
-    *tb = column_tile_bits(*bits1) - *bits1;
+    *tb = kFusedTileBits - *bits1;
     *cells = (size_t)nx;
     *hfloats = (size_t)3 * (kRowLen >> *tb) << *bits1;     // 3 planes x tiles x N1
 }
 
 size_t baseline_fused_workspace_floats(int B, int nx) {
-    if (!baseline_fused_supported(nx)) return 0;
+    if (!baseline_fused_supported(nx, 0.5f)) return 0;
     int bits1, tb;
     size_t cells, hfloats;
     fused_geometry(nx, &bits1, &tb, &cells, &hfloats);
@@ -1194,17 +1252,20 @@ int launch_baseline_fused_cols(float2* Y, float* fused_ws, int slot_in, float* n
     a.H_out = out + (size_t)2 * B * cells;
     a.nat_out = nat_out;
     a.c = c; a.dt = dt; a.nu = nu; a.dx2 = dx2;
-    const int tile_bits = column_tile_bits(bits1);
-    const size_t tile = (size_t)1 << tile_bits;
-    const size_t smem = (tile + (tile >> 5) * 4) * sizeof(float2);
-    dim3 grid((unsigned)(kRowLen >> tb), (unsigned)B);
+    const int tiles = kRowLen >> tb, total = tiles * B;
+    const size_t smem = (size_t)kFusedWork * sizeof(float2) + 2 * ((size_t)sizeof(float2) << kFusedTileBits) +
+                        ((size_t)3 << bits1) * sizeof(float) + 16;
+    int dev = 0, sms = 0;
+    FLUXGNN_CUDA_OK(cudaGetDevice(&dev));
+    FLUXGNN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = total < sms ? total : sms;
 #define FLUXGNN_FUSED(BITS1)                                                                                                  \
     case BITS1:                                                                                                               \
         FLUXGNN_CUDA_OK(cudaFuncSetAttribute(baseline_fused_cols_kernel<BITS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        baseline_fused_cols_kernel<BITS1><<<grid, column_threads(BITS1), smem, stream>>>(a);                                  \
+        baseline_fused_cols_kernel<BITS1><<<grid, kFusedThreads, smem, stream>>>(a, tiles, total);                            \
         break;
     switch (bits1) {
-        FLUXGNN_FUSED(8) FLUXGNN_FUSED(9) FLUXGNN_FUSED(10) FLUXGNN_FUSED(11) FLUXGNN_FUSED(12)
+        FLUXGNN_FUSED(8) FLUXGNN_FUSED(9) FLUXGNN_FUSED(10) FLUXGNN_FUSED(11)
         default: return set_error(FLUXGNN_EUNSUP, "fused classical step: unsupported column length 2^%d", bits1);
     }
 #undef FLUXGNN_FUSED

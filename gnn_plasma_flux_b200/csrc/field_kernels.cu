@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) poisson_direct_kernel(const float* __rest
 __global__ void __launch_bounds__(256) baseline_fv_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                           float* __restrict__ flux_n, int B, int nx,
                                                           float c, float dt, float nu, float dx2) {
+    const float rdx2 = fv_reciprocal(dx2);
     if ((nx & 3) == 0) {
         const int quads = nx >> 2;
         const long long total = (long long)B * quads;
@@ -83,10 +84,10 @@ __global__ void __launch_bounds__(256) baseline_fv_kernel(const float* __restric
             const int im = (i == 0) ? nx - 1 : i - 1;
             const int ip = (i + 4 == nx) ? 0 : i + 4;
             const float nm = __ldg(pn + im), um = __ldg(pu + im), up = __ldg(pu + ip);
-            const FvOut a = fv_cell(nm, n4.x, um, u4.x, u4.y, e4.x, c, dt, nu, dx2);
-            const FvOut b = fv_cell(n4.x, n4.y, u4.x, u4.y, u4.z, e4.y, c, dt, nu, dx2);
-            const FvOut d = fv_cell(n4.y, n4.z, u4.y, u4.z, u4.w, e4.z, c, dt, nu, dx2);
-            const FvOut e = fv_cell(n4.z, n4.w, u4.z, u4.w, up, e4.w, c, dt, nu, dx2);
+            const FvOut a = fv_cell(nm, n4.x, um, u4.x, u4.y, e4.x, c, dt, nu, dx2, rdx2);
+            const FvOut b = fv_cell(n4.x, n4.y, u4.x, u4.y, u4.z, e4.y, c, dt, nu, dx2, rdx2);
+            const FvOut d = fv_cell(n4.y, n4.z, u4.y, u4.z, u4.w, e4.z, c, dt, nu, dx2, rdx2);
+            const FvOut e = fv_cell(n4.z, n4.w, u4.z, u4.w, up, e4.w, c, dt, nu, dx2, rdx2);
             float* po = out + (size_t)ic * 3 * nx;
             *reinterpret_cast<float4*>(po + i) = make_float4(a.n, b.n, d.n, e.n);
             *reinterpret_cast<float4*>(po + nx + i) = make_float4(a.u, b.u, d.u, e.u);
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) baseline_fv_kernel(const float* __restric
         const float* pn = in + (size_t)ic * 3 * nx;
         const float* pu = pn + nx;
         const float* pe = pu + nx;
-        const FvOut o = fv_cell(pn[im], pn[i], pu[im], pu[i], pu[ip], pe[i], c, dt, nu, dx2);
+        const FvOut o = fv_cell(pn[im], pn[i], pu[im], pu[i], pu[ip], pe[i], c, dt, nu, dx2, rdx2);
         float* po = out + (size_t)ic * 3 * nx;
         po[i] = o.n;
         po[nx + i] = o.u;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) baseline_fv_slab_kernel(const float* __re
                                                                float* __restrict__ flux_n, int B, int owned, int halo,
                                                                int out_ld, int out_off, int vec,
                                                                float c, float dt, float nu, float dx2) {
+    const float rdx2 = fv_reciprocal(dx2);
     const int ld = owned + 2 * halo;
     if (vec) {
         const int quads = owned >> 2;
@@ -135,10 +137,10 @@ __global__ void __launch_bounds__(256) baseline_fv_slab_kernel(const float* __re
             const float4 u4 = *reinterpret_cast<const float4*>(pu);
             const float4 e4 = *reinterpret_cast<const float4*>(pe);
             const float nm = __ldg(pn - 1), um = __ldg(pu - 1), up = __ldg(pu + 4);
-            const FvOut a = fv_cell(nm, n4.x, um, u4.x, u4.y, e4.x, c, dt, nu, dx2);
-            const FvOut b = fv_cell(n4.x, n4.y, u4.x, u4.y, u4.z, e4.y, c, dt, nu, dx2);
-            const FvOut d = fv_cell(n4.y, n4.z, u4.y, u4.z, u4.w, e4.z, c, dt, nu, dx2);
-            const FvOut e = fv_cell(n4.z, n4.w, u4.z, u4.w, up, e4.w, c, dt, nu, dx2);
+            const FvOut a = fv_cell(nm, n4.x, um, u4.x, u4.y, e4.x, c, dt, nu, dx2, rdx2);
+            const FvOut b = fv_cell(n4.x, n4.y, u4.x, u4.y, u4.z, e4.y, c, dt, nu, dx2, rdx2);
+            const FvOut d = fv_cell(n4.y, n4.z, u4.y, u4.z, u4.w, e4.z, c, dt, nu, dx2, rdx2);
+            const FvOut e = fv_cell(n4.z, n4.w, u4.z, u4.w, up, e4.w, c, dt, nu, dx2, rdx2);
             float* po = out + (size_t)ic * 3 * out_ld + out_off + i;
             *reinterpret_cast<float4*>(po) = make_float4(a.n, b.n, d.n, e.n);
             *reinterpret_cast<float4*>(po + out_ld) = make_float4(a.u, b.u, d.u, e.u);
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(256) baseline_fv_slab_kernel(const float* __re
         const int i = (int)(idx - (long long)ic * owned);
         const float* pn = in + (size_t)ic * 3 * ld + halo + i;
         const float* pu = pn + ld;
-        const FvOut o = fv_cell(pn[-1], pn[0], pu[-1], pu[0], pu[1], pu[ld], c, dt, nu, dx2);
+        const FvOut o = fv_cell(pn[-1], pn[0], pu[-1], pu[0], pu[1], pu[ld], c, dt, nu, dx2, rdx2);
         float* po = out + (size_t)ic * 3 * out_ld + out_off + i;
         po[0] = o.n;
         po[out_ld] = o.u;

@@ -8,8 +8,26 @@ namespace fluxgnn {
 // Every intermediate is rounded to fp32 exactly where numpy rounds it
 // (python-float scalars are weak, so c, dt, nu and dx^2 act as float32).
 struct FvOut { float n, u, fn; };
+// Correctly rounded x / b without the IEEE division subroutine (whose special-case path nearly every cell takes here:
+// the second difference of a smooth u is a few ulps or exactly zero, and 99 % of the divisions left the fast path).
+// Markstein: with r = RN(1/b), q0 = RN(x r), e = x - q0 b (exact in an FMA), q = RN(q0 + e r) is RN(x/b) unless b's
+// significand is all ones; fv_reciprocal() returns 0 for such a b, for b >= 1 (quotients could become subnormal) and
+// for subnormal b, which selects __fdiv_rn.  Signed zeros and non-finite quotients are passed through from q0.
+__device__ __forceinline__ float fv_reciprocal(float b) {
+    const unsigned bits = __float_as_uint(b);
+    const bool ok = b > 0.f && b < 1.f && (bits & 0x7fffffu) != 0x7fffffu && (bits >> 23) != 0u;
+    return ok ? __frcp_rn(b) : 0.f;
+}
+__device__ __forceinline__ float fv_div(float x, float b, float r) {
+    if (r == 0.f) return __fdiv_rn(x, b);
+    const float q0 = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q0, b, x);
+    const float q = __fmaf_rn(e, r, q0);
+    return (x == 0.f || !(fabsf(q0) < __int_as_float(0x7f800000))) ? q0 : q;
+}
+
 __device__ __forceinline__ FvOut fv_cell(float nm, float n0, float um, float u0, float up, float e0,
-                                         float c, float dt, float nu, float dx2) {
+                                         float c, float dt, float nu, float dx2, float rdx2) {
     FvOut o;
     o.fn = __fmul_rn(n0, u0);                                                          // :70-71
     const float fnm = __fmul_rn(nm, um);
@@ -17,9 +35,32 @@ __device__ __forceinline__ FvOut fv_cell(float nm, float n0, float um, float u0,
     const float fu = __fmul_rn(__fmul_rn(0.5f, u0), u0);                               // :73-74
     const float fum = __fmul_rn(__fmul_rn(0.5f, um), um);
     const float u_adv = __fsub_rn(u0, __fmul_rn(c, __fsub_rn(fu, fum)));               // :90-91
-    const float lap = __fdiv_rn(__fadd_rn(__fsub_rn(up, __fmul_rn(2.0f, u0)), um), dx2);   // :76-78
+    const float lap = fv_div(__fadd_rn(__fsub_rn(up, __fmul_rn(2.0f, u0)), um), dx2, rdx2);   // :76-78
     o.u = __fadd_rn(u_adv, __fmul_rn(dt, __fadd_rn(e0, __fmul_rn(nu, lap))));          // :94
     return o;
+}
+
+// The same update for the two cells of a float2 (cells i, i+1) in packed fp32x2 arithmetic: every operation is the
+// per-component round-to-nearest operation of fv_cell, in the same order, so the results are bit-identical.
+//   nl, ul: n and u of cell i-1;  ur: u of cell i+2;  r = fv_reciprocal(dx2) must be non-zero.
+__device__ __forceinline__ float2 fv_neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ void fv_pair(float nl, float2 n2, float ul, float2 u2, float ur, float2 e2, float c, float dt,
+                                        float nu, float dx2, float r, float2& n_new, float2& u_new) {
+    const float2 nm = make_float2(nl, n2.x), um = make_float2(ul, u2.x), up = make_float2(u2.y, ur);
+    const float2 c2 = make_float2(c, c), half2 = make_float2(0.5f, 0.5f), two2 = make_float2(2.0f, 2.0f);
+    const float2 fn = __fmul2_rn(n2, u2), fnm = __fmul2_rn(nm, um);
+    n_new = __fadd2_rn(n2, fv_neg2(__fmul2_rn(c2, __fadd2_rn(fn, fv_neg2(fnm)))));
+    const float2 fu = __fmul2_rn(__fmul2_rn(half2, u2), u2), fum = __fmul2_rn(__fmul2_rn(half2, um), um);
+    const float2 u_adv = __fadd2_rn(u2, fv_neg2(__fmul2_rn(c2, __fadd2_rn(fu, fv_neg2(fum)))));
+    const float2 x = __fadd2_rn(__fadd2_rn(up, fv_neg2(__fmul2_rn(two2, u2))), um);
+    const float2 r2 = make_float2(r, r), b2 = make_float2(dx2, dx2);
+    const float2 q0 = __fmul2_rn(x, r2);
+    const float2 e = __ffma2_rn(fv_neg2(q0), b2, x);
+    float2 lap = __ffma2_rn(e, r2, q0);
+    const float inf = __int_as_float(0x7f800000);
+    lap.x = (x.x == 0.f || !(fabsf(q0.x) < inf)) ? q0.x : lap.x;
+    lap.y = (x.y == 0.f || !(fabsf(q0.y) < inf)) ? q0.y : lap.y;
+    u_new = __fadd2_rn(u_adv, __fmul2_rn(make_float2(dt, dt), __fadd2_rn(e2, __fmul2_rn(make_float2(nu, nu), lap))));
 }
 
 __global__ void poisson_table_kernel(int nx, double length, double* gtab);
@@ -64,7 +105,7 @@ int launch_poisson_fft(const float* n, long long n_stride, float* E, long long e
 // fused classical step (fft_poisson.cu): inverse column stages + finite-volume update + forward column stages in one
 // kernel, n and u in a tile-major private layout.  Available for four-step grids whose column tiles are at most 32
 // columns wide (nx >= 2^21).
-bool baseline_fused_supported(int nx);
+bool baseline_fused_supported(int nx, float dx2);
 size_t baseline_fused_workspace_floats(int B, int nx);        // 2 x (Pn, Pu) + 2 x H
 int launch_baseline_to_tiles(const float* state, float* fused_ws, int slot, int B, int nx, cudaStream_t stream);
 int launch_baseline_fused_cols(float2* Y, float* fused_ws, int slot_in, float* nat_out, int B, int nx,

@@ -707,23 +707,24 @@ def test_baseline_golden(built_lib, nx):
 
 @pytest.mark.parametrize("log2nx,B,steps", [(21, 2, 3), (22, 1, 4), (23, 2, 5), (24, 1, 6), (24, 2, 3)])
 def test_baseline_fused_rollout_is_bit_identical(built_lib, monkeypatch, log2nx, B, steps):
-    """Multi-step rollouts of long grids run the fused column kernel (inverse column stages + finite-volume update
-    + forward column stages, tile-major private state): same arithmetic per cell, so the result must equal the
-    unfused launch sequence (FLUXGNN_BASELINE_NO_FUSE=1) and a chain of one-step calls bit for bit."""
-    from gnn_plasma_flux_b200 import BaselineSolver
+    """The opt-in fused column kernel of long grids (FLUXGNN_BASELINE_FUSE=1: inverse column stages + finite-volume
+    update + forward column stages in one persistent kernel, tile-major private state fetched by bulk copies): same
+    arithmetic per cell, so the result must equal the default launch sequence and a chain of one-step calls bit
+    for bit."""
+    from gnn_plasma_flux_b200 import BaselineSolver, _lib
     from gnn_plasma_flux_b200.synthetic import stable_initial_conditions
     nx = 1 << log2nx
     dt = 0.2 * (2 * np.pi / nx) ** 2 / 1e-3
     sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device="cuda")
     state = stable_initial_conditions(sol, B)
     state[:, 1] += 1e-3 * torch.randn(B, nx, device="cuda", generator=torch.Generator("cuda").manual_seed(log2nx))
-    before = __import__("gnn_plasma_flux_b200")._lib.launch_count()
-    fused = sol.rollout(state, steps)[0]
-    launches = __import__("gnn_plasma_flux_b200")._lib.launch_count() - before
-    assert launches == 4 + 2 * (steps - 1) + 1                  # FV, to_tiles, A, B; (fused, B) per further step; C
-    monkeypatch.setenv("FLUXGNN_BASELINE_NO_FUSE", "1")
     plain = sol.rollout(state, steps)[0]
-    monkeypatch.delenv("FLUXGNN_BASELINE_NO_FUSE")
+    monkeypatch.setenv("FLUXGNN_BASELINE_FUSE", "1")
+    before = _lib.launch_count()
+    fused = sol.rollout(state, steps)[0]
+    launches = _lib.launch_count() - before
+    monkeypatch.delenv("FLUXGNN_BASELINE_FUSE")
+    assert launches == 4 + 2 * (steps - 1) + 1                  # FV, to_tiles, A, B; (fused, B) per further step; C
     assert torch.isfinite(fused).all()
     assert torch.equal(fused, plain)
     chain = state
