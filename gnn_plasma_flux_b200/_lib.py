@@ -17,6 +17,8 @@ MAX_HOPS = 4
 MAX_LAYERS = 8
 HIDDEN = 128
 INPUT_DIM = 4
+GENERIC_HIDDEN = (16, 32, 64, 128)     # other architectures: the generic FP32-pipe kernels (csrc/generic_kernels.cu)
+GENERIC_MAX_INPUT_DIM = 16
 # fp16 / fp16x3 operand images store 2^8 * W (kTc16WeightScale, csrc/common.cuh): fp16's largest finite value / 2^8
 FP16_WEIGHT_LIMIT = 65504.0 / 256.0
 
@@ -72,6 +74,13 @@ SIGNATURES = {
     "fluxgnn_poisson_dist_unpack": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "fluxgnn_poisson_dist_rank_dft": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_int, c_int, c_void_p]),
     "fluxgnn_poisson_dist_local": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
+    "fluxgnn_generic_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fluxgnn_generic_pack": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p, c_void_p]),
+    "fluxgnn_generic_forward_ring": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                             c_int, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_generic_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_generic_hybrid_rollout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                               c_double, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fluxgnn_pure_gnn_packed_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_pure_gnn_pack": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p, c_void_p]),
     "fluxgnn_pure_gnn_rollout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

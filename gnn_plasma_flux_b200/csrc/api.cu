@@ -125,6 +125,12 @@ static int launch_poisson(const float* n, long long ns, float* E, long long es, 
     return FLUXGNN_OK;
 }
 
+// generic_kernels.cu: the same field-solve dispatch for the generic-architecture rollout
+int launch_poisson_for_generic(const float* n, long long ns, float* E, long long es, const double* gtab, int B, int nx,
+                               double length, void* fft_ws, cudaStream_t stream) {
+    return launch_poisson(n, ns, E, es, gtab, B, nx, length, fft_ws, stream);
+}
+
 }  // namespace fluxgnn
 
 using namespace fluxgnn;

@@ -10,8 +10,11 @@ gradients are enabled it also saves activations and backward() runs hand-written
 Deliberate deviations, all raised loudly rather than served by a second backend:
   * `edge_index` must be the periodic ring that `build_chain_graph` produces
     (any radius); an arbitrary graph raises NotImplementedError.
-  * the CUDA kernel is specialised for input_dim = 4 and hidden_dim = 128
-    (MODEL_CONFIG, src/config.py:19-23) and 1..8 layers.
+  * the tuned FP32-pipe kernel, the tensor-core kernels and the CUDA backward pass are specialised for
+    input_dim = 4 and hidden_dim = 128 (MODEL_CONFIG, src/config.py:19-23); other architectures
+    (input_dim <= 16, hidden_dim in {16, 32, 64, 128}, 1..8 layers -- e.g. FluxGNN(4, 64, 3) of the
+    reference's smoke test, or the class default (2, 32, 2)) run the forward pass on plain generic
+    sm_100a kernels (csrc/generic_kernels.cu), inference only.
 """
 from __future__ import annotations
 
@@ -62,11 +65,21 @@ class FluxGNN(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     # ------------------------------------------------------------------ weights
+    @property
+    def is_generic(self) -> bool:
+        """True for architectures other than MODEL_CONFIG's (input_dim 4, hidden_dim 128): they run on the generic
+        FP32-pipe kernels (csrc/generic_kernels.cu) instead of the tuned / tensor-core ones."""
+        return self.input_dim != _lib.INPUT_DIM or self.hidden_dim != _lib.HIDDEN
+
     def _check_supported(self):
-        if self.input_dim != _lib.INPUT_DIM or self.hidden_dim != _lib.HIDDEN or not 1 <= self.num_layers <= _lib.MAX_LAYERS:
+        ok = 1 <= self.num_layers <= _lib.MAX_LAYERS
+        if self.is_generic:
+            ok = ok and 1 <= self.input_dim <= _lib.GENERIC_MAX_INPUT_DIM and self.hidden_dim in _lib.GENERIC_HIDDEN
+        if not ok:
             raise NotImplementedError(
-                f"the sm_100a kernel supports input_dim={_lib.INPUT_DIM}, hidden_dim={_lib.HIDDEN}, "
-                f"1..{_lib.MAX_LAYERS} layers; got ({self.input_dim}, {self.hidden_dim}, {self.num_layers})")
+                f"the sm_100a kernels support input_dim 1..{_lib.GENERIC_MAX_INPUT_DIM}, hidden_dim in "
+                f"{_lib.GENERIC_HIDDEN}, 1..{_lib.MAX_LAYERS} layers; got ({self.input_dim}, {self.hidden_dim}, "
+                f"{self.num_layers})")
 
     def packed_weights(self, layout: str = "fp32") -> torch.Tensor:
         """Weights in a kernel's streaming layout (device float32), repacked only when a
@@ -74,6 +87,11 @@ class FluxGNN(nn.Module):
         for the FP32-pipe kernel; "tc": pre-swizzled TF32 hi/lo UMMA operand images; "tc16" /
         "tc16_bf16": the 16-bit (fp16 / bfloat16) operand images of the 256-row tensor kernel."""
         self._check_supported()
+        if self.is_generic:
+            if layout not in ("fp32", "generic"):
+                raise NotImplementedError(f"precision modes other than fp32 need input_dim={_lib.INPUT_DIM}, "
+                                          f"hidden_dim={_lib.HIDDEN}; this model is ({self.input_dim}, {self.hidden_dim})")
+            layout = "generic"
         params = list(self.parameters())
         dev = params[0].device
         if dev.type != "cuda":
@@ -99,7 +117,12 @@ class FluxGNN(nn.Module):
                         raise _lib.FluxGNNError(
                             f"fp16 tensor-core layouts need |W| < {_lib.FP16_WEIGHT_LIMIT:g} in the update and edge "
                             f"layers (largest entry {w_max:g}); use precision='bf16', 'tf32x3' or 'fp32' for this model")
-                if layout in ("tc16", "tc16_bf16"):
+                if layout == "generic":
+                    packed = torch.empty(L.fluxgnn_generic_packed_bytes(self.input_dim, self.hidden_dim, self.num_layers) // 4,
+                                         dtype=torch.float32, device=dev)
+                    _lib.check(L.fluxgnn_generic_pack(*ptrs, self.input_dim, self.hidden_dim, self.num_layers,
+                                                      packed.data_ptr(), stream), "fluxgnn_generic_pack")
+                elif layout in ("tc16", "tc16_bf16"):
                     packed = torch.empty(L.fluxgnn_packed_tc16_weight_bytes(self.num_layers) // 4, dtype=torch.float32,
                                          device=dev)
                     code = _lib.TC_PRECISIONS["bf16" if layout == "tc16_bf16" else "fp16x3"]
@@ -144,7 +167,13 @@ class FluxGNN(nn.Module):
             face = torch.empty(B, nx, dtype=torch.float32, device=packed.device) if want_face else None
             stream = torch.cuda.current_stream(packed.device).cuda_stream
             outs = (edges.data_ptr() if want_edges else None, face.data_ptr() if want_face else None, stream)
-            if tensor_path:
+            if self.is_generic:
+                if self.input_dim != 4:
+                    raise ValueError(f"a [n,u,E] state + x gives 4 node features; this model takes {self.input_dim}")
+                _lib.check(_lib.lib().fluxgnn_generic_forward_ring(
+                    packed.data_ptr(), self.input_dim, self.hidden_dim, self.num_layers, None, state.data_ptr(),
+                    x.data_ptr(), B, nx, radius, hops, *outs), "fluxgnn_generic_forward_ring")
+            elif tensor_path:
                 if hops != 1:
                     raise NotImplementedError("the tensor-core forward emits hop-1 edges only")
                 _lib.check(_lib.lib().fluxgnn_forward_ring_tc(
@@ -172,6 +201,19 @@ class FluxGNN(nn.Module):
         packed = self.packed_weights()
         wants_grad = torch.is_grad_enabled() and (node_features.requires_grad or
                                                   any(p.requires_grad for p in self.parameters()))
+        if self.is_generic:
+            if wants_grad:
+                raise NotImplementedError(
+                    "the CUDA backward pass exists for input_dim=4, hidden_dim=128 only; call this model under "
+                    "torch.no_grad() (its forward runs on the generic sm_100a kernels)")
+            feats = node_features.detach().to(device=packed.device, dtype=torch.float32).contiguous()
+            with torch.cuda.device(packed.device):
+                edges = torch.empty(2 * radius * n_nodes, dtype=torch.float32, device=packed.device)
+                _lib.check(_lib.lib().fluxgnn_generic_forward_ring(
+                    packed.data_ptr(), self.input_dim, self.hidden_dim, self.num_layers, feats.data_ptr(), None, None,
+                    1, n_nodes, radius, radius, edges.data_ptr(), None,
+                    torch.cuda.current_stream(packed.device).cuda_stream), "fluxgnn_generic_forward_ring")
+            return edges
         if wants_grad:
             # training (scripts/training/train_ablation.py:128-206): saved activations + CUDA backward
             from .autograd import ring_fluxes_with_grad

@@ -71,6 +71,18 @@ class HybridSolver:
                 out = torch.empty_like(state)
             traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
                     if record_every else None)
+            if self.model.is_generic:         # architectures other than (4, 128, L): generic kernels, launch loop
+                if self.model.input_dim != 4:
+                    raise ValueError(f"HybridSolver feeds 4 node features [n,u,E,x]; the model takes {self.model.input_dim}")
+                ws_bytes = _lib.lib().fluxgnn_generic_workspace_bytes(B, nx)
+                work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+                _lib.check(_lib.lib().fluxgnn_generic_hybrid_rollout(
+                    packed.data_ptr(), self.model.hidden_dim, self.model.num_layers, state.data_ptr(), out.data_ptr(),
+                    x_dev.data_ptr(), gtab.data_ptr() if gtab is not None else None, B, nx, base.length, self.graph_radius,
+                    float(np.float32(base.dt / base.dx)), float(np.float32(base.dt)), n_steps, max(record_every, 1),
+                    traj.data_ptr() if traj is not None else None, work.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream), "fluxgnn_generic_hybrid_rollout")
+                return out, traj
             ws_bytes = _lib.lib().fluxgnn_hybrid_workspace_bytes(B, nx)
             work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -95,6 +107,9 @@ class HybridSolver:
         base = self.baseline
         if state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != base.nx:
             raise ValueError(f"state must be [B,3,{base.nx}], got {tuple(state.shape)}")
+        if self.model.is_generic:
+            raise NotImplementedError("in-kernel diagnostics exist for input_dim=4, hidden_dim=128 models; reduce a recorded "
+                                      "trajectory with rollout_metrics() instead")
         packed = self.model.packed_weights(_lib.weight_layout(self.precision))
         dev = packed.device
         state = state.to(device=dev, dtype=torch.float32).contiguous()
@@ -163,8 +178,8 @@ class HybridSolver:
         one tile overlap the arithmetic of the others; only for nx <= 128 (one launch per call)."""
         dev = torch.device(self.device)
         if zero_copy:
-            if not (host_in.is_pinned() and host_out.is_pinned()) or self.baseline.nx > 128:
-                raise ValueError("zero_copy needs pinned host tensors and nx <= 128")
+            if not (host_in.is_pinned() and host_out.is_pinned()) or self.baseline.nx > 128 or self.model.is_generic:
+                raise ValueError("zero_copy needs pinned host tensors, nx <= 128 and an input_dim=4, hidden_dim=128 model")
             self._rollout_raw(host_in, host_out, n_steps, dev)
             torch.cuda.current_stream(dev).synchronize()
             return host_out

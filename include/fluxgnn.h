@@ -187,6 +187,33 @@ int fluxgnn_hybrid_rollout_tc(const void* packed_tc, int num_layers, int precisi
                               int steps, int record_every, float* traj,
                               void* workspace, void* stream);
 
+/* ---- FluxGNN of any size on the ring --------------------------------------------------------------
+ * src/flux_gnn.py:11-67 for architectures other than (4, 128, L): input_dim 1..16, hidden_dim in
+ * {16, 32, 64, 128}, 1..8 layers -- e.g. FluxGNN(4, 64, 3) of examples/smoke_test.py:50-56 and the class
+ * default (2, 32, 2).  Plain FP32-pipe kernels, one CTA per 128-cell window; same outputs and edge order
+ * as fluxgnn_forward_ring.  Weights: the state_dict tensors as for fluxgnn_pack_weights, packed K-major by
+ * fluxgnn_generic_pack into fluxgnn_generic_packed_bytes(F, H, L) bytes.
+ *   feats[B][nx][F]  node features as FluxGNN.forward receives them (src/graph_constructor.py:30-32), or
+ *   feats = NULL and state[B][3][nx] + x[nx] for input_dim = 4 (features n, u, E, x).
+ * fluxgnn_generic_hybrid_rollout: HybridSolver.step / .run (src/hybrid_solver.py:34-73) with such a model
+ * (input_dim 4): per step the forward kernel, the finite-volume update and the field solve;
+ * workspace: fluxgnn_generic_workspace_bytes(B, nx); gtab as for fluxgnn_hybrid_rollout. */
+size_t fluxgnn_generic_packed_bytes(int input_dim, int hidden, int num_layers);
+int fluxgnn_generic_pack(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
+                         const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
+                         int input_dim, int hidden, int num_layers, void* packed, void* stream);
+int fluxgnn_generic_forward_ring(const void* packed, int input_dim, int hidden, int num_layers,
+                                 const float* feats, const float* state, const float* x,
+                                 int B, int nx, int radius, int hops,
+                                 float* flux_edges, float* face_flux, void* stream);
+size_t fluxgnn_generic_workspace_bytes(int B, int nx);
+int fluxgnn_generic_hybrid_rollout(const void* packed, int hidden, int num_layers,
+                                   const float* state_in, float* state_out,
+                                   const float* x, const double* gtab,
+                                   int B, int nx, double length, int radius, float c, float dt,
+                                   int steps, int record_every, float* traj,
+                                   void* workspace, void* stream);
+
 /* ---- rollout with in-kernel diagnostics -----------------------------------
  * fluxgnn_hybrid_rollout for grids of up to 128 cells that also reduces, inside the persistent kernel
  * and after EVERY step, what scripts/evaluation/evaluate_all.py:134-141 and

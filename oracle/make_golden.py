@@ -238,6 +238,7 @@ def main():
 
     comparison_goldens()
     long_rollout_goldens()
+    generic_architecture_goldens()
 
     manifest = {
         "generated_by": "oracle/make_golden.py",
@@ -306,6 +307,43 @@ def long_rollout_goldens():
     print("  wrote g6b_long_rollout_radius.npz")
 
 
+def generic_architecture_goldens():
+    """G10: the reference FluxGNN at architectures other than MODEL_CONFIG's -- (4, 64, 3) of examples/smoke_test.py:50-56,
+    the class default (2, 32, 2) (src/flux_gnn.py:11), (4, 16, 1) -- forward on ring graphs, and a 5-step hybrid
+    rollout with the (4, 64, 3) model driven with reference objects.  `--only-g10` regenerates just this file."""
+    torch.set_num_threads(1)
+    out = {}
+    for tag, (F, H, L), seed in (("f4h64l3", (4, 64, 3), 5), ("f2h32l2", (2, 32, 2), 6), ("f4h16l1", (4, 16, 1), 7)):
+        torch.manual_seed(seed)
+        ref_model = FluxGNN(input_dim=F, hidden_dim=H, num_layers=L).eval()
+        w = {k: v.numpy().copy() for k, v in ref_model.state_dict().items()}
+        mine = P.init_weights(seed, F, H, L)
+        for key in w:
+            same(mine[key], w[key], f"init_weights[{tag}][{key}]")
+        for nx in (64, 300):
+            base = BaselineSolver(nx=nx)
+            state = base.initial_condition(seed=31)
+            nf4, _ = build_chain_graph(state, base.x)
+            nf = nf4[:, :F].contiguous()                      # F = 2: features [n, u]
+            out[f"{tag}_feats_nx{nx}"] = nf.numpy()
+            for r in (1, 2, 3):
+                edges = torch.from_numpy(P.ring_edges(nx, r))
+                with torch.no_grad():
+                    flux = ref_model(nf, edges).numpy()
+                same(P.fluxgnn_forward(w, nf.numpy(), edges.numpy()), flux, f"forward {tag} nx={nx} r={r}")
+                out[f"{tag}_flux_nx{nx}_r{r}"] = flux
+        if F == 4:
+            base = BaselineSolver(nx=64, dt=5e-3)
+            ics = np.stack([base.initial_condition(seed=s) for s in (0, 1)])
+            for r in (1, 2):
+                runs = np.stack([reference_radius_run(ref_model, base, ic, 5, r, 1) for ic in ics])      # [2,6,3,64]
+                same(P.hybrid_run(w, ics[0], P.Grid(nx=64, dt=5e-3), 5, radius=r), runs[0], f"hybrid_run {tag} r={r}")
+                out[f"{tag}_rollout5_r{r}"] = runs
+            out[f"{tag}_ics"] = ics
+    np.savez_compressed(os.path.join(OUT, "g10_generic_architectures.npz"), **out)
+    print("  wrote g10_generic_architectures.npz")
+
+
 def comparison_goldens():
     """G9: the reference's PureGNN and PINN classes, seeded, against the port; their
     outputs frozen.  `python -m oracle.make_golden --only-g9` regenerates just this file."""
@@ -364,5 +402,7 @@ if __name__ == "__main__":
         comparison_goldens()
     elif "--only-g6b" in sys.argv:
         long_rollout_goldens()
+    elif "--only-g10" in sys.argv:
+        generic_architecture_goldens()
     else:
         main()

@@ -573,6 +573,73 @@ def test_tc_rejects_unsupported_shapes(model):
         make_solver(model, 64, 5e-3, precision="fp8")
 
 
+# ----------------------------------------------------------------------------- other architectures (generic kernels)
+GENERIC_ARCHS = {"f4h64l3": (4, 64, 3, 5), "f2h32l2": (2, 32, 2, 6), "f4h16l1": (4, 16, 1, 7)}
+
+
+def _generic_model(tag):
+    from gnn_plasma_flux_b200 import FluxGNN
+    F, H, L, seed = GENERIC_ARCHS[tag]
+    m = FluxGNN(input_dim=F, hidden_dim=H, num_layers=L)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in P.init_weights(seed, F, H, L).items()})
+    return m.to("cuda").eval()
+
+
+@pytest.mark.parametrize("tag", list(GENERIC_ARCHS))
+def test_generic_architecture_forward_golden(built_lib, tag):
+    """FluxGNN(4, 64, 3) of the reference's smoke test (examples/smoke_test.py:50-56), the class default (2, 32, 2)
+    and (4, 16, 1): model(node_features, edge_index) on ring graphs against the reference model's own outputs."""
+    from gnn_plasma_flux_b200 import ring_edge_index
+    g = load_golden("g10_generic_architectures.npz")
+    model = _generic_model(tag)
+    assert model.is_generic
+    for nx in (64, 300):
+        feats = torch.from_numpy(g[f"{tag}_feats_nx{nx}"]).cuda()
+        for r in (1, 2, 3):
+            ref = g[f"{tag}_flux_nx{nx}_r{r}"]
+            with torch.no_grad():
+                out = model(feats, ring_edge_index(nx, r, device="cuda")).cpu().numpy()
+            assert out.shape == ref.shape
+            assert np.abs(out - ref).max() <= STEP_TOL * np.abs(ref).max(), (nx, r)
+    with pytest.raises(NotImplementedError):                        # no CUDA backward for these sizes: loud, not silent
+        model(torch.from_numpy(g[f"{tag}_feats_nx64"]).cuda().requires_grad_(True), ring_edge_index(64, 1, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        model(torch.from_numpy(g[f"{tag}_feats_nx64"]).cuda(), torch.randint(0, 64, (2, 128), device="cuda"))
+
+
+@pytest.mark.parametrize("tag", ["f4h64l3", "f4h16l1"])
+def test_generic_architecture_hybrid_rollout_golden(built_lib, tag):
+    """HybridSolver with a non-default architecture: 5-step rollouts (nearest-neighbour ring and radius 2) against the
+    reference objects' trajectories; u' of the first step bit-exact; batched equals one by one; tensor modes refuse."""
+    from gnn_plasma_flux_b200 import HybridSolver
+    g = load_golden("g10_generic_architectures.npz")
+    model = _generic_model(tag)
+    ics = g[f"{tag}_ics"]
+    for r in (1, 2):
+        ref = g[f"{tag}_rollout5_r{r}"]                                              # [2,6,3,64]
+        sol = HybridSolver(None, r, nx=64, dt=5e-3, device="cuda", graph_radius=r, model=model)
+        traj = sol.run(ics, n_steps=5)                                                # [6,2,3,64]
+        assert traj.shape == (6, 2, 3, 64)
+        np.testing.assert_array_equal(traj[0], ics)
+        np.testing.assert_array_equal(traj[1][:, 1], ref[:, 1, 1])
+        for t in range(1, 6):
+            assert P.rel_err(traj[t], ref[:, t]).max() <= STEP_TOL * t, (r, t)
+        one = sol.run(ics[1], n_steps=5)
+        np.testing.assert_array_equal(one, traj[:, 1])
+    with pytest.raises(NotImplementedError):
+        HybridSolver(None, 1, nx=64, dt=5e-3, device="cuda", model=model, precision="fp16x3").step(ics)
+    # a longer grid: window tiles + FFT field solve, against the oracle
+    nx, dt = 1024, 3e-4
+    F, H, L, seed = GENERIC_ARCHS[tag]
+    w = P.init_weights(seed, F, H, L)
+    grid = P.Grid(nx=nx, dt=dt)
+    big = np.stack([P.stable_initial_condition(grid, s) for s in range(3)])
+    sol = HybridSolver(None, 2, nx=nx, dt=dt, device="cuda", graph_radius=2, model=model)
+    out, _ = sol.rollout(torch.from_numpy(big).cuda(), 2)
+    orc = batched.hybrid_run(w, torch.from_numpy(big), grid.x, grid.k, grid.dt, grid.dx, 2, radius=2).numpy()
+    assert P.rel_err(out.cpu().numpy(), orc).max() <= 2 * STEP_TOL
+
+
 # ----------------------------------------------------------------------------- domain decomposition
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("world,nx,radius", [(1, 1 << 12, 2), (2, 1 << 12, 3), (4, 1 << 15, 3), (8, 1 << 15, 1), (8, 1000, 2)])

@@ -137,6 +137,23 @@ def test_long_rollout_at_config_radius_golden(weights):
         assert np.abs(ref32[:, -1, 0].astype(np.float64).sum(-1) - mass0).max() < T * nx * np.finfo(np.float32).eps
 
 
+def test_generic_architecture_golden():
+    """G10: the port at architectures other than MODEL_CONFIG's against the reference model's frozen outputs."""
+    g = load_golden("g10_generic_architectures.npz")
+    for tag, (F, H, L, seed) in {"f4h64l3": (4, 64, 3, 5), "f2h32l2": (2, 32, 2, 6), "f4h16l1": (4, 16, 1, 7)}.items():
+        w = P.init_weights(seed, F, H, L)
+        for nx in (64, 300):
+            for r in (1, 3):
+                out = P.fluxgnn_forward(w, g[f"{tag}_feats_nx{nx}"], P.ring_edges(nx, r))
+                np.testing.assert_allclose(out, g[f"{tag}_flux_nx{nx}_r{r}"], rtol=0, atol=2e-6 * np.abs(out).max())
+        if F == 4:
+            run = P.hybrid_run(w, g[f"{tag}_ics"][0], P.Grid(nx=64, dt=5e-3), 5, radius=2)
+            assert P.rel_err(run[-1], g[f"{tag}_rollout5_r2"][0, -1]).max() <= 2e-6
+            closed = batched.hybrid_run(w, torch.from_numpy(g[f"{tag}_ics"]), P.Grid(nx=64).x, P.Grid(nx=64).k, 5e-3,
+                                        P.Grid(nx=64).dx, 5, radius=2).numpy()
+            assert P.rel_err(closed, g[f"{tag}_rollout5_r2"][:, -1]).max() <= 1e-5
+
+
 def test_metrics_and_datagen_golden():
     """the oracle's restatements of evaluate_all.compute_metrics and
     generate_data.generate_dataset against outputs of the reference's own functions."""
