@@ -38,6 +38,40 @@ static int sm_count(int* out) {
     return FLUXGNN_OK;
 }
 
+// FP32-pipe kernel, window / slab tiles: a cluster of c CTAs shares ONE window of 128c - 4(c-1) rows (the pieces overlap
+// by one 4-row chunk and read each other's edge rows of Z through distributed shared memory), so only the window's two
+// outer ends carry the recomputed halo.  Pick the c in 1..4 that needs the fewest SM-tile-steps for this grid, counting
+// the SMs the hardware can actually fill with clusters of that size.  FLUXGNN_CLUSTER=c forces it (1 = off; test hook).
+static void choose_cluster(HybridArgs& a, int cells) {
+    int sms = 0;
+    if (sm_count(&sms) != FLUXGNN_OK) return;
+    const char* force = getenv("FLUXGNN_CLUSTER");
+    const int forced = (force != nullptr && force[0] >= '1' && force[0] <= '4') ? force[0] - '0' : 0;
+    double best = 0.0;
+    int best_c = 1;
+    for (int c = 1; c <= 4; ++c) {
+        if (forced && c != forced) continue;
+        const int rows = kTileRows * c - 4 * (c - 1), valid = rows - 2 * a.halo;
+        if (valid < 8) continue;
+        const int eff_sms = c == 1 ? sms : hybrid_max_active_clusters(c) * c;
+        if (eff_sms < 1) continue;
+        const long long windows = (long long)a.B * ((cells + valid - 1) / valid);
+        const long long slots = eff_sms / c;                                   // windows in flight
+        const long long waves = (windows + slots - 1) / slots;                 // each wave costs one tile-step
+        const double cost = (double)waves * (c == 1 ? 1.0 : 1.02);             // ~2 % for the neighbour handshakes
+        if (best == 0.0 || cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    if (best_c > 1) {
+        a.cluster = best_c;
+        a.valid = kTileRows * best_c - 4 * (best_c - 1) - 2 * a.halo;
+        a.tiles_per_ic = (cells + a.valid - 1) / a.valid;
+        a.num_tiles = (int)((long long)a.B * a.tiles_per_ic);
+    }
+}
+
 // Tiling of [B][nx] cells into 128-row tiles (see hybrid_kernel.cu).
 static int plan_tiles(HybridArgs& a, int* fast_radius) {
     const int nx = a.nx;
@@ -73,6 +107,8 @@ static int plan_tiles(HybridArgs& a, int* fast_radius) {
         if (tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");
         a.num_tiles = (int)tiles;
         *fast_radius = (a.radius <= 4) ? a.radius : 0;
+        if (a.tile_rows == kTileRows && a.tc_group_rows == 0 && a.tc_parts == 0 && a.acts == nullptr && *fast_radius > 0)
+            choose_cluster(a, nx);
     }
     // test hook: walk the prev/next tables even where the 128-bit window path applies
     const char* force = getenv("FLUXGNN_FORCE_GENERIC");
@@ -98,7 +134,11 @@ static int launch_tiles(const HybridArgs& a, int fast_radius, cudaStream_t strea
     if (rc != FLUXGNN_OK) return rc;
     const int groups = a.tc_group_rows ? a.tile_rows / a.tc_group_rows : 1;       // logical tiles per CTA tile
     const int cta_tiles = (a.num_tiles + groups - 1) / groups;
-    const int grid = cta_tiles < sms ? cta_tiles : sms;
+    int grid = cta_tiles < sms ? cta_tiles : sms;
+    if (a.cluster > 1) {                                                          // one window per cluster
+        const int slots = hybrid_max_active_clusters(a.cluster);
+        grid = (a.num_tiles < slots ? a.num_tiles : slots) * a.cluster;
+    }
     if (fast_radius < 0 && a.tile_rows == kTc16TileRows)
         FLUXGNN_CUDA_OK(launch_hybrid_tc16_tiles(a, -fast_radius, grid, stream));
     else if (fast_radius < 0)
@@ -138,6 +178,9 @@ using namespace fluxgnn;
 extern "C" {
 
 int fluxgnn_abi_version(void) { return FLUXGNN_ABI_VERSION; }
+
+/* measurement aid (scripts/time_cluster_windows.py): clusters of `csize` CTAs of the FP32-pipe tile kernel the device holds at once */
+int fluxgnn_debug_max_clusters(int csize) { return hybrid_max_active_clusters(csize); }
 
 const char* fluxgnn_last_error(void) { return g_err; }
 
@@ -560,6 +603,7 @@ int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precisio
     a.num_tiles = (int)tiles;
     a.slab = 1;
     a.ld_in = owned + 2 * halo;
+    if (precision == 0 && radius <= 4) choose_cluster(a, owned);
     if (out_off < 0 || out_ld < out_off + owned)
         return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: output row of %d floats cannot hold %d cells at offset %d",
                          out_ld, owned, out_off);

@@ -20,6 +20,8 @@
 //                 inverse FFTs, conj twiddle, in place.  Rows 0 and N1/2 pair with themselves.
 //     C  columns: inverse length-N1 FFT over k1 -> (E_2j, E_2j+1)
 // No transposes.  Each shared-memory round trip is a radix-16 transform in registers.
+#include <cuda.h>
+
 #include <cstring>
 
 #include "common.cuh"
@@ -440,19 +442,33 @@ __device__ __forceinline__ void gstore(float2* p, float2 v, uint64_t pol) {
 }
 
 __device__ __forceinline__ int cpad(int e) { return e + ((e >> 5) << 2); }     // column tile: 4 pads per 32
+// Column-tile layouts (index of point e = row * T + column):
+//   0  padded (cpad): the plain and cp.async-staged kernels
+//   1  dense: what a TMA tensor copy writes / reads without swizzle
+//   2  dense + SWIZZLE_128B: the 16-byte chunk index (byte address bits 4..6) XORed with address bits 7..9, the
+//      pattern the TMA unit applies; it spreads the short-stride passes over all banks like the padding does
+template <int LAYOUT>
+__device__ __forceinline__ int cidx(int e) {
+    if constexpr (LAYOUT == 0) return cpad(e);
+    else if constexpr (LAYOUT == 1) return e;
+    else return e ^ (((e >> 4) & 7) << 1);
+}
 __device__ __forceinline__ int rpad(int i) { return i + (i >> 4); }             // row: 1 pad per 16
 
 // ---- kernel A / C: column passes -------------------------------------------------------------
 // One pass over blocks of 2^LB rows (j1 units) of a tile of N1 x T elements held at s[cpad(j1*T + t)].
 // kInv = false: DIF, forward, natural j1 in -> position order out;  kInv = true: the transposed DIT pass.
-template <int BITS1, int TILE_BITS, int LB, bool kInv, int THREADS, bool kSub1 = true>
+template <int BITS1, int TILE_BITS, int LB, bool kInv, int THREADS, bool kSub1 = true, bool kStaged = false, int LAYOUT = 0,
+          bool kStagedOut = false>
 __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, float2* __restrict__ gout, float2* s,
                                             int j2_0) {
     constexpr int RB = LB >= 4 ? 4 : LB, R = 1 << RB, SUBB = LB - RB, SUB = 1 << SUBB;
     constexpr int TB = TILE_BITS - BITS1, T = 1 << TB;
     // forward: the pass over the longest blocks comes first and reads global memory; inverse: last and writes it
-    constexpr bool kGlobalIn = kInv ? (SUBB == 0) : (LB == BITS1);
-    constexpr bool kGlobalOut = kInv ? (LB == BITS1) : (SUBB == 0);
+    // (kStaged: the tile was copied into `s` asynchronously beforehand, so the first pass reads shared memory too)
+    constexpr bool kFirst = kInv ? (SUBB == 0) : (LB == BITS1);
+    constexpr bool kGlobalIn = kFirst && !kStaged;
+    constexpr bool kGlobalOut = !kStagedOut && (kInv ? (LB == BITS1) : (SUBB == 0));
     constexpr int ITEMS = (1 << TILE_BITS) >> RB;
     static_assert(ITEMS % THREADS == 0, "tile too small for the CTA");
     constexpr int ITERS = ITEMS / THREADS;
@@ -476,13 +492,13 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
 #pragma unroll
             for (int m = 0; m < R; ++m)
                 v[m] = gload<kHin>(gin + (((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t), pol_in);
-            if constexpr (!kInv && kSub1) {          // rho = n - n0 (src/baseline_solver.py:60)
-#pragma unroll
-                for (int m = 0; m < R; ++m) v[m] = make_float2(__fsub_rn(v[m].x, 1.0f), __fsub_rn(v[m].y, 1.0f));
-            }
         } else {
 #pragma unroll
-            for (int m = 0; m < R; ++m) v[m] = s[cpad(((j1_0 + (m << SUBB)) << TB) + t)];
+            for (int m = 0; m < R; ++m) v[m] = s[cidx<LAYOUT>(((j1_0 + (m << SUBB)) << TB) + t)];
+        }
+        if constexpr (kFirst && !kInv && kSub1) {    // rho = n - n0 (src/baseline_solver.py:60)
+#pragma unroll
+            for (int m = 0; m < R; ++m) v[m] = make_float2(__fsub_rn(v[m].x, 1.0f), __fsub_rn(v[m].y, 1.0f));
         }
         if constexpr (!kSharedTw) pw.init(unit_root((base << kRowBits) + j2_0 + t, LB + kRowBits, sign));
         if constexpr (!kInv) {
@@ -498,22 +514,23 @@ __device__ __forceinline__ void column_pass(const float2* __restrict__ gin, floa
                 gstore<kHout>(gout + (((size_t)(j1_0 + (m << SUBB)) << kRowBits) + j2_0 + t), v[m], pol_out);
         } else {
 #pragma unroll
-            for (int m = 0; m < R; ++m) s[cpad(((j1_0 + (m << SUBB)) << TB) + t)] = v[m];
+            for (int m = 0; m < R; ++m) s[cidx<LAYOUT>(((j1_0 + (m << SUBB)) << TB) + t)] = v[m];
         }
     }
     if constexpr (!kGlobalOut) __syncthreads();
 }
 
-template <int BITS1, int TILE_BITS, int LB, int THREADS, bool kSub1 = true>
+template <int BITS1, int TILE_BITS, int LB, int THREADS, bool kSub1 = true, bool kStaged = false, int LAYOUT = 0,
+          bool kStagedOut = false>
 __device__ __forceinline__ void columns_forward(const float2* gin, float2* gout, float2* s, int j2_0) {
-    column_pass<BITS1, TILE_BITS, LB, false, THREADS, kSub1>(gin, gout, s, j2_0);
+    column_pass<BITS1, TILE_BITS, LB, false, THREADS, kSub1, kStaged, LAYOUT, kStagedOut>(gin, gout, s, j2_0);
     constexpr int SUBB = LB - (LB >= 4 ? 4 : LB);
-    if constexpr (SUBB > 0) columns_forward<BITS1, TILE_BITS, SUBB, THREADS, kSub1>(gin, gout, s, j2_0);
+    if constexpr (SUBB > 0) columns_forward<BITS1, TILE_BITS, SUBB, THREADS, kSub1, kStaged, LAYOUT, kStagedOut>(gin, gout, s, j2_0);
 }
-template <int BITS1, int TILE_BITS, int LB, int THREADS>
+template <int BITS1, int TILE_BITS, int LB, int THREADS, bool kStaged = false, int LAYOUT = 0, bool kStagedOut = false>
 __device__ __forceinline__ void columns_inverse(const float2* gin, float2* gout, float2* s, int j2_0) {
-    column_pass<BITS1, TILE_BITS, LB, true, THREADS>(gin, gout, s, j2_0);
-    if constexpr (LB < BITS1) columns_inverse<BITS1, TILE_BITS, LB + 4, THREADS>(gin, gout, s, j2_0);
+    column_pass<BITS1, TILE_BITS, LB, true, THREADS, true, kStaged, LAYOUT, kStagedOut>(gin, gout, s, j2_0);
+    if constexpr (LB < BITS1) columns_inverse<BITS1, TILE_BITS, LB + 4, THREADS, kStaged, LAYOUT, kStagedOut>(gin, gout, s, j2_0);
 }
 __host__ __device__ constexpr int first_inverse_lb(int bits1) { return bits1 < 4 ? bits1 : ((bits1 & 3) ? (bits1 & 3) : 4); }
 __host__ __device__ constexpr int column_tile_bits(int bits1) {
@@ -547,6 +564,142 @@ poisson_fft_cols_inv_kernel(const float2* __restrict__ Y, float* __restrict__ E,
     const float2* src = Y + ((size_t)blockIdx.y << (BITS1 + kRowBits));
     float2* dst = reinterpret_cast<float2*>(E + (size_t)blockIdx.y * e_stride);
     columns_inverse<BITS1, TILE_BITS, first_inverse_lb(BITS1), column_threads(BITS1)>(src, dst, sfft, j2_0);
+}
+
+// ---- column passes with asynchronously staged tiles (long grids) ------------------------------------------------
+// The plain column kernels above load a tile (2^13 points as 32-byte pieces 32 KiB apart), transform it and store it,
+// strictly in sequence per CTA: with two CTAs per SM only ~20 KiB per SM are in flight on average and the passes reach
+// about half of the HBM bandwidth.  Here ONE persistent 512-thread CTA per SM owns two tile buffers: while it transforms
+// the tile in one of them, cp.async (16-byte copies that bypass the registers and L1) fills the other with the next
+// tile, so a whole tile per SM is always in flight.  Same passes on the same padded layout, hence identical results.
+constexpr int kStagedThreads = 512;
+constexpr int kStagedTileBits = 13;
+constexpr int kStagedTile = (1 << kStagedTileBits) + ((1 << kStagedTileBits) >> 5) * 4;       // float2 elements per buffer
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copy tile `it` = (IC b, column tile) of a [B][N1][4096] float2 matrix into the padded buffer: row j1 = T points
+template <int BITS1>
+__device__ __forceinline__ void stage_tile(float2* buf, const float2* base, long long ic_stride, int it, int tiles) {
+    constexpr int TB = kStagedTileBits - BITS1, T = 1 << TB, N1 = 1 << BITS1;
+    constexpr int kChunksPerRow = T / 2;                              // 16-byte chunks (2 points) per row
+    const int b = it / tiles, tile = it - b * tiles;
+    const float2* src = base + (size_t)b * ic_stride + (tile << TB);
+    for (int c = threadIdx.x; c < N1 * kChunksPerRow; c += kStagedThreads) {
+        const int j1 = c / kChunksPerRow, p = (c - j1 * kChunksPerRow) * 2;
+        cp_async_16(buf + cpad((j1 << TB) + p), src + ((size_t)j1 << kRowBits) + p);
+    }
+}
+
+// kInv = false: pass A (density or complex signal -> Y);  kInv = true: pass C (Y -> field).  in / out strides in float2 per IC.
+template <int BITS1, bool kInv, bool kSub1>
+__global__ void __launch_bounds__(kStagedThreads, 1) poisson_fft_cols_staged_kernel(const float2* __restrict__ in,
+                                                                                   long long in_stride,
+                                                                                   float2* __restrict__ out,
+                                                                                   long long out_stride, int tiles,
+                                                                                   int total) {
+    extern __shared__ __align__(16) float2 sfft[];
+    constexpr int TB = kStagedTileBits - BITS1;
+    int cur = 0;
+    if ((int)blockIdx.x < total) stage_tile<BITS1>(sfft, in, in_stride, blockIdx.x, tiles);
+    cp_async_commit();
+    for (int it = blockIdx.x; it < total; it += gridDim.x, cur ^= 1) {
+        const int nit = it + gridDim.x;
+        float2* tile_buf = sfft + cur * kStagedTile;
+        if (nit < total) stage_tile<BITS1>(sfft + (cur ^ 1) * kStagedTile, in, in_stride, nit, tiles);
+        cp_async_commit();
+        cp_async_wait<1>();                           // this tile's copies have landed (the next tile's may be in flight)
+        __syncthreads();
+        const int b = it / tiles, tile = it - b * tiles;
+        float2* dst = out + (size_t)b * out_stride;
+        if constexpr (kInv)
+            columns_inverse<BITS1, kStagedTileBits, first_inverse_lb(BITS1), kStagedThreads, true>(nullptr, dst, tile_buf, tile << TB);
+        else
+            columns_forward<BITS1, kStagedTileBits, BITS1, kStagedThreads, kSub1, true>(nullptr, dst, tile_buf, tile << TB);
+        __syncthreads();                              // the buffer may be refilled by the next iteration's copies
+    }
+    cp_async_wait<0>();
+}
+
+// ---- column passes through the TMA unit (long grids) ------------------------------------------------------------
+// The column tile (N1 rows of T points, 32..128 bytes each, 32 KiB apart) is one 3-D tensor box per 256 rows for the TMA
+// unit (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG): loads and stores then cost no load/store-unit wavefronts at all
+// -- which, at one wavefront per 32-byte piece, is what bounds the kernels above -- and no registers.  One persistent
+// 512-thread CTA per SM rotates three dense 64 KiB tile buffers (next tile loading, this tile being transformed in
+// place, previous tile being stored); the buffers use the unit's 128-byte swizzle, which keeps every pass free of bank
+// conflicts the way the padding does in the other kernels.  Same passes, same arithmetic, identical results.
+constexpr int kTmaThreads = 512;
+constexpr int kTmaTileBits = 13;
+constexpr int kTmaBoxRows = 256;
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+template <int BITS1, bool kInv, bool kSub1, int LAYOUT>
+__global__ void __launch_bounds__(kTmaThreads, 1) poisson_fft_cols_tma_kernel(const __grid_constant__ CUtensorMap map_in,
+                                                                             const __grid_constant__ CUtensorMap map_out,
+                                                                             int tiles, int total) {
+    extern __shared__ __align__(1024) unsigned char tma_smem[];
+    constexpr int TB = kTmaTileBits - BITS1, T = 1 << TB, N1 = 1 << BITS1;
+    constexpr int kTile = 1 << kTmaTileBits;                           // points per tile buffer (dense)
+    constexpr uint32_t kTileBytes = kTile * 8u;
+    unsigned char* base = tma_smem + ((1024u - (smem_u32(tma_smem) & 1023u)) & 1023u);      // the swizzle needs 1024-byte alignment
+    float2* bufs = reinterpret_cast<float2*>(base);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + 3 * kTileBytes);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue_load = [&](int it, int slot) {                          // thread 0
+        const int b = it / tiles, tile = it - b * tiles;
+        mbar_arrive_expect_tx(&full[slot], kTileBytes);
+        for (int r = 0; r < N1; r += kTmaBoxRows)
+            tma_load_3d(bufs + (size_t)slot * kTile + r * T, &map_in, 2 * (tile << TB), r, b, &full[slot]);
+    };
+    const int stride = gridDim.x;
+    if (tid == 0) {
+        if ((int)blockIdx.x < total) issue_load(blockIdx.x, 0);
+        if ((int)blockIdx.x + stride < total) issue_load(blockIdx.x + stride, 1);
+    }
+    int k = 0;
+    for (int it = blockIdx.x; it < total; it += stride, ++k) {
+        const int slot = k % 3;
+        float2* buf = bufs + (size_t)slot * kTile;
+        mbar_wait(&full[slot], (uint32_t)((k / 3) & 1));
+        const int b = it / tiles, tile = it - b * tiles;
+        if constexpr (kInv)
+            columns_inverse<BITS1, kTmaTileBits, first_inverse_lb(BITS1), kTmaThreads, true, LAYOUT, true>(nullptr, nullptr, buf, tile << TB);
+        else
+            columns_forward<BITS1, kTmaTileBits, BITS1, kTmaThreads, kSub1, true, LAYOUT, true>(nullptr, nullptr, buf, tile << TB);
+        fence_proxy_async();                          // the tile (generic-proxy stores) becomes visible to the TMA unit
+        __syncthreads();
+        if (tid == 0) {
+            for (int r = 0; r < N1; r += kTmaBoxRows) tma_store_3d(&map_out, 2 * (tile << TB), r, b, buf + r * T);
+            tma_commit();
+            // the buffer of iteration k-1 is the target of the load for iteration k+2: its store must have read it
+            if (it + 2 * stride < total) {
+                tma_wait_read<1>();
+                issue_load(it + 2 * stride, (k + 2) % 3);
+            }
+        }
+    }
+    if (tid == 0) tma_wait_read<0>();                 // shared memory must outlive the stores that read it
 }
 
 namespace {
@@ -1113,9 +1266,145 @@ size_t poisson_fft_workspace_bytes(int B, int nx) {
 }
 
 // One column pass of the four-step solve: inverse = 0: density n -> Y (pass A); 1: Y -> field E (pass C).
+// Tensor map of a [B] x [N1 rows] x [8192 floats] array (row pitch 32 KiB, IC stride given in floats), box = one
+// 256-row piece of a column tile; the driver entry point is looked up once (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+static int column_tile_map(CUtensorMap* map, const void* base, long long ic_stride_floats, int B, int bits1, bool swizzle) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return set_error(FLUXGNN_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const int T = 1 << (kTmaTileBits - bits1);
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * kRowLen, (cuuint64_t)1 << bits1, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)2 * kRowLen * sizeof(float), (cuuint64_t)ic_stride_floats * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * T), (cuuint32_t)kTmaBoxRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return set_error(FLUXGNN_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return FLUXGNN_OK;
+}
+
+// 0 = plain / cp.async kernels, 1 = TMA without swizzle, 2 = TMA with the 128-byte swizzle (default for long grids)
+static int tma_cols_mode(int bits1, long long tiles_total) {
+    // Measured (profiles/r2_field_solve_variants.md): 5 % / 3 % faster than the plain kernels for 128- / 64-byte tile rows
+    // (N1 = 512 / 1024), 2 % slower for 32-byte rows (N1 = 2048, where the dense tile has 4-way bank conflicts in the
+    // radix-8 pass), so the default takes the TMA kernels for N1 <= 1024 only.  FLUXGNN_FFT_TMA = 0 / 1 / 2 forces
+    // plain / dense / swizzled (test hook and experiment switch).
+    const char* env = getenv("FLUXGNN_FFT_TMA");
+    const bool forced = env != nullptr && env[0] >= '0' && env[0] <= '2';
+    const int want = forced ? env[0] - '0' : (bits1 <= 10 ? 2 : 0);
+    if (want == 0 || bits1 < 9 || bits1 > 11 || tiles_total < 2 * 148 || encode_tiled_fn() == nullptr) return 0;
+    // SWIZZLE_128B needs 128-byte tile rows (16 points, N1 = 512); narrower boxes fault with it, so they stay dense
+    return (want == 2 && bits1 != 9) ? 1 : want;
+}
+
+template <bool kInv, bool kSub1>
+static int launch_cols_tma(const float* in, long long in_stride_floats, float* out, long long out_stride_floats, int B,
+                           int bits1, int mode, cudaStream_t stream) {
+    CUtensorMap map_in, map_out;
+    int rc = column_tile_map(&map_in, in, in_stride_floats, B, bits1, mode == 2);
+    if (rc != FLUXGNN_OK) return rc;
+    rc = column_tile_map(&map_out, out, out_stride_floats, B, bits1, mode == 2);
+    if (rc != FLUXGNN_OK) return rc;
+    const int tiles = kRowLen >> (kTmaTileBits - bits1), total = tiles * B;
+    const size_t smem = (size_t)3 * (8u << kTmaTileBits) + 64 + 1024;
+    int dev = 0, sms = 0;
+    FLUXGNN_CUDA_OK(cudaGetDevice(&dev));
+    FLUXGNN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = total < sms ? total : sms;
+#define FLUXGNN_TMA_ONE(BITS1, LAYOUT)                                                                                     \
+    {                                                                                                                      \
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_tma_kernel<BITS1, kInv, kSub1, LAYOUT>,                       \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+        poisson_fft_cols_tma_kernel<BITS1, kInv, kSub1, LAYOUT><<<grid, kTmaThreads, smem, stream>>>(map_in, map_out, tiles, total); \
+    }
+#define FLUXGNN_TMA(BITS1)                                          \
+    case BITS1:                                                     \
+        if (mode == 2) FLUXGNN_TMA_ONE(BITS1, 2) else FLUXGNN_TMA_ONE(BITS1, 1) \
+        break;
+    switch (bits1) {
+        FLUXGNN_TMA(9) FLUXGNN_TMA(10) FLUXGNN_TMA(11)
+        default: return set_error(FLUXGNN_EUNSUP, "TMA column pass: unsupported column length 2^%d", bits1);
+    }
+#undef FLUXGNN_TMA
+#undef FLUXGNN_TMA_ONE
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+// Staged (double-buffered, persistent) column pass: in / out are [B] matrices of N1 x 4096 points with the given IC
+// strides (float2).  Returns FLUXGNN_EUNSUP when this shape keeps the plain kernels.
+static bool staged_cols_ok(int bits1, long long tiles_total) {
+    // opt-in (FLUXGNN_FFT_STAGING=1): measured SLOWER than the plain kernels (50 / 45 us against 40 / 36 us per pass at
+    // 2^24 cells): the passes are bound by load/store-unit wavefronts (one per 32-byte piece), not by load latency
+    const char* on = getenv("FLUXGNN_FFT_STAGING");
+    if (on == nullptr || on[0] != '1') return false;
+    return bits1 >= 5 && bits1 <= 11 && tiles_total >= 2 * 148;        // 2^13-point tiles; enough tiles to pipeline
+}
+
+template <bool kInv, bool kSub1>
+static int launch_cols_staged(const float2* in, long long in_stride, float2* out, long long out_stride, int B, int bits1,
+                              cudaStream_t stream) {
+    const int tiles = kRowLen >> (kStagedTileBits - bits1), total = tiles * B;
+    const size_t smem = (size_t)2 * kStagedTile * sizeof(float2);
+    int dev = 0, sms = 0;
+    FLUXGNN_CUDA_OK(cudaGetDevice(&dev));
+    FLUXGNN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = total < sms ? total : sms;
+#define FLUXGNN_STAGED(BITS1)                                                                                              \
+    case BITS1:                                                                                                            \
+        FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_staged_kernel<BITS1, kInv, kSub1>,                            \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+        poisson_fft_cols_staged_kernel<BITS1, kInv, kSub1><<<grid, kStagedThreads, smem, stream>>>(in, in_stride, out,      \
+                                                                                                out_stride, tiles, total); \
+        break;
+    switch (bits1) {
+        FLUXGNN_STAGED(5) FLUXGNN_STAGED(6) FLUXGNN_STAGED(7) FLUXGNN_STAGED(8) FLUXGNN_STAGED(9) FLUXGNN_STAGED(10)
+        FLUXGNN_STAGED(11)
+        default: return set_error(FLUXGNN_EUNSUP, "staged column pass: unsupported column length 2^%d", bits1);
+    }
+#undef FLUXGNN_STAGED
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 int launch_poisson_fft_cols(const float* n, long long n_stride, float2* Y, float* E, long long e_stride, int B, int nx,
                             int inverse, cudaStream_t stream) {
     const int bits1 = ilog2_exact(nx) - 1 - kRowBits;
+    if (bits1 >= 9 && bits1 <= 11) {
+        const int mode = tma_cols_mode(bits1, (long long)B * (kRowLen >> (kTmaTileBits - bits1)));
+        if (mode != 0) {
+            const long long ystride = (long long)2 << (bits1 + kRowBits);                    // floats per IC of Y
+            if (!inverse) return launch_cols_tma<false, true>(n, n_stride, reinterpret_cast<float*>(Y), ystride, B, bits1, mode, stream);
+            return launch_cols_tma<true, true>(reinterpret_cast<const float*>(Y), ystride, E, e_stride, B, bits1, mode, stream);
+        }
+    }
+    if (bits1 <= 11 && staged_cols_ok(bits1, (long long)B * (kRowLen >> (kStagedTileBits - bits1)))) {
+        const long long ystride = (long long)1 << (bits1 + kRowBits);
+        if (!inverse)
+            return launch_cols_staged<false, true>(reinterpret_cast<const float2*>(n), n_stride / 2, Y, ystride, B, bits1, stream);
+        return launch_cols_staged<true, true>(Y, ystride, reinterpret_cast<float2*>(E), e_stride / 2, B, bits1, stream);
+    }
     const int tile_bits = column_tile_bits(bits1);
     const int T = 1 << (tile_bits - bits1);
     const size_t tile = (size_t)1 << tile_bits;
@@ -1339,6 +1628,25 @@ int launch_poisson_dist_local(float2* y, float2* scratch, int P, int S, int G, i
     const float scale = (float)(length / (6.283185307179586476925 * (double)S));
     dim3 gcol((unsigned)(kRowLen / T), (unsigned)P), grow((unsigned)((1 << bits1) / 2), (unsigned)P);
     FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_rows_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+    if (bits1 >= 9 && bits1 <= 11) {
+        const int mode = tma_cols_mode(bits1, (long long)P * (kRowLen / T));
+        if (mode != 0) {
+            rc = launch_cols_tma<false, false>((const float*)y, 2LL * S, (float*)scratch, 2LL * S, P, bits1, mode, stream);
+            if (rc != FLUXGNN_OK) return rc;
+            poisson_fft_rows_diag_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(scratch, bits1, scale, G, kr);
+            FLUXGNN_CUDA_OK(cudaGetLastError());
+            count_launch();
+            return launch_cols_tma<true, true>((const float*)scratch, 2LL * S, (float*)y, 2LL * S, P, bits1, mode, stream);
+        }
+    }
+    if (staged_cols_ok(bits1, (long long)P * (kRowLen / T))) {
+        rc = launch_cols_staged<false, false>(y, S, scratch, S, P, bits1, stream);
+        if (rc != FLUXGNN_OK) return rc;
+        poisson_fft_rows_diag_kernel<<<grow, kFftStepThreads, smem_row, stream>>>(scratch, bits1, scale, G, kr);
+        FLUXGNN_CUDA_OK(cudaGetLastError());
+        count_launch();
+        return launch_cols_staged<true, true>(scratch, S, y, S, P, bits1, stream);
+    }
 #define FLUXGNN_DIST_COLS(BITS1)                                                                                         \
     case BITS1:                                                                                                          \
         FLUXGNN_CUDA_OK(cudaFuncSetAttribute(poisson_fft_cols_fwd_kernel<BITS1, false>,                                  \

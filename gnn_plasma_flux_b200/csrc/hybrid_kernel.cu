@@ -19,6 +19,24 @@ static cudaError_t dispatch(const HybridArgs& a, int fast_radius, int grid, cuda
     }
 }
 
+template <int R, bool kSave>
+cudaError_t max_clusters_one(int csize, int* out);
+
+// Clusters of `csize` CTAs the device runs concurrently (every radius instantiation has the same footprint); cached.
+int hybrid_max_active_clusters(int csize) {
+    static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (csize < 2 || csize > 8) return 0;
+    if (cache[csize] == 0) {
+        int n = 0;
+        if (max_clusters_one<1, false>(csize, &n) != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = -1;
+        }
+        cache[csize] = n;
+    }
+    return cache[csize] > 0 ? cache[csize] : 0;
+}
+
 cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream) {
     return a.acts != nullptr ? dispatch<true>(a, fast_radius, grid, stream) : dispatch<false>(a, fast_radius, grid, stream);
 }

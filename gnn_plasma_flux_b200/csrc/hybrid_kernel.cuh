@@ -39,6 +39,10 @@ struct HybridArgs {
     int slab;                  // 1: one slab of a domain-decomposed grid.  state_in and x are
     int ld_in;                 //    [..][ld_in] = nx owned cells + `halo` ghost cells per side, no
                                //    periodic wrap; nx counts the OWNED cells; outputs are [..][nx]
+    int cluster;               // FP32-pipe kernel, window / slab tiles: CTAs per thread-block cluster (0/1 = none).  The CTAs of a
+                               //    cluster hold consecutive, 4-row overlapping 128-row pieces of ONE window and read each
+                               //    other's edge rows of Z through distributed shared memory, so only the cluster's two outer
+                               //    ends carry a recomputed halo.  num_tiles / valid / tiles_per_ic count cluster windows.
     int ld_out, out_off;       // window / slab outputs: row length of state_out and offset of cell 0 in it
                                //    (0, 0 = [..][nx]; a slab that writes the interior of the next extended state
                                //    passes ld_out = nx + 2*halo, out_off = halo)
@@ -46,6 +50,8 @@ struct HybridArgs {
 
 // fast_radius 1..4 selects the compile-time-radius window path; 0 the generic path.
 cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream);
+
+int hybrid_max_active_clusters(int csize);    // 0 when clusters of that size cannot be launched
 
 // Tensor-core (tcgen05) variant, hybrid_tc_kernel.cu: radius 1..4, a.hops == 1, segments of 32/64/128 rows.
 cudaError_t launch_hybrid_tc_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream);

@@ -64,6 +64,7 @@ struct __align__(128) TileSmem {
     short prevRow[kTileRows], nextRow[kTileRows];
     uint64_t full[kStages], empty[kStages];
     uint64_t skew;                       // split mode: group 1 starts once group 0 is kSkewChunks ahead
+    uint64_t zready, zfree;              // cluster mode: the neighbours' Z is complete / they have read this CTA's Z
 };
 static_assert(sizeof(TileSmem) <= 227 * 1024, "tile does not fit shared memory");
 
@@ -186,12 +187,16 @@ __device__ __forceinline__ void gemm_pass(float (&acc)[8][8], TileSmem& S, Pipe&
 }
 
 // 16-row window Z[n][R0-4 .. R0+11] (periodic inside the segment) of feature n
+// zl / zr: shared::cluster address of the neighbouring CTA's Zs when the window's left / right chunk lies in its piece
+// of the cluster window (0 otherwise); n = feature.
 __device__ __forceinline__ void load_window(float (&v)[16], const float* zrow, int sw,
-                                            int cl, int c0, int c1, int cr) {
-    const float4 l = *reinterpret_cast<const float4*>(zrow + ((cl ^ sw) << 2));
+                                            int cl, int c0, int c1, int cr, uint32_t zl = 0, uint32_t zr = 0, int n = 0) {
+    const float4 l = zl ? ld_cluster_f4(zl + (uint32_t)((n * kTileRows + ((cl ^ sw) << 2)) * 4))
+                        : *reinterpret_cast<const float4*>(zrow + ((cl ^ sw) << 2));
     const float4 m0 = *reinterpret_cast<const float4*>(zrow + ((c0 ^ sw) << 2));
     const float4 m1 = *reinterpret_cast<const float4*>(zrow + ((c1 ^ sw) << 2));
-    const float4 r = *reinterpret_cast<const float4*>(zrow + ((cr ^ sw) << 2));
+    const float4 r = zr ? ld_cluster_f4(zr + (uint32_t)((n * kTileRows + ((cr ^ sw) << 2)) * 4))
+                        : *reinterpret_cast<const float4*>(zrow + ((cr ^ sw) << 2));
     v[0] = l.x;  v[1] = l.y;  v[2] = l.z;  v[3] = l.w;
     v[4] = m0.x; v[5] = m0.y; v[6] = m0.z; v[7] = m0.w;
     v[8] = m1.x; v[9] = m1.y; v[10] = m1.z; v[11] = m1.w;
@@ -236,11 +241,22 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
         mbar_init(&S.skew, kConsumerWarps / 2);
         mbar_fence_init();
     }
+    // cluster mode: this CTA is piece `crank` of a window of `csize` pieces; neighbours exist inside the window only
+    const int csize = a.cluster > 1 ? a.cluster : 1;
+    const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+    const bool hasL = crank > 0, hasR = crank < csize - 1;
+    if (csize > 1 && tid == 0) {
+        mbar_init(&S.zready, (hasL ? 1 : 0) + (hasR ? 1 : 0));
+        mbar_init(&S.zfree, (hasL ? 1 : 0) + (hasR ? 1 : 0));
+        mbar_fence_init();
+    }
     if (a.whole_ic && a.do_update)
         for (int i = tid; i < nx; i += kThreads) S.gtab[i] = a.gtab[i];
     __syncthreads();
+    if (csize > 1) cluster_sync_all();               // nobody signals a barrier that is not initialised yet
 
-    const int my_tiles = (a.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int first_tile = (int)blockIdx.x / csize, tile_stride = (int)gridDim.x / csize;
+    const int my_tiles = (a.num_tiles - first_tile + tile_stride - 1) / tile_stride;
     const int chunks_per_step = (a.L + 1) * 2 * kChunksPerHalf;
 
     if (warp == kConsumerWarps) {
@@ -294,14 +310,31 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
     const int bar = 1 + grp;
     const bool leads_skew = a.split && grp == 0;
     const TileRows T{S.sN, S.sU, S.sE, S.sX, S.sF, S.sRho, S.gtab, S.rowIC, S.rowCell, S.prevRow, S.nextRow};
+    // cluster mode: rows -4..-1 of the first row group are rows 120..123 of the left piece (4-row overlap), rows
+    // 128..131 of the last row group are rows 4..7 of the right piece
+    uint32_t zl = 0, zr_remote = 0, sig_l = 0, sig_r = 0, free_l = 0, free_r = 0;
+    uint32_t zready_parity = 0, zfree_parity = 0;
+    bool z_pending = false;                          // a Z generation of this CTA may still be read by a neighbour
+    if (csize > 1) {
+        if (hasL) {
+            if (ty == 0) { zl = cluster_map(smem_u32(S.Zs), crank - 1); cl = 30; }
+            sig_l = cluster_map(smem_u32(&S.zready), crank - 1);
+            free_l = cluster_map(smem_u32(&S.zfree), crank - 1);
+        }
+        if (hasR) {
+            if (ty == 15) { zr_remote = cluster_map(smem_u32(S.Zs), crank + 1); cr = 1; }
+            sig_r = cluster_map(smem_u32(&S.zready), crank + 1);
+            free_r = cluster_map(smem_u32(&S.zfree), crank + 1);
+        }
+    }
     if (a.split && grp == 1) mbar_wait(&S.skew, 0);
 #ifdef FLUXGNN_FFMA_TIMING
     const long long t_start = clock64();
 #endif
 
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < a.num_tiles; tile += tile_stride) {
         // ---- row bookkeeping + state load -----------------------------------------
-        if (myrow >= 0) tile_load_row(a, T, tile, true, myrow, myrow, 0, kTileRows);
+        if (myrow >= 0) tile_load_row(a, T, tile, true, myrow, myrow, 0, kTileRows, crank);
         named_sync(bar, gthreads);
 
         for (int step = 0; step < a.steps; ++step) {
@@ -352,15 +385,36 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                     }
                     gemm_pass(acc, S, pipe, xo, tx, lane, leads_skew);
                     if (pass == 0) {
+                        if (csize > 1 && z_pending) {        // the neighbours have read the previous layer's edge rows
+                            mbar_wait_cluster(&S.zfree, zfree_parity);
+                            zfree_parity ^= 1;
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float* zr = S.Zs + col_of(tx, j) * kTileRows;
                             *reinterpret_cast<float4*>(zr + ((c0 ^ sw) << 2)) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
                             *reinterpret_cast<float4*>(zr + ((c1 ^ sw) << 2)) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
                         }
+                        // cluster mode: the left neighbour reads rows 4..7 (written by warps 0 and 1), the right one rows
+                        // 120..123 (warps 6 and 7).  Tell them as soon as those rows are stored: the signal then travels
+                        // under the whole second GEMM pass instead of being waited for.
+                        if (csize > 1) {
+                            if (warp < 2) {
+                                named_sync(3, 64);
+                                if (tid == 0 && hasL) mbar_arrive_remote(sig_l);
+                            } else if (warp >= kConsumerWarps - 2) {
+                                named_sync(4, 64);
+                                if (tid == (kConsumerWarps - 2) * 32 && hasR) mbar_arrive_remote(sig_r);
+                            }
+                        }
                     }
                 }
                 named_sync(bar, gthreads);      // Z complete; nobody reads Hs any more
+                if (csize > 1) {                // the neighbours' edge rows of Z (signalled one GEMM pass ago)
+                    mbar_wait_cluster(&S.zready, zready_parity);
+                    zready_parity ^= 1;
+                    z_pending = true;
+                }
 
                 if (layer < a.L) {
                     // ---- node update: h' = relu(Y + mean_{|k|<=r, k!=0} Z_{i+k})  (src/flux_gnn.py:55-60)
@@ -371,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         float h[8];
                         if (R > 0) {
                             float v[16];
-                            load_window(v, zr, sw, cl, c0, c1, cr);
+                            load_window(v, zr, sw, cl, c0, c1, cr, zl, zr_remote, n);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int c = 4 + i;
@@ -398,6 +452,10 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
                     }
                     named_sync(bar, gthreads);  // h' complete; Z free
+                    if (csize > 1 && tid == 0) {
+                        if (hasL) mbar_arrive_remote(free_l);
+                        if (hasR) mbar_arrive_remote(free_r);
+                    }
                     if (kSave)
                         save_rows(S.Hs, a.acts + (size_t)(layer + 1) * a.acts_stride, S, lt, gthreads, row0, nrows, nx);
                 } else {
@@ -428,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                                 const float* zr = S.Zs + n * kTileRows;
                                 if (R > 0) {
                                     float v[16];
-                                    load_window(v, zr, sw, cl, c0, c1, cr);
+                                    load_window(v, zr, sw, cl, c0, c1, cr, zl, zr_remote, n);
 #pragma unroll
                                     for (int i = 0; i < 8; ++i) {
                                         pf[i] = fmaf(w2, fmaxf(acc[i][j] + v[4 + i + hop], 0.f), pf[i]);
@@ -463,6 +521,10 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         }
                     }
                     named_sync(bar, gthreads);
+                    if (csize > 1 && tid == 0) {
+                        if (hasL) mbar_arrive_remote(free_l);
+                        if (hasR) mbar_arrive_remote(free_r);
+                    }
                 }
             }   // layers
 
@@ -514,6 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
         }   // steps
         named_sync(bar, gthreads);   // state arrays are rewritten by the next tile's load
     }       // tiles
+    if (csize > 1 && z_pending) mbar_wait_cluster(&S.zfree, zfree_parity);   // shared memory must outlive the neighbours' reads
 #ifdef FLUXGNN_FFMA_TIMING
     if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
         printf("[ffma timing] warp %d (group %d): total %lld clk, in GEMM passes %lld, of which waiting for weights %lld\n",
@@ -530,8 +593,44 @@ cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(TileSmem));
     if (e != cudaSuccess) return e;
+    if (a.cluster > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = sizeof(TileSmem);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)a.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, hybrid_tile_kernel<R, kSave>, a);
+    }
     hybrid_tile_kernel<R, kSave><<<grid, kThreads, sizeof(TileSmem), stream>>>(a);
     return cudaGetLastError();
+}
+
+// How many clusters of `csize` CTAs of this kernel the device holds at once (one CTA per SM by shared memory; clusters
+// must sit inside a GPC, so this can be less than #SMs / csize).
+template <int R, bool kSave>
+cudaError_t max_clusters_one(int csize, int* out) {
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(TileSmem));
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(csize * 64));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = sizeof(TileSmem);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(out, hybrid_tile_kernel<R, kSave>, &cfg);
 }
 
 }  // namespace fluxgnn

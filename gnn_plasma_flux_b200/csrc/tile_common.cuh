@@ -22,8 +22,10 @@ struct TileRows {
 //                   (src/graph_constructor.py:34-38);
 //   window tiles  : rows [halo, halo + valid) of window t of one IC are owned, the rest is recomputed halo;
 //   slabs         : as windows, with ghost cells instead of the periodic wrap.
+constexpr int kClusterStep = 124;      // rows between the pieces of a cluster window: 128 minus a 4-row (one 16-byte chunk) overlap
+
 __device__ __forceinline__ void tile_load_row(const HybridArgs& a, const TileRows& T, int tile, bool tile_ok, int j, int jl,
-                                              int row0, int rows) {
+                                              int row0, int rows, int crank = 0) {
     const int nx = a.nx;
     int ic, cell, prev = row0 + ((jl - 1) & (rows - 1)), next = row0 + ((jl + 1) & (rows - 1));
     bool live, owned;
@@ -41,10 +43,16 @@ __device__ __forceinline__ void tile_load_row(const HybridArgs& a, const TileRow
     } else {
         ic = tile / a.tiles_per_ic;
         const int t = tile - ic * a.tiles_per_ic;
-        const long long gcell = (long long)t * a.valid - a.halo + jl;
+        // piece `crank` of a cluster window starts kClusterStep rows after its left neighbour; it owns the rows
+        // 4-hops .. 127-hops (first piece: from the halo; last piece: up to the halo), so the owned rows tile the window
+        const int csize = a.cluster > 1 ? a.cluster : 1;
+        const int wrow = crank * kClusterStep + jl;                     // row inside the window
+        const long long gcell = (long long)t * a.valid - a.halo + wrow;
         cell = (int)(((gcell % nx) + nx) % nx);
         live = tile_ok;
-        owned = tile_ok && (jl >= a.halo) && (jl < a.halo + a.valid) && ((long long)t * a.valid + (jl - a.halo) < nx);
+        // (a row's outputs need the edge partial sums of the `hops` rows after it and the face flux of the row before it)
+        const int lo = (crank == 0) ? a.halo : 4 - a.hops, hi = (crank == csize - 1) ? rows - a.halo : rows - a.hops;
+        owned = tile_ok && (jl >= lo) && (jl < hi) && ((long long)t * a.valid + (wrow - a.halo) < nx);
         if (a.slab) {                       // ghost cells instead of the periodic wrap
             long long s = gcell + a.halo;
             s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);

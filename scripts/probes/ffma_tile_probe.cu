@@ -94,6 +94,191 @@ __global__ void __launch_bounds__(kRows* kCols / (TM * TN), 1) probe_scalar(floa
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// Warp-uniform column operand: a warp owns 16 columns and ALL 128 rows (lane = 4 consecutive rows), so the row operand
+// is one conflict-free 128-bit load per lane (512 distinct bytes per warp) and the 16 column values are the same address
+// for every lane (broadcast).  Same 64 FMAs per thread and k-step as the 8x8 tile.
+template <bool kUniformViaShuffle>
+__global__ void __launch_bounds__(256, 1) probe_uniform_b(float* out, int iters) {
+    extern __shared__ __align__(16) float sm[];
+    float* As = sm;
+    float* Bs = sm + kK * kRows;
+    for (int i = threadIdx.x; i < kK * (kRows + kCols); i += blockDim.x) sm[i] = 1e-3f * (float)(i & 63);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 8
+        for (int k = 0; k < kK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(As + k * kRows + lane * 4);
+            float2 b[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(Bs + k * kCols + warp * 16 + j);
+                b[j / 2] = make_float2(v.x, v.y); b[j / 2 + 1] = make_float2(v.z, v.w);
+            }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = __ffma2_rn(make_float2(av[i], av[i]), b[j], acc[i][j]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j].x + acc[i][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 8 rows x 8 columns per thread, lane = (4 row groups) x (8 column groups) as in the tile kernel, but the column
+// operand is read with 64-bit loads (a half-warp phase then covers 16 lanes = two row groups x 8 column groups).
+__global__ void __launch_bounds__(256, 1) probe_8x8_lds64(float* out, int iters) {
+    extern __shared__ __align__(16) float sm[];
+    float* As = sm;
+    float* Bs = sm + kK * kRows;
+    for (int i = threadIdx.x; i < kK * (kRows + kCols); i += blockDim.x) sm[i] = 1e-3f * (float)(i & 63);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ty = (warp >> 1) * 4 + (lane >> 3), tx = (warp & 1) * 8 + (lane & 7);
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 8
+        for (int k = 0; k < kK; ++k) {
+            float a[8];
+            float2 b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(As + k * kRows + ty * 8 + i);
+                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float2*>(Bs + k * kCols + j * 32 + tx * 2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(a[i], a[i]), b[j], acc[i][j]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j].x + acc[i][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+
+// 2 rows x 32 columns per thread: a warp owns 64 rows (lane = 2 consecutive rows, one 64-bit load) and 32 columns
+// (eight warp-uniform 128-bit loads): 4 warps per 64-row group, so two independent row groups per tile remain possible.
+__global__ void __launch_bounds__(256, 1) probe_2x32_uniform(float* out, int iters) {
+    extern __shared__ __align__(16) float sm[];
+    float* As = sm;
+    float* Bs = sm + kK * kRows;
+    for (int i = threadIdx.x; i < kK * (kRows + kCols); i += blockDim.x) sm[i] = 1e-3f * (float)(i & 63);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row0 = (warp >> 2) * 64 + lane * 2, col0 = (warp & 3) * 32;
+    float2 acc[2][16];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 8
+        for (int k = 0; k < kK; ++k) {
+            const float2 a = *reinterpret_cast<const float2*>(As + k * kRows + row0);
+            float2 b[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(Bs + k * kCols + col0 + j);
+                b[j / 2] = make_float2(v.x, v.y); b[j / 2 + 1] = make_float2(v.z, v.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                acc[0][j] = __ffma2_rn(make_float2(a.x, a.x), b[j], acc[0][j]);
+                acc[1][j] = __ffma2_rn(make_float2(a.y, a.y), b[j], acc[1][j]);
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += acc[i][j].x + acc[i][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// The tile kernel's own mapping: lane = (4 row groups of 8 rows) x (8 column groups), rows by two broadcast 128-bit loads,
+// columns 4tx..4tx+3 and 64+4tx.. by two conflict-free 128-bit loads.
+__global__ void __launch_bounds__(256, 1) probe_8x8_kernel_mapping(float* out, int iters) {
+    extern __shared__ __align__(16) float sm[];
+    float* As = sm;
+    float* Bs = sm + kK * kRows;
+    for (int i = threadIdx.x; i < kK * (kRows + kCols); i += blockDim.x) sm[i] = 1e-3f * (float)(i & 63);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ty = (warp >> 1) * 4 + (lane >> 3), tx = (warp & 1) * 8 + (lane & 7);
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 8
+        for (int k = 0; k < kK; ++k) {
+            float a[8];
+            float2 b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(As + k * kRows + ty * 8 + i);
+                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            }
+            const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * kCols + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * kCols + 64 + tx * 4);
+            b[0] = make_float2(b0.x, b0.y); b[1] = make_float2(b0.z, b0.w);
+            b[2] = make_float2(b1.x, b1.y); b[3] = make_float2(b1.z, b1.w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(a[i], a[i]), b[j], acc[i][j]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j].x + acc[i][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename K>
+static void run_kernel(const char* name, K kern, int threads, float* out) {
+    const int iters = 200;
+    const size_t smem = (size_t)kK * (kRows + kCols) * sizeof(float);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    kern<<<148, threads, smem>>>(out, 2);
+    cudaEventRecord(e0);
+    kern<<<148, threads, smem>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * kRows * kCols * kK * iters * 148;
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    printf("%-22s %4d threads, %3d regs: %6.1f TFLOP/s %s\n", name, threads, fa.numRegs, flop / (ms * 1e-3) / 1e12,
+           e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 template <int TM, int TN, bool kScalar = false>
 static void run(const char* name, float* out) {
     const int threads = kRows * kCols / (TM * TN), iters = 200;
@@ -120,6 +305,10 @@ int main() {
     run<8, 16>("8x16", out);
     run<16, 16>("16x16", out);
     run<4, 8>("4x8", out);
+    run_kernel("4x16 uniform cols", probe_uniform_b<false>, 256, out);
+    run_kernel("8x8 cols by LDS.64", probe_8x8_lds64, 256, out);
+    run_kernel("8x8 kernel mapping", probe_8x8_kernel_mapping, 256, out);
+    run_kernel("2x32 uniform cols", probe_2x32_uniform, 256, out);
     run<8, 8, true>("8x8 FFMA", out);
     run<16, 8, true>("16x8 FFMA", out);
     run<8, 16, true>("8x16 FFMA", out);

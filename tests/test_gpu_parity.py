@@ -105,6 +105,41 @@ def test_poisson_fft_vs_oracle(built_lib, nx):
         assert err <= (1e-5 if name == "white" else 3e-6), (name, err)
 
 
+@pytest.mark.parametrize("log2nx,B", [(18, 40), (20, 6), (22, 2), (24, 1)])
+def test_column_pass_variants_are_bit_identical(built_lib, monkeypatch, log2nx, B):
+    """Long grids run the column passes of the four-step solve as persistent CTAs fed by the TMA unit (3-D tensor boxes,
+    128-byte swizzled tile buffers); the cp.async-staged variant and the un-swizzled TMA variant are kept as switches.
+    All of them execute the same passes in the same order, so the field equals the plain column kernels' bit for bit
+    (and the distributed local solve, which shares them, likewise)."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    from gnn_plasma_flux_b200.domain import DistributedFieldSolve, solve_emulated
+    nx = 1 << log2nx
+    sol = BaselineSolver(nx=nx, device="cuda")
+    gen = torch.Generator("cuda").manual_seed(log2nx)
+    n = 1.0 + 0.2 * torch.sin(torch.arange(nx, device="cuda") * (2 * np.pi * 5 / nx)).repeat(B, 1) + \
+        0.01 * torch.randn(B, nx, device="cuda", generator=gen)
+    S = nx // 2
+    dsol = [DistributedFieldSolve(nx, 2 * np.pi, r, 2, "cuda") for r in range(2)]
+
+    def solve_both():
+        E2 = torch.zeros_like(n)
+        solve_emulated(dsol, [n[:, r * S:(r + 1) * S] for r in range(2)], [E2[:, r * S:(r + 1) * S] for r in range(2)])
+        return sol.solve_poisson(n), E2
+
+    monkeypatch.setenv("FLUXGNN_FFT_TMA", "0")
+    plain = solve_both()
+    assert torch.isfinite(plain[0]).all()
+    for env in ({"FLUXGNN_FFT_TMA": "2"}, {"FLUXGNN_FFT_TMA": "1"}, {"FLUXGNN_FFT_TMA": "0", "FLUXGNN_FFT_STAGING": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = solve_both()
+        monkeypatch.delenv("FLUXGNN_FFT_STAGING", raising=False)
+        assert torch.equal(got[0], plain[0]), env
+        assert torch.equal(got[1], plain[1]), env
+    monkeypatch.delenv("FLUXGNN_FFT_TMA")
+    assert torch.equal(sol.solve_poisson(n), plain[0])
+
+
 @pytest.mark.parametrize("nx,B", [(1 << 16, 3), (1 << 20, 2)])
 def test_baseline_large_grid_vs_oracle(built_lib, nx, B):
     """Classical solver on large power-of-two grids (the shape of BASELINE.json configs[4], scaled)."""
@@ -571,6 +606,60 @@ def test_tc_rejects_unsupported_shapes(model):
         make_solver(model, 40, 5e-3, precision="fp16x3").rollout(torch.zeros(2, 3, 40, device="cuda"), 1)
     with pytest.raises(ValueError):
         make_solver(model, 64, 5e-3, precision="fp8")
+
+
+# ----------------------------------------------------------------------------- clustered window tiles
+@pytest.mark.parametrize("nx,radius,B", [(1024, 2, 5), (1000, 3, 3), (4096, 1, 2), (300, 4, 7)])
+def test_cluster_windows_are_bit_identical(model, weights, monkeypatch, nx, radius, B):
+    """Grids above 128 cells: clusters of 2-4 CTAs share one window (4-row overlapping 128-row pieces, edge rows of Z
+    read through distributed shared memory).  Every cell sees the same arithmetic whatever the tiling, so the step, the
+    forward fluxes (all hops) and a slab step must be bit-identical for every cluster size, and within tolerance of the
+    oracle."""
+    dt = 3e-4 * 1024 / nx
+    grid = P.Grid(nx=nx, dt=dt)
+    ics = np.stack([P.stable_initial_condition(grid, s) for s in range(B)])
+    dev = torch.from_numpy(ics).cuda()
+    xd = torch.from_numpy(grid.x.astype(np.float32)).cuda()
+    sol = make_solver(model, nx, dt, graph_radius=radius)
+    outs = {}
+    for c in (1, 2, 3, 4):
+        monkeypatch.setenv("FLUXGNN_CLUSTER", str(c))
+        step, _ = sol.rollout(dev, 2)
+        edges, face = model.ring_fluxes(dev, xd, radius=radius, hops=radius, want_face=True)
+        outs[c] = (step.clone(), edges.clone(), face.clone())
+    monkeypatch.delenv("FLUXGNN_CLUSTER")
+    auto, _ = sol.rollout(dev, 2)
+    for c in (2, 3, 4):
+        for got, want in zip(outs[c], outs[1]):
+            assert torch.equal(got, want), c
+    assert torch.equal(auto, outs[1][0])
+    ref = batched.hybrid_run(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, 2, radius=radius).numpy()
+    assert P.rel_err(outs[2][0].cpu().numpy(), ref).max() <= 2 * STEP_TOL
+
+
+def test_cluster_windows_many_tiles_and_slabs(model, monkeypatch):
+    """More windows than cluster slots (persistent loop over windows) and the slab entry point, forced cluster sizes."""
+    from gnn_plasma_flux_b200.domain import DomainDecomposedHybridSolver, split_slabs, step_emulated
+    nx, B, dt = 2048, 96, 1.5e-4
+    grid = P.Grid(nx=nx, dt=dt)
+    base = np.stack([P.stable_initial_condition(grid, s) for s in range(8)])
+    dev = torch.from_numpy(np.tile(base, (B // 8, 1, 1))).cuda()
+    dev[:, 1] += 1e-3 * torch.randn(B, 1, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    sol = make_solver(model, nx, dt, graph_radius=3)
+    monkeypatch.setenv("FLUXGNN_CLUSTER", "1")
+    want, _ = sol.rollout(dev, 1)
+    for c in (2, 3, 4):
+        monkeypatch.setenv("FLUXGNN_CLUSTER", str(c))
+        got, _ = sol.rollout(dev, 1)
+        assert torch.equal(got, want), c
+    # two virtual ranks: the slab kernel with ghost cells, clustered, against the undivided solver
+    solvers = [DomainDecomposedHybridSolver(model, nx, dt=dt, graph_radius=3, rank=r, world=2, device="cuda",
+                                            field_solve="allgather") for r in range(2)]
+    for c in (1, 3):
+        monkeypatch.setenv("FLUXGNN_CLUSTER", str(c))
+        got = torch.cat(list(step_emulated(solvers, split_slabs(dev[:4].contiguous(), 2))), dim=-1)
+        assert torch.equal(got, want[:4]), c
+    monkeypatch.delenv("FLUXGNN_CLUSTER")
 
 
 # ----------------------------------------------------------------------------- other architectures (generic kernels)
