@@ -58,7 +58,9 @@ static void choose_cluster(HybridArgs& a, int cells) {
         const long long windows = (long long)a.B * ((cells + valid - 1) / valid);
         const long long slots = eff_sms / c;                                   // windows in flight
         const long long waves = (windows + slots - 1) / slots;                 // each wave costs one tile-step
-        const double cost = (double)waves * (c == 1 ? 1.0 : 1.02);             // ~2 % for the neighbour handshakes
+        // measured on B200 (scripts/time_cluster_windows.py, profiles/r2_cluster_windows.md): at equal tile count a
+        // clustered step is ~7 % slower (lock-step of the pieces, remote reads), so clusters must save more than that
+        const double cost = (double)waves * (c == 1 ? 1.0 : 1.07);
         if (best == 0.0 || cost < best) {
             best = cost;
             best_c = c;

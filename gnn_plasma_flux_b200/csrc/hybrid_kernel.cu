@@ -19,8 +19,10 @@ static cudaError_t dispatch(const HybridArgs& a, int fast_radius, int grid, cuda
     }
 }
 
-template <int R, bool kSave>
+template <int R>
 cudaError_t max_clusters_one(int csize, int* out);
+template <int R>
+cudaError_t launch_one_cluster(const HybridArgs& a, int grid, cudaStream_t stream);
 
 // Clusters of `csize` CTAs the device runs concurrently (every radius instantiation has the same footprint); cached.
 int hybrid_max_active_clusters(int csize) {
@@ -28,7 +30,7 @@ int hybrid_max_active_clusters(int csize) {
     if (csize < 2 || csize > 8) return 0;
     if (cache[csize] == 0) {
         int n = 0;
-        if (max_clusters_one<1, false>(csize, &n) != cudaSuccess || n < 1) {
+        if (max_clusters_one<1>(csize, &n) != cudaSuccess || n < 1) {
             (void)cudaGetLastError();
             n = -1;
         }
@@ -38,6 +40,15 @@ int hybrid_max_active_clusters(int csize) {
 }
 
 cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, cudaStream_t stream) {
+    if (a.cluster > 1) {
+        switch (fast_radius) {
+            case 1: return launch_one_cluster<1>(a, grid, stream);
+            case 2: return launch_one_cluster<2>(a, grid, stream);
+            case 3: return launch_one_cluster<3>(a, grid, stream);
+            case 4: return launch_one_cluster<4>(a, grid, stream);
+            default: return cudaErrorInvalidValue;          // api.cu only clusters compile-time radii
+        }
+    }
     return a.acts != nullptr ? dispatch<true>(a, fast_radius, grid, stream) : dispatch<false>(a, fast_radius, grid, stream);
 }
 

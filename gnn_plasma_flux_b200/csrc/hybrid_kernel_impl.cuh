@@ -225,7 +225,9 @@ __device__ __forceinline__ void save_rows(const float* buf, float* dst, const Ti
 // R = 0   : any radius / any nx, neighbours found by walking prev/next tables.
 // kSave: training forward -- also store h^0..h^L, P + b1 and Q row-major for the backward pass.
 // A separate instantiation so that the inference kernel carries none of that code.
-template <int R, bool kSave>
+// kCluster: window / slab tiles whose CTAs form clusters that share one window (HybridArgs::cluster > 1); a separate
+// instantiation so that the ordinary kernel carries none of the remote addressing or handshakes.
+template <int R, bool kSave, bool kCluster = false>
 __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
@@ -242,10 +244,10 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
         mbar_fence_init();
     }
     // cluster mode: this CTA is piece `crank` of a window of `csize` pieces; neighbours exist inside the window only
-    const int csize = a.cluster > 1 ? a.cluster : 1;
-    const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
-    const bool hasL = crank > 0, hasR = crank < csize - 1;
-    if (csize > 1 && tid == 0) {
+    const int csize = kCluster ? a.cluster : 1;
+    const int crank = kCluster ? (int)cluster_ctarank() : 0;
+    const bool hasL = kCluster && crank > 0, hasR = kCluster && crank < csize - 1;
+    if (kCluster && tid == 0) {
         mbar_init(&S.zready, (hasL ? 1 : 0) + (hasR ? 1 : 0));
         mbar_init(&S.zfree, (hasL ? 1 : 0) + (hasR ? 1 : 0));
         mbar_fence_init();
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
     if (a.whole_ic && a.do_update)
         for (int i = tid; i < nx; i += kThreads) S.gtab[i] = a.gtab[i];
     __syncthreads();
-    if (csize > 1) cluster_sync_all();               // nobody signals a barrier that is not initialised yet
+    if (kCluster) cluster_sync_all();                // nobody signals a barrier that is not initialised yet
 
     const int first_tile = (int)blockIdx.x / csize, tile_stride = (int)gridDim.x / csize;
     const int my_tiles = (a.num_tiles - first_tile + tile_stride - 1) / tile_stride;
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
     uint32_t zl = 0, zr_remote = 0, sig_l = 0, sig_r = 0, free_l = 0, free_r = 0;
     uint32_t zready_parity = 0, zfree_parity = 0;
     bool z_pending = false;                          // a Z generation of this CTA may still be read by a neighbour
-    if (csize > 1) {
+    if constexpr (kCluster) {
         if (hasL) {
             if (ty == 0) { zl = cluster_map(smem_u32(S.Zs), crank - 1); cl = 30; }
             sig_l = cluster_map(smem_u32(&S.zready), crank - 1);
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                     }
                     gemm_pass(acc, S, pipe, xo, tx, lane, leads_skew);
                     if (pass == 0) {
-                        if (csize > 1 && z_pending) {        // the neighbours have read the previous layer's edge rows
+                        if (kCluster && z_pending) {         // the neighbours have read the previous layer's edge rows
                             mbar_wait_cluster(&S.zfree, zfree_parity);
                             zfree_parity ^= 1;
                         }
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         // cluster mode: the left neighbour reads rows 4..7 (written by warps 0 and 1), the right one rows
                         // 120..123 (warps 6 and 7).  Tell them as soon as those rows are stored: the signal then travels
                         // under the whole second GEMM pass instead of being waited for.
-                        if (csize > 1) {
+                        if constexpr (kCluster) {
                             if (warp < 2) {
                                 named_sync(3, 64);
                                 if (tid == 0 && hasL) mbar_arrive_remote(sig_l);
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                     }
                 }
                 named_sync(bar, gthreads);      // Z complete; nobody reads Hs any more
-                if (csize > 1) {                // the neighbours' edge rows of Z (signalled one GEMM pass ago)
+                if constexpr (kCluster) {       // the neighbours' edge rows of Z (signalled one GEMM pass ago)
                     mbar_wait_cluster(&S.zready, zready_parity);
                     zready_parity ^= 1;
                     z_pending = true;
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         float h[8];
                         if (R > 0) {
                             float v[16];
-                            load_window(v, zr, sw, cl, c0, c1, cr, zl, zr_remote, n);
+                            load_window(v, zr, sw, cl, c0, c1, cr, kCluster ? zl : 0u, kCluster ? zr_remote : 0u, n);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int c = 4 + i;
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         *reinterpret_cast<float4*>(hr + ((c1 ^ sw) << 2)) = make_float4(h[4], h[5], h[6], h[7]);
                     }
                     named_sync(bar, gthreads);  // h' complete; Z free
-                    if (csize > 1 && tid == 0) {
+                    if (kCluster && tid == 0) {
                         if (hasL) mbar_arrive_remote(free_l);
                         if (hasR) mbar_arrive_remote(free_r);
                     }
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                                 const float* zr = S.Zs + n * kTileRows;
                                 if (R > 0) {
                                     float v[16];
-                                    load_window(v, zr, sw, cl, c0, c1, cr, zl, zr_remote, n);
+                                    load_window(v, zr, sw, cl, c0, c1, cr, kCluster ? zl : 0u, kCluster ? zr_remote : 0u, n);
 #pragma unroll
                                     for (int i = 0; i < 8; ++i) {
                                         pf[i] = fmaf(w2, fmaxf(acc[i][j] + v[4 + i + hop], 0.f), pf[i]);
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
                         }
                     }
                     named_sync(bar, gthreads);
-                    if (csize > 1 && tid == 0) {
+                    if (kCluster && tid == 0) {
                         if (hasL) mbar_arrive_remote(free_l);
                         if (hasR) mbar_arrive_remote(free_r);
                     }
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
         }   // steps
         named_sync(bar, gthreads);   // state arrays are rewritten by the next tile's load
     }       // tiles
-    if (csize > 1 && z_pending) mbar_wait_cluster(&S.zfree, zfree_parity);   // shared memory must outlive the neighbours' reads
+    if (kCluster && z_pending) mbar_wait_cluster(&S.zfree, zfree_parity);   // shared memory must outlive the neighbours' reads
 #ifdef FLUXGNN_FFMA_TIMING
     if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
         printf("[ffma timing] warp %d (group %d): total %lld clk, in GEMM passes %lld, of which waiting for weights %lld\n",
@@ -590,33 +592,39 @@ __global__ void __launch_bounds__(kThreads, 1) hybrid_tile_kernel(const HybridAr
 template <int R, bool kSave>
 cudaError_t launch_one(const HybridArgs& a, int grid, cudaStream_t stream) {
     // per device and per function; cheap and idempotent, so set it on every launch
-    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, kSave, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(TileSmem));
     if (e != cudaSuccess) return e;
-    if (a.cluster > 1) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = sizeof(TileSmem);
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)a.cluster;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, hybrid_tile_kernel<R, kSave>, a);
-    }
-    hybrid_tile_kernel<R, kSave><<<grid, kThreads, sizeof(TileSmem), stream>>>(a);
+    hybrid_tile_kernel<R, kSave, false><<<grid, kThreads, sizeof(TileSmem), stream>>>(a);
     return cudaGetLastError();
+}
+
+// the cluster instantiation (inference, compile-time radius): grid = clusters x a.cluster CTAs
+template <int R>
+cudaError_t launch_one_cluster(const HybridArgs& a, int grid, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(TileSmem));
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = sizeof(TileSmem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, hybrid_tile_kernel<R, false, true>, a);
 }
 
 // How many clusters of `csize` CTAs of this kernel the device holds at once (one CTA per SM by shared memory; clusters
 // must sit inside a GPC, so this can be less than #SMs / csize).
-template <int R, bool kSave>
+template <int R>
 cudaError_t max_clusters_one(int csize, int* out) {
-    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(hybrid_tile_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(TileSmem));
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -630,7 +638,7 @@ cudaError_t max_clusters_one(int csize, int* out) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(out, hybrid_tile_kernel<R, kSave>, &cfg);
+    return cudaOccupancyMaxActiveClusters(out, hybrid_tile_kernel<R, false, true>, &cfg);
 }
 
 }  // namespace fluxgnn

@@ -3,5 +3,4 @@
 
 namespace fluxgnn {
 template cudaError_t launch_one<1, false>(const HybridArgs&, int, cudaStream_t);
-template cudaError_t max_clusters_one<1, false>(int, int*);
 }
