@@ -86,6 +86,10 @@ SIGNATURES = {
     "fluxgnn_pure_gnn_rollout": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fluxgnn_pure_gnn_delta": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "fluxgnn_dense_layer": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    "fluxgnn_baseline_scan_supported": (c_int, [c_int, c_int]),
+    "fluxgnn_baseline_scan_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_baseline_rollout_scan": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float, c_float,
+                                              c_int, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "fluxgnn_baseline_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float,
                                          c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -46,7 +46,19 @@ def _hand_back(t: torch.Tensor, kind: str, lead: int = 0):
 class BaselineSolver:
     """1D fluid-Poisson model with viscosity (upwind fluxes, forward Euler, spectral field solve)."""
 
-    def __init__(self, nx=64, length=2 * math.pi, dt=5e-3, t_end=1.0, nu=1e-3, *, device="cuda"):
+    FIELD_SOLVES = ("auto", "spectral", "scan")
+
+    def __init__(self, nx=64, length=2 * math.pi, dt=5e-3, t_end=1.0, nu=1e-3, *, device="cuda",
+                 field_solve="auto", cert_tol=1e-5):
+        """`field_solve` (keyword-only, not in the reference): how E = Re ifft(i fft(n-1)/k) is evaluated on long grids.
+        "spectral": the FFT kernels, always.  "scan": the certified prefix-sum solve (csrc/scan_poisson.cu; grids of
+        at least 4096 cells, nx % 8 == 0), raising if a field's deviation bound exceeds cert_tol * max|E|.  "auto"
+        (default): the scan solve where it applies, repeated with the FFT solve whenever a certificate fails, so the
+        result is always within cert_tol * max|E| of the spectral operator; `last_field_solve` tells which one ran."""
+        if field_solve not in self.FIELD_SOLVES:
+            raise ValueError(f"field_solve must be one of {self.FIELD_SOLVES}, got {field_solve!r}")
+        self.field_solve, self.cert_tol = field_solve, float(cert_tol)
+        self.last_field_solve, self.last_uncertified_step = None, None
         self.grid = PeriodicGrid(nx, length)
         self.nx, self.length, self.dx = self.grid.nx, self.grid.length, self.grid.dx
         self.dt, self.t_end, self.nu = dt, t_end, nu
@@ -116,15 +128,20 @@ class BaselineSolver:
         return (np.roll(u, -1) - 2 * u + np.roll(u, 1)) / (self.dx ** 2)
 
     # ------------------------------------------------------------------ stepping
-    def rollout(self, state: torch.Tensor, n_steps: int, record_every: int = 0, record_flux: bool = False):
+    def rollout(self, state: torch.Tensor, n_steps: int, record_every: int = 0, record_flux: bool = False,
+                field_solve: str | None = None):
         """Device-resident rollout of state [B,3,nx] (CUDA float32).
-        Returns (final [B,3,nx], traj [n_steps//record_every, B,3,nx] | None, flux_n [n_steps,B,nx] | None)."""
+        Returns (final [B,3,nx], traj [n_steps//record_every, B,3,nx] | None, flux_n [n_steps,B,nx] | None).
+        `field_solve` overrides the constructor's choice for this call."""
         if not torch.is_tensor(state) or state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != self.nx:
             raise ValueError(f"state must be a tensor [B,3,{self.nx}], got {tuple(getattr(state, 'shape', ()))}")
         dev = self.device
         if dev.type != "cuda":
             raise _lib.FluxGNNError(f"BaselineSolver(device={dev}): the step runs in libfluxgnn.so on a CUDA device "
                                     "(there is no CPU fallback)")
+        mode = self.field_solve if field_solve is None else field_solve
+        if mode not in self.FIELD_SOLVES:
+            raise ValueError(f"field_solve must be one of {self.FIELD_SOLVES}, got {mode!r}")
         state = state.to(device=dev, dtype=torch.float32).contiguous()
         B, _, nx = state.shape
         if n_steps < 0:
@@ -132,21 +149,43 @@ class BaselineSolver:
         if n_steps == 0:                      # the reference's loops simply do not run (src/baseline_solver.py:106-116)
             return (state.clone(), state.new_empty((0, B, 3, nx)) if record_every else None,
                     state.new_empty((0, B, nx)) if record_flux else None)
-        _, gtab = self.grid.tables(dev)
+        L = _lib.lib()
+        scalars = (self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)))
         with torch.cuda.device(dev):
             out = torch.empty_like(state)
-            ws_bytes = _lib.lib().fluxgnn_baseline_workspace_bytes(B, nx)
-            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
             traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
                     if record_every else None)
             flux = torch.empty(n_steps, B, nx, dtype=torch.float32, device=dev) if record_flux else None
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.lib().fluxgnn_baseline_rollout(
+            scan_ok = bool(L.fluxgnn_baseline_scan_supported(B, nx))
+            if mode == "scan" and not scan_ok:
+                raise _lib.FluxGNNError(f"field_solve='scan' needs nx >= 4096 and nx % 8 == 0 (B={B}, nx={nx})")
+            if mode != "spectral" and scan_ok:
+                work = torch.empty(L.fluxgnn_baseline_scan_workspace_bytes(B, nx) // 4, dtype=torch.float32, device=dev)
+                flag = torch.empty(1, dtype=torch.int32, device=dev)
+                _lib.check(L.fluxgnn_baseline_rollout_scan(
+                    state.data_ptr(), out.data_ptr(), B, nx, self.length, *scalars, n_steps, max(record_every, 1),
+                    traj.data_ptr() if traj is not None else None, flux.data_ptr() if flux is not None else None,
+                    self.cert_tol, work.data_ptr(), flag.data_ptr(), stream), "fluxgnn_baseline_rollout_scan")
+                first_bad = int(flag.item())          # 4-byte read-back: was every reconstructed field certified?
+                self.last_uncertified_step = None if first_bad == 2 ** 31 - 1 else first_bad
+                if self.last_uncertified_step is None:
+                    self.last_field_solve = "scan"
+                    return out, traj, flux
+                if mode == "scan":
+                    raise _lib.FluxGNNError(
+                        f"field_solve='scan': the field of step {first_bad} is not certified to cert_tol={self.cert_tol:g} "
+                        "(rough density or short grid); use field_solve='auto' or 'spectral'")
+                del work                              # "auto": repeat with the FFT solve
+            _, gtab = self.grid.tables(dev)
+            ws_bytes = L.fluxgnn_baseline_workspace_bytes(B, nx)
+            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+            _lib.check(L.fluxgnn_baseline_rollout(
                 state.data_ptr(), out.data_ptr(), gtab.data_ptr() if gtab is not None else None, B, nx, self.length,
-                self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)),
-                n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
+                *scalars, n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
                 flux.data_ptr() if flux is not None else None,
                 work.data_ptr() if work is not None else None, stream), "fluxgnn_baseline_rollout")
+            self.last_field_solve = "spectral"
         return out, traj, flux
 
     def step(self, state, return_flux=False):

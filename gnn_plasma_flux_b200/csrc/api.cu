@@ -731,4 +731,33 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const doub
     return FLUXGNN_OK;
 }
 
+int fluxgnn_baseline_scan_supported(int B, int nx) { return baseline_scan_supported(B, nx) ? 1 : 0; }
+
+size_t fluxgnn_baseline_scan_workspace_bytes(int B, int nx) {
+    int sms = 0;
+    if (!baseline_scan_supported(B, nx) || sm_count(&sms) != FLUXGNN_OK) return 0;
+    return baseline_scan_workspace_bytes(B, nx, sms);
+}
+
+int fluxgnn_baseline_rollout_scan(const float* state_in, float* state_out, int B, int nx, double length, float c, float dt,
+                                  float nu, float dx2, int steps, int record_every, float* traj, float* flux_n,
+                                  double cert_tol, void* workspace, int* first_uncertified, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!state_in || !state_out || !workspace || !first_uncertified || !(length > 0.0) || !(cert_tol > 0.0))
+        return set_error(FLUXGNN_EINVAL, "baseline_rollout_scan: bad argument");
+    if (state_in == state_out) return set_error(FLUXGNN_EINVAL, "baseline_rollout_scan: state_in and state_out alias");
+    if (steps < 1) return set_error(FLUXGNN_EINVAL, "baseline_rollout_scan: steps must be >= 1, got %d", steps);
+    if (traj && record_every < 1) return set_error(FLUXGNN_EINVAL, "baseline_rollout_scan: record_every must be >= 1");
+    if (!baseline_scan_supported(B, nx))
+        return set_error(FLUXGNN_EUNSUP, "baseline_rollout_scan: needs nx >= 4096 and nx %% 8 == 0 (B=%d nx=%d)", B, nx);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    int launches = 0;
+    FLUXGNN_CUDA_OK(launch_baseline_rollout_scan(state_in, state_out, B, nx, length, c, dt, nu, dx2, steps, record_every, traj,
+                                                 flux_n, cert_tol, workspace, first_uncertified, sms, stream, &launches));
+    count_launch(launches);
+    return FLUXGNN_OK;
+}
+
 }  // extern "C"

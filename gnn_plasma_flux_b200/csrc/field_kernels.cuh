@@ -40,19 +40,27 @@ __device__ __forceinline__ FvOut fv_cell(float nm, float n0, float um, float u0,
     return o;
 }
 
-// The same update for the two cells of a float2 (cells i, i+1) in packed fp32x2 arithmetic: every operation is the
-// per-component round-to-nearest operation of fv_cell, in the same order, so the results are bit-identical.
+// The same update for the two cells of a float2 (cells i, i+1), packed fp32x2 where that is safe: every operation is
+// the per-component round-to-nearest operation of fv_cell, in the same order, so the results are bit-identical.
+// Wherever a PRODUCT feeds a SUM the sum is written as two scalar operations: ptxas (12.9) contracts mul.rn.f32x2 +
+// add.rn.f32x2 into one FFMA2 -- which it never does for scalar .rn operations -- and that would skip the rounding of
+// the product (measured: n' and u' off by an ulp whenever the flux difference is not below rounding; -fmad=false does
+// not prevent it).  The one packed product-into-sum left, up - 2u, is exact either way because 2u is exact.
 //   nl, ul: n and u of cell i-1;  ur: u of cell i+2;  r = fv_reciprocal(dx2) must be non-zero.
 __device__ __forceinline__ float2 fv_neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ void fv_pair(float nl, float2 n2, float ul, float2 u2, float ur, float2 e2, float c, float dt,
                                         float nu, float dx2, float r, float2& n_new, float2& u_new) {
-    const float2 nm = make_float2(nl, n2.x), um = make_float2(ul, u2.x), up = make_float2(u2.y, ur);
+    const float2 um = make_float2(ul, u2.x), up = make_float2(u2.y, ur);
     const float2 c2 = make_float2(c, c), half2 = make_float2(0.5f, 0.5f), two2 = make_float2(2.0f, 2.0f);
-    const float2 fn = __fmul2_rn(n2, u2), fnm = __fmul2_rn(nm, um);
-    n_new = __fadd2_rn(n2, fv_neg2(__fmul2_rn(c2, __fadd2_rn(fn, fv_neg2(fnm)))));
-    const float2 fu = __fmul2_rn(__fmul2_rn(half2, u2), u2), fum = __fmul2_rn(__fmul2_rn(half2, um), um);
-    const float2 u_adv = __fadd2_rn(u2, fv_neg2(__fmul2_rn(c2, __fadd2_rn(fu, fv_neg2(fum)))));
-    const float2 x = __fadd2_rn(__fadd2_rn(up, fv_neg2(__fmul2_rn(two2, u2))), um);
+    const float2 fn = __fmul2_rn(n2, u2);                                             // :70-71
+    const float fnl = __fmul_rn(nl, ul);
+    const float2 tn = __fmul2_rn(c2, make_float2(__fsub_rn(fn.x, fnl), __fsub_rn(fn.y, fn.x)));
+    n_new = make_float2(__fsub_rn(n2.x, tn.x), __fsub_rn(n2.y, tn.y));               // :85-86
+    const float2 fu = __fmul2_rn(__fmul2_rn(half2, u2), u2);                          // :73-74
+    const float ful = __fmul_rn(__fmul_rn(0.5f, ul), ul);
+    const float2 tu = __fmul2_rn(c2, make_float2(__fsub_rn(fu.x, ful), __fsub_rn(fu.y, fu.x)));
+    const float2 u_adv = make_float2(__fsub_rn(u2.x, tu.x), __fsub_rn(u2.y, tu.y));   // :90-91
+    const float2 x = __fadd2_rn(__fadd2_rn(up, fv_neg2(__fmul2_rn(two2, u2))), um);   // :76-78
     const float2 r2 = make_float2(r, r), b2 = make_float2(dx2, dx2);
     const float2 q0 = __fmul2_rn(x, r2);
     const float2 e = __ffma2_rn(fv_neg2(q0), b2, x);
@@ -60,7 +68,9 @@ __device__ __forceinline__ void fv_pair(float nl, float2 n2, float ul, float2 u2
     const float inf = __int_as_float(0x7f800000);
     lap.x = (x.x == 0.f || !(fabsf(q0.x) < inf)) ? q0.x : lap.x;
     lap.y = (x.y == 0.f || !(fabsf(q0.y) < inf)) ? q0.y : lap.y;
-    u_new = __fadd2_rn(u_adv, __fmul2_rn(make_float2(dt, dt), __fadd2_rn(e2, __fmul2_rn(make_float2(nu, nu), lap))));
+    const float2 v = __fmul2_rn(make_float2(nu, nu), lap);
+    const float2 z = __fmul2_rn(make_float2(dt, dt), make_float2(__fadd_rn(e2.x, v.x), __fadd_rn(e2.y, v.y)));
+    u_new = make_float2(__fadd_rn(u_adv.x, z.x), __fadd_rn(u_adv.y, z.y));           // :94
 }
 
 __global__ void poisson_table_kernel(int nx, double length, double* gtab);
@@ -120,5 +130,13 @@ int launch_poisson_dist_pack(const float* n, long long ic_stride, int B, int S, 
 int launch_poisson_rank_dft(const float2* in, float2* out, int G, long long chunk, long long flat0, int S, int inverse,
                             cudaStream_t stream);
 int launch_poisson_dist_local(float2* y, float2* scratch, int P, int S, int G, int kr, double length, cudaStream_t stream);
+
+// scan_poisson.cu: classical rollout with the field reconstructed by a prefix sum and certified against the spectral
+// operator (long grids, nx >= 4096, nx % 8 == 0); the state between steps is (n, u) only
+bool baseline_scan_supported(int B, int nx);
+size_t baseline_scan_workspace_bytes(int B, int nx, int sms);
+cudaError_t launch_baseline_rollout_scan(const float* state_in, float* state_out, int B, int nx, double length, float c, float dt,
+                                         float nu, float dx2, int steps, int record_every, float* traj, float* flux_n,
+                                         double tol, void* workspace, int* flag, int sms, cudaStream_t stream, int* launches);
 
 }  // namespace fluxgnn

@@ -1,0 +1,455 @@
+// Classical step with the field solve as a parallel prefix sum ("scan solve"), sm_100a.
+//
+//   src/baseline_solver.py:80-94   upwind fluxes, viscous Laplacian, forward Euler   (fv_cell, bit-exact)
+//   src/baseline_solver.py:59-68   E = Re ifft(i fft(n - 1) / k)                       (reconstructed, see below)
+//
+// The spectral operator is the zero-mean periodic antiderivative  dE/dx = -(rho - mean rho),  rho = n - 1.  On a
+// long grid it can be evaluated without a transform: with the inclusive prefix C_j = sum_{i<=j} rho_i,
+//   E_j = -dx (C_j - rho_j/2 - (j + 1/2) mean(rho) - mu) + (dx/24)(rho_{j+1} - rho_{j-1}),
+//   mu  = S/2 - M1/N - S/(2N),   S = sum rho_i,   M1 = sum i rho_i        (makes mean(E) = 0),
+// is the trapezoid rule between cell centres plus the first Euler-Maclaurin correction.  Per Fourier mode its
+// multiplier differs from i/k by the factor  1 - r - kappa sin(kappa)/12,  r = (kappa/2) cot(kappa/2),  kappa = k dx,
+// which is bounded by (1/16) (2 sin(kappa/2))^4 on (0, pi]: the deviation from the spectral field is therefore at most
+//   || E_scan - E_spectral ||_inf  <=  rms(Delta^4 rho) * L / (32 sqrt 3)                (Cauchy-Schwarz over the modes)
+// and the kernel EVALUATES that bound for every field it reconstructs (certificate).  A field whose bound exceeds
+// tol * max|E| is reported through `flag` (first uncertified step); the host mirror then repeats the rollout with the
+// FFT solve.  Smooth states on long grids pass with a margin set by fp32 rounding noise (bound ~3e-8 absolute);
+// white noise or short grids do not, and never silently use this path.
+//
+// Because E is a function of n alone, the rollout keeps only (n, u) in HBM between steps: step s+1 reconstructs the field
+// of its input from n and the per-segment sums the previous launch left behind, so a step moves 16 bytes per cell
+// (read n, u; write n', u') instead of 24 + the transform passes.  Every grid is cut into contiguous segments, one
+// persistent CTA each; a CTA streams its segment in 4096-cell chunks through a 3-stage shared-memory ring filled by 1-D
+// bulk copies (TMA, SASS UBLKCP) and carries the running prefix in a register.  No inter-CTA dependency inside a
+// launch: segment prefixes come from the records of the previous launch.
+#include <climits>
+#include <cstring>
+
+#include "common.cuh"
+#include "field_kernels.cuh"
+
+namespace fluxgnn {
+
+namespace {
+
+constexpr int kScanThreads = 512;
+constexpr int kScanPer = 8;                                  // consecutive cells per thread
+constexpr int kScanChunk = kScanThreads * kScanPer;          // 4096 cells
+constexpr int kScanStages = 3;
+constexpr int kScanHalo = 4;                                 // staged halo cells per side (16 bytes)
+constexpr int kScanRow = kScanChunk + 2 * kScanHalo;         // floats per staged array
+
+struct ScanRec {             // what one segment's CTA leaves for the next launch
+    double S;                // sum of rho' over the segment (new state)
+    double M1;               // sum of j * rho'_j, j = cell index inside the IC
+    double D4;               // sum of (Delta^4 rho)^2 of the INPUT state (certificate of the field reconstructed here)
+    float maxE;              // max |E| of the field reconstructed here
+    int pad;
+};
+static_assert(sizeof(ScanRec) == 32, "record layout");
+
+struct ScanArgs {
+    const float* in;         // [B][3][nx]
+    float* out;              // [B][3][nx]: n', u' planes written (modes 0, 1)
+    float* e_out;            // [B][3][nx]-strided base of a state whose E plane receives the input state's field (modes 1, 2)
+    float* flux_out;         // [B][nx] continuity flux n*u of the input state, or null
+    const ScanRec* rec_in;   // [B][segs] from the previous launch (modes 1, 2)
+    ScanRec* rec_out;        // [B][segs]
+    int* flag;               // first uncertified step (INT_MAX = all certified)
+    int step;                // index of the step whose input field the records in rec_in certify
+    int B, nx, segs, seg_chunks;
+    float c, dt, nu, dx2;
+    double dx, length, tol;
+};
+
+struct ScanSmem {
+    float nbuf[kScanStages][kScanRow];
+    float ubuf[kScanStages][kScanRow];
+    float wsum[2][kScanThreads / 32];
+    double red[4][kScanThreads / 32];
+    float redf[kScanThreads / 32];
+    double bc[4];            // broadcast: P_seg, rbar, mu, (unused)
+    uint64_t full[kScanStages];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// MODE 0: first step of a rollout -- E is read from the input state, no reconstruction, no certificate.
+// MODE 1: later steps            -- E reconstructed from n and rec_in; optionally stored to e_out (recorded states).
+// MODE 2: materialise            -- E of the input state reconstructed and stored to e_out; no update.
+// kPacked: the finite-volume update in packed fp32x2 arithmetic (fv_pair; needs fv_reciprocal(dx2) != 0), bit-identical
+// to the scalar form.
+template <int MODE, bool kPacked>
+__global__ void __launch_bounds__(kScanThreads, 2) baseline_scan_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ic = (int)blockIdx.x / a.segs, seg = (int)blockIdx.x - ic * a.segs;
+    const int nx = a.nx;
+    const long long seg_begin = (long long)seg * a.seg_chunks * kScanChunk;
+    long long seg_end = seg_begin + (long long)a.seg_chunks * kScanChunk;
+    if (seg_end > nx) seg_end = nx;
+    const int nchunks = (int)((seg_end - seg_begin + kScanChunk - 1) / kScanChunk);
+    const float* pn = a.in + (size_t)ic * 3 * nx;
+    const float* pu = pn + nx;
+    const float* pe = pu + nx;
+
+    if (tid == 0) {
+        for (int s = 0; s < kScanStages; ++s) mbar_init(&S.full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer (thread 0): stage chunk k = cells [c0, c0 + len) plus 4 halo cells per side, periodic wrap applied here
+    auto issue = [&](int k) {
+        const int st = k % kScanStages;
+        const long long c0 = seg_begin + (long long)k * kScanChunk;
+        const int len = (int)((seg_end - c0 < kScanChunk) ? (seg_end - c0) : kScanChunk);
+        const long long left = (c0 == 0) ? nx - kScanHalo : c0 - kScanHalo;
+        const long long right = (c0 + len == nx) ? 0 : c0 + len;
+        const uint32_t bytes = (uint32_t)(len + 2 * kScanHalo) * 4u;
+        mbar_arrive_expect_tx(&S.full[st], (MODE == 2) ? bytes : 2 * bytes);
+        bulk_g2s(&S.nbuf[st][0], pn + left, kScanHalo * 4, &S.full[st]);
+        bulk_g2s(&S.nbuf[st][kScanHalo], pn + c0, (uint32_t)len * 4u, &S.full[st]);
+        bulk_g2s(&S.nbuf[st][kScanHalo + len], pn + right, kScanHalo * 4, &S.full[st]);
+        if (MODE != 2) {
+            bulk_g2s(&S.ubuf[st][0], pu + left, kScanHalo * 4, &S.full[st]);
+            bulk_g2s(&S.ubuf[st][kScanHalo], pu + c0, (uint32_t)len * 4u, &S.full[st]);
+            bulk_g2s(&S.ubuf[st][kScanHalo + len], pu + right, kScanHalo * 4, &S.full[st]);
+        }
+    };
+    if (tid == 0)
+        for (int k = 0; k < kScanStages && k < nchunks; ++k) issue(k);
+
+    // ---- prologue: sums of the previous launch's records -> segment prefix, mean, zero-mean constant, certificate ----
+    double P = 0.0, rbar = 0.0, mu = 0.0;
+    if (MODE != 0) {
+        double s_all = 0.0, s_before = 0.0, m_all = 0.0, d_all = 0.0;
+        float e_max = 0.f;
+        const ScanRec* rec = a.rec_in + (size_t)ic * a.segs;
+        for (int r = tid; r < a.segs; r += kScanThreads) {
+            const ScanRec v = rec[r];
+            s_all += v.S;
+            if (r < seg) s_before += v.S;
+            m_all += v.M1;
+            d_all += v.D4;
+            e_max = fmaxf(e_max, v.maxE);
+        }
+        s_all = warp_sum(s_all); s_before = warp_sum(s_before); m_all = warp_sum(m_all); d_all = warp_sum(d_all);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e_max = fmaxf(e_max, __shfl_xor_sync(0xffffffffu, e_max, o));
+        if (lane == 0) {
+            S.red[0][warp] = s_all; S.red[1][warp] = s_before; S.red[2][warp] = m_all; S.red[3][warp] = d_all;
+            S.redf[warp] = e_max;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double sa = 0.0, sb = 0.0, ma = 0.0, da = 0.0;
+            float em = 0.f;
+            for (int w = 0; w < kScanThreads / 32; ++w) {
+                sa += S.red[0][w]; sb += S.red[1][w]; ma += S.red[2][w]; da += S.red[3][w];
+                em = fmaxf(em, S.redf[w]);
+            }
+            const double N = (double)nx;
+            S.bc[0] = sb;
+            S.bc[1] = sa / N;
+            S.bc[2] = 0.5 * sa - ma / N - sa / (2.0 * N);
+            // certificate of the field the PREVIOUS launch reconstructed (its records carry D4 and max|E|)
+            if (seg == 0 && a.step > 0) {
+                const double bound = sqrt(da / N) * a.length * (1.0 / (32.0 * 1.7320508075688772));
+                if (!(bound <= a.tol * (double)em)) atomicMin(a.flag, a.step - 1);
+            }
+        }
+        __syncthreads();
+        P = S.bc[0]; rbar = S.bc[1]; mu = S.bc[2];
+    }
+
+    const float rdx2 = fv_reciprocal(a.dx2);
+    const float dxf = (float)a.dx, dx24 = (float)(a.dx / 24.0), rbarf = (float)rbar;
+    double run = P;                      // prefix of rho over the cells of this IC before the current chunk
+    double accS = 0.0, accM = 0.0;
+    float accD = 0.f, accE = 0.f;
+
+    for (int k = 0; k < nchunks; ++k) {
+        const int st = k % kScanStages;
+        const long long c0 = seg_begin + (long long)k * kScanChunk;
+        const int len = (int)((seg_end - c0 < kScanChunk) ? (seg_end - c0) : kScanChunk);
+        const bool active = tid * kScanPer < len;
+        mbar_wait(&S.full[st], (uint32_t)((k / kScanStages) & 1));
+
+        float nv[kScanPer + 4], uv[kScanPer + 2];      // cells -2..9 of n, -1..8 of u relative to the thread's first cell
+        if (active) {
+            const float* sn = &S.nbuf[st][kScanHalo + tid * kScanPer];
+            const float4 n0 = *reinterpret_cast<const float4*>(sn), n1 = *reinterpret_cast<const float4*>(sn + 4);
+            const float2 nl = *reinterpret_cast<const float2*>(sn - 2), nr = *reinterpret_cast<const float2*>(sn + 8);
+            nv[0] = nl.x; nv[1] = nl.y;
+            nv[2] = n0.x; nv[3] = n0.y; nv[4] = n0.z; nv[5] = n0.w;
+            nv[6] = n1.x; nv[7] = n1.y; nv[8] = n1.z; nv[9] = n1.w;
+            nv[10] = nr.x; nv[11] = nr.y;
+            if (MODE != 2) {
+                const float* su = &S.ubuf[st][kScanHalo + tid * kScanPer];
+                const float4 u0 = *reinterpret_cast<const float4*>(su), u1 = *reinterpret_cast<const float4*>(su + 4);
+                uv[0] = su[-1];
+                uv[1] = u0.x; uv[2] = u0.y; uv[3] = u0.z; uv[4] = u0.w;
+                uv[5] = u1.x; uv[6] = u1.y; uv[7] = u1.z; uv[8] = u1.w;
+                uv[9] = su[8];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kScanPer + 4; ++i) nv[i] = 1.0f;
+#pragma unroll
+            for (int i = 0; i < kScanPer + 2; ++i) uv[i] = 0.f;
+        }
+
+        float rho[kScanPer + 4];
+#pragma unroll
+        for (int i = 0; i < kScanPer + 4; ++i) rho[i] = __fsub_rn(nv[i], 1.0f);      // :60, float32 like numpy
+
+        // ---- block-wide exclusive prefix of rho: fp32 inside a warp (at most 256 cells), fp64 across warps and chunks ----
+        float loc[kScanPer];
+        float excl32 = 0.f;
+        if (MODE != 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < kScanPer; ++i) { t += rho[2 + i]; loc[i] = t; }      // inactive threads hold rho = 0
+            float incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) S.wsum[k & 1][warp] = incl;
+            excl32 = incl - t;
+        }
+        __syncthreads();                 // warp totals visible; every thread has copied its cells out of stage `st`
+        if (tid == 0 && k + kScanStages < nchunks) issue(k + kScanStages);
+        double base = 0.0;
+        if (MODE != 0) {
+            // every warp scans the 16 warp totals itself (lanes 0..15, fp64): no second block barrier
+            double w = (lane < kScanThreads / 32) ? (double)S.wsum[k & 1][lane] : 0.0;
+#pragma unroll
+            for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            const double total = __shfl_sync(0xffffffffu, w, kScanThreads / 32 - 1);
+            const double before = __shfl_sync(0xffffffffu, w, (warp + 31) & 31);     // lane warp-1 (warp 0: unused)
+            base = run + (warp ? before : 0.0) + (double)excl32;
+            run += total;
+        }
+        if (!active) continue;
+
+        const long long j0 = c0 + (long long)tid * kScanPer;     // first cell of this thread inside the IC
+        float ev[kScanPer];
+        if (MODE == 0) {
+            const float4 e0 = *reinterpret_cast<const float4*>(pe + j0), e1 = *reinterpret_cast<const float4*>(pe + j0 + 4);
+            ev[0] = e0.x; ev[1] = e0.y; ev[2] = e0.z; ev[3] = e0.w;
+            ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
+        } else {
+            // E_j = -dx (C_j - rho_j/2 - (j + 1/2) rbar - mu) + (dx/24)(rho_{j+1} - rho_{j-1})
+            const float t0 = (float)(-a.dx * (base - ((double)j0 + 0.5) * rbar - mu));
+            float d4 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kScanPer; ++i) {
+                const float br = fmaf(-0.5f, rho[2 + i], loc[i]) - (float)i * rbarf;
+                ev[i] = fmaf(-dxf, br, t0) + dx24 * (rho[3 + i] - rho[1 + i]);
+                accE = fmaxf(accE, fabsf(ev[i]));
+                const float q = fmaf(6.0f, rho[2 + i], fmaf(-4.0f, rho[1 + i] + rho[3 + i], rho[i] + rho[4 + i]));
+                d4 = fmaf(q, q, d4);
+            }
+            accD += d4;
+            if (a.e_out != nullptr) {
+                float* po = a.e_out + (size_t)ic * 3 * nx + 2 * (size_t)nx + j0;
+                *reinterpret_cast<float4*>(po) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+                *reinterpret_cast<float4*>(po + 4) = make_float4(ev[4], ev[5], ev[6], ev[7]);
+            }
+        }
+        if (MODE == 2) continue;
+
+        // ---- finite-volume update (bit-exact numpy order, field_kernels.cuh) and the sums of the new state ----
+        float nn[kScanPer], un[kScanPer];
+        float s1, m1;
+        if (kPacked) {
+            float2 s2 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < kScanPer; i += 2) {
+                float2 n2, u2;
+                fv_pair(nv[1 + i], make_float2(nv[2 + i], nv[3 + i]), uv[i], make_float2(uv[1 + i], uv[2 + i]), uv[3 + i],
+                        make_float2(ev[i], ev[i + 1]), a.c, a.dt, a.nu, a.dx2, rdx2, n2, u2);
+                nn[i] = n2.x; nn[i + 1] = n2.y; un[i] = u2.x; un[i + 1] = u2.y;
+                const float2 r2 = __fadd2_rn(n2, make_float2(-1.0f, -1.0f));
+                s2 = __fadd2_rn(s2, r2);
+                m2 = __ffma2_rn(make_float2((float)i, (float)(i + 1)), r2, m2);
+            }
+            s1 = s2.x + s2.y; m1 = m2.x + m2.y;
+        } else {
+            s1 = 0.f; m1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kScanPer; ++i) {
+                const FvOut o = fv_cell(nv[1 + i], nv[2 + i], uv[i], uv[1 + i], uv[2 + i], ev[i], a.c, a.dt, a.nu, a.dx2, rdx2);
+                nn[i] = o.n; un[i] = o.u;
+                const float r = __fsub_rn(o.n, 1.0f);
+                s1 += r;
+                m1 = fmaf((float)i, r, m1);
+            }
+        }
+        accS += (double)s1;
+        accM = fma((double)j0, (double)s1, accM) + (double)m1;
+        float* po = a.out + (size_t)ic * 3 * nx + j0;
+        *reinterpret_cast<float4*>(po) = make_float4(nn[0], nn[1], nn[2], nn[3]);
+        *reinterpret_cast<float4*>(po + 4) = make_float4(nn[4], nn[5], nn[6], nn[7]);
+        *reinterpret_cast<float4*>(po + nx) = make_float4(un[0], un[1], un[2], un[3]);
+        *reinterpret_cast<float4*>(po + nx + 4) = make_float4(un[4], un[5], un[6], un[7]);
+        if (a.flux_out != nullptr) {                         // F_n = n u of the input state (:70-71, :84)
+            float* pf = a.flux_out + (size_t)ic * nx + j0;
+            *reinterpret_cast<float4*>(pf) = make_float4(__fmul_rn(nv[2], uv[1]), __fmul_rn(nv[3], uv[2]),
+                                                         __fmul_rn(nv[4], uv[3]), __fmul_rn(nv[5], uv[4]));
+            *reinterpret_cast<float4*>(pf + 4) = make_float4(__fmul_rn(nv[6], uv[5]), __fmul_rn(nv[7], uv[6]),
+                                                             __fmul_rn(nv[8], uv[7]), __fmul_rn(nv[9], uv[8]));
+        }
+    }
+
+    // ---- this segment's record ----
+    accS = warp_sum(accS); accM = warp_sum(accM);
+    double accD64 = warp_sum((double)accD);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accE = fmaxf(accE, __shfl_xor_sync(0xffffffffu, accE, o));
+    __syncthreads();                     // the prologue's use of S.red is over
+    if (lane == 0) { S.red[0][warp] = accS; S.red[1][warp] = accM; S.red[2][warp] = accD64; S.redf[warp] = accE; }
+    __syncthreads();
+    if (tid == 0) {
+        ScanRec r;
+        r.S = 0.0; r.M1 = 0.0; r.D4 = 0.0; r.maxE = 0.f; r.pad = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) {
+            r.S += S.red[0][w]; r.M1 += S.red[1][w]; r.D4 += S.red[2][w];
+            r.maxE = fmaxf(r.maxE, S.redf[w]);
+        }
+        if (MODE == 0) { r.D4 = 0.0; r.maxE = 1.0f; }
+        a.rec_out[(size_t)ic * a.segs + seg] = r;
+    }
+}
+
+// certificate of the last reconstructed field (the records of the materialise launch), and flag initialisation
+__global__ void baseline_scan_flag_kernel(const ScanRec* rec, int B, int segs, int nx, double length, double tol, int step,
+                                          int* flag, int init) {
+    if (init) { if (threadIdx.x == 0 && blockIdx.x == 0) *flag = INT_MAX; return; }
+    const int ic = blockIdx.x;
+    double d = 0.0;
+    float em = 0.f;
+    for (int r = threadIdx.x; r < segs; r += 32) {
+        d += rec[(size_t)ic * segs + r].D4;
+        em = fmaxf(em, rec[(size_t)ic * segs + r].maxE);
+    }
+    d = warp_sum(d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) em = fmaxf(em, __shfl_xor_sync(0xffffffffu, em, o));
+    if (threadIdx.x == 0) {
+        const double bound = sqrt(d / (double)nx) * length * (1.0 / (32.0 * 1.7320508075688772));
+        if (!(bound <= tol * (double)em)) atomicMin(flag, step);
+    }
+}
+
+// host mirror of fv_reciprocal()'s predicate: can dx2 be divided by through the Markstein sequence?
+bool fv_reciprocal_host(float b) {
+    unsigned bits;
+    memcpy(&bits, &b, sizeof bits);
+    return b > 0.f && b < 1.f && (bits & 0x7fffffu) != 0x7fffffu && (bits >> 23) != 0u;
+}
+
+void scan_geometry(int B, int nx, int sms, int* segs, int* seg_chunks) {
+    const int nchunks = (nx + kScanChunk - 1) / kScanChunk;
+    int target = (2 * sms) / B;
+    if (target < 1) target = 1;
+    if (target > nchunks) target = nchunks;
+    const int sc = (nchunks + target - 1) / target;
+    *seg_chunks = sc;
+    *segs = (nchunks + sc - 1) / sc;
+}
+
+}  // namespace
+
+bool baseline_scan_supported(int B, int nx) {
+    return nx >= kScanChunk && (nx % kScanPer) == 0 && B >= 1 && B <= 4096;
+}
+
+size_t baseline_scan_workspace_bytes(int B, int nx, int sms) {
+    int segs = 0, sc = 0;
+    scan_geometry(B, nx, sms, &segs, &sc);
+    return (size_t)B * 3 * nx * sizeof(float) + 2 * (size_t)B * segs * sizeof(ScanRec) + 256;
+}
+
+// T-step rollout; see fluxgnn_baseline_rollout_scan in include/fluxgnn.h.  Returns a CUDA error code (0 = ok) and the
+// number of kernels launched through *launches.
+cudaError_t launch_baseline_rollout_scan(const float* state_in, float* state_out, int B, int nx, double length, float c, float dt,
+                                         float nu, float dx2, int steps, int record_every, float* traj, float* flux_n,
+                                         double tol, void* workspace, int* flag, int sms, cudaStream_t stream, int* launches) {
+    int segs = 0, sc = 0;
+    scan_geometry(B, nx, sms, &segs, &sc);
+    const size_t state_floats = (size_t)B * 3 * nx;
+    float* tmp = (float*)workspace;
+    ScanRec* rec[2];
+    rec[0] = reinterpret_cast<ScanRec*>(reinterpret_cast<unsigned char*>(workspace) +
+                                        ((state_floats * sizeof(float) + 255) / 256) * 256);
+    rec[1] = rec[0] + (size_t)B * segs;
+    const size_t smem = sizeof(ScanSmem);
+    cudaError_t e;
+    const bool packed = fv_reciprocal_host(dx2);
+    auto k_first = packed ? baseline_scan_kernel<0, true> : baseline_scan_kernel<0, false>;
+    auto k_step = packed ? baseline_scan_kernel<1, true> : baseline_scan_kernel<1, false>;
+    auto k_final = baseline_scan_kernel<2, false>;
+    if ((e = cudaFuncSetAttribute(k_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    int nl = 0;
+    baseline_scan_flag_kernel<<<1, 32, 0, stream>>>(nullptr, B, segs, nx, length, tol, 0, flag, 1);
+    ++nl;
+    ScanArgs a;
+    a.B = B; a.nx = nx; a.segs = segs; a.seg_chunks = sc;
+    a.c = c; a.dt = dt; a.nu = nu; a.dx2 = dx2;
+    a.dx = length / (double)nx; a.length = length; a.tol = tol;
+    a.flag = flag;
+    const unsigned grid = (unsigned)(B * segs);
+    const float* src = state_in;
+    for (int t = 0; t < steps; ++t) {
+        const bool recorded = traj != nullptr && (t + 1) % record_every == 0;
+        // ping-pong between the workspace and state_out such that the last step lands in state_out; a recorded state is
+        // written straight into its trajectory slot (the next step reads it from there and adds its field)
+        float* dst = ((steps - 1 - t) % 2 == 0) ? state_out : tmp;
+        if (recorded && t != steps - 1) dst = traj + (size_t)((t + 1) / record_every - 1) * state_floats;
+        a.in = src; a.out = dst;
+        a.flux_out = flux_n ? flux_n + (size_t)t * B * nx : nullptr;
+        a.rec_in = rec[(t + 1) & 1]; a.rec_out = rec[t & 1];
+        a.step = t;
+        // the field of a recorded (or the caller's) input state is stored into that state's E plane
+        const bool in_recorded = t > 0 && traj != nullptr && t % record_every == 0;
+        a.e_out = in_recorded ? const_cast<float*>(src) : nullptr;
+        if (t == 0) k_first<<<grid, kScanThreads, smem, stream>>>(a);
+        else k_step<<<grid, kScanThreads, smem, stream>>>(a);
+        ++nl;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        src = dst;
+    }
+    // materialise the field of the final state and certify it
+    a.in = state_out; a.out = nullptr; a.e_out = state_out; a.flux_out = nullptr;
+    a.rec_in = rec[(steps + 1) & 1]; a.rec_out = rec[steps & 1];
+    a.step = steps;
+    k_final<<<grid, kScanThreads, smem, stream>>>(a);
+    ++nl;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    baseline_scan_flag_kernel<<<B, 32, 0, stream>>>(rec[steps & 1], B, segs, nx, length, tol, steps, flag, 0);
+    ++nl;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (traj != nullptr && steps % record_every == 0) {
+        e = cudaMemcpyAsync(traj + (size_t)(steps / record_every - 1) * state_floats, state_out, state_floats * sizeof(float),
+                            cudaMemcpyDeviceToDevice, stream);
+        if (e != cudaSuccess) return e;
+    }
+    *launches = nl;
+    return cudaSuccess;
+}
+
+}  // namespace fluxgnn

@@ -330,6 +330,28 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out,
                              int steps, int record_every, float* traj,
                              float* flux_n, void* workspace, void* stream);
 
+/* ---- classical rollout with the field solve as a certified prefix sum ("scan solve") -----------
+ * The same step as fluxgnn_baseline_rollout (src/baseline_solver.py:80-101) for long grids
+ * (fluxgnn_baseline_scan_supported: nx >= 4096, nx % 8 == 0).  The operator of
+ * src/baseline_solver.py:59-68 is the zero-mean periodic antiderivative of -(n - 1 - mean); it is
+ * evaluated as trapezoid prefix sum + first Euler-Maclaurin term, and for every field so obtained
+ * the kernel evaluates the rigorous bound
+ *     max|E_scan - E_spectral| <= rms(4th difference of n) * length / (32 sqrt 3).
+ * *first_uncertified (DEVICE int) receives the index of the first step whose input field had
+ * bound > cert_tol * max|E| (index `steps` = the field of the final state), INT_MAX if every field
+ * was certified.  The caller reads it after the stream has finished and, if it is not INT_MAX,
+ * repeats the rollout with fluxgnn_baseline_rollout (BaselineSolver.rollout(field_solve="auto")
+ * does exactly that).  Between steps only n and u live in HBM (16 B per cell-update); E is written
+ * for recorded states and the final state.  state_in's E is used for the first step as given.
+ *   workspace: fluxgnn_baseline_scan_workspace_bytes(B, nx) bytes. */
+int fluxgnn_baseline_scan_supported(int B, int nx);
+size_t fluxgnn_baseline_scan_workspace_bytes(int B, int nx);
+int fluxgnn_baseline_rollout_scan(const float* state_in, float* state_out, int B, int nx, double length,
+                                  float c, float dt, float nu, float dx2,
+                                  int steps, int record_every, float* traj, float* flux_n,
+                                  double cert_tol, void* workspace, int* first_uncertified,
+                                  void* stream);
+
 /* ---- the reference's comparison models ---------------------------------------
  * PureGNN (scripts/training/train_pure_gnn.py:35-76), rolled out as in
  * scripts/evaluation/benchmark_timing.py:129-143: per step  state += PureGNN([n,u,E,x], ring edges).

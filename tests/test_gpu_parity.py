@@ -824,7 +824,7 @@ def test_baseline_domain_decomposition_emulated_ranks(built_lib, world, nx, fiel
     from gnn_plasma_flux_b200 import BaselineSolver
     from gnn_plasma_flux_b200.domain import DomainDecomposedBaselineSolver, split_slabs, step_emulated
     dt = 0.2 * (2 * np.pi / nx) ** 2 / 1e-3
-    whole = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device="cuda")
+    whole = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device="cuda", field_solve="spectral")
     grid = P.Grid(nx=nx, dt=dt)
     dev = torch.from_numpy(np.stack([P.stable_initial_condition(grid, s) for s in range(3)])).cuda()
     solvers = [DomainDecomposedBaselineSolver(nx, dt=dt, nu=1e-3, rank=r, world=world, device="cuda", field_solve=field_solve)
@@ -871,7 +871,7 @@ def test_baseline_fused_rollout_is_bit_identical(built_lib, monkeypatch, log2nx,
     from gnn_plasma_flux_b200.synthetic import stable_initial_conditions
     nx = 1 << log2nx
     dt = 0.2 * (2 * np.pi / nx) ** 2 / 1e-3
-    sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device="cuda")
+    sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3, device="cuda", field_solve="spectral")    # the FFT path is under test
     state = stable_initial_conditions(sol, B)
     state[:, 1] += 1e-3 * torch.randn(B, nx, device="cuda", generator=torch.Generator("cuda").manual_seed(log2nx))
     plain = sol.rollout(state, steps)[0]

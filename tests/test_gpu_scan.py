@@ -1,0 +1,157 @@
+"""The certified prefix-sum field solve of the classical solver (csrc/scan_poisson.cu) against the oracle.
+
+Reference operator: src/baseline_solver.py:59-68 (E = Re ifft(i fft(n - 1) / k)) and the step :80-101.  The scan solve
+must (1) leave the finite-volume update bit-exact, (2) stay within the certified distance of the spectral field, (3)
+refuse -- through its certificate -- every input it cannot certify, in which case "auto" repeats with the FFT solve.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import batched, ref_port as P
+
+pytestmark = pytest.mark.gpu
+STEP_TOL = 1e-5          # north_star: fp32 path within 1e-5 relative per step
+
+
+def _stable_dt(nx, nu=1e-3):
+    dx = 2 * np.pi / nx
+    return min(0.02 * dx, 0.2 * dx * dx / nu)
+
+
+def _ics(nx, B, dt):
+    grid = P.Grid(nx=nx, dt=dt, nu=1e-3)
+    return grid, np.stack([P.stable_initial_condition(grid, s) for s in range(B)])
+
+
+def _spectral_fp64(n):
+    """The reference operator evaluated in float64 (numpy), [B, nx] -> [B, nx]."""
+    nx = n.shape[-1]
+    rho = (n - np.float32(1.0)).astype(np.float64)
+    k = 2 * np.pi * np.fft.fftfreq(nx, 2 * np.pi / nx)
+    rh = np.fft.fft(rho, axis=-1)
+    eh = np.zeros_like(rh)
+    eh[..., 1:] = 1j * rh[..., 1:] / k[1:]
+    return np.real(np.fft.ifft(eh, axis=-1))
+
+
+@pytest.mark.parametrize("nx,B", [(4096, 2), (12000, 1), (4096 + 8, 3), (1 << 16, 3), (1 << 20, 2)])
+def test_scan_rollout_vs_oracle(built_lib, nx, B):
+    """n', u' of the first step bit-exact; 5 steps against the CPU port within the per-step tolerance; the field of
+    the final state against the float64 spectral operator applied to the final density."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    dt = _stable_dt(nx)
+    grid, ics = _ics(nx, B, dt)
+    sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="scan")
+    dev = torch.from_numpy(ics).cuda()
+    one, _, flux = sol.rollout(dev, 1, record_flux=True)
+    ref1 = batched.baseline_step(torch.from_numpy(ics), grid.k, grid.dt, grid.dx, grid.nu).numpy()
+    np.testing.assert_array_equal(one.cpu().numpy()[:, :2], ref1[:, :2])
+    np.testing.assert_array_equal(flux[0].cpu().numpy(), ics[:, 0] * ics[:, 1])
+    assert P.rel_err(one.cpu().numpy(), ref1).max() <= STEP_TOL          # the fp32 port's own FFT error is ~1.5e-6 at 2^20
+    out = sol.rollout(dev, 5)[0].cpu().numpy()
+    assert sol.last_field_solve == "scan" and sol.last_uncertified_step is None
+    ref = torch.from_numpy(ics)
+    for _ in range(5):
+        ref = batched.baseline_step(ref, grid.k, grid.dt, grid.dx, grid.nu)
+    assert P.rel_err(out, ref.numpy()).max() <= STEP_TOL
+    e64 = _spectral_fp64(out[:, 0])
+    assert np.abs(out[:, 2] - e64).max() <= 4e-7 * np.abs(e64).max()          # fp32 rounding of E itself
+    assert abs(out[:, 2].astype(np.float64).mean()) <= 1e-7 * np.abs(e64).max()
+
+
+def test_scan_is_closer_to_float64_than_the_fft_solve(built_lib):
+    """At 2^22 cells the fp32 FFT solve carries log2(N) rounding steps; the prefix sum accumulates in float64."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    nx = 1 << 22
+    dt = _stable_dt(nx)
+    _, ics = _ics(nx, 1, dt)
+    dev = torch.from_numpy(ics).cuda()
+    e64 = _spectral_fp64(BaselineSolver(nx=nx, dt=dt, field_solve="scan").rollout(dev, 1)[0][:, 0].cpu().numpy())
+    err = {}
+    for mode in ("scan", "spectral"):
+        out = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve=mode).rollout(dev, 1)[0].cpu().numpy()
+        err[mode] = np.abs(out[:, 2] - e64).max() / np.abs(e64).max()
+    assert err["scan"] <= 2e-7 and err["scan"] <= err["spectral"], err
+
+
+def test_scan_certificate_rejects_rough_density(built_lib):
+    """White noise on the density: the bound exceeds the tolerance, "scan" raises, "auto" repeats the rollout with the
+    FFT solve and returns exactly what "spectral" returns."""
+    from gnn_plasma_flux_b200 import BaselineSolver, _lib
+    nx = 1 << 16
+    dt = _stable_dt(nx)
+    _, ics = _ics(nx, 2, dt)
+    rng = np.random.RandomState(0)
+    ics[:, 0] += (1e-3 * rng.randn(2, nx)).astype(np.float32)
+    dev = torch.from_numpy(ics).cuda()
+    spectral = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="spectral").rollout(dev, 4)[0]
+    auto = BaselineSolver(nx=nx, dt=dt, nu=1e-3)                                  # default: auto
+    got = auto.rollout(dev, 4)[0]
+    assert auto.last_field_solve == "spectral" and auto.last_uncertified_step == 1
+    assert torch.equal(got, spectral)
+    with pytest.raises(_lib.FluxGNNError, match="not certified"):
+        BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="scan").rollout(dev, 4)
+    # the bound is an upper bound: measured deviation of the uncertified scan field from the float64 operator
+    loose = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="scan", cert_tol=1.0)
+    out = loose.rollout(dev, 1)[0].cpu().numpy()
+    e64 = _spectral_fp64(out[:, 0])
+    rho = (out[:, 0] - np.float32(1.0)).astype(np.float64)
+    d4 = np.roll(rho, -2, -1) - 4 * np.roll(rho, -1, -1) + 6 * rho - 4 * np.roll(rho, 1, -1) + np.roll(rho, 2, -1)
+    bound = np.sqrt((d4 ** 2).mean(-1)) * 2 * np.pi / (32 * np.sqrt(3))
+    dev_max = np.abs(out[:, 2] - e64).max(-1)
+    assert (dev_max <= bound).all(), (dev_max, bound)         # (very conservative for white noise: Cauchy-Schwarz)
+
+
+def test_scan_short_or_odd_grids_use_the_fft_solve(built_lib):
+    from gnn_plasma_flux_b200 import BaselineSolver, _lib
+    for nx in (64, 1024, 4100):
+        sol = BaselineSolver(nx=nx, dt=_stable_dt(nx), nu=1e-3)
+        _, ics = _ics(nx, 1, sol.dt)
+        sol.rollout(torch.from_numpy(ics).cuda(), 2)
+        assert sol.last_field_solve == "spectral"
+        with pytest.raises(_lib.FluxGNNError, match="nx >= 4096"):
+            sol.rollout(torch.from_numpy(ics).cuda(), 2, field_solve="scan")
+
+
+@pytest.mark.parametrize("record_every", [1, 3])
+def test_scan_trajectory_and_flux(built_lib, record_every):
+    """Recorded states carry their reconstructed field; fluxes and trajectory agree with the FFT path."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    nx, B, steps = 1 << 14, 2, 9
+    dt = _stable_dt(nx)
+    _, ics = _ics(nx, B, dt)
+    dev = torch.from_numpy(ics).cuda()
+    a = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="spectral").rollout(dev, steps, record_every, True)
+    b = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="scan").rollout(dev, steps, record_every, True)
+    assert b[1].shape == (steps // record_every, B, 3, nx) and b[2].shape == (steps, B, nx)
+    assert torch.equal(b[1][-1], b[0])
+    assert torch.equal(a[2][0], b[2][0])                          # F_n of the first step: same inputs
+    assert P.rel_err(b[0].cpu().numpy(), a[0].cpu().numpy()).max() <= 5e-6                       # final state
+    assert P.rel_err(b[1].cpu().numpy().reshape(-1, 3, nx), a[1].cpu().numpy().reshape(-1, 3, nx)).max() <= 5e-6
+    assert float((a[2] - b[2]).abs().max() / a[2].abs().max()) <= 5e-6                            # fluxes
+    # run(): the reference's list-of-states API on top of the same call
+    states, fluxes = BaselineSolver(nx=nx, dt=dt, nu=1e-3).run(ics[0], n_steps=4)
+    assert states.shape == (5, 3, nx) and fluxes.shape == (4, nx)
+    np.testing.assert_array_equal(states[0], ics[0])
+
+
+def test_scan_full_size_c5(built_lib):
+    """BASELINE.json configs[4] at full size: 2^24 cells, 10 steps.  Properties: mass conserved to round-off, zero-mean
+    field, every field certified, agreement with the FFT path within the fp32 accuracy of the FFT path."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    nx = 1 << 24
+    dt = _stable_dt(nx)
+    _, ics = _ics(nx, 1, dt)
+    dev = torch.from_numpy(ics).cuda()
+    sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3)
+    out = sol.rollout(dev, 10)[0]
+    assert sol.last_field_solve == "scan" and sol.last_uncertified_step is None
+    ref = sol.rollout(dev, 10, field_solve="spectral")[0]
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[:, 0], ref[:, 0])                      # the field only enters through dt * E, below rounding here
+    assert P.rel_err(out.cpu().numpy(), ref.cpu().numpy()).max() <= 3e-6
+    o = out.cpu().numpy()
+    assert abs(o[0, 0].astype(np.float64).sum() - ics[0, 0].astype(np.float64).sum()) <= 4 * nx * np.finfo(np.float32).eps
+    e64 = _spectral_fp64(o[:, 0])
+    assert np.abs(o[:, 2] - e64).max() <= 4e-7 * np.abs(e64).max()
