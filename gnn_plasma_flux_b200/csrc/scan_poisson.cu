@@ -19,7 +19,7 @@
 // Because E is a function of n alone, the rollout keeps only (n, u) in HBM between steps: step s+1 reconstructs the field
 // of its input from n and the per-segment sums the previous launch left behind, so a step moves 16 bytes per cell
 // (read n, u; write n', u') instead of 24 + the transform passes.  Every grid is cut into contiguous segments, one
-// persistent CTA each; a CTA streams its segment in 4096-cell chunks through a 3-stage shared-memory ring filled by 1-D
+// persistent CTA each; a 256-thread CTA streams its segment in 2048-cell chunks through a 3-stage shared-memory ring filled by 1-D
 // bulk copies (TMA, SASS UBLKCP) and carries the running prefix in a register.  No inter-CTA dependency inside a
 // launch: segment prefixes come from the records of the previous launch.
 #include <climits>
@@ -32,9 +32,13 @@ namespace fluxgnn {
 
 namespace {
 
-constexpr int kScanThreads = 512;
+#ifndef FLUXGNN_SCAN_THREADS
+#define FLUXGNN_SCAN_THREADS 256
+#endif
+constexpr int kScanThreads = FLUXGNN_SCAN_THREADS;     // 1024 threads per SM: 4 CTAs of 256 (smaller barrier domains than 2 x 512)
+constexpr int kScanCtasPerSm = 1024 / kScanThreads;
 constexpr int kScanPer = 8;                                  // consecutive cells per thread
-constexpr int kScanChunk = kScanThreads * kScanPer;          // 4096 cells
+constexpr int kScanChunk = kScanThreads * kScanPer;          // 2048 cells
 constexpr int kScanStages = 3;
 constexpr int kScanHalo = 4;                                 // staged halo cells per side (16 bytes)
 constexpr int kScanRow = kScanChunk + 2 * kScanHalo;         // floats per staged array
@@ -84,7 +88,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // kPacked: the finite-volume update in packed fp32x2 arithmetic (fv_pair; needs fv_reciprocal(dx2) != 0), bit-identical
 // to the scalar form.
 template <int MODE, bool kPacked>
-__global__ void __launch_bounds__(kScanThreads, 2) baseline_scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScanSmem& S = *reinterpret_cast<ScanSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -225,11 +229,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) baseline_scan_kernel(const Sc
             if (lane == 31) S.wsum[k & 1][warp] = incl;
             excl32 = incl - t;
         }
-        __syncthreads();                 // warp totals visible; every thread has copied its cells out of stage `st`
-        if (tid == 0 && k + kScanStages < nchunks) issue(k + kScanStages);
+        __syncthreads();                 // warp totals visible
+        // Refill the stage of the PREVIOUS chunk: a thread that has arrived here has finished that chunk's arithmetic, so
+        // its shared-memory reads have really completed.  (Refilling this chunk's own stage here raced: the loads above are
+        // only issued, not performed, when the barrier completes, and the bulk copy -- async proxy -- overtook them.)
+        if (tid == 0 && k >= 1 && k - 1 + kScanStages < nchunks) issue(k - 1 + kScanStages);
         double base = 0.0;
         if (MODE != 0) {
-            // every warp scans the 16 warp totals itself (lanes 0..15, fp64): no second block barrier
+            // every warp scans the warp totals itself (one lane each, fp64): no second block barrier
             double w = (lane < kScanThreads / 32) ? (double)S.wsum[k & 1][lane] : 0.0;
 #pragma unroll
             for (int o = 1; o < kScanThreads / 32; o <<= 1) {
@@ -362,7 +369,7 @@ bool fv_reciprocal_host(float b) {
 
 void scan_geometry(int B, int nx, int sms, int* segs, int* seg_chunks) {
     const int nchunks = (nx + kScanChunk - 1) / kScanChunk;
-    int target = (2 * sms) / B;
+    int target = (kScanCtasPerSm * sms) / B;
     if (target < 1) target = 1;
     if (target > nchunks) target = nchunks;
     const int sc = (nchunks + target - 1) / target;
@@ -373,7 +380,7 @@ void scan_geometry(int B, int nx, int sms, int* segs, int* seg_chunks) {
 }  // namespace
 
 bool baseline_scan_supported(int B, int nx) {
-    return nx >= kScanChunk && (nx % kScanPer) == 0 && B >= 1 && B <= 4096;
+    return nx >= 4096 && (nx % kScanPer) == 0 && B >= 1 && B <= 4096;
 }
 
 size_t baseline_scan_workspace_bytes(int B, int nx, int sms) {
