@@ -74,6 +74,7 @@ struct ScanSmem {
     float redf[kScanThreads / 32];
     double bc[4];            // broadcast: P_seg, rbar, mu, (unused)
     uint64_t full[kScanStages];
+    uint64_t empty[kScanStages];   // one arrival per warp once its loads of the stage have been performed
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
     const float* pe = pu + nx;
 
     if (tid == 0) {
-        for (int s = 0; s < kScanStages; ++s) mbar_init(&S.full[s], 1);
+        for (int s = 0; s < kScanStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], kScanThreads / 32); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -229,11 +230,17 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
             if (lane == 31) S.wsum[k & 1][warp] = incl;
             excl32 = incl - t;
         }
+        // The stage may be refilled once every warp's loads from it have been PERFORMED, not merely issued: a block
+        // barrier alone does not order the in-flight loads against the bulk copy of the async proxy (measured: sporadic
+        // stale cells with four CTAs per SM).  Each warp therefore releases the stage through an mbarrier arrival, which
+        // is ordered behind its loads, and the producer waits for the eight arrivals before it issues the refill.
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.empty[st]);
         __syncthreads();                 // warp totals visible
-        // Refill the stage of the PREVIOUS chunk: a thread that has arrived here has finished that chunk's arithmetic, so
-        // its shared-memory reads have really completed.  (Refilling this chunk's own stage here raced: the loads above are
-        // only issued, not performed, when the barrier completes, and the bulk copy -- async proxy -- overtook them.)
-        if (tid == 0 && k >= 1 && k - 1 + kScanStages < nchunks) issue(k - 1 + kScanStages);
+        if (tid == 0 && k + kScanStages < nchunks) {
+            mbar_wait(&S.empty[st], (uint32_t)((k / kScanStages) & 1));
+            issue(k + kScanStages);
+        }
         double base = 0.0;
         if (MODE != 0) {
             // every warp scans the warp totals itself (one lane each, fp64): no second block barrier
