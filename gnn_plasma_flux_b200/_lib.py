@@ -90,6 +90,12 @@ SIGNATURES = {
     "fluxgnn_baseline_scan_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_baseline_rollout_scan": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float, c_float,
                                               c_int, c_int, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_scan_slab_supported": (c_int, [c_int, c_int]),
+    "fluxgnn_scan_slab_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_scan_slab_sums": (c_int, [c_void_p, c_longlong, c_int, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_scan_slab_field": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_double,
+                                        c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p]),
+    "fluxgnn_scan_slab_certify": (c_int, [c_int, c_int, c_int, c_double, c_void_p, c_double, c_int, c_void_p, c_void_p]),
     "fluxgnn_baseline_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_baseline_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_float, c_float,
                                          c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -760,4 +760,50 @@ int fluxgnn_baseline_rollout_scan(const float* state_in, float* state_out, int B
     return FLUXGNN_OK;
 }
 
+int fluxgnn_scan_slab_supported(int B, int S) { return scan_slab_supported(B, S) ? 1 : 0; }
+
+size_t fluxgnn_scan_slab_workspace_bytes(int B, int S) {
+    int sms = 0;
+    if (!scan_slab_supported(B, S) || sm_count(&sms) != FLUXGNN_OK) return 0;
+    return scan_slab_workspace_bytes(B, S, sms);
+}
+
+int fluxgnn_scan_slab_sums(const float* n, long long n_ld, int B, int S, long long j_base, void* workspace, void* msg,
+                           void* stream) {
+    if (!n || !workspace || !msg || n_ld < S) return set_error(FLUXGNN_EINVAL, "scan_slab_sums: bad argument");
+    if (!scan_slab_supported(B, S)) return set_error(FLUXGNN_EUNSUP, "scan_slab_sums: needs S %% 8 == 0, S >= 64 (B=%d S=%d)", B, S);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    FLUXGNN_CUDA_OK(launch_scan_slab_sums(n, n_ld, B, S, j_base, workspace, msg, sms, (cudaStream_t)stream));
+    count_launch(2);
+    return FLUXGNN_OK;
+}
+
+int fluxgnn_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
+                            double length, const void* msg_all, void* workspace, double cert_tol, int step,
+                            int* first_uncertified, void* stream) {
+    if (!n || !E || !msg_all || !workspace || !first_uncertified || n_ld < S || e_ld < S || ranks < 1 || rank < 0 ||
+        rank >= ranks || !(length > 0.0) || !(cert_tol > 0.0) || step < 0)
+        return set_error(FLUXGNN_EINVAL, "scan_slab_field: bad argument");
+    if (!scan_slab_supported(B, S)) return set_error(FLUXGNN_EUNSUP, "scan_slab_field: needs S %% 8 == 0, S >= 64 (B=%d S=%d)", B, S);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    FLUXGNN_CUDA_OK(launch_scan_slab_field(n, n_ld, E, e_ld, B, S, rank, ranks, length, msg_all, workspace, cert_tol, step,
+                                           first_uncertified, sms, (cudaStream_t)stream));
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+int fluxgnn_scan_slab_certify(int B, int S, int ranks, double length, const void* msg_all, double cert_tol, int step,
+                              int* first_uncertified, void* stream) {
+    if (!msg_all || !first_uncertified || B < 1 || S < 1 || ranks < 1 || !(length > 0.0) || !(cert_tol > 0.0))
+        return set_error(FLUXGNN_EINVAL, "scan_slab_certify: bad argument");
+    FLUXGNN_CUDA_OK(launch_scan_slab_certify(B, S, ranks, length, msg_all, cert_tol, step, first_uncertified,
+                                             (cudaStream_t)stream));
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 }  // extern "C"

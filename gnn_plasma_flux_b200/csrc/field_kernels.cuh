@@ -139,4 +139,15 @@ cudaError_t launch_baseline_rollout_scan(const float* state_in, float* state_out
                                          float nu, float dx2, int steps, int record_every, float* traj, float* flux_n,
                                          double tol, void* workspace, int* flag, int sms, cudaStream_t stream, int* launches);
 
+// scan_poisson.cu, slab form (domain decomposition): per-rank sums + message, reconstruction from the gathered messages
+bool scan_slab_supported(int B, int S);
+size_t scan_slab_workspace_bytes(int B, int S, int sms);
+cudaError_t launch_scan_slab_sums(const float* n, long long n_ld, int B, int S, long long j_base, void* workspace, void* msg,
+                                  int sms, cudaStream_t stream);
+cudaError_t launch_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
+                                   double length, const void* msg_all, void* workspace, double tol, int step, int* flag, int sms,
+                                   cudaStream_t stream);
+cudaError_t launch_scan_slab_certify(int B, int S, int ranks, double length, const void* msg_all, double tol, int step, int* flag,
+                                     cudaStream_t stream);
+
 }  // namespace fluxgnn

@@ -384,6 +384,242 @@ void scan_geometry(int B, int nx, int sms, int* segs, int* seg_chunks) {
     *segs = (nchunks + sc - 1) / sc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same solve for ONE SLAB of a domain-decomposed grid (gnn_plasma_flux_b200/domain.py, field_solve="scan"): the
+// "distributed Poisson reduction" of BASELINE.json's north_star.  Rank r owns cells [r S, (r+1) S) of every IC.
+//   slab_sums  : per-segment S = sum rho, M1 = sum j rho (j global)                          -> workspace
+//   slab_msg   : the rank's 48-byte message per IC: totals, the certificate sums of the field it reconstructed last,
+//                and its first / last two densities (the neighbours' stencil needs them)      -> all-gather, 48 B x B
+//   slab_field : prefix over the ranks before this one + the segments before this CTA's, then the reconstruction
+//                and certificate of scan_poisson's single-GPU kernel.  Plain loads (slabs of the hybrid solver start
+//                at halo = L r + 1 cells, not 16-byte aligned), neighbours through warp shuffles.
+// One collective of a few hundred bytes replaces the four all-to-alls (4 bytes per cell each) of the distributed FFT.
+// ---------------------------------------------------------------------------------------------------------------
+struct SlabMsg {
+    double S, M1, D4;        // totals of this rank's slab: sum rho, sum j rho, sum (Delta^4 rho)^2 of its previous field
+    float maxE;              // max |E| of its previous field
+    float edge[4];           // n of its first two and last two cells
+    float pad;
+};
+static_assert(sizeof(SlabMsg) == 48, "message layout");
+
+struct SlabSeg { double S, M1, D4; float maxE; int pad; };      // per-segment scratch (sums now, certificate of the last field)
+
+constexpr int kSlabThreads = 256;
+constexpr int kSlabChunk = kSlabThreads * kScanPer;
+
+__host__ __device__ inline void slab_geometry(int B, int S, int sms, int* segs, int* seg_chunks) {
+    const int nchunks = (S + kSlabChunk - 1) / kSlabChunk;
+    int target = (4 * sms) / B;
+    if (target < 1) target = 1;
+    if (target > nchunks) target = nchunks;
+    const int sc = (nchunks + target - 1) / target;
+    *seg_chunks = sc;
+    *segs = (nchunks + sc - 1) / sc;
+}
+
+__device__ __forceinline__ void slab_load8(const float* row, long long j, bool vec, float (&v)[8]) {
+    if (vec) {
+        const float4 a = *reinterpret_cast<const float4*>(row + j), b = *reinterpret_cast<const float4*>(row + j + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = row[j + i];
+    }
+}
+
+__global__ void __launch_bounds__(kSlabThreads) slab_sums_kernel(const float* __restrict__ n, long long n_ld, int S, int segs,
+                                                                 int seg_chunks, long long j_base, SlabSeg* __restrict__ seg_out) {
+    __shared__ double red[2][kSlabThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ic = (int)blockIdx.x / segs, seg = (int)blockIdx.x - ic * segs;
+    const float* row = n + (size_t)ic * n_ld;
+    const bool vec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) && (n_ld & 3) == 0;
+    const long long begin = (long long)seg * seg_chunks * kSlabChunk;
+    long long end = begin + (long long)seg_chunks * kSlabChunk;
+    if (end > S) end = S;
+    double accS = 0.0, accM = 0.0;
+    for (long long j0 = begin + (long long)tid * kScanPer; j0 < end; j0 += kSlabChunk) {
+        float v[8];
+        slab_load8(row, j0, vec, v);
+        float s1 = 0.f, m1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float r = __fsub_rn(v[i], 1.0f);
+            s1 += r;
+            m1 = fmaf((float)i, r, m1);
+        }
+        accS += (double)s1;
+        accM = fma((double)(j_base + j0), (double)s1, accM) + (double)m1;
+    }
+    accS = warp_sum(accS); accM = warp_sum(accM);
+    if (lane == 0) { red[0][warp] = accS; red[1][warp] = accM; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kSlabThreads / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+        SlabSeg& o = seg_out[(size_t)ic * segs + seg];      // D4 / maxE keep the certificate of the previous field
+        o.S = a; o.M1 = b;
+    }
+}
+
+__global__ void slab_msg_kernel(const float* __restrict__ n, long long n_ld, int S, int segs, const SlabSeg* __restrict__ seg_rec,
+                                SlabMsg* __restrict__ msg) {
+    const int ic = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    SlabMsg m;
+    m.S = 0.0; m.M1 = 0.0; m.D4 = 0.0; m.maxE = 0.f; m.pad = 0.f;
+    for (int s = 0; s < segs; ++s) {
+        const SlabSeg r = seg_rec[(size_t)ic * segs + s];
+        m.S += r.S; m.M1 += r.M1; m.D4 += r.D4; m.maxE = fmaxf(m.maxE, r.maxE);
+    }
+    const float* row = n + (size_t)ic * n_ld;
+    m.edge[0] = row[0]; m.edge[1] = row[1]; m.edge[2] = row[S - 2]; m.edge[3] = row[S - 1];
+    msg[ic] = m;
+}
+
+struct SlabFieldArgs {
+    const float* n; long long n_ld; float* E; long long e_ld;
+    int B, S, segs, seg_chunks, rank, ranks, step;
+    double dx, length, tol;
+    const SlabMsg* msg_all;      // [ranks][B]
+    SlabSeg* seg_rec;            // [B][segs]: S, M1 of this launch's density in; D4, maxE of the field reconstructed here out
+    int* flag;
+};
+
+__global__ void __launch_bounds__(kSlabThreads) slab_field_kernel(const SlabFieldArgs a) {
+    __shared__ float wsum[2][kSlabThreads / 32];
+    __shared__ double redd[kSlabThreads / 32];
+    __shared__ float redf[kSlabThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ic = (int)blockIdx.x / a.segs, seg = (int)blockIdx.x - ic * a.segs;
+    const int S = a.S;
+    const float* row = a.n + (size_t)ic * a.n_ld;
+    float* out = a.E + (size_t)ic * a.e_ld;
+    const bool vec_in = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) && (a.n_ld & 3) == 0;
+    const bool vec_out = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (a.e_ld & 3) == 0;
+    const long long begin = (long long)seg * a.seg_chunks * kSlabChunk;
+    long long end = begin + (long long)a.seg_chunks * kSlabChunk;
+    if (end > S) end = S;
+
+    // ---- prologue (every thread, same order everywhere): totals over the ranks, prefix of ranks and segments before ----
+    double s_tot = 0.0, m_tot = 0.0, d_tot = 0.0, P = 0.0;
+    float e_max = 0.f;
+    for (int g = 0; g < a.ranks; ++g) {
+        const SlabMsg& m = a.msg_all[(size_t)g * a.B + ic];
+        s_tot += m.S; m_tot += m.M1; d_tot += m.D4; e_max = fmaxf(e_max, m.maxE);
+        if (g < a.rank) P += m.S;
+    }
+    for (int s = 0; s < seg; ++s) P += a.seg_rec[(size_t)ic * a.segs + s].S;
+    const double N = (double)S * (double)a.ranks;
+    const double rbar = s_tot / N, mu = 0.5 * s_tot - m_tot / N - s_tot / (2.0 * N);
+    if (seg == 0 && tid == 0 && a.step > 0) {              // certificate of the field of the previous call
+        const double bound = sqrt(d_tot / N) * a.length * (1.0 / (32.0 * 1.7320508075688772));
+        if (!(bound <= a.tol * (double)e_max)) atomicMin(a.flag, a.step - 1);
+    }
+    const SlabMsg& ml = a.msg_all[(size_t)((a.rank + a.ranks - 1) % a.ranks) * a.B + ic];
+    const SlabMsg& mr = a.msg_all[(size_t)((a.rank + 1) % a.ranks) * a.B + ic];
+    const float left2[2] = {ml.edge[2], ml.edge[3]}, right2[2] = {mr.edge[0], mr.edge[1]};
+    auto fetch = [&](long long j) -> float {              // density of slab cell j in [-2, S+1]
+        return j < 0 ? left2[j + 2] : (j >= S ? right2[j - S] : row[j]);
+    };
+
+    const float dxf = (float)a.dx, dx24 = (float)(a.dx / 24.0), rbarf = (float)rbar;
+    const long long j_base = (long long)a.rank * S;
+    double run = P;
+    float accD = 0.f, accE = 0.f;
+    int k = 0;
+    for (long long c0 = begin; c0 < end; c0 += kSlabChunk, ++k) {
+        const long long j0 = c0 + (long long)tid * kScanPer;
+        const bool active = j0 < end;
+        float v[8];
+        if (active) slab_load8(row, j0, vec_in, v);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 1.0f;
+        }
+        // neighbours: the adjacent lanes hold them, except at warp, chunk and slab ends
+        float l0 = __shfl_up_sync(0xffffffffu, v[6], 1), l1 = __shfl_up_sync(0xffffffffu, v[7], 1);
+        float r0 = __shfl_down_sync(0xffffffffu, v[0], 1), r1 = __shfl_down_sync(0xffffffffu, v[1], 1);
+        if (active) {
+            if (lane == 0) { l0 = fetch(j0 - 2); l1 = fetch(j0 - 1); }
+            if (lane == 31 || j0 + 8 >= end) { r0 = fetch(j0 + 8); r1 = fetch(j0 + 9); }
+        }
+        float rho[12];
+        rho[0] = __fsub_rn(l0, 1.0f); rho[1] = __fsub_rn(l1, 1.0f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rho[2 + i] = __fsub_rn(v[i], 1.0f);
+        rho[10] = __fsub_rn(r0, 1.0f); rho[11] = __fsub_rn(r1, 1.0f);
+        float loc[8], t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { t += rho[2 + i]; loc[i] = t; }
+        float incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wsum[k & 1][warp] = incl;
+        __syncthreads();
+        double w = (lane < kSlabThreads / 32) ? (double)wsum[k & 1][lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < kSlabThreads / 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        const double total = __shfl_sync(0xffffffffu, w, kSlabThreads / 32 - 1);
+        const double before = __shfl_sync(0xffffffffu, w, (warp + 31) & 31);
+        const double base = run + (warp ? before : 0.0) + (double)(incl - t);
+        run += total;
+        if (!active) continue;
+        const float t0 = (float)(-a.dx * (base - ((double)(j_base + j0) + 0.5) * rbar - mu));
+        float ev[8], d4 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float br = fmaf(-0.5f, rho[2 + i], loc[i]) - (float)i * rbarf;
+            ev[i] = fmaf(-dxf, br, t0) + dx24 * (rho[3 + i] - rho[1 + i]);
+            accE = fmaxf(accE, fabsf(ev[i]));
+            const float q = fmaf(6.0f, rho[2 + i], fmaf(-4.0f, rho[1 + i] + rho[3 + i], rho[i] + rho[4 + i]));
+            d4 = fmaf(q, q, d4);
+        }
+        accD += d4;
+        if (vec_out) {
+            *reinterpret_cast<float4*>(out + j0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+            *reinterpret_cast<float4*>(out + j0 + 4) = make_float4(ev[4], ev[5], ev[6], ev[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[j0 + i] = ev[i];
+        }
+    }
+    double d = warp_sum((double)accD);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accE = fmaxf(accE, __shfl_xor_sync(0xffffffffu, accE, o));
+    if (lane == 0) { redd[warp] = d; redf[warp] = accE; }
+    __syncthreads();
+    if (tid == 0) {
+        double dd = 0.0;
+        float em = 0.f;
+        for (int w2 = 0; w2 < kSlabThreads / 32; ++w2) { dd += redd[w2]; em = fmaxf(em, redf[w2]); }
+        SlabSeg& o = a.seg_rec[(size_t)ic * a.segs + seg];
+        o.D4 = dd; o.maxE = em;
+    }
+}
+
+// the certificate of the LAST field of a run: the messages of one more sums + all-gather round carry its sums
+__global__ void slab_certify_kernel(const SlabMsg* __restrict__ msg_all, int B, int S, int ranks, double length, double tol,
+                                    int step, int* flag) {
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ic >= B) return;
+    double d = 0.0;
+    float em = 0.f;
+    for (int g = 0; g < ranks; ++g) {
+        d += msg_all[(size_t)g * B + ic].D4;
+        em = fmaxf(em, msg_all[(size_t)g * B + ic].maxE);
+    }
+    const double bound = sqrt(d / ((double)S * ranks)) * length * (1.0 / (32.0 * 1.7320508075688772));
+    if (!(bound <= tol * (double)em)) atomicMin(flag, step);
+}
+
 }  // namespace
 
 bool baseline_scan_supported(int B, int nx) {
@@ -464,6 +700,45 @@ cudaError_t launch_baseline_rollout_scan(const float* state_in, float* state_out
     }
     *launches = nl;
     return cudaSuccess;
+}
+
+// ---- slab (domain-decomposed) entry points; see include/fluxgnn.h ----
+bool scan_slab_supported(int B, int S) { return B >= 1 && B <= 4096 && S >= 64 && (S % kScanPer) == 0; }
+
+size_t scan_slab_workspace_bytes(int B, int S, int sms) {
+    int segs = 0, sc = 0;
+    slab_geometry(B, S, sms, &segs, &sc);
+    return (size_t)B * segs * sizeof(SlabSeg);
+}
+
+cudaError_t launch_scan_slab_sums(const float* n, long long n_ld, int B, int S, long long j_base, void* workspace, void* msg,
+                                  int sms, cudaStream_t stream) {
+    int segs = 0, sc = 0;
+    slab_geometry(B, S, sms, &segs, &sc);
+    slab_sums_kernel<<<(unsigned)(B * segs), kSlabThreads, 0, stream>>>(n, n_ld, S, segs, sc, j_base, (SlabSeg*)workspace);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    slab_msg_kernel<<<(unsigned)B, 32, 0, stream>>>(n, n_ld, S, segs, (const SlabSeg*)workspace, (SlabMsg*)msg);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
+                                   double length, const void* msg_all, void* workspace, double tol, int step, int* flag, int sms,
+                                   cudaStream_t stream) {
+    SlabFieldArgs a;
+    a.n = n; a.n_ld = n_ld; a.E = E; a.e_ld = e_ld;
+    a.B = B; a.S = S; a.rank = rank; a.ranks = ranks; a.step = step;
+    slab_geometry(B, S, sms, &a.segs, &a.seg_chunks);
+    a.length = length; a.dx = length / ((double)S * ranks); a.tol = tol;
+    a.msg_all = (const SlabMsg*)msg_all; a.seg_rec = (SlabSeg*)workspace; a.flag = flag;
+    slab_field_kernel<<<(unsigned)(B * a.segs), kSlabThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_slab_certify(int B, int S, int ranks, double length, const void* msg_all, double tol, int step, int* flag,
+                                     cudaStream_t stream) {
+    slab_certify_kernel<<<(unsigned)((B + 63) / 64), 64, 0, stream>>>((const SlabMsg*)msg_all, B, S, ranks, length, tol, step, flag);
+    return cudaGetLastError();
 }
 
 }  // namespace fluxgnn

@@ -186,6 +186,116 @@ def solve_emulated(solvers, n_rows, E_rows):
         solvers[r].unpack(a[r], E_rows[r])
 
 
+class DistributedScanSolve:
+    """The field solve as a distributed prefix sum (csrc/scan_poisson.cu, slab form; north_star's "distributed Poisson
+    reduction"): every rank sums its slab, ONE all-gather of 48 bytes per IC and rank carries the sums (plus the edge
+    densities the neighbours' stencil needs and the certificate sums of the previous field), then every rank
+    reconstructs its slab of E.  No transform, no all-to-all.  The certificate (bound on the distance to the spectral
+    operator, evaluated for every field) travels one step behind; `first_uncertified` closes the record."""
+
+    MSG_BYTES = 48
+    NEVER = 2 ** 31 - 1
+
+    def __init__(self, nx: int, length: float, rank: int, world: int, device, cert_tol: float = 1e-5, cpu_stages=None):
+        self.nx, self.length, self.rank, self.world = int(nx), float(length), rank, world
+        self.S = self.nx // world
+        if self.S % 8 or self.S < 64:
+            raise ValueError(f"the distributed scan solve needs slabs of a multiple of 8 cells (>= 64), got {self.S}")
+        self.device = torch.device(device)
+        self.cert_tol = float(cert_tol)
+        self._stages = cpu_stages           # test hook: CPU stand-ins for the CUDA stages
+        self._state = {}
+
+    def state(self, B: int):
+        st = self._state.get(B)
+        if st is None:
+            if self._stages:
+                st = {"work": None, "msg": torch.zeros(B, 8, dtype=torch.float64), "cert": torch.zeros(B, 2, dtype=torch.float64)}
+            else:
+                ws = _lib.lib().fluxgnn_scan_slab_workspace_bytes(B, self.S)
+                st = {"work": torch.zeros(ws, dtype=torch.uint8, device=self.device),       # zeroed once: carries the certificate sums
+                      "msg": torch.empty(B * self.MSG_BYTES, dtype=torch.uint8, device=self.device)}
+            st["flag"] = torch.full((1,), self.NEVER, dtype=torch.int32, device=self.device)
+            st["step"] = 0
+            self._state[B] = st
+        return st
+
+    # ---- stages ----
+    def sums(self, n_rows: torch.Tensor, st):
+        if self._stages:
+            return self._stages["sums"](self, n_rows, st)
+        B = n_rows.shape[0]
+        _lib.check(_lib.lib().fluxgnn_scan_slab_sums(n_rows.data_ptr(), n_rows.stride(0) if B > 1 else self.S, B, self.S,
+                                                     self.rank * self.S, st["work"].data_ptr(), st["msg"].data_ptr(),
+                                                     _stream(self.device)), "fluxgnn_scan_slab_sums")
+
+    def field(self, n_rows: torch.Tensor, E_rows: torch.Tensor, msg_all: torch.Tensor, st):
+        if self._stages:
+            return self._stages["field"](self, n_rows, E_rows, msg_all, st)
+        B = n_rows.shape[0]
+        _lib.check(_lib.lib().fluxgnn_scan_slab_field(
+            n_rows.data_ptr(), n_rows.stride(0) if B > 1 else self.S, E_rows.data_ptr(), E_rows.stride(0) if B > 1 else self.S,
+            B, self.S, self.rank, self.world, self.length, msg_all.data_ptr(), st["work"].data_ptr(), self.cert_tol, st["step"],
+            st["flag"].data_ptr(), _stream(self.device)), "fluxgnn_scan_slab_field")
+
+    def certify(self, msg_all: torch.Tensor, st, B: int):
+        if self._stages:
+            return self._stages["certify"](self, msg_all, st)
+        _lib.check(_lib.lib().fluxgnn_scan_slab_certify(B, self.S, self.world, self.length, msg_all.data_ptr(), self.cert_tol,
+                                                        st["step"] - 1, st["flag"].data_ptr(), _stream(self.device)),
+                   "fluxgnn_scan_slab_certify")
+
+    # ---- one solve on one rank ----
+    def solve(self, n_rows: torch.Tensor, E_rows: torch.Tensor, comm):
+        """E_rows[B,S] <- field of the global density whose slab is n_rows[B,S] (both may be strided row views)."""
+        st = self.state(n_rows.shape[0])
+        with torch.cuda.device(self.device) if self.device.type == "cuda" else _nullctx():
+            self.sums(n_rows, st)
+            msg_all = comm.all_gather(st["msg"])
+            self.field(n_rows, E_rows, msg_all, st)
+        st["step"] += 1
+
+    def first_uncertified(self, n_rows: torch.Tensor, comm):
+        """Index of the first field solve of this solver whose certificate failed (None: all certified).  Every rank
+        calls it together; `n_rows` is the current density slab (its sums ride along, they are not used)."""
+        st = self.state(n_rows.shape[0])
+        if st["step"] == 0:
+            return None
+        with torch.cuda.device(self.device) if self.device.type == "cuda" else _nullctx():
+            self.sums(n_rows, st)
+            msg_all = comm.all_gather(st["msg"])
+            self.certify(msg_all, st, n_rows.shape[0])
+        bad = int(st["flag"].item())
+        return None if bad == self.NEVER else bad
+
+
+def scan_solve_emulated(solvers, n_rows, E_rows):
+    """DistributedScanSolve.solve for G virtual ranks in one process: the all-gather becomes a stack."""
+    G = len(solvers)
+    sts = [solvers[r].state(n_rows[r].shape[0]) for r in range(G)]
+    for r in range(G):
+        solvers[r].sums(n_rows[r], sts[r])
+    msg_all = torch.stack([st["msg"] for st in sts]).contiguous()
+    for r in range(G):
+        solvers[r].field(n_rows[r], E_rows[r], msg_all, sts[r])
+        sts[r]["step"] += 1
+
+
+def scan_first_uncertified_emulated(solvers, n_rows):
+    G = len(solvers)
+    sts = [solvers[r].state(n_rows[r].shape[0]) for r in range(G)]
+    if sts[0]["step"] == 0:
+        return None
+    for r in range(G):
+        solvers[r].sums(n_rows[r], sts[r])
+    msg_all = torch.stack([st["msg"] for st in sts]).contiguous()
+    bad = DistributedScanSolve.NEVER
+    for r in range(G):
+        solvers[r].certify(msg_all, sts[r], n_rows[r].shape[0])
+        bad = min(bad, int(sts[r]["flag"].item()))
+    return None if bad == DistributedScanSolve.NEVER else bad
+
+
 class _nullctx:
     def __enter__(self):
         return self
@@ -203,7 +313,7 @@ class _DomainDecomposedSolver:
     """Shared host logic: extended ping-pong state, halo exchange, field solve, step orchestration."""
 
     def __init__(self, nx, length, dt, halo, rank, world, device, field_solve, slab_fn=None, field_fn=None,
-                 field_stages=None):
+                 field_stages=None, cert_tol=1e-5):
         if nx % world:
             raise ValueError(f"nx={nx} is not divisible by the number of ranks {world}")
         self.nx, self.length, self.dt = int(nx), float(length), float(dt)
@@ -212,8 +322,8 @@ class _DomainDecomposedSolver:
         self.halo = int(halo)
         if self.owned < self.halo:
             raise ValueError(f"a slab of {self.owned} cells is narrower than the halo of {self.halo}")
-        if field_solve not in ("auto", "alltoall", "allgather"):
-            raise ValueError("field_solve must be 'auto', 'alltoall' or 'allgather'")
+        if field_solve not in ("auto", "alltoall", "allgather", "scan"):
+            raise ValueError("field_solve must be 'auto', 'alltoall', 'allgather' or 'scan'")
         if field_solve == "auto":            # the distributed solve needs power-of-two slabs and rank counts
             ok = not (self.owned & (self.owned - 1)) and self.owned >= 256 and not (world & (world - 1)) and world <= 16
             field_solve = "alltoall" if ok else "allgather"
@@ -230,6 +340,10 @@ class _DomainDecomposedSolver:
         self._edges = {}
         self._dist = (DistributedFieldSolve(self.nx, self.length, rank, world, self.device, field_stages)
                       if field_solve == "alltoall" else None)
+        # "scan": distributed prefix-sum solve (one all-gather of 48 B per IC and rank); certified per field, see
+        # first_uncertified().  Explicit opt-in: a failed certificate is reported, not repaired, on this path.
+        self._scan = (DistributedScanSolve(self.nx, self.length, rank, world, self.device, cert_tol, field_stages)
+                      if field_solve == "scan" else None)
 
     # ---- extended state ----
     def _buffers(self, B: int):
@@ -281,6 +395,9 @@ class _DomainDecomposedSolver:
     def _solve_field(self, nxt: torch.Tensor, comm):
         """E' of the new density (channel 0 of `nxt`'s interior) into channel 2 of `nxt`'s interior."""
         inner = self.interior(nxt)
+        if self._scan is not None:
+            self._scan.solve(inner[:, 0], inner[:, 2], comm)
+            return
         if self._dist is not None:
             self._dist.solve(inner[:, 0], inner[:, 2], comm)
             return
@@ -288,6 +405,13 @@ class _DomainDecomposedSolver:
         gathered = comm.all_gather(inner[:, 0].contiguous())                    # [world,B,S]
         n_full = gathered.permute(1, 0, 2).reshape(nxt.shape[0], self.nx)
         inner[:, 2].copy_(self.field(n_full)[:, self.rank * S:(self.rank + 1) * S])
+
+    def first_uncertified(self, local: torch.Tensor, comm):
+        """field_solve="scan": index of the first step whose field failed its certificate, None if all passed (or if
+        another field solve is in use).  Collective: every rank calls it with its current local state."""
+        if self._scan is None:
+            return None
+        return self._scan.first_uncertified(self._adopt(local)[..., self.halo:self.halo + self.owned][:, 0], comm)
 
     # ---- one step, one process per rank ----
     def step(self, local: torch.Tensor, comm) -> torch.Tensor:
@@ -396,7 +520,9 @@ def step_emulated(solvers, locals_):
     for r in range(G):
         solvers[r]._slab_fn(curs[r], nxts[r])
     inner = [solvers[r].interior(nxts[r]) for r in range(G)]
-    if solvers[0]._dist is not None:
+    if solvers[0]._scan is not None:
+        scan_solve_emulated([s._scan for s in solvers], [i[:, 0] for i in inner], [i[:, 2] for i in inner])
+    elif solvers[0]._dist is not None:
         solve_emulated([s._dist for s in solvers], [i[:, 0] for i in inner], [i[:, 2] for i in inner])
     else:
         n_full = torch.cat([i[:, 0] for i in inner], dim=-1)

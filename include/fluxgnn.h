@@ -352,6 +352,30 @@ int fluxgnn_baseline_rollout_scan(const float* state_in, float* state_out, int B
                                   double cert_tol, void* workspace, int* first_uncertified,
                                   void* stream);
 
+/* ---- the scan solve on one slab of a domain-decomposed grid (north_star's "distributed
+ * Poisson reduction") ------------------------------------------------------------------------
+ * Rank r of `ranks` owns cells [r S, (r+1) S) of every IC (S % 8 == 0).  Per field solve:
+ *   1. fluxgnn_scan_slab_sums: the slab's sums into `msg` (B records of FLUXGNN_SCAN_MSG_BYTES);
+ *   2. the caller all-gathers the messages -> msg_all[ranks][B];
+ *   3. fluxgnn_scan_slab_field: E rows of the slab, the operator of src/baseline_solver.py:59-68 as
+ *      in fluxgnn_baseline_rollout_scan, certificate included: *first_uncertified (device int, set
+ *      to INT_MAX by the caller before step 0) receives step-1 if the field of the PREVIOUS call
+ *      had bound > cert_tol * max|E| (its sums travel in the messages); after the last step one
+ *      more sums + all-gather + fluxgnn_scan_slab_certify closes the record.
+ *   n / E: [B] rows, row strides n_ld / e_ld floats (views into the extended slab buffers).
+ *   workspace: fluxgnn_scan_slab_workspace_bytes(B, S) bytes, ZEROED by the caller once, then kept
+ *   across calls (it carries the certificate sums from one call to the next). */
+#define FLUXGNN_SCAN_MSG_BYTES 48
+int fluxgnn_scan_slab_supported(int B, int S);
+size_t fluxgnn_scan_slab_workspace_bytes(int B, int S);
+int fluxgnn_scan_slab_sums(const float* n, long long n_ld, int B, int S, long long j_base,
+                           void* workspace, void* msg, void* stream);
+int fluxgnn_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S,
+                            int rank, int ranks, double length, const void* msg_all, void* workspace,
+                            double cert_tol, int step, int* first_uncertified, void* stream);
+int fluxgnn_scan_slab_certify(int B, int S, int ranks, double length, const void* msg_all,
+                              double cert_tol, int step, int* first_uncertified, void* stream);
+
 /* ---- the reference's comparison models ---------------------------------------
  * PureGNN (scripts/training/train_pure_gnn.py:35-76), rolled out as in
  * scripts/evaluation/benchmark_timing.py:129-143: per step  state += PureGNN([n,u,E,x], ring edges).
