@@ -19,7 +19,7 @@
 // Because E is a function of n alone, the rollout keeps only (n, u) in HBM between steps: step s+1 reconstructs the field
 // of its input from n and the per-segment sums the previous launch left behind, so a step moves 16 bytes per cell
 // (read n, u; write n', u') instead of 24 + the transform passes.  Every grid is cut into contiguous segments, one
-// persistent CTA each; a 256-thread CTA streams its segment in 2048-cell chunks through a 3-stage shared-memory ring filled by 1-D
+// persistent CTA each; a 128-thread CTA streams its segment in 1024-cell chunks through a 4-stage shared-memory ring filled by 1-D
 // bulk copies (TMA, SASS UBLKCP) and carries the running prefix in a register.  No inter-CTA dependency inside a
 // launch: segment prefixes come from the records of the previous launch.
 #include <climits>
@@ -33,13 +33,22 @@ namespace fluxgnn {
 namespace {
 
 #ifndef FLUXGNN_SCAN_THREADS
-#define FLUXGNN_SCAN_THREADS 256
+#define FLUXGNN_SCAN_THREADS 128
 #endif
-constexpr int kScanThreads = FLUXGNN_SCAN_THREADS;     // 1024 threads per SM: 4 CTAs of 256 (smaller barrier domains than 2 x 512)
-constexpr int kScanCtasPerSm = 1024 / kScanThreads;
+// Measured at 2^24 cells x batch 8 (us per 2^24 cells): 512 threads x 2 CTAs per SM 59; 256 x 4 (64 registers: spills) 63;
+// 256 x 3 52.6; 384 x 2 58; 64 x 12 52; 128 x 6 49.9; 128 x 5, four stages 47.3 (5.67 TB/s on the 16 B/cell that move):
+// small barrier domains, 102 registers per thread, no spills.
+constexpr int kScanThreads = FLUXGNN_SCAN_THREADS;
+#ifndef FLUXGNN_SCAN_CTAS
+#define FLUXGNN_SCAN_CTAS 5
+#endif
+constexpr int kScanCtasPerSm = FLUXGNN_SCAN_CTAS;
 constexpr int kScanPer = 8;                                  // consecutive cells per thread
-constexpr int kScanChunk = kScanThreads * kScanPer;          // 2048 cells
-constexpr int kScanStages = 3;
+constexpr int kScanChunk = kScanThreads * kScanPer;          // 1024 cells
+#ifndef FLUXGNN_SCAN_STAGES
+#define FLUXGNN_SCAN_STAGES 4
+#endif
+constexpr int kScanStages = FLUXGNN_SCAN_STAGES;
 constexpr int kScanHalo = 4;                                 // staged halo cells per side (16 bytes)
 constexpr int kScanRow = kScanChunk + 2 * kScanHalo;         // floats per staged array
 
@@ -74,7 +83,6 @@ struct ScanSmem {
     float redf[kScanThreads / 32];
     double bc[4];            // broadcast: P_seg, rbar, mu, (unused)
     uint64_t full[kScanStages];
-    uint64_t empty[kScanStages];   // one arrival per warp once its loads of the stage have been performed
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -95,16 +103,15 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ic = (int)blockIdx.x / a.segs, seg = (int)blockIdx.x - ic * a.segs;
     const int nx = a.nx;
-    const long long seg_begin = (long long)seg * a.seg_chunks * kScanChunk;
-    long long seg_end = seg_begin + (long long)a.seg_chunks * kScanChunk;
-    if (seg_end > nx) seg_end = nx;
+    const int seg_begin = seg * a.seg_chunks * kScanChunk;              // cell indices fit an int (nx is one)
+    int seg_end = (int)min((long long)seg_begin + (long long)a.seg_chunks * kScanChunk, (long long)nx);
     const int nchunks = (int)((seg_end - seg_begin + kScanChunk - 1) / kScanChunk);
     const float* pn = a.in + (size_t)ic * 3 * nx;
     const float* pu = pn + nx;
     const float* pe = pu + nx;
 
     if (tid == 0) {
-        for (int s = 0; s < kScanStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], kScanThreads / 32); }
+        for (int s = 0; s < kScanStages; ++s) mbar_init(&S.full[s], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -112,10 +119,10 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
     // producer (thread 0): stage chunk k = cells [c0, c0 + len) plus 4 halo cells per side, periodic wrap applied here
     auto issue = [&](int k) {
         const int st = k % kScanStages;
-        const long long c0 = seg_begin + (long long)k * kScanChunk;
-        const int len = (int)((seg_end - c0 < kScanChunk) ? (seg_end - c0) : kScanChunk);
-        const long long left = (c0 == 0) ? nx - kScanHalo : c0 - kScanHalo;
-        const long long right = (c0 + len == nx) ? 0 : c0 + len;
+        const int c0 = seg_begin + k * kScanChunk;
+        const int len = (seg_end - c0 < kScanChunk) ? (seg_end - c0) : kScanChunk;
+        const int left = (c0 == 0) ? nx - kScanHalo : c0 - kScanHalo;
+        const int right = (c0 + len == nx) ? 0 : c0 + len;
         const uint32_t bytes = (uint32_t)(len + 2 * kScanHalo) * 4u;
         mbar_arrive_expect_tx(&S.full[st], (MODE == 2) ? bytes : 2 * bytes);
         bulk_g2s(&S.nbuf[st][0], pn + left, kScanHalo * 4, &S.full[st]);
@@ -179,12 +186,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
     double accS = 0.0, accM = 0.0;
     float accD = 0.f, accE = 0.f;
 
-    for (int k = 0; k < nchunks; ++k) {
-        const int st = k % kScanStages;
-        const long long c0 = seg_begin + (long long)k * kScanChunk;
-        const int len = (int)((seg_end - c0 < kScanChunk) ? (seg_end - c0) : kScanChunk);
-        const bool active = tid * kScanPer < len;
-        mbar_wait(&S.full[st], (uint32_t)((k / kScanStages) & 1));
+    int st = 0;                          // ring stage and phase parity of chunk k (k % kScanStages, (k / kScanStages) & 1)
+    uint32_t parity = 0;
+    int j0 = seg_begin + tid * kScanPer;                        // first cell of this thread inside the IC
+    for (int k = 0; k < nchunks; ++k, j0 += kScanChunk, st = (st + 1 == kScanStages) ? 0 : st + 1, parity ^= (st == 0)) {
+        const bool active = j0 < seg_end;
+        mbar_wait(&S.full[st], parity);
 
         float nv[kScanPer + 4], uv[kScanPer + 2];      // cells -2..9 of n, -1..8 of u relative to the thread's first cell
         if (active) {
@@ -230,17 +237,13 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
             if (lane == 31) S.wsum[k & 1][warp] = incl;
             excl32 = incl - t;
         }
-        // The stage may be refilled once every warp's loads from it have been PERFORMED, not merely issued: a block
-        // barrier alone does not order the in-flight loads against the bulk copy of the async proxy (measured: sporadic
-        // stale cells with four CTAs per SM).  Each warp therefore releases the stage through an mbarrier arrival, which
-        // is ordered behind its loads, and the producer waits for the eight arrivals before it issues the refill.
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[st]);
         __syncthreads();                 // warp totals visible
-        if (tid == 0 && k + kScanStages < nchunks) {
-            mbar_wait(&S.empty[st], (uint32_t)((k / kScanStages) & 1));
-            issue(k + kScanStages);
-        }
+        // Refill the stage of the PREVIOUS chunk.  A thread that has arrived here has issued every instruction of that
+        // chunk's arithmetic, and instructions issue in order with their operands ready, so its shared-memory loads from
+        // that stage have been performed.  Anything weaker races with the bulk copy of the async proxy: refilling THIS
+        // chunk's stage after the barrier (its loads are merely in flight), or releasing it through mbarrier arrivals
+        // issued behind the loads, both produced sporadic stale cells under scripts/stress_scan.py.
+        if (tid == 0 && k >= 1 && k - 1 + kScanStages < nchunks) issue(k - 1 + kScanStages);
         double base = 0.0;
         if (MODE != 0) {
             // every warp scans the warp totals itself (one lane each, fp64): no second block barrier
@@ -257,7 +260,6 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
         }
         if (!active) continue;
 
-        const long long j0 = c0 + (long long)tid * kScanPer;     // first cell of this thread inside the IC
         float ev[kScanPer];
         if (MODE == 0) {
             const float4 e0 = *reinterpret_cast<const float4*>(pe + j0), e1 = *reinterpret_cast<const float4*>(pe + j0 + 4);
