@@ -786,7 +786,7 @@ def test_distributed_field_solve_emulated(built_lib, world, nx, batch):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
-@pytest.mark.parametrize("world,nx,radius", [(1, 1 << 12, 2), (2, 1 << 12, 3), (4, 1 << 15, 3), (8, 1 << 15, 1)])
+@pytest.mark.parametrize("world,nx,radius", [(1, 1 << 12, 2), (2, 1 << 12, 3), (4, 1 << 15, 3), (8, 1 << 15, 1), (8, 1 << 20, 3)])
 def test_domain_decomposition_alltoall_emulated_ranks(model, weights, precision, world, nx, radius):
     """The default decomposition (distributed field solve) on G virtual ranks: n', u' of the first step are
     bit-identical to the undivided solver (same slab arithmetic, same inputs), E' agrees to rounding, and three

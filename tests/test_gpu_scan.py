@@ -201,7 +201,7 @@ def test_decomposed_scan_solve_reports_rough_density(built_lib):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
-@pytest.mark.parametrize("world,nx,radius", [(2, 1 << 12, 3), (4, 1 << 15, 2), (8, 1 << 15, 1)])
+@pytest.mark.parametrize("world,nx,radius", [(2, 1 << 12, 3), (4, 1 << 15, 2), (8, 1 << 15, 1), (8, 1 << 20, 3)])
 def test_hybrid_decomposed_scan_solve(precision, world, nx, radius):
     """BASELINE.json configs[3] scaled down: the hybrid step on G virtual ranks, halo exchange + distributed prefix-sum
     field solve, against the undivided solver (slabs start at halo = 4r+1 cells: the unaligned load path)."""
