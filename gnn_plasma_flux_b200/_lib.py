@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLUXGNN_LIB") or os.path.join(_HERE, "libfluxgnn.so")   # FLUXGNN_LIB: experiment builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_HOPS = 4
 MAX_LAYERS = 8
 HIDDEN = 128
@@ -117,11 +117,13 @@ def lib() -> ctypes.CDLL:
                 f"{LIB_PATH} not found: build it with `python -m gnn_plasma_flux_b200.build` "
                 "(nvcc, sm_100a). There is no CPU fallback.")
         handle = ctypes.CDLL(LIB_PATH)
+        handle.fluxgnn_abi_version.restype = c_int
+        if handle.fluxgnn_abi_version() != ABI_VERSION:          # checked first: a stale library lacks newer symbols
+            raise FluxGNNError(f"{LIB_PATH} has ABI version {handle.fluxgnn_abi_version()}, this package needs "
+                               f"{ABI_VERSION}: rebuild it with `python -m gnn_plasma_flux_b200.build`")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.fluxgnn_abi_version() != ABI_VERSION:
-            raise FluxGNNError("libfluxgnn.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib
 

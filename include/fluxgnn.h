@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FLUXGNN_ABI_VERSION 2
+#define FLUXGNN_ABI_VERSION 3
 
 #define FLUXGNN_OK        0
 #define FLUXGNN_EINVAL   -1   /* bad argument (shape, null pointer, unsupported size) */
