@@ -21,14 +21,46 @@ from . import _lib
 from .grid import PeriodicGrid
 
 
+_STAGING_MIN_BYTES = 1 << 18     # below this a pageable copy is as fast as staging through pinned memory
+_staging = {}                    # (device, nbytes, role) -> pinned uint8 buffer, reused across calls
+_staging_events = {}             # data_ptr of an input staging buffer -> event after its last host-to-device copy
+
+
+def _pinned(device, nbytes: int, role: str) -> torch.Tensor:
+    key = (str(device), nbytes, role)
+    buf = _staging.get(key)
+    if buf is None:
+        if len(_staging) >= 16:              # a handful of shapes at most; do not hoard pinned memory
+            torch.cuda.synchronize()
+            _staging.clear()
+            _staging_events.clear()
+        buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        _staging[key] = buf
+    return buf
+
+
 def _as_device_batch(state, device):
     """-> (tensor [B,3,nx] float32 contiguous on device, kind) with kind in
-    {'np1','npB','t1','tB'} describing how to hand the result back."""
+    {'np1','npB','t1','tB'} describing how to hand the result back.  Large numpy inputs travel through a reused
+    pinned staging buffer (one host memcpy + an asynchronous DMA instead of a pageable copy)."""
     if isinstance(state, np.ndarray):
         arr = np.ascontiguousarray(state, dtype=np.float32)
         kind = "np1" if arr.ndim == 2 else "npB"
-        t = torch.from_numpy(arr if arr.ndim == 3 else arr[None])
-        return t.to(device, non_blocking=False), kind
+        arr3 = arr if arr.ndim == 3 else arr[None]
+        dev = torch.device(device)
+        if dev.type == "cuda" and arr3.nbytes >= _STAGING_MIN_BYTES:
+            raw = _pinned(dev, arr3.nbytes, "in")
+            pin = raw.view(torch.float32).view(arr3.shape)
+            done = _staging_events.get(raw.data_ptr())
+            if done is not None:
+                done.synchronize()          # the previous call's DMA out of this buffer must be over before it is overwritten
+            pin.numpy()[...] = arr3
+            out = pin.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            _staging_events[raw.data_ptr()] = ev
+            return out, kind
+        return torch.from_numpy(arr3).to(device, non_blocking=False), kind
     if not torch.is_tensor(state):
         raise TypeError("state must be a numpy array or a torch tensor")
     kind = "t1" if state.dim() == 2 else "tB"
@@ -40,7 +72,15 @@ def _hand_back(t: torch.Tensor, kind: str, lead: int = 0):
     """Undo _as_device_batch; `lead` = number of leading (time) axes in front of [B,3,nx]."""
     if kind in ("np1", "t1"):
         t = t.select(lead, 0)
-    return t.cpu().numpy() if kind.startswith("np") else t
+    if not kind.startswith("np"):
+        return t
+    nbytes = t.numel() * t.element_size()
+    if t.is_cuda and t.dtype == torch.float32 and nbytes >= _STAGING_MIN_BYTES:
+        pin = _pinned(t.device, nbytes, "out").view(torch.float32).view(t.shape)
+        pin.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return pin.numpy().copy()           # a fresh array, as the reference returns
+    return t.cpu().numpy()
 
 
 class BaselineSolver:
