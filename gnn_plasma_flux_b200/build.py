@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfluxgnn.so")
-SOURCES = ["api.cu", "field_kernels.cu", "fft_poisson.cu", "scan_poisson.cu", "hybrid_kernel.cu", "hybrid_tc_kernel.cu", "hybrid_tc16_kernel.cu", "train_kernels.cu", "comparison_kernels.cu", "generic_kernels.cu"] + [f"hybrid_r{r}.cu" for r in range(5)] + [f"hybrid_train_r{r}.cu" for r in range(5)] + [f"hybrid_cluster_r{r}.cu" for r in range(1, 5)]
+SOURCES = ["api.cu", "field_kernels.cu", "fft_poisson.cu", "scan_poisson.cu", "hybrid_kernel.cu", "hybrid_tc_kernel.cu", "hybrid_tc16_kernel.cu", "train_kernels.cu", "comparison_kernels.cu", "generic_kernels.cu", "hybrid_latency_kernel.cu"] + [f"hybrid_r{r}.cu" for r in range(5)] + [f"hybrid_train_r{r}.cu" for r in range(5)] + [f"hybrid_cluster_r{r}.cu" for r in range(1, 5)]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -417,6 +417,19 @@ static int hybrid_rollout_impl(int precision, const void* packed, int num_layers
         a.traj = traj;
         a.diag = diag;
         a.steps = steps;
+        // Latency mode: with fewer tiles than cluster slots the tile kernel would use one SM per tile and leave the rest
+        // idle; a cluster of 8 CTAs per tile splits every layer's output features instead (bit-identical results).
+        // FLUXGNN_LATENCY=0 / 1 forces the choice (test hook).
+        if (precision == 0 && hybrid_latency_supported(a)) {
+            const char* env = getenv("FLUXGNN_LATENCY");
+            const bool forced = env != nullptr && env[0] == '1', off = env != nullptr && env[0] == '0';
+            const int slots = off ? 0 : hybrid_latency_max_clusters();
+            if (slots > 0 && (forced || a.num_tiles <= 2 * slots)) {
+                FLUXGNN_CUDA_OK(launch_hybrid_latency(a, a.num_tiles < slots ? a.num_tiles : slots, stream));
+                count_launch();
+                return FLUXGNN_OK;
+            }
+        }
         return launch_tiles(a, fast, stream);
     }
     if (diag != nullptr)

@@ -53,6 +53,12 @@ cudaError_t launch_hybrid_tiles(const HybridArgs& a, int fast_radius, int grid, 
 
 int hybrid_max_active_clusters(int csize);    // 0 when clusters of that size cannot be launched
 
+// Latency mode, hybrid_latency_kernel.cu: one whole-IC tile per cluster of 8 CTAs that split the output features; results
+// bit-identical to launch_hybrid_tiles.  For rollouts of fewer tiles than the device has cluster slots.
+int hybrid_latency_max_clusters();
+bool hybrid_latency_supported(const HybridArgs& a);
+cudaError_t launch_hybrid_latency(const HybridArgs& a, int clusters, cudaStream_t stream);
+
 // Tensor-core (tcgen05) variant, hybrid_tc_kernel.cu: radius 1..4, a.hops == 1, segments of 32/64/128 rows.
 cudaError_t launch_hybrid_tc_tiles(const HybridArgs& a, int radius, int grid, cudaStream_t stream);
 
