@@ -35,6 +35,7 @@ SIGNATURES = {
     "fluxgnn_abi_version": (c_int, []),
     "fluxgnn_last_error": (c_char_p, []),
     "fluxgnn_launch_count": (c_ulonglong, []),
+    "fluxgnn_latency_cluster_slots": (c_int, []),
     "fluxgnn_ffma_probe": (c_longlong, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fluxgnn_packed_weight_bytes": (c_size_t, [c_int]),
     "fluxgnn_pack_weights": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),

@@ -819,4 +819,7 @@ int fluxgnn_scan_slab_certify(int B, int S, int ranks, double length, const void
     return FLUXGNN_OK;
 }
 
+// Clusters of 8 CTAs the latency mode of fluxgnn_hybrid_rollout runs concurrently on the current device (0: unavailable).
+int fluxgnn_latency_cluster_slots(void) { return hybrid_latency_max_clusters(); }
+
 }  // extern "C"

@@ -12,13 +12,16 @@
 //   src/flux_gnn.py:63-66     edge readout           per-CTA partial dot products, exchanged as 2 x 128 floats per CTA
 //   src/hybrid_solver.py:45-58, src/baseline_solver.py:59-68   update and field solve: every CTA redundantly, CTA 0 writes
 //
-// A product thread (the first 128 of 256) owns TWO rows and the 8 features of one tx -- the weight operand is a warp-wide
-// broadcast, so two rows per thread halve its shared-memory traffic --, and every sum runs in the tile kernel's order (k = 0..127 per
-// accumulator; window sums hop by hop; the edge readout's chain over j, then the pair tx even + tx odd, then the
-// tile kernel's butterfly tree across the CTAs), so the result is BIT-IDENTICAL to hybrid_tile_kernel -- the tests
-// compare with torch.equal.  Weights: each CTA stages its 16 KiB slice of a layer (2 halves x 128 k x 16 columns) from
+// A product thread (the first 128 of 256) owns 4 consecutive rows and 4 features (j = 0..3 or 4..7 of one tx) of both halves:
+// 32 accumulators fed by three 128-bit shared-memory loads per k (the product is bound by the shared-memory return path,
+// and a 4 x 4 tile needs the fewest operand bytes per multiply-add).  Every sum runs in the tile kernel's order (k = 0..127
+// per accumulator; window sums hop by hop; the edge readout's chain over j -- handed from the j < 4 lane to its j >= 4
+// neighbour by a shuffle --, then the pair tx even + tx odd, then the tile kernel's butterfly tree across the CTAs), so
+// the result is BIT-IDENTICAL to hybrid_tile_kernel -- the tests compare with torch.equal.  Weights: each CTA stages its 16 KiB slice of a layer (2 halves x 128 k x 16 columns) from
 // the packed stream (L2-resident) into shared memory, the next layer's slice is prefetched into registers under the
 // current product.
+#include <cstdio>
+
 #include "common.cuh"
 #include "hybrid_kernel.cuh"
 #include "tile_common.cuh"
@@ -27,17 +30,26 @@ namespace fluxgnn {
 
 namespace {
 
+#ifdef FLUXGNN_LAT_TIMING
+#define LAT_TICK(slot) do { if (tid == 0 && blockIdx.x == 0) { const long long n__ = clock64(); lat_t[slot] += n__ - lat_last; lat_last = n__; } } while (0)
+#else
+#define LAT_TICK(slot) do {} while (0)
+#endif
+
+#ifndef FLUXGNN_LAT_UNROLL
+#define FLUXGNN_LAT_UNROLL 8          // clk per k-step of the product: unroll 4: 66, 8: 60, 16: 58 (floor of the shared-memory return path: 48)
+#endif
+constexpr int kLatUnroll = FLUXGNN_LAT_UNROLL;
 constexpr int kLatCluster = 8;
 constexpr int kLatThreads = 256;
 constexpr int kLatFeat = kH / kLatCluster;        // 16 output features per CTA
-constexpr int kLatMaxR = 8;                       // neighbour rows kept in registers; larger radii are not dispatched here
+constexpr int kLatMaxR = 4;                       // neighbour rows kept in registers; larger radii are not dispatched here
 
 struct __align__(128) LatSmem {
     float Hs[2][kH * kTileRows];                  // activations [buffer][feature][row], a complete copy in every CTA
     float Zs[kLatFeat * kTileRows];               // neighbour half of this CTA's features [local feature][row]
     float Wl[2][2][kH][kLatFeat];                 // weight slice [buffer][half: 0 = neighbour/col, 1 = self/row][k][column]
     float edge_all[kLatCluster][2][kTileRows];    // per source CTA: fwd / bwd partial sums (tx even + tx odd) of every row
-    float pair[2][kTileRows];                     // tx odd -> tx even hand-over of the edge readout
     float sN[kTileRows], sU[kTileRows], sE[kTileRows], sX[kTileRows];
     float sF[kTileRows], sRho[kTileRows];
     double gtab[kTileRows];
@@ -47,16 +59,19 @@ struct __align__(128) LatSmem {
 };
 static_assert(sizeof(LatSmem) <= 227 * 1024, "latency tile does not fit shared memory");
 
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const HybridArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LatSmem& S = *reinterpret_cast<LatSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const bool gemm = tid < kTileRows;                     // product / epilogue threads: rows r0 and r0 + 64, thread column txl
-    const int r0 = tid & 63, txl = (tid >> 6) & 1;
+    const bool gemm = tid < kTileRows;                     // product / epilogue threads
+    const int lane = tid & 31;
+    const int rg = ((tid >> 5) & 3) * 8 + (lane >> 2);    // rows 4 rg .. 4 rg + 3
+    const int txl = (lane >> 1) & 1, jh = lane & 1;        // thread column txl, features j = 4 jh .. 4 jh + 3 of it
+    const int R0 = 4 * rg;
     const int row = tid & (kTileRows - 1);                 // the row a thread looks after outside the products
     const int crank = (int)cluster_ctarank();
     const int tx = 2 * crank + txl;                        // the tile kernel's thread column whose 8 features this thread owns
@@ -95,16 +110,19 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
         }
     };
     cluster_sync_all();                                    // every CTA of the cluster is running before remote stores start
+#ifdef FLUXGNN_LAT_TIMING
+    long long lat_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lat_last = clock64();
+#endif
 
     for (int tile = first_tile; tile < a.num_tiles; tile += tile_stride) {
         if (tid < kTileRows) tile_load_row(a, T, tile, true, tid, tid, 0, kTileRows);
         fetch_weights(0);
         __syncthreads();
-        // neighbour rows of this thread's two rows, hop by hop (periodic inside the IC)
-        int rp[2][kLatMaxR], rm[2][kLatMaxR];
+        // neighbour rows of this thread's four rows, hop by hop (periodic inside the IC)
+        int rp[4][kLatMaxR], rm[4][kLatMaxR];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            int p = r0 + 64 * q, m = r0 + 64 * q;
+        for (int q = 0; q < 4; ++q) {
+            int p = R0 + q, m = R0 + q;
 #pragma unroll
             for (int k = 0; k < kLatMaxR; ++k) {
                 if (k < radius) { p = S.nextRow[p]; m = S.prevRow[m]; }
@@ -116,16 +134,27 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
             // ---- input MLP (src/flux_gnn.py:49): all 128 features of this thread's row, 64 per thread ----
             {
                 const float fn = S.sN[row], fu = S.sU[row], fe = S.sE[row], fx = S.sX[row];
-                for (int f = (tid >> 7) * 64; f < (tid >> 7) * 64 + 64; ++f) {
-                    float v = fmaf(__ldg(a.packed + SmallParams::w_in + 0 * kH + f), fn, __ldg(a.packed + SmallParams::b_in + f));
-                    v = fmaf(__ldg(a.packed + SmallParams::w_in + 1 * kH + f), fu, v);
-                    v = fmaf(__ldg(a.packed + SmallParams::w_in + 2 * kH + f), fe, v);
-                    v = fmaf(__ldg(a.packed + SmallParams::w_in + 3 * kH + f), fx, v);
-                    S.Hs[0][f * kTileRows + row] = fmaxf(v, 0.f);
+                const float4* w4 = reinterpret_cast<const float4*>(a.packed + SmallParams::w_in);
+                const float4* b4 = reinterpret_cast<const float4*>(a.packed + SmallParams::b_in);
+                for (int g = (tid >> 7) * 16; g < (tid >> 7) * 16 + 16; ++g) {        // four features per iteration
+                    const float4 w0 = __ldg(w4 + g), w1 = __ldg(w4 + kH / 4 + g), w2 = __ldg(w4 + 2 * (kH / 4) + g),
+                                 w3 = __ldg(w4 + 3 * (kH / 4) + g), b = __ldg(b4 + g);
+                    const float wv[4][4] = {{w0.x, w1.x, w2.x, w3.x}, {w0.y, w1.y, w2.y, w3.y}, {w0.z, w1.z, w2.z, w3.z},
+                                            {w0.w, w1.w, w2.w, w3.w}};
+                    const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v = fmaf(wv[i][0], fn, bv[i]);
+                        v = fmaf(wv[i][1], fu, v);
+                        v = fmaf(wv[i][2], fe, v);
+                        v = fmaf(wv[i][3], fx, v);
+                        S.Hs[0][(4 * g + i) * kTileRows + row] = fmaxf(v, 0.f);
+                    }
                 }
             }
             store_weights(0);                              // layer 0's slice (fetched before the step / under the last layer)
             __syncthreads();
+            LAT_TICK(0);
 
             int cur = 0;
             for (int layer = 0; layer <= a.L; ++layer, cur ^= 1) {
@@ -134,94 +163,114 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
                 if (layer < a.L) fetch_weights(layer + 1);
                 else if (step + 1 < a.steps) fetch_weights(0);
                 const float* bias = a.packed + (layer < a.L ? SmallParams::b_upd + layer * kH : SmallParams::b_e1);
-                float accZ[2][8], accY[2][8];
+                float accZ[4][4], accY[4][4];              // [row][feature jj]
                 if (gemm) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float b = __ldg(bias + tx + 16 * j);
-                        accZ[0][j] = 0.f; accZ[1][j] = 0.f; accY[0][j] = b; accY[1][j] = b;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float b = __ldg(bias + tx + 16 * (4 * jh + jj));
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { accZ[q][jj] = 0.f; accY[q][jj] = b; }
                     }
-                    const float* hrow = &S.Hs[cur][r0];
-                    const float* wz = &S.Wl[wb][0][0][txl * 8];
-                    const float* wy = &S.Wl[wb][1][0][txl * 8];
-#pragma unroll 4
+                    const float* hrow = &S.Hs[cur][R0];
+                    const float* wz = &S.Wl[wb][0][0][txl * 8 + jh * 4];
+                    const float* wy = &S.Wl[wb][1][0][txl * 8 + jh * 4];
+#pragma unroll kLatUnroll
                     for (int k = 0; k < kH; ++k) {
-                        const float h0 = hrow[k * kTileRows], h1 = hrow[k * kTileRows + 64];
-                        const float4 z0 = *reinterpret_cast<const float4*>(wz + k * kLatFeat);
-                        const float4 z1 = *reinterpret_cast<const float4*>(wz + k * kLatFeat + 4);
-                        const float4 y0 = *reinterpret_cast<const float4*>(wy + k * kLatFeat);
-                        const float4 y1 = *reinterpret_cast<const float4*>(wy + k * kLatFeat + 4);
-                        const float wzv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-                        const float wyv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+                        const float4 h = *reinterpret_cast<const float4*>(hrow + k * kTileRows);
+                        const float4 z = *reinterpret_cast<const float4*>(wz + k * kLatFeat);
+                        const float4 y = *reinterpret_cast<const float4*>(wy + k * kLatFeat);
+                        const float hv[4] = {h.x, h.y, h.z, h.w}, zv[4] = {z.x, z.y, z.z, z.w}, yv[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            accZ[0][j] = fmaf(h0, wzv[j], accZ[0][j]); accZ[1][j] = fmaf(h1, wzv[j], accZ[1][j]);
-                            accY[0][j] = fmaf(h0, wyv[j], accY[0][j]); accY[1][j] = fmaf(h1, wyv[j], accY[1][j]);
-                        }
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                accZ[q][jj] = fmaf(hv[q], zv[jj], accZ[q][jj]);
+                                accY[q][jj] = fmaf(hv[q], yv[jj], accY[q][jj]);
+                            }
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        S.Zs[(txl * 8 + j) * kTileRows + r0] = accZ[0][j];
-                        S.Zs[(txl * 8 + j) * kTileRows + r0 + 64] = accZ[1][j];
-                    }
+                    for (int jj = 0; jj < 4; ++jj)
+                        *reinterpret_cast<float4*>(&S.Zs[(txl * 8 + 4 * jh + jj) * kTileRows + R0]) =
+                            make_float4(accZ[0][jj], accZ[1][jj], accZ[2][jj], accZ[3][jj]);
                 }
                 if (layer < a.L) store_weights(wb ^ 1);    // nobody reads that buffer during this layer
                 __syncthreads();                           // Z of this CTA's features complete
+                LAT_TICK(1);
 
                 if (layer < a.L) {
                     // ---- h' = relu(Y + mean_{|k|<=r, k!=0} Z_{i+k})  (src/flux_gnn.py:55-60) into buffer cur^1 of every CTA ----
                     if (gemm) {
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const uint32_t off0 = (uint32_t)(((cur ^ 1) * kH * kTileRows + r0 + 64 * q) * 4);
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const float* zr = &S.Zs[(txl * 8 + 4 * jh + jj) * kTileRows];
+                            float hq[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float* zr = &S.Zs[(txl * 8 + j) * kTileRows];
+                            for (int q = 0; q < 4; ++q) {
                                 float s = zr[rp[q][0]] + zr[rm[q][0]];
 #pragma unroll
                                 for (int k = 1; k < kLatMaxR; ++k)
                                     if (k < radius) { s += zr[rp[q][k]]; s += zr[rm[q][k]]; }
-                                const float h = fmaxf(fmaf(s, inv_deg, accY[q][j]), 0.f);
-                                const uint32_t off = off0 + (uint32_t)((tx + 16 * j) * kTileRows * 4);
-#pragma unroll
-                                for (int p = 0; p < kLatCluster; ++p) st_cluster_f32(peer_hs[p] + off, h);
+                                hq[q] = fmaxf(fmaf(s, inv_deg, accY[q][jj]), 0.f);
                             }
+                            const uint32_t off = (uint32_t)((((cur ^ 1) * kH + tx + 16 * (4 * jh + jj)) * kTileRows + R0) * 4);
+                            const float4 hv = make_float4(hq[0], hq[1], hq[2], hq[3]);
+#pragma unroll
+                            for (int p = 0; p < kLatCluster; ++p) st_cluster_f4(peer_hs[p] + off, hv);
                         }
                     }
+                    LAT_TICK(2);
                     cluster_sync_all();                    // every CTA holds the complete h'; Zs is free again
+                    LAT_TICK(3);
                 } else {
-                    // ---- edge readout (src/flux_gnn.py:63-66): accY = P + b1, Zs = Q; hop 1 only ----
-                    float pf[2] = {0.f, 0.f}, pb[2] = {0.f, 0.f};
+                    // ---- edge readout (src/flux_gnn.py:63-66): accY = P + b1, Zs = Q; hop 1 only.  The tile kernel sums
+                    // w2 relu(.) over j = 0..7 in one chain per (row, tx): the j < 4 lane runs its half and hands the sum to
+                    // its j >= 4 neighbour, which continues the chain ----
                     if (gemm) {
+                        float w2[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float w2 = __ldg(a.packed + SmallParams::w_e2 + tx + 16 * j);
-                            const float* zr = &S.Zs[(txl * 8 + j) * kTileRows];
+                        for (int jj = 0; jj < 4; ++jj) w2[jj] = __ldg(a.packed + SmallParams::w_e2 + tx + 16 * (4 * jh + jj));
+                        float pf[4], pb[4];
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                pf[q] = fmaf(w2, fmaxf(accY[q][j] + zr[rp[q][0]], 0.f), pf[q]);
-                                pb[q] = fmaf(w2, fmaxf(accY[q][j] + zr[rm[q][0]], 0.f), pb[q]);
+                        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                // pass 0: chains seeded with 0 (final for the j < 4 lanes); pass 1: the j >= 4 lanes redo theirs
+                                // seeded with the neighbour's result
+                                float sf = 0.f, sb = 0.f;
+                                if (pass == 1) {
+                                    sf = __shfl_xor_sync(0xffffffffu, pf[q], 1);
+                                    sb = __shfl_xor_sync(0xffffffffu, pb[q], 1);
+                                }
+                                if (pass == 0 || jh == 1) {
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) {
+                                        const float* zr = &S.Zs[(txl * 8 + 4 * jh + jj) * kTileRows];
+                                        sf = fmaf(w2[jj], fmaxf(accY[q][jj] + zr[rp[q][0]], 0.f), sf);
+                                        sb = fmaf(w2[jj], fmaxf(accY[q][jj] + zr[rm[q][0]], 0.f), sb);
+                                    }
+                                    pf[q] = sf; pb[q] = sb;
+                                }
                             }
                         }
-                        if (txl == 1) {
-                            S.pair[0][r0] = pf[0]; S.pair[0][r0 + 64] = pf[1];
-                            S.pair[1][r0] = pb[0]; S.pair[1][r0 + 64] = pb[1];
-                        }
-                    }
-                    __syncthreads();
-                    if (gemm && txl == 0) {
+                        // the complete sums of a thread column sit in its j >= 4 lane; tx even + tx odd, then to every CTA
+                        float cf[4], cb[4];
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int r = r0 + 64 * q;
-                            const float cf = pf[q] + S.pair[0][r], cb = pb[q] + S.pair[1][r];      // tx even + tx odd
+                        for (int q = 0; q < 4; ++q) {
+                            cf[q] = pf[q] + __shfl_xor_sync(0xffffffffu, pf[q], 2);
+                            cb[q] = pb[q] + __shfl_xor_sync(0xffffffffu, pb[q], 2);
+                        }
+                        if (txl == 0 && jh == 1) {
+                            const float4 f4 = make_float4(cf[0], cf[1], cf[2], cf[3]), b4 = make_float4(cb[0], cb[1], cb[2], cb[3]);
 #pragma unroll
                             for (int p = 0; p < kLatCluster; ++p) {
-                                st_cluster_f32(peer_edge[p] + (uint32_t)(r * 4), cf);
-                                st_cluster_f32(peer_edge[p] + (uint32_t)((kTileRows + r) * 4), cb);
+                                st_cluster_f4(peer_edge[p] + (uint32_t)(R0 * 4), f4);
+                                st_cluster_f4(peer_edge[p] + (uint32_t)((kTileRows + R0) * 4), b4);
                             }
                         }
                     }
+                    LAT_TICK(4);
                     cluster_sync_all();
+                    LAT_TICK(3);
                 }
             }   // layers
 
@@ -255,11 +304,17 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
             }
             __syncthreads();
             if (crank == 0 && tid < kTileRows) tile_write_out_row(a, T, tid, step);
+            LAT_TICK(5);
             // the next step's first cluster barrier comes after its first product; edge_all is rewritten only after four more
         }   // steps
         __syncthreads();
     }       // tiles
     cluster_sync_all();                                    // shared memory must outlive the peers' remote stores
+#ifdef FLUXGNN_LAT_TIMING
+    if (tid == 0 && blockIdx.x == 0)
+        printf("[latency timing] clk per step: input %lld, products %lld, node epilogue + push %lld, cluster barriers %lld, edge readout %lld, update + field %lld\n",
+               lat_t[0] / a.steps, lat_t[1] / a.steps, lat_t[2] / a.steps, lat_t[3] / a.steps, lat_t[4] / a.steps, lat_t[5] / a.steps);
+#endif
 }
 
 }  // namespace

@@ -330,6 +330,13 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out,
                              int steps, int record_every, float* traj,
                              float* flux_n, void* workspace, void* stream);
 
+/* Latency mode of fluxgnn_hybrid_rollout (fp32 kernel, whole-IC tiles, radius <= 4): when a rollout has at most twice as
+ * many 128-row tiles as the device has cluster slots, every tile is computed by a cluster of 8 CTAs that split the
+ * output features of each layer (csrc/hybrid_latency_kernel.cu) -- bit-identical results, ~3x lower time per step for the
+ * reference's own timing protocol of one 64-cell IC (scripts/evaluation/benchmark_timing.py:63-72).
+ * FLUXGNN_LATENCY=0 / 1 in the environment forces the choice. */
+int fluxgnn_latency_cluster_slots(void);
+
 /* ---- classical rollout with the field solve as a certified prefix sum ("scan solve") -----------
  * The same step as fluxgnn_baseline_rollout (src/baseline_solver.py:80-101) for long grids
  * (fluxgnn_baseline_scan_supported: nx >= 4096, nx % 8 == 0).  The operator of

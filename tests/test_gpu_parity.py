@@ -1164,3 +1164,51 @@ def test_integration_md_stub_runs(model, tmp_path):
     ours = make_solver(model, 64, 5e-3).run(ic, n_steps=12)
     assert got.shape == (13, 3, 64) and got.dtype == np.float32
     np.testing.assert_array_equal(got, ours)
+
+
+# ----------------------------------------------------------------------------- latency mode (cluster of 8 CTAs per tile)
+@pytest.mark.parametrize("nx,B,radius,steps", [(64, 1, 1, 50), (64, 20, 1, 30), (64, 5, 3, 4), (32, 7, 2, 5), (128, 3, 4, 3),
+                                               (40, 4, 1, 5), (36, 3, 2, 4), (64, 70, 3, 3)])
+def test_latency_mode_is_bit_identical(model, monkeypatch, nx, B, radius, steps):
+    """csrc/hybrid_latency_kernel.cu: a cluster of 8 CTAs per whole-IC tile splits every layer's output features and keeps
+    every sum in the tile kernel's order, so trajectories must be bit-identical to the tile kernel (FLUXGNN_LATENCY=0):
+    the reference's timing protocol (1 IC x 64 cells x 50 steps), C1 (20 ICs x 30 steps), several ICs per tile, grids that
+    take the generic neighbour walk (36, 40 cells), radius 4, and more tiles than cluster slots (B = 70)."""
+    from gnn_plasma_flux_b200 import _lib
+    from gnn_plasma_flux_b200.synthetic import stable_initial_conditions
+    if _lib.lib().fluxgnn_latency_cluster_slots() < 1:
+        pytest.skip("clusters of 8 CTAs with 180 KB of shared memory are not launchable on this device")
+    sol = make_solver(model, nx, 1e-3, graph_radius=radius)
+    state = stable_initial_conditions(sol.baseline, B)
+    monkeypatch.setenv("FLUXGNN_LATENCY", "0")
+    want, want_traj = sol.rollout(state, steps, record_every=1)
+    monkeypatch.setenv("FLUXGNN_LATENCY", "1")
+    before = _lib.launch_count()
+    got, got_traj = sol.rollout(state, steps, record_every=1)
+    assert _lib.launch_count() - before == 1                        # the whole rollout is one cluster launch
+    monkeypatch.delenv("FLUXGNN_LATENCY")
+    assert torch.isfinite(got).all()
+    assert torch.equal(got, want) and torch.equal(got_traj, want_traj)
+    if B <= 20:                                                     # the default dispatch picks it for few tiles
+        auto, _ = sol.rollout(state, steps)
+        assert torch.equal(auto, want)
+
+
+def test_latency_mode_diagnostics_and_reference_api(model, monkeypatch):
+    """In-kernel diagnostics and the numpy API through the latency mode equal the tile kernel's."""
+    from gnn_plasma_flux_b200 import _lib
+    if _lib.lib().fluxgnn_latency_cluster_slots() < 1:
+        pytest.skip("clusters of 8 CTAs are not launchable on this device")
+    sol = make_solver(model, 64, 5e-3)
+    ics = np.stack([sol.baseline.initial_condition(seed=s) for s in range(3)])
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FLUXGNN_LATENCY", mode)
+        final, diag = sol.rollout_diagnostics(torch.from_numpy(ics).cuda(), 12)
+        out[mode] = (sol.run(ics[0], n_steps=20), sol.run(ics, n_steps=5), final.cpu().numpy(),
+                     {k: v.cpu().numpy() for k, v in diag.items()})
+    monkeypatch.delenv("FLUXGNN_LATENCY")
+    for i in range(3):
+        np.testing.assert_array_equal(out["0"][i], out["1"][i])
+    for k in out["0"][3]:
+        np.testing.assert_array_equal(out["0"][3][k], out["1"][3][k])
