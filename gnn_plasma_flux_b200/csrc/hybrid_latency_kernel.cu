@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
                             for (int p = 0; p < kLatCluster; ++p) st_cluster_f4(peer_hs[p] + off, hv);
                         }
                     }
+                    // (tried: slice to local shared memory first, then all eight warps copy it to the peers -- slower, 14.5 k + 8.0 k
+                    //  of barrier instead of 13.0 k + 5.8 k clk per step: the pushes are bound by the SM's egress, not by issue)
                     LAT_TICK(2);
                     cluster_sync_all();                    // every CTA holds the complete h'; Zs is free again
                     LAT_TICK(3);
