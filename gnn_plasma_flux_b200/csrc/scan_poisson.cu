@@ -465,16 +465,23 @@ __global__ void __launch_bounds__(kSlabThreads) slab_sums_kernel(const float* __
     }
 }
 
+// one warp per IC; lane l sums the records l, l + 32, ..., then a fixed butterfly: deterministic, and 32 loads in flight
+// instead of a serial chain of `segs` dependent ones (16 us at 74 segments)
 __global__ void slab_msg_kernel(const float* __restrict__ n, long long n_ld, int S, int segs, const SlabSeg* __restrict__ seg_rec,
                                 SlabMsg* __restrict__ msg) {
-    const int ic = blockIdx.x;
-    if (threadIdx.x != 0) return;
-    SlabMsg m;
-    m.S = 0.0; m.M1 = 0.0; m.D4 = 0.0; m.maxE = 0.f; m.pad = 0.f;
-    for (int s = 0; s < segs; ++s) {
-        const SlabSeg r = seg_rec[(size_t)ic * segs + s];
-        m.S += r.S; m.M1 += r.M1; m.D4 += r.D4; m.maxE = fmaxf(m.maxE, r.maxE);
+    const int ic = blockIdx.x, lane = threadIdx.x;
+    double s = 0.0, m1 = 0.0, d4 = 0.0;
+    float em = 0.f;
+    for (int q = lane; q < segs; q += 32) {
+        const SlabSeg r = seg_rec[(size_t)ic * segs + q];
+        s += r.S; m1 += r.M1; d4 += r.D4; em = fmaxf(em, r.maxE);
     }
+    s = warp_sum(s); m1 = warp_sum(m1); d4 = warp_sum(d4);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) em = fmaxf(em, __shfl_xor_sync(0xffffffffu, em, o));
+    if (lane != 0) return;
+    SlabMsg m;
+    m.S = s; m.M1 = m1; m.D4 = d4; m.maxE = em; m.pad = 0.f;
     const float* row = n + (size_t)ic * n_ld;
     m.edge[0] = row[0]; m.edge[1] = row[1]; m.edge[2] = row[S - 2]; m.edge[3] = row[S - 1];
     msg[ic] = m;
@@ -504,15 +511,31 @@ __global__ void __launch_bounds__(kSlabThreads) slab_field_kernel(const SlabFiel
     long long end = begin + (long long)a.seg_chunks * kSlabChunk;
     if (end > S) end = S;
 
-    // ---- prologue (every thread, same order everywhere): totals over the ranks, prefix of ranks and segments before ----
+    // ---- prologue: totals over the ranks, prefix of the ranks and segments before (parallel loads, fixed reduction order) ----
     double s_tot = 0.0, m_tot = 0.0, d_tot = 0.0, P = 0.0;
     float e_max = 0.f;
-    for (int g = 0; g < a.ranks; ++g) {
-        const SlabMsg& m = a.msg_all[(size_t)g * a.B + ic];
-        s_tot += m.S; m_tot += m.M1; d_tot += m.D4; e_max = fmaxf(e_max, m.maxE);
-        if (g < a.rank) P += m.S;
+    {
+        double v_s = 0.0, v_m = 0.0, v_d = 0.0, v_p = 0.0;
+        float v_e = 0.f;
+        for (int g = tid; g < a.ranks; g += kSlabThreads) {
+            const SlabMsg& m = a.msg_all[(size_t)g * a.B + ic];
+            v_s += m.S; v_m += m.M1; v_d += m.D4; v_e = fmaxf(v_e, m.maxE);
+            if (g < a.rank) v_p += m.S;
+        }
+        for (int q = tid; q < seg; q += kSlabThreads) v_p += a.seg_rec[(size_t)ic * a.segs + q].S;
+        v_s = warp_sum(v_s); v_m = warp_sum(v_m); v_d = warp_sum(v_d); v_p = warp_sum(v_p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v_e = fmaxf(v_e, __shfl_xor_sync(0xffffffffu, v_e, o));
+        __shared__ double pro[4][kSlabThreads / 32];
+        __shared__ float prof[kSlabThreads / 32];
+        if (lane == 0) { pro[0][warp] = v_s; pro[1][warp] = v_m; pro[2][warp] = v_d; pro[3][warp] = v_p; prof[warp] = v_e; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kSlabThreads / 32; ++w) {
+            s_tot += pro[0][w]; m_tot += pro[1][w]; d_tot += pro[2][w]; P += pro[3][w];
+            e_max = fmaxf(e_max, prof[w]);
+        }
     }
-    for (int s = 0; s < seg; ++s) P += a.seg_rec[(size_t)ic * a.segs + s].S;
     const double N = (double)S * (double)a.ranks;
     const double rbar = s_tot / N, mu = 0.5 * s_tot - m_tot / N - s_tot / (2.0 * N);
     if (seg == 0 && tid == 0 && a.step > 0) {              // certificate of the field of the previous call

@@ -3,7 +3,9 @@
     python scripts/profile_run.py c3 [precision]     8192 ICs x 1024 cells, radius 2 (configs[2], the per-GPU share at 8 GPUs)
     python scripts/profile_run.py c5 [batch]         classical solver, 2^24 cells, 4-step rollout (configs[4])
     python scripts/profile_run.py dist               distributed field solve, 8 virtual ranks x 2^21 cells x batch 8 (configs[3])
-    python scripts/profile_run.py generic            FluxGNN(4, 64, 3) hybrid step, 4096 ICs x 64 cells"""
+    python scripts/profile_run.py generic            FluxGNN(4, 64, 3) hybrid step, 4096 ICs x 64 cells
+    python scripts/profile_run.py latency            latency mode: 1 IC x 64 cells x 50 steps (the reference's timing protocol)
+    python scripts/profile_run.py slabscan           distributed prefix-sum field solve, 8 virtual ranks x 2^21 cells x batch 8"""
 import os
 import sys
 
@@ -46,6 +48,21 @@ elif what == "generic":
     state = stable_initial_conditions(sol.baseline, 4096, distinct=64)
     for _ in range(3):
         state, _ = sol.rollout(state, 1)
+elif what == "latency":
+    sol = HybridSolver(None, 1, nx=64, dt=5e-3, device=dev, model=seeded_model(0, dev))
+    state = stable_initial_conditions(sol.baseline, 1)
+    for _ in range(3):
+        state, _ = sol.rollout(state, 50)
+elif what == "slabscan":
+    from gnn_plasma_flux_b200.domain import DistributedScanSolve, scan_solve_emulated
+    G, S, B = 8, 1 << 21, 8
+    nx = G * S
+    n = 1.0 + 0.1 * torch.sin(torch.arange(nx, device=dev, dtype=torch.float32) * (2 * np.pi * 3 / nx)).repeat(B, 1)
+    E = torch.zeros_like(n)
+    solvers = [DistributedScanSolve(nx, 2 * np.pi, rk, G, dev) for rk in range(G)]
+    for _ in range(2):
+        scan_solve_emulated(solvers, [n[:, k * S:(k + 1) * S] for k in range(G)], [E[:, k * S:(k + 1) * S] for k in range(G)])
+    state = E
 else:
     raise SystemExit(__doc__)
 torch.cuda.synchronize()
