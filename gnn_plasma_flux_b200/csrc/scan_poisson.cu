@@ -648,7 +648,7 @@ __global__ void slab_certify_kernel(const SlabMsg* __restrict__ msg_all, int B, 
 }  // namespace
 
 bool baseline_scan_supported(int B, int nx) {
-    return nx >= 4096 && (nx % kScanPer) == 0 && B >= 1 && B <= 4096;
+    return nx >= 4096 && nx <= (1 << 30) && (nx % kScanPer) == 0 && B >= 1 && B <= 4096;      // cell indices are ints
 }
 
 size_t baseline_scan_workspace_bytes(int B, int nx, int sms) {
