@@ -190,43 +190,83 @@ class BaselineSolver:
             return (state.clone(), state.new_empty((0, B, 3, nx)) if record_every else None,
                     state.new_empty((0, B, nx)) if record_flux else None)
         L = _lib.lib()
-        scalars = (self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)))
         with torch.cuda.device(dev):
-            out = torch.empty_like(state)
             traj = (torch.empty(n_steps // record_every, B, 3, nx, dtype=torch.float32, device=dev)
                     if record_every else None)
             flux = torch.empty(n_steps, B, nx, dtype=torch.float32, device=dev) if record_flux else None
-            stream = torch.cuda.current_stream(dev).cuda_stream
             scan_ok = bool(L.fluxgnn_baseline_scan_supported(B, nx))
             if mode == "scan" and not scan_ok:
                 raise _lib.FluxGNNError(f"field_solve='scan' needs nx >= 4096 and nx % 8 == 0 (B={B}, nx={nx})")
-            if mode != "spectral" and scan_ok:
-                work = torch.empty(L.fluxgnn_baseline_scan_workspace_bytes(B, nx) // 4, dtype=torch.float32, device=dev)
-                flag = torch.empty(1, dtype=torch.int32, device=dev)
-                _lib.check(L.fluxgnn_baseline_rollout_scan(
-                    state.data_ptr(), out.data_ptr(), B, nx, self.length, *scalars, n_steps, max(record_every, 1),
-                    traj.data_ptr() if traj is not None else None, flux.data_ptr() if flux is not None else None,
-                    self.cert_tol, work.data_ptr(), flag.data_ptr(), stream), "fluxgnn_baseline_rollout_scan")
-                first_bad = int(flag.item())          # 4-byte read-back: was every reconstructed field certified?
-                self.last_uncertified_step = None if first_bad == 2 ** 31 - 1 else first_bad
-                if self.last_uncertified_step is None:
-                    self.last_field_solve = "scan"
-                    return out, traj, flux
-                if mode == "scan":
-                    raise _lib.FluxGNNError(
-                        f"field_solve='scan': the field of step {first_bad} is not certified to cert_tol={self.cert_tol:g} "
-                        "(rough density or short grid); use field_solve='auto' or 'spectral'")
-                del work                              # "auto": repeat with the FFT solve
-            _, gtab = self.grid.tables(dev)
-            ws_bytes = L.fluxgnn_baseline_workspace_bytes(B, nx)
-            work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
-            _lib.check(L.fluxgnn_baseline_rollout(
-                state.data_ptr(), out.data_ptr(), gtab.data_ptr() if gtab is not None else None, B, nx, self.length,
-                *scalars, n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
-                flux.data_ptr() if flux is not None else None,
-                work.data_ptr() if work is not None else None, stream), "fluxgnn_baseline_rollout")
-            self.last_field_solve = "spectral"
-        return out, traj, flux
+            if mode == "spectral" or not scan_ok:
+                out = self._rollout_spectral(state, n_steps, record_every, traj, flux)
+                self.last_field_solve, self.last_uncertified_step = "spectral", None
+                return out, traj, flux
+            # "auto" / "scan".  The rounding noise of n grows like the square root of the step count and with it the
+            # (conservative) certificate bound, so a long "auto" rollout is cut into chunks: a chunk whose certificate
+            # fails is repeated with the FFT solve, and so are all later ones (the noise only grows) -- at most one
+            # chunk of work is wasted.
+            chunk = n_steps
+            if mode == "auto" and n_steps > self.AUTO_CHUNK:
+                chunk = self.AUTO_CHUNK if not record_every else max(record_every, self.AUTO_CHUNK // record_every * record_every)
+            cur, done, ran_scan, ran_fft = state, 0, False, False
+            self.last_uncertified_step = None
+            while done < n_steps:
+                k = min(chunk, n_steps - done)
+                tv = traj[done // record_every:(done + k) // record_every] if traj is not None else None
+                fv = flux[done:done + k] if flux is not None else None
+                if not ran_fft:
+                    out, first_bad = self._rollout_scan(cur, k, record_every, tv, fv)
+                    if first_bad is None:
+                        ran_scan = True
+                    else:
+                        if self.last_uncertified_step is None:
+                            self.last_uncertified_step = done + first_bad
+                        if mode == "scan":
+                            raise _lib.FluxGNNError(
+                                f"field_solve='scan': the field of step {done + first_bad} is not certified to "
+                                f"cert_tol={self.cert_tol:g} (rough density, short grid, or rounding noise accumulated over "
+                                "many steps); use field_solve='auto' or 'spectral'")
+                        ran_fft = True
+                if ran_fft:
+                    out = self._rollout_spectral(cur, k, record_every, tv, fv)
+                cur, done = out, done + k
+            self.last_field_solve = "scan" if not ran_fft else ("scan+spectral" if ran_scan else "spectral")
+        return cur, traj, flux
+
+    AUTO_CHUNK = 128
+
+    def _scalars(self):
+        return (self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)))
+
+    def _rollout_scan(self, state, n_steps, record_every, traj, flux):
+        """fluxgnn_baseline_rollout_scan -> (final state, first uncertified step of this call or None)."""
+        L, dev = _lib.lib(), self.device
+        B, _, nx = state.shape
+        out = torch.empty_like(state)
+        work = torch.empty(L.fluxgnn_baseline_scan_workspace_bytes(B, nx) // 4, dtype=torch.float32, device=dev)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(L.fluxgnn_baseline_rollout_scan(
+            state.data_ptr(), out.data_ptr(), B, nx, self.length, *self._scalars(), n_steps, max(record_every, 1),
+            traj.data_ptr() if traj is not None else None, flux.data_ptr() if flux is not None else None,
+            self.cert_tol, work.data_ptr(), flag.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+            "fluxgnn_baseline_rollout_scan")
+        first_bad = int(flag.item())                  # 4-byte read-back: was every reconstructed field certified?
+        return out, (None if first_bad == 2 ** 31 - 1 else first_bad)
+
+    def _rollout_spectral(self, state, n_steps, record_every, traj, flux):
+        L, dev = _lib.lib(), self.device
+        B, _, nx = state.shape
+        out = torch.empty_like(state)
+        _, gtab = self.grid.tables(dev)
+        ws_bytes = L.fluxgnn_baseline_workspace_bytes(B, nx)
+        work = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+        _lib.check(L.fluxgnn_baseline_rollout(
+            state.data_ptr(), out.data_ptr(), gtab.data_ptr() if gtab is not None else None, B, nx, self.length,
+            *self._scalars(), n_steps, max(record_every, 1), traj.data_ptr() if traj is not None else None,
+            flux.data_ptr() if flux is not None else None,
+            work.data_ptr() if work is not None else None, torch.cuda.current_stream(dev).cuda_stream),
+            "fluxgnn_baseline_rollout")
+        return out
 
     def step(self, state, return_flux=False):
         """One step (src/baseline_solver.py:80-101); with return_flux also the continuity flux F_n."""

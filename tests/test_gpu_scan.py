@@ -246,3 +246,57 @@ def test_scan_repeated_launches_are_bit_stable(built_lib, nx, B):
         out = sol.rollout(state, 1, field_solve="scan")[0]
         assert torch.equal(out[:, :2], ref1[:, :2])
         sol.rollout(state, 5, field_solve="scan")
+
+
+def test_scan_more_ics_than_resident_ctas(built_lib):
+    """900 ICs of 4096 cells: one segment (CTA) per IC, more CTAs than the device holds at once."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    from gnn_plasma_flux_b200.synthetic import stable_initial_conditions
+    nx, B = 4096, 900
+    # (cert_tol loosened: among 900 random ICs a few have fields of ~3e-3, for which the rounding-noise part of the
+    #  conservative bound, ~3e-8 and growing with the square root of the step count, exceeds 1e-5 * max|E| -- "auto"
+    #  would repeat those with the FFT solve; the subject here is the launch geometry)
+    sol = BaselineSolver(nx=nx, dt=_stable_dt(nx), nu=1e-3, device="cuda", cert_tol=1e-3)
+    state = stable_initial_conditions(sol, B)
+    ref = sol.rollout(state, 4, field_solve="spectral")[0]
+    got = sol.rollout(state, 4, field_solve="scan")[0]
+    assert sol.last_field_solve == "scan"
+    assert P.rel_err(got.cpu().numpy(), ref.cpu().numpy()).max() <= 2e-6
+    one = sol.rollout(state, 1, field_solve="scan")[0]
+    assert torch.equal(one[:, :2], sol.rollout(state, 1, field_solve="spectral")[0][:, :2])
+
+
+def test_auto_rollout_falls_back_chunk_by_chunk(built_lib, monkeypatch):
+    """The rounding noise of n -- and with it the conservative bound -- can only grow with the step count, so a long
+    "auto" rollout runs in chunks: the first chunk whose certificate fails, and all later ones, are repeated with the FFT
+    solve.  The failure is injected here (third chunk reports step 5 of the chunk as uncertified)."""
+    from gnn_plasma_flux_b200 import BaselineSolver
+    monkeypatch.setattr(BaselineSolver, "AUTO_CHUNK", 16)
+    nx, B, steps = 1 << 16, 2, 100
+    dt = _stable_dt(nx)
+    _, ics = _ics(nx, B, dt)
+    dev = torch.from_numpy(ics).cuda()
+    sol = BaselineSolver(nx=nx, dt=dt, nu=1e-3)
+    real, calls = sol._rollout_scan, []
+
+    def flaky(state, n_steps, record_every, traj, flux):
+        out, bad = real(state, n_steps, record_every, traj, flux)
+        calls.append(n_steps)
+        return out, (5 if len(calls) == 3 else bad)
+
+    monkeypatch.setattr(sol, "_rollout_scan", flaky)
+    got = sol.rollout(dev, steps, record_every=4, record_flux=True)
+    assert calls == [16, 16, 16]                                  # two certified chunks, the third rejected, then FFT only
+    assert sol.last_field_solve == "scan+spectral" and sol.last_uncertified_step == 32 + 5
+    ref = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="spectral").rollout(dev, steps, record_every=4, record_flux=True)
+    assert got[1].shape == ref[1].shape == (steps // 4, B, 3, nx) and got[2].shape == (steps, B, nx)
+    assert torch.equal(got[1][-1], got[0])
+    assert P.rel_err(got[0].cpu().numpy(), ref[0].cpu().numpy()).max() <= 5e-6
+    assert P.rel_err(got[1].cpu().numpy().reshape(-1, 3, nx), ref[1].cpu().numpy().reshape(-1, 3, nx)).max() <= 5e-6
+    assert float((got[2] - ref[2]).abs().max() / ref[2].abs().max()) <= 5e-6
+    # without the injected failure the same rollout is certified throughout, chunk after chunk
+    easy = BaselineSolver(nx=nx, dt=dt, nu=1e-3)
+    out = easy.rollout(dev, steps, record_every=4)
+    assert easy.last_field_solve == "scan" and easy.last_uncertified_step is None
+    one_call = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="scan").rollout(dev, steps, record_every=4)
+    assert P.rel_err(out[0].cpu().numpy(), one_call[0].cpu().numpy()).max() <= 1e-6     # chunks re-materialise E: same to rounding
