@@ -93,12 +93,13 @@ class BaselineSolver:
         """`field_solve` (keyword-only, not in the reference): how E = Re ifft(i fft(n-1)/k) is evaluated on long grids.
         "spectral": the FFT kernels, always.  "scan": the certified prefix-sum solve (csrc/scan_poisson.cu; grids of
         at least 4096 cells, nx % 8 == 0), raising if a field's deviation bound exceeds cert_tol * max|E|.  "auto"
-        (default): the scan solve where it applies, repeated with the FFT solve whenever a certificate fails, so the
-        result is always within cert_tol * max|E| of the spectral operator; `last_field_solve` tells which one ran."""
+        (default): the scan solve where it applies; an IC whose certificate fails is repeated with the FFT solve, so the
+        result is always within cert_tol * max|E| of the spectral operator.  `last_field_solve` tells what ran ("scan",
+        "spectral" or "scan+spectral"), `last_uncertified_ics` which ICs were repeated."""
         if field_solve not in self.FIELD_SOLVES:
             raise ValueError(f"field_solve must be one of {self.FIELD_SOLVES}, got {field_solve!r}")
         self.field_solve, self.cert_tol = field_solve, float(cert_tol)
-        self.last_field_solve, self.last_uncertified_step = None, None
+        self.last_field_solve, self.last_uncertified_step, self.last_uncertified_ics = None, None, []
         self.grid = PeriodicGrid(nx, length)
         self.nx, self.length, self.dx = self.grid.nx, self.grid.length, self.grid.dx
         self.dt, self.t_end, self.nu = dt, t_end, nu
@@ -199,38 +200,51 @@ class BaselineSolver:
                 raise _lib.FluxGNNError(f"field_solve='scan' needs nx >= 4096 and nx % 8 == 0 (B={B}, nx={nx})")
             if mode == "spectral" or not scan_ok:
                 out = self._rollout_spectral(state, n_steps, record_every, traj, flux)
-                self.last_field_solve, self.last_uncertified_step = "spectral", None
+                self.last_field_solve, self.last_uncertified_step, self.last_uncertified_ics = "spectral", None, []
                 return out, traj, flux
-            # "auto" / "scan".  The rounding noise of n grows like the square root of the step count and with it the
-            # (conservative) certificate bound, so a long "auto" rollout is cut into chunks: a chunk whose certificate
-            # fails is repeated with the FFT solve, and so are all later ones (the noise only grows) -- at most one
-            # chunk of work is wasted.
+            # "auto" / "scan".  Certificates are per IC: an IC whose certificate fails is repeated with the FFT solve,
+            # the others keep the scan result.  The rounding noise of n -- and with it the (conservative) bound -- can
+            # only grow with the step count, so a long "auto" rollout is cut into chunks and an IC that failed once
+            # stays with the FFT solve: at most one chunk of its work is wasted.
             chunk = n_steps
             if mode == "auto" and n_steps > self.AUTO_CHUNK:
                 chunk = self.AUTO_CHUNK if not record_every else max(record_every, self.AUTO_CHUNK // record_every * record_every)
-            cur, done, ran_scan, ran_fft = state, 0, False, False
+            cur, done = state, 0
+            fft_ics = torch.zeros(B, dtype=torch.bool)                   # (host) ICs that left the scan path
             self.last_uncertified_step = None
             while done < n_steps:
                 k = min(chunk, n_steps - done)
                 tv = traj[done // record_every:(done + k) // record_every] if traj is not None else None
                 fv = flux[done:done + k] if flux is not None else None
-                if not ran_fft:
-                    out, first_bad = self._rollout_scan(cur, k, record_every, tv, fv)
-                    if first_bad is None:
-                        ran_scan = True
-                    else:
+                if bool(fft_ics.all()):
+                    out = self._rollout_spectral(cur, k, record_every, tv, fv)
+                else:
+                    out, first_bad = self._rollout_scan(cur, k, record_every, tv, fv)          # [B] int32, INT_MAX = certified
+                    failed = first_bad != 2 ** 31 - 1
+                    if bool(failed.any()):
+                        step_bad = done + int(first_bad.min())
                         if self.last_uncertified_step is None:
-                            self.last_uncertified_step = done + first_bad
+                            self.last_uncertified_step = step_bad
                         if mode == "scan":
                             raise _lib.FluxGNNError(
-                                f"field_solve='scan': the field of step {done + first_bad} is not certified to "
-                                f"cert_tol={self.cert_tol:g} (rough density, short grid, or rounding noise accumulated over "
-                                "many steps); use field_solve='auto' or 'spectral'")
-                        ran_fft = True
-                if ran_fft:
-                    out = self._rollout_spectral(cur, k, record_every, tv, fv)
+                                f"field_solve='scan': the field of step {step_bad} (IC {int(first_bad.argmin())}) is not "
+                                f"certified to cert_tol={self.cert_tol:g} (rough density, weak field, short grid, or rounding "
+                                "noise accumulated over many steps); use field_solve='auto' or 'spectral'")
+                    fft_ics |= failed
+                    if bool(fft_ics.any()):
+                        idx = fft_ics.nonzero().flatten().to(dev)
+                        sub_t = tv.new_empty((tv.shape[0], idx.numel(), 3, nx)) if tv is not None else None
+                        sub_f = fv.new_empty((k, idx.numel(), nx)) if fv is not None else None
+                        sub = self._rollout_spectral(cur.index_select(0, idx).contiguous(), k, record_every, sub_t, sub_f)
+                        out.index_copy_(0, idx, sub)
+                        if tv is not None:
+                            tv.index_copy_(1, idx, sub_t)
+                        if fv is not None:
+                            fv.index_copy_(1, idx, sub_f)
                 cur, done = out, done + k
-            self.last_field_solve = "scan" if not ran_fft else ("scan+spectral" if ran_scan else "spectral")
+            n_fft = int(fft_ics.sum())
+            self.last_uncertified_ics = fft_ics.nonzero().flatten().tolist()
+            self.last_field_solve = "scan" if n_fft == 0 else ("spectral" if n_fft == B else "scan+spectral")
         return cur, traj, flux
 
     AUTO_CHUNK = 128
@@ -239,19 +253,18 @@ class BaselineSolver:
         return (self._c, float(np.float32(self.dt)), float(np.float32(self.nu)), float(np.float32(self.dx ** 2)))
 
     def _rollout_scan(self, state, n_steps, record_every, traj, flux):
-        """fluxgnn_baseline_rollout_scan -> (final state, first uncertified step of this call or None)."""
+        """fluxgnn_baseline_rollout_scan -> (final state, host int32[B]: first uncertified step per IC, INT_MAX = none)."""
         L, dev = _lib.lib(), self.device
         B, _, nx = state.shape
         out = torch.empty_like(state)
         work = torch.empty(L.fluxgnn_baseline_scan_workspace_bytes(B, nx) // 4, dtype=torch.float32, device=dev)
-        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        flag = torch.empty(B, dtype=torch.int32, device=dev)
         _lib.check(L.fluxgnn_baseline_rollout_scan(
             state.data_ptr(), out.data_ptr(), B, nx, self.length, *self._scalars(), n_steps, max(record_every, 1),
             traj.data_ptr() if traj is not None else None, flux.data_ptr() if flux is not None else None,
             self.cert_tol, work.data_ptr(), flag.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
             "fluxgnn_baseline_rollout_scan")
-        first_bad = int(flag.item())                  # 4-byte read-back: was every reconstructed field certified?
-        return out, (None if first_bad == 2 ** 31 - 1 else first_bad)
+        return out, flag.cpu()                        # read-back of B ints: was every reconstructed field certified?
 
     def _rollout_spectral(self, state, n_steps, record_every, traj, flux):
         L, dev = _lib.lib(), self.device

@@ -12,8 +12,8 @@
 // which is bounded by (1/16) (2 sin(kappa/2))^4 on (0, pi]: the deviation from the spectral field is therefore at most
 //   || E_scan - E_spectral ||_inf  <=  rms(Delta^4 rho) * L / (32 sqrt 3)                (Cauchy-Schwarz over the modes)
 // and the kernel EVALUATES that bound for every field it reconstructs (certificate).  A field whose bound exceeds
-// tol * max|E| is reported through `flag` (first uncertified step); the host mirror then repeats the rollout with the
-// FFT solve.  Smooth states on long grids pass with a margin set by fp32 rounding noise (bound ~3e-8 absolute);
+// tol * max|E| is reported through `flag` (first uncertified step, per IC); the host mirror then repeats those ICs with
+// the FFT solve.  Smooth states on long grids pass with a margin set by fp32 rounding noise (bound ~3e-8 absolute);
 // white noise or short grids do not, and never silently use this path.
 //
 // Because E is a function of n alone, the rollout keeps only (n, u) in HBM between steps: step s+1 reconstructs the field
@@ -68,7 +68,7 @@ struct ScanArgs {
     float* flux_out;         // [B][nx] continuity flux n*u of the input state, or null
     const ScanRec* rec_in;   // [B][segs] from the previous launch (modes 1, 2)
     ScanRec* rec_out;        // [B][segs]
-    int* flag;               // first uncertified step (INT_MAX = all certified)
+    int* flag;               // [B]: first uncertified step of every IC (INT_MAX = all certified)
     int step;                // index of the step whose input field the records in rec_in certify
     int B, nx, segs, seg_chunks;
     float c, dt, nu, dx2;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
             // certificate of the field the PREVIOUS launch reconstructed (its records carry D4 and max|E|)
             if (seg == 0 && a.step > 0) {
                 const double bound = sqrt(da / N) * a.length * (1.0 / (32.0 * 1.7320508075688772));
-                if (!(bound <= a.tol * (double)em)) atomicMin(a.flag, a.step - 1);
+                if (!(bound <= a.tol * (double)em)) atomicMin(a.flag + ic, a.step - 1);
             }
         }
         __syncthreads();
@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) baseline_scan_ke
 // certificate of the last reconstructed field (the records of the materialise launch), and flag initialisation
 __global__ void baseline_scan_flag_kernel(const ScanRec* rec, int B, int segs, int nx, double length, double tol, int step,
                                           int* flag, int init) {
-    if (init) { if (threadIdx.x == 0 && blockIdx.x == 0) *flag = INT_MAX; return; }
     const int ic = blockIdx.x;
+    if (init) { if (threadIdx.x == 0) flag[ic] = INT_MAX; return; }
     double d = 0.0;
     float em = 0.f;
     for (int r = threadIdx.x; r < segs; r += 32) {
@@ -365,7 +365,7 @@ __global__ void baseline_scan_flag_kernel(const ScanRec* rec, int B, int segs, i
     for (int o = 16; o > 0; o >>= 1) em = fmaxf(em, __shfl_xor_sync(0xffffffffu, em, o));
     if (threadIdx.x == 0) {
         const double bound = sqrt(d / (double)nx) * length * (1.0 / (32.0 * 1.7320508075688772));
-        if (!(bound <= tol * (double)em)) atomicMin(flag, step);
+        if (!(bound <= tol * (double)em)) atomicMin(flag + ic, step);
     }
 }
 
@@ -680,7 +680,7 @@ cudaError_t launch_baseline_rollout_scan(const float* state_in, float* state_out
     if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     int nl = 0;
-    baseline_scan_flag_kernel<<<1, 32, 0, stream>>>(nullptr, B, segs, nx, length, tol, 0, flag, 1);
+    baseline_scan_flag_kernel<<<B, 32, 0, stream>>>(nullptr, B, segs, nx, length, tol, 0, flag, 1);
     ++nl;
     ScanArgs a;
     a.B = B; a.nx = nx; a.segs = segs; a.seg_chunks = sc;

@@ -344,10 +344,10 @@ int fluxgnn_latency_cluster_slots(void);
  * evaluated as trapezoid prefix sum + first Euler-Maclaurin term, and for every field so obtained
  * the kernel evaluates the rigorous bound
  *     max|E_scan - E_spectral| <= rms(4th difference of n) * length / (32 sqrt 3).
- * *first_uncertified (DEVICE int) receives the index of the first step whose input field had
- * bound > cert_tol * max|E| (index `steps` = the field of the final state), INT_MAX if every field
- * was certified.  The caller reads it after the stream has finished and, if it is not INT_MAX,
- * repeats the rollout with fluxgnn_baseline_rollout (BaselineSolver.rollout(field_solve="auto")
+ * first_uncertified (DEVICE int[B]) receives, per IC, the index of the first step whose input field had
+ * bound > cert_tol * max|E| (index `steps` = the field of the final state), INT_MAX if every field of
+ * that IC was certified.  The caller reads it after the stream has finished and repeats the ICs that
+ * are not INT_MAX with fluxgnn_baseline_rollout (BaselineSolver.rollout(field_solve="auto")
  * does exactly that).  Between steps only n and u live in HBM (16 B per cell-update); E is written
  * for recorded states and the final state.  state_in's E is used for the first step as given.
  *   workspace: fluxgnn_baseline_scan_workspace_bytes(B, nx) bytes. */

@@ -88,8 +88,16 @@ def test_scan_certificate_rejects_rough_density(built_lib):
     spectral = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="spectral").rollout(dev, 4)[0]
     auto = BaselineSolver(nx=nx, dt=dt, nu=1e-3)                                  # default: auto
     got = auto.rollout(dev, 4)[0]
-    assert auto.last_field_solve == "spectral" and auto.last_uncertified_step == 1
+    assert auto.last_field_solve == "spectral" and auto.last_uncertified_step == 1 and auto.last_uncertified_ics == [0, 1]
     assert torch.equal(got, spectral)
+    # certificates are per IC: with one smooth and one rough IC only the rough one is repeated
+    mixed = dev.clone()
+    mixed[0] = torch.from_numpy(_ics(nx, 1, dt)[1][0]).cuda()
+    got2, traj2, flux2 = auto.rollout(mixed, 4, record_every=2, record_flux=True)
+    assert auto.last_field_solve == "scan+spectral" and auto.last_uncertified_ics == [1]
+    want2 = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="spectral").rollout(mixed, 4, record_every=2, record_flux=True)
+    assert torch.equal(got2[1], want2[0][1]) and torch.equal(traj2[:, 1], want2[1][:, 1]) and torch.equal(flux2[:, 1], want2[2][:, 1])
+    assert P.rel_err(got2[:1].cpu().numpy(), want2[0][:1].cpu().numpy()).max() <= 2e-6
     with pytest.raises(_lib.FluxGNNError, match="not certified"):
         BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="scan").rollout(dev, 4)
     # the bound is an upper bound: measured deviation of the uncertified scan field from the float64 operator
@@ -280,14 +288,17 @@ def test_auto_rollout_falls_back_chunk_by_chunk(built_lib, monkeypatch):
     real, calls = sol._rollout_scan, []
 
     def flaky(state, n_steps, record_every, traj, flux):
-        out, bad = real(state, n_steps, record_every, traj, flux)
+        out, bad = real(state, n_steps, record_every, traj, flux)       # bad: int32[B], INT_MAX = certified
         calls.append(n_steps)
-        return out, (5 if len(calls) == 3 else bad)
+        if len(calls) == 3:
+            bad = bad.clone()
+            bad[1] = 5                                                 # IC 1 reports step 5 of this chunk as uncertified
+        return out, bad
 
     monkeypatch.setattr(sol, "_rollout_scan", flaky)
     got = sol.rollout(dev, steps, record_every=4, record_flux=True)
-    assert calls == [16, 16, 16]                                  # two certified chunks, the third rejected, then FFT only
-    assert sol.last_field_solve == "scan+spectral" and sol.last_uncertified_step == 32 + 5
+    assert calls == [16] * 6 + [4]                                # IC 0 stays on the scan path to the end (100 = 6 x 16 + 4)
+    assert sol.last_field_solve == "scan+spectral" and sol.last_uncertified_step == 32 + 5 and sol.last_uncertified_ics == [1]
     ref = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="spectral").rollout(dev, steps, record_every=4, record_flux=True)
     assert got[1].shape == ref[1].shape == (steps // 4, B, 3, nx) and got[2].shape == (steps, B, nx)
     assert torch.equal(got[1][-1], got[0])
