@@ -56,6 +56,15 @@ def is_ring(edge_index: torch.Tensor, num_nodes: int):
 def build_chain_graph(full_state, x, device=None, radius: int = 1):
     """full_state [3, nx] (numpy or torch: n, u, E), x [nx] ->
     (node_features [nx, 4] float32 = [n, u, E, x], edge_index [2, 2*radius*nx] int64)."""
+    if isinstance(full_state, np.ndarray) and not torch.is_tensor(x):
+        # host inputs: assemble [nx, 4] on the host, one copy to the device (the reference does four)
+        feats = np.empty((full_state.shape[1], 4), dtype=np.float32)
+        feats[:, :3] = np.asarray(full_state[:3], dtype=np.float32).T
+        feats[:, 3] = np.asarray(x, dtype=np.float32)
+        node_features = torch.from_numpy(feats)
+        if device is not None:
+            node_features = node_features.to(device)
+        return node_features, _cached_ring(feats.shape[0], radius, node_features.device)
     if isinstance(full_state, np.ndarray):
         chans = [torch.from_numpy(np.ascontiguousarray(full_state[c], dtype=np.float32)) for c in range(3)]
     else:
@@ -66,4 +75,22 @@ def build_chain_graph(full_state, x, device=None, radius: int = 1):
         chans = [c.to(device) for c in chans]
     pos = torch.as_tensor(x, dtype=torch.float32, device=device)
     node_features = torch.stack((*chans, pos), dim=-1)
-    return node_features, ring_edge_index(chans[0].shape[0], radius, device=device)
+    return node_features, _cached_ring(chans[0].shape[0], radius, torch.device(device))
+
+
+_ring_cache = {}
+
+
+def _cached_ring(nx: int, radius: int, device) -> torch.Tensor:
+    """A fresh tagged copy of the ring's edge_index (the caller may write to it); the master copy is built once per
+    (nx, radius, device) instead of with eight small kernels per call."""
+    key = (int(nx), int(radius), str(device))
+    master = _ring_cache.get(key)
+    if master is None:
+        if len(_ring_cache) >= 64:
+            _ring_cache.clear()
+        master = ring_edge_index(nx, radius, device=device)
+        _ring_cache[key] = master
+    out = master.clone()
+    out._fluxgnn_ring = (int(nx), int(radius), out._version)
+    return out
