@@ -314,6 +314,20 @@ static int tc_shape_ok(int whole_ic, int nx, int radius) {
     return FLUXGNN_OK;
 }
 
+// Latency mode: with fewer tiles than cluster slots the tile kernel would use one SM per tile and leave the rest idle; a
+// cluster of 8 CTAs per tile splits every layer's output features instead (bit-identical results).  FLUXGNN_LATENCY=0 / 1
+// forces the choice (test hook).  Returns 0 when it launched, 1 when the caller should use the tile kernel, < 0 on error.
+static int try_latency_mode(const HybridArgs& a, int precision, cudaStream_t stream) {
+    if (precision != 0 || !hybrid_latency_supported(a)) return 1;
+    const char* env = getenv("FLUXGNN_LATENCY");
+    const bool forced = env != nullptr && env[0] == '1', off = env != nullptr && env[0] == '0';
+    const int slots = off ? 0 : hybrid_latency_max_clusters();
+    if (slots < 1 || !(forced || a.num_tiles <= 2 * slots)) return 1;
+    FLUXGNN_CUDA_OK(launch_hybrid_latency(a, a.num_tiles < slots ? a.num_tiles : slots, stream));
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 static int forward_ring_impl(int precision, const void* packed, int num_layers, const float* state, const float* x,
                              int B, int nx, int radius, int hops, float* flux_edges, float* face_flux,
                              void* stream, float* acts = nullptr) {
@@ -343,6 +357,8 @@ static int forward_ring_impl(int precision, const void* packed, int num_layers, 
         if (rc != FLUXGNN_OK) return rc;
         fast = -radius;
     }
+    int lat = try_latency_mode(a, precision, (cudaStream_t)stream);
+    if (lat != 1) return lat;                              // 0: launched, < 0: error
     return launch_tiles(a, fast, (cudaStream_t)stream);
 }
 
@@ -417,19 +433,8 @@ static int hybrid_rollout_impl(int precision, const void* packed, int num_layers
         a.traj = traj;
         a.diag = diag;
         a.steps = steps;
-        // Latency mode: with fewer tiles than cluster slots the tile kernel would use one SM per tile and leave the rest
-        // idle; a cluster of 8 CTAs per tile splits every layer's output features instead (bit-identical results).
-        // FLUXGNN_LATENCY=0 / 1 forces the choice (test hook).
-        if (precision == 0 && hybrid_latency_supported(a)) {
-            const char* env = getenv("FLUXGNN_LATENCY");
-            const bool forced = env != nullptr && env[0] == '1', off = env != nullptr && env[0] == '0';
-            const int slots = off ? 0 : hybrid_latency_max_clusters();
-            if (slots > 0 && (forced || a.num_tiles <= 2 * slots)) {
-                FLUXGNN_CUDA_OK(launch_hybrid_latency(a, a.num_tiles < slots ? a.num_tiles : slots, stream));
-                count_launch();
-                return FLUXGNN_OK;
-            }
-        }
+        int lat = try_latency_mode(a, precision, stream);
+        if (lat != 1) return lat;                          // 0: launched, < 0: error
         return launch_tiles(a, fast, stream);
     }
     if (diag != nullptr)

@@ -9,7 +9,8 @@
 //                                                    h' of its features is stored into the next-layer buffer of ALL 8 CTAs
 //                                                    through distributed shared memory (st.shared::cluster), one cluster
 //                                                    barrier per layer, activations double-buffered
-//   src/flux_gnn.py:63-66     edge readout           per-CTA partial dot products, exchanged as 2 x 128 floats per CTA
+//   src/flux_gnn.py:63-66     edge readout           per-CTA partial dot products, exchanged as 2 x 128 floats per CTA and hop
+//                                                    (forward-only calls emit every hop's directed-edge fluxes)
 //   src/hybrid_solver.py:45-58, src/baseline_solver.py:59-68   update and field solve: every CTA redundantly, CTA 0 writes
 //
 // A product thread (the first 128 of 256) owns 4 consecutive rows and 4 features (j = 0..3 or 4..7 of one tx) of both halves:
@@ -49,7 +50,7 @@ struct __align__(128) LatSmem {
     float Hs[2][kH * kTileRows];                  // activations [buffer][feature][row], a complete copy in every CTA
     float Zs[kLatFeat * kTileRows];               // neighbour half of this CTA's features [local feature][row]
     float Wl[2][2][kH][kLatFeat];                 // weight slice [buffer][half: 0 = neighbour/col, 1 = self/row][k][column]
-    float edge_all[kLatCluster][2][kTileRows];    // per source CTA: fwd / bwd partial sums (tx even + tx odd) of every row
+    float edge_all[kLatCluster][kLatMaxR][2][kTileRows];   // per source CTA and hop: fwd / bwd partial sums (tx even + tx odd) of every row
     float sN[kTileRows], sU[kTileRows], sE[kTileRows], sX[kTileRows];
     float sF[kTileRows], sRho[kTileRows];
     double gtab[kTileRows];
@@ -87,9 +88,10 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
 #pragma unroll
     for (int p = 0; p < kLatCluster; ++p) {
         peer_hs[p] = cluster_map(smem_u32(&S.Hs[0][0]), p);
-        peer_edge[p] = cluster_map(smem_u32(&S.edge_all[crank][0][0]), p);
+        peer_edge[p] = cluster_map(smem_u32(&S.edge_all[crank][0][0][0]), p);
     }
-    for (int i = tid; i < nx; i += kLatThreads) S.gtab[i] = a.gtab[i];
+    if (a.do_update)
+        for (int i = tid; i < nx; i += kLatThreads) S.gtab[i] = a.gtab[i];
 
     // this CTA's slice of a layer's weights: 1024 float4, four per thread
     float4 wreg[4];
@@ -231,42 +233,47 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
                         float w2[4];
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) w2[jj] = __ldg(a.packed + SmallParams::w_e2 + tx + 16 * (4 * jh + jj));
-                        float pf[4], pb[4];
 #pragma unroll
-                        for (int pass = 0; pass < 2; ++pass) {
+                        for (int hop = 1; hop <= kLatMaxR; ++hop) {
+                            if (hop > a.hops) break;
+                            float pf[4], pb[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                // pass 0: chains seeded with 0 (final for the j < 4 lanes); pass 1: the j >= 4 lanes redo theirs
-                                // seeded with the neighbour's result
-                                float sf = 0.f, sb = 0.f;
-                                if (pass == 1) {
-                                    sf = __shfl_xor_sync(0xffffffffu, pf[q], 1);
-                                    sb = __shfl_xor_sync(0xffffffffu, pb[q], 1);
-                                }
-                                if (pass == 0 || jh == 1) {
+                            for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-                                    for (int jj = 0; jj < 4; ++jj) {
-                                        const float* zr = &S.Zs[(txl * 8 + 4 * jh + jj) * kTileRows];
-                                        sf = fmaf(w2[jj], fmaxf(accY[q][jj] + zr[rp[q][0]], 0.f), sf);
-                                        sb = fmaf(w2[jj], fmaxf(accY[q][jj] + zr[rm[q][0]], 0.f), sb);
+                                for (int q = 0; q < 4; ++q) {
+                                    // pass 0: chains seeded with 0 (final for the j < 4 lanes); pass 1: the j >= 4 lanes redo theirs
+                                    // seeded with the neighbour's result
+                                    float sf = 0.f, sb = 0.f;
+                                    if (pass == 1) {
+                                        sf = __shfl_xor_sync(0xffffffffu, pf[q], 1);
+                                        sb = __shfl_xor_sync(0xffffffffu, pb[q], 1);
                                     }
-                                    pf[q] = sf; pb[q] = sb;
+                                    if (pass == 0 || jh == 1) {
+#pragma unroll
+                                        for (int jj = 0; jj < 4; ++jj) {
+                                            const float* zr = &S.Zs[(txl * 8 + 4 * jh + jj) * kTileRows];
+                                            sf = fmaf(w2[jj], fmaxf(accY[q][jj] + zr[rp[q][hop - 1]], 0.f), sf);
+                                            sb = fmaf(w2[jj], fmaxf(accY[q][jj] + zr[rm[q][hop - 1]], 0.f), sb);
+                                        }
+                                        pf[q] = sf; pb[q] = sb;
+                                    }
                                 }
                             }
-                        }
-                        // the complete sums of a thread column sit in its j >= 4 lane; tx even + tx odd, then to every CTA
-                        float cf[4], cb[4];
+                            // the complete sums of a thread column sit in its j >= 4 lane; tx even + tx odd, then to every CTA
+                            float cf[4], cb[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            cf[q] = pf[q] + __shfl_xor_sync(0xffffffffu, pf[q], 2);
-                            cb[q] = pb[q] + __shfl_xor_sync(0xffffffffu, pb[q], 2);
-                        }
-                        if (txl == 0 && jh == 1) {
-                            const float4 f4 = make_float4(cf[0], cf[1], cf[2], cf[3]), b4 = make_float4(cb[0], cb[1], cb[2], cb[3]);
+                            for (int q = 0; q < 4; ++q) {
+                                cf[q] = pf[q] + __shfl_xor_sync(0xffffffffu, pf[q], 2);
+                                cb[q] = pb[q] + __shfl_xor_sync(0xffffffffu, pb[q], 2);
+                            }
+                            if (txl == 0 && jh == 1) {
+                                const float4 f4 = make_float4(cf[0], cf[1], cf[2], cf[3]), b4 = make_float4(cb[0], cb[1], cb[2], cb[3]);
+                                const uint32_t off = (uint32_t)(((hop - 1) * 2 * kTileRows + R0) * 4);
 #pragma unroll
-                            for (int p = 0; p < kLatCluster; ++p) {
-                                st_cluster_f4(peer_edge[p] + (uint32_t)(R0 * 4), f4);
-                                st_cluster_f4(peer_edge[p] + (uint32_t)((kTileRows + R0) * 4), b4);
+                                for (int p = 0; p < kLatCluster; ++p) {
+                                    st_cluster_f4(peer_edge[p] + off, f4);
+                                    st_cluster_f4(peer_edge[p] + off + (uint32_t)(kTileRows * 4), b4);
+                                }
                             }
                         }
                     }
@@ -276,21 +283,35 @@ __global__ void __launch_bounds__(kLatThreads, 1) hybrid_latency_kernel(const Hy
                 }
             }   // layers
 
-            // ---- face flux (src/hybrid_solver.py:45-48): the tile kernel's summation tree over the thread columns ----
+            // ---- directed-edge fluxes and face flux (src/hybrid_solver.py:45-48): the tile kernel's summation tree over the
+            // thread columns ----
             if (tid < kTileRows) {
                 const int j = tid;
                 const float b2 = __ldg(a.packed + SmallParams::b_e2);
-                auto tree = [&](int dir, int r) {
-                    const float h0 = (S.edge_all[0][dir][r] + S.edge_all[1][dir][r]) + (S.edge_all[2][dir][r] + S.edge_all[3][dir][r]);
-                    const float h1 = (S.edge_all[4][dir][r] + S.edge_all[5][dir][r]) + (S.edge_all[6][dir][r] + S.edge_all[7][dir][r]);
-                    return (h0 + h1) + b2;
-                };
-                const float fwd = tree(0, j), bwd = tree(1, S.nextRow[j]);
-                const float face = 0.5f * (fwd + bwd);
-                if (crank == 0 && a.face_flux != nullptr && S.rowIC[j] >= 0)
-                    a.face_flux[(size_t)S.rowIC[j] * nx + S.rowCell[j]] = face;
+                const int ic = S.rowIC[j], cell = S.rowCell[j];
+                float face = 0.f;
+                int jn = j;
+                for (int hop = 1; hop <= a.hops; ++hop) {
+                    jn = S.nextRow[jn];
+                    auto tree = [&](int dir, int r) {
+                        const float h0 = (S.edge_all[0][hop - 1][dir][r] + S.edge_all[1][hop - 1][dir][r]) +
+                                         (S.edge_all[2][hop - 1][dir][r] + S.edge_all[3][hop - 1][dir][r]);
+                        const float h1 = (S.edge_all[4][hop - 1][dir][r] + S.edge_all[5][hop - 1][dir][r]) +
+                                         (S.edge_all[6][hop - 1][dir][r] + S.edge_all[7][hop - 1][dir][r]);
+                        return (h0 + h1) + b2;
+                    };
+                    const float fwd = tree(0, j), bwd = tree(1, jn);
+                    if (hop == 1) face = 0.5f * (fwd + bwd);
+                    if (crank == 0 && a.flux_edges != nullptr && ic >= 0) {
+                        float* fe = a.flux_edges + (size_t)ic * 2 * a.hops * nx + (size_t)(2 * (hop - 1)) * nx + cell;
+                        fe[0] = fwd;
+                        fe[nx] = bwd;
+                    }
+                }
+                if (crank == 0 && a.face_flux != nullptr && ic >= 0) a.face_flux[(size_t)ic * nx + cell] = face;
                 S.sF[j] = face;
             }
+            if (!a.do_update) continue;                    // forward only (steps == 1)
             __syncthreads();
             // ---- finite-volume update (src/hybrid_solver.py:51-58), field solve (src/baseline_solver.py:59-68) ----
             float n_new = 0.f, u_new = 0.f;
@@ -345,8 +366,8 @@ int hybrid_latency_max_clusters() {
 }
 
 bool hybrid_latency_supported(const HybridArgs& a) {
-    return a.whole_ic && a.do_update && a.hops == 1 && a.flux_edges == nullptr && a.acts == nullptr && a.tc_parts == 0 &&
-           a.tile_rows == kTileRows && a.radius <= kLatMaxR && !a.slab;
+    return a.whole_ic && a.hops >= 1 && a.hops <= kLatMaxR && a.acts == nullptr && a.tc_parts == 0 &&
+           a.tile_rows == kTileRows && a.radius <= kLatMaxR && !a.slab && (a.do_update || a.steps == 1);
 }
 
 cudaError_t launch_hybrid_latency(const HybridArgs& a, int clusters, cudaStream_t stream) {

@@ -330,7 +330,7 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out,
                              int steps, int record_every, float* traj,
                              float* flux_n, void* workspace, void* stream);
 
-/* Latency mode of fluxgnn_hybrid_rollout (fp32 kernel, whole-IC tiles, radius <= 4): when a rollout has at most twice as
+/* Latency mode of fluxgnn_hybrid_rollout and fluxgnn_forward_ring (fp32 kernel, whole-IC tiles, radius <= 4): when a call has at most twice as
  * many 128-row tiles as the device has cluster slots, every tile is computed by a cluster of 8 CTAs that split the
  * output features of each layer (csrc/hybrid_latency_kernel.cu) -- bit-identical results, ~3x lower time per step for the
  * reference's own timing protocol of one 64-cell IC (scripts/evaluation/benchmark_timing.py:63-72).

@@ -1212,3 +1212,25 @@ def test_latency_mode_diagnostics_and_reference_api(model, monkeypatch):
         np.testing.assert_array_equal(out["0"][i], out["1"][i])
     for k in out["0"][3]:
         np.testing.assert_array_equal(out["0"][3][k], out["1"][3][k])
+
+
+@pytest.mark.parametrize("nx,radius", [(64, 1), (64, 3), (40, 2), (128, 4), (36, 1)])
+def test_latency_mode_forward_is_bit_identical(model, monkeypatch, nx, radius):
+    """FluxGNN.forward on one ring graph (the reference's per-sample call, src/flux_gnn.py:40-67) through the latency mode:
+    every hop's directed-edge fluxes bit-identical to the tile kernel's, and equal to the golden tolerance of the oracle."""
+    from gnn_plasma_flux_b200 import _lib, build_chain_graph
+    if _lib.lib().fluxgnn_latency_cluster_slots() < 1:
+        pytest.skip("clusters of 8 CTAs are not launchable on this device")
+    grid = P.Grid(nx=nx)
+    state = P.stable_initial_condition(grid, 3)
+    nf, ei = build_chain_graph(state, grid.x.astype(np.float32), device="cuda", radius=radius)
+    out = {}
+    with torch.no_grad():
+        for mode in ("0", "1"):
+            monkeypatch.setenv("FLUXGNN_LATENCY", mode)
+            before = _lib.launch_count()
+            out[mode] = model(nf, ei).cpu().numpy()
+            assert _lib.launch_count() - before == 1
+    monkeypatch.delenv("FLUXGNN_LATENCY")
+    assert out["1"].shape == (2 * radius * nx,)
+    np.testing.assert_array_equal(out["0"], out["1"])
