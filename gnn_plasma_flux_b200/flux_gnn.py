@@ -50,10 +50,12 @@ class FluxGNN(nn.Module):
         SGD) do NOT bump the version counter: call invalidate_packed() after them.  load_state_dict(), train(),
         eval() and .to()/.cuda()/.float() invalidate automatically."""
         self._packed.clear()
+        self.__dict__.pop("_param_slots", None)
         return self
 
     def load_state_dict(self, *args, **kwargs):
         self._packed.clear()
+        self.__dict__.pop("_param_slots", None)
         return super().load_state_dict(*args, **kwargs)
 
     def train(self, mode: bool = True):
@@ -62,7 +64,18 @@ class FluxGNN(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         self._packed.clear()
+        self.__dict__.pop("_param_slots", None)
         return super()._apply(fn, *args, **kwargs)
+
+    def _live_parameters(self):
+        """The parameters as they are NOW, without walking the module tree on every call (that walk cost more than the
+        latency-mode kernel of a single IC): the (module, attribute) slots are collected once -- the layer structure is
+        fixed by the constructor -- and read afresh each time, so replaced Parameter objects are seen."""
+        slots = self.__dict__.get("_param_slots")
+        if slots is None:
+            slots = [(m, name) for m in self.modules() for name, _ in m.named_parameters(recurse=False)]
+            self.__dict__["_param_slots"] = slots
+        return [getattr(m, name) for m, name in slots]
 
     # ------------------------------------------------------------------ weights
     @property
@@ -92,7 +105,7 @@ class FluxGNN(nn.Module):
                 raise NotImplementedError(f"precision modes other than fp32 need input_dim={_lib.INPUT_DIM}, "
                                           f"hidden_dim={_lib.HIDDEN}; this model is ({self.input_dim}, {self.hidden_dim})")
             layout = "generic"
-        params = list(self.parameters())
+        params = self._live_parameters()
         dev = params[0].device
         if dev.type != "cuda":
             raise _lib.FluxGNNError("FluxGNN parameters are on %s: the forward pass needs a CUDA device "
@@ -200,7 +213,7 @@ class FluxGNN(nn.Module):
             raise NotImplementedError(f"forward() emits at most {_lib.MAX_HOPS} hop blocks; radius={radius}")
         packed = self.packed_weights()
         wants_grad = torch.is_grad_enabled() and (node_features.requires_grad or
-                                                  any(p.requires_grad for p in self.parameters()))
+                                                  any(p.requires_grad for p in self._live_parameters()))
         if self.is_generic:
             if wants_grad:
                 raise NotImplementedError(
