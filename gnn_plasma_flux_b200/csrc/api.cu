@@ -696,6 +696,21 @@ int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const doub
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc != FLUXGNN_OK) return rc;
+    // Short grids with the direct field solve (the reference's default 64 cells): the whole rollout of an IC in one
+    // persistent CTA, one launch instead of two per step; bit-identical (FLUXGNN_BASELINE_PERSIST=0: test hook).
+    {
+        const char* env = getenv("FLUXGNN_BASELINE_PERSIST");
+        if (!poisson_fft_supported(nx) && nx <= kBaselineSmallMaxNx && gtab != nullptr && !(env != nullptr && env[0] == '0')) {
+            const size_t smem = (size_t)nx * (sizeof(double) + 6 * sizeof(float));
+            FLUXGNN_CUDA_OK(cudaFuncSetAttribute(baseline_small_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int threads = nx >= 256 ? 256 : ((nx + 31) / 32) * 32;
+            baseline_small_rollout_kernel<<<(unsigned)B, threads, smem, stream>>>(state_in, state_out, traj, flux_n, gtab, B, nx, steps,
+                                                                                 record_every < 1 ? 1 : record_every, c, dt, nu, dx2);
+            FLUXGNN_CUDA_OK(cudaGetLastError());
+            count_launch();
+            return FLUXGNN_OK;
+        }
+    }
     const size_t state_floats = (size_t)B * 3 * nx;
     void* fft_ws = workspace ? (void*)((float*)workspace + state_floats) : nullptr;
     const long long cells = (long long)B * nx;

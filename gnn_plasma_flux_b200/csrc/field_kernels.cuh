@@ -78,6 +78,9 @@ __global__ void poisson_direct_kernel(const float* n, long long n_stride, float*
                                       const double* gtab, int nx);
 __global__ void baseline_fv_kernel(const float* in, float* out, float* flux_n, int B, int nx,
                                    float c, float dt, float nu, float dx2);
+constexpr int kBaselineSmallMaxNx = 1024;     // persistent one-CTA-per-IC classical rollout (direct field solve, nx^2 work per step)
+__global__ void baseline_small_rollout_kernel(const float* in, float* out, float* traj, float* flux_n, const double* gtab, int B,
+                                              int nx, int steps, int record_every, float c, float dt, float nu, float dx2);
 __global__ void baseline_fv_slab_kernel(const float* in, float* out, float* flux_n, int B, int owned, int halo,
                                         int out_ld, int out_off, int vec, float c, float dt, float nu, float dx2);
 __global__ void pack_weights_kernel(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,

@@ -1234,3 +1234,20 @@ def test_latency_mode_forward_is_bit_identical(model, monkeypatch, nx, radius):
     monkeypatch.delenv("FLUXGNN_LATENCY")
     assert out["1"].shape == (2 * radius * nx,)
     np.testing.assert_array_equal(out["0"], out["1"])
+
+
+@pytest.mark.parametrize("nx,B,steps", [(64, 1, 50), (64, 20, 7), (128, 300, 3), (100, 5, 9), (1000, 2, 4), (37, 3, 5)])
+def test_baseline_persistent_short_grid_rollout_is_bit_identical(built_lib, monkeypatch, nx, B, steps):
+    """Grids in the direct-field-solve regime (the reference's default 64 cells): the whole classical rollout of an IC in
+    one persistent CTA must equal the launch-per-step path bit for bit (states, trajectory, fluxes)."""
+    from gnn_plasma_flux_b200 import BaselineSolver, _lib
+    sol = BaselineSolver(nx=nx, dt=1e-3, nu=1e-3)
+    ics = torch.from_numpy(np.stack([sol.initial_condition(seed=s) for s in range(B)])).cuda()
+    monkeypatch.setenv("FLUXGNN_BASELINE_PERSIST", "0")
+    want = sol.rollout(ics, steps, record_every=2 if steps > 2 else 1, record_flux=True)
+    monkeypatch.delenv("FLUXGNN_BASELINE_PERSIST")
+    before = _lib.launch_count()
+    got = sol.rollout(ics, steps, record_every=2 if steps > 2 else 1, record_flux=True)
+    assert _lib.launch_count() - before == 1
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
