@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FLUXGNN_LIB") or os.path.join(_HERE, "libfluxgnn.so")   # FLUXGNN_LIB: experiment builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_HOPS = 4
 MAX_LAYERS = 8
 HIDDEN = 128
@@ -64,6 +64,11 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p]),
     "fluxgnn_backward_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fluxgnn_backward_ring": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 11),
+    "fluxgnn_hybrid_step_train": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double,
+                                          c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fluxgnn_step_backward_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fluxgnn_hybrid_step_backward": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 5 + [c_int] * 3 + [c_float] * 2
+                                     + [c_void_p] * 11),
     "fluxgnn_rollout_metrics": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     "fluxgnn_hybrid_slab_step": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                          c_float, c_float, c_void_p]),

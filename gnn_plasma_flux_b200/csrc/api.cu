@@ -398,7 +398,8 @@ size_t fluxgnn_baseline_workspace_bytes(int B, int nx) {
 static int hybrid_rollout_impl(int precision, const void* packed, int num_layers, const float* state_in,
                                float* state_out, const float* x, const double* gtab, int B, int nx, double length,
                                int radius, float c, float dt, int steps, int record_every, float* traj,
-                               void* workspace, void* stream_, float* diag = nullptr) {
+                               void* workspace, void* stream_, float* diag = nullptr, float* acts = nullptr,
+                               float* face_flux = nullptr) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_model(packed, num_layers, B, nx, radius);
     if (rc != FLUXGNN_OK) return rc;
@@ -416,6 +417,9 @@ static int hybrid_rollout_impl(int precision, const void* packed, int num_layers
     a.do_update = 1;
     a.c = c; a.dt = dt;
     a.record_every = record_every < 1 ? 1 : record_every;
+    a.acts = acts;                                        // training step: the kernel also saves its activations
+    a.acts_stride = (long long)B * nx * kH;
+    a.face_flux = face_flux;
     int fast = 0;
     if (precision != 0) tc_configure(a, precision);
     rc = plan_tiles(a, &fast);
@@ -563,6 +567,47 @@ int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_
     bwd_input_kernel<<<g8, blk, 0, stream>>>(G2, acts, w_in, state, x, dstate, g_w_in, g_b_in, rows, nx);
     count_launch();
     FLUXGNN_CUDA_OK(cudaGetLastError());
+    return FLUXGNN_OK;
+}
+
+size_t fluxgnn_step_backward_workspace_bytes(int B, int nx) {
+    if (B < 1 || nx < 1) return 0;
+    return fluxgnn_backward_workspace_bytes(B, nx) + (size_t)2 * B * nx * sizeof(float);
+}
+
+int fluxgnn_hybrid_step_train(const void* packed, int num_layers, const float* state_in, float* state_out,
+                              const float* x, const double* gtab, int B, int nx, double length, int radius, float c,
+                              float dt, float* face_flux, float* acts, void* workspace, void* stream) {
+    if (!acts) return set_error(FLUXGNN_EINVAL, "hybrid_step_train: acts is required");
+    return hybrid_rollout_impl(0, packed, num_layers, state_in, state_out, x, gtab, B, nx, length, radius, c, dt, 1, 1,
+                               nullptr, workspace, stream, nullptr, acts, face_flux);
+}
+
+int fluxgnn_hybrid_step_backward(const float* w_in, const float* w_upd, const float* w_e1, const float* w_e2,
+                                 int num_layers, const float* state, const float* x, const float* acts,
+                                 const float* g_state_out, const float* g_face, int B, int nx, int radius, float c, float dt,
+                                 float* g_w_in, float* g_b_in, float* g_w_upd, float* g_b_upd, float* g_w_e1, float* g_b_e1,
+                                 float* g_w_e2, float* g_b_e2, float* dstate, void* workspace, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!g_state_out || !dstate || !workspace || !state)
+        return set_error(FLUXGNN_EINVAL, "hybrid_step_backward: null pointer");
+    if (B < 1 || nx < 1) return set_error(FLUXGNN_EINVAL, "hybrid_step_backward: bad shape (B=%d nx=%d)", B, nx);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    const long long cells = (long long)B * nx;
+    const long long blocks = (cells + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < 16LL * sms ? blocks : 16LL * sms);
+    float* dflux = (float*)((char*)workspace + fluxgnn_backward_workspace_bytes(B, nx));
+    step_bwd_flux_kernel<<<grid, 256, 0, stream>>>(g_state_out, g_face, dflux, cells, nx, c);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    rc = fluxgnn_backward_ring(w_in, w_upd, w_e1, w_e2, num_layers, state, x, acts, dflux, B, nx, radius, 1, g_w_in, g_b_in,
+                               g_w_upd, g_b_upd, g_w_e1, g_b_e1, g_w_e2, g_b_e2, dstate, workspace, stream_);
+    if (rc != FLUXGNN_OK) return rc;
+    step_bwd_direct_kernel<<<grid, 256, 0, stream>>>(g_state_out, state, dstate, cells, nx, c, dt);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
     return FLUXGNN_OK;
 }
 

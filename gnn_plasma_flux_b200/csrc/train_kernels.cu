@@ -316,4 +316,47 @@ __global__ void __launch_bounds__(256) bwd_input_kernel(const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward of the finite-volume part of one hybrid step (src/hybrid_solver.py:45-58 as the training
+// rollout writes it, scripts/training/train_ablation.py:180-195):
+//   F_i  = 0.5 (fwd_i + bwd_i)                       fwd_i = flux_edges[i], bwd_i = flux_edges[nx + i]
+//   n'_i = n_i - c (F_i - F_{i-1})
+//   u'_i = u_i - c (0.5 u_i^2 - 0.5 u_{i-1}^2) + dt E_i
+//   E'   = field solve of n', DETACHED (train_ablation.py:198-200: it goes through numpy)
+// step_bwd_flux_kernel: gradient w.r.t. the two hop-1 edge blocks from the gradients w.r.t. n' and
+// (optionally) the face flux itself:  dF_i = gF_i - c (gn'_i - gn'_{i+1});  dfwd_i = dbwd_i = 0.5 dF_i.
+__global__ void __launch_bounds__(256) step_bwd_flux_kernel(const float* __restrict__ g_out, const float* __restrict__ g_face,
+                                                            float* __restrict__ dflux, long long cells, int nx, float c) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < cells; t += (long long)gridDim.x * blockDim.x) {
+        const long long ic = t / nx;
+        const int i = (int)(t - ic * nx);
+        const int ip = (i + 1 == nx) ? 0 : i + 1;
+        const float* gn = g_out + ic * 3 * nx;
+        float dF = -c * (gn[i] - gn[ip]);
+        if (g_face != nullptr) dF += g_face[t];
+        float* d = dflux + ic * 2 * nx;
+        d[i] = 0.5f * dF;
+        d[nx + i] = 0.5f * dF;
+    }
+}
+
+// step_bwd_direct_kernel: the paths that do not go through the network, ADDED to dstate (which already
+// holds the network's input gradients):  dn_i += gn'_i;  du_i += gu'_i (1 - c u_i) + gu'_{i+1} c u_i;  dE_i += dt gu'_i.
+__global__ void __launch_bounds__(256) step_bwd_direct_kernel(const float* __restrict__ g_out, const float* __restrict__ state,
+                                                              float* __restrict__ dstate, long long cells, int nx, float c,
+                                                              float dt) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < cells; t += (long long)gridDim.x * blockDim.x) {
+        const long long ic = t / nx;
+        const int i = (int)(t - ic * nx);
+        const int ip = (i + 1 == nx) ? 0 : i + 1;
+        const float* g = g_out + ic * 3 * nx;
+        const float u = state[ic * 3 * nx + nx + i];
+        float* d = dstate + ic * 3 * nx;
+        const float gu = g[nx + i], gup = g[nx + ip];
+        d[i] += g[i];
+        d[nx + i] += gu * (1.0f - c * u) + gup * (c * u);
+        d[2 * (size_t)nx + i] += dt * gu;
+    }
+}
+
 }  // namespace fluxgnn

@@ -14,5 +14,9 @@ __global__ void bwd_edge_kernel(const float* P, const float* Q, const float* w2,
                                 float* dQ, float* dw2, float* db1, float* db2, long long rows, int nx, int hops);
 __global__ void bwd_input_kernel(const float* dH0, const float* H0, const float* w_in, const float* state,
                                  const float* x, float* dstate, float* dw_in, float* db_in, long long rows, int nx);
+__global__ void step_bwd_flux_kernel(const float* g_out, const float* g_face, float* dflux, long long cells, int nx,
+                                     float c);
+__global__ void step_bwd_direct_kernel(const float* g_out, const float* state, float* dstate, long long cells, int nx,
+                                       float c, float dt);
 
 }  // namespace fluxgnn

@@ -98,6 +98,36 @@ class HybridSolver:
                 work.data_ptr() if work is not None else None, stream), "fluxgnn_hybrid_rollout")
         return out, traj
 
+    def step_with_grad(self, state: torch.Tensor):
+        """One DIFFERENTIABLE step on state [B,3,nx] (or [3,nx]): returns (state', face_flux) with autograd edges to
+        `state` and to self.model's parameters -- the body of the reference's multi-step training rollout
+        (scripts/training/train_ablation.py:172-206: model -> face flux -> n', u' in torch ops -> field solve through
+        numpy) as one fused forward launch and one hand-written backward call.  E' carries no gradient (detached in
+        the reference, :198-200).  fp32 kernel, input_dim=4 / hidden_dim=128 models."""
+        from .autograd import hybrid_step_with_grad
+        base = self.baseline
+        if self.model.is_generic:
+            raise NotImplementedError("step_with_grad exists for input_dim=4, hidden_dim=128 models")
+        single = state.dim() == 2
+        if single:
+            state = state[None]
+        if state.dim() != 3 or state.shape[1] != 3 or state.shape[2] != base.nx:
+            raise ValueError(f"state must be [B,3,{base.nx}] or [3,{base.nx}], got {tuple(state.shape)}")
+        out, face = hybrid_step_with_grad(self.model, base.grid, base.length, self.graph_radius,
+                                          float(np.float32(base.dt / base.dx)), float(np.float32(base.dt)), state)
+        return (out[0], face[0]) if single else (out, face)
+
+    def rollout_with_grad(self, state: torch.Tensor, n_steps: int):
+        """n_steps chained step_with_grad calls: list of the n_steps + 1 states (state0 first, like run()) and the list
+        of the n_steps face fluxes, every one differentiable back to state0 and the parameters -- the
+        `rollout_steps` loop of train_ablation.py:172-206 without its per-step host round trip."""
+        states, faces = [state], []
+        for _ in range(n_steps):
+            nxt, face = self.step_with_grad(states[-1])
+            states.append(nxt)
+            faces.append(face)
+        return states, faces
+
     def rollout_diagnostics(self, state: torch.Tensor, n_steps: int):
         """Advance state [B,3,nx] (nx <= 128) by n_steps in one persistent launch and reduce the per-step
         diagnostics of the reference's evaluation scripts inside the kernel (no trajectory is stored):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FLUXGNN_ABI_VERSION 3
+#define FLUXGNN_ABI_VERSION 4
 
 #define FLUXGNN_OK        0
 #define FLUXGNN_EINVAL   -1   /* bad argument (shape, null pointer, unsupported size) */
@@ -248,6 +248,31 @@ int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_
                           float* g_w_in, float* g_b_in, float* g_w_upd, float* g_b_upd,
                           float* g_w_e1, float* g_b_e1, float* g_w_e2, float* g_b_e2,
                           float* dstate, void* workspace, void* stream);
+
+/* ---- one differentiable hybrid step (the training rollout) -----------
+ * The body of the reference's multi-step training rollout, scripts/training/train_ablation.py:172-206:
+ * per step  model(build_chain_graph(state)) -> face flux -> n', u' in torch ops (differentiable) ->
+ * field solve through numpy (DETACHED, :198-200).  Here the forward is ONE launch of the fused tile
+ * kernel in its activation-saving instantiation (plus the field-solve kernel for nx > 128), and the
+ * backward is fluxgnn_backward_ring bracketed by the two finite-volume adjoint kernels.
+ *   fluxgnn_hybrid_step_train: as fluxgnn_hybrid_rollout with steps = 1, and also writes
+ *       face_flux[B][nx] (nullable; F_pred of train_ablation.py:126) and acts (fluxgnn_train_acts_bytes).
+ *       workspace: fluxgnn_hybrid_workspace_bytes(B, nx) (may be NULL when that is 0).
+ *   fluxgnn_hybrid_step_backward: g_state_out[B][3][nx] = gradient w.r.t. the step's output (the E
+ *       channel is ignored: E' is detached), g_face[B][nx] = gradient w.r.t. face_flux (nullable).
+ *       ADDS the parameter gradients into g_* (as fluxgnn_backward_ring) and WRITES dstate[B][3][nx],
+ *       the gradient w.r.t. (n, u, E) of state_in through the network and through the update formulas.
+ *       workspace: fluxgnn_step_backward_workspace_bytes(B, nx). */
+int fluxgnn_hybrid_step_train(const void* packed, int num_layers, const float* state_in, float* state_out,
+                              const float* x, const double* gtab, int B, int nx, double length, int radius,
+                              float c, float dt, float* face_flux, float* acts, void* workspace, void* stream);
+size_t fluxgnn_step_backward_workspace_bytes(int B, int nx);
+int fluxgnn_hybrid_step_backward(const float* w_in, const float* w_upd, const float* w_e1, const float* w_e2,
+                                 int num_layers, const float* state, const float* x, const float* acts,
+                                 const float* g_state_out, const float* g_face, int B, int nx, int radius,
+                                 float c, float dt, float* g_w_in, float* g_b_in, float* g_w_upd, float* g_b_upd,
+                                 float* g_w_e1, float* g_b_e1, float* g_w_e2, float* g_b_e2, float* dstate,
+                                 void* workspace, void* stream);
 
 /* ---- rollout diagnostics on the device ---------------------------
  * The metrics every evaluation script of the reference computes on the host after

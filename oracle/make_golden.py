@@ -239,6 +239,7 @@ def main():
     comparison_goldens()
     long_rollout_goldens()
     generic_architecture_goldens()
+    training_rollout_goldens()
 
     manifest = {
         "generated_by": "oracle/make_golden.py",
@@ -397,9 +398,79 @@ def comparison_goldens():
     print("  wrote g9_comparison_models.npz")
 
 
+def training_rollout_goldens():
+    """G11: the reference's multi-step TRAINING rollout under its own autograd --
+    scripts/training/train_ablation.py:172-206 driven with the reference's FluxGNN, build_chain_graph and
+    that script's solve_poisson_np (detached, through numpy, as there) -- for the fused differentiable step
+    (HybridSolver.step_with_grad).  The loss is the script's multi-step energy term (:204-205) plus seeded
+    linear functionals of every step's face flux and of the final n, u, so that every gradient path carries
+    signal.  `python -m oracle.make_golden --only-g11` regenerates just this file."""
+    sys.path.insert(0, os.path.join(REF, "scripts", "training"))
+    from train_ablation import solve_poisson_np               # noqa: E402  (reference)
+    torch.set_num_threads(1)
+    w = dict(np.load(os.path.join(OUT, "weights_seed0.npz")))
+    g11 = {}
+    for tag, nx, radius, dt, steps in (("nx64_r1", 64, 1, 5e-3, 3), ("nx64_r3", 64, 3, 5e-3, 3), ("nx256_r2", 256, 2, 1e-3, 2)):
+        base = BaselineSolver(nx=nx, dt=dt)
+        dx = base.dx
+        ref_model = FluxGNN(input_dim=4, hidden_dim=128, num_layers=4)
+        ref_model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+        ref_model.train()
+        edges = torch.from_numpy(P.ring_edges(nx, radius))
+        ics = np.stack([base.initial_condition(seed=40 + s) for s in range(2)]).astype(np.float32)
+        rs = np.random.RandomState(7 + nx + radius)
+        cot_face = rs.randn(2, steps, nx).astype(np.float32)
+        cot_n = rs.randn(2, nx).astype(np.float32)
+        cot_u = rs.randn(2, nx).astype(np.float32)
+        x = torch.from_numpy(base.x.astype(np.float32))
+        loss = 0.0
+        st0 = [torch.from_numpy(ic).requires_grad_(True) for ic in ics]
+        finals, faces = [], []
+        for b in range(2):
+            state_roll = st0[b]
+            energies = []
+            for k in range(steps):                            # train_ablation.py:176-201
+                n_r, u_r, E_r = state_roll[0], state_roll[1], state_roll[2]
+                energies.append(0.5 * torch.mean(u_r ** 2))
+                node_f_r, _ = build_chain_graph(state_roll, x, device="cpu")
+                flux_edge_r = ref_model(node_f_r, edges)
+                F_r = 0.5 * (flux_edge_r[:nx] + flux_edge_r[nx:2 * nx])
+                n_next_r = n_r - (dt / dx) * (F_r - torch.roll(F_r, 1))
+                F_u_r = 0.5 * u_r * u_r
+                u_next_r = (u_r - (dt / dx) * (F_u_r - torch.roll(F_u_r, 1))) + dt * E_r
+                E_next_r = torch.from_numpy(solve_poisson_np(n_next_r.detach().cpu().numpy(), 1.0, dx))
+                state_roll = torch.stack([n_next_r, u_next_r, E_next_r], dim=0)
+                loss = loss + (F_r * torch.from_numpy(cot_face[b, k])).sum()
+                faces.append(F_r.detach().numpy())
+            energies = torch.stack(energies)
+            loss = loss + torch.mean((energies - energies[0]) ** 2)                 # :204-205
+            loss = loss + (state_roll[0] * torch.from_numpy(cot_n[b])).sum() + (state_roll[1] * torch.from_numpy(cot_u[b])).sum()
+            finals.append(state_roll.detach().numpy())
+        loss.backward()
+        g11[f"{tag}_ics"] = ics
+        g11[f"{tag}_cot_face"], g11[f"{tag}_cot_n"], g11[f"{tag}_cot_u"] = cot_face, cot_n, cot_u
+        g11[f"{tag}_final"] = np.stack(finals)
+        g11[f"{tag}_faces"] = np.stack(faces).reshape(2, steps, nx)
+        g11[f"{tag}_loss"] = np.float64(loss.item())
+        g11[f"{tag}_dstate0"] = np.stack([s.grad.numpy() for s in st0])
+        for name, p_ in ref_model.named_parameters():
+            g = p_.grad.numpy()
+            if g.size <= 1024:
+                g11[f"{tag}_grad_{name}"] = g
+            else:
+                g11[f"{tag}_gradnorm_{name}"] = np.float64(np.linalg.norm(g.astype(np.float64)))
+                g11[f"{tag}_gradcorner_{name}"] = g[:8, :8].copy()
+                g11[f"{tag}_gradrows_{name}"] = g[[5, 77], :].copy()
+        print(f"  ok  reference training rollout {tag}: loss {loss.item():.6e}")
+    np.savez_compressed(os.path.join(OUT, "g11_training_rollout.npz"), **g11)
+    print("  wrote g11_training_rollout.npz")
+
+
 if __name__ == "__main__":
     if "--only-g9" in sys.argv:
         comparison_goldens()
+    elif "--only-g11" in sys.argv:
+        training_rollout_goldens()
     elif "--only-g6b" in sys.argv:
         long_rollout_goldens()
     elif "--only-g10" in sys.argv:

@@ -7,6 +7,7 @@ Tolerances (BASELINE.json north_star): fp32 path <= 1e-5 relative per step
 reference's own fp32-vs-fp64 noise floor; integer/byte-exact work (n', u' of the
 classical solver, whose every fp32 rounding is reproduced) must be bit-exact.
 """
+import os
 import numpy as np
 import pytest
 import torch
@@ -1029,7 +1030,94 @@ def test_training_loop_reduces_flux_loss(weights, built_lib):
         loss = torch.mean((face - target) ** 2)
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(loss.item())
+    assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], losses[::6]
+
+
+@pytest.mark.parametrize("tag,nx,radius,dt,steps", [("nx64_r1", 64, 1, 5e-3, 3), ("nx64_r3", 64, 3, 5e-3, 3),
+                                                     ("nx256_r2", 256, 2, 1e-3, 2)])
+def test_training_rollout_vs_reference_autograd(weights, built_lib, tmp_path, tag, nx, radius, dt, steps):
+    """The fused differentiable step chained `steps` times (HybridSolver.rollout_with_grad) against the reference's
+    own training rollout under its own autograd (scripts/training/train_ablation.py:172-206, golden g11): same
+    loss -- the script's multi-step energy term plus seeded functionals of every face flux and of the final
+    n, u -- same gradients w.r.t. every parameter and w.r.t. the initial state.  Whole-IC tiles (nx=64) and
+    window tiles + FFT field solve (nx=256)."""
+    from gnn_plasma_flux_b200 import FluxGNN, HybridSolver, MODEL_CONFIG
+    g = load_golden("g11_training_rollout.npz")
+    m = FluxGNN(**MODEL_CONFIG)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    solver = HybridSolver(None, radius, nx=nx, dt=dt, model=m, graph_radius=radius)
+    solver.model.train()
+    st0 = torch.from_numpy(g[f"{tag}_ics"]).cuda().requires_grad_(True)
+    states, faces = solver.rollout_with_grad(st0, steps)
+    energies = torch.stack([0.5 * torch.mean(s[:, 1] ** 2, dim=1) for s in states[:-1]])        # [steps, B]
+    loss = torch.mean((energies - energies[0]) ** 2, dim=0).sum()
+    loss = loss + (torch.stack(faces, dim=1) * torch.from_numpy(g[f"{tag}_cot_face"]).cuda()).sum()
+    loss = loss + (states[-1][:, 0] * torch.from_numpy(g[f"{tag}_cot_n"]).cuda()).sum()
+    loss = loss + (states[-1][:, 1] * torch.from_numpy(g[f"{tag}_cot_u"]).cuda()).sum()
+    loss.backward()
+    assert P.rel_err(states[-1].detach().cpu().numpy(), g[f"{tag}_final"]).max() <= steps * STEP_TOL
+    assert _rel(torch.stack(faces, dim=1).detach().cpu().numpy(), g[f"{tag}_faces"]) <= steps * STEP_TOL
+    assert abs(loss.item() - float(g[f"{tag}_loss"])) <= 1e-4 * abs(float(g[f"{tag}_loss"]))
+    assert _rel(st0.grad.cpu().numpy(), g[f"{tag}_dstate0"]) <= GRAD_TOL
+    for name, p_ in solver.model.named_parameters():
+        gr = p_.grad.cpu().numpy()
+        if f"{tag}_grad_{name}" in g:
+            assert _rel(gr, g[f"{tag}_grad_{name}"]) <= GRAD_TOL, name
+        else:
+            assert abs(np.linalg.norm(gr.astype(np.float64)) / float(g[f"{tag}_gradnorm_{name}"]) - 1) <= GRAD_TOL, name
+            scale = np.abs(gr).max()
+            assert np.abs(gr[:8, :8] - g[f"{tag}_gradcorner_{name}"]).max() <= GRAD_TOL * scale, name
+            assert np.abs(gr[[5, 77], :] - g[f"{tag}_gradrows_{name}"]).max() <= GRAD_TOL * scale, name
+
+
+@pytest.mark.parametrize("nx,B,radius", [(64, 7, 3), (1024, 2, 2), (40, 3, 1)])
+def test_step_with_grad_forward_is_the_inference_step(weights, built_lib, nx, B, radius):
+    """The activation-saving instantiation computes the same step as the inference kernel, bit for bit, and the face
+    flux it returns is the one fluxgnn_forward_ring emits."""
+    from gnn_plasma_flux_b200 import FluxGNN, HybridSolver, MODEL_CONFIG
+    m = FluxGNN(**MODEL_CONFIG)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    solver = HybridSolver(None, radius, nx=nx, dt=1e-3, model=m, graph_radius=radius)
+    grid = P.Grid(nx=nx)
+    st = torch.from_numpy(np.stack([P.initial_condition(grid, seed=s) for s in range(B)])).cuda()
+    with torch.no_grad():
+        want, _ = solver.rollout(st, 1)
+    got, face = solver.step_with_grad(st.clone().requires_grad_(True))
+    assert got.requires_grad and face.requires_grad
+    if nx <= 128:
+        os.environ["FLUXGNN_LATENCY"] = "0"                     # few tiles: compare with the tile kernel, not latency mode
+        try:
+            with torch.no_grad():
+                want, _ = solver.rollout(st, 1)
+        finally:
+            del os.environ["FLUXGNN_LATENCY"]
+    assert torch.equal(got.detach(), want)
+    c = np.float32(solver.baseline.dt / solver.baseline.dx)
+    n1 = st[:, 0] - c * (face.detach() - torch.roll(face.detach(), 1, dims=1))
+    assert _rel(n1.cpu().numpy(), want[:, 0].cpu().numpy()) <= 1e-6
+
+
+def test_training_rollout_loop_reduces_energy_drift(weights, built_lib):
+    """A miniature of train_ablation.py's `multi_step` configuration: Adam on flux MSE + the 3-step energy term,
+    through HybridSolver.rollout_with_grad (fused forward, hand-written backward)."""
+    from gnn_plasma_flux_b200 import FluxGNN, HybridSolver, MODEL_CONFIG
+    torch.manual_seed(0)
+    solver = HybridSolver(None, 1, nx=64, dt=5e-3, model=FluxGNN(**MODEL_CONFIG))
+    solver.model.train()
+    grid = P.Grid(nx=64)
+    st = torch.from_numpy(np.stack([P.initial_condition(grid, seed=s) for s in range(8)])).cuda()
+    target = st[:, 0] * st[:, 1]
+    opt = torch.optim.Adam(solver.model.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(25):
+        opt.zero_grad()
+        states, faces = solver.rollout_with_grad(st, 3)
+        energies = torch.stack([0.5 * torch.mean(s[:, 1] ** 2, dim=1) for s in states[:-1]])
+        loss = torch.mean((faces[0] - target) ** 2) + 10.0 * torch.mean((energies - energies[0]) ** 2)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
     assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], losses[::6]
 
 
