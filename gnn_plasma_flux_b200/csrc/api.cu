@@ -111,6 +111,26 @@ static int plan_tiles(HybridArgs& a, int* fast_radius) {
         *fast_radius = (a.radius <= 4) ? a.radius : 0;
         if (a.tile_rows == kTileRows && a.tc_group_rows == 0 && a.tc_parts == 0 && a.acts == nullptr && *fast_radius > 0)
             choose_cluster(a, nx);
+        // Packed remainders: when the last window of an IC is short enough that several of them (each with its own halo
+        // on both sides) fit one tile, the last windows of consecutive ICs share tiles -- BASELINE configs[2]
+        // (1024 cells, radius 2: 9 windows of 110 cells + 34) takes 9.5 instead of 10 tiles per IC.  The arithmetic of
+        // a row does not depend on where in which tile it is computed: results are bit-identical (test hook
+        // FLUXGNN_NO_PACK=1 disables it).
+        const char* nopack = getenv("FLUXGNN_NO_PACK");
+        const int full = nx / a.valid, rem = nx - full * a.valid;
+        if (a.cluster <= 1 && full >= 1 && rem > 0 && a.B > 1 && !(nopack != nullptr && nopack[0] == '1')) {
+            const int seg = rem + 2 * a.halo, per_tile = rows / seg;
+            if (per_tile >= 2) {
+                a.pack_full = full;
+                a.pack_per_tile = per_tile < a.B ? per_tile : a.B;
+                a.pack_seg = seg;
+                a.pack_rem = rem;
+                a.tiles_per_ic = full;
+                const long long packed_tiles = (long long)a.B * full + ((long long)a.B + a.pack_per_tile - 1) / a.pack_per_tile;
+                if (packed_tiles > 0x7fffffffLL) return set_error(FLUXGNN_EINVAL, "too many tiles");
+                a.num_tiles = (int)packed_tiles;
+            }
+        }
     }
     // test hook: walk the prev/next tables even where the 128-bit window path applies
     const char* force = getenv("FLUXGNN_FORCE_GENERIC");

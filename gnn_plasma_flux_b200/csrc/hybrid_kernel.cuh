@@ -43,6 +43,9 @@ struct HybridArgs {
                                //    cluster hold consecutive, 4-row overlapping 128-row pieces of ONE window and read each
                                //    other's edge rows of Z through distributed shared memory, so only the cluster's two outer
                                //    ends carry a recomputed halo.  num_tiles / valid / tiles_per_ic count cluster windows.
+    int pack_full;             // window tiles of a periodic grid whose last window is short: > 0 = full windows per IC; the
+    int pack_per_tile;         //    first B * pack_full tiles are those, every later tile holds pack_per_tile LAST windows
+    int pack_seg, pack_rem;    //    (of consecutive ICs) as segments of pack_seg = pack_rem + 2 * halo rows, pack_rem owned each
     int ld_out, out_off;       // window / slab outputs: row length of state_out and offset of cell 0 in it
                                //    (0, 0 = [..][nx]; a slab that writes the interior of the next extended state
                                //    passes ld_out = nx + 2*halo, out_off = halo)

@@ -41,24 +41,38 @@ __device__ __forceinline__ void tile_load_row(const HybridArgs& a, const TileRow
             next = (cell == nx - 1) ? j - nx + 1 : j + 1;
         }
     } else {
-        ic = tile / a.tiles_per_ic;
-        const int t = tile - ic * a.tiles_per_ic;
-        // piece `crank` of a cluster window starts kClusterStep rows after its left neighbour; it owns the rows
-        // 4-hops .. 127-hops (first piece: from the halo; last piece: up to the halo), so the owned rows tile the window
-        const int csize = a.cluster > 1 ? a.cluster : 1;
-        const int wrow = crank * kClusterStep + jl;                     // row inside the window
-        const long long gcell = (long long)t * a.valid - a.halo + wrow;
-        cell = (int)(((gcell % nx) + nx) % nx);
-        live = tile_ok;
-        // (a row's outputs need the edge partial sums of the `hops` rows after it and the face flux of the row before it)
-        const int lo = (crank == 0) ? a.halo : 4 - a.hops, hi = (crank == csize - 1) ? rows - a.halo : rows - a.hops;
-        owned = tile_ok && (jl >= lo) && (jl < hi) && ((long long)t * a.valid + (wrow - a.halo) < nx);
-        if (a.slab) {                       // ghost cells instead of the periodic wrap
-            long long s = gcell + a.halo;
-            s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
-            src = (int)s;
-            ld = a.ld_in;
-            cell = (int)(gcell < 0 ? 0 : (gcell >= nx ? nx - 1 : gcell));
+        // packed remainders (api.cu plan_tiles): the short last windows of pack_per_tile consecutive ICs share one tile,
+        // each a segment with its own halo on both sides; rows next to a junction see the other segment's cells, which is
+        // harmless because they are halo rows whose results are dropped
+        const long long full_tiles = (long long)a.B * a.pack_full;
+        if (a.pack_full > 0 && tile >= full_tiles) {
+            const int seg = jl / a.pack_seg, w = jl - seg * a.pack_seg;
+            const long long lic = (long long)(tile - full_tiles) * a.pack_per_tile + seg;
+            ic = (int)lic;
+            live = tile_ok && seg < a.pack_per_tile && lic < a.B;
+            const long long gcell = (long long)a.pack_full * a.valid - a.halo + w;
+            cell = (int)(((gcell % nx) + nx) % nx);
+            owned = live && w >= a.halo && w < a.halo + a.pack_rem;
+        } else {
+            ic = tile / a.tiles_per_ic;
+            const int t = tile - ic * a.tiles_per_ic;
+            // piece `crank` of a cluster window starts kClusterStep rows after its left neighbour; it owns the rows
+            // 4-hops .. 127-hops (first piece: from the halo; last piece: up to the halo), so the owned rows tile the window
+            const int csize = a.cluster > 1 ? a.cluster : 1;
+            const int wrow = crank * kClusterStep + jl;                     // row inside the window
+            const long long gcell = (long long)t * a.valid - a.halo + wrow;
+            cell = (int)(((gcell % nx) + nx) % nx);
+            live = tile_ok;
+            // (a row's outputs need the edge partial sums of the `hops` rows after it and the face flux of the row before it)
+            const int lo = (crank == 0) ? a.halo : 4 - a.hops, hi = (crank == csize - 1) ? rows - a.halo : rows - a.hops;
+            owned = tile_ok && (jl >= lo) && (jl < hi) && ((long long)t * a.valid + (wrow - a.halo) < nx);
+            if (a.slab) {                       // ghost cells instead of the periodic wrap
+                long long s = gcell + a.halo;
+                s = s < 0 ? 0 : (s >= a.ld_in ? a.ld_in - 1 : s);
+                src = (int)s;
+                ld = a.ld_in;
+                cell = (int)(gcell < 0 ? 0 : (gcell >= nx ? nx - 1 : gcell));
+            }
         }
     }
     T.rowIC[j] = owned ? ic : -1;

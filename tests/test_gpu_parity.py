@@ -663,6 +663,37 @@ def test_cluster_windows_many_tiles_and_slabs(model, monkeypatch):
     monkeypatch.delenv("FLUXGNN_CLUSTER")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "tf32x3"])
+@pytest.mark.parametrize("nx,B,radius", [(1024, 5, 2), (1000, 9, 2), (240, 21, 1), (1024, 2, 2)])
+def test_packed_remainder_windows_are_bit_identical(model, weights, monkeypatch, precision, nx, B, radius):
+    """Grids whose last window is short (BASELINE configs[2]: 1024 cells at radius 2 = 9 windows of 110 cells + 34): the
+    last windows of consecutive ICs share tiles (csrc/api.cu plan_tiles, tile_common.cuh).  Where a row is computed does
+    not change its arithmetic: two steps, the forward fluxes of every hop and the training forward must equal the
+    unpacked tiling (FLUXGNN_NO_PACK=1) bit for bit, for full and partly filled remainder tiles, and match the oracle."""
+    dt = 3e-4 * 1024 / nx
+    grid = P.Grid(nx=nx, dt=dt)
+    ics = np.stack([P.stable_initial_condition(grid, s) for s in range(B)])
+    dev = torch.from_numpy(ics).cuda()
+    xd = torch.from_numpy(grid.x.astype(np.float32)).cuda()
+    sol = make_solver(model, nx, dt, graph_radius=radius, precision=precision)
+    hops = radius if precision == "fp32" else 1
+
+    def run():
+        step, _ = sol.rollout(dev, 2)
+        edges, face = model.ring_fluxes(dev, xd, radius=radius, hops=hops, want_face=True, precision=precision)
+        return step.clone(), edges.clone(), face.clone()
+
+    monkeypatch.setenv("FLUXGNN_NO_PACK", "1")
+    want = run()
+    monkeypatch.delenv("FLUXGNN_NO_PACK")
+    got = run()
+    for g_, w_ in zip(got, want):
+        assert torch.equal(g_, w_)
+    if precision == "fp32":
+        ref = batched.hybrid_run(weights, torch.from_numpy(ics), grid.x, grid.k, grid.dt, grid.dx, 2, radius=radius).numpy()
+        assert P.rel_err(got[0].cpu().numpy(), ref).max() <= 2 * STEP_TOL
+
+
 # ----------------------------------------------------------------------------- other architectures (generic kernels)
 GENERIC_ARCHS = {"f4h64l3": (4, 64, 3, 5), "f2h32l2": (2, 32, 2, 6), "f4h16l1": (4, 16, 1, 7)}
 
