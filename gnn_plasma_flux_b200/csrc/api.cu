@@ -562,7 +562,7 @@ int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_
     if (rc_sm != FLUXGNN_OK) return rc_sm;
     const long long row_groups = (rows + 7) / 8;                  // elementwise kernels: grid-stride, 8 rows per block pass
     const unsigned g8 = (unsigned)(row_groups < 16LL * sms ? row_groups : 16LL * sms);
-    const unsigned g64 = (unsigned)((rows + 63) / 64);
+    const unsigned g128 = (unsigned)((rows + 127) / 128);          // row-product GEMMs: one block per 128 rows
     const long long slabs = (rows + 255) / 256;                   // weight-gradient GEMMs: at most 2 blocks per SM
     const unsigned g256 = (unsigned)(slabs < 2LL * sms ? slabs : 2LL * sms);
     // edge readout
@@ -570,7 +570,7 @@ int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_
     const float* HL = acts + (size_t)L * stride;
     bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G0, HL, g_w_e1, 2 * kH, rows);          // d W1[:, :H] = dP^T h
     bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G1, HL, g_w_e1 + kH, 2 * kH, rows);     // d W1[:, H:] = dQ^T h
-    bwd_gemm_nn_kernel<<<g64, 256, 0, stream>>>(G0, w_e1, G1, w_e1 + kH, 2 * kH, G2, rows);
+    bwd_gemm_nn_kernel<<<g128, 256, 0, stream>>>(G0, w_e1, G1, w_e1 + kH, 2 * kH, G2, rows);
     count_launch(4);
     // message-passing layers, last to first
     for (int l = L - 1; l >= 0; --l) {
@@ -581,7 +581,7 @@ int fluxgnn_backward_ring(const float* w_in, const float* w_upd, const float* w_
                                                      nx, radius);
         bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G0, Hl, gW, 2 * kH, rows);           // d W[:, :H] = dpre^T h
         bwd_gemm_tn_kernel<<<g256, 256, 0, stream>>>(G1, Hl, gW + kH, 2 * kH, rows);      // d W[:, H:] = mean(dpre)^T h
-        bwd_gemm_nn_kernel<<<g64, 256, 0, stream>>>(G0, W, G1, W + kH, 2 * kH, G2, rows);
+        bwd_gemm_nn_kernel<<<g128, 256, 0, stream>>>(G0, W, G1, W + kH, 2 * kH, G2, rows);
         count_launch(4);
     }
     bwd_input_kernel<<<g8, blk, 0, stream>>>(G2, acts, w_in, state, x, dstate, g_w_in, g_b_in, rows, nx);

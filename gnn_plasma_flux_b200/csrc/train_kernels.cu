@@ -73,120 +73,149 @@ __global__ void __launch_bounds__(256) bwd_mask_mean_kernel(const float* __restr
     }
 }
 
-// C[rows][128] = A1[rows][128] W1[128][ldw] + A2[rows][128] W2[128][ldw]   (W row-major, first 128 columns used)
-// Block: 64 rows x 128 columns, 256 threads, 4 rows x 8 columns each, K in slabs of 16.
-__global__ void __launch_bounds__(256) bwd_gemm_nn_kernel(const float* __restrict__ A1, const float* __restrict__ W1,
-                                                          const float* __restrict__ A2, const float* __restrict__ W2,
-                                                          int ldw, float* __restrict__ C, long long rows) {
-    __shared__ float As[16][64 + 4];       // [k][row]
-    __shared__ float Ws[16][128];          // [k][col]
-    const int tid = threadIdx.x;
-    const int tr = tid >> 4, tc = tid & 15;                      // 16 x 16 threads
-    const long long row0 = (long long)blockIdx.x * 64;
-    float acc[4][8];
+// ---- the two GEMM shapes of the backward pass ----------------------------------------------------
+// Both are 128 x 128 output tiles over K slabs of 16 held k-major in shared memory (As[k][m], Bs[k][n]), 256 threads
+// with an 8 x 8 register tile each: thread (tm, tn) owns rows {4 tm .. 4 tm + 3} u {64 + 4 tm ..} and columns
+// {4 tn ..} u {64 + 4 tn ..}, so every operand load is a conflict-free LDS.128 (a quarter warp reads one broadcast
+// row chunk and eight consecutive column chunks).  Slabs are double-buffered: the next slab travels global ->
+// registers while the current one is multiplied, one __syncthreads per slab.
+constexpr int kSlab = 16;
+
+struct SlabRegs {
+    float4 a0, a1, b0, b1;
+};
+
+__device__ __forceinline__ void mma_slab(float (&acc)[8][8], const float (*As)[128], const float (*Bs)[128], int tm, int tn) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < kSlab; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][4 * tm]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + 4 * tm]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][4 * tn]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + 4 * tn]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int prod = 0; prod < 2; ++prod) {
-        const float* A = prod ? A2 : A1;
-        const float* W = prod ? W2 : W1;
-        if (A == nullptr) continue;
-        for (int k0 = 0; k0 < kH; k0 += 16) {
-            // A slab: 64 rows x 16 k  (thread: row = tid/4, 4 consecutive k)
-            {
-                const int r = tid >> 2, kq = (tid & 3) * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + r < rows) v = *reinterpret_cast<const float4*>(A + (row0 + r) * kH + k0 + kq);
-                As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
-            }
-            // W slab: 16 k x 128 columns  (thread: k = tid/16, 8 consecutive columns)
-            {
-                const int k = tid >> 4, c = (tid & 15) * 8;
-                const float4 v0 = *reinterpret_cast<const float4*>(W + (size_t)(k0 + k) * ldw + c);
-                const float4 v1 = *reinterpret_cast<const float4*>(W + (size_t)(k0 + k) * ldw + c + 4);
-                *reinterpret_cast<float4*>(&Ws[k][c]) = v0;
-                *reinterpret_cast<float4*>(&Ws[k][c + 4]) = v1;
-            }
-            __syncthreads();
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float4 a = *reinterpret_cast<const float4*>(&As[k][tr * 4]);
-                const float4 b0 = *reinterpret_cast<const float4*>(&Ws[k][tc * 8]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&Ws[k][tc * 8 + 4]);
-                const float av[4] = {a.x, a.y, a.z, a.w};
-                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-            }
-            __syncthreads();
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long r = row0 + tr * 4 + i;
-        if (r < rows) {
-            *reinterpret_cast<float4*>(C + r * kH + tc * 8) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            *reinterpret_cast<float4*>(C + r * kH + tc * 8 + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-        }
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
 }
 
-// dW[n][ldw-strided k] += sum_rows A[row][n] * Bm[row][k]   (both [rows][128]); split over row slabs.
-// Persistent blocks: each walks its share of the rows, keeps the full 128 x 128 partial product in
-// registers (256 threads x 8 x 8) and issues its atomicAdds once at the end.
-__global__ void __launch_bounds__(256) bwd_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
-                                                          float* __restrict__ dW, int ldw, long long rows) {
-    __shared__ float As[16][128];          // [row in slab][n]
-    __shared__ float Bs[16][128];          // [row in slab][k]
+// C[rows][128] = A1[rows][128] W1[128][ldw] + A2[rows][128] W2[128][ldw]   (W row-major, first 128 columns used)
+// One block per 128 rows; the 16 K slabs run over A1/W1 then A2/W2.  A is row-major, so its slab is transposed on
+// the way into shared memory (thread = one row, 8 consecutive k: 32 consecutive rows per warp -> conflict-free stores).
+__global__ void __launch_bounds__(256, 2) bwd_gemm_nn_kernel(const float* __restrict__ A1, const float* __restrict__ W1,
+                                                             const float* __restrict__ A2, const float* __restrict__ W2,
+                                                             int ldw, float* __restrict__ C, long long rows) {
+    __shared__ __align__(16) float As[2][kSlab][128];     // [k][row]
+    __shared__ __align__(16) float Bs[2][kSlab][128];     // [k][col]
     const int tid = threadIdx.x;
-    const int tn = tid >> 4, tk = tid & 15;
-    const long long per_block = ((rows + gridDim.x - 1) / gridDim.x + 15) / 16 * 16;
-    const long long row_begin = (long long)blockIdx.x * per_block;
-    const long long row_end = row_begin + per_block < rows ? row_begin + per_block : rows;
+    const int tm = tid >> 4, tn = tid & 15;
+    const long long row0 = (long long)blockIdx.x * 128;
+    const int lrow = tid & 127, lkq = (tid >> 7) * 8;             // A loader: row, first of 8 k
+    const int wk = tid >> 4, wc = (tid & 15) * 8;                  // W loader: k, first of 8 columns
+    const bool row_ok = row0 + lrow < rows;
+    const int slabs = (A2 != nullptr ? 2 : 1) * (kH / kSlab);
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    if (row_begin >= rows) return;
-    for (long long r0 = row_begin; r0 < row_end; r0 += 16) {
-        {
-            const int r = tid >> 4, c = (tid & 15) * 8;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
-            if (r0 + r < row_end) {
-                a0 = *reinterpret_cast<const float4*>(A + (r0 + r) * kH + c);
-                a1 = *reinterpret_cast<const float4*>(A + (r0 + r) * kH + c + 4);
-                b0 = *reinterpret_cast<const float4*>(Bm + (r0 + r) * kH + c);
-                b1 = *reinterpret_cast<const float4*>(Bm + (r0 + r) * kH + c + 4);
-            }
-            *reinterpret_cast<float4*>(&As[r][c]) = a0;
-            *reinterpret_cast<float4*>(&As[r][c + 4]) = a1;
-            *reinterpret_cast<float4*>(&Bs[r][c]) = b0;
-            *reinterpret_cast<float4*>(&Bs[r][c + 4]) = b1;
+    SlabRegs g;
+    auto fetch = [&](int sl) {
+        const float* A = sl < kH / kSlab ? A1 : A2;
+        const float* W = sl < kH / kSlab ? W1 : W2;
+        const int k0 = (sl % (kH / kSlab)) * kSlab;
+        g.a0 = g.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok) {
+            g.a0 = *reinterpret_cast<const float4*>(A + (row0 + lrow) * kH + k0 + lkq);
+            g.a1 = *reinterpret_cast<const float4*>(A + (row0 + lrow) * kH + k0 + lkq + 4);
         }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[r][tn * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[r][tn * 8 + 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[r][tk * 8]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[r][tk * 8 + 4]);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
+        g.b0 = *reinterpret_cast<const float4*>(W + (size_t)(k0 + wk) * ldw + wc);
+        g.b1 = *reinterpret_cast<const float4*>(W + (size_t)(k0 + wk) * ldw + wc + 4);
+    };
+    auto stash = [&](int buf) {
+        As[buf][lkq + 0][lrow] = g.a0.x; As[buf][lkq + 1][lrow] = g.a0.y; As[buf][lkq + 2][lrow] = g.a0.z; As[buf][lkq + 3][lrow] = g.a0.w;
+        As[buf][lkq + 4][lrow] = g.a1.x; As[buf][lkq + 5][lrow] = g.a1.y; As[buf][lkq + 6][lrow] = g.a1.z; As[buf][lkq + 7][lrow] = g.a1.w;
+        *reinterpret_cast<float4*>(&Bs[buf][wk][wc]) = g.b0;
+        *reinterpret_cast<float4*>(&Bs[buf][wk][wc + 4]) = g.b1;
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int sl = 0; sl < slabs; ++sl) {
+        const int buf = sl & 1;
+        if (sl + 1 < slabs) fetch(sl + 1);
+        mma_slab(acc, As[buf], Bs[buf], tm, tn);
+        if (sl + 1 < slabs) stash(buf ^ 1);
         __syncthreads();
     }
 #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + (i < 4 ? 4 * tm + i : 64 + 4 * tm + (i - 4));
+        if (r < rows) {
+            *reinterpret_cast<float4*>(C + r * kH + 4 * tn) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4*>(C + r * kH + 64 + 4 * tn) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+    }
+}
+
+// dW[n][ldw-strided k] += sum_rows A[row][n] * Bm[row][k]   (both [rows][128]); split over row ranges.
+// Persistent blocks: each walks its share of the rows in 16-row slabs (both operands are k-major as stored), keeps
+// the full 128 x 128 partial product in registers and issues its atomicAdds once at the end.
+__global__ void __launch_bounds__(256, 2) bwd_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                             float* __restrict__ dW, int ldw, long long rows) {
+    __shared__ __align__(16) float As[2][kSlab][128];     // [row in slab][n]
+    __shared__ __align__(16) float Bs[2][kSlab][128];     // [row in slab][k]
+    const int tid = threadIdx.x;
+    const int tm = tid >> 4, tn = tid & 15;
+    const long long per_block = ((rows + gridDim.x - 1) / gridDim.x + kSlab - 1) / kSlab * kSlab;
+    const long long row_begin = (long long)blockIdx.x * per_block;
+    const long long row_end = row_begin + per_block < rows ? row_begin + per_block : rows;
+    if (row_begin >= rows) return;
+    const int lr = tid >> 4, lc = (tid & 15) * 8;                  // loader: row in slab, first of 8 features
+    float acc[8][8];
+#pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(dW + (size_t)(tn * 8 + i) * ldw + tk * 8 + j, acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    SlabRegs g;
+    auto fetch = [&](long long r0) {
+        g.a0 = g.a1 = g.b0 = g.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + lr < row_end) {
+            g.a0 = *reinterpret_cast<const float4*>(A + (r0 + lr) * kH + lc);
+            g.a1 = *reinterpret_cast<const float4*>(A + (r0 + lr) * kH + lc + 4);
+            g.b0 = *reinterpret_cast<const float4*>(Bm + (r0 + lr) * kH + lc);
+            g.b1 = *reinterpret_cast<const float4*>(Bm + (r0 + lr) * kH + lc + 4);
+        }
+    };
+    auto stash = [&](int buf) {
+        *reinterpret_cast<float4*>(&As[buf][lr][lc]) = g.a0;
+        *reinterpret_cast<float4*>(&As[buf][lr][lc + 4]) = g.a1;
+        *reinterpret_cast<float4*>(&Bs[buf][lr][lc]) = g.b0;
+        *reinterpret_cast<float4*>(&Bs[buf][lr][lc + 4]) = g.b1;
+    };
+    fetch(row_begin);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (long long r0 = row_begin; r0 < row_end; r0 += kSlab) {
+        const bool more = r0 + kSlab < row_end;
+        if (more) fetch(r0 + kSlab);
+        mma_slab(acc, As[buf], Bs[buf], tm, tn);
+        if (more) stash(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = i < 4 ? 4 * tm + i : 64 + 4 * tm + (i - 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = j < 4 ? 4 * tn + j : 64 + 4 * tn + (j - 4);
+            atomicAdd(dW + (size_t)n * ldw + k, acc[i][j]);
+        }
+    }
 }
 
 // Edge readout backward.  P already contains b1.  For hop k (edge blocks [i -> i+k], [i+k -> i]):
