@@ -694,6 +694,27 @@ def test_packed_remainder_windows_are_bit_identical(model, weights, monkeypatch,
         assert P.rel_err(got[0].cpu().numpy(), ref).max() <= 2 * STEP_TOL
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("nx,B", [(64, 3001), (40, 2500), (128, 900)])
+def test_numpy_step_chunked_zero_copy_is_bit_identical(model, precision, nx, B):
+    """solver.step(numpy [B,3,nx]) for big batches runs as a few zero-copy launches over pinned staging memory
+    (HybridSolver._step_numpy_chunked); same kernel per IC, so it must equal the device-resident step bit for bit,
+    twice in a row (the staging buffers are reused)."""
+    if precision != "fp32" and nx == 40:
+        pytest.skip("tensor path: whole-IC tiles need nx in {32, 64, 128}")
+    grid = P.Grid(nx=nx, dt=1e-3)
+    base = np.stack([P.stable_initial_condition(grid, s) for s in range(16)])
+    ics = np.tile(base, (B // 16 + 1, 1, 1))[:B].copy()
+    ics[:, 1] += (1e-3 * np.random.RandomState(0).randn(B, 1)).astype(np.float32)
+    sol = make_solver(model, nx, 1e-3, graph_radius=2, precision=precision)
+    assert ics.nbytes >= sol.CHUNKED_MIN_BYTES
+    want, _ = sol.rollout(torch.from_numpy(ics).cuda(), 1)
+    for _ in range(2):
+        got = sol.step(ics)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == ics.shape
+        np.testing.assert_array_equal(got, want.cpu().numpy())
+
+
 # ----------------------------------------------------------------------------- other architectures (generic kernels)
 GENERIC_ARCHS = {"f4h64l3": (4, 64, 3, 5), "f2h32l2": (2, 32, 2, 6), "f4h16l1": (4, 16, 1, 7)}
 
