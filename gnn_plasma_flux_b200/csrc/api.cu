@@ -905,6 +905,33 @@ int fluxgnn_scan_slab_certify(int B, int S, int ranks, double length, const void
 }
 
 // Clusters of 8 CTAs the latency mode of fluxgnn_hybrid_rollout runs concurrently on the current device (0: unavailable).
+int fluxgnn_peer_halo_push(const float* state_ext, float* left_ext, float* right_ext, int B, int owned, int halo,
+                           int ch0, int ch1, void* stream) {
+    if (!state_ext || !left_ext || !right_ext || B < 1 || owned < 1 || halo < 1 || halo > owned || ch0 < 0 || ch1 > 3 ||
+        ch0 >= ch1)
+        return set_error(FLUXGNN_EINVAL, "peer_halo_push: bad argument (B=%d owned=%d halo=%d channels %d..%d)", B, owned,
+                         halo, ch0, ch1);
+    const long long total = (long long)B * (ch1 - ch0) * 2 * halo;
+    const unsigned grid = (unsigned)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
+    peer_halo_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(state_ext, left_ext, right_ext, B, owned, halo, ch0, ch1);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+int fluxgnn_peer_allgather(const void* src, long long bytes, const void* peer_bases_dev, long long offset, int rank,
+                           int world, void* stream) {
+    if (!src || !peer_bases_dev || bytes < 16 || bytes % 16 || offset < 0 || offset % 16 || rank < 0 || world < 1 ||
+        rank >= world || ((size_t)src & 15))
+        return set_error(FLUXGNN_EINVAL, "peer_allgather: bad argument (bytes=%lld offset=%lld rank=%d world=%d)", bytes,
+                         offset, rank, world);
+    peer_allgather_kernel<<<(unsigned)world, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, bytes,
+                                                                              (void* const*)peer_bases_dev, offset, rank);
+    FLUXGNN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return FLUXGNN_OK;
+}
+
 int fluxgnn_latency_cluster_slots(void) { return hybrid_latency_max_clusters(); }
 
 }  // extern "C"

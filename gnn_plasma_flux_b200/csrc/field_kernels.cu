@@ -456,4 +456,35 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w_in, const flo
     }
 }
 
+// ---- peer-memory exchange of a domain-decomposed grid (NVLink P2P stores, no NCCL on the step path) -------------
+// The ranks' extended states live in symmetric memory (every rank has every other rank's buffer mapped).  After a step a
+// rank stores its first / last `halo` cells straight into the ghost regions of its ring neighbours' extended states:
+//   left neighbour's right ghosts  ext_left [b][ch][halo + owned + i] = ext[b][ch][halo + i]
+//   right neighbour's left ghosts  ext_right[b][ch][i]               = ext[b][ch][owned + i]          i < halo
+// for the channels ch0 <= ch < ch1.  One thread per (b, ch, side, i).
+__global__ void __launch_bounds__(256) peer_halo_push_kernel(const float* __restrict__ ext, float* __restrict__ ext_left,
+                                                             float* __restrict__ ext_right, int B, int owned, int halo,
+                                                             int ch0, int ch1) {
+    const int ld = owned + 2 * halo;
+    const long long total = (long long)B * (ch1 - ch0) * 2 * halo;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % halo);
+        const int side = (int)((t / halo) & 1);
+        const long long bc = t / (2 * halo);
+        const int ch = ch0 + (int)(bc % (ch1 - ch0));
+        const long long b = bc / (ch1 - ch0);
+        const size_t row = ((size_t)b * 3 + ch) * ld;
+        if (side == 0) ext_left[row + halo + owned + i] = ext[row + halo + i];
+        else ext_right[row + i] = ext[row + owned + i];
+    }
+}
+
+// All-gather by peer stores: block p copies this rank's `bytes` (a multiple of 16) into slot `rank` of the gather
+// buffer of rank p, which sits `offset` bytes into p's symmetric allocation (bases[p]).
+__global__ void __launch_bounds__(256) peer_allgather_kernel(const uint4* __restrict__ src, long long bytes,
+                                                             void* const* __restrict__ bases, long long offset, int rank) {
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(bases[blockIdx.x]) + offset + (long long)rank * bytes);
+    for (long long i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace fluxgnn

@@ -153,4 +153,9 @@ cudaError_t launch_scan_slab_field(const float* n, long long n_ld, float* E, lon
 cudaError_t launch_scan_slab_certify(int B, int S, int ranks, double length, const void* msg_all, double tol, int step, int* flag,
                                      cudaStream_t stream);
 
+// field_kernels.cu: peer-memory (symmetric memory, NVLink P2P) halo stores and all-gather of a domain-decomposed grid
+__global__ void peer_halo_push_kernel(const float* ext, float* ext_left, float* ext_right, int B, int owned, int halo,
+                                      int ch0, int ch1);
+__global__ void peer_allgather_kernel(const uint4* src, long long bytes, void* const* bases, long long offset, int rank);
+
 }  // namespace fluxgnn

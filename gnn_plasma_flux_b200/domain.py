@@ -72,6 +72,83 @@ class TorchDistComm:
         return out
 
 
+# ------------------------------------------------------------------------------------------- peer memory
+class _PeerBlock:
+    """One symmetric allocation: the same number of bytes on every rank, every rank's copy addressable from here."""
+
+    def __init__(self, fabric, local, views, bases_dev, barrier):
+        self.fabric, self.local, self._views, self.bases_dev, self.barrier = fabric, local, views, bases_dev, barrier
+
+    def view(self, rank: int, offset_bytes: int, shape, dtype=torch.float32) -> torch.Tensor:
+        """Tensor over `shape` elements of rank `rank`'s copy, starting `offset_bytes` into it."""
+        return self._views(rank, offset_bytes, tuple(shape), dtype)
+
+
+class SymmetricMemoryFabric:
+    """Peer memory of the ranks of a process group, one process per GPU: torch.distributed._symmetric_memory
+    allocations (CUDA VMM, mapped into every rank over NVLink / NVSwitch) with their signal pads.  Halo cells and
+    field-solve messages are then plain stores into the neighbours' memory (fluxgnn_peer_halo_push,
+    fluxgnn_peer_allgather) ordered by the signal-pad barrier: no NCCL call on the step path."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        self._symm = symm
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def allocate(self, nbytes: int) -> _PeerBlock:
+        local = self._symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        hdl = self._symm.rendezvous(local, self.group.group_name)
+
+        def views(rank, offset_bytes, shape, dtype):
+            item = torch.empty((), dtype=dtype).element_size()
+            if rank == self.rank:
+                n = int(np.prod(shape)) * item
+                return local[offset_bytes:offset_bytes + n].view(dtype).view(shape)
+            return hdl.get_buffer(rank, shape, dtype, offset_bytes // item)
+
+        return _PeerBlock(self, local, views, int(hdl.buffer_ptrs_dev), hdl.barrier)
+
+
+class EmulatedFabric:
+    """G virtual ranks inside ONE process on one GPU (tests): `EmulatedFabric.create(G, device)` returns the G rank
+    objects; a peer's block is simply that rank's tensor, the barrier is stream order."""
+
+    def __init__(self, shared, rank, world, device):
+        self._shared, self.rank, self.world, self.device = shared, rank, world, torch.device(device)
+        self._count = 0
+
+    @classmethod
+    def create(cls, world: int, device="cuda"):
+        shared = {"blocks": {}, "bases": {}}
+        return [cls(shared, r, world, device) for r in range(world)]
+
+    def allocate(self, nbytes: int) -> _PeerBlock:
+        idx = self._count
+        self._count += 1
+        blocks = self._shared["blocks"].setdefault(idx, {})
+        local = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        blocks[self.rank] = local
+
+        def views(rank, offset_bytes, shape, dtype):
+            item = torch.empty((), dtype=dtype).element_size()
+            n = int(np.prod(shape)) * item
+            return blocks[rank][offset_bytes:offset_bytes + n].view(dtype).view(shape)
+
+        block = _PeerBlock(self, local, views, None, lambda: None)
+        shared, world, device = self._shared, self.world, self.device
+
+        def bases():            # device array of the G base pointers, built once every rank has allocated
+            if idx not in shared["bases"]:
+                shared["bases"][idx] = torch.tensor([blocks[r].data_ptr() for r in range(world)], dtype=torch.int64,
+                                                    device=device)
+            return shared["bases"][idx].data_ptr()
+
+        block._bases_fn = bases
+        return block
+
+
 # ------------------------------------------------------------------------------------------- field solve
 class DistributedFieldSolve:
     """Per-rank stages of the distributed spectral field solve (include/fluxgnn.h, fluxgnn_poisson_dist_*).
@@ -313,7 +390,16 @@ class _DomainDecomposedSolver:
     """Shared host logic: extended ping-pong state, halo exchange, field solve, step orchestration."""
 
     def __init__(self, nx, length, dt, halo, rank, world, device, field_solve, slab_fn=None, field_fn=None,
-                 field_stages=None, cert_tol=1e-5):
+                 field_stages=None, cert_tol=1e-5, fabric=None):
+        self._fabric = fabric                # peer memory (SymmetricMemoryFabric / EmulatedFabric): step_peer(), advance()
+        self._peer = {}
+        self._graphs = {}
+        if fabric is not None:
+            if field_solve not in ("auto", "scan"):
+                raise ValueError("the peer-memory step uses the distributed prefix-sum field solve: field_solve='scan'")
+            field_solve = "scan"
+            if (fabric.rank, fabric.world) != (rank, world):
+                raise ValueError(f"fabric is rank {fabric.rank} of {fabric.world}, the solver rank {rank} of {world}")
         if nx % world:
             raise ValueError(f"nx={nx} is not divisible by the number of ranks {world}")
         self.nx, self.length, self.dt = int(nx), float(length), float(dt)
@@ -348,6 +434,25 @@ class _DomainDecomposedSolver:
     # ---- extended state ----
     def _buffers(self, B: int):
         hit = self._ext.get(B)
+        if hit is None and self._fabric is not None:
+            # one symmetric block: the two extended states, then the gather buffer of the field-solve messages
+            rank, world = self.rank, self.world
+            ext_bytes = (B * 3 * self.ld * 4 + 255) // 256 * 256
+            msg_bytes = B * DistributedScanSolve.MSG_BYTES
+            block = self._fabric.allocate(2 * ext_bytes + world * msg_bytes)
+            left, right = (rank - 1) % world, (rank + 1) % world
+            shape = (B, 3, self.ld)
+            hit = [block.view(rank, k * ext_bytes, shape) for k in range(2)]
+            for t in hit:
+                t.zero_()
+            self._peer[B] = {"block": block, "msg_off": 2 * ext_bytes, "msg_bytes": msg_bytes, "left": None, "right": None,
+                             # the neighbours' views are resolved at the first push (all ranks have allocated by then)
+                             "neighbours": lambda: ([block.view(left, k * ext_bytes, shape) for k in range(2)],
+                                                    [block.view(right, k * ext_bytes, shape) for k in range(2)]),
+                             "msg_all": block.view(rank, 2 * ext_bytes, (world, msg_bytes), torch.uint8)}
+            self._ext[B] = hit
+            self._cur[B] = 0
+            self._edges[B] = None
         if hit is None:
             hit = [torch.zeros(B, 3, self.ld, dtype=torch.float32, device=self.device) for _ in range(2)]
             self._ext[B] = hit
@@ -426,6 +531,87 @@ class _DomainDecomposedSolver:
         self._cur[B] = 1 - self._cur[B]
         return self.interior(nxt)
 
+    # ---- one step over peer memory: no NCCL, three phases separated by two barriers ----
+    def _peer_push(self, B: int):
+        """My first / last H cells of the CURRENT state (n, u, E) -> the ghost zones of the ring neighbours' current
+        buffers (NVLink stores).  The neighbours read them after the next barrier."""
+        k, p = self._cur[B], self._peer[B]
+        if p["left"] is None:
+            p["left"], p["right"] = p["neighbours"]()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fluxgnn_peer_halo_push(self._ext[B][k].data_ptr(), p["left"][k].data_ptr(),
+                                                         p["right"][k].data_ptr(), B, self.owned, self.halo, 0, 3,
+                                                         _stream(self.device)), "fluxgnn_peer_halo_push")
+
+    def _peer_compute(self, B: int):
+        """Slab kernel (n', u' into the other buffer), this slab's prefix sums, and the 48-byte message per IC stored into
+        every rank's gather buffer."""
+        k, p = self._cur[B], self._peer[B]
+        nxt = self._ext[B][1 - k]
+        self._slab_fn(self._ext[B][k], nxt)
+        st = self._scan.state(B)
+        self._scan.sums(self.interior(nxt)[:, 0], st)
+        block = p["block"]
+        bases = block.bases_dev if block.bases_dev is not None else block._bases_fn()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fluxgnn_peer_allgather(st["msg"].data_ptr(), p["msg_bytes"], bases, p["msg_off"], self.rank,
+                                                         self.world, _stream(self.device)), "fluxgnn_peer_allgather")
+
+    def _peer_field(self, B: int):
+        """E' of this slab from the gathered messages; the new state becomes the current one."""
+        k, p = self._cur[B], self._peer[B]
+        inner = self.interior(self._ext[B][1 - k])
+        st = self._scan.state(B)
+        self._scan.field(inner[:, 0], inner[:, 2], p["msg_all"], st)
+        st["step"] += 1
+        self._cur[B] = 1 - k
+        return inner
+
+    def step_peer(self, local: torch.Tensor) -> torch.Tensor:
+        """step() over peer memory (the solver was built with fabric=...): halo push -> barrier -> slab kernel, slab sums,
+        message stores -> barrier -> field.  Every rank calls it together; returns the interior view like step()."""
+        if self._fabric is None:
+            raise ValueError("step_peer needs a solver built with fabric=SymmetricMemoryFabric(...)")
+        B = self._adopt(local).shape[0]
+        barrier = self._peer[B]["block"].barrier
+        self._peer_push(B)
+        barrier()
+        self._peer_compute(B)
+        barrier()
+        return self._peer_field(B)
+
+    def advance(self, local: torch.Tensor, n_steps: int, graph: bool = True) -> torch.Tensor:
+        """n_steps of step_peer.  graph=True: after two eager steps, PAIRS of steps (one per ping-pong buffer) are
+        captured once into a CUDA graph -- kernels, peer stores and barriers alike -- and replayed, so a step costs no
+        host work.  (The certificate index a replayed step reports is the one baked at capture: first_uncertified()
+        then tells THAT a field failed, not exactly which.)"""
+        state = local
+        done = 0
+        while done < min(n_steps, 2):
+            state = self.step_peer(state)
+            done += 1
+        pairs = (n_steps - done) // 2 if graph else 0
+        if pairs > 0:
+            B = state.shape[0]
+            g = self._graphs.get(B)
+            if g is None:
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                step0 = self._scan.state(B)["step"]
+                with torch.cuda.graph(g):
+                    self.step_peer(self.step_peer(state))
+                self._scan.state(B)["step"] = step0          # capture ran nothing
+                self._graphs[B] = g
+            for _ in range(pairs):
+                g.replay()
+            self._scan.state(B)["step"] += 2 * pairs
+            done += 2 * pairs
+            state = self.interior(self._ext[B][self._cur[B]])
+        while done < n_steps:
+            state = self.step_peer(state)
+            done += 1
+        return state
+
     def time_shares(self, local: torch.Tensor, comm, reps: int = 3):
         """Device time of a full step against the slab kernel alone (all ranks call this together):
         {"step_ms", "slab_kernel_ms", "exchange_and_solve_share"}."""
@@ -452,14 +638,14 @@ class DomainDecomposedHybridSolver(_DomainDecomposedSolver):
     """The hybrid step on one slab of a grid of `nx` cells split over `world` ranks."""
 
     def __init__(self, model, nx, length=2 * np.pi, dt=5e-3, graph_radius=1, rank=0, world=1, device="cuda",
-                 precision="fp32", slab_fn=None, field_fn=None, field_solve="auto", field_stages=None):
+                 precision="fp32", slab_fn=None, field_fn=None, field_solve="auto", field_stages=None, fabric=None):
         self.model = model
         self.radius = int(graph_radius)
         if precision != "fp32" and precision not in _lib.TC_PRECISIONS:
             raise ValueError(f"precision must be 'fp32' or one of {sorted(_lib.TC_PRECISIONS)}, got {precision!r}")
         self.precision = precision
         super().__init__(nx, length, dt, model.num_layers * self.radius + 1, rank, world, device, field_solve,
-                         slab_fn, field_fn, field_stages)
+                         slab_fn, field_fn, field_stages, fabric=fabric)
 
     def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor):
         tensor_path = self.precision != "fp32"
@@ -487,9 +673,10 @@ class DomainDecomposedBaselineSolver(_DomainDecomposedSolver):
     fluxgnn_baseline_slab_step, distributed field solve."""
 
     def __init__(self, nx, length=2 * np.pi, dt=5e-3, nu=1e-3, rank=0, world=1, device="cuda", slab_fn=None,
-                 field_fn=None, field_solve="auto", field_stages=None):
+                 field_fn=None, field_solve="auto", field_stages=None, fabric=None):
         self.nu = float(nu)
-        super().__init__(nx, length, dt, 4, rank, world, device, field_solve, slab_fn, field_fn, field_stages)
+        super().__init__(nx, length, dt, 4, rank, world, device, field_solve, slab_fn, field_fn, field_stages,
+                         fabric=fabric)
 
     def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor):
         B = ext.shape[0]
@@ -531,3 +718,15 @@ def step_emulated(solvers, locals_):
     for r in range(G):
         solvers[r]._cur[B] = 1 - solvers[r]._cur[B]
     return inner
+
+
+def step_peer_emulated(solvers, locals_):
+    """step_peer for G virtual ranks in one process (solvers built with the objects of EmulatedFabric.create(G)): the
+    three phases run rank by rank, stream order stands in for the barriers.  Exercises the real peer kernels."""
+    G = len(solvers)
+    B = [solvers[r]._adopt(locals_[r]).shape[0] for r in range(G)][0]
+    for r in range(G):
+        solvers[r]._peer_push(B)
+    for r in range(G):
+        solvers[r]._peer_compute(B)
+    return [solvers[r]._peer_field(B) for r in range(G)]

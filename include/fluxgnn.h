@@ -307,6 +307,21 @@ int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precisio
                                 int out_ld, int out_off, int B, int owned, int halo, int radius,
                                 float c, float dt, void* stream);
 
+/* ---- peer-memory exchange of a domain-decomposed grid (halo exchange + distributed field solve) ----
+ * For ranks whose extended states sit in SYMMETRIC memory (every rank has its peers' allocations mapped over
+ * NVLink; gnn_plasma_flux_b200.domain.SymmetricMemoryFabric): the exchange is plain stores into the peers'
+ * memory, ordered by the fabric's signal-pad barrier -- no NCCL call on the step path.
+ *   fluxgnn_peer_halo_push: stores channels ch0..ch1-1 of this rank's first / last `halo` owned cells into the
+ *       right ghosts of left_ext / the left ghosts of right_ext (the ring neighbours' extended states
+ *       [B][3][owned + 2*halo], peer pointers).
+ *   fluxgnn_peer_allgather: copies `bytes` (multiple of 16) from src into slot `rank` of every rank's gather
+ *       buffer, which sits `offset` bytes into that rank's symmetric allocation; peer_bases_dev is a DEVICE array
+ *       of the `world` allocation base pointers (torch's _SymmetricMemory.buffer_ptrs_dev). */
+int fluxgnn_peer_halo_push(const float* state_ext, float* left_ext, float* right_ext, int B, int owned, int halo,
+                           int ch0, int ch1, void* stream);
+int fluxgnn_peer_allgather(const void* src, long long bytes, const void* peer_bases_dev, long long offset, int rank,
+                           int world, void* stream);
+
 /* ---- one slab of the classical solver (baseline-only domain decomposition) ------
  * src/baseline_solver.py:80-94 (upwind fluxes, viscous Laplacian, forward Euler) for `owned`
  * consecutive cells of a longer periodic grid:  state_ext[B][3][owned + 2*halo] carries `halo` >= 1

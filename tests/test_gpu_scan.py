@@ -239,6 +239,46 @@ def test_hybrid_decomposed_scan_solve(precision, world, nx, radius):
     assert verdict is None or nx < (1 << 15), verdict
 
 
+@pytest.mark.parametrize("kind,world,nx,radius", [("baseline", 4, 1 << 14, 0), ("baseline", 1, 4096, 0), ("baseline", 2, 12000, 0),
+                                                   ("hybrid", 2, 1 << 12, 3), ("hybrid", 8, 1 << 15, 2)])
+def test_peer_memory_step_equals_the_collective_step(built_lib, kind, world, nx, radius):
+    """The step over peer memory (halo cells and field-solve messages stored straight into the neighbours' buffers:
+    fluxgnn_peer_halo_push, fluxgnn_peer_allgather; G virtual ranks on an EmulatedFabric) against the same solvers'
+    collective step (halo exchange + all-gather, emulated): bit-identical n', u', E' over four steps, and n', u' of the
+    first step bit-exact against the undivided solver."""
+    from gnn_plasma_flux_b200 import BaselineSolver, HybridSolver
+    from gnn_plasma_flux_b200.domain import (DomainDecomposedBaselineSolver, DomainDecomposedHybridSolver, EmulatedFabric,
+                                             split_slabs, step_emulated, step_peer_emulated)
+    from gnn_plasma_flux_b200.synthetic import seeded_model
+    if kind == "baseline":
+        dt = _stable_dt(nx)
+        whole = BaselineSolver(nx=nx, dt=dt, nu=1e-3, field_solve="spectral")
+        make = lambda r, fabric: DomainDecomposedBaselineSolver(nx, dt=dt, nu=1e-3, rank=r, world=world, device="cuda",
+                                                                field_solve="scan", fabric=fabric)
+        first = lambda st: whole.rollout(st, 1)[0]
+    else:
+        model = seeded_model(0, torch.device("cuda"))
+        dt = 0.02 * (2 * np.pi / nx)
+        whole = HybridSolver(None, radius, nx=nx, dt=dt, device="cuda", graph_radius=radius, model=model)
+        make = lambda r, fabric: DomainDecomposedHybridSolver(model, nx, dt=dt, graph_radius=radius, rank=r, world=world,
+                                                              device="cuda", field_solve="scan", fabric=fabric)
+        first = lambda st: whole.rollout(st, 1)[0]
+    _, ics = _ics(nx, 3, dt)
+    dev = torch.from_numpy(ics).cuda()
+    fabrics = EmulatedFabric.create(world, "cuda")
+    peers = [make(r, fabrics[r]) for r in range(world)]
+    colls = [make(r, None) for r in range(world)]
+    a, b = split_slabs(dev, world), split_slabs(dev, world)
+    for t in range(4):
+        a = step_peer_emulated(peers, a)
+        b = step_emulated(colls, b)
+        got, want = torch.cat(list(a), dim=-1), torch.cat(list(b), dim=-1)
+        assert torch.equal(got, want), t
+        if t == 0:
+            assert torch.equal(got[:, :2], first(dev)[:, :2])
+    assert torch.isfinite(got).all()
+
+
 @pytest.mark.parametrize("nx,B", [(1 << 20, 16), (1 << 22, 8), (1 << 18, 40)])
 def test_scan_repeated_launches_are_bit_stable(built_lib, nx, B):
     """Race hunt (the short form of scripts/stress_scan.py): at large batch every SM holds several CTAs whose bulk-copy
