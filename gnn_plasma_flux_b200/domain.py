@@ -445,6 +445,7 @@ class _DomainDecomposedSolver:
             hit = [block.view(rank, k * ext_bytes, shape) for k in range(2)]
             for t in hit:
                 t.zero_()
+            block.barrier()          # a faster neighbour must not push its halo cells before this rank has zeroed its buffers
             self._peer[B] = {"block": block, "msg_off": 2 * ext_bytes, "msg_bytes": msg_bytes, "left": None, "right": None,
                              # the neighbours' views are resolved at the first push (all ranks have allocated by then)
                              "neighbours": lambda: ([block.view(left, k * ext_bytes, shape) for k in range(2)],
@@ -581,32 +582,38 @@ class _DomainDecomposedSolver:
         return self._peer_field(B)
 
     def advance(self, local: torch.Tensor, n_steps: int, graph: bool = True) -> torch.Tensor:
-        """n_steps of step_peer.  graph=True: after two eager steps, PAIRS of steps (one per ping-pong buffer) are
-        captured once into a CUDA graph -- kernels, peer stores and barriers alike -- and replayed, so a step costs no
-        host work.  (The certificate index a replayed step reports is the one baked at capture: first_uncertified()
-        then tells THAT a field failed, not exactly which.)"""
-        state = local
-        done = 0
-        while done < min(n_steps, 2):
-            state = self.step_peer(state)
-            done += 1
-        pairs = (n_steps - done) // 2 if graph else 0
-        if pairs > 0:
-            B = state.shape[0]
-            g = self._graphs.get(B)
-            if g is None:
+        """n_steps of step_peer.  graph=True: PAIRS of steps (one per ping-pong buffer) are captured once into a CUDA graph
+        -- kernels, peer stores and barriers alike -- and replayed, so a step costs no host work; the first call runs two
+        eager steps before it captures.  (The certificate index a replayed step reports is the one baked at capture:
+        first_uncertified() then tells THAT a field failed, not exactly which.)"""
+        state, done = local, 0
+        B = local.shape[0]
+        if graph and n_steps >= 2:
+            hit = self._graphs.get(B)
+            if hit is None and n_steps >= 4:
+                state = self.step_peer(self.step_peer(state))
+                done = 2
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
-                step0 = self._scan.state(B)["step"]
+                st = self._scan.state(B)
+                step0, k0 = st["step"], self._cur[B]
                 with torch.cuda.graph(g):
                     self.step_peer(self.step_peer(state))
-                self._scan.state(B)["step"] = step0          # capture ran nothing
-                self._graphs[B] = g
-            for _ in range(pairs):
-                g.replay()
-            self._scan.state(B)["step"] += 2 * pairs
-            done += 2 * pairs
-            state = self.interior(self._ext[B][self._cur[B]])
+                st["step"] = step0                                # the capture ran nothing
+                hit = self._graphs[B] = (g, k0)
+            if hit is not None:
+                g, k0 = hit
+                self._adopt(state)                                # a foreign tensor is copied into the current buffer
+                if self._cur[B] != k0 and done < n_steps:         # the graph starts from buffer k0
+                    state = self.step_peer(state)
+                    done += 1
+                pairs = (n_steps - done) // 2
+                for _ in range(pairs):
+                    g.replay()
+                if pairs:
+                    self._scan.state(B)["step"] += 2 * pairs
+                    done += 2 * pairs
+                    state = self.interior(self._ext[B][self._cur[B]])
         while done < n_steps:
             state = self.step_peer(state)
             done += 1
