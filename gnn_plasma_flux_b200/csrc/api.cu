@@ -648,9 +648,9 @@ int fluxgnn_hybrid_slab_step(const void* packed, int num_layers, int precision, 
                                        halo, radius, c, dt, stream);
 }
 
-int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precision, const float* state_ext,
-                                const float* x_ext, float* state_out, int out_ld, int out_off, int B, int owned,
-                                int halo, int radius, float c, float dt, void* stream) {
+static int hybrid_slab_step_impl(const void* packed, int num_layers, int precision, const float* state_ext,
+                                 const float* x_ext, float* state_out, int out_ld, int out_off, int B, int owned,
+                                 int halo, int radius, float c, float dt, float* left_out, float* right_out, void* stream) {
     int rc = check_model(packed, num_layers, B, owned, radius);
     if (rc != FLUXGNN_OK) return rc;
     if (!state_ext || !x_ext || !state_out) return set_error(FLUXGNN_EINVAL, "hybrid_slab_step: null pointer");
@@ -694,6 +694,10 @@ int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precisio
                          out_ld, owned, out_off);
     a.ld_out = out_ld;
     a.out_off = out_off;
+    if ((left_out != nullptr || right_out != nullptr) && out_off < halo)
+        return set_error(FLUXGNN_EINVAL, "hybrid_slab_step_peer: the output rows need %d ghost cells in front of cell 0", halo);
+    a.peer_left = left_out;
+    a.peer_right = right_out;
     int fast = (radius <= 4) ? radius : 0;
     if (precision != 0) {
         rc = tc_shape_ok(0, owned, radius);
@@ -701,6 +705,21 @@ int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precisio
         fast = -radius;
     }
     return launch_tiles(a, fast, (cudaStream_t)stream);
+}
+
+int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precision, const float* state_ext,
+                                const float* x_ext, float* state_out, int out_ld, int out_off, int B, int owned,
+                                int halo, int radius, float c, float dt, void* stream) {
+    return hybrid_slab_step_impl(packed, num_layers, precision, state_ext, x_ext, state_out, out_ld, out_off, B, owned, halo,
+                                 radius, c, dt, nullptr, nullptr, stream);
+}
+
+int fluxgnn_hybrid_slab_step_peer(const void* packed, int num_layers, int precision, const float* state_ext,
+                                  const float* x_ext, float* state_out, int out_ld, int out_off, int B, int owned,
+                                  int halo, int radius, float c, float dt, float* left_out, float* right_out, void* stream) {
+    if (!left_out || !right_out) return set_error(FLUXGNN_EINVAL, "hybrid_slab_step_peer: null neighbour pointer");
+    return hybrid_slab_step_impl(packed, num_layers, precision, state_ext, x_ext, state_out, out_ld, out_off, B, owned, halo,
+                                 radius, c, dt, left_out, right_out, stream);
 }
 
 int fluxgnn_poisson_dist_pack(const float* n, long long ic_stride, int B, int S, void* z, void* stream) {
@@ -725,8 +744,9 @@ int fluxgnn_poisson_dist_local(void* y, void* scratch, int P, int S, int G, int 
     return launch_poisson_dist_local((float2*)y, (float2*)scratch, P, S, G, rank, length, (cudaStream_t)stream);
 }
 
-int fluxgnn_baseline_slab_step(const float* state_ext, float* state_out, int out_ld, int out_off, float* flux_n,
-                               int B, int owned, int halo, float c, float dt, float nu, float dx2, void* stream) {
+static int baseline_slab_step_impl(const float* state_ext, float* state_out, int out_ld, int out_off, float* flux_n,
+                                   int B, int owned, int halo, float c, float dt, float nu, float dx2, float* left_out,
+                                   float* right_out, void* stream) {
     if (!state_ext || !state_out || B < 1 || owned < 1 || halo < 1)
         return set_error(FLUXGNN_EINVAL, "baseline_slab_step: bad argument (B=%d owned=%d halo=%d)", B, owned, halo);
     if (out_off < 0 || out_ld < out_off + owned)
@@ -740,11 +760,28 @@ int fluxgnn_baseline_slab_step(const float* state_ext, float* state_out, int out
     const long long cells = (long long)B * owned;
     long long blocks = ((vec ? cells / 4 : cells) + 255) / 256;
     if (blocks > (long long)sms * 64) blocks = (long long)sms * 64;
+    if ((left_out != nullptr || right_out != nullptr) && (out_off < halo || owned < halo))
+        return set_error(FLUXGNN_EINVAL, "baseline_slab_step_peer: the output rows need %d ghost cells in front of cell 0", halo);
     baseline_fv_slab_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(state_ext, state_out, flux_n, B, owned, halo,
-                                                                              out_ld, out_off, vec ? 1 : 0, c, dt, nu, dx2);
+                                                                              out_ld, out_off, vec ? 1 : 0, c, dt, nu, dx2,
+                                                                              left_out, right_out);
     FLUXGNN_CUDA_OK(cudaGetLastError());
     count_launch();
     return FLUXGNN_OK;
+}
+
+int fluxgnn_baseline_slab_step(const float* state_ext, float* state_out, int out_ld, int out_off, float* flux_n,
+                               int B, int owned, int halo, float c, float dt, float nu, float dx2, void* stream) {
+    return baseline_slab_step_impl(state_ext, state_out, out_ld, out_off, flux_n, B, owned, halo, c, dt, nu, dx2, nullptr,
+                                   nullptr, stream);
+}
+
+int fluxgnn_baseline_slab_step_peer(const float* state_ext, float* state_out, int out_ld, int out_off, float* flux_n,
+                                    int B, int owned, int halo, float c, float dt, float nu, float dx2, float* left_out,
+                                    float* right_out, void* stream) {
+    if (!left_out || !right_out) return set_error(FLUXGNN_EINVAL, "baseline_slab_step_peer: null neighbour pointer");
+    return baseline_slab_step_impl(state_ext, state_out, out_ld, out_off, flux_n, B, owned, halo, c, dt, nu, dx2, left_out,
+                                   right_out, stream);
 }
 
 int fluxgnn_baseline_rollout(const float* state_in, float* state_out, const double* gtab, int B, int nx,
@@ -890,6 +927,22 @@ int fluxgnn_scan_slab_field(const float* n, long long n_ld, float* E, long long 
     if (rc != FLUXGNN_OK) return rc;
     FLUXGNN_CUDA_OK(launch_scan_slab_field(n, n_ld, E, e_ld, B, S, rank, ranks, length, msg_all, workspace, cert_tol, step,
                                            first_uncertified, sms, (cudaStream_t)stream));
+    count_launch();
+    return FLUXGNN_OK;
+}
+
+int fluxgnn_scan_slab_field_peer(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
+                                 double length, const void* msg_all, void* workspace, double cert_tol, int step,
+                                 int* first_uncertified, float* E_left, float* E_right, int halo, void* stream) {
+    if (!n || !E || !msg_all || !workspace || !first_uncertified || n_ld < S || e_ld < S || ranks < 1 || rank < 0 ||
+        rank >= ranks || !(length > 0.0) || !(cert_tol > 0.0) || step < 0 || !E_left || !E_right || halo < 1 || halo > S)
+        return set_error(FLUXGNN_EINVAL, "scan_slab_field_peer: bad argument");
+    if (!scan_slab_supported(B, S)) return set_error(FLUXGNN_EUNSUP, "scan_slab_field: needs S %% 8 == 0, S >= 64 (B=%d S=%d)", B, S);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    FLUXGNN_CUDA_OK(launch_scan_slab_field(n, n_ld, E, e_ld, B, S, rank, ranks, length, msg_all, workspace, cert_tol, step,
+                                           first_uncertified, sms, (cudaStream_t)stream, E_left, E_right, halo));
     count_launch();
     return FLUXGNN_OK;
 }

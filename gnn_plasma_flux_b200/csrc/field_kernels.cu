@@ -181,9 +181,24 @@ __global__ void __launch_bounds__(256) baseline_small_rollout_kernel(const float
 __global__ void __launch_bounds__(256) baseline_fv_slab_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                float* __restrict__ flux_n, int B, int owned, int halo,
                                                                int out_ld, int out_off, int vec,
-                                                               float c, float dt, float nu, float dx2) {
+                                                               float c, float dt, float nu, float dx2,
+                                                               float* __restrict__ left_out, float* __restrict__ right_out) {
     const float rdx2 = fv_reciprocal(dx2);
     const int ld = owned + 2 * halo;
+    // slabs over peer memory (left_out / right_out = the ring neighbours' next extended states, nullable): n', u' of the
+    // first / last `halo` owned cells also go into the neighbours' ghost zones -- the halo exchange is this store
+    auto edge_store = [&](int ic, int cell, float nv, float uv) {
+        if (left_out != nullptr && cell < halo) {
+            float* pl = left_out + (size_t)ic * 3 * out_ld + out_off + owned + cell;
+            pl[0] = nv;
+            pl[out_ld] = uv;
+        }
+        if (right_out != nullptr && cell >= owned - halo) {
+            float* pr = right_out + (size_t)ic * 3 * out_ld + out_off - owned + cell;
+            pr[0] = nv;
+            pr[out_ld] = uv;
+        }
+    };
     if (vec) {
         const int quads = owned >> 2;
         const long long total = (long long)B * quads;
@@ -207,6 +222,10 @@ __global__ void __launch_bounds__(256) baseline_fv_slab_kernel(const float* __re
             *reinterpret_cast<float4*>(po + out_ld) = make_float4(a.u, b.u, d.u, e.u);
             if (flux_n != nullptr)
                 *reinterpret_cast<float4*>(flux_n + (size_t)ic * owned + i) = make_float4(a.fn, b.fn, d.fn, e.fn);
+            if (i < halo || i + 4 > owned - halo) {
+                edge_store(ic, i, a.n, a.u); edge_store(ic, i + 1, b.n, b.u);
+                edge_store(ic, i + 2, d.n, d.u); edge_store(ic, i + 3, e.n, e.u);
+            }
         }
         return;
     }
@@ -221,6 +240,7 @@ __global__ void __launch_bounds__(256) baseline_fv_slab_kernel(const float* __re
         float* po = out + (size_t)ic * 3 * out_ld + out_off + i;
         po[0] = o.n;
         po[out_ld] = o.u;
+        edge_store(ic, i, o.n, o.u);
         if (flux_n != nullptr) flux_n[idx] = o.fn;
     }
 }

@@ -82,7 +82,8 @@ constexpr int kBaselineSmallMaxNx = 1024;     // persistent one-CTA-per-IC class
 __global__ void baseline_small_rollout_kernel(const float* in, float* out, float* traj, float* flux_n, const double* gtab, int B,
                                               int nx, int steps, int record_every, float c, float dt, float nu, float dx2);
 __global__ void baseline_fv_slab_kernel(const float* in, float* out, float* flux_n, int B, int owned, int halo,
-                                        int out_ld, int out_off, int vec, float c, float dt, float nu, float dx2);
+                                        int out_ld, int out_off, int vec, float c, float dt, float nu, float dx2,
+                                        float* left_out, float* right_out);
 __global__ void pack_weights_kernel(const float* w_in, const float* b_in, const float* w_upd, const float* b_upd,
                                     const float* w_e1, const float* b_e1, const float* w_e2, const float* b_e2,
                                     int L, float* packed);
@@ -149,7 +150,7 @@ cudaError_t launch_scan_slab_sums(const float* n, long long n_ld, int B, int S, 
                                   int sms, cudaStream_t stream);
 cudaError_t launch_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
                                    double length, const void* msg_all, void* workspace, double tol, int step, int* flag, int sms,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, float* E_left = nullptr, float* E_right = nullptr, int halo = 0);
 cudaError_t launch_scan_slab_certify(int B, int S, int ranks, double length, const void* msg_all, double tol, int step, int* flag,
                                      cudaStream_t stream);
 

@@ -46,6 +46,9 @@ struct HybridArgs {
     int pack_full;             // window tiles of a periodic grid whose last window is short: > 0 = full windows per IC; the
     int pack_per_tile;         //    first B * pack_full tiles are those, every later tile holds pack_per_tile LAST windows
     int pack_seg, pack_rem;    //    (of consecutive ICs) as segments of pack_seg = pack_rem + 2 * halo rows, pack_rem owned each
+    float* peer_left;          // slabs over peer memory (nullable): the ring neighbours' NEXT extended states, laid out like
+    float* peer_right;         //    state_out (ld_out, out_off).  n', u' of the first / last `halo` owned cells are ALSO stored
+                               //    into the left neighbour's right ghost zone / the right neighbour's left ghost zone (NVLink)
     int ld_out, out_off;       // window / slab outputs: row length of state_out and offset of cell 0 in it
                                //    (0, 0 = [..][nx]; a slab that writes the interior of the next extended state
                                //    passes ld_out = nx + 2*halo, out_off = halo)

@@ -494,6 +494,9 @@ struct SlabFieldArgs {
     const SlabMsg* msg_all;      // [ranks][B]
     SlabSeg* seg_rec;            // [B][segs]: S, M1 of this launch's density in; D4, maxE of the field reconstructed here out
     int* flag;
+    float* E_left;               // slabs over peer memory (nullable): the E rows of the ring neighbours' next states, laid out like
+    float* E_right;              //   E / e_ld.  The first / last `halo` cells of this slab's field are ALSO stored into the left
+    int halo;                    //   neighbour's right ghost zone (its cells S .. S+halo-1) / the right one's left ghosts (-halo .. -1)
 };
 
 __global__ void __launch_bounds__(kSlabThreads) slab_field_kernel(const SlabFieldArgs a) {
@@ -614,6 +617,18 @@ __global__ void __launch_bounds__(kSlabThreads) slab_field_kernel(const SlabFiel
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) out[j0 + i] = ev[i];
+        }
+        if (a.E_left != nullptr && j0 < a.halo) {              // the halo exchange of E' is this store
+            float* pl = a.E_left + (size_t)ic * a.e_ld + S;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (j0 + i < a.halo) pl[j0 + i] = ev[i];
+        }
+        if (a.E_right != nullptr && j0 + 8 > S - a.halo) {
+            float* pr = a.E_right + (size_t)ic * a.e_ld - S;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (j0 + i >= S - a.halo) pr[j0 + i] = ev[i];
         }
     }
     double d = warp_sum((double)accD);
@@ -749,8 +764,9 @@ cudaError_t launch_scan_slab_sums(const float* n, long long n_ld, int B, int S, 
 
 cudaError_t launch_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
                                    double length, const void* msg_all, void* workspace, double tol, int step, int* flag, int sms,
-                                   cudaStream_t stream) {
+                                   cudaStream_t stream, float* E_left, float* E_right, int halo) {
     SlabFieldArgs a;
+    a.E_left = E_left; a.E_right = E_right; a.halo = halo;
     a.n = n; a.n_ld = n_ld; a.E = E; a.e_ld = e_ld;
     a.B = B; a.S = S; a.rank = rank; a.ranks = ranks; a.step = step;
     slab_geometry(B, S, sms, &a.segs, &a.seg_chunks);

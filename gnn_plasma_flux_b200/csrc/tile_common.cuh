@@ -113,6 +113,18 @@ __device__ __forceinline__ void tile_store_window_row(const HybridArgs& a, const
     float* so = a.state_out + (size_t)T.rowIC[j] * 3 * ld + a.out_off + T.rowCell[j];
     so[0] = n_new;
     so[ld] = u_new;
+    // slabs over peer memory: the halo exchange is this store (the neighbours' ghost zones of their next state)
+    const int cell = T.rowCell[j];
+    if (a.peer_left != nullptr && cell < a.halo) {
+        float* pl = a.peer_left + (size_t)T.rowIC[j] * 3 * ld + a.out_off + a.nx + cell;
+        pl[0] = n_new;
+        pl[ld] = u_new;
+    }
+    if (a.peer_right != nullptr && cell >= a.nx - a.halo) {
+        float* pr = a.peer_right + (size_t)T.rowIC[j] * 3 * ld + a.out_off - a.nx + cell;
+        pr[0] = n_new;
+        pr[ld] = u_new;
+    }
 }
 
 // Whole-IC tiles: the new state stays in shared memory; rho = n' - n0 (src/baseline_solver.py:60).

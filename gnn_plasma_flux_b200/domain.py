@@ -306,10 +306,19 @@ class DistributedScanSolve:
                                                      self.rank * self.S, st["work"].data_ptr(), st["msg"].data_ptr(),
                                                      _stream(self.device)), "fluxgnn_scan_slab_sums")
 
-    def field(self, n_rows: torch.Tensor, E_rows: torch.Tensor, msg_all: torch.Tensor, st):
+    def field(self, n_rows: torch.Tensor, E_rows: torch.Tensor, msg_all: torch.Tensor, st, peers=None):
+        """peers = (E rows of the left neighbour's next state, of the right neighbour's, halo): the kernel also stores the
+        slab's edge cells of E' into the neighbours' ghost zones (peer memory)."""
         if self._stages:
             return self._stages["field"](self, n_rows, E_rows, msg_all, st)
         B = n_rows.shape[0]
+        if peers is not None:
+            _lib.check(_lib.lib().fluxgnn_scan_slab_field_peer(
+                n_rows.data_ptr(), n_rows.stride(0) if B > 1 else self.S, E_rows.data_ptr(), E_rows.stride(0) if B > 1 else self.S,
+                B, self.S, self.rank, self.world, self.length, msg_all.data_ptr(), st["work"].data_ptr(), self.cert_tol,
+                st["step"], st["flag"].data_ptr(), peers[0].data_ptr(), peers[1].data_ptr(), peers[2], _stream(self.device)),
+                "fluxgnn_scan_slab_field_peer")
+            return
         _lib.check(_lib.lib().fluxgnn_scan_slab_field(
             n_rows.data_ptr(), n_rows.stride(0) if B > 1 else self.S, E_rows.data_ptr(), E_rows.stride(0) if B > 1 else self.S,
             B, self.S, self.rank, self.world, self.length, msg_all.data_ptr(), st["work"].data_ptr(), self.cert_tol, st["step"],
@@ -475,7 +484,8 @@ class _DomainDecomposedSolver:
         bufs = self._buffers(B)
         cur = bufs[self._cur[B]]
         mine = self.interior(cur)
-        if not (local.data_ptr() == mine.data_ptr() and local.stride() == mine.stride()):
+        self._fresh = not (local.data_ptr() == mine.data_ptr() and local.stride() == mine.stride())
+        if self._fresh:
             mine.copy_(local.to(device=self.device, dtype=torch.float32))
         return cur
 
@@ -532,24 +542,38 @@ class _DomainDecomposedSolver:
         self._cur[B] = 1 - self._cur[B]
         return self.interior(nxt)
 
-    # ---- one step over peer memory: no NCCL, three phases separated by two barriers ----
-    def _peer_push(self, B: int):
-        """My first / last H cells of the CURRENT state (n, u, E) -> the ghost zones of the ring neighbours' current
-        buffers (NVLink stores).  The neighbours read them after the next barrier."""
-        k, p = self._cur[B], self._peer[B]
+    # ---- one step over peer memory: no NCCL; the exchange is fused into the producing kernels ----
+    def _neighbours(self, B: int):
+        p = self._peer[B]
         if p["left"] is None:
             p["left"], p["right"] = p["neighbours"]()
+        return p
+
+    def _peer_push(self, B: int):
+        """My first / last H cells of the CURRENT state (n, u, E) -> the ghost zones of the ring neighbours' current
+        buffers (NVLink stores).  Only after a state was copied in from outside; in the steady state the slab and field
+        kernels have stored them already."""
+        k, p = self._cur[B], self._neighbours(B)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().fluxgnn_peer_halo_push(self._ext[B][k].data_ptr(), p["left"][k].data_ptr(),
                                                          p["right"][k].data_ptr(), B, self.owned, self.halo, 0, 3,
                                                          _stream(self.device)), "fluxgnn_peer_halo_push")
 
+    def _peer_begin(self, local: torch.Tensor) -> int:
+        """Adopt `local`; a state copied in from outside also needs its edge cells pushed to the neighbours (every rank
+        passes the same kind of state, so the barrier count matches)."""
+        B = self._adopt(local).shape[0]
+        if self._fresh:
+            self._peer_push(B)
+            self._peer[B]["block"].barrier()
+        return B
+
     def _peer_compute(self, B: int):
-        """Slab kernel (n', u' into the other buffer), this slab's prefix sums, and the 48-byte message per IC stored into
-        every rank's gather buffer."""
-        k, p = self._cur[B], self._peer[B]
+        """Slab kernel: n', u' into the other buffer AND, for the edge cells, into the neighbours' ghost zones of THEIR
+        other buffer; then this slab's prefix sums and the 48-byte message per IC stored into every rank's gather buffer."""
+        k, p = self._cur[B], self._neighbours(B)
         nxt = self._ext[B][1 - k]
-        self._slab_fn(self._ext[B][k], nxt)
+        self._slab_fn(self._ext[B][k], nxt, p["left"][1 - k], p["right"][1 - k])
         st = self._scan.state(B)
         self._scan.sums(self.interior(nxt)[:, 0], st)
         block = p["block"]
@@ -559,27 +583,30 @@ class _DomainDecomposedSolver:
                                                          self.world, _stream(self.device)), "fluxgnn_peer_allgather")
 
     def _peer_field(self, B: int):
-        """E' of this slab from the gathered messages; the new state becomes the current one."""
-        k, p = self._cur[B], self._peer[B]
+        """E' of this slab from the gathered messages, its edge cells also into the neighbours' ghost zones; the new state
+        becomes the current one."""
+        k, p = self._cur[B], self._neighbours(B)
         inner = self.interior(self._ext[B][1 - k])
         st = self._scan.state(B)
-        self._scan.field(inner[:, 0], inner[:, 2], p["msg_all"], st)
+        peers = (self.interior(p["left"][1 - k])[:, 2], self.interior(p["right"][1 - k])[:, 2], self.halo)
+        self._scan.field(inner[:, 0], inner[:, 2], p["msg_all"], st, peers)
         st["step"] += 1
         self._cur[B] = 1 - k
         return inner
 
     def step_peer(self, local: torch.Tensor) -> torch.Tensor:
-        """step() over peer memory (the solver was built with fabric=...): halo push -> barrier -> slab kernel, slab sums,
-        message stores -> barrier -> field.  Every rank calls it together; returns the interior view like step()."""
+        """step() over peer memory (the solver was built with fabric=...): slab kernel (+ halo stores of n', u'), slab
+        sums, message stores -> barrier -> field kernel (+ halo stores of E') -> barrier.  Every rank calls it together;
+        returns the interior view like step()."""
         if self._fabric is None:
             raise ValueError("step_peer needs a solver built with fabric=SymmetricMemoryFabric(...)")
-        B = self._adopt(local).shape[0]
+        B = self._peer_begin(local)
         barrier = self._peer[B]["block"].barrier
-        self._peer_push(B)
-        barrier()
         self._peer_compute(B)
         barrier()
-        return self._peer_field(B)
+        out = self._peer_field(B)
+        barrier()
+        return out
 
     def advance(self, local: torch.Tensor, n_steps: int, graph: bool = True) -> torch.Tensor:
         """n_steps of step_peer.  graph=True: PAIRS of steps (one per ping-pong buffer) are captured once into a CUDA graph
@@ -603,7 +630,7 @@ class _DomainDecomposedSolver:
                 hit = self._graphs[B] = (g, k0)
             if hit is not None:
                 g, k0 = hit
-                self._adopt(state)                                # a foreign tensor is copied into the current buffer
+                self._peer_begin(state)                           # a foreign tensor is copied in and its edges pushed
                 if self._cur[B] != k0 and done < n_steps:         # the graph starts from buffer k0
                     state = self.step_peer(state)
                     done += 1
@@ -654,17 +681,22 @@ class DomainDecomposedHybridSolver(_DomainDecomposedSolver):
         super().__init__(nx, length, dt, model.num_layers * self.radius + 1, rank, world, device, field_solve,
                          slab_fn, field_fn, field_stages, fabric=fabric)
 
-    def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor):
+    def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor, left=None, right=None):
+        """left / right: the ring neighbours' next extended states (peer memory) -- the kernel then stores the edge cells of
+        n', u' into their ghost zones too."""
         tensor_path = self.precision != "fp32"
         packed = self.model.packed_weights(_lib.weight_layout(self.precision))
         B = ext.shape[0]
         with torch.cuda.device(self.device):
             dx = self.length / self.nx
-            _lib.check(_lib.lib().fluxgnn_hybrid_slab_step_ld(
-                packed.data_ptr(), self.model.num_layers, _lib.TC_PRECISIONS[self.precision] if tensor_path else 0,
-                ext.data_ptr(), self.x_ext.data_ptr(), nxt.data_ptr(), self.ld, self.halo, B, self.owned, self.halo,
-                self.radius, float(np.float32(self.dt / dx)), float(np.float32(self.dt)), _stream(self.device)),
-                "fluxgnn_hybrid_slab_step_ld")
+            head = (packed.data_ptr(), self.model.num_layers, _lib.TC_PRECISIONS[self.precision] if tensor_path else 0,
+                    ext.data_ptr(), self.x_ext.data_ptr(), nxt.data_ptr(), self.ld, self.halo, B, self.owned, self.halo,
+                    self.radius, float(np.float32(self.dt / dx)), float(np.float32(self.dt)))
+            if left is not None:
+                _lib.check(_lib.lib().fluxgnn_hybrid_slab_step_peer(*head, left.data_ptr(), right.data_ptr(),
+                                                                    _stream(self.device)), "fluxgnn_hybrid_slab_step_peer")
+            else:
+                _lib.check(_lib.lib().fluxgnn_hybrid_slab_step_ld(*head, _stream(self.device)), "fluxgnn_hybrid_slab_step_ld")
 
     def advance_slab(self, ext: torch.Tensor) -> torch.Tensor:
         """ext [B,3,owned+2*halo] (ghosts included) -> [B,3,owned] with n', u' (E' not yet)."""
@@ -685,14 +717,18 @@ class DomainDecomposedBaselineSolver(_DomainDecomposedSolver):
         super().__init__(nx, length, dt, 4, rank, world, device, field_solve, slab_fn, field_fn, field_stages,
                          fabric=fabric)
 
-    def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor):
+    def _cuda_slab(self, ext: torch.Tensor, nxt: torch.Tensor, left=None, right=None):
         B = ext.shape[0]
         dx = self.length / self.nx
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().fluxgnn_baseline_slab_step(
-                ext.data_ptr(), nxt.data_ptr(), self.ld, self.halo, None, B, self.owned, self.halo,
-                float(np.float32(self.dt / dx)), float(np.float32(self.dt)), float(np.float32(self.nu)),
-                float(np.float32(dx ** 2)), _stream(self.device)), "fluxgnn_baseline_slab_step")
+            head = (ext.data_ptr(), nxt.data_ptr(), self.ld, self.halo, None, B, self.owned, self.halo,
+                    float(np.float32(self.dt / dx)), float(np.float32(self.dt)), float(np.float32(self.nu)),
+                    float(np.float32(dx ** 2)))
+            if left is not None:
+                _lib.check(_lib.lib().fluxgnn_baseline_slab_step_peer(*head, left.data_ptr(), right.data_ptr(),
+                                                                      _stream(self.device)), "fluxgnn_baseline_slab_step_peer")
+            else:
+                _lib.check(_lib.lib().fluxgnn_baseline_slab_step(*head, _stream(self.device)), "fluxgnn_baseline_slab_step")
 
 
 def split_slabs(state: torch.Tensor, world: int):
@@ -733,7 +769,8 @@ def step_peer_emulated(solvers, locals_):
     G = len(solvers)
     B = [solvers[r]._adopt(locals_[r]).shape[0] for r in range(G)][0]
     for r in range(G):
-        solvers[r]._peer_push(B)
+        if solvers[r]._fresh:
+            solvers[r]._peer_push(B)
     for r in range(G):
         solvers[r]._peer_compute(B)
     return [solvers[r]._peer_field(B) for r in range(G)]

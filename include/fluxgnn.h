@@ -317,6 +317,22 @@ int fluxgnn_hybrid_slab_step_ld(const void* packed, int num_layers, int precisio
  *   fluxgnn_peer_allgather: copies `bytes` (multiple of 16) from src into slot `rank` of every rank's gather
  *       buffer, which sits `offset` bytes into that rank's symmetric allocation; peer_bases_dev is a DEVICE array
  *       of the `world` allocation base pointers (torch's _SymmetricMemory.buffer_ptrs_dev). */
+/* The same exchange FUSED into the producing kernels (the steady state of the peer-memory step): the slab kernels
+ * store n', u' of their first / last `halo` owned cells also into left_out / right_out -- the ring neighbours' NEXT
+ * extended states, laid out like state_out (out_ld, out_off >= halo) -- and the field kernel of the prefix-sum solve
+ * stores E' of those cells into E_left / E_right (the E rows of the neighbours' next states, laid out like E / e_ld).
+ * Otherwise identical to fluxgnn_hybrid_slab_step_ld, fluxgnn_baseline_slab_step and fluxgnn_scan_slab_field. */
+int fluxgnn_hybrid_slab_step_peer(const void* packed, int num_layers, int precision,
+                                  const float* state_ext, const float* x_ext, float* state_out,
+                                  int out_ld, int out_off, int B, int owned, int halo, int radius,
+                                  float c, float dt, float* left_out, float* right_out, void* stream);
+int fluxgnn_baseline_slab_step_peer(const float* state_ext, float* state_out, int out_ld, int out_off, float* flux_n,
+                                    int B, int owned, int halo, float c, float dt, float nu, float dx2,
+                                    float* left_out, float* right_out, void* stream);
+int fluxgnn_scan_slab_field_peer(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank,
+                                 int ranks, double length, const void* msg_all, void* workspace, double cert_tol,
+                                 int step, int* first_uncertified, float* E_left, float* E_right, int halo,
+                                 void* stream);
 int fluxgnn_peer_halo_push(const float* state_ext, float* left_ext, float* right_ext, int B, int owned, int halo,
                            int ch0, int ch1, void* stream);
 int fluxgnn_peer_allgather(const void* src, long long bytes, const void* peer_bases_dev, long long offset, int rank,

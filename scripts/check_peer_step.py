@@ -1,7 +1,8 @@
 """Multi-GPU check of the peer-memory step (torchrun, one process per GPU):
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/check_peer_step.py
 Every rank advances its slab (1) with the collective step (NCCL halo exchange + all-gather, field_solve="scan"),
-(2) with step_peer over symmetric memory, (3) with advance(graph=True); all three must agree bit for bit, and the first
+(2) with step_peer over symmetric memory, (3) with advance(graph=True), (4) with step_peer while the ranks' streams are
+stalled at different steps (race hunt); all must agree bit for bit, and the first
 step's n', u' must equal the undivided solver's.  Prints device time per step of each variant."""
 import json, os, sys
 import numpy as np, torch, torch.distributed as dist
@@ -34,13 +35,21 @@ for kind, nx, B, steps in (("baseline", 1 << 24, 1, 40), ("hybrid_fp16x3", 1 << 
     local = full[..., rank * S:(rank + 1) * S].contiguous()
     want1 = whole.rollout(full, 1)[0][..., rank * S:(rank + 1) * S]
     res, ms, certified = {}, {}, {}
-    for variant in ("collective", "peer", "peer_graph"):
+    for variant in ("collective", "peer", "peer_graph", "peer_skewed"):
         sol = make(None if variant == "collective" else fabric)
+        counter = [0]
 
         def run(state, n):
             if variant == "collective":
                 for _ in range(n):
                     state = sol.step(state, comm)
+                return state
+            if variant == "peer_skewed":                   # race hunt: the ranks' streams stall at different steps
+                for _ in range(n):
+                    counter[0] += 1
+                    if (counter[0] * 7 + rank * 3) % 5 == 0:
+                        torch.cuda._sleep(3_000_000)
+                    state = sol.step_peer(state)
                 return state
             return sol.advance(state, n, graph=variant == "peer_graph")
 
@@ -60,7 +69,7 @@ for kind, nx, B, steps in (("baseline", 1 << 24, 1, 40), ("hybrid_fp16x3", 1 << 
         bad = sol.first_uncertified(state, comm)          # (the hybrid step's kinked n' certifies on long grids only)
         assert bad is None or kind != "baseline", (kind, variant, bad)
         certified[variant] = bad is None
-    for variant in ("peer", "peer_graph"):
+    for variant in ("peer", "peer_graph", "peer_skewed"):
         assert torch.equal(res[variant], res["collective"]), (kind, variant, "differs from the collective step")
     out[kind] = {"nx": nx, "batch": B, "ranks": world, "ms_per_step": ms,
                  "cell_updates_per_sec": {k: B * nx / (v * 1e-3) for k, v in ms.items()}, "bit_identical": True,
