@@ -90,9 +90,12 @@ class SymmetricMemoryFabric:
     field-solve messages are then plain stores into the neighbours' memory (fluxgnn_peer_halo_push,
     fluxgnn_peer_allgather) ordered by the signal-pad barrier: no NCCL call on the step path."""
 
-    def __init__(self, group=None, device=None):
+    def __init__(self, group=None, device=None, barrier_timeout_ms: int = 60000):
+        """barrier_timeout_ms: a barrier that waits longer than this for a peer traps (a CUDA error on this rank) instead
+        of spinning forever -- a rank that died must not hang the others' GPUs."""
         import torch.distributed._symmetric_memory as symm
         self._symm = symm
+        self.barrier_timeout_ms = int(barrier_timeout_ms)
         self.group = dist.group.WORLD if group is None else group
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -108,7 +111,8 @@ class SymmetricMemoryFabric:
                 return local[offset_bytes:offset_bytes + n].view(dtype).view(shape)
             return hdl.get_buffer(rank, shape, dtype, offset_bytes // item)
 
-        return _PeerBlock(self, local, views, int(hdl.buffer_ptrs_dev), hdl.barrier)
+        timeout = self.barrier_timeout_ms
+        return _PeerBlock(self, local, views, int(hdl.buffer_ptrs_dev), lambda: hdl.barrier(0, timeout))
 
 
 class EmulatedFabric:
