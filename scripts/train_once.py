@@ -1,3 +1,5 @@
+"""Two training forward + backward passes at the C2 shape (4096 ICs x 64 cells, radius 3), nothing else: the command behind
+the ncu launch list profiles/r2_train_launches.csv."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
