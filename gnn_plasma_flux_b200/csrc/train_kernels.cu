@@ -85,19 +85,48 @@ struct SlabRegs {
     float4 a0, a1, b0, b1;
 };
 
-__device__ __forceinline__ void mma_slab(float (&acc)[8][8], const float (*As)[128], const float (*Bs)[128], int tm, int tn) {
+// Packed accumulators (fma.rn.f32x2, SASS FFMA2: one issue slot per two multiply-adds, which is what lets the operand
+// loads issue in the shadow of the arithmetic): for row pair p and column pair q
+//   d[p][q] = {acc[2p][2q],   acc[2p+1][2q+1]},   x[p][q] = {acc[2p][2q+1], acc[2p+1][2q]}
+// (a pair) * (b pair) and (a pair) * (swapped b pair) -- the scheme of the forward kernel's gemm_pass.
+struct PackedAcc {
+    float2 d[4][4], x[4][4];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[p][q] = x[p][q] = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void unpack(float (&acc)[8][8]) const {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[2 * p][2 * q] = d[p][q].x;
+                acc[2 * p + 1][2 * q + 1] = d[p][q].y;
+                acc[2 * p][2 * q + 1] = x[p][q].x;
+                acc[2 * p + 1][2 * q] = x[p][q].y;
+            }
+    }
+};
+
+__device__ __forceinline__ void mma_slab(PackedAcc& c, const float (*As)[128], const float (*Bs)[128], int tm, int tn) {
 #pragma unroll
     for (int k = 0; k < kSlab; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(&As[k][4 * tm]);
         const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + 4 * tm]);
         const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][4 * tn]);
         const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + 4 * tn]);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float2 A[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+        const float2 B[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        const float2 Bx[4] = {make_float2(b0.y, b0.x), make_float2(b0.w, b0.z), make_float2(b1.y, b1.x), make_float2(b1.w, b1.z)};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int q = 0; q < 4; ++q) {
+                c.d[p][q] = __ffma2_rn(A[p], B[q], c.d[p][q]);
+                c.x[p][q] = __ffma2_rn(A[p], Bx[q], c.x[p][q]);
+            }
     }
 }
 
@@ -116,11 +145,8 @@ __global__ void __launch_bounds__(256, 2) bwd_gemm_nn_kernel(const float* __rest
     const int wk = tid >> 4, wc = (tid & 15) * 8;                  // W loader: k, first of 8 columns
     const bool row_ok = row0 + lrow < rows;
     const int slabs = (A2 != nullptr ? 2 : 1) * (kH / kSlab);
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    PackedAcc pacc;
+    pacc.clear();
     SlabRegs g;
     auto fetch = [&](int sl) {
         const float* A = sl < kH / kSlab ? A1 : A2;
@@ -146,10 +172,12 @@ __global__ void __launch_bounds__(256, 2) bwd_gemm_nn_kernel(const float* __rest
     for (int sl = 0; sl < slabs; ++sl) {
         const int buf = sl & 1;
         if (sl + 1 < slabs) fetch(sl + 1);
-        mma_slab(acc, As[buf], Bs[buf], tm, tn);
+        mma_slab(pacc, As[buf], Bs[buf], tm, tn);
         if (sl + 1 < slabs) stash(buf ^ 1);
         __syncthreads();
     }
+    float acc[8][8];
+    pacc.unpack(acc);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long long r = row0 + (i < 4 ? 4 * tm + i : 64 + 4 * tm + (i - 4));
@@ -174,11 +202,8 @@ __global__ void __launch_bounds__(256, 2) bwd_gemm_tn_kernel(const float* __rest
     const long long row_end = row_begin + per_block < rows ? row_begin + per_block : rows;
     if (row_begin >= rows) return;
     const int lr = tid >> 4, lc = (tid & 15) * 8;                  // loader: row in slab, first of 8 features
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    PackedAcc pacc;
+    pacc.clear();
     SlabRegs g;
     auto fetch = [&](long long r0) {
         g.a0 = g.a1 = g.b0 = g.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -202,11 +227,13 @@ __global__ void __launch_bounds__(256, 2) bwd_gemm_tn_kernel(const float* __rest
     for (long long r0 = row_begin; r0 < row_end; r0 += kSlab) {
         const bool more = r0 + kSlab < row_end;
         if (more) fetch(r0 + kSlab);
-        mma_slab(acc, As[buf], Bs[buf], tm, tn);
+        mma_slab(pacc, As[buf], Bs[buf], tm, tn);
         if (more) stash(buf ^ 1);
         __syncthreads();
         buf ^= 1;
     }
+    float acc[8][8];
+    pacc.unpack(acc);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int n = i < 4 ? 4 * tm + i : 64 + 4 * tm + (i - 4);
