@@ -537,6 +537,9 @@ class _DomainDecomposedSolver:
     def step(self, local: torch.Tensor, comm) -> torch.Tensor:
         """local [B,3,owned] -> new local state (the interior VIEW of this solver's extended buffer; pass it back
         to step() and no copy is made).  `comm` provides exchange_halos / all_to_all / all_gather."""
+        if self._fabric is not None:
+            raise ValueError("this solver was built with fabric=...: its exchange runs over peer memory, call step_peer() / "
+                             "advance() (every rank together) instead of step(state, comm)")
         cur = self._adopt(local)
         B = cur.shape[0]
         nxt = self._ext[B][1 - self._cur[B]]
