@@ -81,6 +81,8 @@ SIGNATURES = {
     "fluxgnn_scan_slab_field_peer": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_double,
                                              c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                              c_void_p]),
+    "fluxgnn_scan_slab_sums_peer": (c_int, [c_void_p, c_longlong, c_int, c_int, c_longlong, c_void_p, c_void_p, c_void_p,
+                                            c_longlong, c_int, c_int, c_void_p]),
     "fluxgnn_peer_halo_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fluxgnn_peer_allgather": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_void_p]),
     "fluxgnn_baseline_slab_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,

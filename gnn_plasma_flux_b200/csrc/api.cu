@@ -915,6 +915,21 @@ int fluxgnn_scan_slab_sums(const float* n, long long n_ld, int B, int S, long lo
     return FLUXGNN_OK;
 }
 
+int fluxgnn_scan_slab_sums_peer(const float* n, long long n_ld, int B, int S, long long j_base, void* workspace, void* msg,
+                                const void* peer_bases_dev, long long offset, int rank, int world, void* stream) {
+    if (!n || !workspace || !msg || n_ld < S || !peer_bases_dev || offset < 0 || offset % 16 || world < 1 || rank < 0 ||
+        rank >= world)
+        return set_error(FLUXGNN_EINVAL, "scan_slab_sums_peer: bad argument");
+    if (!scan_slab_supported(B, S)) return set_error(FLUXGNN_EUNSUP, "scan_slab_sums: needs S %% 8 == 0, S >= 64 (B=%d S=%d)", B, S);
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != FLUXGNN_OK) return rc;
+    FLUXGNN_CUDA_OK(launch_scan_slab_sums(n, n_ld, B, S, j_base, workspace, msg, sms, (cudaStream_t)stream,
+                                          (void* const*)peer_bases_dev, offset, rank, world));
+    count_launch(2);
+    return FLUXGNN_OK;
+}
+
 int fluxgnn_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
                             double length, const void* msg_all, void* workspace, double cert_tol, int step,
                             int* first_uncertified, void* stream) {

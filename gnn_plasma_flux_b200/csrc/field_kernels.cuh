@@ -147,7 +147,8 @@ cudaError_t launch_baseline_rollout_scan(const float* state_in, float* state_out
 bool scan_slab_supported(int B, int S);
 size_t scan_slab_workspace_bytes(int B, int S, int sms);
 cudaError_t launch_scan_slab_sums(const float* n, long long n_ld, int B, int S, long long j_base, void* workspace, void* msg,
-                                  int sms, cudaStream_t stream);
+                                  int sms, cudaStream_t stream, void* const* bases = nullptr, long long offset = 0, int rank = 0,
+                                  int world = 0);
 cudaError_t launch_scan_slab_field(const float* n, long long n_ld, float* E, long long e_ld, int B, int S, int rank, int ranks,
                                    double length, const void* msg_all, void* workspace, double tol, int step, int* flag, int sms,
                                    cudaStream_t stream, float* E_left = nullptr, float* E_right = nullptr, int halo = 0);

@@ -467,8 +467,11 @@ __global__ void __launch_bounds__(kSlabThreads) slab_sums_kernel(const float* __
 
 // one warp per IC; lane l sums the records l, l + 32, ..., then a fixed butterfly: deterministic, and 32 loads in flight
 // instead of a serial chain of `segs` dependent ones (16 us at 74 segments)
+// Peer memory (bases != nullptr): the message is also stored into slot `rank` of EVERY rank's gather buffer, which sits
+// `offset` bytes into that rank's symmetric allocation -- the all-gather of the distributed solve is this store.
 __global__ void slab_msg_kernel(const float* __restrict__ n, long long n_ld, int S, int segs, const SlabSeg* __restrict__ seg_rec,
-                                SlabMsg* __restrict__ msg) {
+                                SlabMsg* __restrict__ msg, void* const* __restrict__ bases, long long offset, int rank,
+                                int world, int B) {
     const int ic = blockIdx.x, lane = threadIdx.x;
     double s = 0.0, m1 = 0.0, d4 = 0.0;
     float em = 0.f;
@@ -485,6 +488,9 @@ __global__ void slab_msg_kernel(const float* __restrict__ n, long long n_ld, int
     const float* row = n + (size_t)ic * n_ld;
     m.edge[0] = row[0]; m.edge[1] = row[1]; m.edge[2] = row[S - 2]; m.edge[3] = row[S - 1];
     msg[ic] = m;
+    if (bases != nullptr)
+        for (int p = 0; p < world; ++p)
+            reinterpret_cast<SlabMsg*>(static_cast<char*>(bases[p]) + offset)[(size_t)rank * B + ic] = m;
 }
 
 struct SlabFieldArgs {
@@ -752,13 +758,14 @@ size_t scan_slab_workspace_bytes(int B, int S, int sms) {
 }
 
 cudaError_t launch_scan_slab_sums(const float* n, long long n_ld, int B, int S, long long j_base, void* workspace, void* msg,
-                                  int sms, cudaStream_t stream) {
+                                  int sms, cudaStream_t stream, void* const* bases, long long offset, int rank, int world) {
     int segs = 0, sc = 0;
     slab_geometry(B, S, sms, &segs, &sc);
     slab_sums_kernel<<<(unsigned)(B * segs), kSlabThreads, 0, stream>>>(n, n_ld, S, segs, sc, j_base, (SlabSeg*)workspace);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    slab_msg_kernel<<<(unsigned)B, 32, 0, stream>>>(n, n_ld, S, segs, (const SlabSeg*)workspace, (SlabMsg*)msg);
+    slab_msg_kernel<<<(unsigned)B, 32, 0, stream>>>(n, n_ld, S, segs, (const SlabSeg*)workspace, (SlabMsg*)msg, bases, offset,
+                                                    rank, world, B);
     return cudaGetLastError();
 }
 

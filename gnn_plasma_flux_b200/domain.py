@@ -302,10 +302,18 @@ class DistributedScanSolve:
         return st
 
     # ---- stages ----
-    def sums(self, n_rows: torch.Tensor, st):
+    def sums(self, n_rows: torch.Tensor, st, gather=None):
+        """gather = (device pointer table of the ranks' symmetric allocations, offset of the gather buffer in them): the
+        message kernel then stores this rank's messages into every rank's gather buffer itself (peer memory)."""
         if self._stages:
             return self._stages["sums"](self, n_rows, st)
         B = n_rows.shape[0]
+        if gather is not None:
+            _lib.check(_lib.lib().fluxgnn_scan_slab_sums_peer(
+                n_rows.data_ptr(), n_rows.stride(0) if B > 1 else self.S, B, self.S, self.rank * self.S, st["work"].data_ptr(),
+                st["msg"].data_ptr(), gather[0], gather[1], self.rank, self.world, _stream(self.device)),
+                "fluxgnn_scan_slab_sums_peer")
+            return
         _lib.check(_lib.lib().fluxgnn_scan_slab_sums(n_rows.data_ptr(), n_rows.stride(0) if B > 1 else self.S, B, self.S,
                                                      self.rank * self.S, st["work"].data_ptr(), st["msg"].data_ptr(),
                                                      _stream(self.device)), "fluxgnn_scan_slab_sums")
@@ -577,17 +585,16 @@ class _DomainDecomposedSolver:
 
     def _peer_compute(self, B: int):
         """Slab kernel: n', u' into the other buffer AND, for the edge cells, into the neighbours' ghost zones of THEIR
-        other buffer; then this slab's prefix sums and the 48-byte message per IC stored into every rank's gather buffer."""
+        other buffer; then this slab's prefix sums, whose message kernel stores the 48-byte message per IC into every
+        rank's gather buffer."""
         k, p = self._cur[B], self._neighbours(B)
         nxt = self._ext[B][1 - k]
         self._slab_fn(self._ext[B][k], nxt, p["left"][1 - k], p["right"][1 - k])
         st = self._scan.state(B)
-        self._scan.sums(self.interior(nxt)[:, 0], st)
         block = p["block"]
         bases = block.bases_dev if block.bases_dev is not None else block._bases_fn()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().fluxgnn_peer_allgather(st["msg"].data_ptr(), p["msg_bytes"], bases, p["msg_off"], self.rank,
-                                                         self.world, _stream(self.device)), "fluxgnn_peer_allgather")
+            self._scan.sums(self.interior(nxt)[:, 0], st, gather=(bases, p["msg_off"]))
 
     def _peer_field(self, B: int):
         """E' of this slab from the gathered messages, its edge cells also into the neighbours' ghost zones; the new state

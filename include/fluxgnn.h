@@ -333,6 +333,12 @@ int fluxgnn_scan_slab_field_peer(const float* n, long long n_ld, float* E, long 
                                  int ranks, double length, const void* msg_all, void* workspace, double cert_tol,
                                  int step, int* first_uncertified, float* E_left, float* E_right, int halo,
                                  void* stream);
+/* fluxgnn_scan_slab_sums whose message kernel also stores the 48-byte message of every IC into slot `rank` of every
+ * rank's gather buffer (`offset` bytes into the symmetric allocations whose bases peer_bases_dev lists): the all-gather
+ * of the distributed prefix-sum solve fused into its producer. */
+int fluxgnn_scan_slab_sums_peer(const float* n, long long n_ld, int B, int S, long long j_base, void* workspace,
+                                void* msg, const void* peer_bases_dev, long long offset, int rank, int world,
+                                void* stream);
 int fluxgnn_peer_halo_push(const float* state_ext, float* left_ext, float* right_ext, int B, int owned, int halo,
                            int ch0, int ch1, void* stream);
 int fluxgnn_peer_allgather(const void* src, long long bytes, const void* peer_bases_dev, long long offset, int rank,
