@@ -119,3 +119,23 @@ def test_baseline_host_surface():
         np.testing.assert_array_equal(g.x, o.x)
         np.testing.assert_array_equal(g.k, o.k)
         assert g.dx == o.dx
+
+
+def test_emulated_fabric_blocks_alias_and_offsets():
+    """Host logic of the peer-memory fabric (domain.EmulatedFabric, the one-process stand-in for symmetric memory): a
+    view of rank r's block aliases that rank's allocation at the given byte offset, whichever rank asks for it."""
+    import torch
+    from gnn_plasma_flux_b200.domain import EmulatedFabric
+    fabrics = EmulatedFabric.create(3, "cpu")
+    blocks = [f.allocate(4096) for f in fabrics]
+    assert all(b.local.numel() == 4096 and b.local.dtype == torch.uint8 for b in blocks)
+    mine = blocks[1].view(1, 256, (2, 3, 8))                    # rank 1's own view
+    theirs = blocks[0].view(1, 256, (2, 3, 8))                  # rank 0 looking at rank 1's block
+    assert mine.dtype == torch.float32 and mine.data_ptr() == theirs.data_ptr() == blocks[1].local.data_ptr() + 256
+    theirs.fill_(7.0)
+    assert float(mine.sum()) == 7.0 * 48
+    assert float(blocks[2].view(2, 256, (48,)).abs().sum()) == 0.0     # another rank's block is untouched
+    msg = blocks[2].view(0, 1024, (3, 96), torch.uint8)
+    assert msg.data_ptr() == blocks[0].local.data_ptr() + 1024 and msg.shape == (3, 96)
+    second = [f.allocate(64) for f in fabrics]                  # allocations pair up by order
+    assert second[0].view(2, 0, (16,)).data_ptr() == second[2].local.data_ptr()
