@@ -279,6 +279,39 @@ def test_peer_memory_step_equals_the_collective_step(built_lib, kind, world, nx,
     assert torch.isfinite(got).all()
 
 
+def test_peer_exchange_entry_points(built_lib):
+    """fluxgnn_peer_halo_push and fluxgnn_peer_allgather through the C ABI, three virtual ranks on one GPU: every ghost
+    zone receives exactly the neighbour's edge cells of the requested channels, every gather slot the sender's bytes."""
+    from gnn_plasma_flux_b200 import _lib
+    L = _lib.lib()
+    G, B, S, H = 3, 4, 40, 5
+    ld = S + 2 * H
+    gen = torch.Generator("cuda").manual_seed(3)
+    ext = [torch.randn(B, 3, ld, device="cuda", generator=gen) for _ in range(G)]
+    before = [e.clone() for e in ext]
+    stream = torch.cuda.current_stream().cuda_stream
+    for r in range(G):
+        _lib.check(L.fluxgnn_peer_halo_push(before[r].data_ptr(), ext[(r - 1) % G].data_ptr(), ext[(r + 1) % G].data_ptr(),
+                                            B, S, H, 0, 2, stream), "fluxgnn_peer_halo_push")
+    for r in range(G):
+        left, right = before[(r - 1) % G], before[(r + 1) % G]
+        assert torch.equal(ext[r][:, :2, :H], left[:, :2, S:S + H])             # left ghosts = left neighbour's last H cells
+        assert torch.equal(ext[r][:, :2, H + S:], right[:, :2, H:2 * H])        # right ghosts = right neighbour's first H
+        assert torch.equal(ext[r][:, 2], before[r][:, 2])                       # channel 2 was not requested
+        assert torch.equal(ext[r][:, :, H:H + S], before[r][:, :, H:H + S])     # interiors untouched
+    nbytes, offset = 96, 64
+    blocks = [torch.zeros(offset + G * nbytes + 32, dtype=torch.uint8, device="cuda") for _ in range(G)]
+    bases = torch.tensor([b.data_ptr() for b in blocks], dtype=torch.int64, device="cuda")
+    msgs = [torch.randint(0, 255, (nbytes,), dtype=torch.uint8, device="cuda", generator=gen) for _ in range(G)]
+    for r in range(G):
+        _lib.check(L.fluxgnn_peer_allgather(msgs[r].data_ptr(), nbytes, bases.data_ptr(), offset, r, G, stream),
+                   "fluxgnn_peer_allgather")
+    for b in blocks:
+        assert torch.equal(b[offset:offset + G * nbytes], torch.cat(msgs))
+        assert int(b[:offset].sum()) == 0 and int(b[offset + G * nbytes:].sum()) == 0
+    assert L.fluxgnn_peer_allgather(msgs[0].data_ptr(), 40, bases.data_ptr(), offset, 0, G, stream) < 0    # not a multiple of 16
+
+
 @pytest.mark.parametrize("nx,B", [(1 << 20, 16), (1 << 22, 8), (1 << 18, 40)])
 def test_scan_repeated_launches_are_bit_stable(built_lib, nx, B):
     """Race hunt (the short form of scripts/stress_scan.py): at large batch every SM holds several CTAs whose bulk-copy
