@@ -19,6 +19,11 @@ cells per side), in two ping-pong buffers.  Per time step:
      1/G of the spectrum.  `field_solve="allgather"` keeps round 1's variant (all-gather of n', the whole FFT
      replicated on every rank: G times the bytes and the arithmetic) as a cross-check.
 
+Built with `fabric=SymmetricMemoryFabric()` the same solvers run the step over PEER MEMORY instead (`step_peer`,
+`advance`): extended states and the gather buffer of the prefix-sum solve live in symmetric memory, the slab / field /
+message kernels store the edge cells and messages straight into the neighbours' buffers, two signal-pad barriers order
+a step, and pairs of steps replay as one CUDA graph.
+
 One process per GPU; `TorchDistComm` speaks torch.distributed (NCCL on GPUs, gloo in the CPU tests).
 `step_emulated` runs G virtual ranks inside one process on one GPU -- the way to exercise the
 decomposition without G devices (separate processes that wait on one another must not share a GPU).
@@ -87,8 +92,10 @@ class _PeerBlock:
 class SymmetricMemoryFabric:
     """Peer memory of the ranks of a process group, one process per GPU: torch.distributed._symmetric_memory
     allocations (CUDA VMM, mapped into every rank over NVLink / NVSwitch) with their signal pads.  Halo cells and
-    field-solve messages are then plain stores into the neighbours' memory (fluxgnn_peer_halo_push,
-    fluxgnn_peer_allgather) ordered by the signal-pad barrier: no NCCL call on the step path."""
+    field-solve messages are then plain stores into the neighbours' memory, issued by the kernels that produce them
+    (fluxgnn_hybrid_slab_step_peer, fluxgnn_baseline_slab_step_peer, fluxgnn_scan_slab_sums_peer,
+    fluxgnn_scan_slab_field_peer; fluxgnn_peer_halo_push / fluxgnn_peer_allgather are the stand-alone forms) and ordered
+    by the signal-pad barrier: no NCCL call on the step path."""
 
     def __init__(self, group=None, device=None, barrier_timeout_ms: int = 60000):
         """barrier_timeout_ms: a barrier that waits longer than this for a peer traps (a CUDA error on this rank) instead
