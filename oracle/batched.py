@@ -96,6 +96,31 @@ def hybrid_step(w: dict, state: torch.Tensor, x, k, dt: float, dx: float, radius
         return torch.stack([n_new, u_new, poisson(n_new, k)], dim=1)
 
 
+def training_rollout(w: dict, state: torch.Tensor, x, k, dt: float, dx: float, n_steps: int, radius: int = 1):
+    """The reference's multi-step TRAINING rollout, scripts/training/train_ablation.py:172-206, batched and
+    differentiable: per step  model -> face flux -> n', u' with autograd edges -> field solve of n' DETACHED (it goes
+    through numpy there, :198-200).  Returns (list of the n_steps + 1 states, list of the n_steps face fluxes); `w` may
+    hold tensors that require grad, `state` too.  The checker of HybridSolver.rollout_with_grad."""
+    x = torch.as_tensor(np.asarray(x, dtype=np.float32))
+    k = torch.as_tensor(np.asarray(k))
+    nx = state.shape[-1]
+    c, dt32 = float(np.float32(dt / dx)), float(np.float32(dt))
+    states, faces = [state], []
+    for _ in range(n_steps):
+        cur = states[-1]
+        fl = edge_fluxes(w, cur, x.to(cur.dtype) if cur.dtype == torch.float64 else x, radius, hops=1)
+        face = 0.5 * (fl[:, :nx] + fl[:, nx:])
+        n, u, E = cur[:, 0], cur[:, 1], cur[:, 2]
+        n_new = n - c * (face - torch.roll(face, 1, dims=-1))
+        fu = 0.5 * u * u
+        u_new = (u - c * (fu - torch.roll(fu, 1, dims=-1))) + dt32 * E
+        with torch.no_grad():
+            E_new = poisson(n_new.detach(), k)
+        states.append(torch.stack([n_new, u_new, E_new], dim=1))
+        faces.append(face)
+    return states, faces
+
+
 def hybrid_run(w, state0: torch.Tensor, x, k, dt, dx, n_steps: int, radius: int = 1, record_every: int = 0):
     """Rollout; returns the final state, or [1+T/record_every, B, 3, nx] when recording."""
     state = state0

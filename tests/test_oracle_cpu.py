@@ -180,3 +180,34 @@ def test_comparison_models_golden():
         np.testing.assert_array_equal(P.pure_gnn_rollout(w, g["ics"][1], x32, 10), g[f"pgnn{hidden}_rollout10"][1])
     wp = P.init_pinn_weights(11, 192, 256, 4)
     np.testing.assert_array_equal(P.pinn_forward(wp, g["ics"]), g["pinn_step"])
+
+
+def test_training_rollout_gradients_golden(weights):
+    """Golden g11 (the reference's multi-step training rollout under its OWN autograd, train_ablation.py:172-206) against
+    fp64 autograd of the oracle's restatement batched.training_rollout: the same loss, the same gradients w.r.t. every
+    parameter and the initial state.  This is the checker HybridSolver.rollout_with_grad is held to on the GPU."""
+    g = load_golden("g11_training_rollout.npz")
+    for tag, nx, radius, dt, steps in (("nx64_r1", 64, 1, 5e-3, 3), ("nx64_r3", 64, 3, 5e-3, 3), ("nx256_r2", 256, 2, 1e-3, 2)):
+        grid = P.Grid(nx=nx, dt=dt)
+        wt = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in weights.items()}
+        st0 = torch.from_numpy(g[f"{tag}_ics"]).double().requires_grad_(True)
+        states, faces = batched.training_rollout(wt, st0, grid.x, grid.k, grid.dt, grid.dx, steps, radius=radius)
+        energies = torch.stack([0.5 * torch.mean(s[:, 1] ** 2, dim=1) for s in states[:-1]])
+        loss = torch.mean((energies - energies[0]) ** 2, dim=0).sum()
+        loss = loss + (torch.stack(faces, dim=1) * torch.from_numpy(g[f"{tag}_cot_face"]).double()).sum()
+        loss = loss + (states[-1][:, 0] * torch.from_numpy(g[f"{tag}_cot_n"]).double()).sum()
+        loss = loss + (states[-1][:, 1] * torch.from_numpy(g[f"{tag}_cot_u"]).double()).sum()
+        loss.backward()
+        rel = lambda a, b: np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max() / max(np.abs(b).max(), 1e-12)
+        assert P.rel_err(states[-1].detach().numpy().astype(np.float32), g[f"{tag}_final"]).max() <= 3e-5, tag
+        assert abs(loss.item() - float(g[f"{tag}_loss"])) <= 1e-4 * abs(float(g[f"{tag}_loss"])), tag
+        assert rel(st0.grad.numpy(), g[f"{tag}_dstate0"]) <= 2e-4, tag
+        for name, p_ in wt.items():
+            gr = p_.grad.numpy()
+            if f"{tag}_grad_{name}" in g:
+                assert rel(gr, g[f"{tag}_grad_{name}"]) <= 2e-4, (tag, name)
+            else:
+                assert abs(np.linalg.norm(gr) / float(g[f"{tag}_gradnorm_{name}"]) - 1) <= 2e-4, (tag, name)
+                scale = np.abs(gr).max()
+                assert np.abs(gr[:8, :8] - g[f"{tag}_gradcorner_{name}"]).max() <= 2e-4 * scale, (tag, name)
+                assert np.abs(gr[[5, 77], :] - g[f"{tag}_gradrows_{name}"]).max() <= 2e-4 * scale, (tag, name)
