@@ -1123,6 +1123,43 @@ def test_training_rollout_vs_reference_autograd(weights, built_lib, tmp_path, ta
             assert np.abs(gr[[5, 77], :] - g[f"{tag}_gradrows_{name}"]).max() <= GRAD_TOL * scale, name
 
 
+@pytest.mark.parametrize("nx,B,radius,steps", [(1024, 3, 2, 2), (40, 4, 1, 3), (128, 2, 4, 2)])
+def test_training_rollout_vs_oracle_autograd(weights, built_lib, nx, B, radius, steps):
+    """rollout_with_grad on shapes the reference goldens do not cover -- window tiles with packed remainder windows and
+    the FFT field solve (1024 cells), a grid that is not a multiple of 8 (neighbour walk), radius 4 -- against fp64
+    autograd of the oracle's restatement of the training rollout (batched.training_rollout, itself pinned to g11)."""
+    from gnn_plasma_flux_b200 import FluxGNN, HybridSolver, MODEL_CONFIG
+    m = FluxGNN(**MODEL_CONFIG)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    dt = 3e-4 * 1024 / nx if nx >= 256 else 5e-3
+    grid = P.Grid(nx=nx, dt=dt)
+    # the reference's noisy ICs: on SMOOTH states of a fine grid even the fp32 and fp64 evaluations of the oracle itself
+    # disagree by 1e-2 on single weight-gradient entries (ReLU masks at the kinks), which says nothing about a kernel
+    ics = np.stack([P.initial_condition(grid, seed=s) for s in range(B)])
+    rs = np.random.RandomState(nx + radius)
+    cot_n, cot_u = rs.randn(B, nx).astype(np.float32), rs.randn(B, nx).astype(np.float32)
+    cot_f = rs.randn(B, steps, nx).astype(np.float32)
+
+    def loss_of(states, faces, cast):
+        energies = torch.stack([0.5 * torch.mean(s[:, 1] ** 2, dim=1) for s in states[:-1]])
+        return (torch.mean((energies - energies[0]) ** 2, dim=0).sum()
+                + (torch.stack(faces, dim=1) * cast(cot_f)).sum()
+                + (states[-1][:, 0] * cast(cot_n)).sum() + (states[-1][:, 1] * cast(cot_u)).sum())
+
+    solver = HybridSolver(None, radius, nx=nx, dt=dt, model=m, graph_radius=radius)
+    st = torch.from_numpy(ics).cuda().requires_grad_(True)
+    states, faces = solver.rollout_with_grad(st, steps)
+    loss_of(states, faces, lambda a: torch.from_numpy(a).cuda()).backward()
+    wt = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in weights.items()}
+    st64 = torch.from_numpy(ics).double().requires_grad_(True)
+    ref_states, ref_faces = batched.training_rollout(wt, st64, grid.x, grid.k, grid.dt, grid.dx, steps, radius=radius)
+    loss_of(ref_states, ref_faces, lambda a: torch.from_numpy(a).double()).backward()
+    assert P.rel_err(states[-1].detach().cpu().numpy(), ref_states[-1].detach().numpy().astype(np.float32)).max() <= steps * STEP_TOL
+    assert _rel(st.grad.cpu().numpy(), st64.grad.numpy()) <= GRAD_TOL
+    for name, p_ in solver.model.named_parameters():
+        assert _rel(p_.grad.cpu().numpy(), wt[name].grad.numpy()) <= GRAD_TOL, name
+
+
 @pytest.mark.parametrize("nx,B,radius", [(64, 7, 3), (1024, 2, 2), (40, 3, 1)])
 def test_step_with_grad_forward_is_the_inference_step(weights, built_lib, nx, B, radius):
     """The activation-saving instantiation computes the same step as the inference kernel, bit for bit, and the face
